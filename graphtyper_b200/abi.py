@@ -1,0 +1,360 @@
+"""ctypes mirror of include/gtb200.h (the C-ABI structs) plus array marshalling helpers.
+
+Used by the Python harness (tests, bench, smoke) to call either the product library
+(graphtyper_b200/csrc -> libgtb200.so) or, in tests only, the oracle library
+(oracle/_build/libgtb_oracle.so).  Both take exactly the same plain-pointer structs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+SEQ_STRIDE = 76
+INVALID_ID = 0xFFFFFFFF
+SPECIAL_START = 0xD0000000
+
+u8p = C.POINTER(C.c_uint8)
+u16p = C.POINTER(C.c_uint16)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+
+
+class GraphView(C.Structure):
+    _fields_ = [
+        ("n_ref", C.c_uint32), ("n_var", C.c_uint32), ("is_sv_graph", C.c_int32), ("reserved", C.c_int32),
+        ("ref_order", u32p), ("ref_seq_off", u64p), ("ref_var_off", u32p),
+        ("var_order", u32p), ("var_seq_off", u64p), ("var_out_ref", u32p),
+        ("seq", u8p), ("seq_len", C.c_uint64),
+        ("var_ev_off", u32p), ("var_ev", i64p), ("var_aev_off", u32p), ("var_aev", i64p),
+        ("n_special", C.c_uint32), ("actual_poses", u32p), ("ref_reach_poses", u32p),
+        ("n_sp_keys", C.c_uint32), ("sp_keys", u32p), ("sp_off", u32p), ("sp_list", u32p),
+    ]
+
+
+class Label(C.Structure):
+    _fields_ = [("start", C.c_uint32), ("end", C.c_uint32), ("var_id", C.c_uint32)]
+
+
+class ReadBatch(C.Structure):
+    _fields_ = [
+        ("n_reads", C.c_uint32), ("seq_stride", C.c_uint32),
+        ("seq4", u8p), ("lseq", u16p), ("flag", u16p), ("mapq", u8p), ("isize", i32p),
+        ("same_tid", u8p), ("score_diff", u8p), ("clipped", u8p), ("sample", i32p),
+        ("mate", i32p), ("dup_of", i32p),
+    ]
+
+
+class Accumulators(C.Structure):
+    _fields_ = [
+        ("n_bubbles", C.c_uint32), ("n_samples", C.c_uint32),
+        ("bubble_id", u32p), ("n_alleles", u32p), ("score_off", u64p), ("cov_off", u64p),
+        ("log_score", u16p), ("gt_coverage", u16p), ("max_log_score", u16p),
+        ("ambiguous_depth", u8p), ("ambiguous_depth_alt", u8p), ("alt_proper_pair_depth", u8p),
+        ("saturated", u32p),
+        ("vs_clipped_reads", u64p), ("vs_mapq_squared", u64p),
+        ("pa_clipped_bp", u64p), ("pa_mapq_squared", u64p), ("pa_score_diff", u64p), ("pa_mismatches", u64p),
+        ("read_strand", u32p),
+    ]
+
+
+class SubmitStats(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("n_alignments", C.c_uint64), ("n_oriented", C.c_uint64),
+                ("n_pairs_scored", C.c_uint64), ("n_singles_scored", C.c_uint64),
+                ("n_capacity_overflow", C.c_uint64), ("kernel_launches", C.c_uint64)]
+
+
+def _ptr(a: Optional[np.ndarray], typ):
+    if a is None:
+        return C.cast(None, typ)
+    return a.ctypes.data_as(typ)
+
+
+class HostGraph:
+    """Owns the numpy arrays behind a GraphView (keeps them alive)."""
+
+    FIELDS = ["ref_order", "ref_seq_off", "ref_var_off", "var_order", "var_seq_off", "var_out_ref", "seq",
+              "var_ev_off", "var_ev", "var_aev_off", "var_aev", "actual_poses", "ref_reach_poses",
+              "sp_keys", "sp_off", "sp_list"]
+    DTYPES = {"ref_order": np.uint32, "ref_seq_off": np.uint64, "ref_var_off": np.uint32, "var_order": np.uint32,
+              "var_seq_off": np.uint64, "var_out_ref": np.uint32, "seq": np.uint8, "var_ev_off": np.uint32,
+              "var_ev": np.int64, "var_aev_off": np.uint32, "var_aev": np.int64, "actual_poses": np.uint32,
+              "ref_reach_poses": np.uint32, "sp_keys": np.uint32, "sp_off": np.uint32, "sp_list": np.uint32}
+
+    def __init__(self, arrays: Dict[str, np.ndarray], is_sv_graph: bool = False):
+        self.a = {k: np.ascontiguousarray(arrays[k], dtype=self.DTYPES[k]) for k in self.FIELDS}
+        self.is_sv_graph = bool(is_sv_graph)
+        a = self.a
+        v = GraphView()
+        v.n_ref = len(a["ref_order"])
+        v.n_var = len(a["var_order"])
+        v.is_sv_graph = 1 if self.is_sv_graph else 0
+        v.ref_order = _ptr(a["ref_order"], u32p)
+        v.ref_seq_off = _ptr(a["ref_seq_off"], u64p)
+        v.ref_var_off = _ptr(a["ref_var_off"], u32p)
+        v.var_order = _ptr(a["var_order"], u32p)
+        v.var_seq_off = _ptr(a["var_seq_off"], u64p)
+        v.var_out_ref = _ptr(a["var_out_ref"], u32p)
+        v.seq = _ptr(a["seq"], u8p)
+        v.seq_len = len(a["seq"])
+        v.var_ev_off = _ptr(a["var_ev_off"], u32p)
+        v.var_ev = _ptr(a["var_ev"], i64p)
+        v.var_aev_off = _ptr(a["var_aev_off"], u32p)
+        v.var_aev = _ptr(a["var_aev"], i64p)
+        v.n_special = len(a["actual_poses"])
+        v.actual_poses = _ptr(a["actual_poses"], u32p)
+        v.ref_reach_poses = _ptr(a["ref_reach_poses"], u32p)
+        v.n_sp_keys = len(a["sp_keys"])
+        v.sp_keys = _ptr(a["sp_keys"], u32p)
+        v.sp_off = _ptr(a["sp_off"], u32p)
+        v.sp_list = _ptr(a["sp_list"], u32p)
+        self.view = v
+
+    @classmethod
+    def from_gtba(cls, d: Dict[str, np.ndarray]) -> "HostGraph":
+        return cls(d, is_sv_graph=bool(d["meta"][0]))
+
+    @property
+    def n_bubbles(self) -> int:
+        return len(self.a["ref_order"]) - 1
+
+
+class HostBatch:
+    """Owns the arrays behind a ReadBatch."""
+
+    def __init__(self, seq4, lseq, flag, mapq, isize, same_tid, score_diff, clipped, sample, mate, dup_of,
+                 seq_stride: int = SEQ_STRIDE):
+        n = len(lseq)
+        self.seq4 = np.ascontiguousarray(seq4, dtype=np.uint8).reshape(n, seq_stride)
+        self.lseq = np.ascontiguousarray(lseq, dtype=np.uint16)
+        self.flag = np.ascontiguousarray(flag, dtype=np.uint16)
+        self.mapq = np.ascontiguousarray(mapq, dtype=np.uint8)
+        self.isize = np.ascontiguousarray(isize, dtype=np.int32)
+        self.same_tid = np.ascontiguousarray(same_tid, dtype=np.uint8)
+        self.score_diff = np.ascontiguousarray(score_diff, dtype=np.uint8)
+        self.clipped = np.ascontiguousarray(clipped, dtype=np.uint8)
+        self.sample = np.ascontiguousarray(sample, dtype=np.int32)
+        self.mate = np.ascontiguousarray(mate, dtype=np.int32)
+        self.dup_of = np.ascontiguousarray(dup_of, dtype=np.int32)
+        b = ReadBatch()
+        b.n_reads = n
+        b.seq_stride = seq_stride
+        b.seq4 = _ptr(self.seq4, u8p)
+        b.lseq = _ptr(self.lseq, u16p)
+        b.flag = _ptr(self.flag, u16p)
+        b.mapq = _ptr(self.mapq, u8p)
+        b.isize = _ptr(self.isize, i32p)
+        b.same_tid = _ptr(self.same_tid, u8p)
+        b.score_diff = _ptr(self.score_diff, u8p)
+        b.clipped = _ptr(self.clipped, u8p)
+        b.sample = _ptr(self.sample, i32p)
+        b.mate = _ptr(self.mate, i32p)
+        b.dup_of = _ptr(self.dup_of, i32p)
+        self.view = b
+
+    def __len__(self) -> int:
+        return len(self.lseq)
+
+    def nbytes_h2d(self) -> int:
+        return sum(x.nbytes for x in (self.seq4, self.lseq, self.flag, self.mapq, self.isize, self.same_tid,
+                                      self.score_diff, self.clipped, self.sample, self.mate, self.dup_of))
+
+
+class HostAccumulators:
+    """Caller-owned accumulator buffers sized from (n_bubbles, n_scores, n_cov, n_samples)."""
+
+    def __init__(self, n_bubbles: int, n_scores: int, n_cov: int, n_samples: int):
+        NB, NS = n_bubbles, n_samples
+        self.bubble_id = np.zeros(NB, np.uint32)
+        self.n_alleles = np.zeros(NB, np.uint32)
+        self.score_off = np.zeros(NB + 1, np.uint64)
+        self.cov_off = np.zeros(NB + 1, np.uint64)
+        self.log_score = np.zeros(n_scores * NS, np.uint16)
+        self.gt_coverage = np.zeros(n_cov * NS, np.uint16)
+        self.max_log_score = np.zeros(NB * NS, np.uint16)
+        self.ambiguous_depth = np.zeros(NB * NS, np.uint8)
+        self.ambiguous_depth_alt = np.zeros(NB * NS, np.uint8)
+        self.alt_proper_pair_depth = np.zeros(NB * NS, np.uint8)
+        self.saturated = np.zeros(NB * NS, np.uint32)
+        self.vs_clipped_reads = np.zeros(NB, np.uint64)
+        self.vs_mapq_squared = np.zeros(NB, np.uint64)
+        self.pa_clipped_bp = np.zeros(n_cov, np.uint64)
+        self.pa_mapq_squared = np.zeros(n_cov, np.uint64)
+        self.pa_score_diff = np.zeros(n_cov, np.uint64)
+        self.pa_mismatches = np.zeros(n_cov, np.uint64)
+        self.read_strand = np.zeros(n_cov * 4, np.uint32)
+        a = Accumulators()
+        a.n_bubbles = NB
+        a.n_samples = NS
+        for name, typ in Accumulators._fields_[2:]:
+            setattr(a, name, _ptr(getattr(self, name), typ))
+        self.view = a
+        self.n_samples = NS
+        self.n_bubbles = NB
+
+    ARRAYS = ["bubble_id", "n_alleles", "score_off", "cov_off", "log_score", "gt_coverage", "max_log_score",
+              "ambiguous_depth", "ambiguous_depth_alt", "alt_proper_pair_depth", "saturated",
+              "vs_clipped_reads", "vs_mapq_squared", "pa_clipped_bp", "pa_mapq_squared", "pa_score_diff",
+              "pa_mismatches", "read_strand"]
+
+    def as_dict(self) -> Dict[str, np.ndarray]:
+        return {k: getattr(self, k) for k in self.ARRAYS}
+
+
+# ----------------------------------------------------------------------------- read preparation (host)
+
+_NIB = np.full(256, 15, dtype=np.uint8)
+for _c, _v in zip(b"=ACMGRSVTWYHKDBN", range(16)):
+    _NIB[_c] = _v
+    _NIB[ord(chr(_c).lower())] = _v
+
+
+def pack_seq4(seq_ascii: np.ndarray, seq_stride: int = SEQ_STRIDE) -> np.ndarray:
+    """ASCII [n, L] -> BAM 4-bit packed [n, seq_stride] (high nibble first), as sam_parse1 stores it."""
+    n, L = seq_ascii.shape
+    nib = _NIB[seq_ascii]
+    if L % 2:
+        nib = np.concatenate([nib, np.zeros((n, 1), np.uint8)], axis=1)
+    packed = (nib[:, 0::2] << 4) | nib[:, 1::2]
+    out = np.zeros((n, seq_stride), np.uint8)
+    out[:, :packed.shape[1]] = packed
+    return out
+
+
+def score_diff_from_tags(as_tag: np.ndarray, xs_tag: np.ndarray) -> np.ndarray:
+    """get_score_diff (src/typer/alignment.cpp:140-325): as/xs = -1 when the tag is absent."""
+    a = as_tag.astype(np.int64)
+    x = xs_tag.astype(np.int64)
+    zero = (a == -1) | (a < x)
+    x = np.where(x == -1, 0, x)
+    d = np.minimum(a - x, 255)
+    return np.where(zero, 0, d).astype(np.uint8)
+
+
+def compute_dup_of(pos: np.ndarray, lseq: np.ndarray, seq4: np.ndarray, tid: Optional[np.ndarray] = None) -> np.ndarray:
+    """equal_pos_seq chain (include/graphtyper/utilities/hts_utils.hpp:110-128, hts_parallel_reader.cpp:666-684)."""
+    n = len(pos)
+    dup = np.full(n, -1, np.int32)
+    if n < 2:
+        return dup
+    eq = (pos[1:] == pos[:-1]) & (lseq[1:] == lseq[:-1])
+    if tid is not None:
+        eq &= tid[1:] == tid[:-1]
+    idx = np.nonzero(eq)[0]
+    if len(idx):
+        nb = (lseq[idx + 1].astype(np.int64) + 1) // 2
+        same = np.ones(len(idx), bool)
+        # compare packed bytes over (l_qseq+1)/2 (all reads usually share one length)
+        for L in np.unique(nb):
+            m = nb == L
+            same[m] = (seq4[idx[m] + 1, :L] == seq4[idx[m], :L]).all(axis=1)
+        eq[idx] = same
+    is_dup = np.concatenate([[False], eq])
+    # root = last non-dup record before i
+    root = np.where(~is_dup, np.arange(n), 0)
+    root = np.maximum.accumulate(root)
+    dup[is_dup] = root[is_dup]
+    return dup
+
+
+def compute_mates(name_id: np.ndarray, flag: np.ndarray, rg: Optional[np.ndarray] = None) -> np.ndarray:
+    """Read-name map semantics of genotype_only (hts_parallel_reader.cpp:270-337): within a read group the
+    1st paired record of a name waits, the 2nd pairs with it (and removes it), the 3rd waits again ..."""
+    n = len(name_id)
+    mate = np.full(n, -1, np.int32)
+    paired = (flag & 1) != 0
+    idx = np.nonzero(paired)[0]
+    if len(idx) == 0:
+        return mate
+    key = name_id[idx].astype(np.int64)
+    if rg is not None:
+        key = key * (int(rg.max()) + 1) + rg[idx]
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    # rank within each run of equal keys
+    start = np.concatenate([[True], ks[1:] != ks[:-1]])
+    run_start = np.maximum.accumulate(np.where(start, np.arange(len(ks)), 0))
+    rank = np.arange(len(ks)) - run_start
+    second = (rank % 2) == 1
+    sec_pos = np.nonzero(second)[0]
+    mate[idx[order[sec_pos]]] = idx[order[sec_pos - 1]]
+    return mate
+
+
+def batch_from_readsets(readsets: Sequence, region_idx: Optional[Sequence[np.ndarray]] = None,
+                        flag_filter: int = 3840) -> HostBatch:
+    """Builds one pool's batch from synth.ReadSet objects (one per sample), merged in the reference's k-way
+    merge order: (pos, then the 4-bit sequence bytes), ties keeping file order
+    (Cmp_gt_pair_bam1_t_fun, include/graphtyper/utilities/hts_utils.hpp:60-108)."""
+    cols = {k: [] for k in ("pos", "flag", "mapq", "isize", "seq", "as", "xs", "sample", "name")}
+    for s, rs in enumerate(readsets):
+        idx = np.arange(len(rs)) if region_idx is None else region_idx[s]
+        keep = (rs.flag[idx] & flag_filter) == 0
+        idx = idx[keep]
+        cols["pos"].append(rs.pos[idx])
+        cols["flag"].append(rs.flag[idx])
+        cols["mapq"].append(rs.mapq[idx])
+        cols["isize"].append(rs.isize[idx])
+        cols["seq"].append(rs.seq[idx])
+        cols["as"].append(rs.as_tag[idx])
+        cols["xs"].append(rs.xs_tag[idx])
+        cols["sample"].append(np.full(len(idx), s, np.int32))
+        # names are unique per sample: offset ids per sample so the name map never collides across RGs
+        cols["name"].append(rs.name_id[idx].astype(np.int64) * len(readsets) + s)
+    cat = {k: np.concatenate(v) for k, v in cols.items()}
+    n = len(cat["pos"])
+    L = cat["seq"].shape[1] if n else 0
+    seq4 = pack_seq4(cat["seq"]) if n else np.zeros((0, SEQ_STRIDE), np.uint8)
+    if len(readsets) > 1:
+        order = merge_order(cat["pos"], np.full(n, L), seq4, cat["sample"])
+        for k in cat:
+            cat[k] = cat[k][order]
+        seq4 = seq4[order]
+    lseq = np.full(n, L, np.uint16)
+    dup = compute_dup_of(cat["pos"], lseq, seq4)
+    mate = compute_mates(cat["name"], cat["flag"])
+    sd = score_diff_from_tags(cat["as"], cat["xs"])
+    return HostBatch(seq4, lseq, cat["flag"], cat["mapq"], np.clip(cat["isize"], -2**31, 2**31 - 1),
+                     np.ones(n, np.uint8), sd, np.zeros(n, np.uint8), cat["sample"], mate, dup)
+
+
+def merge_order(pos: np.ndarray, lseq: np.ndarray, seq4: np.ndarray, file_index: np.ndarray) -> np.ndarray:
+    """Order of HtsParallelReader's heap merge: ascending (tid,) pos, l_qseq, sequence bytes; equal records keep
+    heap order (approximated by file index, then input order)."""
+    n = len(pos)
+    nb = seq4.shape[1]
+    keys = [np.arange(n), file_index]
+    for c in range(nb - 1, -1, -1):
+        keys.append(seq4[:, c])
+    keys.append(lseq)
+    keys.append(pos)
+    return np.lexsort(tuple(keys))
+
+
+def batch_from_probe(d: Dict[str, np.ndarray]) -> HostBatch:
+    """Batch from the record columns dumped by oracle/_ref/bin/gt_probe (<out>.reads.gtba)."""
+    n = len(d["flag"])
+    seq4 = np.zeros((n, SEQ_STRIDE), np.uint8)
+    off = d["seq_off"].astype(np.int64)
+    ln = (off[1:] - off[:-1])
+    for L in np.unique(ln):
+        m = np.nonzero(ln == L)[0]
+        gather = off[m][:, None] + np.arange(L)[None, :]
+        seq4[m[:, None], np.arange(L)[None, :]] = d["seq4"][gather]
+    names = d["names"].tobytes()
+    noff = d["name_off"].astype(np.int64)
+    ids: Dict[bytes, int] = {}
+    name_id = np.empty(n, np.int64)
+    for i in range(n):
+        nm = names[noff[i]:noff[i + 1]]
+        name_id[i] = ids.setdefault(nm, len(ids))
+    lseq = d["lseq"].astype(np.uint16)
+    dup = compute_dup_of(d["pos"], lseq, seq4, d["tid"])
+    assert np.array_equal(dup >= 0, d["isdup"] != 0), "dup detection differs from the reference loop"
+    mate = compute_mates(name_id, d["flag"], d["rg"].astype(np.int64))
+    return HostBatch(seq4, lseq, d["flag"], d["mapq"], np.clip(d["isize"], -2**31, 2**31 - 1),
+                     (d["tid"] == d["mtid"]).astype(np.uint8), d["score_diff"], np.zeros(n, np.uint8),
+                     d["sample"], mate, dup)

@@ -1,0 +1,203 @@
+/* gtb200.h -- C ABI of libgtb200: the B200-native read -> pangenome-graph genotyping path.
+ *
+ * This is the drop-in boundary.  The reference (graphtyper v2.7.7) has no
+ * FFI layer; the seams this ABI replaces are C++ call sites:
+ *
+ *   gtb_region_begin()   replaces  PHIndex index_graph(Graph const&)                include/graphtyper/index/indexer.hpp:16
+ *                                  (called at src/utilities/genotype.cpp:294,550, genotype_sv.cpp:97)
+ *                                  and uploads the flattened gyper::graph            include/graphtyper/graph/graph.hpp:39-171
+ *   gtb_pool_begin()     replaces  VcfWriter writer; writer.set_samples(...)         src/utilities/hts_parallel_reader.cpp:493-494
+ *   gtb_submit_reads()   replaces  the per-record body of the pool loop: get_sequence + align_read +
+ *                                  update_paths + get_better_paths + VcfWriter::update_haplotype_scores_geno
+ *                                  (src/utilities/hts_parallel_reader.cpp:245-338,655-708; src/typer/alignment.cpp:331,482,557;
+ *                                  src/typer/vcf_writer.cpp:88-250,503-676; src/graph/haplotype.cpp:180-585)
+ *   gtb_pool_finish()    replaces  reading VcfWriter::haplotypes[*].hap_samples[*]   include/graphtyper/typer/vcf_writer.hpp:51-52
+ *                                  (input of Vcf::add_haplotype, src/typer/vcf.cpp:1507)
+ *   gtb_calls_from_accumulators()  = get_haplotype_phred + SampleCall ctor/get_gt_call/get_gq
+ *                                  (src/typer/vcf.cpp:47-81, src/typer/sample_call.cpp:34-131)
+ *
+ * Conventions: every function returns 0 on success or a negative gtb_status; gtb_last_error() gives the
+ * message (the C++ shim on the reference side turns that into print_log(error)+exit(1), the reference's
+ * own error convention).  All pointers are plain host pointers; sizes are element counts.  No torch or
+ * CUDA types appear here.  All positions are the reference's 1-based ABSOLUTE positions
+ * (include/graphtyper/graph/absolute_position.hpp:13-39); special positions are >= GTB_SPECIAL_START.
+ */
+#ifndef GTB200_H
+#define GTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTB_K 32u                       /* include/graphtyper/constants.hpp.in:20 */
+#define GTB_INVALID_ID 0xFFFFFFFFu      /* constants.hpp.in:21 */
+#define GTB_SPECIAL_START 0xD0000000u   /* constants.hpp.in:33 */
+#define GTB_MAX_READ_LENGTH 151u        /* constants.hpp.in:27 */
+#define GTB_SEQ_STRIDE 76u              /* bytes of 4-bit bases per read: ceil(151/2) */
+
+typedef enum gtb_status {
+  GTB_OK = 0,
+  GTB_ERR_ARG = -1,        /* bad argument / inconsistent view */
+  GTB_ERR_CUDA = -2,       /* CUDA runtime failure (or no device: the product path never falls back to the CPU) */
+  GTB_ERR_STATE = -3,      /* call order violated */
+  GTB_ERR_CAPACITY = -4,   /* a device-side capacity was exceeded (paths per read, alleles per bubble ...) */
+  GTB_ERR_INPUT = -5,      /* input the reference aborts on (e.g. two mates both first-in-pair) */
+  GTB_ERR_NCCL = -6
+} gtb_status;
+
+/* Flattened gyper::Graph (ref_nodes / var_nodes, graph.hpp:45-52): ref node r is followed by the bubble
+ * var nodes [ref_var_off[r], ref_var_off[r+1]) (allele 0 = reference allele, graph.cpp:341-345), which all
+ * lead to ref node r+1.  Sequence bytes are ASCII. */
+typedef struct gtb_graph_view {
+  uint32_t n_ref;
+  uint32_t n_var;
+  int32_t is_sv_graph;
+  int32_t reserved;
+  const uint32_t *ref_order;    /* [n_ref]    Label::order of each ref node */
+  const uint64_t *ref_seq_off;  /* [n_ref+1]  into seq */
+  const uint32_t *ref_var_off;  /* [n_ref+1]  CSR of out_var_ids */
+  const uint32_t *var_order;    /* [n_var] */
+  const uint64_t *var_seq_off;  /* [n_var+1]  into seq */
+  const uint32_t *var_out_ref;  /* [n_var]    VarNode::out_ref_id */
+  const uint8_t *seq;           /* [seq_len] */
+  uint64_t seq_len;
+  const uint32_t *var_ev_off;   /* [n_var+1]  VarNode::events (sorted), may be NULL when no events */
+  const int64_t *var_ev;
+  const uint32_t *var_aev_off;  /* [n_var+1]  VarNode::anti_events */
+  const int64_t *var_aev;
+  uint32_t n_special;           /* Graph::actual_poses / ref_reach_poses (graph.cpp:1759-1803) */
+  const uint32_t *actual_poses;
+  const uint32_t *ref_reach_poses;
+  uint32_t n_sp_keys;           /* Graph::ref_reach_to_special_pos, keys ascending */
+  const uint32_t *sp_keys;      /* [n_sp_keys] */
+  const uint32_t *sp_off;       /* [n_sp_keys+1] */
+  const uint32_t *sp_list;      /* special position codes */
+} gtb_graph_view;
+
+/* One KmerLabel (include/graphtyper/index/kmer_label.hpp:13-38). */
+typedef struct gtb_label {
+  uint32_t start;
+  uint32_t end;
+  uint32_t var_id;
+} gtb_label;
+
+/* Records of one pool in the order the reference's k-way merge delivers them
+ * (HtsParallelReader::read_record, hts_parallel_reader.cpp:98-136), after the flag filter. */
+typedef struct gtb_read_batch {
+  uint32_t n_reads;
+  uint32_t seq_stride;        /* bytes per read in seq4 (>= (max lseq+1)/2); GTB_SEQ_STRIDE typical */
+  const uint8_t *seq4;        /* BAM 4-bit bases, high nibble first (bam_get_seq) */
+  const uint16_t *lseq;       /* core.l_qseq */
+  const uint16_t *flag;       /* core.flag */
+  const uint8_t *mapq;        /* core.qual */
+  const int32_t *isize;       /* core.isize clamped to int32 */
+  const uint8_t *same_tid;    /* core.tid == core.mtid */
+  const uint8_t *score_diff;  /* AS-XS as get_score_diff() computes it (alignment.cpp:140-325) */
+  const uint8_t *clipped;     /* clipped_count(rec) > 3 (alignment.cpp:105-138; always 0 in the reference) */
+  const int32_t *sample;      /* sample index within the pool */
+  const int32_t *mate;        /* index (in this batch) of the earlier record this one pairs with, else -1
+                                 (read-name map semantics of genotype_only, hts_parallel_reader.cpp:270-337) */
+  const int32_t *dup_of;      /* index of the record whose alignment is re-used (equal_pos_seq shortcut,
+                                 hts_parallel_reader.cpp:666-684), else -1 */
+} gtb_read_batch;
+
+/* Per-pool accumulators = VcfWriter::haplotypes[b].hap_samples[s] (+ var_stats), bubble-major:
+ * for bubble b (cnum = n_alleles[b], tri = cnum(cnum+1)/2) and sample s
+ *   log_score     [ score_off[b] * n_samples + s * tri .. +tri )
+ *   gt_coverage   [ cov_off[b]   * n_samples + s * cnum .. +cnum )
+ *   per-sample scalars at [b * n_samples + s]
+ *   per-allele stats at [cov_off[b] + a]
+ * Buffers are owned by the caller and sized with gtb_accumulator_sizes(). */
+typedef struct gtb_accumulators {
+  uint32_t n_bubbles;
+  uint32_t n_samples;
+  uint32_t *bubble_id;        /* [n_bubbles]  Genotype::id = order of the bubble's var nodes */
+  uint32_t *n_alleles;        /* [n_bubbles] */
+  uint64_t *score_off;        /* [n_bubbles+1] prefix sum of tri */
+  uint64_t *cov_off;          /* [n_bubbles+1] prefix sum of cnum */
+  uint16_t *log_score;        /* [score_off[n_bubbles] * n_samples] */
+  uint16_t *gt_coverage;      /* [cov_off[n_bubbles] * n_samples] */
+  uint16_t *max_log_score;    /* [n_bubbles * n_samples] */
+  uint8_t *ambiguous_depth;   /* [n_bubbles * n_samples] */
+  uint8_t *ambiguous_depth_alt;
+  uint8_t *alt_proper_pair_depth;
+  uint32_t *saturated;        /* [n_bubbles * n_samples] 1 when the max_log_score guard (haplotype.cpp:561) fired:
+                                 result is order dependent beyond ~6000x depth, out of contract */
+  uint64_t *vs_clipped_reads; /* [n_bubbles]  VarStats::clipped_reads */
+  uint64_t *vs_mapq_squared;  /* [n_bubbles] */
+  uint64_t *pa_clipped_bp;    /* [cov_off[n_bubbles]] VarStatsPerAllele */
+  uint64_t *pa_mapq_squared;
+  uint64_t *pa_score_diff;
+  uint64_t *pa_mismatches;
+  uint32_t *read_strand;      /* [cov_off[n_bubbles] * 4]  r1_forward r1_reverse r2_forward r2_reverse */
+} gtb_accumulators;
+
+/* Counters of one gtb_submit_reads call (diagnostics + bench bookkeeping). */
+typedef struct gtb_submit_stats {
+  uint64_t n_records;         /* records in the batch */
+  uint64_t n_alignments;      /* distinct (record) alignments run (non-duplicates) */
+  uint64_t n_oriented;        /* read orientations aligned (1 or 2 per alignment) */
+  uint64_t n_pairs_scored;    /* pairs passed to the accumulator */
+  uint64_t n_singles_scored;
+  uint64_t n_capacity_overflow; /* reads that exceeded a device capacity (must be 0; else GTB_ERR_CAPACITY) */
+  uint64_t kernel_launches;   /* kernels launched by this call */
+} gtb_submit_stats;
+
+typedef struct gtb_ctx gtb_ctx;
+
+const char *gtb_last_error(void);
+const char *gtb_version(void);
+
+/* device_id < 0: host-only context (index build, host finalisation); compute entry points then fail. */
+int gtb_create(int device_id, gtb_ctx **out);
+void gtb_destroy(gtb_ctx *ctx);
+
+/* Region: flatten + index build (host) + upload (device). Regions are identified by a small integer so
+ * several regions can be resident and processed by ONE batched launch (region-batched mode). */
+int gtb_region_begin(gtb_ctx *ctx, int region_id, const gtb_graph_view *graph);
+int gtb_region_end(gtb_ctx *ctx, int region_id);
+
+/* Index inspection (parity with PHIndex contents): keys ascending, labels in bucket order. */
+int gtb_index_size(gtb_ctx *ctx, int region_id, uint64_t *n_keys, uint64_t *n_labels);
+int gtb_index_export(gtb_ctx *ctx, int region_id, uint64_t *keys, uint32_t *label_off, gtb_label *labels);
+
+/* Pool of samples for one region. */
+int gtb_pool_begin(gtb_ctx *ctx, int region_id, int n_samples);
+int gtb_submit_reads(gtb_ctx *ctx, int region_id, const gtb_read_batch *batch, gtb_submit_stats *stats);
+int gtb_accumulator_sizes(gtb_ctx *ctx, int region_id, uint32_t *n_bubbles, uint64_t *n_scores, uint64_t *n_cov);
+int gtb_pool_finish(gtb_ctx *ctx, int region_id, gtb_accumulators *out);
+
+/* Region-batched submission: regions[i] / batches[i] for i < n; one fused launch sequence for all. */
+int gtb_submit_reads_multi(gtb_ctx *ctx, int n, const int *region_ids, const gtb_read_batch *batches,
+                           gtb_submit_stats *stats);
+
+/* Debug/parity taps of the last gtb_submit_reads on a region (sizes via the *_sizes call first).
+ * Seeds: for alignment a (= non-duplicate record, in batch order), orientation o, ham h (0 exact, 1 Hamming-1),
+ * slot i: labels in PHIndex::multi_get order (ph_index.cpp:66-107). */
+int gtb_debug_enable(gtb_ctx *ctx, int on);
+int gtb_debug_seed_sizes(gtb_ctx *ctx, int region_id, uint64_t *n_units, uint64_t *n_slots, uint64_t *n_labels);
+int gtb_debug_seeds(gtb_ctx *ctx, int region_id, uint32_t *unit_record, uint32_t *nslots /*[n_units*2*2]*/,
+                    uint32_t *nlabels, gtb_label *labels);
+/* Paths: GenotypePaths of align_read (alignment.cpp:331) per (alignment, orientation). */
+int gtb_debug_path_sizes(gtb_ctx *ctx, int region_id, uint64_t *n_units, uint64_t *n_paths, uint64_t *n_vars,
+                         uint64_t *n_nums);
+int gtb_debug_paths(gtb_ctx *ctx, int region_id, uint32_t *gp_npaths /*[n_units*2]*/, uint32_t *gp_longest,
+                    uint32_t *p_fields /*[n_paths*6]: start end rs re mm nvar*/, uint32_t *v_order,
+                    uint32_t *v_nnum, uint16_t *v_nums);
+
+/* Host finalisation (pure function of the accumulators): PL (uint8), GT pair, GQ per bubble x sample. */
+int gtb_calls_from_accumulators(const gtb_accumulators *acc, uint8_t *phred /*[n_scores*n_samples]*/,
+                                uint16_t *gt /*[n_bubbles*n_samples*2]*/, uint8_t *gq /*[n_bubbles*n_samples]*/);
+
+/* Multi-GPU: sum-reduce widened accumulators of a region over an NCCL communicator supplied by the host
+ * (ncclComm_t passed as void*; all ranks call; result valid on every rank).  Used when ONE sample's reads
+ * are split over GPUs; with sample sharding no collective is needed. */
+int gtb_allreduce_accumulators(gtb_ctx *ctx, int region_id, void *nccl_comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTB200_H */
