@@ -308,7 +308,7 @@ def batch_from_readsets(readsets: Sequence, region_idx: Optional[Sequence[np.nda
     n = len(cat["pos"])
     L = cat["seq"].shape[1] if n else 0
     seq4 = pack_seq4(cat["seq"]) if n else np.zeros((0, SEQ_STRIDE), np.uint8)
-    if len(readsets) > 1:
+    if n:
         order = merge_order(cat["pos"], np.full(n, L), seq4, cat["sample"])
         for k in cat:
             cat[k] = cat[k][order]
@@ -323,10 +323,12 @@ def batch_from_readsets(readsets: Sequence, region_idx: Optional[Sequence[np.nda
 
 def merge_order(pos: np.ndarray, lseq: np.ndarray, seq4: np.ndarray, file_index: np.ndarray) -> np.ndarray:
     """Order of HtsParallelReader's heap merge: ascending (tid,) pos, l_qseq, sequence bytes; equal records keep
-    heap order (approximated by file index, then input order)."""
+    heap order.  Within one file same-position records are std::sort-ed descending and popped from the back
+    (HtsReader::get_next_read_in_order, src/utilities/hts_reader.cpp:166-303), so fully equal records come out
+    in reverse file order; across files the tie order is the heap's (approximated by file index)."""
     n = len(pos)
     nb = seq4.shape[1]
-    keys = [np.arange(n), file_index]
+    keys = [-np.arange(n), file_index]
     for c in range(nb - 1, -1, -1):
         keys.append(seq4[:, c])
     keys.append(lseq)

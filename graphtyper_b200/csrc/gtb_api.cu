@@ -1,0 +1,1183 @@
+// gtb_api.cu -- C-ABI entry points (include/gtb200.h) and host orchestration (product code).
+//
+// Host responsibilities (the reference keeps these on the host too): graph flattening checks, k-mer index
+// construction (gtb_index_host.hpp), packing one region into a single device arena, batching records
+// (alignment units for the duplicate-read shortcut, mate links), kernel launches on a private stream,
+// accumulator download + saturation, PHRED conversion.  There is NO CPU fallback for the compute path: without
+// a usable CUDA device gtb_create(device >= 0) fails and every compute entry point returns GTB_ERR_CUDA.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include "gtb_device.cuh"
+
+using namespace gtb;
+
+namespace
+{
+thread_local std::string g_err;
+
+int fail(int code, const std::string & msg)
+{
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do                                                                                                \
+  {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return fail(GTB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));               \
+  } while (0)
+
+struct DeviceBuffer
+{
+  void * p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n)
+  {
+    if (n <= cap)
+      return 0;
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t const want = n + n / 4 + 4096;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess)
+      return fail(GTB_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    cap = want;
+    return 0;
+  }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct PinnedBuffer
+{
+  void * p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n)
+  {
+    if (n <= cap)
+      return 0;
+    if (p)
+      cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t const want = n + n / 4 + 4096;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess)
+      return fail(GTB_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    cap = want;
+    return 0;
+  }
+  void release()
+  {
+    if (p)
+      cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct Region
+{
+  int id = -1;
+  int slot = -1; // index into the device region table
+  // host copies
+  std::vector<uint32_t> bubble_order, n_alleles, score_off, cov_off;
+  HostIndex index;
+  uint32_t n_bubbles = 0;
+  int n_samples = 0;
+  bool pool_open = false;
+  // device
+  DeviceBuffer arena;   // graph + index
+  DeviceBuffer accum;   // accumulators (allocated at pool_begin)
+  DevRegion dev{};      // pointers into arena/accum
+  size_t accum_bytes = 0;
+};
+
+struct Ctx
+{
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::map<int, std::unique_ptr<Region>> regions;
+  std::vector<int> slot_region; // slot -> region id (-1 free)
+  DeviceBuffer d_regions;       // DevRegion table
+  bool regions_dirty = true;
+  // batch
+  DeviceBuffer d_batch, d_summaries, d_pool, d_counters, d_tap_counts, d_tap_pool;
+  PinnedBuffer h_batch, h_counters;
+  LaunchParams last{};
+  bool have_last = false;
+  uint32_t last_n_tasks = 0;
+  bool debug = false;
+  std::vector<int> last_regions; // region ids of the last submit, in batch order
+  std::vector<uint32_t> last_unit_begin; // per region of the last submit: first unit index (size n+1)
+  std::vector<uint32_t> last_rec_begin;
+  float t_h2d = 0, t_align = 0, t_score = 0, t_d2h = 0;
+  // nccl (loaded lazily with dlopen, see gtb_nccl.cpp part below)
+  void * nccl_lib = nullptr;
+  void * nccl_comm = nullptr;
+  int nccl_rank = 0, nccl_size = 1;
+};
+
+int upload_region_table(Ctx * c)
+{
+  if (!c->regions_dirty)
+    return 0;
+  size_t const n = c->slot_region.size();
+  std::vector<DevRegion> tab(std::max<size_t>(n, 1));
+  for (size_t s = 0; s < n; ++s)
+    if (c->slot_region[s] >= 0)
+      tab[s] = c->regions[c->slot_region[s]]->dev;
+  if (int rc = c->d_regions.reserve(tab.size() * sizeof(DevRegion)))
+    return rc;
+  CUDA_TRY(cudaMemcpyAsync(c->d_regions.p, tab.data(), tab.size() * sizeof(DevRegion), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->regions_dirty = false;
+  return 0;
+}
+
+int validate_graph(const gtb_graph_view * g)
+{
+  if (!g || g->n_ref == 0)
+    return fail(GTB_ERR_ARG, "empty graph view");
+  if (!g->ref_order || !g->ref_seq_off || !g->ref_var_off || !g->seq)
+    return fail(GTB_ERR_ARG, "graph view has null arrays");
+  if (g->n_var && (!g->var_order || !g->var_seq_off || !g->var_out_ref))
+    return fail(GTB_ERR_ARG, "graph view has null var arrays");
+  if (g->seq_len >= 0xFFFFFFFFull)
+    return fail(GTB_ERR_ARG, "graph sequence larger than 4 GiB");
+  if (g->ref_var_off[0] != 0 || g->ref_var_off[g->n_ref] != g->n_var)
+    return fail(GTB_ERR_ARG, "ref_var_off is not a CSR over the var nodes");
+  if (g->ref_var_off[g->n_ref - 1] != g->n_var)
+    return fail(GTB_ERR_ARG, "the last ref node must have no out variants");
+  for (uint32_t r = 0; r + 1 < g->n_ref; ++r)
+  {
+    uint32_t const deg = g->ref_var_off[r + 1] - g->ref_var_off[r];
+    if (deg < 2)
+      return fail(GTB_ERR_ARG, "every bubble needs a reference allele and at least one alternative allele "
+                               "(the reference drops records without alts, graph.cpp:60-71)");
+    if (deg > (uint32_t)MAX_ALLELES)
+      return fail(GTB_ERR_CAPACITY, "bubble with more than 32 alleles: not supported by the device path yet");
+    if (g->ref_order[r] > g->ref_order[r + 1])
+      return fail(GTB_ERR_ARG, "ref node orders must be non-decreasing");
+    for (uint32_t v = g->ref_var_off[r]; v < g->ref_var_off[r + 1]; ++v)
+      if (g->var_out_ref[v] != r + 1)
+        return fail(GTB_ERR_ARG, "var_out_ref does not match the bubble structure");
+  }
+  return 0;
+}
+
+template <typename T>
+size_t place(size_t & off, size_t count)
+{
+  size_t const o = align_up(off, 16);
+  off = o + count * sizeof(T);
+  return o;
+}
+
+} // namespace
+
+extern "C"
+{
+const char * gtb_last_error(void) { return g_err.c_str(); }
+const char * gtb_version(void) { return "graphtyper_b200 0.1 (sm_100a)"; }
+
+int gtb_create(int device_id, gtb_ctx ** out)
+{
+  if (!out)
+    return fail(GTB_ERR_ARG, "null out");
+  auto * c = new Ctx();
+  c->device = device_id;
+  if (device_id >= 0)
+  {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= device_id)
+    {
+      delete c;
+      return fail(GTB_ERR_CUDA, std::string("no usable CUDA device ") + std::to_string(device_id) + ": " +
+                                  (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range") +
+                                  " (the compute path has no CPU fallback)");
+    }
+    e = cudaSetDevice(device_id);
+    if (e == cudaSuccess)
+      e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+      e = cudaEventCreate(&c->ev[i]);
+    if (e != cudaSuccess)
+    {
+      delete c;
+      return fail(GTB_ERR_CUDA, std::string("CUDA init failed: ") + cudaGetErrorString(e));
+    }
+  }
+  *out = reinterpret_cast<gtb_ctx *>(c);
+  return 0;
+}
+
+void gtb_destroy(gtb_ctx * ctx)
+{
+  if (!ctx)
+    return;
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (c->device >= 0)
+  {
+    cudaSetDevice(c->device);
+    if (c->stream)
+      cudaStreamSynchronize(c->stream);
+    for (auto & kv : c->regions)
+    {
+      kv.second->arena.release();
+      kv.second->accum.release();
+    }
+    c->d_regions.release();
+    c->d_batch.release();
+    c->d_summaries.release();
+    c->d_pool.release();
+    c->d_counters.release();
+    c->d_tap_counts.release();
+    c->d_tap_pool.release();
+    c->h_batch.release();
+    c->h_counters.release();
+    for (auto & e : c->ev)
+      if (e)
+        cudaEventDestroy(e);
+    if (c->stream)
+      cudaStreamDestroy(c->stream);
+  }
+  delete c;
+}
+
+int gtb_region_begin(gtb_ctx * ctx, int region_id, const gtb_graph_view * g)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c)
+    return fail(GTB_ERR_ARG, "null ctx");
+  if (c->regions.count(region_id))
+    return fail(GTB_ERR_STATE, "region id already in use");
+  if (int rc = validate_graph(g))
+    return rc;
+  auto R = std::make_unique<Region>();
+  R->id = region_id;
+  R->n_bubbles = g->n_ref - 1;
+  {
+    IndexBuilder ib(*g);
+    const char * err = nullptr;
+    if (!ib.build(R->index, &err))
+      return fail(GTB_ERR_ARG, err ? err : "index build failed");
+  }
+  R->score_off.assign(1, 0);
+  R->cov_off.assign(1, 0);
+  for (uint32_t b = 0; b < R->n_bubbles; ++b)
+  {
+    uint32_t const v0 = g->ref_var_off[b];
+    uint32_t const cnum = g->ref_var_off[b + 1] - v0;
+    R->bubble_order.push_back(g->var_order[v0]);
+    R->n_alleles.push_back(cnum);
+    R->score_off.push_back(R->score_off.back() + cnum * (cnum + 1) / 2);
+    R->cov_off.push_back(R->cov_off.back() + cnum);
+  }
+
+  if (c->device >= 0)
+  {
+    cudaSetDevice(c->device);
+    // ---- pack the arena
+    size_t off = 0;
+    size_t const o_ref_order = place<uint32_t>(off, g->n_ref);
+    size_t const o_ref_seq_off = place<uint32_t>(off, g->n_ref + 1);
+    size_t const o_ref_var_off = place<uint32_t>(off, g->n_ref + 1);
+    size_t const o_var_order = place<uint32_t>(off, g->n_var);
+    size_t const o_var_seq_off = place<uint32_t>(off, g->n_var + 1);
+    size_t const o_var_out_ref = place<uint32_t>(off, g->n_var);
+    size_t const o_seq = place<uint8_t>(off, g->seq_len + 16);
+    size_t const o_actual = place<uint32_t>(off, g->n_special);
+    size_t const o_rreach = place<uint32_t>(off, g->n_special);
+    size_t const o_sp_keys = place<uint32_t>(off, g->n_sp_keys);
+    size_t const o_sp_off = place<uint32_t>(off, g->n_sp_keys + 1);
+    size_t const n_sp_list = g->n_sp_keys ? g->sp_off[g->n_sp_keys] : 0;
+    size_t const o_sp_list = place<uint32_t>(off, n_sp_list);
+    size_t const o_bubble_order = place<uint32_t>(off, R->n_bubbles);
+    size_t const o_score_off = place<uint32_t>(off, R->n_bubbles + 1);
+    size_t const o_cov_off = place<uint32_t>(off, R->n_bubbles + 1);
+    size_t const o_table = place<IndexSlot>(off, R->index.table.size());
+    size_t const o_labels = place<DevLabel>(off, R->index.labels.size());
+    size_t const total = align_up(off, 256);
+
+    if (int rc = c->h_batch.reserve(total))
+      return rc;
+    uint8_t * h = static_cast<uint8_t *>(c->h_batch.p);
+    memset(h, 0, total);
+    auto put32 = [&](size_t o, const uint32_t * src, size_t n)
+    {
+      if (n)
+        memcpy(h + o, src, n * 4);
+    };
+    auto put64as32 = [&](size_t o, const uint64_t * src, size_t n)
+    {
+      uint32_t * d = reinterpret_cast<uint32_t *>(h + o);
+      for (size_t i = 0; i < n; ++i)
+        d[i] = (uint32_t)src[i];
+    };
+    put32(o_ref_order, g->ref_order, g->n_ref);
+    put64as32(o_ref_seq_off, g->ref_seq_off, g->n_ref + 1);
+    put32(o_ref_var_off, g->ref_var_off, g->n_ref + 1);
+    put32(o_var_order, g->var_order, g->n_var);
+    put64as32(o_var_seq_off, g->var_seq_off, g->n_var + 1);
+    put32(o_var_out_ref, g->var_out_ref, g->n_var);
+    memcpy(h + o_seq, g->seq, g->seq_len);
+    put32(o_actual, g->actual_poses, g->n_special);
+    put32(o_rreach, g->ref_reach_poses, g->n_special);
+    put32(o_sp_keys, g->sp_keys, g->n_sp_keys);
+    if (g->n_sp_keys)
+      put32(o_sp_off, g->sp_off, g->n_sp_keys + 1);
+    put32(o_sp_list, g->sp_list, n_sp_list);
+    put32(o_bubble_order, R->bubble_order.data(), R->n_bubbles);
+    put32(o_score_off, R->score_off.data(), R->n_bubbles + 1);
+    put32(o_cov_off, R->cov_off.data(), R->n_bubbles + 1);
+    memcpy(h + o_table, R->index.table.data(), R->index.table.size() * sizeof(IndexSlot));
+    memcpy(h + o_labels, R->index.labels.data(), R->index.labels.size() * sizeof(DevLabel));
+
+    if (int rc = R->arena.reserve(total))
+      return rc;
+    CUDA_TRY(cudaMemcpyAsync(R->arena.p, h, total, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+
+    uint8_t * d = static_cast<uint8_t *>(R->arena.p);
+    DevRegion & D = R->dev;
+    memset(&D, 0, sizeof(D));
+    D.n_ref = g->n_ref;
+    D.n_var = g->n_var;
+    D.n_special = g->n_special;
+    D.n_sp_keys = g->n_sp_keys;
+    D.is_sv = g->is_sv_graph ? 1u : 0u;
+    D.n_bubbles = R->n_bubbles;
+    D.n_samples = 0;
+    D.table_mask = R->index.table_mask;
+    {
+      int shift = 64;
+      for (size_t cap = R->index.table.size(); cap > 1; cap >>= 1)
+        --shift;
+      D.table_shift = shift;
+    }
+    D.ref_order = reinterpret_cast<const uint32_t *>(d + o_ref_order);
+    D.ref_seq_off = reinterpret_cast<const uint32_t *>(d + o_ref_seq_off);
+    D.ref_var_off = reinterpret_cast<const uint32_t *>(d + o_ref_var_off);
+    D.var_order = reinterpret_cast<const uint32_t *>(d + o_var_order);
+    D.var_seq_off = reinterpret_cast<const uint32_t *>(d + o_var_seq_off);
+    D.var_out_ref = reinterpret_cast<const uint32_t *>(d + o_var_out_ref);
+    D.seq = d + o_seq;
+    D.actual_poses = reinterpret_cast<const uint32_t *>(d + o_actual);
+    D.ref_reach_poses = reinterpret_cast<const uint32_t *>(d + o_rreach);
+    D.sp_keys = reinterpret_cast<const uint32_t *>(d + o_sp_keys);
+    D.sp_off = reinterpret_cast<const uint32_t *>(d + o_sp_off);
+    D.sp_list = reinterpret_cast<const uint32_t *>(d + o_sp_list);
+    D.bubble_order = reinterpret_cast<const uint32_t *>(d + o_bubble_order);
+    D.score_off = reinterpret_cast<const uint32_t *>(d + o_score_off);
+    D.cov_off = reinterpret_cast<const uint32_t *>(d + o_cov_off);
+    D.table = reinterpret_cast<const IndexSlot *>(d + o_table);
+    D.labels = reinterpret_cast<const DevLabel *>(d + o_labels);
+
+    // slot in the device region table
+    int slot = -1;
+    for (size_t s = 0; s < c->slot_region.size(); ++s)
+      if (c->slot_region[s] < 0)
+      {
+        slot = (int)s;
+        break;
+      }
+    if (slot < 0)
+    {
+      slot = (int)c->slot_region.size();
+      c->slot_region.push_back(-1);
+    }
+    if (slot > 0xFFFF)
+      return fail(GTB_ERR_CAPACITY, "more than 65536 resident regions");
+    c->slot_region[slot] = region_id;
+    R->slot = slot;
+    c->regions_dirty = true;
+  }
+  c->regions[region_id] = std::move(R);
+  return 0;
+}
+
+int gtb_region_end(gtb_ctx * ctx, int region_id)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  auto it = c->regions.find(region_id);
+  if (it == c->regions.end())
+    return fail(GTB_ERR_STATE, "unknown region");
+  if (c->device >= 0)
+  {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    it->second->arena.release();
+    it->second->accum.release();
+    if (it->second->slot >= 0)
+      c->slot_region[it->second->slot] = -1;
+    c->regions_dirty = true;
+  }
+  c->regions.erase(it);
+  c->have_last = false;
+  return 0;
+}
+
+int gtb_index_size(gtb_ctx * ctx, int region_id, uint64_t * n_keys, uint64_t * n_labels)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  auto it = c->regions.find(region_id);
+  if (it == c->regions.end())
+    return fail(GTB_ERR_STATE, "unknown region");
+  *n_keys = it->second->index.keys.size();
+  *n_labels = it->second->index.labels.size();
+  return 0;
+}
+
+int gtb_index_export(gtb_ctx * ctx, int region_id, uint64_t * keys, uint32_t * label_off, gtb_label * labels)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  auto it = c->regions.find(region_id);
+  if (it == c->regions.end())
+    return fail(GTB_ERR_STATE, "unknown region");
+  HostIndex const & ix = it->second->index;
+  memcpy(keys, ix.keys.data(), ix.keys.size() * 8);
+  memcpy(label_off, ix.label_off.data(), ix.label_off.size() * 4);
+  memcpy(labels, ix.labels.data(), ix.labels.size() * sizeof(gtb_label));
+  return 0;
+}
+
+int gtb_pool_begin(gtb_ctx * ctx, int region_id, int n_samples)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  auto it = c->regions.find(region_id);
+  if (it == c->regions.end())
+    return fail(GTB_ERR_STATE, "unknown region");
+  if (c->device < 0)
+    return fail(GTB_ERR_CUDA, "host-only context: the genotyping path needs a CUDA device (no CPU fallback)");
+  if (n_samples <= 0)
+    return fail(GTB_ERR_ARG, "n_samples must be positive");
+  Region & R = *it->second;
+  cudaSetDevice(c->device);
+  size_t const NB = R.n_bubbles, NS = (size_t)n_samples;
+  size_t const n_scores = R.score_off.back(), n_cov = R.cov_off.back();
+  size_t off = 0;
+  size_t const o_ls = place<uint32_t>(off, n_scores * NS);
+  size_t const o_gc = place<uint32_t>(off, n_cov * NS);
+  size_t const o_ml = place<uint32_t>(off, NB * NS);
+  size_t const o_amb = place<uint32_t>(off, NB * NS);
+  size_t const o_amba = place<uint32_t>(off, NB * NS);
+  size_t const o_altpp = place<uint32_t>(off, NB * NS);
+  size_t const o_vcr = place<unsigned long long>(off, NB);
+  size_t const o_vmq = place<unsigned long long>(off, NB);
+  size_t const o_pcb = place<unsigned long long>(off, n_cov);
+  size_t const o_pmq = place<unsigned long long>(off, n_cov);
+  size_t const o_psd = place<unsigned long long>(off, n_cov);
+  size_t const o_pmm = place<unsigned long long>(off, n_cov);
+  size_t const o_rs = place<uint32_t>(off, n_cov * 4);
+  size_t const total = align_up(off, 256);
+  if (int rc = R.accum.reserve(total))
+    return rc;
+  CUDA_TRY(cudaMemsetAsync(R.accum.p, 0, total, c->stream));
+  R.accum_bytes = total;
+  uint8_t * d = static_cast<uint8_t *>(R.accum.p);
+  DevRegion & D = R.dev;
+  D.n_samples = (uint32_t)n_samples;
+  D.log_score = reinterpret_cast<uint32_t *>(d + o_ls);
+  D.gt_cov = reinterpret_cast<uint32_t *>(d + o_gc);
+  D.max_log_score = reinterpret_cast<uint32_t *>(d + o_ml);
+  D.amb = reinterpret_cast<uint32_t *>(d + o_amb);
+  D.amb_alt = reinterpret_cast<uint32_t *>(d + o_amba);
+  D.alt_pp = reinterpret_cast<uint32_t *>(d + o_altpp);
+  D.vs_clipped_reads = reinterpret_cast<unsigned long long *>(d + o_vcr);
+  D.vs_mapq_squared = reinterpret_cast<unsigned long long *>(d + o_vmq);
+  D.pa_clipped_bp = reinterpret_cast<unsigned long long *>(d + o_pcb);
+  D.pa_mapq_squared = reinterpret_cast<unsigned long long *>(d + o_pmq);
+  D.pa_score_diff = reinterpret_cast<unsigned long long *>(d + o_psd);
+  D.pa_mismatches = reinterpret_cast<unsigned long long *>(d + o_pmm);
+  D.read_strand = reinterpret_cast<uint32_t *>(d + o_rs);
+  R.n_samples = n_samples;
+  R.pool_open = true;
+  c->regions_dirty = true;
+  return 0;
+}
+
+static int run_kernels(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
+{
+  LaunchParams & P = c->last;
+  CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, sizeof(DevCounters), c->stream));
+  CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+  launch_align(P, c->stream);
+  CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+  launch_score(P, c->stream);
+  CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  if (record_h2d)
+    cudaEventElapsedTime(&c->t_h2d, c->ev[0], c->ev[1]);
+  cudaEventElapsedTime(&c->t_align, c->ev[1], c->ev[2]);
+  cudaEventElapsedTime(&c->t_score, c->ev[2], c->ev[3]);
+  cudaEventElapsedTime(&c->t_d2h, c->ev[3], c->ev[4]);
+  DevCounters const * k = static_cast<DevCounters *>(c->h_counters.p);
+  if (stats)
+  {
+    stats->n_records = P.batch.n_records;
+    stats->n_alignments = P.batch.n_units;
+    stats->n_oriented = k->n_oriented;
+    stats->n_pairs_scored = k->n_pairs_scored;
+    stats->n_singles_scored = k->n_singles_scored;
+    stats->n_capacity_overflow = k->n_overflow;
+    stats->kernel_launches = (P.batch.n_units ? 1 : 0) + (P.batch.n_records ? 1 : 0);
+  }
+  if (k->n_input_error)
+    return fail(GTB_ERR_INPUT, "two mates with the same IS_FIRST_IN_PAIR flag (the reference aborts here, "
+                               "hts_parallel_reader.cpp:306-315)");
+  if (k->n_overflow)
+    return fail(GTB_ERR_CAPACITY, std::to_string(k->n_overflow) +
+                                    " read(s) exceeded a device working-set capacity (gtb_device.cuh); results incomplete");
+  return 0;
+}
+
+int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const gtb_read_batch * batches,
+                           gtb_submit_stats * stats)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || n <= 0 || !region_ids || !batches)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  if (c->device < 0)
+    return fail(GTB_ERR_CUDA, "host-only context: the genotyping path needs a CUDA device (no CPU fallback)");
+  cudaSetDevice(c->device);
+  size_t total = 0;
+  std::vector<Region *> regs(n);
+  for (int i = 0; i < n; ++i)
+  {
+    auto it = c->regions.find(region_ids[i]);
+    if (it == c->regions.end())
+      return fail(GTB_ERR_STATE, "unknown region in submit");
+    if (!it->second->pool_open)
+      return fail(GTB_ERR_STATE, "gtb_pool_begin must precede gtb_submit_reads");
+    regs[i] = it->second.get();
+    if (batches[i].n_reads && batches[i].seq_stride != GTB_SEQ_STRIDE)
+      return fail(GTB_ERR_ARG, "seq_stride must be GTB_SEQ_STRIDE (76)");
+    total += batches[i].n_reads;
+  }
+  if (total >= 0x7FFFFFFFull)
+    return fail(GTB_ERR_ARG, "batch too large");
+  if (int rc = upload_region_table(c))
+    return rc;
+
+  // ---- staging layout (one pinned buffer, one H2D copy)
+  size_t off = 0;
+  size_t const o_seq4 = place<uint8_t>(off, total * GTB_SEQ_STRIDE);
+  size_t const o_lseq = place<uint16_t>(off, total);
+  size_t const o_flag = place<uint16_t>(off, total);
+  size_t const o_region = place<uint16_t>(off, total);
+  size_t const o_mapq = place<uint8_t>(off, total);
+  size_t const o_same = place<uint8_t>(off, total);
+  size_t const o_sd = place<uint8_t>(off, total);
+  size_t const o_clip = place<uint8_t>(off, total);
+  size_t const o_isize = place<int32_t>(off, total);
+  size_t const o_sample = place<int32_t>(off, total);
+  size_t const o_mate = place<int32_t>(off, total);
+  size_t const o_unit = place<int32_t>(off, total);
+  size_t const o_urec = place<int32_t>(off, total);
+  size_t const bytes = align_up(off, 256);
+  if (int rc = c->h_batch.reserve(bytes))
+    return rc;
+  uint8_t * h = static_cast<uint8_t *>(c->h_batch.p);
+  int32_t * h_unit = reinterpret_cast<int32_t *>(h + o_unit);
+  int32_t * h_urec = reinterpret_cast<int32_t *>(h + o_urec);
+  int32_t * h_mate = reinterpret_cast<int32_t *>(h + o_mate);
+  uint16_t * h_region = reinterpret_cast<uint16_t *>(h + o_region);
+  size_t base = 0;
+  uint32_t n_units = 0;
+  c->last_regions.assign(region_ids, region_ids + n);
+  c->last_unit_begin.assign(1, 0);
+  c->last_rec_begin.assign(1, 0);
+  for (int i = 0; i < n; ++i)
+  {
+    gtb_read_batch const & b = batches[i];
+    size_t const m = b.n_reads;
+    if (m)
+    {
+      memcpy(h + o_seq4 + base * GTB_SEQ_STRIDE, b.seq4, m * GTB_SEQ_STRIDE);
+      memcpy(h + o_lseq + base * 2, b.lseq, m * 2);
+      memcpy(h + o_flag + base * 2, b.flag, m * 2);
+      memcpy(h + o_mapq + base, b.mapq, m);
+      memcpy(h + o_same + base, b.same_tid, m);
+      memcpy(h + o_sd + base, b.score_diff, m);
+      if (b.clipped)
+        memcpy(h + o_clip + base, b.clipped, m);
+      else
+        memset(h + o_clip + base, 0, m);
+      memcpy(h + o_isize + base * 4, b.isize, m * 4);
+      memcpy(h + o_sample + base * 4, b.sample, m * 4);
+    }
+    for (size_t k = 0; k < m; ++k)
+    {
+      h_region[base + k] = (uint16_t)regs[i]->slot;
+      if (b.sample[k] < 0 || b.sample[k] >= regs[i]->n_samples)
+        return fail(GTB_ERR_ARG, "sample index out of range");
+      int32_t const d = b.dup_of ? b.dup_of[k] : -1;
+      if (d < 0)
+      {
+        h_unit[base + k] = (int32_t)n_units;
+        h_urec[n_units] = (int32_t)(base + k);
+        ++n_units;
+      }
+      else
+      {
+        if ((size_t)d >= k)
+          return fail(GTB_ERR_ARG, "dup_of must reference an earlier record of the same batch");
+        h_unit[base + k] = h_unit[base + d];
+      }
+      int32_t const mt = b.mate ? b.mate[k] : -1;
+      if (mt >= 0 && (size_t)mt >= k)
+        return fail(GTB_ERR_ARG, "mate must reference an earlier record of the same batch");
+      h_mate[base + k] = mt < 0 ? -1 : (int32_t)(base + mt);
+    }
+    base += m;
+    c->last_unit_begin.push_back(n_units);
+    c->last_rec_begin.push_back((uint32_t)base);
+  }
+
+  uint32_t const n_tasks = n_units * 2;
+  if (int rc = c->d_batch.reserve(bytes))
+    return rc;
+  if (int rc = c->d_summaries.reserve((size_t)n_tasks * sizeof(TaskSummary) + 16))
+    return rc;
+  size_t const pool_words = (size_t)n_tasks * INLINE_WORDS + (size_t)n_units * 64 + 65536;
+  if (int rc = c->d_pool.reserve(pool_words * 4))
+    return rc;
+  if (int rc = c->d_counters.reserve(sizeof(DevCounters)))
+    return rc;
+  if (int rc = c->h_counters.reserve(sizeof(DevCounters)))
+    return rc;
+
+  CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->d_batch.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
+
+  LaunchParams & P = c->last;
+  memset(&P, 0, sizeof(P));
+  uint8_t * d = static_cast<uint8_t *>(c->d_batch.p);
+  P.regions = static_cast<const DevRegion *>(c->d_regions.p);
+  P.batch.n_records = (uint32_t)total;
+  P.batch.n_units = n_units;
+  P.batch.seq4 = d + o_seq4;
+  P.batch.lseq = reinterpret_cast<const uint16_t *>(d + o_lseq);
+  P.batch.flag = reinterpret_cast<const uint16_t *>(d + o_flag);
+  P.batch.region = reinterpret_cast<const uint16_t *>(d + o_region);
+  P.batch.mapq = d + o_mapq;
+  P.batch.same_tid = d + o_same;
+  P.batch.score_diff = d + o_sd;
+  P.batch.clipped = d + o_clip;
+  P.batch.isize = reinterpret_cast<const int32_t *>(d + o_isize);
+  P.batch.sample = reinterpret_cast<const int32_t *>(d + o_sample);
+  P.batch.mate = reinterpret_cast<const int32_t *>(d + o_mate);
+  P.batch.unit = reinterpret_cast<const int32_t *>(d + o_unit);
+  P.batch.unit_record = reinterpret_cast<const int32_t *>(d + o_urec);
+  P.summaries = static_cast<TaskSummary *>(c->d_summaries.p);
+  P.path_pool = static_cast<uint32_t *>(c->d_pool.p);
+  P.path_pool_cap = pool_words;
+  P.counters = static_cast<DevCounters *>(c->d_counters.p);
+  if (c->debug)
+  {
+    size_t const tap_counts = (size_t)n_tasks * (NLISTS * 2 + 1) * 4;
+    size_t const tap_labels = (size_t)n_tasks * 512 + 65536;
+    if (int rc = c->d_tap_counts.reserve(tap_counts + 64))
+      return rc;
+    if (int rc = c->d_tap_pool.reserve(tap_labels * sizeof(DevLabel)))
+      return rc;
+    uint32_t * tc = static_cast<uint32_t *>(c->d_tap_counts.p);
+    P.tap.list_count = tc;
+    P.tap.list_off = tc + (size_t)n_tasks * NLISTS;
+    P.tap.nslots = tc + (size_t)n_tasks * NLISTS * 2;
+    P.tap.pool = static_cast<DevLabel *>(c->d_tap_pool.p);
+    P.tap.pool_cap = tap_labels;
+  }
+  c->last_n_tasks = n_tasks;
+  c->have_last = true;
+  return run_kernels(c, stats, true);
+}
+
+int gtb_submit_reads(gtb_ctx * ctx, int region_id, const gtb_read_batch * batch, gtb_submit_stats * stats)
+{
+  return gtb_submit_reads_multi(ctx, 1, &region_id, batch, stats);
+}
+
+// Re-runs the kernels on the batch that is already resident in HBM (bench: device-resident throughput).
+int gtb_replay_last(gtb_ctx * ctx, gtb_submit_stats * stats)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !c->have_last)
+    return fail(GTB_ERR_STATE, "no resident batch to replay");
+  cudaSetDevice(c->device);
+  return run_kernels(c, stats, false);
+}
+
+// Device times (ms) of the last submit/replay measured with CUDA events on the library's stream.
+int gtb_last_timing(gtb_ctx * ctx, float * h2d_ms, float * align_ms, float * score_ms, float * d2h_ms)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (h2d_ms)
+    *h2d_ms = c->t_h2d;
+  if (align_ms)
+    *align_ms = c->t_align;
+  if (score_ms)
+    *score_ms = c->t_score;
+  if (d2h_ms)
+    *d2h_ms = c->t_d2h;
+  return 0;
+}
+
+// Zeroes a region's accumulators (bench: repeated passes over the same batch).
+int gtb_pool_reset(gtb_ctx * ctx, int region_id)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  auto it = c->regions.find(region_id);
+  if (it == c->regions.end() || !it->second->pool_open)
+    return fail(GTB_ERR_STATE, "unknown region / pool not open");
+  cudaSetDevice(c->device);
+  CUDA_TRY(cudaMemsetAsync(it->second->accum.p, 0, it->second->accum_bytes, c->stream));
+  return 0;
+}
+
+int gtb_accumulator_sizes(gtb_ctx * ctx, int region_id, uint32_t * n_bubbles, uint64_t * n_scores, uint64_t * n_cov)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  auto it = c->regions.find(region_id);
+  if (it == c->regions.end())
+    return fail(GTB_ERR_STATE, "unknown region");
+  *n_bubbles = it->second->n_bubbles;
+  *n_scores = it->second->score_off.back();
+  *n_cov = it->second->cov_off.back();
+  return 0;
+}
+
+int gtb_pool_finish(gtb_ctx * ctx, int region_id, gtb_accumulators * out)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  auto it = c->regions.find(region_id);
+  if (it == c->regions.end() || !it->second->pool_open)
+    return fail(GTB_ERR_STATE, "unknown region / pool not open");
+  Region & R = *it->second;
+  cudaSetDevice(c->device);
+  if (int rc = c->h_batch.reserve(R.accum_bytes))
+    return rc;
+  uint8_t * h = static_cast<uint8_t *>(c->h_batch.p);
+  CUDA_TRY(cudaMemcpyAsync(h, R.accum.p, R.accum_bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  uint8_t const * d0 = static_cast<uint8_t *>(R.accum.p);
+  auto host_of = [&](const void * devp) { return h + (static_cast<const uint8_t *>(devp) - d0); };
+  uint32_t const NB = R.n_bubbles, NS = (uint32_t)R.n_samples;
+  uint64_t const n_scores = R.score_off.back(), n_cov = R.cov_off.back();
+  out->n_bubbles = NB;
+  out->n_samples = NS;
+  for (uint32_t b = 0; b < NB; ++b)
+  {
+    out->bubble_id[b] = R.bubble_order[b];
+    out->n_alleles[b] = R.n_alleles[b];
+  }
+  for (uint32_t b = 0; b <= NB; ++b)
+  {
+    out->score_off[b] = R.score_off[b];
+    out->cov_off[b] = R.cov_off[b];
+  }
+  const uint32_t * ls = reinterpret_cast<const uint32_t *>(host_of(R.dev.log_score));
+  const uint32_t * gc = reinterpret_cast<const uint32_t *>(host_of(R.dev.gt_cov));
+  const uint32_t * ml = reinterpret_cast<const uint32_t *>(host_of(R.dev.max_log_score));
+  const uint32_t * amb = reinterpret_cast<const uint32_t *>(host_of(R.dev.amb));
+  const uint32_t * amba = reinterpret_cast<const uint32_t *>(host_of(R.dev.amb_alt));
+  const uint32_t * altpp = reinterpret_cast<const uint32_t *>(host_of(R.dev.alt_pp));
+  for (uint64_t i = 0; i < n_scores * NS; ++i)
+    out->log_score[i] = (uint16_t)std::min<uint32_t>(ls[i], 0xFFFFu);
+  for (uint64_t i = 0; i < n_cov * NS; ++i)
+    out->gt_coverage[i] = (uint16_t)std::min<uint32_t>(gc[i], 0xFFFFu); // HapSample::increment_allele_depth saturates
+  for (uint64_t i = 0; i < (uint64_t)NB * NS; ++i)
+  {
+    // explain_to_score stops adding reads once max_log_score >= 0xFFFF - eps (haplotype.cpp:561): with eps <= 8
+    // nothing was dropped while the total stays below 0xFFFF - 8; beyond that the result is order dependent.
+    out->saturated[i] = ml[i] >= (0xFFFFu - 8u) ? 1u : 0u;
+    out->max_log_score[i] = (uint16_t)std::min<uint32_t>(ml[i], 0xFFFFu);
+    out->ambiguous_depth[i] = (uint8_t)std::min<uint32_t>(amb[i], 0xFFu);
+    out->ambiguous_depth_alt[i] = (uint8_t)std::min<uint32_t>(amba[i], 0xFFu);
+    out->alt_proper_pair_depth[i] = (uint8_t)std::min<uint32_t>(altpp[i], 0xFFu);
+  }
+  memcpy(out->vs_clipped_reads, host_of(R.dev.vs_clipped_reads), (size_t)NB * 8);
+  memcpy(out->vs_mapq_squared, host_of(R.dev.vs_mapq_squared), (size_t)NB * 8);
+  memcpy(out->pa_clipped_bp, host_of(R.dev.pa_clipped_bp), n_cov * 8);
+  memcpy(out->pa_mapq_squared, host_of(R.dev.pa_mapq_squared), n_cov * 8);
+  memcpy(out->pa_score_diff, host_of(R.dev.pa_score_diff), n_cov * 8);
+  memcpy(out->pa_mismatches, host_of(R.dev.pa_mismatches), n_cov * 8);
+  memcpy(out->read_strand, host_of(R.dev.read_strand), n_cov * 16);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ debug taps
+int gtb_debug_enable(gtb_ctx * ctx, int on)
+{
+  reinterpret_cast<Ctx *>(ctx)->debug = on != 0;
+  return 0;
+}
+
+static int find_last_region(Ctx * c, int region_id)
+{
+  for (size_t i = 0; i < c->last_regions.size(); ++i)
+    if (c->last_regions[i] == region_id)
+      return (int)i;
+  return -1;
+}
+
+int gtb_debug_seed_sizes(gtb_ctx * ctx, int region_id, uint64_t * n_units, uint64_t * n_slots, uint64_t * n_labels)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  int const k = c->have_last ? find_last_region(c, region_id) : -1;
+  if (k < 0 || !c->last.tap.list_count)
+    return fail(GTB_ERR_STATE, "no debug tap for this region (gtb_debug_enable before submit)");
+  cudaSetDevice(c->device);
+  uint32_t const u0 = c->last_unit_begin[k], u1 = c->last_unit_begin[k + 1];
+  size_t const nt = (size_t)(u1 - u0) * 2;
+  std::vector<uint32_t> counts(nt * NLISTS), nsl(nt);
+  CUDA_TRY(cudaMemcpy(counts.data(), c->last.tap.list_count + (size_t)u0 * 2 * NLISTS, counts.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(nsl.data(), c->last.tap.nslots + (size_t)u0 * 2, nsl.size() * 4, cudaMemcpyDeviceToHost));
+  uint64_t ns = 0, nl = 0;
+  for (size_t t = 0; t < nt; ++t)
+  {
+    ns += (uint64_t)nsl[t] * 2;
+    for (uint32_t l = 0; l < nsl[t] * 2; ++l)
+      nl += counts[t * NLISTS + l];
+  }
+  *n_units = u1 - u0;
+  *n_slots = ns;
+  *n_labels = nl;
+  return 0;
+}
+
+int gtb_debug_seeds(gtb_ctx * ctx, int region_id, uint32_t * unit_record, uint32_t * nslots, uint32_t * nlabels,
+                    gtb_label * labels)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  int const k = c->have_last ? find_last_region(c, region_id) : -1;
+  if (k < 0 || !c->last.tap.list_count)
+    return fail(GTB_ERR_STATE, "no debug tap for this region");
+  cudaSetDevice(c->device);
+  uint32_t const u0 = c->last_unit_begin[k], u1 = c->last_unit_begin[k + 1];
+  size_t const nu = u1 - u0, nt = nu * 2;
+  std::vector<uint32_t> counts(nt * NLISTS), offs(nt * NLISTS), nsl(nt);
+  std::vector<int32_t> urec(nu);
+  CUDA_TRY(cudaMemcpy(counts.data(), c->last.tap.list_count + (size_t)u0 * 2 * NLISTS, counts.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(offs.data(), c->last.tap.list_off + (size_t)u0 * 2 * NLISTS, offs.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(nsl.data(), c->last.tap.nslots + (size_t)u0 * 2, nsl.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(urec.data(), c->last.batch.unit_record + u0, nu * 4, cudaMemcpyDeviceToHost));
+  DevCounters k_host;
+  CUDA_TRY(cudaMemcpy(&k_host, c->d_counters.p, sizeof(k_host), cudaMemcpyDeviceToHost));
+  std::vector<DevLabel> pool(k_host.dbg_label_words);
+  if (!pool.empty())
+    CUDA_TRY(cudaMemcpy(pool.data(), c->last.tap.pool, pool.size() * sizeof(DevLabel), cudaMemcpyDeviceToHost));
+  size_t si = 0, li = 0;
+  for (size_t u = 0; u < nu; ++u)
+  {
+    unit_record[u] = (uint32_t)(urec[u] - (int32_t)c->last_rec_begin[k]);
+    for (int o = 0; o < 2; ++o)
+    {
+      size_t const t = u * 2 + o;
+      for (int hm = 0; hm < 2; ++hm)
+      {
+        nslots[(u * 2 + o) * 2 + hm] = nsl[t];
+        for (uint32_t s = 0; s < nsl[t]; ++s)
+        {
+          uint32_t const l = s * 2 + hm;
+          uint32_t const cnt = counts[t * NLISTS + l];
+          nlabels[si++] = cnt;
+          for (uint32_t q = 0; q < cnt; ++q)
+          {
+            DevLabel const & d = pool[offs[t * NLISTS + l] + q];
+            labels[li].start = d.start;
+            labels[li].end = d.end;
+            labels[li].var_id = d.var;
+            ++li;
+          }
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+static int fetch_paths(Ctx * c, int k, std::vector<TaskSummary> & sums, std::vector<uint32_t> & pool)
+{
+  uint32_t const u0 = c->last_unit_begin[k], u1 = c->last_unit_begin[k + 1];
+  sums.resize((size_t)(u1 - u0) * 2);
+  if (!sums.empty())
+    CUDA_TRY(cudaMemcpy(sums.data(), c->last.summaries + (size_t)u0 * 2, sums.size() * sizeof(TaskSummary), cudaMemcpyDeviceToHost));
+  DevCounters k_host;
+  CUDA_TRY(cudaMemcpy(&k_host, c->d_counters.p, sizeof(k_host), cudaMemcpyDeviceToHost));
+  size_t const words = (size_t)c->last_n_tasks * INLINE_WORDS + k_host.path_words;
+  pool.resize(std::min<size_t>(words, c->last.path_pool_cap));
+  if (!pool.empty())
+    CUDA_TRY(cudaMemcpy(pool.data(), c->last.path_pool, pool.size() * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gtb_debug_path_sizes(gtb_ctx * ctx, int region_id, uint64_t * n_units, uint64_t * n_paths, uint64_t * n_vars,
+                         uint64_t * n_nums)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  int const k = c->have_last ? find_last_region(c, region_id) : -1;
+  if (k < 0)
+    return fail(GTB_ERR_STATE, "region was not part of the last submit");
+  cudaSetDevice(c->device);
+  std::vector<TaskSummary> sums;
+  std::vector<uint32_t> pool;
+  if (int rc = fetch_paths(c, k, sums, pool))
+    return rc;
+  uint64_t np = 0, nv = 0, nn = 0;
+  for (auto const & s : sums)
+  {
+    const uint32_t * w = pool.data() + s.path_off;
+    for (uint32_t p = 0; p < s.npaths; ++p)
+    {
+      uint32_t const nvar = w[3] >> 16;
+      ++np;
+      nv += nvar;
+      for (uint32_t q = 0; q < nvar; ++q)
+        nn += (uint64_t)__builtin_popcount(w[4 + 2 * q + 1]);
+      w += 4 + 2 * nvar;
+    }
+  }
+  *n_units = sums.size() / 2;
+  *n_paths = np;
+  *n_vars = nv;
+  *n_nums = nn;
+  return 0;
+}
+
+int gtb_debug_paths(gtb_ctx * ctx, int region_id, uint32_t * gp_npaths, uint32_t * gp_longest, uint32_t * p_fields,
+                    uint32_t * v_order, uint32_t * v_nnum, uint16_t * v_nums)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  int const k = c->have_last ? find_last_region(c, region_id) : -1;
+  if (k < 0)
+    return fail(GTB_ERR_STATE, "region was not part of the last submit");
+  cudaSetDevice(c->device);
+  std::vector<TaskSummary> sums;
+  std::vector<uint32_t> pool;
+  if (int rc = fetch_paths(c, k, sums, pool))
+    return rc;
+  size_t pi = 0, vi = 0, ni = 0;
+  for (size_t t = 0; t < sums.size(); ++t)
+  {
+    TaskSummary const & s = sums[t];
+    gp_npaths[t] = s.npaths;
+    gp_longest[t] = s.longest;
+    const uint32_t * w = pool.data() + s.path_off;
+    for (uint32_t p = 0; p < s.npaths; ++p)
+    {
+      uint32_t const nvar = w[3] >> 16;
+      uint32_t * f = p_fields + pi * 6;
+      f[0] = w[0];
+      f[1] = w[1];
+      f[2] = w[2] & 0xFFFFu;
+      f[3] = w[2] >> 16;
+      f[4] = w[3] & 0xFFFFu;
+      f[5] = nvar;
+      ++pi;
+      for (uint32_t q = 0; q < nvar; ++q)
+      {
+        v_order[vi] = w[4 + 2 * q];
+        uint32_t const mask = w[4 + 2 * q + 1];
+        v_nnum[vi] = (uint32_t)__builtin_popcount(mask);
+        ++vi;
+        for (int a = 0; a < 32; ++a)
+          if ((mask >> a) & 1u)
+            v_nums[ni++] = (uint16_t)a;
+      }
+      w += 4 + 2 * nvar;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ host finalisation
+// get_haplotype_phred (src/typer/vcf.cpp:47-81) + SampleCall::get_gt_call / get_gq (src/typer/sample_call.cpp:78-131)
+int gtb_calls_from_accumulators(const gtb_accumulators * acc, uint8_t * phred, uint16_t * gt, uint8_t * gq)
+{
+  if (!acc || !phred || !gt || !gq)
+    return fail(GTB_ERR_ARG, "null argument");
+  uint32_t const NB = acc->n_bubbles, NS = acc->n_samples;
+  for (uint32_t b = 0; b < NB; ++b)
+  {
+    uint64_t const tri = acc->score_off[b + 1] - acc->score_off[b];
+    uint32_t const cnum = acc->n_alleles[b];
+    for (uint32_t s = 0; s < NS; ++s)
+    {
+      const uint16_t * ls = acc->log_score + acc->score_off[b] * NS + (uint64_t)s * tri;
+      uint8_t * ph = phred + acc->score_off[b] * NS + (uint64_t)s * tri;
+      uint16_t mx = 0;
+      bool all_same = true;
+      for (uint64_t i = 0; i < tri; ++i)
+        mx = std::max(mx, ls[i]);
+      for (uint64_t i = 0; i < tri; ++i)
+        all_same = all_same && ls[i] == mx;
+      int zeros = 0;
+      uint8_t second = 255;
+      bool have_gt = false;
+      uint64_t i = 0;
+      for (uint32_t y = 0; y < cnum; ++y)
+        for (uint32_t x = 0; x <= y; ++x, ++i)
+        {
+          uint8_t p = 0;
+          if (!all_same)
+          {
+            long long const sc = std::llround((double)(mx - ls[i]) * 3.01029995663981195213738894724493026768189881462108541);
+            p = sc < 255 ? (uint8_t)sc : (uint8_t)255;
+          }
+          ph[i] = p;
+          if (p == 0)
+          {
+            ++zeros;
+            if (!have_gt)
+            {
+              gt[((uint64_t)b * NS + s) * 2 + 0] = (uint16_t)x;
+              gt[((uint64_t)b * NS + s) * 2 + 1] = (uint16_t)y;
+              have_gt = true;
+            }
+          }
+          else if (p < second)
+            second = p;
+        }
+      gq[(uint64_t)b * NS + s] = zeros >= 2 ? 0 : second;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU reduce
+// NCCL is bound lazily (dlopen) so the library loads on hosts without it and never clashes with the NCCL copy
+// PyTorch bundles.  The communicator is created here from a unique id the caller distributes (e.g. with
+// torch.distributed.broadcast): gtb_nccl_unique_id on rank 0 -> gtb_nccl_init on every rank.
+typedef struct
+{
+  char internal[128];
+} gtb_nccl_id;
+
+namespace
+{
+struct NcclApi
+{
+  int (*GetUniqueId)(gtb_nccl_id *) = nullptr;
+  int (*CommInitRank)(void **, int, gtb_nccl_id, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  const char * (*GetErrorString)(int) = nullptr;
+  void * lib = nullptr;
+} g_nccl;
+
+int load_nccl()
+{
+  if (g_nccl.lib)
+    return 0;
+  const char * names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char * n : names)
+  {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    if (g_nccl.lib)
+      break;
+  }
+  if (!g_nccl.lib)
+    return fail(GTB_ERR_NCCL, std::string("cannot dlopen libnccl: ") + dlerror());
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(g_nccl.lib, "ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(g_nccl.lib, "ncclCommInitRank"));
+  g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(g_nccl.lib, "ncclAllReduce"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(g_nccl.lib, "ncclCommDestroy"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(g_nccl.lib, "ncclGetErrorString"));
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    return fail(GTB_ERR_NCCL, "libnccl lacks required symbols");
+  return 0;
+}
+} // namespace
+
+int gtb_nccl_unique_id(uint8_t * id128)
+{
+  if (int rc = load_nccl())
+    return rc;
+  gtb_nccl_id id;
+  int const r = g_nccl.GetUniqueId(&id);
+  if (r != 0)
+    return fail(GTB_ERR_NCCL, std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  memcpy(id128, id.internal, 128);
+  return 0;
+}
+
+int gtb_nccl_init(gtb_ctx * ctx, int n_ranks, int rank, const uint8_t * id128)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (c->device < 0)
+    return fail(GTB_ERR_CUDA, "host-only context");
+  if (int rc = load_nccl())
+    return rc;
+  cudaSetDevice(c->device);
+  gtb_nccl_id id;
+  memcpy(id.internal, id128, 128);
+  int const r = g_nccl.CommInitRank(&c->nccl_comm, n_ranks, id, rank);
+  if (r != 0)
+    return fail(GTB_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  c->nccl_rank = rank;
+  c->nccl_size = n_ranks;
+  return 0;
+}
+
+// Sum-reduce of the widened accumulators of one region over all ranks (additive: SURVEY.md section 8e).
+// The accumulator arena is laid out as uint32 [..] then uint64 [..] then uint32 read_strand; it is reduced as
+// three typed spans.  nccl_comm == NULL uses the communicator of gtb_nccl_init.
+int gtb_allreduce_accumulators(gtb_ctx * ctx, int region_id, void * nccl_comm)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  auto it = c->regions.find(region_id);
+  if (it == c->regions.end() || !it->second->pool_open)
+    return fail(GTB_ERR_STATE, "unknown region / pool not open");
+  void * comm = nccl_comm ? nccl_comm : c->nccl_comm;
+  if (!comm)
+    return fail(GTB_ERR_STATE, "no NCCL communicator (gtb_nccl_init)");
+  if (int rc = load_nccl())
+    return rc;
+  Region & R = *it->second;
+  cudaSetDevice(c->device);
+  uint8_t * base = static_cast<uint8_t *>(R.accum.p);
+  uint8_t * u64_begin = reinterpret_cast<uint8_t *>(R.dev.vs_clipped_reads);
+  uint8_t * rs_begin = reinterpret_cast<uint8_t *>(R.dev.read_strand);
+  uint8_t * end = base + R.accum_bytes;
+  // ncclUint32 = 3, ncclUint64 = 5, ncclSum = 0
+  int r = g_nccl.AllReduce(base, base, (size_t)(u64_begin - base) / 4, 3, 0, comm, c->stream);
+  if (r == 0)
+    r = g_nccl.AllReduce(u64_begin, u64_begin, (size_t)(rs_begin - u64_begin) / 8, 5, 0, comm, c->stream);
+  if (r == 0)
+    r = g_nccl.AllReduce(rs_begin, rs_begin, (size_t)(end - rs_begin) / 4, 3, 0, comm, c->stream);
+  if (r != 0)
+    return fail(GTB_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,147 @@
+// gtb_device.cuh -- device-side data layout shared by the kernels and the host orchestration (product code).
+#pragma once
+
+#include <cstdint>
+
+#include "../../include/gtb200.h"
+#include "gtb_index_host.hpp"
+
+namespace gtb
+{
+// ---- capacities of the per-warp shared-memory working set (exceeding one flags the task, never silently wrong)
+constexpr int MAXP = 24;      // paths per read orientation held during chaining/extension
+constexpr int MAXV = 12;      // bubbles per path
+constexpr int REF_CAP = 160;  // staged index bucket references per read orientation
+constexpr int MAX_SLOTS = 4;  // seed slots: 1 + (151-32)/31
+constexpr int NLISTS = MAX_SLOTS * 2;
+constexpr int CAND_CAP = 32;  // partial sequences during bubble expansion (reference limit: 128)
+constexpr int CAND_V = 16;    // var nodes per candidate
+constexpr int MAXLOC = 8;     // graph locations of a position (reference limit: 256)
+constexpr int WL_CAP = 96;    // labels staged by one walk_read_starts/ends call
+constexpr int MAX_SEQ = 152;  // bases per read (GTB_SEQ_STRIDE * 2)
+constexpr int MAX_TOUCH = 16; // bubbles touched by one read in the accumulate kernel
+using allele_mask_t = uint32_t; // allele set of one bubble on a path: bit a = allele a  (<= 32 alleles per bubble)
+constexpr int MAX_ALLELES = 32;
+
+struct DevLabel
+{
+  uint32_t start, end, var;
+};
+
+// One region resident on the device: flat graph + k-mer table + widened accumulators.  All pointers point into
+// one arena allocation (a single H2D copy per region).
+struct DevRegion
+{
+  // graph (include/gtb200.h: gtb_graph_view)
+  uint32_t n_ref, n_var, n_special, n_sp_keys;
+  uint32_t is_sv, n_bubbles, n_samples, table_mask;
+  int table_shift, pad0;
+  const uint32_t * ref_order;
+  const uint32_t * ref_seq_off; // [n_ref+1]
+  const uint32_t * ref_var_off; // [n_ref+1]
+  const uint32_t * var_order;
+  const uint32_t * var_seq_off; // [n_var+1]
+  const uint32_t * var_out_ref;
+  const uint8_t * seq;
+  const uint32_t * actual_poses;
+  const uint32_t * ref_reach_poses;
+  const uint32_t * sp_keys;
+  const uint32_t * sp_off;
+  const uint32_t * sp_list;
+  const uint32_t * bubble_order; // [n_bubbles] order of bubble b's var nodes (Genotype::id)
+  const uint32_t * score_off;    // [n_bubbles+1]
+  const uint32_t * cov_off;      // [n_bubbles+1]
+  // index
+  const IndexSlot * table;
+  const DevLabel * labels;
+  // accumulators (widened; clamped on download)
+  uint32_t * log_score;     // [score_off[NB] * NS]
+  uint32_t * gt_cov;        // [cov_off[NB] * NS]
+  uint32_t * max_log_score; // [NB * NS]
+  uint32_t * amb;           // [NB * NS]
+  uint32_t * amb_alt;
+  uint32_t * alt_pp;
+  unsigned long long * vs_clipped_reads; // [NB]
+  unsigned long long * vs_mapq_squared;
+  unsigned long long * pa_clipped_bp;    // [cov_off[NB]]
+  unsigned long long * pa_mapq_squared;
+  unsigned long long * pa_score_diff;
+  unsigned long long * pa_mismatches;
+  uint32_t * read_strand;                // [cov_off[NB] * 4]
+};
+
+// Records of one submit (possibly several regions concatenated), SoA on the device.
+struct DevBatch
+{
+  uint32_t n_records, n_units;
+  const uint8_t * seq4;     // [n * GTB_SEQ_STRIDE]
+  const uint16_t * lseq;
+  const uint16_t * flag;
+  const uint8_t * mapq;
+  const int32_t * isize;
+  const uint8_t * same_tid;
+  const uint8_t * score_diff;
+  const uint8_t * clipped;
+  const int32_t * sample;
+  const int32_t * mate;        // batch-global index or -1
+  const int32_t * unit;        // alignment unit of each record
+  const uint16_t * region;     // region slot of each record
+  const int32_t * unit_record; // [n_units] record that defines the unit
+};
+
+// Result of aligning one read orientation (GenotypePaths summary) -- 16 bytes.
+struct TaskSummary
+{
+  uint16_t npaths;
+  uint16_t longest;
+  uint16_t mm0;       // paths[0].mismatches
+  uint16_t altcalls;  // alternative_call_count (genotype_paths.cpp:1043-1057)
+  uint16_t bits;      // TS_* flags
+  uint16_t pad;
+  uint32_t path_off;  // word offset into the path pool
+};
+constexpr uint16_t TS_ALL_UNIQUE = 1, TS_OVERFLOW = 2, TS_COMPUTED = 4;
+
+// Path pool record (uint32 words): start, end, rs | re << 16, mm | nvar << 16, then nvar x (order, mask)
+constexpr int PATH_HDR_WORDS = 4;
+constexpr int INLINE_WORDS = 24; // inline path-record words per task before spilling to the overflow pool
+
+struct DevCounters
+{
+  unsigned long long path_words;     // bump cursor of the path pool
+  unsigned long long n_oriented;
+  unsigned long long n_pairs_scored;
+  unsigned long long n_singles_scored;
+  unsigned long long n_overflow;
+  unsigned long long n_input_error;  // mates with equal IS_FIRST_IN_PAIR
+  unsigned long long dbg_label_words; // bump cursor of the debug seed pool
+  unsigned long long pad;
+};
+
+// Debug tap of the seed stage: per task, per list (slot*2 + ham): count and offset into a label pool
+struct DevSeedTap
+{
+  uint32_t * list_count; // [n_tasks * NLISTS]
+  uint32_t * list_off;   // [n_tasks * NLISTS]
+  uint32_t * nslots;     // [n_tasks]
+  DevLabel * pool;
+  unsigned long long pool_cap;
+};
+
+struct LaunchParams
+{
+  const DevRegion * regions;
+  DevBatch batch;
+  TaskSummary * summaries; // [n_units * 2]
+  uint32_t * path_pool;
+  unsigned long long path_pool_cap; // words
+  DevCounters * counters;
+  DevSeedTap tap; // tap.list_count == nullptr when disabled
+};
+
+// host launchers (gtb_kernels.cu)
+void launch_align(const LaunchParams & p, void * stream);
+void launch_score(const LaunchParams & p, void * stream);
+int align_kernel_blocks_per_sm();
+
+} // namespace gtb

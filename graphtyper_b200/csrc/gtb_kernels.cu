@@ -1,0 +1,1863 @@
+// gtb_kernels.cu -- sm_100a kernels of the read -> graph genotyping path (product code).
+//
+//   align_kernel : one warp per (alignment unit, read orientation).
+//       A. unpack the 4-bit read, build the 32-mer seed keys (warp reduce), probe the region's open-addressed
+//          k-mer table for the exact key and its 96 Hamming-1 neighbours, lanes probing different keys
+//          (replaces to_uint64_vec / query_index / PHIndex::multi_get, src/utilities/type_conversions.cpp:207-288,
+//          src/utilities/kmer_help_functions.cpp:51-119, src/index/ph_index.cpp:66-107);
+//       B. chain the seed labels into paths (GenotypePaths::add_next_kmer_labels, src/typer/genotype_paths.cpp:294-352,
+//          Path merge src/typer/path.cpp:38-82);
+//       C. extend both read ends through the bubble graph under the shrinking mismatch budget
+//          (walk_read_starts/ends genotype_paths.cpp:483-621, Graph::get_locations_of_a_position graph.cpp:931-1185,
+//          get_labels_forward/backward graph.cpp:1187-1701, count_mismatches graph_utils.hpp:7-69);
+//       D. apply the path filters (alignment.cpp:68-87) and write a compact GenotypePaths record.
+//   score_kernel : one thread per record: mate/orientation selection (get_better_paths alignment.cpp:557-622,
+//       compare_pair_of_genotype_paths genotype_paths.cpp:943-1169), read acceptance (vcf_writer.cpp:28-60) and the
+//       integer likelihood / depth / stat accumulation (vcf_writer.cpp:503-676, haplotype.cpp:180-585) as atomics
+//       into widened per-bubble per-sample accumulators.
+//
+// The working set of a read lives in shared memory (one WS per warp); phases B-D are data-dependent scalar
+// logic executed by lane 0 while phase A (the memory-bound part: ~388 table probes per read) uses all lanes.
+// Order-sensitive semantics of the reference (bucket order, path order, candidate order) are preserved.
+
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "gtb_device.cuh"
+
+namespace gtb
+{
+namespace
+{
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr uint32_t BIGMM = 0x4000u; // "rejected" mismatch count ('<' / '>' in the graph sequence)
+constexpr uint32_t INVALID = 0xFFFFFFFFu;
+constexpr uint32_t SPECIAL_START = 0xD0000000u;
+constexpr uint16_t F_PAIRED = 1, F_PROPER = 2, F_REV = 16, F_MREV = 32, F_FIRST = 64, F_MAPQ_BAD = 4096;
+
+struct Path
+{
+  uint32_t start, end;
+  uint16_t rs, re, mm, nvar;
+  uint32_t order[MAXV];
+  allele_mask_t mask[MAXV];
+};
+
+struct Cand
+{
+  uint32_t len;
+  uint32_t pos;
+  uint32_t mm;
+  uint32_t nvar;
+  uint32_t vars[CAND_V];
+};
+
+struct Loc
+{
+  uint32_t type; // 'R' or 'V'
+  uint32_t node, order, offset;
+};
+
+struct WS
+{
+  Path paths[MAXP];
+  Path pp[MAXP];
+  Path op, np;
+  Cand cands[CAND_CAP];
+  DevLabel wl[WL_CAP];
+  uint2 refs[REF_CAP];
+  Loc locs[MAXLOC];
+  uint16_t list_start[NLISTS + 1];
+  uint16_t wl_list_start[MAXP + 1];
+  uint16_t wl_list_idx[MAXP];
+  uint8_t matched[MAXP];
+  uint8_t seq[MAX_SEQ + 8]; // 4-bit codes in phase A, IUPAC characters afterwards
+  int npaths, npp;
+  uint32_t longest;
+  uint32_t overflow;
+};
+
+__device__ __forceinline__ uint8_t comp4(uint8_t c) // seqan TranslateTableIupacToIupacComplement_: 4-bit reversal
+{
+  return (uint8_t)(((c & 1) << 3) | ((c & 2) << 1) | ((c & 4) >> 1) | ((c & 8) >> 3));
+}
+
+__device__ __constant__ char IUPAC_CHAR[17] = "UACMGRSVTWYHKDBN";
+
+// ------------------------------------------------------------------------------------------------ graph accessors
+struct GR
+{
+  const DevRegion & R;
+  __device__ GR(const DevRegion & r) : R(r) {}
+  __device__ uint32_t ref_len(uint32_t r) const { return R.ref_seq_off[r + 1] - R.ref_seq_off[r]; }
+  __device__ uint32_t var_len(uint32_t v) const { return R.var_seq_off[v + 1] - R.var_seq_off[v]; }
+  __device__ const uint8_t * ref_dna(uint32_t r) const { return R.seq + R.ref_seq_off[r]; }
+  __device__ const uint8_t * var_dna(uint32_t v) const { return R.seq + R.var_seq_off[v]; }
+  __device__ uint32_t ref_reach(uint32_t r) const { return R.ref_order[r] + ref_len(r) - 1; }
+  __device__ uint32_t var_reach(uint32_t v) const { return R.var_order[v] + var_len(v) - 1; }
+  __device__ uint32_t variant_num(uint32_t v) const { return v - R.ref_var_off[R.var_out_ref[v] - 1]; }
+  __device__ uint32_t bubble_ref_reach(uint32_t v) const { return var_reach(R.ref_var_off[R.var_out_ref[v] - 1]); }
+  __device__ bool is_special(uint32_t p) const { return p >= SPECIAL_START && (p - SPECIAL_START) < R.n_special; }
+  __device__ uint32_t ref_reach_pos(uint32_t p) const { return is_special(p) ? R.ref_reach_poses[p - SPECIAL_START] : p; }
+  __device__ uint32_t actual_pos(uint32_t p) const { return is_special(p) ? R.actual_poses[p - SPECIAL_START] : p; }
+  __device__ uint32_t special(uint32_t pos, uint32_t ref_reach) const // graph.cpp:1775-1782
+  {
+    int lo = 0, hi = (int)R.n_sp_keys;
+    while (lo < hi)
+    {
+      int mid = (lo + hi) >> 1;
+      if (R.sp_keys[mid] < ref_reach)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    if (lo >= (int)R.n_sp_keys || R.sp_keys[lo] != ref_reach)
+      return INVALID;
+    uint32_t const idx = pos - ref_reach - 1;
+    if (R.sp_off[lo] + idx >= R.sp_off[lo + 1])
+      return INVALID;
+    return R.sp_list[R.sp_off[lo] + idx];
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ phase A: seeds
+__device__ __forceinline__ bool probe(const DevRegion & R, uint64_t key, uint32_t & off, uint32_t & cnt)
+{
+  uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> R.table_shift);
+  const uint4 * tab = reinterpret_cast<const uint4 *>(R.table);
+  while (true)
+  {
+    uint4 const s = __ldg(tab + h);
+    if (s.w == 0)
+      return false;
+    uint64_t const k = (uint64_t)s.x | ((uint64_t)s.y << 32);
+    if (k == key)
+    {
+      off = s.z;
+      cnt = s.w;
+      return true;
+    }
+    h = (h + 1) & R.table_mask;
+  }
+}
+
+// Appends the bucket references of `nk` keys (key k produced by keyfn(k)) to S.refs in key order, applying the
+// "more than 75 labels while probing several keys => give the slot up" rule of PHIndex::multi_get.
+template <typename KeyFn>
+__device__ void query_list(WS & S, const DevRegion & R, KeyFn keyfn, int nk, bool multi, int lane, int & nrefs)
+{
+  int const start = nrefs;
+  uint32_t total = 0;
+  bool dropped = false;
+  for (int base = 0; base < nk; base += 32)
+  {
+    int const k = base + lane;
+    bool found = false;
+    uint32_t off = 0, cnt = 0;
+    if (k < nk)
+      found = probe(R, keyfn(k), off, cnt);
+    uint32_t inc = found ? cnt : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      uint32_t const t = __shfl_up_sync(FULL, inc, d);
+      if (lane >= d)
+        inc += t;
+    }
+    bool const exceed = multi && found && (total + inc) > 75u;
+    if (__any_sync(FULL, exceed))
+    {
+      dropped = true;
+      break;
+    }
+    unsigned const fm = __ballot_sync(FULL, found);
+    int const pos = nrefs + __popc(fm & ((1u << lane) - 1u));
+    if (found && pos < REF_CAP)
+      S.refs[pos] = make_uint2(off, cnt);
+    nrefs += __popc(fm);
+    total += __shfl_sync(FULL, inc, 31);
+  }
+  if (dropped)
+    nrefs = start;
+  if (nrefs > REF_CAP)
+  {
+    if (lane == 0)
+      S.overflow = 1;
+    nrefs = start;
+  }
+}
+
+// to_uint64_vec for a slot with IUPAC / N bases (type_conversions.cpp:207-266); lane 0 only; returns key count
+__device__ int expand_keys(const uint8_t * codes, uint64_t * keys, int cap)
+{
+  int n = 1;
+  keys[0] = 0;
+  for (int i = 0; i < 32; ++i)
+  {
+    int const origin = n;
+    if (origin > 97)
+      return 0;
+    uint8_t const c = codes[i];
+    for (int k = 0; k < origin; ++k)
+    {
+      if (c == 15 || c == 0)
+      {
+        if (n + 3 > cap)
+          return -1;
+        keys[n++] = keys[k] * 4 + 0;
+        keys[n++] = keys[k] * 4 + 1;
+        keys[n++] = keys[k] * 4 + 2;
+        keys[k] = keys[k] * 4 + 3;
+      }
+      else
+      {
+        int set_count = __popc((unsigned)c);
+        for (int b = 0; b < 4; ++b)
+          if (c & (1 << b))
+          {
+            if (set_count == 1)
+              keys[k] = keys[k] * 4 + b;
+            else
+            {
+              if (n + 1 > cap)
+                return -1;
+              keys[n++] = keys[k] * 4 + b;
+            }
+            --set_count;
+          }
+      }
+    }
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------ phase B: chaining
+__device__ __forceinline__ uint32_t psize(const Path & p) { return (uint32_t)p.re - p.rs + 1u; }
+
+__device__ void merge_with_current(WS & S, const GR & g, Path & p, const DevLabel & l) // path.cpp:105-129
+{
+  if (l.var == INVALID)
+    return;
+  uint32_t const vo = g.R.var_order[l.var];
+  allele_mask_t const bit = (allele_mask_t)1 << g.variant_num(l.var);
+  for (int i = 0; i < p.nvar; ++i)
+    if (p.order[i] == vo)
+    {
+      p.mask[i] |= bit;
+      return;
+    }
+  if (p.nvar >= MAXV)
+  {
+    S.overflow = 1;
+    return;
+  }
+  p.order[p.nvar] = vo;
+  p.mask[p.nvar] = bit;
+  ++p.nvar;
+}
+
+// find_all_nonduplicated_paths, one label at a time (genotype_paths.cpp:32-66)
+__device__ void pp_add_label(WS & S, const GR & g, const DevLabel & l, uint16_t rs, uint16_t re, uint16_t mm)
+{
+  for (int d = 0; d < S.npp; ++d)
+    if (S.pp[d].start == l.start && S.pp[d].end == l.end)
+    {
+      merge_with_current(S, g, S.pp[d], l);
+      return;
+    }
+  if (S.npp >= MAXP)
+  {
+    S.overflow = 1;
+    return;
+  }
+  Path & p = S.pp[S.npp++];
+  p.start = l.start;
+  p.end = l.end;
+  p.rs = rs;
+  p.re = re;
+  p.mm = mm;
+  p.nvar = 0;
+  if (l.var != INVALID)
+  {
+    p.order[0] = g.R.var_order[l.var];
+    p.mask[0] = (allele_mask_t)1 << g.variant_num(l.var);
+    p.nvar = 1;
+  }
+}
+
+// Path(p1, p2) (path.cpp:38-82); false = empty allele intersection (the caller drops the merge)
+__device__ bool merge_paths(WS & S, const Path & p1, const Path & p2, Path & out)
+{
+  out = p2;
+  for (int i = 0; i < p1.nvar; ++i)
+  {
+    bool found = false;
+    for (int j = 0; j < out.nvar; ++j)
+      if (p1.order[i] == out.order[j])
+      {
+        out.mask[j] &= p1.mask[i];
+        if (out.mask[j] == 0)
+          return false;
+        found = true;
+        break;
+      }
+    if (!found)
+    {
+      if (out.nvar >= MAXV)
+      {
+        S.overflow = 1;
+        return false;
+      }
+      out.order[out.nvar] = p1.order[i];
+      out.mask[out.nvar] = p1.mask[i];
+      ++out.nvar;
+    }
+  }
+  out.rs = p1.rs;
+  out.start = p1.start;
+  out.mm = (uint16_t)(out.mm + p1.mm);
+  return true;
+}
+
+__device__ void push_path(WS & S, const Path & p)
+{
+  if (S.npaths >= MAXP)
+  {
+    S.overflow = 1;
+    return;
+  }
+  S.paths[S.npaths++] = p;
+}
+
+// second half of add_next_kmer_labels (genotype_paths.cpp:308-351): S.pp holds the grouped new labels
+__device__ void add_next(WS & S, uint32_t rs)
+{
+  int const orig = S.npaths;
+  for (int j = 0; j < S.npp; ++j)
+    S.matched[j] = 0;
+  for (int i = 0; i < orig; ++i)
+  {
+    if (S.paths[i].re != rs)
+      continue;
+    bool once = false;
+    S.op = S.paths[i];
+    for (int j = 0; j < S.npp; ++j)
+    {
+      if (S.op.end != S.pp[j].start)
+        continue;
+      if (!merge_paths(S, S.op, S.pp[j], S.np))
+        continue;
+      S.matched[j] = 1;
+      if (once)
+        push_path(S, S.np);
+      else
+      {
+        S.longest = max(psize(S.np), S.longest);
+        S.paths[i] = S.np;
+        once = true;
+      }
+    }
+  }
+  for (int j = 0; j < S.npp; ++j)
+    if (!S.matched[j])
+    {
+      S.longest = max(psize(S.pp[j]), S.longest);
+      push_path(S, S.pp[j]);
+    }
+}
+
+// second half of add_prev_kmer_labels (genotype_paths.cpp:247-291)
+__device__ void add_prev(WS & S, uint32_t re)
+{
+  int const orig = S.npaths;
+  for (int j = 0; j < S.npp; ++j)
+    S.matched[j] = 0;
+  for (int i = 0; i < orig; ++i)
+  {
+    if (S.paths[i].rs != re)
+      continue;
+    bool once = false;
+    S.op = S.paths[i];
+    for (int j = 0; j < S.npp; ++j)
+    {
+      if (S.pp[j].end != S.op.start)
+        continue;
+      if (!merge_paths(S, S.pp[j], S.op, S.np))
+        continue;
+      S.matched[j] = 1;
+      if (once)
+        push_path(S, S.np);
+      else
+      {
+        S.longest = max(psize(S.np), S.longest);
+        S.paths[i] = S.np;
+        once = true;
+      }
+    }
+  }
+  for (int j = 0; j < S.npp; ++j)
+    if (!S.matched[j])
+    {
+      S.longest = max(psize(S.pp[j]), S.longest);
+      push_path(S, S.pp[j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ filters
+__device__ void remove_short_paths(WS & S) // genotype_paths.cpp:824-834
+{
+  if (S.longest <= 1)
+    return;
+  int w = 0;
+  for (int i = 0; i < S.npaths; ++i)
+    if (psize(S.paths[i]) >= S.longest)
+    {
+      if (w != i)
+        S.paths[w] = S.paths[i];
+      ++w;
+    }
+  S.npaths = w;
+}
+
+__device__ void update_longest(WS & S)
+{
+  uint32_t L = 0;
+  for (int i = 0; i < S.npaths; ++i)
+    L = max(L, psize(S.paths[i]));
+  S.longest = L;
+}
+
+__device__ bool all_paths_unique(const WS & S, const GR & g) // genotype_paths.cpp:219-231
+{
+  for (int i = 1; i < S.npaths; ++i)
+    if (g.ref_reach_pos(S.paths[0].start) != g.ref_reach_pos(S.paths[i].start) &&
+        g.ref_reach_pos(S.paths[0].end) != g.ref_reach_pos(S.paths[i].end))
+      return false;
+  return true;
+}
+
+__device__ bool path_is_reference(const Path & p)
+{
+  for (int i = 0; i < p.nvar; ++i)
+    if ((p.mask[i] & 1u) == 0)
+      return false;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ phase C: graph walk
+// mismatches between read[koff + have + i] and dna[i] (graph_utils.hpp:7-37); BIGMM when the graph has '<' or '>'
+__device__ uint32_t cmp_fwd(const WS & S, int koff, uint32_t RL, uint32_t have, const uint8_t * dna, uint32_t n)
+{
+  if (have >= RL)
+    return 0;
+  uint32_t const m = min(n, RL - have);
+  uint32_t mm = 0;
+  const uint8_t * rd = S.seq + koff + have;
+  for (uint32_t i = 0; i < m; ++i)
+  {
+    uint8_t const gc = dna[i], rc = rd[i];
+    if (gc == '>' || gc == '<')
+      return BIGMM;
+    mm += (gc != rc && rc != 'N' && gc != 'N');
+  }
+  return mm;
+}
+
+// backward: the k-mer is read[0 .. RL), the candidate already covers its last `have` bases (graph_utils.hpp:39-69)
+__device__ uint32_t cmp_bwd(const WS & S, uint32_t RL, uint32_t have, const uint8_t * dna, uint32_t n)
+{
+  if (have >= RL)
+    return 0;
+  uint32_t const m = min(n, RL - have);
+  uint32_t mm = 0;
+  for (uint32_t i = 0; i < m; ++i)
+  {
+    uint8_t const gc = dna[n - 1 - i], rc = S.seq[RL - 1 - have - i];
+    if (gc == '>' || gc == '<')
+      return BIGMM;
+    mm += (gc != rc && rc != 'N' && gc != 'N');
+  }
+  return mm;
+}
+
+// Graph::get_locations_of_a_position (graph.cpp:931-1029,1154-1185) -> S.locs; returns count
+__device__ int get_locations(WS & S, const GR & g, uint32_t pos, const Path & path)
+{
+  const DevRegion & R = g.R;
+  bool const sp = g.is_special(pos);
+  if (sp)
+    pos = R.actual_poses[pos - SPECIAL_START];
+  int n = 0;
+  if (pos < R.ref_order[0])
+    return 0;
+  if (R.n_ref == 1)
+  {
+    S.locs[0] = Loc{'R', 0u, R.ref_order[0], pos - R.ref_order[0]};
+    return 1;
+  }
+  // rr = last ref node whose order <= pos
+  int lo = 1, hi = (int)R.n_ref;
+  while (lo < hi)
+  {
+    int const mid = (lo + hi) >> 1;
+    if (R.ref_order[mid] <= pos)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  int rr = lo - 1;
+  if (pos < R.ref_order[rr] + g.ref_len(rr))
+  {
+    if (!sp)
+    {
+      S.locs[0] = Loc{'R', (uint32_t)rr, R.ref_order[rr], pos - R.ref_order[rr]};
+      return 1;
+    }
+    --rr;
+  }
+  long long const PADDING = R.is_sv ? 1000000 : 1000;
+  bool const path_empty = path.start == path.end;
+  while (rr >= 0 && (long long)g.ref_reach(rr) + PADDING > (long long)pos)
+  {
+    uint32_t const vb = R.ref_var_off[rr], ve = R.ref_var_off[rr + 1];
+    for (uint32_t v = vb; v < ve; ++v)
+    {
+      uint32_t const vo = R.var_order[v];
+      if (pos >= vo && pos <= g.var_reach(v))
+      {
+        int j = -1;
+        for (int k = 0; k < path.nvar; ++k)
+          if (path.order[k] == vo)
+          {
+            j = k;
+            break;
+          }
+        if (j < 0)
+          continue;
+        if (path_empty || ((path.mask[j] >> (v - vb)) & 1u))
+        {
+          if (n >= MAXLOC)
+          {
+            S.overflow = 1;
+            return n;
+          }
+          S.locs[n++] = Loc{'V', v, vo, pos - vo};
+        }
+      }
+    }
+    --rr;
+  }
+  return n;
+}
+
+__device__ void emit_labels(WS & S, const Cand & c, uint32_t a, uint32_t b, bool cand_is_end, int & wn)
+{
+  // forward walk: (start = a fixed, end = cand.pos); backward: (start = cand.pos, end = b fixed)
+  uint32_t const st = cand_is_end ? a : c.pos;
+  uint32_t const en = cand_is_end ? c.pos : b;
+  if (c.nvar == 0)
+  {
+    if (wn >= WL_CAP)
+    {
+      S.overflow = 1;
+      return;
+    }
+    S.wl[wn++] = DevLabel{st, en, INVALID};
+    return;
+  }
+  for (uint32_t k = 0; k < c.nvar; ++k)
+  {
+    if (wn >= WL_CAP)
+    {
+      S.overflow = 1;
+      return;
+    }
+    S.wl[wn++] = DevLabel{st, en, c.vars[k]};
+  }
+}
+
+__device__ __forceinline__ bool cand_add_var(WS & S, Cand & c, uint32_t v)
+{
+  if (c.nvar >= CAND_V)
+  {
+    S.overflow = 1;
+    return false;
+  }
+  c.vars[c.nvar++] = v;
+  return true;
+}
+
+// Graph::get_labels_forward (graph.cpp:1187-1439). Candidate sequences are never materialised: a candidate is
+// (length so far, mismatches so far, var nodes, end position); mismatches are additive over appended nodes.
+__device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, uint32_t RL, uint32_t & max_mm, int & wn)
+{
+  const DevRegion & R = g.R;
+  int const w0 = wn;
+  int nc = 1;
+  uint32_t vb = 0, ve = 0;
+  {
+    Cand & c = S.cands[0];
+    c.nvar = 0;
+    c.pos = 0;
+    if (s.type == 'V')
+    {
+      uint32_t const v = s.node;
+      c.vars[0] = v;
+      c.nvar = 1;
+      uint32_t const n = g.var_len(v) - s.offset;
+      c.len = n;
+      c.mm = cmp_fwd(S, koff, RL, 0, g.var_dna(v) + s.offset, n);
+      if (n >= RL)
+      {
+        uint32_t ep = g.var_reach(v) - (n - RL);
+        uint32_t const rr = g.bubble_ref_reach(v);
+        if (ep > rr)
+          ep = g.special(ep, rr);
+        c.pos = ep;
+      }
+      else
+      {
+        uint32_t const r = R.var_out_ref[v];
+        vb = R.ref_var_off[r];
+        ve = R.ref_var_off[r + 1];
+        uint32_t const rn = g.ref_len(r);
+        c.mm += cmp_fwd(S, koff, RL, c.len, g.ref_dna(r), rn);
+        c.len += rn;
+        c.pos = g.ref_reach(r) - (c.len - RL);
+      }
+    }
+    else
+    {
+      uint32_t const r = s.node;
+      vb = R.ref_var_off[r];
+      ve = R.ref_var_off[r + 1];
+      uint32_t const n = g.ref_len(r) - s.offset;
+      c.len = n;
+      c.mm = cmp_fwd(S, koff, RL, 0, g.ref_dna(r) + s.offset, n);
+      c.pos = g.ref_reach(r) - (n - RL);
+    }
+  }
+
+  if (ve > vb && S.cands[0].len < RL)
+  {
+    uint32_t r = R.var_out_ref[vb];
+    bool all_long = false;
+    while (!all_long && nc < 128 && ve > vb)
+    {
+      all_long = true;
+      int orig = nc;
+      uint32_t const rn = g.ref_len(r);
+      const uint8_t * rdna = g.ref_dna(r);
+      uint32_t const rreach = g.ref_reach(r);
+      for (int j = 0; j < orig; ++j)
+      {
+        if (S.cands[j].len >= RL)
+          continue;
+        for (uint32_t v = vb; v + 1 < ve; ++v)
+        {
+          Cand const & base = S.cands[j];
+          uint32_t const m = g.var_len(v);
+          uint32_t mm = base.mm + cmp_fwd(S, koff, RL, base.len, g.var_dna(v), m);
+          uint32_t len = base.len + m;
+          bool const enough = len >= RL;
+          if (!enough)
+          {
+            mm += cmp_fwd(S, koff, RL, len, rdna, rn);
+            len += rn;
+          }
+          if (mm <= max_mm)
+          {
+            if (nc >= CAND_CAP)
+            {
+              S.overflow = 1;
+              continue;
+            }
+            Cand & nw = S.cands[nc];
+            nw = base;
+            if (!cand_add_var(S, nw, v))
+              continue;
+            nw.len = len;
+            nw.mm = mm;
+            if (len < RL)
+              all_long = false;
+            if (enough)
+            {
+              uint32_t ep = g.var_reach(v) - (len - RL);
+              uint32_t const rr = g.bubble_ref_reach(v);
+              if (ep > rr)
+                ep = g.special(ep, rr);
+              nw.pos = ep;
+            }
+            else
+              nw.pos = rreach - (len - RL);
+            ++nc;
+          }
+        }
+        // the last allele replaces candidate j in place (or erases it)
+        {
+          uint32_t const v = ve - 1;
+          Cand & c = S.cands[j];
+          uint32_t const m = g.var_len(v);
+          uint32_t mm = c.mm + cmp_fwd(S, koff, RL, c.len, g.var_dna(v), m);
+          uint32_t len = c.len + m;
+          bool const enough = len >= RL;
+          if (!enough)
+          {
+            mm += cmp_fwd(S, koff, RL, len, rdna, rn);
+            len += rn;
+          }
+          if (mm <= max_mm && cand_add_var(S, c, v))
+          {
+            c.len = len;
+            c.mm = mm;
+            if (len < RL)
+              all_long = false;
+            if (enough)
+            {
+              uint32_t ep = g.var_reach(v) - (len - RL);
+              uint32_t const rr = g.bubble_ref_reach(v);
+              if (ep > rr)
+                ep = g.special(ep, rr);
+              c.pos = ep;
+            }
+            else
+              c.pos = rreach - (len - RL);
+          }
+          else
+          {
+            for (int k = j; k + 1 < nc; ++k)
+              S.cands[k] = S.cands[k + 1];
+            --nc;
+            --orig;
+            --j;
+          }
+        }
+      }
+      if (!all_long)
+      {
+        vb = R.ref_var_off[r];
+        ve = R.ref_var_off[r + 1];
+        ++r;
+      }
+      else
+        break;
+    }
+  }
+
+  uint32_t start_pos = s.order + s.offset;
+  if (s.type == 'V')
+  {
+    uint32_t const rr = g.bubble_ref_reach(s.node);
+    if (start_pos > rr)
+      start_pos = g.special(start_pos, rr);
+  }
+  for (int j = 0; j < nc; ++j)
+  {
+    Cand const & c = S.cands[j];
+    if (c.len < RL)
+      continue;
+    if (c.mm > max_mm)
+      continue;
+    if (c.mm < max_mm)
+    {
+      max_mm = c.mm;
+      wn = w0;
+    }
+    emit_labels(S, c, start_pos, 0, true, wn);
+  }
+}
+
+// Graph::get_labels_backward (graph.cpp:1441-1701)
+__device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL, uint32_t & max_mm, int & wn)
+{
+  const DevRegion & R = g.R;
+  int const w0 = wn;
+  int nc = 1;
+  uint32_t vb = 0, ve = 0;
+  {
+    Cand & c = S.cands[0];
+    c.nvar = 0;
+    c.pos = 0;
+    if (e.type == 'V')
+    {
+      uint32_t const v = e.node;
+      c.vars[0] = v;
+      c.nvar = 1;
+      uint32_t const n = e.offset + 1;
+      c.len = n;
+      c.mm = cmp_bwd(S, RL, 0, g.var_dna(v), n);
+      if (n >= RL)
+      {
+        uint32_t sp = R.var_order[v] + (n - RL);
+        uint32_t const rr = g.bubble_ref_reach(v);
+        if (sp > rr)
+          sp = g.special(sp, rr);
+        c.pos = sp;
+      }
+      else
+      {
+        uint32_t const r = R.var_out_ref[v] - 1;
+        uint32_t const rn = g.ref_len(r);
+        c.mm += cmp_bwd(S, RL, c.len, g.ref_dna(r), rn);
+        c.len += rn;
+        c.pos = R.ref_order[r] + (c.len - RL);
+        if (r != 0)
+        {
+          vb = R.ref_var_off[r - 1];
+          ve = R.ref_var_off[r];
+        }
+      }
+    }
+    else
+    {
+      uint32_t const r = e.node;
+      if (r != 0)
+      {
+        vb = R.ref_var_off[r - 1];
+        ve = R.ref_var_off[r];
+      }
+      uint32_t const n = e.offset + 1;
+      c.len = n;
+      c.mm = cmp_bwd(S, RL, 0, g.ref_dna(r), n);
+      c.pos = R.ref_order[r] + (n - RL);
+    }
+  }
+
+  if (ve > vb && S.cands[0].len < RL)
+  {
+    uint32_t r = R.var_out_ref[vb] - 1;
+    bool all_long = false;
+    while (!all_long && nc < 128 && ve > vb)
+    {
+      all_long = true;
+      int orig = nc;
+      uint32_t const rn = g.ref_len(r);
+      const uint8_t * rdna = g.ref_dna(r);
+      uint32_t const rorder = R.ref_order[r];
+      for (int j = 0; j < orig; ++j)
+      {
+        if (S.cands[j].len >= RL)
+          continue;
+        for (uint32_t v = vb; v + 1 < ve; ++v)
+        {
+          Cand const & base = S.cands[j];
+          uint32_t const m = g.var_len(v);
+          uint32_t mm = base.mm + cmp_bwd(S, RL, base.len, g.var_dna(v), m);
+          uint32_t len = base.len + m;
+          bool const enough = len >= RL;
+          if (!enough)
+          {
+            mm += cmp_bwd(S, RL, len, rdna, rn);
+            len += rn;
+          }
+          if (mm <= max_mm)
+          {
+            if (nc >= CAND_CAP)
+            {
+              S.overflow = 1;
+              continue;
+            }
+            Cand & nw = S.cands[nc];
+            nw = base;
+            if (!cand_add_var(S, nw, v))
+              continue;
+            nw.len = len;
+            nw.mm = mm;
+            if (len < RL)
+              all_long = false;
+            if (enough)
+            {
+              uint32_t sp = R.var_order[v] + (len - RL);
+              uint32_t const rr = g.bubble_ref_reach(v);
+              if (sp > rr)
+                sp = g.special(sp, rr);
+              nw.pos = sp;
+            }
+            else
+              nw.pos = rorder + (len - RL);
+            ++nc;
+          }
+        }
+        {
+          uint32_t const v = ve - 1;
+          Cand & c = S.cands[j];
+          uint32_t const m = g.var_len(v);
+          uint32_t mm = c.mm + cmp_bwd(S, RL, c.len, g.var_dna(v), m);
+          uint32_t len = c.len + m;
+          bool const enough = len >= RL;
+          if (!enough)
+          {
+            mm += cmp_bwd(S, RL, len, rdna, rn);
+            len += rn;
+          }
+          if (mm <= max_mm && cand_add_var(S, c, v))
+          {
+            c.len = len;
+            c.mm = mm;
+            if (len < RL)
+              all_long = false;
+            if (enough)
+            {
+              uint32_t sp = R.var_order[v] + (len - RL);
+              uint32_t const rr = g.bubble_ref_reach(v);
+              if (sp > rr)
+                sp = g.special(sp, rr);
+              c.pos = sp;
+            }
+            else
+              c.pos = rorder + (len - RL);
+          }
+          else
+          {
+            for (int k = j; k + 1 < nc; ++k)
+              S.cands[k] = S.cands[k + 1];
+            --nc;
+            --orig;
+            --j;
+          }
+        }
+      }
+      if (!all_long)
+      {
+        if (r != 0)
+        {
+          --r;
+          vb = R.ref_var_off[r];
+          ve = R.ref_var_off[r + 1];
+        }
+        else
+        {
+          vb = ve = 0;
+          break;
+        }
+      }
+      else
+        break;
+    }
+  }
+
+  uint32_t end_pos = e.order + e.offset;
+  if (e.type == 'V')
+  {
+    uint32_t const rr = g.bubble_ref_reach(e.node);
+    if (end_pos > rr)
+      end_pos = g.special(end_pos, rr);
+  }
+  for (int j = 0; j < nc; ++j)
+  {
+    Cand const & c = S.cands[j];
+    if (c.len < RL)
+      continue;
+    if (c.mm < max_mm)
+    {
+      max_mm = c.mm;
+      wn = w0;
+      emit_labels(S, c, 0, end_pos, false, wn);
+    }
+    else if (c.mm == max_mm)
+      emit_labels(S, c, 0, end_pos, false, wn);
+  }
+}
+
+// walk_read_ends (forward = true, genotype_paths.cpp:483-553) / walk_read_starts (forward = false, :555-621)
+__device__ void walk(WS & S, const GR & g, uint32_t L, bool forward)
+{
+  if (S.npaths == 0 || psize(S.paths[0]) == L)
+    return;
+  // MAX_SEED_NUMBER_FOR_WALKING (256) / _ALLOWING_MISMATCHES (64) can never be reached with MAXP paths
+  uint32_t best_mm = 7;
+  int nlists = 0;
+  int committed = 0;
+  S.wl_list_start[0] = 0;
+  for (int pi = 0; pi < S.npaths; ++pi)
+  {
+    Path const & p = S.paths[pi];
+    uint32_t klen;
+    int koff = 0;
+    int nloc;
+    if (forward)
+    {
+      if (p.re == L - 1)
+        continue;
+      nloc = get_locations(S, g, p.end, p);
+      klen = L - p.re;
+      koff = p.re;
+    }
+    else
+    {
+      if (p.rs == 0)
+        continue;
+      klen = (uint32_t)p.rs + 1u;
+      nloc = get_locations(S, g, p.start, p);
+    }
+    if (nloc == 0)
+      continue;
+    uint32_t mm = min(2u + klen / 11u, best_mm);
+    // iterative_dfs (graph.cpp:1703-1754)
+    int const pend0 = committed;
+    int pend1 = committed;
+    for (int li = 0; li < nloc; ++li)
+    {
+      uint32_t m2 = mm;
+      int t1 = pend1;
+      Loc const loc = S.locs[li];
+      if (forward)
+        labels_forward(S, g, loc, koff, klen, m2, t1);
+      else
+        labels_backward(S, g, loc, klen, m2, t1);
+      if (t1 > pend1)
+      {
+        if (m2 < mm)
+        {
+          mm = m2;
+          int const cnt = t1 - pend1;
+          for (int k = 0; k < cnt; ++k)
+            S.wl[pend0 + k] = S.wl[pend1 + k];
+          pend1 = pend0 + cnt;
+        }
+        else if (m2 == mm)
+          pend1 = t1;
+      }
+    }
+    if (pend1 > pend0)
+    {
+      uint16_t const idx = forward ? p.re : p.rs;
+      if (mm < best_mm)
+      {
+        int const cnt = pend1 - pend0;
+        for (int k = 0; k < cnt; ++k)
+          S.wl[k] = S.wl[pend0 + k];
+        nlists = 1;
+        S.wl_list_start[0] = 0;
+        S.wl_list_start[1] = (uint16_t)cnt;
+        S.wl_list_idx[0] = idx;
+        best_mm = mm;
+        committed = cnt;
+      }
+      else if (mm == best_mm)
+      {
+        S.wl_list_idx[nlists] = idx;
+        S.wl_list_start[nlists + 1] = (uint16_t)pend1;
+        ++nlists;
+        committed = pend1;
+      }
+    }
+  }
+  for (int l = 0; l < nlists; ++l)
+  {
+    S.npp = 0;
+    uint16_t const idx = S.wl_list_idx[l];
+    for (int k = S.wl_list_start[l]; k < S.wl_list_start[l + 1]; ++k)
+    {
+      if (forward)
+        pp_add_label(S, g, S.wl[k], idx, (uint16_t)(L - 1), (uint16_t)best_mm);
+      else
+        pp_add_label(S, g, S.wl[k], 0, idx, (uint16_t)best_mm);
+    }
+    if (forward)
+      add_next(S, idx);
+    else
+      add_prev(S, idx);
+  }
+}
+
+// remove_support_from_read_ends (genotype_paths.cpp:382-430), SV graphs only
+__device__ void remove_support_from_read_ends(WS & S, const GR & g)
+{
+  for (int pi = 0; pi < S.npaths; ++pi)
+  {
+    Path & p = S.paths[pi];
+    if (p.nvar == 0)
+      continue;
+    if (!g.is_special(p.start) && !g.is_special(p.end))
+      continue;
+    int imin = 0, imax = 0;
+    for (int k = 1; k < p.nvar; ++k)
+    {
+      if (p.order[k] < p.order[imin])
+        imin = k;
+      if (p.order[k] > p.order[imax]) // std::minmax_element returns the LAST max; orders are unique so no tie
+        imax = k;
+    }
+    if (g.is_special(p.end) && (long long)g.actual_pos(p.end) <= (long long)p.order[imax] + 4)
+      p.mask[imax] = 0;
+    if (g.is_special(p.start))
+    {
+      bool amb;
+      if (g.is_special(p.start + 4u))
+        amb = g.ref_reach_pos(p.start) != g.ref_reach_pos(p.start + 4u);
+      else
+        amb = true;
+      if (amb)
+        p.mask[imin] = 0;
+    }
+  }
+}
+
+} // namespace
+
+// ================================================================================================ align kernel
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParams P)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WS * all = reinterpret_cast<WS *>(smem_raw);
+  int const lane = threadIdx.x & 31;
+  int const wib = threadIdx.x >> 5;
+  WS & S = all[wib];
+  int const total_warps = gridDim.x * WARPS_PER_BLOCK;
+  unsigned long long n_oriented = 0, n_overflow = 0;
+  uint32_t const n_tasks = P.batch.n_units * 2;
+
+  for (uint32_t task = blockIdx.x * WARPS_PER_BLOCK + wib; task < n_tasks; task += total_warps)
+  {
+    uint32_t const unit = task >> 1;
+    int const orient = task & 1;
+    int const rec = P.batch.unit_record[unit];
+    uint16_t const flag = P.batch.flag[rec];
+    int const L = P.batch.lseq[rec];
+    TaskSummary sum;
+    sum.npaths = 0;
+    sum.longest = 0;
+    sum.mm0 = 0;
+    sum.altcalls = 0;
+    sum.bits = TS_ALL_UNIQUE;
+    sum.pad = 0;
+    sum.path_off = task * INLINE_WORDS;
+
+    // align_read (alignment.cpp:331-363): which orientations are aligned
+    bool run = L >= 63 && L <= MAX_SEQ;
+    if (orient == 1)
+    {
+      int32_t const isz = P.batch.isize[rec];
+      bool const fwd_only = (flag & F_PAIRED) == 0 ||
+                            (P.batch.same_tid[rec] && isz > -1200 && isz < 1200 &&
+                             (((flag & F_REV) != 0) != ((flag & F_MREV) != 0)));
+      run = run && !fwd_only;
+    }
+    if (!run)
+    {
+      if (lane == 0)
+      {
+        if (L > MAX_SEQ)
+        {
+          sum.bits |= TS_OVERFLOW;
+          ++n_overflow;
+        }
+        P.summaries[task] = sum;
+        if (P.tap.list_count)
+          P.tap.nslots[task] = 0;
+      }
+      continue;
+    }
+    const DevRegion & R = P.regions[P.batch.region[rec]];
+    GR g(R);
+    __syncwarp();
+
+    // ---- A. unpack (reverse-complement for orientation 1: hts_parallel_reader.cpp:226-243)
+    {
+      const uint8_t * s4 = P.batch.seq4 + (size_t)rec * GTB_SEQ_STRIDE;
+      for (int j = lane; j < L; j += 32)
+      {
+        int const src = orient ? (L - 1 - j) : j;
+        uint8_t const byte = s4[src >> 1];
+        uint8_t c = (src & 1) ? (byte & 15) : (byte >> 4);
+        if (orient)
+          c = comp4(c);
+        S.seq[j] = c;
+      }
+      if (lane == 0)
+      {
+        S.overflow = 0;
+        S.npaths = 0;
+        S.npp = 0;
+        S.longest = 0;
+      }
+    }
+    __syncwarp();
+
+    int const nslots = 1 + (L - 32) / 31; // get_num_kmers (kmer_help_functions.cpp:10-17)
+    int nrefs = 0;
+    if (lane == 0)
+      S.list_start[0] = 0;
+    for (int i = 0; i < nslots; ++i)
+    {
+      uint8_t const c = S.seq[31 * i + lane];
+      bool const pure = __all_sync(FULL, __popc((unsigned)c) == 1);
+      if (pure)
+      {
+        uint64_t const val = (uint64_t)(__ffs((int)c) - 1) << (2 * (31 - lane));
+        uint32_t const lo = __reduce_or_sync(FULL, (uint32_t)val);
+        uint32_t const hi = __reduce_or_sync(FULL, (uint32_t)(val >> 32));
+        uint64_t const key = (uint64_t)lo | ((uint64_t)hi << 32);
+        query_list(S, R, [key](int) { return key; }, 1, false, lane, nrefs);
+        if (lane == 0)
+          S.list_start[2 * i + 1] = (uint16_t)nrefs;
+        // the 96 Hamming-1 neighbours, key order bb*3 + j (type_conversions.cpp:272-288)
+        query_list(S, R, [key](int k) { return key ^ ((uint64_t)(k % 3 + 1) << (2 * (k / 3))); }, 96, true, lane, nrefs);
+        if (lane == 0)
+          S.list_start[2 * i + 2] = (uint16_t)nrefs;
+      }
+      else
+      {
+        // IUPAC / N bases: expand on lane 0 into the (not yet used) path storage
+        uint64_t * keys = reinterpret_cast<uint64_t *>(S.paths);
+        int nk = 0;
+        if (lane == 0)
+        {
+          nk = expand_keys(S.seq + 31 * i, keys, (int)(sizeof(Path) * MAXP * 2 / sizeof(uint64_t)));
+          if (nk < 0)
+          {
+            S.overflow = 1;
+            nk = 0;
+          }
+        }
+        nk = __shfl_sync(FULL, nk, 0);
+        __syncwarp();
+        int const before = nrefs;
+        if (nk > 0)
+          query_list(S, R, [keys](int k) { return keys[k]; }, nk, nk > 1, lane, nrefs);
+        if (lane == 0)
+          S.list_start[2 * i + 1] = (uint16_t)nrefs;
+        __syncwarp();
+        // a slot without a unique exact key gets no Hamming-1 keys: the same keys are queried again
+        int const cnt = nrefs - before;
+        if (nrefs + cnt > REF_CAP)
+        {
+          if (lane == 0)
+            S.overflow = 1;
+        }
+        else
+        {
+          for (int k = lane; k < cnt; k += 32)
+            S.refs[nrefs + k] = S.refs[before + k];
+          nrefs += cnt;
+        }
+        if (lane == 0)
+          S.list_start[2 * i + 2] = (uint16_t)nrefs;
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+
+    // optional debug tap of the seed lists
+    if (P.tap.list_count)
+    {
+      uint32_t tot = 0;
+      if (lane == 0)
+      {
+        for (int l = 0; l < 2 * nslots; ++l)
+        {
+          uint32_t c = 0;
+          for (int k = S.list_start[l]; k < S.list_start[l + 1]; ++k)
+            c += S.refs[k].y;
+          P.tap.list_count[(size_t)task * NLISTS + l] = c;
+          tot += c;
+        }
+        for (int l = 2 * nslots; l < NLISTS; ++l)
+          P.tap.list_count[(size_t)task * NLISTS + l] = 0;
+        P.tap.nslots[task] = nslots;
+        unsigned long long base = atomicAdd(&P.counters->dbg_label_words, (unsigned long long)tot);
+        if (base + tot > P.tap.pool_cap)
+        {
+          S.overflow = 1;
+          for (int l = 0; l < NLISTS; ++l)
+            P.tap.list_count[(size_t)task * NLISTS + l] = 0;
+        }
+        else
+        {
+          unsigned long long o = base;
+          for (int l = 0; l < 2 * nslots; ++l)
+          {
+            P.tap.list_off[(size_t)task * NLISTS + l] = (uint32_t)o;
+            for (int k = S.list_start[l]; k < S.list_start[l + 1]; ++k)
+              for (uint32_t q = 0; q < S.refs[k].y; ++q)
+                P.tap.pool[o++] = R.labels[S.refs[k].x + q];
+          }
+        }
+      }
+    }
+
+    // ---- B..D on lane 0
+    if (lane == 0)
+    {
+      // "all k-mers extremely common" bail-out (alignment.cpp:35-49)
+      bool any_small = false;
+      for (int i = 0; i < nslots && !any_small; ++i)
+      {
+        uint32_t c = 0;
+        for (int k = S.list_start[2 * i]; k < S.list_start[2 * i + 1]; ++k)
+          c += S.refs[k].y;
+        if (c < 512u)
+          any_small = true;
+      }
+      if (any_small)
+      {
+        for (int l = 0; l < 2 * nslots; ++l)
+        {
+          uint16_t const rs = (uint16_t)(31 * (l >> 1));
+          S.npp = 0;
+          for (int k = S.list_start[l]; k < S.list_start[l + 1]; ++k)
+          {
+            uint2 const ref = S.refs[k];
+            for (uint32_t q = 0; q < ref.y; ++q)
+            {
+              DevLabel const lab = R.labels[ref.x + q];
+              pp_add_label(S, g, lab, rs, (uint16_t)(rs + 31), (uint16_t)(l & 1));
+            }
+          }
+          add_next(S, rs);
+        }
+        remove_short_paths(S);
+        // codes -> IUPAC characters for the graph walk
+        for (int j = 0; j < L; ++j)
+          S.seq[j] = (uint8_t)IUPAC_CHAR[S.seq[j]];
+        walk(S, g, (uint32_t)L, false); // starts before ends (alignment.cpp:71-72)
+        walk(S, g, (uint32_t)L, true);
+        update_longest(S);
+        remove_short_paths(S);
+        // remove_paths_with_too_many_mismatches (genotype_paths.cpp:360-380)
+        if (S.npaths > 0)
+        {
+          uint16_t mn = 10;
+          for (int i = 0; i < S.npaths; ++i)
+            mn = min(mn, S.paths[i].mm);
+          int w = 0;
+          for (int i = 0; i < S.npaths; ++i)
+            if (S.paths[i].mm <= mn)
+            {
+              if (w != i)
+                S.paths[w] = S.paths[i];
+              ++w;
+            }
+          S.npaths = w;
+        }
+        if (R.is_sv) // remove_fully_special_paths (genotype_paths.cpp:476-481)
+        {
+          int w = 0;
+          for (int i = 0; i < S.npaths; ++i)
+            if (g.ref_reach_pos(S.paths[i].start) != g.ref_reach_pos(S.paths[i].end))
+            {
+              if (w != i)
+                S.paths[w] = S.paths[i];
+              ++w;
+            }
+          S.npaths = w;
+        }
+        // remove_non_ref_paths_when_read_matches_ref (genotype_paths.cpp:460-474)
+        if (!all_paths_unique(S, g))
+        {
+          bool any_ref = false;
+          for (int i = 0; i < S.npaths; ++i)
+            if (path_is_reference(S.paths[i]))
+            {
+              any_ref = true;
+              break;
+            }
+          if (any_ref)
+          {
+            int w = 0;
+            for (int i = 0; i < S.npaths; ++i)
+              if (path_is_reference(S.paths[i]))
+              {
+                if (w != i)
+                  S.paths[w] = S.paths[i];
+                ++w;
+              }
+            S.npaths = w;
+          }
+        }
+        update_longest(S);
+        remove_short_paths(S);
+        if (R.is_sv)
+          remove_support_from_read_ends(S, g);
+      }
+
+      // ---- write the GenotypePaths record
+      if (S.overflow)
+      {
+        sum.bits |= TS_OVERFLOW;
+        ++n_overflow;
+        S.npaths = 0;
+        S.longest = 0;
+      }
+      sum.bits |= TS_COMPUTED;
+      sum.npaths = (uint16_t)S.npaths;
+      sum.longest = (uint16_t)S.longest;
+      if (S.npaths > 0)
+      {
+        sum.mm0 = S.paths[0].mm;
+        if (!all_paths_unique(S, g))
+          sum.bits &= ~TS_ALL_UNIQUE;
+        uint32_t words = 0, alt = 0;
+        for (int i = 0; i < S.npaths; ++i)
+        {
+          words += PATH_HDR_WORDS + 2u * S.paths[i].nvar;
+          for (int k = 0; k < S.paths[i].nvar; ++k)
+            alt += (S.paths[i].mask[k] & 1u) == 0;
+        }
+        sum.altcalls = (uint16_t)min(alt, 0xFFFFu);
+        unsigned long long off = (unsigned long long)task * INLINE_WORDS;
+        bool ok = true;
+        if (words > INLINE_WORDS)
+        {
+          unsigned long long const base = (unsigned long long)n_tasks * INLINE_WORDS;
+          off = base + atomicAdd(&P.counters->path_words, (unsigned long long)words);
+          if (off + words > P.path_pool_cap)
+            ok = false;
+        }
+        if (!ok)
+        {
+          sum.bits |= TS_OVERFLOW;
+          sum.npaths = 0;
+          ++n_overflow;
+        }
+        else
+        {
+          sum.path_off = (uint32_t)off;
+          uint32_t * w = P.path_pool + off;
+          for (int i = 0; i < S.npaths; ++i)
+          {
+            Path const & p = S.paths[i];
+            *w++ = p.start;
+            *w++ = p.end;
+            *w++ = (uint32_t)p.rs | ((uint32_t)p.re << 16);
+            *w++ = (uint32_t)p.mm | ((uint32_t)p.nvar << 16);
+            for (int k = 0; k < p.nvar; ++k)
+            {
+              *w++ = p.order[k];
+              *w++ = (uint32_t)p.mask[k];
+            }
+          }
+        }
+      }
+      P.summaries[task] = sum;
+      ++n_oriented;
+    }
+    __syncwarp();
+  }
+  if (lane == 0)
+  {
+    if (n_oriented)
+      atomicAdd(&P.counters->n_oriented, n_oriented);
+    if (n_overflow)
+      atomicAdd(&P.counters->n_overflow, n_overflow);
+  }
+}
+
+// ================================================================================================ score kernel
+namespace
+{
+constexpr uint16_t NO_COVERAGE = 0xFFFFu, MULTI_ALT_COVERAGE = 0xFFFEu, MULTI_REF_COVERAGE = 0xFFFDu;
+
+struct Geno // one GenotypePaths as the pool loop sees it after update_paths (alignment.cpp:482-538)
+{
+  TaskSummary s;
+  uint16_t flags;
+  uint16_t read_length;
+  uint8_t mapq;
+  uint8_t score_diff;
+  bool proper_pair; // GenotypePaths::is_proper_pair(): ml_insert_size != 0x7FFFFFFF
+};
+
+__device__ __forceinline__ uint32_t T_of(const Geno & g) { return g.s.npaths > 0 ? g.s.longest : 0u; }
+
+// compare_pair_of_genotype_paths (genotype_paths.cpp:976-1169)
+__device__ int compare_pairs(const Geno & a1, const Geno & a2, const Geno & b1, const Geno & b2)
+{
+  uint32_t const T11 = T_of(a1), T12 = T_of(a2), T21 = T_of(b1), T22 = T_of(b2);
+  uint32_t const MAX1 = max(T11, T12), MAX2 = max(T21, T22);
+  uint32_t const P1 = a1.read_length, P2 = a2.read_length, MIN = 94;
+  bool const perf1 = T11 >= P1 && T12 >= P2, perf2 = T21 >= P1 && T22 >= P2;
+  if (perf1 || perf2)
+  {
+    if (perf1 && perf2)
+    {
+      uint32_t const m1 = (uint32_t)a1.s.mm0 + a2.s.mm0, m2 = (uint32_t)b1.s.mm0 + b2.s.mm0;
+      if (m1 < m2)
+        return 1;
+      if (m2 < m1)
+        return 2;
+      uint32_t const n1 = (uint32_t)a1.s.npaths + a2.s.npaths, n2 = (uint32_t)b1.s.npaths + b2.s.npaths;
+      if (n1 < n2)
+        return 1;
+      if (n2 < n1)
+        return 2;
+      uint32_t const c1 = (uint32_t)a1.s.altcalls + a2.s.altcalls, c2 = (uint32_t)b1.s.altcalls + b2.s.altcalls;
+      return c1 >= c2 ? 1 : 2;
+    }
+    return perf1 ? 1 : 2;
+  }
+  if (MAX2 >= MIN && MAX2 > MAX1)
+    return 2;
+  if (MAX1 >= MIN && MAX1 > MAX2)
+    return 1;
+  if (MAX1 >= MIN && MAX2 >= MIN)
+  {
+    uint32_t m1 = 10, m2 = 10;
+    if (T11 == MAX1)
+      m1 = min(m1, (uint32_t)a1.s.mm0);
+    if (T12 == MAX1)
+      m1 = min(m1, (uint32_t)a2.s.mm0);
+    if (T21 == MAX2)
+      m2 = min(m2, (uint32_t)b1.s.mm0);
+    if (T22 == MAX2)
+      m2 = min(m2, (uint32_t)b2.s.mm0);
+    if (m1 < m2)
+      return 1;
+    if (m2 < m1)
+      return 2;
+    if (min(T11, T12) < min(T21, T22))
+      return 1;
+    if (min(T21, T22) < min(T11, T12))
+      return 2;
+    return 0;
+  }
+  if (MAX2 == 0u && T11 >= 63u && T12 >= 63u)
+    return 1;
+  if (MAX1 == 0u && T21 >= 63u && T22 >= 63u)
+    return 2;
+  return 1;
+}
+
+// are_genotype_paths_good (vcf_writer.cpp:28-60); all surviving paths have size == longest
+__device__ bool geno_good(const DevRegion & R, const Geno & g)
+{
+  if (g.s.npaths == 0)
+    return false;
+  bool const fully = g.s.longest == g.read_length;
+  bool const uniq = (g.s.bits & TS_ALL_UNIQUE) != 0;
+  if (!fully && (!uniq || g.s.longest < 63))
+    return false;
+  double const ratio = (double)g.s.mm0 / (double)g.s.longest;
+  if (ratio > 0.05)
+    return false;
+  if (!fully && ratio > 0.025)
+    return false;
+  if (R.is_sv)
+    if (!fully || g.s.longest < 90 || ratio > 0.03)
+      return false;
+  return true;
+}
+
+__device__ __forceinline__ void add_coverage(uint16_t & coverage, uint16_t c) // haplotype.cpp:180-227
+{
+  if (coverage == NO_COVERAGE)
+    coverage = c;
+  else if (coverage == MULTI_ALT_COVERAGE)
+  {
+    if (c == 0)
+      coverage = MULTI_REF_COVERAGE;
+  }
+  else if (coverage == MULTI_REF_COVERAGE)
+  {
+  }
+  else if (coverage != c)
+    coverage = (coverage == 0 || c == 0) ? MULTI_REF_COVERAGE : MULTI_ALT_COVERAGE;
+}
+
+// push_to_haplotype_scores (vcf_writer.cpp:503-676) + explain_to_score / coverage_to_gts / *_to_stats
+__device__ bool push_scores(const LaunchParams & P, const DevRegion & R, const Geno & geno, int sample)
+{
+  GR g(R);
+  int const clipped_bp = (int)geno.read_length - (int)geno.s.longest;
+  bool const fully = clipped_bp == 0;
+  bool const non_unique = (geno.s.bits & TS_ALL_UNIQUE) == 0;
+  uint32_t const mismatches = geno.s.mm0;
+
+  uint32_t t_hap[MAX_TOUCH];
+  allele_mask_t t_expl[MAX_TOUCH];
+  uint16_t t_cov[MAX_TOUCH];
+  bool t_ovl[MAX_TOUCH];
+  int nt = 0;
+
+  const uint32_t * w = P.path_pool + geno.s.path_off;
+  for (int pi = 0; pi < geno.s.npaths; ++pi)
+  {
+    uint32_t const start = w[0], end = w[1];
+    uint32_t const nvar = w[3] >> 16;
+    w += PATH_HDR_WORDS;
+    long long const rs = (long long)g.ref_reach_pos(start), re = (long long)g.ref_reach_pos(end);
+    for (uint32_t k = 0; k < nvar; ++k)
+    {
+      uint32_t const order = w[2 * k];
+      allele_mask_t const mask = (allele_mask_t)w[2 * k + 1];
+      if (mask == 0)
+        continue;
+      // id2hap (vcf_writer.cpp:84): bubble index of this var order
+      int lo = 0, hi = (int)R.n_bubbles;
+      while (lo < hi)
+      {
+        int const mid = (lo + hi) >> 1;
+        if (R.bubble_order[mid] <= order)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      uint32_t const hap = (uint32_t)(lo - 1);
+      int t = -1;
+      for (int q = 0; q < nt; ++q)
+        if (t_hap[q] == hap)
+        {
+          t = q;
+          break;
+        }
+      if (t < 0)
+      {
+        if (nt >= MAX_TOUCH)
+          return false;
+        t = nt++;
+        t_hap[t] = hap;
+        t_expl[t] = 0;
+        t_cov[t] = NO_COVERAGE;
+        t_ovl[t] = false;
+      }
+      bool const overlapping = (rs + 3) <= (long long)order && (re - 3) > (long long)order;
+      t_ovl[t] = t_ovl[t] || overlapping;
+      t_expl[t] |= mask;
+      if (__popc(mask) == 1)
+        add_coverage(t_cov[t], (uint16_t)(__ffs((int)mask) - 1));
+      else
+      {
+        add_coverage(t_cov[t], 1);
+        add_coverage(t_cov[t], (mask & 1u) ? 0 : 2);
+      }
+    }
+    w += 2 * nvar;
+  }
+
+  uint32_t const NS = R.n_samples;
+  for (int t = 0; t < nt; ++t)
+  {
+    uint32_t const b = t_hap[t];
+    uint16_t const cov = t_cov[t];
+    uint32_t const c0 = R.cov_off[b];
+    uint32_t const cnum = R.cov_off[b + 1] - c0;
+    // *_to_stats (haplotype.cpp:229-313)
+    if (clipped_bp != 0)
+    {
+      long const scaled = (clipped_bp * 1000l) / geno.read_length;
+      if (cov != NO_COVERAGE)
+        atomicAdd(&R.vs_clipped_reads[b], 1ull);
+      if (cov < MULTI_REF_COVERAGE)
+        atomicAdd(&R.pa_clipped_bp[c0 + cov], (unsigned long long)scaled);
+    }
+    if (geno.mapq != 255)
+    {
+      unsigned long long const sq = (unsigned long long)geno.mapq * geno.mapq;
+      if (cov != NO_COVERAGE)
+        atomicAdd(&R.vs_mapq_squared[b], sq);
+      if (cov < MULTI_REF_COVERAGE)
+        atomicAdd(&R.pa_mapq_squared[c0 + cov], sq);
+    }
+    if (cov < MULTI_REF_COVERAGE)
+    {
+      bool const fwd = (geno.flags & F_REV) == 0, first = (geno.flags & F_FIRST) != 0;
+      atomicAdd(&R.read_strand[(size_t)(c0 + cov) * 4 + (first ? 0 : 2) + (fwd ? 0 : 1)], 1u);
+      uint32_t const mm8 = mismatches & 0xFFu;
+      if (mm8 != 0)
+        atomicAdd(&R.pa_mismatches[c0 + cov], (unsigned long long)((mm8 * 1000l) / geno.read_length));
+      if (geno.score_diff != 0)
+        atomicAdd(&R.pa_score_diff[c0 + cov], (unsigned long long)geno.score_diff);
+    }
+    // explain_to_score (haplotype.cpp:462-585)
+    long eps = 12;
+    eps -= (long)mismatches;
+    if (non_unique)
+      eps -= 3;
+    if (geno.flags & F_MAPQ_BAD)
+      eps -= 2;
+    if (!fully)
+      eps -= 3;
+    if (!t_ovl[t])
+      eps -= 1;
+    uint32_t const e = (uint32_t)(max(eps, 8l) - 4);
+    size_t const bs = (size_t)b * NS + sample;
+    atomicAdd(&R.max_log_score[bs], e);
+    {
+      uint32_t const tri = R.score_off[b + 1] - R.score_off[b];
+      uint32_t * ls = R.log_score + (size_t)R.score_off[b] * NS + (size_t)sample * tri;
+      allele_mask_t const E = t_expl[t];
+      uint32_t i = 0;
+      for (uint32_t y = 0; y < cnum; ++y)
+      {
+        bool const ey = (E >> y) & 1u;
+        for (uint32_t x = 0; x <= y; ++x, ++i)
+        {
+          bool const ex = (E >> x) & 1u;
+          if (ex && ey)
+            atomicAdd(&ls[i], e);
+          else if (ex || ey)
+            atomicAdd(&ls[i], e - 1);
+        }
+      }
+    }
+    // coverage_to_gts (haplotype.cpp:315-361); saturation applied on download
+    if (cov == MULTI_REF_COVERAGE)
+      atomicAdd(&R.amb[bs], 1u);
+    else if (cov == MULTI_ALT_COVERAGE)
+    {
+      atomicAdd(&R.amb[bs], 1u);
+      atomicAdd(&R.amb_alt[bs], 1u);
+      if (geno.proper_pair)
+        atomicAdd(&R.alt_pp[bs], 1u);
+    }
+    else if (cov != NO_COVERAGE)
+    {
+      atomicAdd(&R.gt_cov[(size_t)c0 * NS + (size_t)sample * cnum + cov], 1u);
+      if (cov > 0 && geno.proper_pair)
+        atomicAdd(&R.alt_pp[bs], 1u);
+    }
+  }
+  return true;
+}
+
+// GenotypePaths pair of one record as update_paths leaves it
+__device__ void make_genos(const LaunchParams & P, int rec, Geno & first, Geno & second)
+{
+  int const unit = P.batch.unit[rec];
+  uint16_t const flag = P.batch.flag[rec];
+  first.s = P.summaries[2 * unit];
+  second.s = P.summaries[2 * unit + 1];
+  first.read_length = second.read_length = P.batch.lseq[rec];
+  first.mapq = second.mapq = P.batch.mapq[rec];
+  first.score_diff = second.score_diff = P.batch.score_diff[rec];
+  int32_t const isz = P.batch.isize[rec];
+  bool const pp = (isz < 0 ? -(long long)isz : (long long)isz) != 0x7FFFFFFFll;
+  first.proper_pair = second.proper_pair = pp;
+  first.flags = flag & ~F_PROPER;
+  if (P.batch.mapq[rec] < 25)
+    first.flags |= F_MAPQ_BAD;
+  second.flags = (flag ^ F_REV) & ~F_PROPER; // note: no IS_MAPQ_BAD on the flipped orientation (alignment.cpp:520)
+  if (P.batch.clipped[rec])
+  {
+    first.flags |= 8192;
+    second.flags |= 8192;
+  }
+}
+} // namespace
+
+__global__ void __launch_bounds__(128) score_kernel(LaunchParams P)
+{
+  uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.batch.n_records)
+    return;
+  uint16_t const flag = P.batch.flag[i];
+  int32_t const m = P.batch.mate[i];
+  const DevRegion & R = P.regions[P.batch.region[i]];
+  int const sample = P.batch.sample[i];
+
+  if (m >= 0)
+  {
+    Geno g[4]; // prev.first, prev.second, cur.first, cur.second
+    make_genos(P, m, g[0], g[1]);
+    make_genos(P, (int)i, g[2], g[3]);
+    if (((g[0].s.bits | g[1].s.bits | g[2].s.bits | g[3].s.bits) & TS_OVERFLOW) != 0)
+      return; // counted by the align kernel; the host reports GTB_ERR_CAPACITY
+    if ((g[2].flags & F_FIRST) == (g[0].flags & F_FIRST))
+    {
+      atomicAdd(&P.counters->n_input_error, 1ull);
+      return;
+    }
+    // get_better_paths (alignment.cpp:557-622)
+    int arr[4] = {-1, -1, -1, -1};
+    for (int k = 0; k < 4; ++k)
+      arr[((g[k].flags & F_FIRST) != 0) + 2 * ((g[k].flags & F_REV) == 0)] = k;
+    if (arr[0] < 0 || arr[1] < 0 || arr[2] < 0 || arr[3] < 0)
+      return;
+    int const c = compare_pairs(g[arr[3]], g[arr[0]], g[arr[1]], g[arr[2]]);
+    int s1 = -1, s2 = -1;
+    if (c == 1)
+    {
+      s1 = arr[3];
+      s2 = arr[0];
+    }
+    else if (c == 2)
+    {
+      s1 = arr[1];
+      s2 = arr[2];
+    }
+    if (s1 < 0)
+      return;
+    bool ok = true;
+    if (geno_good(R, g[s1]))
+      ok = push_scores(P, R, g[s1], sample) && ok;
+    if (geno_good(R, g[s2]))
+      ok = push_scores(P, R, g[s2], sample) && ok;
+    if (!ok)
+      atomicAdd(&P.counters->n_overflow, 1ull);
+    atomicAdd(&P.counters->n_pairs_scored, 1ull);
+  }
+  else if ((flag & F_PAIRED) == 0)
+  {
+    // update_unpaired_read_paths (alignment.cpp:365-449) + compare (genotype_paths.cpp:943-974)
+    Geno a, b;
+    make_genos(P, (int)i, a, b);
+    if (((a.s.bits | b.s.bits) & TS_OVERFLOW) != 0)
+      return;
+    a.proper_pair = b.proper_pair = false; // ml_insert_size stays INSERT_SIZE_WHEN_NOT_PROPER_PAIR
+    uint32_t const T1 = a.s.longest, T2 = b.s.longest; // longest_path_size() (0 when there are no paths)
+    int c = 0;
+    if (T1 > T2 && T1 > 94)
+      c = 1;
+    else if (T2 > T1 && T2 > 94)
+      c = 2;
+    else if (T2 == T1 && T1 > 94)
+      c = (b.s.mm0 < a.s.mm0) ? 2 : 1;
+    if (c == 0)
+      return;
+    Geno & sel = c == 1 ? a : b;
+    if (c == 2 && P.batch.mapq[i] < 25)
+      sel.flags |= F_MAPQ_BAD; // the unpaired path does set IS_MAPQ_BAD on the flipped orientation (alignment.cpp:419)
+    if (geno_good(R, sel))
+    {
+      if (!push_scores(P, R, sel, sample))
+        atomicAdd(&P.counters->n_overflow, 1ull);
+      atomicAdd(&P.counters->n_singles_scored, 1ull);
+    }
+  }
+}
+
+// ================================================================================================ launchers
+static int g_align_blocks_per_sm = 0;
+
+int align_kernel_blocks_per_sm()
+{
+  if (g_align_blocks_per_sm == 0)
+  {
+    size_t const smem = sizeof(WS) * WARPS_PER_BLOCK;
+    cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_kernel, WARPS_PER_BLOCK * 32, smem) != cudaSuccess || nb < 1)
+      nb = 1;
+    g_align_blocks_per_sm = nb;
+  }
+  return g_align_blocks_per_sm;
+}
+
+void launch_align(const LaunchParams & p, void * stream)
+{
+  size_t const smem = sizeof(WS) * WARPS_PER_BLOCK;
+  int const bps = align_kernel_blocks_per_sm();
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  uint32_t const n_tasks = p.batch.n_units * 2;
+  uint32_t const need = (n_tasks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  uint32_t grid = (uint32_t)(sms * bps); // persistent: a multiple of the SM count
+  if (need < grid)
+    grid = need;
+  if (grid == 0)
+    return;
+  align_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(p);
+}
+
+void launch_score(const LaunchParams & p, void * stream)
+{
+  if (p.batch.n_records == 0)
+    return;
+  uint32_t const grid = (p.batch.n_records + 127) / 128;
+  score_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+}
+
+} // namespace gtb

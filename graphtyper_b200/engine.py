@@ -1,0 +1,213 @@
+"""Python binding of libgtb200.so (the C ABI of include/gtb200.h) for the harness: tests, bench, smoke.
+
+The product is the shared library; this file only marshals numpy arrays through ctypes.  It raises loudly
+when the CUDA library is missing or when a compute entry point is used without a device -- there is no CPU
+fallback anywhere on this path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgtb200.so")
+
+EXPORTS = [
+    "gtb_last_error", "gtb_version", "gtb_create", "gtb_destroy", "gtb_region_begin", "gtb_region_end",
+    "gtb_index_size", "gtb_index_export", "gtb_pool_begin", "gtb_submit_reads", "gtb_accumulator_sizes",
+    "gtb_pool_finish", "gtb_submit_reads_multi", "gtb_debug_enable", "gtb_debug_seed_sizes", "gtb_debug_seeds",
+    "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_replay_last",
+    "gtb_last_timing", "gtb_pool_reset", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators",
+]
+
+
+class GtbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libgtb200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.gtb_last_error.restype = C.c_char_p
+    L.gtb_version.restype = C.c_char_p
+    L.gtb_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.gtb_destroy.argtypes = [vp]
+    L.gtb_destroy.restype = None
+    L.gtb_region_begin.argtypes = [vp, C.c_int, C.POINTER(abi.GraphView)]
+    L.gtb_region_end.argtypes = [vp, C.c_int]
+    L.gtb_index_size.argtypes = [vp, C.c_int, abi.u64p, abi.u64p]
+    L.gtb_index_export.argtypes = [vp, C.c_int, abi.u64p, abi.u32p, C.POINTER(abi.Label)]
+    L.gtb_pool_begin.argtypes = [vp, C.c_int, C.c_int]
+    L.gtb_submit_reads.argtypes = [vp, C.c_int, C.POINTER(abi.ReadBatch), C.POINTER(abi.SubmitStats)]
+    L.gtb_submit_reads_multi.argtypes = [vp, C.c_int, abi.i32p, C.POINTER(abi.ReadBatch), C.POINTER(abi.SubmitStats)]
+    L.gtb_accumulator_sizes.argtypes = [vp, C.c_int, abi.u32p, abi.u64p, abi.u64p]
+    L.gtb_pool_finish.argtypes = [vp, C.c_int, C.POINTER(abi.Accumulators)]
+    L.gtb_debug_enable.argtypes = [vp, C.c_int]
+    L.gtb_debug_seed_sizes.argtypes = [vp, C.c_int, abi.u64p, abi.u64p, abi.u64p]
+    L.gtb_debug_seeds.argtypes = [vp, C.c_int, abi.u32p, abi.u32p, abi.u32p, C.POINTER(abi.Label)]
+    L.gtb_debug_path_sizes.argtypes = [vp, C.c_int, abi.u64p, abi.u64p, abi.u64p, abi.u64p]
+    L.gtb_debug_paths.argtypes = [vp, C.c_int, abi.u32p, abi.u32p, abi.u32p, abi.u32p, abi.u32p, abi.u16p]
+    L.gtb_calls_from_accumulators.argtypes = [C.POINTER(abi.Accumulators), abi.u8p, abi.u16p, abi.u8p]
+    L.gtb_replay_last.argtypes = [vp, C.POINTER(abi.SubmitStats)]
+    fp = C.POINTER(C.c_float)
+    L.gtb_last_timing.argtypes = [vp, fp, fp, fp, fp]
+    L.gtb_pool_reset.argtypes = [vp, C.c_int]
+    L.gtb_nccl_unique_id.argtypes = [abi.u8p]
+    L.gtb_nccl_init.argtypes = [vp, C.c_int, C.c_int, abi.u8p]
+    L.gtb_allreduce_accumulators.argtypes = [vp, C.c_int, vp]
+    _lib = L
+    return L
+
+
+class Context:
+    """One gtb_ctx: a device (or host-only when device < 0) with resident regions."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        self._check(self.lib.gtb_create(device, C.byref(self.h)))
+        self.device = device
+        self._graphs: Dict[int, abi.HostGraph] = {}
+        self._samples: Dict[int, int] = {}
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise GtbError(rc, self.lib.gtb_last_error().decode())
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.gtb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- regions / index
+    def region_begin(self, region_id: int, graph: abi.HostGraph) -> None:
+        self._check(self.lib.gtb_region_begin(self.h, region_id, C.byref(graph.view)))
+        self._graphs[region_id] = graph
+
+    def region_end(self, region_id: int) -> None:
+        self._check(self.lib.gtb_region_end(self.h, region_id))
+        self._graphs.pop(region_id, None)
+        self._samples.pop(region_id, None)
+
+    def index_export(self, region_id: int) -> Dict[str, np.ndarray]:
+        nk, nl = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.gtb_index_size(self.h, region_id, C.byref(nk), C.byref(nl)))
+        keys = np.zeros(nk.value, np.uint64)
+        off = np.zeros(nk.value + 1, np.uint32)
+        labels = np.zeros(nl.value * 3, np.uint32)
+        self._check(self.lib.gtb_index_export(self.h, region_id, keys.ctypes.data_as(abi.u64p),
+                                              off.ctypes.data_as(abi.u32p),
+                                              C.cast(labels.ctypes.data, C.POINTER(abi.Label))))
+        return {"keys": keys, "label_off": off, "labels": labels}
+
+    # -- pools
+    def pool_begin(self, region_id: int, n_samples: int) -> None:
+        self._check(self.lib.gtb_pool_begin(self.h, region_id, n_samples))
+        self._samples[region_id] = n_samples
+
+    def pool_reset(self, region_id: int) -> None:
+        self._check(self.lib.gtb_pool_reset(self.h, region_id))
+
+    def submit(self, region_id: int, batch: abi.HostBatch) -> abi.SubmitStats:
+        st = abi.SubmitStats()
+        self._check(self.lib.gtb_submit_reads(self.h, region_id, C.byref(batch.view), C.byref(st)))
+        return st
+
+    def submit_multi(self, region_ids: Sequence[int], batches: Sequence[abi.HostBatch]) -> abi.SubmitStats:
+        n = len(region_ids)
+        ids = (C.c_int32 * n)(*region_ids)
+        arr = (abi.ReadBatch * n)(*[b.view for b in batches])
+        st = abi.SubmitStats()
+        self._check(self.lib.gtb_submit_reads_multi(self.h, n, ids, arr, C.byref(st)))
+        return st
+
+    def replay(self) -> abi.SubmitStats:
+        st = abi.SubmitStats()
+        self._check(self.lib.gtb_replay_last(self.h, C.byref(st)))
+        return st
+
+    def last_timing(self) -> Tuple[float, float, float, float]:
+        a, b, c, d = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+        self._check(self.lib.gtb_last_timing(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
+    def pool_finish(self, region_id: int) -> abi.HostAccumulators:
+        nb, ns, nc = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.gtb_accumulator_sizes(self.h, region_id, C.byref(nb), C.byref(ns), C.byref(nc)))
+        acc = abi.HostAccumulators(nb.value, ns.value, nc.value, self._samples[region_id])
+        self._check(self.lib.gtb_pool_finish(self.h, region_id, C.byref(acc.view)))
+        return acc
+
+    # -- debug taps
+    def debug_enable(self, on: bool = True) -> None:
+        self._check(self.lib.gtb_debug_enable(self.h, 1 if on else 0))
+
+    def debug_seeds(self, region_id: int) -> Dict[str, np.ndarray]:
+        nu, ns, nl = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.gtb_debug_seed_sizes(self.h, region_id, C.byref(nu), C.byref(ns), C.byref(nl)))
+        unit_record = np.zeros(nu.value, np.uint32)
+        nslots = np.zeros(nu.value * 4, np.uint32)
+        nlabels = np.zeros(ns.value, np.uint32)
+        labels = np.zeros(nl.value * 3, np.uint32)
+        self._check(self.lib.gtb_debug_seeds(self.h, region_id, unit_record.ctypes.data_as(abi.u32p),
+                                             nslots.ctypes.data_as(abi.u32p), nlabels.ctypes.data_as(abi.u32p),
+                                             C.cast(labels.ctypes.data, C.POINTER(abi.Label))))
+        return {"unit_record": unit_record, "nslots": nslots, "nlabels": nlabels, "labels": labels}
+
+    def debug_paths(self, region_id: int) -> Dict[str, np.ndarray]:
+        nu, np_, nv, nn = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.gtb_debug_path_sizes(self.h, region_id, C.byref(nu), C.byref(np_), C.byref(nv), C.byref(nn)))
+        out = {"gp_npaths": np.zeros(nu.value * 2, np.uint32), "gp_longest": np.zeros(nu.value * 2, np.uint32),
+               "p_fields": np.zeros(np_.value * 6, np.uint32), "v_order": np.zeros(nv.value, np.uint32),
+               "v_nnum": np.zeros(nv.value, np.uint32), "v_nums": np.zeros(nn.value, np.uint16)}
+        self._check(self.lib.gtb_debug_paths(self.h, region_id, out["gp_npaths"].ctypes.data_as(abi.u32p),
+                                             out["gp_longest"].ctypes.data_as(abi.u32p),
+                                             out["p_fields"].ctypes.data_as(abi.u32p),
+                                             out["v_order"].ctypes.data_as(abi.u32p),
+                                             out["v_nnum"].ctypes.data_as(abi.u32p),
+                                             out["v_nums"].ctypes.data_as(abi.u16p)))
+        return out
+
+    # -- host finalisation
+    def calls(self, acc: abi.HostAccumulators):
+        phred = np.zeros(len(acc.log_score), np.uint8)
+        gt = np.zeros(acc.n_bubbles * acc.n_samples * 2, np.uint16)
+        gq = np.zeros(acc.n_bubbles * acc.n_samples, np.uint8)
+        self._check(self.lib.gtb_calls_from_accumulators(C.byref(acc.view), phred.ctypes.data_as(abi.u8p),
+                                                         gt.ctypes.data_as(abi.u16p), gq.ctypes.data_as(abi.u8p)))
+        return phred, gt, gq
+
+    # -- multi-GPU
+    def nccl_unique_id(self) -> np.ndarray:
+        buf = np.zeros(128, np.uint8)
+        self._check(self.lib.gtb_nccl_unique_id(buf.ctypes.data_as(abi.u8p)))
+        return buf
+
+    def nccl_init(self, n_ranks: int, rank: int, uid: np.ndarray) -> None:
+        uid = np.ascontiguousarray(uid, dtype=np.uint8)
+        self._check(self.lib.gtb_nccl_init(self.h, n_ranks, rank, uid.ctypes.data_as(abi.u8p)))
+
+    def allreduce(self, region_id: int) -> None:
+        self._check(self.lib.gtb_allreduce_accumulators(self.h, region_id, None))

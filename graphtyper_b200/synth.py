@@ -169,7 +169,8 @@ def _cigar_for(refpos: np.ndarray) -> Tuple[int, str]:
 def simulate_reads(ref: np.ndarray, sites: List[Site], gt: np.ndarray, sample: str, seed: int,
                    coverage: float = 30.0, read_len: int = 150, frag_lo: int = 320, frag_hi: int = 480,
                    err: float = 0.002, n_rate: float = 0.0, name_prefix: Optional[str] = None,
-                   lowmapq_rate: float = 0.0) -> ReadSet:
+                   lowmapq_rate: float = 0.0, unpaired_rate: float = 0.0, improper_rate: float = 0.0,
+                   flip_rate: float = 0.0) -> ReadSet:
     """gt: [n_sites, 2] allele indices for this sample."""
     rng = np.random.default_rng(seed)
     haps = [build_haplotype(ref, sites, gt[:, h]) for h in range(2)]
@@ -235,9 +236,25 @@ def simulate_reads(ref: np.ndarray, sites: List[Site], gt: np.ndarray, sample: s
         lm = rng.random(n_pairs) < lowmapq_rate
         mapq[left[lm]] = 10
         mapq[right[lm]] = 10
+    # stress options: unpaired singles, improper pairs (both orientations get aligned), strand-flipped SEQ
+    if unpaired_rate > 0:
+        up = rng.random(n_pairs) < unpaired_rate
+        flag[left[up]] = 0
+        flag[right[up]] = 16
+    if improper_rate > 0:
+        ip = (rng.random(n_pairs) < improper_rate) & ((flag[left] & 1) != 0)
+        first_left = (flag[left] & 64) != 0
+        flag[left[ip]] = np.where(first_left[ip], 65, 129)
+        flag[right[ip]] = np.where(first_left[ip], 129, 65)
+        if flip_rate > 0:
+            fl = ip & (rng.random(n_pairs) < flip_rate)
+            rows = np.concatenate([left[fl], right[fl]])
+            seqs[rows] = _COMP[seqs[rows][:, ::-1]]
     as_tag = (L - 5 * nerr).astype(np.int32)
     xs_tag = np.where(rng.random(2 * n_pairs) < 0.3, rng.integers(20, 100, size=2 * n_pairs), -1).astype(np.int32)
     name_id = np.repeat(np.arange(n_pairs, dtype=np.int64), 2)
+    if unpaired_rate > 0:
+        name_id[right[up]] += n_pairs  # singles get their own names
     # drop pairs where either mate has no aligned base (cannot happen with <=6 bp insertions) and sort
     order = np.lexsort((np.arange(2 * n_pairs), pos))
     prefix = name_prefix if name_prefix is not None else f"{sample}_r"
@@ -319,13 +336,16 @@ class Dataset:
 
 
 def make_dataset(length: int, n_sites: int, n_samples: int = 1, seed: int = 11, coverage: float = 30.0,
-                 err: float = 0.002, n_rate: float = 0.0, lowmapq_rate: float = 0.0) -> Dataset:
+                 err: float = 0.002, n_rate: float = 0.0, lowmapq_rate: float = 0.0, unpaired_rate: float = 0.0,
+                 improper_rate: float = 0.0, flip_rate: float = 0.0, read_len: int = 150) -> Dataset:
     ref = make_reference(length, seed)
     sites = make_sites(ref, n_sites, seed + 1)
     gts = make_genotypes(n_sites, n_samples, seed + 2)
     samples = [f"SAMP{k + 1}" for k in range(n_samples)]
     reads = [simulate_reads(ref, sites, gts[k], samples[k], seed + 100 + k, coverage=coverage, err=err,
-                            n_rate=n_rate, lowmapq_rate=lowmapq_rate) for k in range(n_samples)]
+                            n_rate=n_rate, lowmapq_rate=lowmapq_rate, unpaired_rate=unpaired_rate,
+                            improper_rate=improper_rate, flip_rate=flip_rate, read_len=read_len)
+             for k in range(n_samples)]
     return Dataset(ref, sites, gts, samples, reads)
 
 

@@ -192,6 +192,17 @@ int gtb_debug_paths(gtb_ctx *ctx, int region_id, uint32_t *gp_npaths /*[n_units*
 int gtb_calls_from_accumulators(const gtb_accumulators *acc, uint8_t *phred /*[n_scores*n_samples]*/,
                                 uint16_t *gt /*[n_bubbles*n_samples*2]*/, uint8_t *gq /*[n_bubbles*n_samples]*/);
 
+/* Bench/ops helpers: re-run the kernels on the batch already resident in HBM; device times (ms) of the last
+ * submit/replay from CUDA events on the library's stream; zero a region's accumulators. */
+int gtb_replay_last(gtb_ctx *ctx, gtb_submit_stats *stats);
+int gtb_last_timing(gtb_ctx *ctx, float *h2d_ms, float *align_ms, float *score_ms, float *d2h_ms);
+int gtb_pool_reset(gtb_ctx *ctx, int region_id);
+
+/* NCCL bootstrap (libnccl is bound lazily with dlopen): rank 0 creates the 128-byte unique id, the caller
+ * distributes it (e.g. torch.distributed.broadcast), every rank calls gtb_nccl_init. */
+int gtb_nccl_unique_id(uint8_t *id128);
+int gtb_nccl_init(gtb_ctx *ctx, int n_ranks, int rank, const uint8_t *id128);
+
 /* Multi-GPU: sum-reduce widened accumulators of a region over an NCCL communicator supplied by the host
  * (ncclComm_t passed as void*; all ranks call; result valid on every rank).  Used when ONE sample's reads
  * are split over GPUs; with sample sharding no collective is needed. */

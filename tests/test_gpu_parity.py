@@ -1,0 +1,99 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against (a) the golden vectors of the compiled
+reference and (b) the oracle on the same inputs.  Bit-exact: seeds, paths, accumulators, PL/GT/GQ."""
+import os
+
+import numpy as np
+import pytest
+
+import compare
+from conftest import fixture_prefixes
+from graphtyper_b200 import abi, engine, gtba
+
+ALL = fixture_prefixes(include_big=True)
+pytestmark = pytest.mark.gpu
+
+
+def n_samples_of(rd):
+    return len(rd["sample_names"].tobytes().split(b"\n")) - 1
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = engine.Context(device=0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("pre", ALL, ids=[os.path.basename(p) for p in ALL])
+def test_cuda_matches_reference(pre, ctx):
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    rd = gtba.load(pre + ".reads.gtba")
+    b = abi.batch_from_probe(rd)
+    ns = n_samples_of(rd)
+    ctx.region_begin(7, g)
+    try:
+        compare.compare_index(gtba.load(pre + ".index.gtba"), ctx.index_export(7))
+        ctx.pool_begin(7, ns)
+        ctx.debug_enable(True)
+        st = ctx.submit(7, b)
+        assert st.n_capacity_overflow == 0
+        assert st.kernel_launches == 2
+        assert compare.compare_seeds(compare.probe_seeds(rd), ctx.debug_seeds(7), "cuda") > 0
+        compare.compare_paths(compare.probe_paths(rd), ctx.debug_paths(7), "cuda")
+        acc = ctx.pool_finish(7)
+        pa = gtba.load(pre + ".accum.gtba")
+        compare.compare_accum(compare.probe_accum(pa), acc.as_dict(), "cuda")
+        ph, gt, gq = ctx.calls(acc)
+        assert np.array_equal(ph, pa["call_phred"])
+        assert np.array_equal(gt, pa["call_gt"])
+        assert np.array_equal(gq, pa["call_gq"])
+        assert not acc.saturated.any()
+    finally:
+        ctx.debug_enable(False)
+        ctx.region_end(7)
+
+
+def test_region_batched_submit_equals_separate(ctx):
+    """Several regions in ONE launch give the same accumulators as one launch per region."""
+    pres = ALL[:3]
+    graphs, batches, ns = [], [], []
+    for k, pre in enumerate(pres):
+        graphs.append(abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba")))
+        rd = gtba.load(pre + ".reads.gtba")
+        batches.append(abi.batch_from_probe(rd))
+        ns.append(n_samples_of(rd))
+        ctx.region_begin(100 + k, graphs[-1])
+        ctx.pool_begin(100 + k, ns[-1])
+    try:
+        st = ctx.submit_multi([100 + k for k in range(len(pres))], batches)
+        assert st.n_records == sum(len(b) for b in batches)
+        for k, pre in enumerate(pres):
+            acc = ctx.pool_finish(100 + k)
+            compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), acc.as_dict(), "cuda-multi")
+    finally:
+        for k in range(len(pres)):
+            ctx.region_end(100 + k)
+
+
+def test_replay_accumulates_linearly(ctx):
+    """Size-independent property: accumulators are additive -- replaying the resident batch doubles every sum."""
+    pre = ALL[0]
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    rd = gtba.load(pre + ".reads.gtba")
+    b = abi.batch_from_probe(rd)
+    ctx.region_begin(9, g)
+    try:
+        ctx.pool_begin(9, n_samples_of(rd))
+        ctx.submit(9, b)
+        a1 = ctx.pool_finish(9).as_dict()
+        ctx.replay()
+        a2 = ctx.pool_finish(9).as_dict()
+        for k in ("log_score", "gt_coverage", "pa_mapq_squared", "read_strand", "vs_mapq_squared"):
+            assert np.array_equal(a2[k].astype(np.int64), 2 * a1[k].astype(np.int64)), k
+        ctx.pool_reset(9)
+        ctx.replay()
+        a3 = ctx.pool_finish(9).as_dict()
+        for k in ("log_score", "gt_coverage", "read_strand"):
+            assert np.array_equal(a3[k], a1[k]), k
+    finally:
+        ctx.region_end(9)

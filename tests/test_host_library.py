@@ -1,0 +1,73 @@
+"""CPU suite for the product library: it loads, exports every symbol include/gtb200.h declares, its host-side
+index builder reproduces the reference's PHIndex (keys, labels, bucket order) on the golden fixtures, the host
+finalisation reproduces PL/GT/GQ, and the compute path refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import compare
+from conftest import ROOT, fixture_prefixes
+from graphtyper_b200 import abi, engine, gtba
+
+SMALL = fixture_prefixes(include_big=False)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gtb200.h")).read()
+    declared = set(re.findall(r"\b(gtb_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = engine.load_library()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libgtb200.so does not export {name}"
+    assert set(engine.EXPORTS) <= declared
+    assert b"sm_100a" in lib.gtb_version()
+
+
+@pytest.mark.parametrize("pre", SMALL, ids=[os.path.basename(p) for p in SMALL])
+def test_host_index_matches_reference(pre):
+    ctx = engine.Context(device=-1)
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    ctx.region_begin(0, g)
+    compare.compare_index(gtba.load(pre + ".index.gtba"), ctx.index_export(0))
+    ctx.region_end(0)
+    ctx.close()
+
+
+@pytest.mark.parametrize("pre", SMALL, ids=[os.path.basename(p) for p in SMALL])
+def test_host_finalisation_matches_reference(pre):
+    pa = gtba.load(pre + ".accum.gtba")
+    ref = compare.probe_accum(pa)
+    ns, nb = int(pa["meta"][0]), int(pa["meta"][1])
+    acc = abi.HostAccumulators(nb, int(ref["score_off"][-1]), int(ref["cov_off"][-1]), ns)
+    for k in ("n_alleles", "score_off", "cov_off", "log_score"):
+        getattr(acc, k)[:] = ref[k]
+    ctx = engine.Context(device=-1)
+    ph, gt, gq = ctx.calls(acc)
+    assert np.array_equal(ph, pa["call_phred"])
+    assert np.array_equal(gt, pa["call_gt"])
+    assert np.array_equal(gq, pa["call_gq"])
+    ctx.close()
+
+
+def test_no_cpu_fallback():
+    ctx = engine.Context(device=-1)
+    g = abi.HostGraph.from_gtba(gtba.load(SMALL[0] + ".graph.gtba"))
+    ctx.region_begin(0, g)
+    with pytest.raises(engine.GtbError) as e:
+        ctx.pool_begin(0, 1)
+    assert e.value.code == -2
+    ctx.close()
+
+
+def test_rejects_malformed_graph():
+    d = dict(gtba.load(SMALL[0] + ".graph.gtba"))
+    d["ref_var_off"] = d["ref_var_off"].copy()
+    d["ref_var_off"][1] = 1  # a bubble with a single allele
+    g = abi.HostGraph(d)
+    ctx = engine.Context(device=-1)
+    with pytest.raises(engine.GtbError):
+        ctx.region_begin(0, g)
+    ctx.close()

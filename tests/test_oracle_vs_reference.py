@@ -1,0 +1,66 @@
+"""CPU suite: the oracle (oracle/gtb_oracle.cpp) against golden vectors produced by the compiled, unmodified
+reference (tests/golden/make_golden.py).  Pins every stage: index contents and bucket order, per-seed label
+lists, per-read GenotypePaths, per-bubble accumulators, PL/GT/GQ."""
+import os
+
+import numpy as np
+import pytest
+
+import compare
+from conftest import fixture_prefixes
+from graphtyper_b200 import abi, gtba
+
+SMALL = fixture_prefixes(include_big=False)
+
+
+def n_samples_of(rd):
+    return len(rd["sample_names"].tobytes().split(b"\n")) - 1
+
+
+@pytest.mark.parametrize("pre", SMALL, ids=[os.path.basename(p) for p in SMALL])
+def test_oracle_matches_reference(pre, oracle_lib):
+    O = oracle_lib
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    h = O.index_build(g)
+    compare.compare_index(gtba.load(pre + ".index.gtba"), O.index_export(h))
+    rd = gtba.load(pre + ".reads.gtba")
+    b = abi.batch_from_probe(rd)
+    ns = n_samples_of(rd)
+    r = O.pool_run(g, h, ns, b)
+    assert compare.compare_seeds(compare.probe_seeds(rd), O.result_seeds(r), "oracle") > 0
+    compare.compare_paths(compare.probe_paths(rd), O.result_paths(r), "oracle")
+    acc = O.result_accum(r, ns)
+    pa = gtba.load(pre + ".accum.gtba")
+    compare.compare_accum(compare.probe_accum(pa), acc.as_dict(), "oracle")
+    ph, gt, gq = O.calls(acc)
+    assert np.array_equal(ph, pa["call_phred"])
+    assert np.array_equal(gt, pa["call_gt"])
+    assert np.array_equal(gq, pa["call_gq"])
+    assert not acc.saturated.any()
+    O.result_free(r)
+    O.index_free(h)
+
+
+def test_kmer_codec_known_answers(oracle_lib):
+    """Known answers of the reference's own unit tests for the k-mer codec
+    (test/utilities/test_kmer_help_functions.cpp, test/utilities/test_utilities.cpp:123-162):
+    first base in the most significant bits, A0 C1 G2 T3; 96 Hamming-1 neighbours = XOR of {1,2,3} << 2*bb."""
+    # a graph with a single 32-base ref node indexes exactly one k-mer with the expected key
+    seq = b"ACGT" * 8
+    arrays = {
+        "ref_order": np.array([1], np.uint32), "ref_seq_off": np.array([0, 32], np.uint64),
+        "ref_var_off": np.array([0, 0], np.uint32), "var_order": np.zeros(0, np.uint32),
+        "var_seq_off": np.array([32], np.uint64), "var_out_ref": np.zeros(0, np.uint32),
+        "seq": np.frombuffer(seq, np.uint8), "var_ev_off": np.zeros(1, np.uint32), "var_ev": np.zeros(0, np.int64),
+        "var_aev_off": np.zeros(1, np.uint32), "var_aev": np.zeros(0, np.int64),
+        "actual_poses": np.zeros(0, np.uint32), "ref_reach_poses": np.zeros(0, np.uint32),
+        "sp_keys": np.zeros(0, np.uint32), "sp_off": np.zeros(1, np.uint32), "sp_list": np.zeros(0, np.uint32)}
+    g = abi.HostGraph(arrays)
+    h = oracle_lib.index_build(g)
+    ix = oracle_lib.index_export(h)
+    key = 0
+    for c in seq:
+        key = (key << 2) | b"ACGT".index(c)
+    assert ix["keys"].tolist() == [key]
+    assert ix["labels"].tolist() == [1, 32, 0xFFFFFFFF]
+    oracle_lib.index_free(h)
