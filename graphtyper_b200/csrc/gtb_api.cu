@@ -125,7 +125,7 @@ struct Ctx
   DeviceBuffer d_regions;       // DevRegion table
   bool regions_dirty = true;
   // batch
-  DeviceBuffer d_batch, d_summaries, d_pool, d_counters, d_tap_counts, d_tap_pool;
+  DeviceBuffer d_batch, d_summaries, d_pool, d_counters, d_tap_counts, d_tap_pool, d_spill;
   PinnedBuffer h_batch, h_counters;
   LaunchParams last{};
   bool have_last = false;
@@ -258,6 +258,7 @@ void gtb_destroy(gtb_ctx * ctx)
     c->d_counters.release();
     c->d_tap_counts.release();
     c->d_tap_pool.release();
+    c->d_spill.release();
     c->h_batch.release();
     c->h_counters.release();
     for (auto & e : c->ev)
@@ -554,8 +555,16 @@ static int run_kernels(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     return fail(GTB_ERR_INPUT, "two mates with the same IS_FIRST_IN_PAIR flag (the reference aborts here, "
                                "hts_parallel_reader.cpp:306-315)");
   if (k->n_overflow)
+  {
+    static const char * names[12] = {"refs", "vars", "paths", "locs", "labels", "cand_vars", "cands", "keys", "tap",
+                                     "pool", "read_len", "-"};
+    std::string why;
+    for (int q = 0; q < 12; ++q)
+      if (k->reasons[q])
+        why += std::string(" ") + names[q] + "=" + std::to_string(k->reasons[q]);
     return fail(GTB_ERR_CAPACITY, std::to_string(k->n_overflow) +
-                                    " read(s) exceeded a device working-set capacity (gtb_device.cuh); results incomplete");
+                                    " read(s) exceeded a device working-set capacity (gtb_device.cuh):" + why);
+  }
   return 0;
 }
 
@@ -672,6 +681,8 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
     return rc;
   if (int rc = c->d_counters.reserve(sizeof(DevCounters)))
     return rc;
+  if (int rc = c->d_spill.reserve(align_spill_bytes()))
+    return rc;
   if (int rc = c->h_counters.reserve(sizeof(DevCounters)))
     return rc;
 
@@ -701,6 +712,7 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   P.path_pool = static_cast<uint32_t *>(c->d_pool.p);
   P.path_pool_cap = pool_words;
   P.counters = static_cast<DevCounters *>(c->d_counters.p);
+  P.cand_spill = c->d_spill.p;
   if (c->debug)
   {
     size_t const tap_counts = (size_t)n_tasks * (NLISTS * 2 + 1) * 4;

@@ -10,11 +10,12 @@ namespace gtb
 {
 // ---- capacities of the per-warp shared-memory working set (exceeding one flags the task, never silently wrong)
 constexpr int MAXP = 24;      // paths per read orientation held during chaining/extension
-constexpr int MAXV = 12;      // bubbles per path
+constexpr int MAXV = 16;      // bubbles per path
 constexpr int REF_CAP = 160;  // staged index bucket references per read orientation
 constexpr int MAX_SLOTS = 4;  // seed slots: 1 + (151-32)/31
 constexpr int NLISTS = MAX_SLOTS * 2;
 constexpr int CAND_CAP = 32;  // partial sequences during bubble expansion (reference limit: 128)
+constexpr int CAND_SPILL = 480; // further candidates per warp in global scratch (32 + 480 = 512)
 constexpr int CAND_V = 16;    // var nodes per candidate
 constexpr int MAXLOC = 8;     // graph locations of a position (reference limit: 256)
 constexpr int WL_CAP = 96;    // labels staged by one walk_read_starts/ends call
@@ -115,7 +116,8 @@ struct DevCounters
   unsigned long long n_overflow;
   unsigned long long n_input_error;  // mates with equal IS_FIRST_IN_PAIR
   unsigned long long dbg_label_words; // bump cursor of the debug seed pool
-  unsigned long long pad;
+  unsigned long long n_touch_overflow;
+  unsigned long long reasons[12];    // overflow histogram: refs vars paths locs labels candv cands keys tap pool len -
 };
 
 // Debug tap of the seed stage: per task, per list (slot*2 + ham): count and offset into a label pool
@@ -137,11 +139,13 @@ struct LaunchParams
   unsigned long long path_pool_cap; // words
   DevCounters * counters;
   DevSeedTap tap; // tap.list_count == nullptr when disabled
+  void * cand_spill; // per-resident-warp global extension of the bubble-expansion candidate list
 };
 
 // host launchers (gtb_kernels.cu)
 void launch_align(const LaunchParams & p, void * stream);
 void launch_score(const LaunchParams & p, void * stream);
 int align_kernel_blocks_per_sm();
+size_t align_spill_bytes();
 
 } // namespace gtb

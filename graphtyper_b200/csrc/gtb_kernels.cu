@@ -31,6 +31,8 @@ namespace
 {
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS_PER_BLOCK = 4;
+constexpr uint32_t OV_REFS = 1, OV_VARS = 2, OV_PATHS = 4, OV_LOCS = 8, OV_LABELS = 16, OV_CANDV = 32, OV_CANDS = 64,
+                   OV_KEYS = 128, OV_TAP = 256, OV_POOL = 512, OV_LEN = 1024;
 constexpr uint32_t BIGMM = 0x4000u; // "rejected" mismatch count ('<' / '>' in the graph sequence)
 constexpr uint32_t INVALID = 0xFFFFFFFFu;
 constexpr uint32_t SPECIAL_START = 0xD0000000u;
@@ -73,10 +75,15 @@ struct WS
   uint16_t wl_list_idx[MAXP];
   uint8_t matched[MAXP];
   uint8_t seq[MAX_SEQ + 8]; // 4-bit codes in phase A, IUPAC characters afterwards
+  Cand * cand_spill;        // this warp's global-memory extension of cands[] (CAND_SPILL entries)
   int npaths, npp;
   uint32_t longest;
   uint32_t overflow;
 };
+
+// candidate i of the bubble expansion: the first CAND_CAP live in shared memory, the (rare) rest in a per-warp
+// global scratch area, so that the reference's limit of 128 open candidates (+ one round of growth) fits
+__device__ __forceinline__ Cand & cand_at(WS & S, int i) { return i < CAND_CAP ? S.cands[i] : S.cand_spill[i - CAND_CAP]; }
 
 __device__ __forceinline__ uint8_t comp4(uint8_t c) // seqan TranslateTableIupacToIupacComplement_: 4-bit reversal
 {
@@ -183,7 +190,7 @@ __device__ void query_list(WS & S, const DevRegion & R, KeyFn keyfn, int nk, boo
   if (nrefs > REF_CAP)
   {
     if (lane == 0)
-      S.overflow = 1;
+      S.overflow |= OV_REFS;
     nrefs = start;
   }
 }
@@ -249,7 +256,7 @@ __device__ void merge_with_current(WS & S, const GR & g, Path & p, const DevLabe
     }
   if (p.nvar >= MAXV)
   {
-    S.overflow = 1;
+    S.overflow |= OV_VARS;
     return;
   }
   p.order[p.nvar] = vo;
@@ -268,7 +275,7 @@ __device__ void pp_add_label(WS & S, const GR & g, const DevLabel & l, uint16_t 
     }
   if (S.npp >= MAXP)
   {
-    S.overflow = 1;
+    S.overflow |= OV_PATHS;
     return;
   }
   Path & p = S.pp[S.npp++];
@@ -306,7 +313,7 @@ __device__ bool merge_paths(WS & S, const Path & p1, const Path & p2, Path & out
     {
       if (out.nvar >= MAXV)
       {
-        S.overflow = 1;
+        S.overflow |= OV_VARS;
         return false;
       }
       out.order[out.nvar] = p1.order[i];
@@ -324,7 +331,7 @@ __device__ void push_path(WS & S, const Path & p)
 {
   if (S.npaths >= MAXP)
   {
-    S.overflow = 1;
+    S.overflow |= OV_PATHS;
     return;
   }
   S.paths[S.npaths++] = p;
@@ -539,7 +546,7 @@ __device__ int get_locations(WS & S, const GR & g, uint32_t pos, const Path & pa
         {
           if (n >= MAXLOC)
           {
-            S.overflow = 1;
+            S.overflow |= OV_LOCS;
             return n;
           }
           S.locs[n++] = Loc{'V', v, vo, pos - vo};
@@ -560,7 +567,7 @@ __device__ void emit_labels(WS & S, const Cand & c, uint32_t a, uint32_t b, bool
   {
     if (wn >= WL_CAP)
     {
-      S.overflow = 1;
+      S.overflow |= OV_LABELS;
       return;
     }
     S.wl[wn++] = DevLabel{st, en, INVALID};
@@ -570,7 +577,7 @@ __device__ void emit_labels(WS & S, const Cand & c, uint32_t a, uint32_t b, bool
   {
     if (wn >= WL_CAP)
     {
-      S.overflow = 1;
+      S.overflow |= OV_LABELS;
       return;
     }
     S.wl[wn++] = DevLabel{st, en, c.vars[k]};
@@ -581,7 +588,7 @@ __device__ __forceinline__ bool cand_add_var(WS & S, Cand & c, uint32_t v)
 {
   if (c.nvar >= CAND_V)
   {
-    S.overflow = 1;
+    S.overflow |= OV_CANDV;
     return false;
   }
   c.vars[c.nvar++] = v;
@@ -597,7 +604,7 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
   int nc = 1;
   uint32_t vb = 0, ve = 0;
   {
-    Cand & c = S.cands[0];
+    Cand & c = cand_at(S, 0);
     c.nvar = 0;
     c.pos = 0;
     if (s.type == 'V')
@@ -639,7 +646,7 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
     }
   }
 
-  if (ve > vb && S.cands[0].len < RL)
+  if (ve > vb && cand_at(S, 0).len < RL)
   {
     uint32_t r = R.var_out_ref[vb];
     bool all_long = false;
@@ -652,11 +659,11 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
       uint32_t const rreach = g.ref_reach(r);
       for (int j = 0; j < orig; ++j)
       {
-        if (S.cands[j].len >= RL)
+        if (cand_at(S, j).len >= RL)
           continue;
         for (uint32_t v = vb; v + 1 < ve; ++v)
         {
-          Cand const & base = S.cands[j];
+          Cand const & base = cand_at(S, j);
           uint32_t const m = g.var_len(v);
           uint32_t mm = base.mm + cmp_fwd(S, koff, RL, base.len, g.var_dna(v), m);
           uint32_t len = base.len + m;
@@ -668,12 +675,12 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
           }
           if (mm <= max_mm)
           {
-            if (nc >= CAND_CAP)
+            if (nc >= CAND_CAP + CAND_SPILL)
             {
-              S.overflow = 1;
+              S.overflow |= OV_CANDS;
               continue;
             }
-            Cand & nw = S.cands[nc];
+            Cand & nw = cand_at(S, nc);
             nw = base;
             if (!cand_add_var(S, nw, v))
               continue;
@@ -697,7 +704,7 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
         // the last allele replaces candidate j in place (or erases it)
         {
           uint32_t const v = ve - 1;
-          Cand & c = S.cands[j];
+          Cand & c = cand_at(S, j);
           uint32_t const m = g.var_len(v);
           uint32_t mm = c.mm + cmp_fwd(S, koff, RL, c.len, g.var_dna(v), m);
           uint32_t len = c.len + m;
@@ -727,7 +734,7 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
           else
           {
             for (int k = j; k + 1 < nc; ++k)
-              S.cands[k] = S.cands[k + 1];
+              cand_at(S, k) = cand_at(S, k + 1);
             --nc;
             --orig;
             --j;
@@ -754,7 +761,7 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
   }
   for (int j = 0; j < nc; ++j)
   {
-    Cand const & c = S.cands[j];
+    Cand const & c = cand_at(S, j);
     if (c.len < RL)
       continue;
     if (c.mm > max_mm)
@@ -776,7 +783,7 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
   int nc = 1;
   uint32_t vb = 0, ve = 0;
   {
-    Cand & c = S.cands[0];
+    Cand & c = cand_at(S, 0);
     c.nvar = 0;
     c.pos = 0;
     if (e.type == 'V')
@@ -824,7 +831,7 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
     }
   }
 
-  if (ve > vb && S.cands[0].len < RL)
+  if (ve > vb && cand_at(S, 0).len < RL)
   {
     uint32_t r = R.var_out_ref[vb] - 1;
     bool all_long = false;
@@ -837,11 +844,11 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
       uint32_t const rorder = R.ref_order[r];
       for (int j = 0; j < orig; ++j)
       {
-        if (S.cands[j].len >= RL)
+        if (cand_at(S, j).len >= RL)
           continue;
         for (uint32_t v = vb; v + 1 < ve; ++v)
         {
-          Cand const & base = S.cands[j];
+          Cand const & base = cand_at(S, j);
           uint32_t const m = g.var_len(v);
           uint32_t mm = base.mm + cmp_bwd(S, RL, base.len, g.var_dna(v), m);
           uint32_t len = base.len + m;
@@ -853,12 +860,12 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
           }
           if (mm <= max_mm)
           {
-            if (nc >= CAND_CAP)
+            if (nc >= CAND_CAP + CAND_SPILL)
             {
-              S.overflow = 1;
+              S.overflow |= OV_CANDS;
               continue;
             }
-            Cand & nw = S.cands[nc];
+            Cand & nw = cand_at(S, nc);
             nw = base;
             if (!cand_add_var(S, nw, v))
               continue;
@@ -881,7 +888,7 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
         }
         {
           uint32_t const v = ve - 1;
-          Cand & c = S.cands[j];
+          Cand & c = cand_at(S, j);
           uint32_t const m = g.var_len(v);
           uint32_t mm = c.mm + cmp_bwd(S, RL, c.len, g.var_dna(v), m);
           uint32_t len = c.len + m;
@@ -911,7 +918,7 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
           else
           {
             for (int k = j; k + 1 < nc; ++k)
-              S.cands[k] = S.cands[k + 1];
+              cand_at(S, k) = cand_at(S, k + 1);
             --nc;
             --orig;
             --j;
@@ -946,7 +953,7 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
   }
   for (int j = 0; j < nc; ++j)
   {
-    Cand const & c = S.cands[j];
+    Cand const & c = cand_at(S, j);
     if (c.len < RL)
       continue;
     if (c.mm < max_mm)
@@ -1143,6 +1150,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParam
         {
           sum.bits |= TS_OVERFLOW;
           ++n_overflow;
+          atomicAdd(&P.counters->reasons[10], 1ull);
         }
         P.summaries[task] = sum;
         if (P.tap.list_count)
@@ -1169,6 +1177,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParam
       if (lane == 0)
       {
         S.overflow = 0;
+        S.cand_spill = static_cast<Cand *>(P.cand_spill) + (size_t)(blockIdx.x * WARPS_PER_BLOCK + wib) * CAND_SPILL;
         S.npaths = 0;
         S.npp = 0;
         S.longest = 0;
@@ -1208,7 +1217,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParam
           nk = expand_keys(S.seq + 31 * i, keys, (int)(sizeof(Path) * MAXP * 2 / sizeof(uint64_t)));
           if (nk < 0)
           {
-            S.overflow = 1;
+            S.overflow |= OV_KEYS;
             nk = 0;
           }
         }
@@ -1225,7 +1234,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParam
         if (nrefs + cnt > REF_CAP)
         {
           if (lane == 0)
-            S.overflow = 1;
+            S.overflow |= OV_REFS;
         }
         else
         {
@@ -1260,7 +1269,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParam
         unsigned long long base = atomicAdd(&P.counters->dbg_label_words, (unsigned long long)tot);
         if (base + tot > P.tap.pool_cap)
         {
-          S.overflow = 1;
+          S.overflow |= OV_TAP;
           for (int l = 0; l < NLISTS; ++l)
             P.tap.list_count[(size_t)task * NLISTS + l] = 0;
         }
@@ -1378,6 +1387,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParam
       {
         sum.bits |= TS_OVERFLOW;
         ++n_overflow;
+        for (int q = 0; q < 12; ++q)
+          if ((S.overflow >> q) & 1u)
+            atomicAdd(&P.counters->reasons[q], 1ull);
         S.npaths = 0;
         S.longest = 0;
       }
@@ -1411,6 +1423,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParam
           sum.bits |= TS_OVERFLOW;
           sum.npaths = 0;
           ++n_overflow;
+          atomicAdd(&P.counters->reasons[9], 1ull);
         }
         else
         {
@@ -1833,6 +1846,15 @@ int align_kernel_blocks_per_sm()
     g_align_blocks_per_sm = nb;
   }
   return g_align_blocks_per_sm;
+}
+
+size_t align_spill_bytes()
+{
+  int const bps = align_kernel_blocks_per_sm();
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (size_t)sms * bps * WARPS_PER_BLOCK * CAND_SPILL * sizeof(Cand);
 }
 
 void launch_align(const LaunchParams & p, void * stream)
