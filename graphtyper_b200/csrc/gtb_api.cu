@@ -119,13 +119,13 @@ struct Ctx
 {
   int device = -1;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::map<int, std::unique_ptr<Region>> regions;
   std::vector<int> slot_region; // slot -> region id (-1 free)
   DeviceBuffer d_regions;       // DevRegion table
   bool regions_dirty = true;
   // batch
-  DeviceBuffer d_batch, d_summaries, d_pool, d_counters, d_tap_counts, d_tap_pool, d_spill;
+  DeviceBuffer d_batch, d_summaries, d_pool, d_counters, d_tap_counts, d_tap_pool, d_spill, d_seedrecs, d_slow;
   PinnedBuffer h_batch, h_counters;
   LaunchParams last{};
   bool have_last = false;
@@ -134,7 +134,8 @@ struct Ctx
   std::vector<int> last_regions; // region ids of the last submit, in batch order
   std::vector<uint32_t> last_unit_begin; // per region of the last submit: first unit index (size n+1)
   std::vector<uint32_t> last_rec_begin;
-  float t_h2d = 0, t_align = 0, t_score = 0, t_d2h = 0;
+  float t_h2d = 0, t_align = 0, t_score = 0, t_d2h = 0, t_probe = 0, t_chain = 0, t_slow = 0;
+  unsigned long long last_n_slow = 0;
   // nccl (loaded lazily with dlopen, see gtb_nccl.cpp part below)
   void * nccl_lib = nullptr;
   void * nccl_comm = nullptr;
@@ -224,7 +225,7 @@ int gtb_create(int device_id, gtb_ctx ** out)
     e = cudaSetDevice(device_id);
     if (e == cudaSuccess)
       e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i)
       e = cudaEventCreate(&c->ev[i]);
     if (e != cudaSuccess)
     {
@@ -259,6 +260,8 @@ void gtb_destroy(gtb_ctx * ctx)
     c->d_tap_counts.release();
     c->d_tap_pool.release();
     c->d_spill.release();
+    c->d_seedrecs.release();
+    c->d_slow.release();
     c->h_batch.release();
     c->h_counters.release();
     for (auto & e : c->ev)
@@ -526,8 +529,14 @@ static int run_kernels(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
 {
   LaunchParams & P = c->last;
   CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, sizeof(DevCounters), c->stream));
+  // orientations that are not aligned keep an all-zero summary (no paths)
+  CUDA_TRY(cudaMemsetAsync(P.summaries, 0, (size_t)P.batch.n_units * 2 * sizeof(TaskSummary), c->stream));
   CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-  launch_align(P, c->stream);
+  launch_probe(P, c->stream);
+  CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+  launch_chain(P, c->stream);
+  CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
+  launch_slow(P, c->stream);
   CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
   launch_score(P, c->stream);
   CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
@@ -538,18 +547,22 @@ static int run_kernels(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
   if (record_h2d)
     cudaEventElapsedTime(&c->t_h2d, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->t_align, c->ev[1], c->ev[2]);
+  cudaEventElapsedTime(&c->t_probe, c->ev[1], c->ev[5]);
+  cudaEventElapsedTime(&c->t_chain, c->ev[5], c->ev[6]);
+  cudaEventElapsedTime(&c->t_slow, c->ev[6], c->ev[2]);
   cudaEventElapsedTime(&c->t_score, c->ev[2], c->ev[3]);
   cudaEventElapsedTime(&c->t_d2h, c->ev[3], c->ev[4]);
   DevCounters const * k = static_cast<DevCounters *>(c->h_counters.p);
+  c->last_n_slow = k->n_slow;
   if (stats)
   {
     stats->n_records = P.batch.n_records;
     stats->n_alignments = P.batch.n_units;
-    stats->n_oriented = k->n_oriented;
+    stats->n_oriented = P.n_active;
     stats->n_pairs_scored = k->n_pairs_scored;
     stats->n_singles_scored = k->n_singles_scored;
     stats->n_capacity_overflow = k->n_overflow;
-    stats->kernel_launches = (P.batch.n_units ? 1 : 0) + (P.batch.n_records ? 1 : 0);
+    stats->kernel_launches = (P.n_active ? 3 : 0) + (P.batch.n_records ? 1 : 0);
   }
   if (k->n_input_error)
     return fail(GTB_ERR_INPUT, "two mates with the same IS_FIRST_IN_PAIR flag (the reference aborts here, "
@@ -611,6 +624,7 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   size_t const o_mate = place<int32_t>(off, total);
   size_t const o_unit = place<int32_t>(off, total);
   size_t const o_urec = place<int32_t>(off, total);
+  size_t const o_active = place<uint32_t>(off, total * 2);
   size_t const bytes = align_up(off, 256);
   if (int rc = c->h_batch.reserve(bytes))
     return rc;
@@ -671,7 +685,36 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
     c->last_rec_begin.push_back((uint32_t)base);
   }
 
+  // ---- read orientations that are aligned at all (align_read, src/typer/alignment.cpp:331-363):
+  //      forward always; reverse complement unless unpaired or a properly oriented pair within 1200 bp
+  uint32_t * h_active = reinterpret_cast<uint32_t *>(h + o_active);
+  uint32_t n_active = 0;
+  {
+    const uint16_t * hl = reinterpret_cast<const uint16_t *>(h + o_lseq);
+    const uint16_t * hf = reinterpret_cast<const uint16_t *>(h + o_flag);
+    const int32_t * hi = reinterpret_cast<const int32_t *>(h + o_isize);
+    const uint8_t * hs = h + o_same;
+    for (uint32_t u = 0; u < n_units; ++u)
+    {
+      int32_t const r = h_urec[u];
+      uint16_t const L = hl[r], flag = hf[r];
+      if (L > (uint16_t)MAX_SEQ)
+        return fail(GTB_ERR_CAPACITY, "read longer than 152 bases (reference MAX_READ_LENGTH is 151)");
+      if (L < 63)
+        continue; // hard restriction of align_read (2 * K - 1)
+      h_active[n_active++] = u * 2;
+      bool const fwd_only = (flag & 1u) == 0 ||
+                            (hs[r] && hi[r] > -1200 && hi[r] < 1200 && (((flag & 16u) != 0) != ((flag & 32u) != 0)));
+      if (!fwd_only)
+        h_active[n_active++] = u * 2 + 1;
+    }
+  }
+
   uint32_t const n_tasks = n_units * 2;
+  if (int rc = c->d_seedrecs.reserve((size_t)n_active * SEED_REC_BYTES + 64))
+    return rc;
+  if (int rc = c->d_slow.reserve((size_t)n_active * 4 + 64))
+    return rc;
   if (int rc = c->d_batch.reserve(bytes))
     return rc;
   if (int rc = c->d_summaries.reserve((size_t)n_tasks * sizeof(TaskSummary) + 16))
@@ -713,6 +756,10 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   P.path_pool_cap = pool_words;
   P.counters = static_cast<DevCounters *>(c->d_counters.p);
   P.cand_spill = c->d_spill.p;
+  P.n_active = n_active;
+  P.active_tasks = reinterpret_cast<const uint32_t *>(d + o_active);
+  P.seed_recs = c->d_seedrecs.p;
+  P.slow_tasks = static_cast<uint32_t *>(c->d_slow.p);
   if (c->debug)
   {
     size_t const tap_counts = (size_t)n_tasks * (NLISTS * 2 + 1) * 4;
@@ -760,6 +807,24 @@ int gtb_last_timing(gtb_ctx * ctx, float * h2d_ms, float * align_ms, float * sco
     *score_ms = c->t_score;
   if (d2h_ms)
     *d2h_ms = c->t_d2h;
+  return 0;
+}
+
+// Per-kernel device times (ms) of the last submit/replay and the number of tasks the slow kernel handled.
+int gtb_last_kernel_timing(gtb_ctx * ctx, float * probe_ms, float * chain_ms, float * slow_ms, float * score_ms,
+                           uint64_t * n_slow)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (probe_ms)
+    *probe_ms = c->t_probe;
+  if (chain_ms)
+    *chain_ms = c->t_chain;
+  if (slow_ms)
+    *slow_ms = c->t_slow;
+  if (score_ms)
+    *score_ms = c->t_score;
+  if (n_slow)
+    *n_slow = c->last_n_slow;
   return 0;
 }
 

@@ -20,6 +20,12 @@ constexpr int CAND_V = 16;    // var nodes per candidate
 constexpr int MAXLOC = 8;     // graph locations of a position (reference limit: 256)
 constexpr int WL_CAP = 96;    // labels staged by one walk_read_starts/ends call
 constexpr int MAX_SEQ = 152;  // bases per read (GTB_SEQ_STRIDE * 2)
+// chain_kernel (one thread per read orientation, working set in local memory) -- small capacities, overflow -> slow_kernel
+constexpr int FAST_P = 6, FAST_V = 8, FAST_C = 6, FAST_CV = 8, FAST_WL = 12, FAST_LOC = 4;
+constexpr int SEED_INLINE = 10;     // index bucket references handed from probe_kernel to chain_kernel per task
+constexpr int SEED_REC_BYTES = 16 + 8 * SEED_INLINE;
+constexpr int PROBE_WARPS = 8;      // warps per block of probe_kernel
+constexpr int CHAIN_THREADS = 128;  // threads per block of chain_kernel
 constexpr int MAX_TOUCH = 16; // bubbles touched by one read in the accumulate kernel
 using allele_mask_t = uint32_t; // allele set of one bubble on a path: bit a = allele a  (<= 32 alleles per bubble)
 constexpr int MAX_ALLELES = 32;
@@ -116,7 +122,7 @@ struct DevCounters
   unsigned long long n_overflow;
   unsigned long long n_input_error;  // mates with equal IS_FIRST_IN_PAIR
   unsigned long long dbg_label_words; // bump cursor of the debug seed pool
-  unsigned long long n_touch_overflow;
+  unsigned long long n_slow;         // tasks queued for slow_kernel
   unsigned long long reasons[12];    // overflow histogram: refs vars paths locs labels candv cands keys tap pool len -
 };
 
@@ -140,10 +146,16 @@ struct LaunchParams
   DevCounters * counters;
   DevSeedTap tap; // tap.list_count == nullptr when disabled
   void * cand_spill; // per-resident-warp global extension of the bubble-expansion candidate list
+  uint32_t n_active;            // read orientations that are actually aligned (align_read, alignment.cpp:331-363)
+  const uint32_t * active_tasks; // [n_active] task id = unit * 2 + orientation
+  void * seed_recs;             // [n_active] SeedRec
+  uint32_t * slow_tasks;        // [n_active] queue filled by chain_kernel
 };
 
 // host launchers (gtb_kernels.cu)
-void launch_align(const LaunchParams & p, void * stream);
+void launch_probe(const LaunchParams & p, void * stream);
+void launch_chain(const LaunchParams & p, void * stream);
+void launch_slow(const LaunchParams & p, void * stream);
 void launch_score(const LaunchParams & p, void * stream);
 int align_kernel_blocks_per_sm();
 size_t align_spill_bytes();

@@ -38,57 +38,93 @@ constexpr uint32_t INVALID = 0xFFFFFFFFu;
 constexpr uint32_t SPECIAL_START = 0xD0000000u;
 constexpr uint16_t F_PAIRED = 1, F_PROPER = 2, F_REV = 16, F_MREV = 32, F_FIRST = 64, F_MAPQ_BAD = 4096;
 
-struct Path
-{
-  uint32_t start, end;
-  uint16_t rs, re, mm, nvar;
-  uint32_t order[MAXV];
-  allele_mask_t mask[MAXV];
-};
-
-struct Cand
-{
-  uint32_t len;
-  uint32_t pos;
-  uint32_t mm;
-  uint32_t nvar;
-  uint32_t vars[CAND_V];
-};
-
 struct Loc
 {
   uint32_t type; // 'R' or 'V'
   uint32_t node, order, offset;
 };
 
-struct WS
+__device__ __forceinline__ uint8_t comp4(uint8_t c) // seqan TranslateTableIupacToIupacComplement_: 4-bit reversal
 {
-  Path paths[MAXP];
-  Path pp[MAXP];
+  return (uint8_t)(((c & 1) << 3) | ((c & 2) << 1) | ((c & 4) >> 1) | ((c & 8) >> 3));
+}
+
+// seqan Iupac value -> char "UACMGRSVTWYHKDBN" (alphabet_residue_tabs.h:222-240) without a memory lookup
+__device__ __forceinline__ uint8_t iupac_char(uint8_t c)
+{
+  uint64_t const lo = 0x565352474D434155ull; // "UACMGRSV" little endian
+  uint64_t const hi = 0x4E42444B48595754ull; // "TWYHKDBN"
+  return (uint8_t)(((c < 8 ? lo : hi) >> (8 * (c & 7))) & 0xFF);
+}
+
+// Working set of one read orientation during chaining / extension / filtering.  Two instantiations:
+//   SlowState : big capacities, lives in shared memory, one warp per task (lane 0 runs the scalar logic)
+//   FastState : small capacities, lives in per-thread local memory, one THREAD per task (32 tasks per warp);
+//               a task that exceeds a small capacity is re-run by the slow kernel.
+template <int P_, int V_, int C_, int CV_, int WL_, int LOC_>
+struct StateT
+{
+  static constexpr int MAXP = P_, MAXV = V_, CANDS = C_, CANDV = CV_, WLCAP = WL_, MAXLOC = LOC_;
+  struct Path
+  {
+    uint32_t start, end;
+    uint16_t rs, re, mm, nvar;
+    uint32_t order[V_];
+    allele_mask_t mask[V_];
+  };
+  struct Cand
+  {
+    uint32_t len;
+    uint32_t pos;
+    uint32_t mm;
+    uint32_t nvar;
+    uint32_t vars[CV_];
+  };
+  Path paths[P_];
+  Path pp[P_];
   Path op, np;
-  Cand cands[CAND_CAP];
-  DevLabel wl[WL_CAP];
-  uint2 refs[REF_CAP];
-  Loc locs[MAXLOC];
-  uint16_t list_start[NLISTS + 1];
-  uint16_t wl_list_start[MAXP + 1];
-  uint16_t wl_list_idx[MAXP];
-  uint8_t matched[MAXP];
-  uint8_t seq[MAX_SEQ + 8]; // 4-bit codes in phase A, IUPAC characters afterwards
-  Cand * cand_spill;        // this warp's global-memory extension of cands[] (CAND_SPILL entries)
+  Cand cands[C_];
+  DevLabel wl[WL_];
+  Loc locs[LOC_];
+  uint16_t wl_list_start[P_ + 1];
+  uint16_t wl_list_idx[P_];
+  uint8_t matched[P_];
   int npaths, npp;
   uint32_t longest;
   uint32_t overflow;
 };
 
-// candidate i of the bubble expansion: the first CAND_CAP live in shared memory, the (rare) rest in a per-warp
-// global scratch area, so that the reference's limit of 128 open candidates (+ one round of growth) fits
-__device__ __forceinline__ Cand & cand_at(WS & S, int i) { return i < CAND_CAP ? S.cands[i] : S.cand_spill[i - CAND_CAP]; }
-
-__device__ __forceinline__ uint8_t comp4(uint8_t c) // seqan TranslateTableIupacToIupacComplement_: 4-bit reversal
+struct SlowState : StateT<MAXP, MAXV, CAND_CAP, CAND_V, WL_CAP, MAXLOC>
 {
-  return (uint8_t)(((c & 1) << 3) | ((c & 2) << 1) | ((c & 4) >> 1) | ((c & 8) >> 3));
-}
+  static constexpr int CAND_TOTAL = CAND_CAP + CAND_SPILL;
+  uint2 refs[REF_CAP];
+  uint16_t list_start[NLISTS + 1];
+  uint8_t seq[MAX_SEQ + 8]; // 4-bit codes in phase A, IUPAC characters afterwards
+  Cand * cand_spill;        // this warp's global-memory extension of cands[] (CAND_SPILL entries)
+  __device__ __forceinline__ uint8_t rd(int j) const { return seq[j]; }
+  // candidate i of the bubble expansion: the first CAND_CAP live in shared memory, the (rare) rest in a per-warp
+  // global scratch area, so that the reference's limit of 128 open candidates (+ one round of growth) fits
+  __device__ __forceinline__ Cand & cand_at(int i) { return i < CAND_CAP ? cands[i] : cand_spill[i - CAND_CAP]; }
+};
+
+struct FastState : StateT<FAST_P, FAST_V, FAST_C, FAST_CV, FAST_WL, FAST_LOC>
+{
+  static constexpr int CAND_TOTAL = FAST_C;
+  const uint8_t * s4; // packed 4-bit read
+  int L, orient;
+  __device__ __forceinline__ uint8_t rd(int j) const
+  {
+    int const src = orient ? (L - 1 - j) : j;
+    uint8_t const b = __ldg(s4 + (src >> 1));
+    uint8_t c = (src & 1) ? (b & 15) : (b >> 4);
+    if (orient)
+      c = comp4(c);
+    return iupac_char(c);
+  }
+  __device__ __forceinline__ Cand & cand_at(int i) { return cands[i]; }
+};
+
+using WS = SlowState;
 
 __device__ __constant__ char IUPAC_CHAR[17] = "UACMGRSVTWYHKDBN";
 
@@ -240,9 +276,11 @@ __device__ int expand_keys(const uint8_t * codes, uint64_t * keys, int cap)
 }
 
 // ------------------------------------------------------------------------------------------------ phase B: chaining
-__device__ __forceinline__ uint32_t psize(const Path & p) { return (uint32_t)p.re - p.rs + 1u; }
+template <class PathT>
+__device__ __forceinline__ uint32_t psize(const PathT & p) { return (uint32_t)p.re - p.rs + 1u; }
 
-__device__ void merge_with_current(WS & S, const GR & g, Path & p, const DevLabel & l) // path.cpp:105-129
+template <class W>
+__device__ void merge_with_current(W & S, const GR & g, typename W::Path & p, const DevLabel & l) // path.cpp:105-129
 {
   if (l.var == INVALID)
     return;
@@ -254,7 +292,7 @@ __device__ void merge_with_current(WS & S, const GR & g, Path & p, const DevLabe
       p.mask[i] |= bit;
       return;
     }
-  if (p.nvar >= MAXV)
+  if (p.nvar >= W::MAXV)
   {
     S.overflow |= OV_VARS;
     return;
@@ -265,7 +303,8 @@ __device__ void merge_with_current(WS & S, const GR & g, Path & p, const DevLabe
 }
 
 // find_all_nonduplicated_paths, one label at a time (genotype_paths.cpp:32-66)
-__device__ void pp_add_label(WS & S, const GR & g, const DevLabel & l, uint16_t rs, uint16_t re, uint16_t mm)
+template <class W>
+__device__ void pp_add_label(W & S, const GR & g, const DevLabel & l, uint16_t rs, uint16_t re, uint16_t mm)
 {
   for (int d = 0; d < S.npp; ++d)
     if (S.pp[d].start == l.start && S.pp[d].end == l.end)
@@ -273,12 +312,12 @@ __device__ void pp_add_label(WS & S, const GR & g, const DevLabel & l, uint16_t 
       merge_with_current(S, g, S.pp[d], l);
       return;
     }
-  if (S.npp >= MAXP)
+  if (S.npp >= W::MAXP)
   {
     S.overflow |= OV_PATHS;
     return;
   }
-  Path & p = S.pp[S.npp++];
+  typename W::Path & p = S.pp[S.npp++];
   p.start = l.start;
   p.end = l.end;
   p.rs = rs;
@@ -294,7 +333,8 @@ __device__ void pp_add_label(WS & S, const GR & g, const DevLabel & l, uint16_t 
 }
 
 // Path(p1, p2) (path.cpp:38-82); false = empty allele intersection (the caller drops the merge)
-__device__ bool merge_paths(WS & S, const Path & p1, const Path & p2, Path & out)
+template <class W>
+__device__ bool merge_paths(W & S, const typename W::Path & p1, const typename W::Path & p2, typename W::Path & out)
 {
   out = p2;
   for (int i = 0; i < p1.nvar; ++i)
@@ -311,7 +351,7 @@ __device__ bool merge_paths(WS & S, const Path & p1, const Path & p2, Path & out
       }
     if (!found)
     {
-      if (out.nvar >= MAXV)
+      if (out.nvar >= W::MAXV)
       {
         S.overflow |= OV_VARS;
         return false;
@@ -327,9 +367,10 @@ __device__ bool merge_paths(WS & S, const Path & p1, const Path & p2, Path & out
   return true;
 }
 
-__device__ void push_path(WS & S, const Path & p)
+template <class W>
+__device__ void push_path(W & S, const typename W::Path & p)
 {
-  if (S.npaths >= MAXP)
+  if (S.npaths >= W::MAXP)
   {
     S.overflow |= OV_PATHS;
     return;
@@ -338,7 +379,8 @@ __device__ void push_path(WS & S, const Path & p)
 }
 
 // second half of add_next_kmer_labels (genotype_paths.cpp:308-351): S.pp holds the grouped new labels
-__device__ void add_next(WS & S, uint32_t rs)
+template <class W>
+__device__ void add_next(W & S, uint32_t rs)
 {
   int const orig = S.npaths;
   for (int j = 0; j < S.npp; ++j)
@@ -375,7 +417,8 @@ __device__ void add_next(WS & S, uint32_t rs)
 }
 
 // second half of add_prev_kmer_labels (genotype_paths.cpp:247-291)
-__device__ void add_prev(WS & S, uint32_t re)
+template <class W>
+__device__ void add_prev(W & S, uint32_t re)
 {
   int const orig = S.npaths;
   for (int j = 0; j < S.npp; ++j)
@@ -412,7 +455,8 @@ __device__ void add_prev(WS & S, uint32_t re)
 }
 
 // ------------------------------------------------------------------------------------------------ filters
-__device__ void remove_short_paths(WS & S) // genotype_paths.cpp:824-834
+template <class W>
+__device__ void remove_short_paths(W & S) // genotype_paths.cpp:824-834
 {
   if (S.longest <= 1)
     return;
@@ -427,7 +471,8 @@ __device__ void remove_short_paths(WS & S) // genotype_paths.cpp:824-834
   S.npaths = w;
 }
 
-__device__ void update_longest(WS & S)
+template <class W>
+__device__ void update_longest(W & S)
 {
   uint32_t L = 0;
   for (int i = 0; i < S.npaths; ++i)
@@ -435,7 +480,8 @@ __device__ void update_longest(WS & S)
   S.longest = L;
 }
 
-__device__ bool all_paths_unique(const WS & S, const GR & g) // genotype_paths.cpp:219-231
+template <class W>
+__device__ bool all_paths_unique(const W & S, const GR & g) // genotype_paths.cpp:219-231
 {
   for (int i = 1; i < S.npaths; ++i)
     if (g.ref_reach_pos(S.paths[0].start) != g.ref_reach_pos(S.paths[i].start) &&
@@ -444,7 +490,8 @@ __device__ bool all_paths_unique(const WS & S, const GR & g) // genotype_paths.c
   return true;
 }
 
-__device__ bool path_is_reference(const Path & p)
+template <class PathT>
+__device__ bool path_is_reference(const PathT & p)
 {
   for (int i = 0; i < p.nvar; ++i)
     if ((p.mask[i] & 1u) == 0)
@@ -454,16 +501,17 @@ __device__ bool path_is_reference(const Path & p)
 
 // ------------------------------------------------------------------------------------------------ phase C: graph walk
 // mismatches between read[koff + have + i] and dna[i] (graph_utils.hpp:7-37); BIGMM when the graph has '<' or '>'
-__device__ uint32_t cmp_fwd(const WS & S, int koff, uint32_t RL, uint32_t have, const uint8_t * dna, uint32_t n)
+template <class W>
+__device__ uint32_t cmp_fwd(const W & S, int koff, uint32_t RL, uint32_t have, const uint8_t * dna, uint32_t n)
 {
   if (have >= RL)
     return 0;
   uint32_t const m = min(n, RL - have);
   uint32_t mm = 0;
-  const uint8_t * rd = S.seq + koff + have;
+  int const r0 = koff + (int)have;
   for (uint32_t i = 0; i < m; ++i)
   {
-    uint8_t const gc = dna[i], rc = rd[i];
+    uint8_t const gc = dna[i], rc = S.rd(r0 + (int)i);
     if (gc == '>' || gc == '<')
       return BIGMM;
     mm += (gc != rc && rc != 'N' && gc != 'N');
@@ -472,7 +520,8 @@ __device__ uint32_t cmp_fwd(const WS & S, int koff, uint32_t RL, uint32_t have, 
 }
 
 // backward: the k-mer is read[0 .. RL), the candidate already covers its last `have` bases (graph_utils.hpp:39-69)
-__device__ uint32_t cmp_bwd(const WS & S, uint32_t RL, uint32_t have, const uint8_t * dna, uint32_t n)
+template <class W>
+__device__ uint32_t cmp_bwd(const W & S, uint32_t RL, uint32_t have, const uint8_t * dna, uint32_t n)
 {
   if (have >= RL)
     return 0;
@@ -480,7 +529,7 @@ __device__ uint32_t cmp_bwd(const WS & S, uint32_t RL, uint32_t have, const uint
   uint32_t mm = 0;
   for (uint32_t i = 0; i < m; ++i)
   {
-    uint8_t const gc = dna[n - 1 - i], rc = S.seq[RL - 1 - have - i];
+    uint8_t const gc = dna[n - 1 - i], rc = S.rd((int)(RL - 1 - have - i));
     if (gc == '>' || gc == '<')
       return BIGMM;
     mm += (gc != rc && rc != 'N' && gc != 'N');
@@ -489,7 +538,8 @@ __device__ uint32_t cmp_bwd(const WS & S, uint32_t RL, uint32_t have, const uint
 }
 
 // Graph::get_locations_of_a_position (graph.cpp:931-1029,1154-1185) -> S.locs; returns count
-__device__ int get_locations(WS & S, const GR & g, uint32_t pos, const Path & path)
+template <class W>
+__device__ int get_locations(W & S, const GR & g, uint32_t pos, const typename W::Path & path)
 {
   const DevRegion & R = g.R;
   bool const sp = g.is_special(pos);
@@ -544,7 +594,7 @@ __device__ int get_locations(WS & S, const GR & g, uint32_t pos, const Path & pa
           continue;
         if (path_empty || ((path.mask[j] >> (v - vb)) & 1u))
         {
-          if (n >= MAXLOC)
+          if (n >= W::MAXLOC)
           {
             S.overflow |= OV_LOCS;
             return n;
@@ -558,14 +608,15 @@ __device__ int get_locations(WS & S, const GR & g, uint32_t pos, const Path & pa
   return n;
 }
 
-__device__ void emit_labels(WS & S, const Cand & c, uint32_t a, uint32_t b, bool cand_is_end, int & wn)
+template <class W>
+__device__ void emit_labels(W & S, const typename W::Cand & c, uint32_t a, uint32_t b, bool cand_is_end, int & wn)
 {
   // forward walk: (start = a fixed, end = cand.pos); backward: (start = cand.pos, end = b fixed)
   uint32_t const st = cand_is_end ? a : c.pos;
   uint32_t const en = cand_is_end ? c.pos : b;
   if (c.nvar == 0)
   {
-    if (wn >= WL_CAP)
+    if (wn >= W::WLCAP)
     {
       S.overflow |= OV_LABELS;
       return;
@@ -575,7 +626,7 @@ __device__ void emit_labels(WS & S, const Cand & c, uint32_t a, uint32_t b, bool
   }
   for (uint32_t k = 0; k < c.nvar; ++k)
   {
-    if (wn >= WL_CAP)
+    if (wn >= W::WLCAP)
     {
       S.overflow |= OV_LABELS;
       return;
@@ -584,9 +635,10 @@ __device__ void emit_labels(WS & S, const Cand & c, uint32_t a, uint32_t b, bool
   }
 }
 
-__device__ __forceinline__ bool cand_add_var(WS & S, Cand & c, uint32_t v)
+template <class W>
+__device__ __forceinline__ bool cand_add_var(W & S, typename W::Cand & c, uint32_t v)
 {
-  if (c.nvar >= CAND_V)
+  if (c.nvar >= W::CANDV)
   {
     S.overflow |= OV_CANDV;
     return false;
@@ -597,14 +649,15 @@ __device__ __forceinline__ bool cand_add_var(WS & S, Cand & c, uint32_t v)
 
 // Graph::get_labels_forward (graph.cpp:1187-1439). Candidate sequences are never materialised: a candidate is
 // (length so far, mismatches so far, var nodes, end position); mismatches are additive over appended nodes.
-__device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, uint32_t RL, uint32_t & max_mm, int & wn)
+template <class W>
+__device__ void labels_forward(W & S, const GR & g, const Loc & s, int koff, uint32_t RL, uint32_t & max_mm, int & wn)
 {
   const DevRegion & R = g.R;
   int const w0 = wn;
   int nc = 1;
   uint32_t vb = 0, ve = 0;
   {
-    Cand & c = cand_at(S, 0);
+    typename W::Cand & c = S.cand_at(0);
     c.nvar = 0;
     c.pos = 0;
     if (s.type == 'V')
@@ -646,7 +699,7 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
     }
   }
 
-  if (ve > vb && cand_at(S, 0).len < RL)
+  if (ve > vb && S.cand_at(0).len < RL)
   {
     uint32_t r = R.var_out_ref[vb];
     bool all_long = false;
@@ -659,11 +712,11 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
       uint32_t const rreach = g.ref_reach(r);
       for (int j = 0; j < orig; ++j)
       {
-        if (cand_at(S, j).len >= RL)
+        if (S.cand_at(j).len >= RL)
           continue;
         for (uint32_t v = vb; v + 1 < ve; ++v)
         {
-          Cand const & base = cand_at(S, j);
+          typename W::Cand const & base = S.cand_at(j);
           uint32_t const m = g.var_len(v);
           uint32_t mm = base.mm + cmp_fwd(S, koff, RL, base.len, g.var_dna(v), m);
           uint32_t len = base.len + m;
@@ -675,12 +728,12 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
           }
           if (mm <= max_mm)
           {
-            if (nc >= CAND_CAP + CAND_SPILL)
+            if (nc >= W::CAND_TOTAL)
             {
               S.overflow |= OV_CANDS;
               continue;
             }
-            Cand & nw = cand_at(S, nc);
+            typename W::Cand & nw = S.cand_at(nc);
             nw = base;
             if (!cand_add_var(S, nw, v))
               continue;
@@ -704,7 +757,7 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
         // the last allele replaces candidate j in place (or erases it)
         {
           uint32_t const v = ve - 1;
-          Cand & c = cand_at(S, j);
+          typename W::Cand & c = S.cand_at(j);
           uint32_t const m = g.var_len(v);
           uint32_t mm = c.mm + cmp_fwd(S, koff, RL, c.len, g.var_dna(v), m);
           uint32_t len = c.len + m;
@@ -734,7 +787,7 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
           else
           {
             for (int k = j; k + 1 < nc; ++k)
-              cand_at(S, k) = cand_at(S, k + 1);
+              S.cand_at(k) = S.cand_at(k + 1);
             --nc;
             --orig;
             --j;
@@ -761,7 +814,7 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
   }
   for (int j = 0; j < nc; ++j)
   {
-    Cand const & c = cand_at(S, j);
+    typename W::Cand const & c = S.cand_at(j);
     if (c.len < RL)
       continue;
     if (c.mm > max_mm)
@@ -776,14 +829,15 @@ __device__ void labels_forward(WS & S, const GR & g, const Loc & s, int koff, ui
 }
 
 // Graph::get_labels_backward (graph.cpp:1441-1701)
-__device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL, uint32_t & max_mm, int & wn)
+template <class W>
+__device__ void labels_backward(W & S, const GR & g, const Loc & e, uint32_t RL, uint32_t & max_mm, int & wn)
 {
   const DevRegion & R = g.R;
   int const w0 = wn;
   int nc = 1;
   uint32_t vb = 0, ve = 0;
   {
-    Cand & c = cand_at(S, 0);
+    typename W::Cand & c = S.cand_at(0);
     c.nvar = 0;
     c.pos = 0;
     if (e.type == 'V')
@@ -831,7 +885,7 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
     }
   }
 
-  if (ve > vb && cand_at(S, 0).len < RL)
+  if (ve > vb && S.cand_at(0).len < RL)
   {
     uint32_t r = R.var_out_ref[vb] - 1;
     bool all_long = false;
@@ -844,11 +898,11 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
       uint32_t const rorder = R.ref_order[r];
       for (int j = 0; j < orig; ++j)
       {
-        if (cand_at(S, j).len >= RL)
+        if (S.cand_at(j).len >= RL)
           continue;
         for (uint32_t v = vb; v + 1 < ve; ++v)
         {
-          Cand const & base = cand_at(S, j);
+          typename W::Cand const & base = S.cand_at(j);
           uint32_t const m = g.var_len(v);
           uint32_t mm = base.mm + cmp_bwd(S, RL, base.len, g.var_dna(v), m);
           uint32_t len = base.len + m;
@@ -860,12 +914,12 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
           }
           if (mm <= max_mm)
           {
-            if (nc >= CAND_CAP + CAND_SPILL)
+            if (nc >= W::CAND_TOTAL)
             {
               S.overflow |= OV_CANDS;
               continue;
             }
-            Cand & nw = cand_at(S, nc);
+            typename W::Cand & nw = S.cand_at(nc);
             nw = base;
             if (!cand_add_var(S, nw, v))
               continue;
@@ -888,7 +942,7 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
         }
         {
           uint32_t const v = ve - 1;
-          Cand & c = cand_at(S, j);
+          typename W::Cand & c = S.cand_at(j);
           uint32_t const m = g.var_len(v);
           uint32_t mm = c.mm + cmp_bwd(S, RL, c.len, g.var_dna(v), m);
           uint32_t len = c.len + m;
@@ -918,7 +972,7 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
           else
           {
             for (int k = j; k + 1 < nc; ++k)
-              cand_at(S, k) = cand_at(S, k + 1);
+              S.cand_at(k) = S.cand_at(k + 1);
             --nc;
             --orig;
             --j;
@@ -953,7 +1007,7 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
   }
   for (int j = 0; j < nc; ++j)
   {
-    Cand const & c = cand_at(S, j);
+    typename W::Cand const & c = S.cand_at(j);
     if (c.len < RL)
       continue;
     if (c.mm < max_mm)
@@ -968,7 +1022,8 @@ __device__ void labels_backward(WS & S, const GR & g, const Loc & e, uint32_t RL
 }
 
 // walk_read_ends (forward = true, genotype_paths.cpp:483-553) / walk_read_starts (forward = false, :555-621)
-__device__ void walk(WS & S, const GR & g, uint32_t L, bool forward)
+template <class W>
+__device__ void walk(W & S, const GR & g, uint32_t L, bool forward)
 {
   if (S.npaths == 0 || psize(S.paths[0]) == L)
     return;
@@ -979,7 +1034,7 @@ __device__ void walk(WS & S, const GR & g, uint32_t L, bool forward)
   S.wl_list_start[0] = 0;
   for (int pi = 0; pi < S.npaths; ++pi)
   {
-    Path const & p = S.paths[pi];
+    typename W::Path const & p = S.paths[pi];
     uint32_t klen;
     int koff = 0;
     int nloc;
@@ -1070,11 +1125,12 @@ __device__ void walk(WS & S, const GR & g, uint32_t L, bool forward)
 }
 
 // remove_support_from_read_ends (genotype_paths.cpp:382-430), SV graphs only
-__device__ void remove_support_from_read_ends(WS & S, const GR & g)
+template <class W>
+__device__ void remove_support_from_read_ends(W & S, const GR & g)
 {
   for (int pi = 0; pi < S.npaths; ++pi)
   {
-    Path & p = S.paths[pi];
+    typename W::Path & p = S.paths[pi];
     if (p.nvar == 0)
       continue;
     if (!g.is_special(p.start) && !g.is_special(p.end))
@@ -1104,8 +1160,405 @@ __device__ void remove_support_from_read_ends(WS & S, const GR & g)
 
 } // namespace
 
-// ================================================================================================ align kernel
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParams P)
+// ================================================================================================ task body (B..D)
+namespace
+{
+// Phases B-D for one read orientation: chain the seed lists, extend both ends, filter (alignment.cpp:35-87).
+// refs / list_start describe the 2*nslots seed lists as index bucket references in PHIndex::multi_get order.
+template <class W>
+__device__ void run_task(W & S, const GR & g, const uint2 * refs, const uint16_t * list_start, int nslots, int L)
+{
+  const DevRegion & R = g.R;
+  // "all k-mers extremely common" bail-out (alignment.cpp:35-49)
+  bool any_small = false;
+  for (int i = 0; i < nslots && !any_small; ++i)
+  {
+    uint32_t c = 0;
+    for (int k = list_start[2 * i]; k < list_start[2 * i + 1]; ++k)
+      c += refs[k].y;
+    if (c < 512u)
+      any_small = true;
+  }
+  if (!any_small)
+    return;
+  for (int l = 0; l < 2 * nslots; ++l)
+  {
+    uint16_t const rs = (uint16_t)(31 * (l >> 1));
+    if (list_start[l] == list_start[l + 1])
+      continue; // add_next_kmer_labels with no labels changes nothing
+    S.npp = 0;
+    for (int k = list_start[l]; k < list_start[l + 1]; ++k)
+    {
+      uint2 const ref = refs[k];
+      for (uint32_t q = 0; q < ref.y; ++q)
+      {
+        DevLabel const lab = R.labels[ref.x + q];
+        pp_add_label(S, g, lab, rs, (uint16_t)(rs + 31), (uint16_t)(l & 1));
+      }
+    }
+    add_next(S, rs);
+  }
+  remove_short_paths(S);
+  walk(S, g, (uint32_t)L, false); // starts before ends (alignment.cpp:71-72)
+  walk(S, g, (uint32_t)L, true);
+  update_longest(S);
+  remove_short_paths(S);
+  // remove_paths_with_too_many_mismatches (genotype_paths.cpp:360-380)
+  if (S.npaths > 0)
+  {
+    uint16_t mn = 10;
+    for (int i = 0; i < S.npaths; ++i)
+      mn = min(mn, S.paths[i].mm);
+    int w = 0;
+    for (int i = 0; i < S.npaths; ++i)
+      if (S.paths[i].mm <= mn)
+      {
+        if (w != i)
+          S.paths[w] = S.paths[i];
+        ++w;
+      }
+    S.npaths = w;
+  }
+  if (R.is_sv) // remove_fully_special_paths (genotype_paths.cpp:476-481)
+  {
+    int w = 0;
+    for (int i = 0; i < S.npaths; ++i)
+      if (g.ref_reach_pos(S.paths[i].start) != g.ref_reach_pos(S.paths[i].end))
+      {
+        if (w != i)
+          S.paths[w] = S.paths[i];
+        ++w;
+      }
+    S.npaths = w;
+  }
+  // remove_non_ref_paths_when_read_matches_ref (genotype_paths.cpp:460-474)
+  if (!all_paths_unique(S, g))
+  {
+    bool any_ref = false;
+    for (int i = 0; i < S.npaths; ++i)
+      if (path_is_reference(S.paths[i]))
+      {
+        any_ref = true;
+        break;
+      }
+    if (any_ref)
+    {
+      int w = 0;
+      for (int i = 0; i < S.npaths; ++i)
+        if (path_is_reference(S.paths[i]))
+        {
+          if (w != i)
+            S.paths[w] = S.paths[i];
+          ++w;
+        }
+      S.npaths = w;
+    }
+  }
+  update_longest(S);
+  remove_short_paths(S);
+  if (R.is_sv)
+    remove_support_from_read_ends(S, g);
+}
+
+// Writes the GenotypePaths record of a finished task; returns false when the path pool is exhausted.
+template <class W>
+__device__ bool write_result(const W & S, const GR & g, const LaunchParams & P, uint32_t task, uint32_t n_tasks_total)
+{
+  TaskSummary sum;
+  sum.npaths = (uint16_t)S.npaths;
+  sum.longest = (uint16_t)S.longest;
+  sum.mm0 = 0;
+  sum.altcalls = 0;
+  sum.bits = TS_ALL_UNIQUE | TS_COMPUTED;
+  sum.pad = 0;
+  sum.path_off = task * INLINE_WORDS;
+  bool ok = true;
+  if (S.npaths > 0)
+  {
+    sum.mm0 = S.paths[0].mm;
+    if (!all_paths_unique(S, g))
+      sum.bits &= ~TS_ALL_UNIQUE;
+    uint32_t words = 0, alt = 0;
+    for (int i = 0; i < S.npaths; ++i)
+    {
+      words += PATH_HDR_WORDS + 2u * S.paths[i].nvar;
+      for (int k = 0; k < S.paths[i].nvar; ++k)
+        alt += (S.paths[i].mask[k] & 1u) == 0;
+    }
+    sum.altcalls = (uint16_t)min(alt, 0xFFFFu);
+    unsigned long long off = (unsigned long long)task * INLINE_WORDS;
+    if (words > INLINE_WORDS)
+    {
+      unsigned long long const base = (unsigned long long)n_tasks_total * INLINE_WORDS;
+      off = base + atomicAdd(&P.counters->path_words, (unsigned long long)words);
+      if (off + words > P.path_pool_cap)
+        ok = false;
+    }
+    if (!ok)
+    {
+      sum.bits |= TS_OVERFLOW;
+      sum.npaths = 0;
+      atomicAdd(&P.counters->reasons[9], 1ull);
+      atomicAdd(&P.counters->n_overflow, 1ull);
+    }
+    else
+    {
+      sum.path_off = (uint32_t)off;
+      uint32_t * w = P.path_pool + off;
+      for (int i = 0; i < S.npaths; ++i)
+      {
+        auto const & p = S.paths[i];
+        *w++ = p.start;
+        *w++ = p.end;
+        *w++ = (uint32_t)p.rs | ((uint32_t)p.re << 16);
+        *w++ = (uint32_t)p.mm | ((uint32_t)p.nvar << 16);
+        for (int k = 0; k < p.nvar; ++k)
+        {
+          *w++ = p.order[k];
+          *w++ = (uint32_t)p.mask[k];
+        }
+      }
+    }
+  }
+  P.summaries[task] = sum;
+  return ok;
+}
+
+// debug tap of the seed lists (lane 0 / one thread): labels of every list in multi_get order
+__device__ bool write_seed_tap(const LaunchParams & P, const DevRegion & R, uint32_t task, const uint2 * refs,
+                               const uint16_t * list_start, int nslots)
+{
+  uint32_t tot = 0;
+  for (int l = 0; l < 2 * nslots; ++l)
+  {
+    uint32_t c = 0;
+    for (int k = list_start[l]; k < list_start[l + 1]; ++k)
+      c += refs[k].y;
+    P.tap.list_count[(size_t)task * NLISTS + l] = c;
+    tot += c;
+  }
+  for (int l = 2 * nslots; l < NLISTS; ++l)
+    P.tap.list_count[(size_t)task * NLISTS + l] = 0;
+  P.tap.nslots[task] = nslots;
+  unsigned long long const base = atomicAdd(&P.counters->dbg_label_words, (unsigned long long)tot);
+  if (base + tot > P.tap.pool_cap)
+  {
+    for (int l = 0; l < NLISTS; ++l)
+      P.tap.list_count[(size_t)task * NLISTS + l] = 0;
+    return false;
+  }
+  unsigned long long o = base;
+  for (int l = 0; l < 2 * nslots; ++l)
+  {
+    P.tap.list_off[(size_t)task * NLISTS + l] = (uint32_t)o;
+    for (int k = list_start[l]; k < list_start[l + 1]; ++k)
+      for (uint32_t q = 0; q < refs[k].y; ++q)
+        P.tap.pool[o++] = R.labels[refs[k].x + q];
+  }
+  return true;
+}
+
+// Seed record handed from probe_kernel to chain_kernel (global memory, 96 bytes)
+struct SeedRec
+{
+  uint8_t cnt[NLISTS]; // bucket references per list
+  uint8_t nslots;
+  uint8_t slow;        // 1: needs the slow kernel (IUPAC/N seed, or more than SEED_INLINE references)
+  uint16_t pad;
+  uint2 refs[SEED_INLINE];
+};
+static_assert(sizeof(SeedRec) == SEED_REC_BYTES, "SeedRec layout");
+
+__device__ __forceinline__ void push_slow(const LaunchParams & P, uint32_t task)
+{
+  unsigned long long const i = atomicAdd(&P.counters->n_slow, 1ull);
+  P.slow_tasks[i] = task;
+}
+} // namespace
+
+// ================================================================================================ probe kernel
+// One warp per active task; phase A only.  Tiny shared state -> high occupancy; all lanes busy.
+__global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(LaunchParams P)
+{
+  __shared__ uint8_t s_codes[PROBE_WARPS][MAX_SEQ + 8];
+  __shared__ uint2 s_refs[PROBE_WARPS][SEED_INLINE];
+  int const lane = threadIdx.x & 31;
+  int const wib = threadIdx.x >> 5;
+  uint32_t const t = blockIdx.x * PROBE_WARPS + wib;
+  if (t >= P.n_active)
+    return;
+  uint32_t const task = P.active_tasks[t];
+  uint32_t const unit = task >> 1;
+  int const orient = task & 1;
+  int const rec = P.batch.unit_record[unit];
+  int const L = P.batch.lseq[rec];
+  const DevRegion & R = P.regions[P.batch.region[rec]];
+  uint8_t * codes = s_codes[wib];
+  uint2 * refs = s_refs[wib];
+  {
+    const uint8_t * s4 = P.batch.seq4 + (size_t)rec * GTB_SEQ_STRIDE;
+    for (int j = lane; j < L; j += 32)
+    {
+      int const src = orient ? (L - 1 - j) : j;
+      uint8_t const byte = __ldg(s4 + (src >> 1));
+      uint8_t c = (src & 1) ? (byte & 15) : (byte >> 4);
+      if (orient)
+        c = comp4(c);
+      codes[j] = c;
+    }
+  }
+  __syncwarp();
+  int const nslots = 1 + (L - 32) / 31; // get_num_kmers (kmer_help_functions.cpp:10-17)
+  int nrefs = 0;
+  bool slow = false;
+  uint32_t cnts = 0, cnts_hi = 0; // 8 x 8-bit list counts
+  for (int i = 0; i < nslots && !slow; ++i)
+  {
+    uint8_t const c = codes[31 * i + lane];
+    if (!__all_sync(FULL, __popc((unsigned)c) == 1))
+    {
+      slow = true; // IUPAC / N in a seed: key expansion runs in the slow kernel
+      break;
+    }
+    uint64_t const val = (uint64_t)(__ffs((int)c) - 1) << (2 * (31 - lane));
+    uint32_t const lo = __reduce_or_sync(FULL, (uint32_t)val);
+    uint32_t const hi = __reduce_or_sync(FULL, (uint32_t)(val >> 32));
+    uint64_t const key = (uint64_t)lo | ((uint64_t)hi << 32);
+    // exact key (lane 0 probes) + the 96 Hamming-1 neighbours in key order bb*3 + j (type_conversions.cpp:272-288)
+    int before = nrefs;
+    {
+      uint32_t off = 0, cnt = 0;
+      bool f = false;
+      if (lane == 0)
+        f = probe(R, key, off, cnt);
+      f = __shfl_sync(FULL, (int)f, 0) != 0;
+      if (f)
+      {
+        if (nrefs < SEED_INLINE)
+        {
+          if (lane == 0)
+            refs[nrefs] = make_uint2(off, cnt);
+        }
+        else
+          slow = true;
+        ++nrefs;
+      }
+    }
+    uint32_t const c0 = (uint32_t)(nrefs - before);
+    before = nrefs;
+    {
+      uint32_t total = 0;
+      bool dropped = false;
+      for (int base = 0; base < 96; base += 32)
+      {
+        int const k = base + lane;
+        uint64_t const nk = key ^ ((uint64_t)(k % 3 + 1) << (2 * (k / 3)));
+        uint32_t off = 0, cnt = 0;
+        bool const found = probe(R, nk, off, cnt);
+        unsigned const fm = __ballot_sync(FULL, found);
+        if (fm == 0)
+          continue;
+        uint32_t inc = found ? cnt : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+          uint32_t const tt = __shfl_up_sync(FULL, inc, d);
+          if (lane >= d)
+            inc += tt;
+        }
+        if (__any_sync(FULL, found && (total + inc) > 75u)) // PHIndex::multi_get give-up rule (ph_index.cpp:84-89)
+        {
+          dropped = true;
+          break;
+        }
+        int const pos = nrefs + __popc(fm & ((1u << lane) - 1u));
+        if (found)
+        {
+          if (pos < SEED_INLINE)
+            refs[pos] = make_uint2(off, cnt);
+        }
+        nrefs += __popc(fm);
+        total += __shfl_sync(FULL, inc, 31);
+      }
+      if (dropped)
+        nrefs = before;
+      if (nrefs > SEED_INLINE)
+        slow = true;
+    }
+    uint32_t const c1 = (uint32_t)(nrefs - before);
+    if (i < 2)
+      cnts |= (c0 << (16 * i)) | (c1 << (16 * i + 8));
+    else
+      cnts_hi |= (c0 << (16 * (i - 2))) | (c1 << (16 * (i - 2) + 8));
+  }
+  __syncwarp();
+  SeedRec * out = reinterpret_cast<SeedRec *>(P.seed_recs) + t;
+  if (lane == 0)
+  {
+    uint32_t * w = reinterpret_cast<uint32_t *>(out);
+    w[0] = cnts;
+    w[1] = cnts_hi;
+    w[2] = (uint32_t)nslots | ((slow ? 1u : 0u) << 8);
+  }
+  if (!slow && lane < nrefs)
+    out->refs[lane] = refs[lane];
+}
+
+// ================================================================================================ chain kernel
+// One THREAD per active task: phases B-D on a small per-thread working set (local memory).  Tasks that exceed a
+// small capacity, or that probe_kernel marked, are queued for slow_kernel.
+__global__ void __launch_bounds__(CHAIN_THREADS) chain_kernel(LaunchParams P)
+{
+  uint32_t const t = blockIdx.x * CHAIN_THREADS + threadIdx.x;
+  if (t >= P.n_active)
+    return;
+  uint32_t const task = P.active_tasks[t];
+  const SeedRec * recp = reinterpret_cast<const SeedRec *>(P.seed_recs) + t;
+  uint32_t const w2 = reinterpret_cast<const uint32_t *>(recp)[2];
+  if ((w2 >> 8) & 1u)
+  {
+    push_slow(P, task);
+    return;
+  }
+  uint32_t const unit = task >> 1;
+  int const rec = P.batch.unit_record[unit];
+  const DevRegion & R = P.regions[P.batch.region[rec]];
+  GR g(R);
+  FastState S;
+  S.s4 = P.batch.seq4 + (size_t)rec * GTB_SEQ_STRIDE;
+  S.L = P.batch.lseq[rec];
+  S.orient = task & 1;
+  S.npaths = 0;
+  S.npp = 0;
+  S.longest = 0;
+  S.overflow = 0;
+  int const nslots = (int)(w2 & 0xFFu);
+  uint16_t list_start[NLISTS + 1];
+  {
+    uint32_t const c_lo = reinterpret_cast<const uint32_t *>(recp)[0], c_hi = reinterpret_cast<const uint32_t *>(recp)[1];
+    list_start[0] = 0;
+#pragma unroll
+    for (int l = 0; l < NLISTS; ++l)
+    {
+      uint32_t const c = ((l < 4 ? c_lo : c_hi) >> (8 * (l & 3))) & 0xFFu;
+      list_start[l + 1] = (uint16_t)(list_start[l] + c);
+    }
+  }
+  if (P.tap.list_count)
+    write_seed_tap(P, R, task, recp->refs, list_start, nslots);
+  run_task(S, g, recp->refs, list_start, nslots, S.L);
+  if (S.overflow)
+  {
+    push_slow(P, task);
+    return;
+  }
+  write_result(S, g, P, task, P.batch.n_units * 2);
+}
+
+// ================================================================================================ slow kernel
+// One warp per queued task, big shared-memory working set, lane 0 runs the scalar logic.  Handles seeds with
+// IUPAC/N bases (key expansion, type_conversions.cpp:207-266) and everything chain_kernel's capacities cannot hold.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) slow_kernel(LaunchParams P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WS * all = reinterpret_cast<WS *>(smem_raw);
@@ -1113,56 +1566,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParam
   int const wib = threadIdx.x >> 5;
   WS & S = all[wib];
   int const total_warps = gridDim.x * WARPS_PER_BLOCK;
-  unsigned long long n_oriented = 0, n_overflow = 0;
+  uint32_t const n_slow = (uint32_t)P.counters->n_slow;
   uint32_t const n_tasks = P.batch.n_units * 2;
 
-  for (uint32_t task = blockIdx.x * WARPS_PER_BLOCK + wib; task < n_tasks; task += total_warps)
+  for (uint32_t si = blockIdx.x * WARPS_PER_BLOCK + wib; si < n_slow; si += total_warps)
   {
+    uint32_t const task = P.slow_tasks[si];
     uint32_t const unit = task >> 1;
     int const orient = task & 1;
     int const rec = P.batch.unit_record[unit];
-    uint16_t const flag = P.batch.flag[rec];
     int const L = P.batch.lseq[rec];
-    TaskSummary sum;
-    sum.npaths = 0;
-    sum.longest = 0;
-    sum.mm0 = 0;
-    sum.altcalls = 0;
-    sum.bits = TS_ALL_UNIQUE;
-    sum.pad = 0;
-    sum.path_off = task * INLINE_WORDS;
-
-    // align_read (alignment.cpp:331-363): which orientations are aligned
-    bool run = L >= 63 && L <= MAX_SEQ;
-    if (orient == 1)
-    {
-      int32_t const isz = P.batch.isize[rec];
-      bool const fwd_only = (flag & F_PAIRED) == 0 ||
-                            (P.batch.same_tid[rec] && isz > -1200 && isz < 1200 &&
-                             (((flag & F_REV) != 0) != ((flag & F_MREV) != 0)));
-      run = run && !fwd_only;
-    }
-    if (!run)
-    {
-      if (lane == 0)
-      {
-        if (L > MAX_SEQ)
-        {
-          sum.bits |= TS_OVERFLOW;
-          ++n_overflow;
-          atomicAdd(&P.counters->reasons[10], 1ull);
-        }
-        P.summaries[task] = sum;
-        if (P.tap.list_count)
-          P.tap.nslots[task] = 0;
-      }
-      continue;
-    }
     const DevRegion & R = P.regions[P.batch.region[rec]];
     GR g(R);
     __syncwarp();
-
-    // ---- A. unpack (reverse-complement for orientation 1: hts_parallel_reader.cpp:226-243)
     {
       const uint8_t * s4 = P.batch.seq4 + (size_t)rec * GTB_SEQ_STRIDE;
       for (int j = lane; j < L; j += 32)
@@ -1177,7 +1593,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParam
       if (lane == 0)
       {
         S.overflow = 0;
-        S.cand_spill = static_cast<Cand *>(P.cand_spill) + (size_t)(blockIdx.x * WARPS_PER_BLOCK + wib) * CAND_SPILL;
+        S.cand_spill = static_cast<WS::Cand *>(P.cand_spill) + (size_t)(blockIdx.x * WARPS_PER_BLOCK + wib) * CAND_SPILL;
         S.npaths = 0;
         S.npp = 0;
         S.longest = 0;
@@ -1185,7 +1601,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParam
     }
     __syncwarp();
 
-    int const nslots = 1 + (L - 32) / 31; // get_num_kmers (kmer_help_functions.cpp:10-17)
+    int const nslots = 1 + (L - 32) / 31;
     int nrefs = 0;
     if (lane == 0)
       S.list_start[0] = 0;
@@ -1202,7 +1618,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParam
         query_list(S, R, [key](int) { return key; }, 1, false, lane, nrefs);
         if (lane == 0)
           S.list_start[2 * i + 1] = (uint16_t)nrefs;
-        // the 96 Hamming-1 neighbours, key order bb*3 + j (type_conversions.cpp:272-288)
         query_list(S, R, [key](int k) { return key ^ ((uint64_t)(k % 3 + 1) << (2 * (k / 3))); }, 96, true, lane, nrefs);
         if (lane == 0)
           S.list_start[2 * i + 2] = (uint16_t)nrefs;
@@ -1214,7 +1629,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParam
         int nk = 0;
         if (lane == 0)
         {
-          nk = expand_keys(S.seq + 31 * i, keys, (int)(sizeof(Path) * MAXP * 2 / sizeof(uint64_t)));
+          nk = expand_keys(S.seq + 31 * i, keys, (int)(sizeof(WS::Path) * MAXP * 2 / sizeof(uint64_t)));
           if (nk < 0)
           {
             S.overflow |= OV_KEYS;
@@ -1248,213 +1663,36 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) align_kernel(LaunchParam
       }
     }
     __syncwarp();
+    // codes -> IUPAC characters for the graph walk (all lanes)
+    for (int j = lane; j < L; j += 32)
+      S.seq[j] = iupac_char(S.seq[j]);
+    __syncwarp();
 
-    // optional debug tap of the seed lists
-    if (P.tap.list_count)
-    {
-      uint32_t tot = 0;
-      if (lane == 0)
-      {
-        for (int l = 0; l < 2 * nslots; ++l)
-        {
-          uint32_t c = 0;
-          for (int k = S.list_start[l]; k < S.list_start[l + 1]; ++k)
-            c += S.refs[k].y;
-          P.tap.list_count[(size_t)task * NLISTS + l] = c;
-          tot += c;
-        }
-        for (int l = 2 * nslots; l < NLISTS; ++l)
-          P.tap.list_count[(size_t)task * NLISTS + l] = 0;
-        P.tap.nslots[task] = nslots;
-        unsigned long long base = atomicAdd(&P.counters->dbg_label_words, (unsigned long long)tot);
-        if (base + tot > P.tap.pool_cap)
-        {
-          S.overflow |= OV_TAP;
-          for (int l = 0; l < NLISTS; ++l)
-            P.tap.list_count[(size_t)task * NLISTS + l] = 0;
-        }
-        else
-        {
-          unsigned long long o = base;
-          for (int l = 0; l < 2 * nslots; ++l)
-          {
-            P.tap.list_off[(size_t)task * NLISTS + l] = (uint32_t)o;
-            for (int k = S.list_start[l]; k < S.list_start[l + 1]; ++k)
-              for (uint32_t q = 0; q < S.refs[k].y; ++q)
-                P.tap.pool[o++] = R.labels[S.refs[k].x + q];
-          }
-        }
-      }
-    }
-
-    // ---- B..D on lane 0
     if (lane == 0)
     {
-      // "all k-mers extremely common" bail-out (alignment.cpp:35-49)
-      bool any_small = false;
-      for (int i = 0; i < nslots && !any_small; ++i)
-      {
-        uint32_t c = 0;
-        for (int k = S.list_start[2 * i]; k < S.list_start[2 * i + 1]; ++k)
-          c += S.refs[k].y;
-        if (c < 512u)
-          any_small = true;
-      }
-      if (any_small)
-      {
-        for (int l = 0; l < 2 * nslots; ++l)
-        {
-          uint16_t const rs = (uint16_t)(31 * (l >> 1));
-          S.npp = 0;
-          for (int k = S.list_start[l]; k < S.list_start[l + 1]; ++k)
-          {
-            uint2 const ref = S.refs[k];
-            for (uint32_t q = 0; q < ref.y; ++q)
-            {
-              DevLabel const lab = R.labels[ref.x + q];
-              pp_add_label(S, g, lab, rs, (uint16_t)(rs + 31), (uint16_t)(l & 1));
-            }
-          }
-          add_next(S, rs);
-        }
-        remove_short_paths(S);
-        // codes -> IUPAC characters for the graph walk
-        for (int j = 0; j < L; ++j)
-          S.seq[j] = (uint8_t)IUPAC_CHAR[S.seq[j]];
-        walk(S, g, (uint32_t)L, false); // starts before ends (alignment.cpp:71-72)
-        walk(S, g, (uint32_t)L, true);
-        update_longest(S);
-        remove_short_paths(S);
-        // remove_paths_with_too_many_mismatches (genotype_paths.cpp:360-380)
-        if (S.npaths > 0)
-        {
-          uint16_t mn = 10;
-          for (int i = 0; i < S.npaths; ++i)
-            mn = min(mn, S.paths[i].mm);
-          int w = 0;
-          for (int i = 0; i < S.npaths; ++i)
-            if (S.paths[i].mm <= mn)
-            {
-              if (w != i)
-                S.paths[w] = S.paths[i];
-              ++w;
-            }
-          S.npaths = w;
-        }
-        if (R.is_sv) // remove_fully_special_paths (genotype_paths.cpp:476-481)
-        {
-          int w = 0;
-          for (int i = 0; i < S.npaths; ++i)
-            if (g.ref_reach_pos(S.paths[i].start) != g.ref_reach_pos(S.paths[i].end))
-            {
-              if (w != i)
-                S.paths[w] = S.paths[i];
-              ++w;
-            }
-          S.npaths = w;
-        }
-        // remove_non_ref_paths_when_read_matches_ref (genotype_paths.cpp:460-474)
-        if (!all_paths_unique(S, g))
-        {
-          bool any_ref = false;
-          for (int i = 0; i < S.npaths; ++i)
-            if (path_is_reference(S.paths[i]))
-            {
-              any_ref = true;
-              break;
-            }
-          if (any_ref)
-          {
-            int w = 0;
-            for (int i = 0; i < S.npaths; ++i)
-              if (path_is_reference(S.paths[i]))
-              {
-                if (w != i)
-                  S.paths[w] = S.paths[i];
-                ++w;
-              }
-            S.npaths = w;
-          }
-        }
-        update_longest(S);
-        remove_short_paths(S);
-        if (R.is_sv)
-          remove_support_from_read_ends(S, g);
-      }
-
-      // ---- write the GenotypePaths record
+      if (P.tap.list_count && !write_seed_tap(P, R, task, S.refs, S.list_start, nslots))
+        S.overflow |= OV_TAP;
+      run_task(S, g, S.refs, S.list_start, nslots, L);
       if (S.overflow)
       {
-        sum.bits |= TS_OVERFLOW;
-        ++n_overflow;
+        TaskSummary sum;
+        sum.npaths = 0;
+        sum.longest = 0;
+        sum.mm0 = 0;
+        sum.altcalls = 0;
+        sum.bits = TS_OVERFLOW | TS_COMPUTED;
+        sum.pad = 0;
+        sum.path_off = task * INLINE_WORDS;
+        P.summaries[task] = sum;
+        atomicAdd(&P.counters->n_overflow, 1ull);
         for (int q = 0; q < 12; ++q)
           if ((S.overflow >> q) & 1u)
             atomicAdd(&P.counters->reasons[q], 1ull);
-        S.npaths = 0;
-        S.longest = 0;
       }
-      sum.bits |= TS_COMPUTED;
-      sum.npaths = (uint16_t)S.npaths;
-      sum.longest = (uint16_t)S.longest;
-      if (S.npaths > 0)
-      {
-        sum.mm0 = S.paths[0].mm;
-        if (!all_paths_unique(S, g))
-          sum.bits &= ~TS_ALL_UNIQUE;
-        uint32_t words = 0, alt = 0;
-        for (int i = 0; i < S.npaths; ++i)
-        {
-          words += PATH_HDR_WORDS + 2u * S.paths[i].nvar;
-          for (int k = 0; k < S.paths[i].nvar; ++k)
-            alt += (S.paths[i].mask[k] & 1u) == 0;
-        }
-        sum.altcalls = (uint16_t)min(alt, 0xFFFFu);
-        unsigned long long off = (unsigned long long)task * INLINE_WORDS;
-        bool ok = true;
-        if (words > INLINE_WORDS)
-        {
-          unsigned long long const base = (unsigned long long)n_tasks * INLINE_WORDS;
-          off = base + atomicAdd(&P.counters->path_words, (unsigned long long)words);
-          if (off + words > P.path_pool_cap)
-            ok = false;
-        }
-        if (!ok)
-        {
-          sum.bits |= TS_OVERFLOW;
-          sum.npaths = 0;
-          ++n_overflow;
-          atomicAdd(&P.counters->reasons[9], 1ull);
-        }
-        else
-        {
-          sum.path_off = (uint32_t)off;
-          uint32_t * w = P.path_pool + off;
-          for (int i = 0; i < S.npaths; ++i)
-          {
-            Path const & p = S.paths[i];
-            *w++ = p.start;
-            *w++ = p.end;
-            *w++ = (uint32_t)p.rs | ((uint32_t)p.re << 16);
-            *w++ = (uint32_t)p.mm | ((uint32_t)p.nvar << 16);
-            for (int k = 0; k < p.nvar; ++k)
-            {
-              *w++ = p.order[k];
-              *w++ = (uint32_t)p.mask[k];
-            }
-          }
-        }
-      }
-      P.summaries[task] = sum;
-      ++n_oriented;
+      else
+        write_result(S, g, P, task, n_tasks);
     }
     __syncwarp();
-  }
-  if (lane == 0)
-  {
-    if (n_oriented)
-      atomicAdd(&P.counters->n_oriented, n_oriented);
-    if (n_overflow)
-      atomicAdd(&P.counters->n_overflow, n_overflow);
   }
 }
 
@@ -1839,39 +2077,57 @@ int align_kernel_blocks_per_sm()
   if (g_align_blocks_per_sm == 0)
   {
     size_t const smem = sizeof(WS) * WARPS_PER_BLOCK;
-    cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_kernel, WARPS_PER_BLOCK * 32, smem) != cudaSuccess || nb < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, slow_kernel, WARPS_PER_BLOCK * 32, smem) != cudaSuccess || nb < 1)
       nb = 1;
     g_align_blocks_per_sm = nb;
   }
   return g_align_blocks_per_sm;
 }
 
-size_t align_spill_bytes()
+static int sm_count()
 {
-  int const bps = align_kernel_blocks_per_sm();
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return (size_t)sms * bps * WARPS_PER_BLOCK * CAND_SPILL * sizeof(Cand);
+  static int sms = 0;
+  if (sms == 0)
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
 }
 
-void launch_align(const LaunchParams & p, void * stream)
+size_t align_spill_bytes()
 {
-  size_t const smem = sizeof(WS) * WARPS_PER_BLOCK;
-  int const bps = align_kernel_blocks_per_sm();
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  uint32_t const n_tasks = p.batch.n_units * 2;
-  uint32_t const need = (n_tasks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-  uint32_t grid = (uint32_t)(sms * bps); // persistent: a multiple of the SM count
-  if (need < grid)
-    grid = need;
-  if (grid == 0)
+  return (size_t)sm_count() * align_kernel_blocks_per_sm() * WARPS_PER_BLOCK * CAND_SPILL * sizeof(WS::Cand);
+}
+
+void launch_probe(const LaunchParams & p, void * stream)
+{
+  if (p.n_active == 0)
     return;
-  align_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(p);
+  uint32_t const grid = (p.n_active + PROBE_WARPS - 1) / PROBE_WARPS;
+  probe_kernel<<<grid, PROBE_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+}
+
+void launch_chain(const LaunchParams & p, void * stream)
+{
+  if (p.n_active == 0)
+    return;
+  uint32_t const grid = (p.n_active + CHAIN_THREADS - 1) / CHAIN_THREADS;
+  chain_kernel<<<grid, CHAIN_THREADS, 0, (cudaStream_t)stream>>>(p);
+}
+
+// persistent grid (a multiple of the SM count); the number of queued tasks is read on the device
+void launch_slow(const LaunchParams & p, void * stream)
+{
+  if (p.n_active == 0)
+    return;
+  size_t const smem = sizeof(WS) * WARPS_PER_BLOCK;
+  uint32_t const grid = (uint32_t)(sm_count() * align_kernel_blocks_per_sm());
+  slow_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(p);
 }
 
 void launch_score(const LaunchParams & p, void * stream)

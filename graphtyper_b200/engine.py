@@ -22,7 +22,7 @@ EXPORTS = [
     "gtb_index_size", "gtb_index_export", "gtb_pool_begin", "gtb_submit_reads", "gtb_accumulator_sizes",
     "gtb_pool_finish", "gtb_submit_reads_multi", "gtb_debug_enable", "gtb_debug_seed_sizes", "gtb_debug_seeds",
     "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_replay_last",
-    "gtb_last_timing", "gtb_pool_reset", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators",
+    "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators",
 ]
 
 
@@ -67,6 +67,7 @@ def load_library() -> C.CDLL:
     L.gtb_replay_last.argtypes = [vp, C.POINTER(abi.SubmitStats)]
     fp = C.POINTER(C.c_float)
     L.gtb_last_timing.argtypes = [vp, fp, fp, fp, fp]
+    L.gtb_last_kernel_timing.argtypes = [vp, fp, fp, fp, fp, abi.u64p]
     L.gtb_pool_reset.argtypes = [vp, C.c_int]
     L.gtb_nccl_unique_id.argtypes = [abi.u8p]
     L.gtb_nccl_init.argtypes = [vp, C.c_int, C.c_int, abi.u8p]
@@ -152,6 +153,12 @@ class Context:
         a, b, c, d = C.c_float(), C.c_float(), C.c_float(), C.c_float()
         self._check(self.lib.gtb_last_timing(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return a.value, b.value, c.value, d.value
+
+    def last_kernel_timing(self) -> Dict[str, float]:
+        a, b, c, d, n = C.c_float(), C.c_float(), C.c_float(), C.c_float(), C.c_uint64()
+        self._check(self.lib.gtb_last_kernel_timing(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(n)))
+        return {"probe_kernel": a.value, "chain_kernel": b.value, "slow_kernel": c.value, "score_kernel": d.value,
+                "n_slow_tasks": int(n.value)}
 
     def pool_finish(self, region_id: int) -> abi.HostAccumulators:
         nb, ns, nc = C.c_uint32(), C.c_uint64(), C.c_uint64()

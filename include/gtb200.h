@@ -196,6 +196,8 @@ int gtb_calls_from_accumulators(const gtb_accumulators *acc, uint8_t *phred /*[n
  * submit/replay from CUDA events on the library's stream; zero a region's accumulators. */
 int gtb_replay_last(gtb_ctx *ctx, gtb_submit_stats *stats);
 int gtb_last_timing(gtb_ctx *ctx, float *h2d_ms, float *align_ms, float *score_ms, float *d2h_ms);
+int gtb_last_kernel_timing(gtb_ctx *ctx, float *probe_ms, float *chain_ms, float *slow_ms, float *score_ms,
+                           uint64_t *n_slow);
 int gtb_pool_reset(gtb_ctx *ctx, int region_id);
 
 /* NCCL bootstrap (libnccl is bound lazily with dlopen): rank 0 creates the 128-byte unique id, the caller
