@@ -531,6 +531,8 @@ static int run_kernels(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
   CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, sizeof(DevCounters), c->stream));
   // orientations that are not aligned keep an all-zero summary (no paths)
   CUDA_TRY(cudaMemsetAsync(P.summaries, 0, (size_t)P.batch.n_units * 2 * sizeof(TaskSummary), c->stream));
+  if (P.tap.list_count)
+    CUDA_TRY(cudaMemsetAsync(P.tap.list_count, 0, (size_t)P.batch.n_units * 2 * (NLISTS * 2 + 1) * 4, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
   launch_probe(P, c->stream);
   CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
