@@ -282,8 +282,9 @@ def main() -> None:
         torch.cuda.synchronize()
 
     def reset():
-        for k in ids:
-            ctx.pool_reset(k)
+        ctx.pool_reset_multi(ids)
+
+    acc_bufs = [ctx.alloc_accumulators(k) for k in ids]
 
     h2d_bytes = sum(b.nbytes_h2d() for b in batches)
 
@@ -291,7 +292,7 @@ def main() -> None:
     def e2e_step():
         reset()
         st = ctx.submit_multi(ids, batches)
-        accs = [ctx.pool_finish(k) for k in ids]
+        accs = ctx.pool_finish_multi(ids, out=acc_bufs)
         if world > 1:
             for k in ids:
                 ctx.allreduce(k)

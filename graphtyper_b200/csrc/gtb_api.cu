@@ -7,6 +7,9 @@
 // a usable CUDA device gtb_create(device >= 0) fails and every compute entry point returns GTB_ERR_CUDA.
 
 #include <algorithm>
+#include <atomic>
+#include <functional>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -126,7 +129,7 @@ struct Ctx
   bool regions_dirty = true;
   // batch
   DeviceBuffer d_batch, d_summaries, d_pool, d_counters, d_tap_counts, d_tap_pool, d_spill, d_seedrecs, d_slow;
-  PinnedBuffer h_batch, h_counters;
+  PinnedBuffer h_batch, h_counters, h_accum;
   LaunchParams last{};
   bool have_last = false;
   uint32_t last_n_tasks = 0;
@@ -188,6 +191,29 @@ int validate_graph(const gtb_graph_view * g)
         return fail(GTB_ERR_ARG, "var_out_ref does not match the bubble structure");
   }
   return 0;
+}
+
+// tiny fork-join helper for the host-side staging work (regions are independent)
+void parallel_for(int n, const std::function<void(int)> & fn)
+{
+  int const hw = (int)std::thread::hardware_concurrency();
+  int const T = std::max(1, std::min({n, 8, hw > 0 ? hw : 1}));
+  if (T <= 1)
+  {
+    for (int i = 0; i < n; ++i)
+      fn(i);
+    return;
+  }
+  std::vector<std::thread> th;
+  th.reserve(T);
+  for (int t = 0; t < T; ++t)
+    th.emplace_back([&, t]()
+                    {
+                      for (int i = t; i < n; i += T)
+                        fn(i);
+                    });
+  for (auto & x : th)
+    x.join();
 }
 
 template <typename T>
@@ -264,6 +290,7 @@ void gtb_destroy(gtb_ctx * ctx)
     c->d_slow.release();
     c->h_batch.release();
     c->h_counters.release();
+    c->h_accum.release();
     for (auto & e : c->ev)
       if (e)
         cudaEventDestroy(e);
@@ -635,81 +662,128 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   int32_t * h_urec = reinterpret_cast<int32_t *>(h + o_urec);
   int32_t * h_mate = reinterpret_cast<int32_t *>(h + o_mate);
   uint16_t * h_region = reinterpret_cast<uint16_t *>(h + o_region);
-  size_t base = 0;
-  uint32_t n_units = 0;
   c->last_regions.assign(region_ids, region_ids + n);
+  // ---- pass 1 (parallel over regions): alignment units per region (records that are not duplicates of a previous one)
+  std::vector<size_t> rec_base(n + 1, 0);
+  std::vector<uint32_t> unit_base(n + 1, 0), active_cnt(n, 0);
+  for (int i = 0; i < n; ++i)
+    rec_base[i + 1] = rec_base[i] + batches[i].n_reads;
+  parallel_for(n, [&](int i)
+               {
+                 gtb_read_batch const & b = batches[i];
+                 uint32_t cnt = b.n_reads;
+                 if (b.dup_of)
+                 {
+                   cnt = 0;
+                   for (uint32_t k = 0; k < b.n_reads; ++k)
+                     cnt += b.dup_of[k] < 0;
+                 }
+                 unit_base[i + 1] = cnt;
+               });
+  for (int i = 0; i < n; ++i)
+    unit_base[i + 1] += unit_base[i];
+  uint32_t const n_units = unit_base[n];
+  uint32_t * h_active = reinterpret_cast<uint32_t *>(h + o_active);
+  std::atomic<int> err_code{0};
+  // ---- pass 2 (parallel over regions): copy the columns, number the units, rebase mate links, list the read
+  //      orientations that are aligned at all (align_read, src/typer/alignment.cpp:331-363: forward always; reverse
+  //      complement unless unpaired or a properly oriented pair within 1200 bp)
+  parallel_for(n, [&](int i)
+               {
+                 gtb_read_batch const & b = batches[i];
+                 size_t const m = b.n_reads, base = rec_base[i];
+                 if (m == 0)
+                   return;
+                 memcpy(h + o_seq4 + base * GTB_SEQ_STRIDE, b.seq4, m * GTB_SEQ_STRIDE);
+                 memcpy(h + o_lseq + base * 2, b.lseq, m * 2);
+                 memcpy(h + o_flag + base * 2, b.flag, m * 2);
+                 memcpy(h + o_mapq + base, b.mapq, m);
+                 memcpy(h + o_same + base, b.same_tid, m);
+                 memcpy(h + o_sd + base, b.score_diff, m);
+                 if (b.clipped)
+                   memcpy(h + o_clip + base, b.clipped, m);
+                 else
+                   memset(h + o_clip + base, 0, m);
+                 memcpy(h + o_isize + base * 4, b.isize, m * 4);
+                 memcpy(h + o_sample + base * 4, b.sample, m * 4);
+                 uint32_t u = unit_base[i];
+                 uint32_t * act = h_active + 2 * (size_t)unit_base[i];
+                 uint32_t na = 0;
+                 uint16_t const slot = (uint16_t)regs[i]->slot;
+                 int const ns = regs[i]->n_samples;
+                 for (size_t k = 0; k < m; ++k)
+                 {
+                   h_region[base + k] = slot;
+                   if (b.sample[k] < 0 || b.sample[k] >= ns)
+                   {
+                     err_code = 1;
+                     return;
+                   }
+                   int32_t const d = b.dup_of ? b.dup_of[k] : -1;
+                   if (d < 0)
+                   {
+                     h_unit[base + k] = (int32_t)u;
+                     h_urec[u] = (int32_t)(base + k);
+                     uint16_t const L = b.lseq[k], flag = b.flag[k];
+                     if (L > (uint16_t)MAX_SEQ)
+                     {
+                       err_code = 4;
+                       return;
+                     }
+                     if (L >= 63) // hard restriction of align_read (2 * K - 1)
+                     {
+                       act[na++] = u * 2;
+                       bool const fwd_only = (flag & 1u) == 0 || (b.same_tid[k] && b.isize[k] > -1200 && b.isize[k] < 1200 &&
+                                                                 (((flag & 16u) != 0) != ((flag & 32u) != 0)));
+                       if (!fwd_only)
+                         act[na++] = u * 2 + 1;
+                     }
+                     ++u;
+                   }
+                   else
+                   {
+                     if ((size_t)d >= k)
+                     {
+                       err_code = 2;
+                       return;
+                     }
+                     h_unit[base + k] = h_unit[base + d];
+                   }
+                   int32_t const mt = b.mate ? b.mate[k] : -1;
+                   if (mt >= 0 && (size_t)mt >= k)
+                   {
+                     err_code = 3;
+                     return;
+                   }
+                   h_mate[base + k] = mt < 0 ? -1 : (int32_t)(base + mt);
+                 }
+                 active_cnt[i] = na;
+               });
+  switch (err_code.load())
+  {
+  case 1:
+    return fail(GTB_ERR_ARG, "sample index out of range");
+  case 2:
+    return fail(GTB_ERR_ARG, "dup_of must reference an earlier record of the same batch");
+  case 3:
+    return fail(GTB_ERR_ARG, "mate must reference an earlier record of the same batch");
+  case 4:
+    return fail(GTB_ERR_CAPACITY, "read longer than 152 bases (reference MAX_READ_LENGTH is 151)");
+  default:
+    break;
+  }
+  // compact the per-region active lists
+  uint32_t n_active = 0;
   c->last_unit_begin.assign(1, 0);
   c->last_rec_begin.assign(1, 0);
   for (int i = 0; i < n; ++i)
   {
-    gtb_read_batch const & b = batches[i];
-    size_t const m = b.n_reads;
-    if (m)
-    {
-      memcpy(h + o_seq4 + base * GTB_SEQ_STRIDE, b.seq4, m * GTB_SEQ_STRIDE);
-      memcpy(h + o_lseq + base * 2, b.lseq, m * 2);
-      memcpy(h + o_flag + base * 2, b.flag, m * 2);
-      memcpy(h + o_mapq + base, b.mapq, m);
-      memcpy(h + o_same + base, b.same_tid, m);
-      memcpy(h + o_sd + base, b.score_diff, m);
-      if (b.clipped)
-        memcpy(h + o_clip + base, b.clipped, m);
-      else
-        memset(h + o_clip + base, 0, m);
-      memcpy(h + o_isize + base * 4, b.isize, m * 4);
-      memcpy(h + o_sample + base * 4, b.sample, m * 4);
-    }
-    for (size_t k = 0; k < m; ++k)
-    {
-      h_region[base + k] = (uint16_t)regs[i]->slot;
-      if (b.sample[k] < 0 || b.sample[k] >= regs[i]->n_samples)
-        return fail(GTB_ERR_ARG, "sample index out of range");
-      int32_t const d = b.dup_of ? b.dup_of[k] : -1;
-      if (d < 0)
-      {
-        h_unit[base + k] = (int32_t)n_units;
-        h_urec[n_units] = (int32_t)(base + k);
-        ++n_units;
-      }
-      else
-      {
-        if ((size_t)d >= k)
-          return fail(GTB_ERR_ARG, "dup_of must reference an earlier record of the same batch");
-        h_unit[base + k] = h_unit[base + d];
-      }
-      int32_t const mt = b.mate ? b.mate[k] : -1;
-      if (mt >= 0 && (size_t)mt >= k)
-        return fail(GTB_ERR_ARG, "mate must reference an earlier record of the same batch");
-      h_mate[base + k] = mt < 0 ? -1 : (int32_t)(base + mt);
-    }
-    base += m;
-    c->last_unit_begin.push_back(n_units);
-    c->last_rec_begin.push_back((uint32_t)base);
-  }
-
-  // ---- read orientations that are aligned at all (align_read, src/typer/alignment.cpp:331-363):
-  //      forward always; reverse complement unless unpaired or a properly oriented pair within 1200 bp
-  uint32_t * h_active = reinterpret_cast<uint32_t *>(h + o_active);
-  uint32_t n_active = 0;
-  {
-    const uint16_t * hl = reinterpret_cast<const uint16_t *>(h + o_lseq);
-    const uint16_t * hf = reinterpret_cast<const uint16_t *>(h + o_flag);
-    const int32_t * hi = reinterpret_cast<const int32_t *>(h + o_isize);
-    const uint8_t * hs = h + o_same;
-    for (uint32_t u = 0; u < n_units; ++u)
-    {
-      int32_t const r = h_urec[u];
-      uint16_t const L = hl[r], flag = hf[r];
-      if (L > (uint16_t)MAX_SEQ)
-        return fail(GTB_ERR_CAPACITY, "read longer than 152 bases (reference MAX_READ_LENGTH is 151)");
-      if (L < 63)
-        continue; // hard restriction of align_read (2 * K - 1)
-      h_active[n_active++] = u * 2;
-      bool const fwd_only = (flag & 1u) == 0 ||
-                            (hs[r] && hi[r] > -1200 && hi[r] < 1200 && (((flag & 16u) != 0) != ((flag & 32u) != 0)));
-      if (!fwd_only)
-        h_active[n_active++] = u * 2 + 1;
-    }
+    uint32_t * src = h_active + 2 * (size_t)unit_base[i];
+    if (src != h_active + n_active && active_cnt[i])
+      memmove(h_active + n_active, src, (size_t)active_cnt[i] * 4);
+    n_active += active_cnt[i];
+    c->last_unit_begin.push_back(unit_base[i + 1]);
+    c->last_rec_begin.push_back((uint32_t)rec_base[i + 1]);
   }
 
   uint32_t const n_tasks = n_units * 2;
@@ -854,19 +928,8 @@ int gtb_accumulator_sizes(gtb_ctx * ctx, int region_id, uint32_t * n_bubbles, ui
   return 0;
 }
 
-int gtb_pool_finish(gtb_ctx * ctx, int region_id, gtb_accumulators * out)
+static void convert_accumulators(Region const & R, const uint8_t * h, gtb_accumulators * out)
 {
-  auto * c = reinterpret_cast<Ctx *>(ctx);
-  auto it = c->regions.find(region_id);
-  if (it == c->regions.end() || !it->second->pool_open)
-    return fail(GTB_ERR_STATE, "unknown region / pool not open");
-  Region & R = *it->second;
-  cudaSetDevice(c->device);
-  if (int rc = c->h_batch.reserve(R.accum_bytes))
-    return rc;
-  uint8_t * h = static_cast<uint8_t *>(c->h_batch.p);
-  CUDA_TRY(cudaMemcpyAsync(h, R.accum.p, R.accum_bytes, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
   uint8_t const * d0 = static_cast<uint8_t *>(R.accum.p);
   auto host_of = [&](const void * devp) { return h + (static_cast<const uint8_t *>(devp) - d0); };
   uint32_t const NB = R.n_bubbles, NS = (uint32_t)R.n_samples;
@@ -910,6 +973,54 @@ int gtb_pool_finish(gtb_ctx * ctx, int region_id, gtb_accumulators * out)
   memcpy(out->pa_score_diff, host_of(R.dev.pa_score_diff), n_cov * 8);
   memcpy(out->pa_mismatches, host_of(R.dev.pa_mismatches), n_cov * 8);
   memcpy(out->read_strand, host_of(R.dev.read_strand), n_cov * 16);
+}
+
+// Downloads the accumulators of several regions with ONE stream synchronisation; conversion runs in parallel.
+int gtb_pool_finish_multi(gtb_ctx * ctx, int n, const int * region_ids, gtb_accumulators * outs)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || n <= 0 || !region_ids || !outs)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  if (c->device < 0)
+    return fail(GTB_ERR_CUDA, "host-only context");
+  cudaSetDevice(c->device);
+  std::vector<Region *> regs(n);
+  std::vector<size_t> off(n + 1, 0);
+  for (int i = 0; i < n; ++i)
+  {
+    auto it = c->regions.find(region_ids[i]);
+    if (it == c->regions.end() || !it->second->pool_open)
+      return fail(GTB_ERR_STATE, "unknown region / pool not open");
+    regs[i] = it->second.get();
+    off[i + 1] = off[i] + align_up(regs[i]->accum_bytes, 256);
+  }
+  if (int rc = c->h_accum.reserve(off[n]))
+    return rc;
+  uint8_t * h = static_cast<uint8_t *>(c->h_accum.p);
+  for (int i = 0; i < n; ++i)
+    CUDA_TRY(cudaMemcpyAsync(h + off[i], regs[i]->accum.p, regs[i]->accum_bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  parallel_for(n, [&](int i) { convert_accumulators(*regs[i], h + off[i], &outs[i]); });
+  return 0;
+}
+
+int gtb_pool_finish(gtb_ctx * ctx, int region_id, gtb_accumulators * out)
+{
+  return gtb_pool_finish_multi(ctx, 1, &region_id, out);
+}
+
+// Zeroes the accumulators of several regions (one call, no synchronisation).
+int gtb_pool_reset_multi(gtb_ctx * ctx, int n, const int * region_ids)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  cudaSetDevice(c->device);
+  for (int i = 0; i < n; ++i)
+  {
+    auto it = c->regions.find(region_ids[i]);
+    if (it == c->regions.end() || !it->second->pool_open)
+      return fail(GTB_ERR_STATE, "unknown region / pool not open");
+    CUDA_TRY(cudaMemsetAsync(it->second->accum.p, 0, it->second->accum_bytes, c->stream));
+  }
   return 0;
 }
 

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libgtb200.so")
 EXPORTS = [
     "gtb_last_error", "gtb_version", "gtb_create", "gtb_destroy", "gtb_region_begin", "gtb_region_end",
     "gtb_index_size", "gtb_index_export", "gtb_pool_begin", "gtb_submit_reads", "gtb_accumulator_sizes",
-    "gtb_pool_finish", "gtb_submit_reads_multi", "gtb_debug_enable", "gtb_debug_seed_sizes", "gtb_debug_seeds",
+    "gtb_pool_finish", "gtb_pool_finish_multi", "gtb_pool_reset_multi", "gtb_submit_reads_multi", "gtb_debug_enable", "gtb_debug_seed_sizes", "gtb_debug_seeds",
     "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_replay_last",
     "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators",
 ]
@@ -58,6 +58,8 @@ def load_library() -> C.CDLL:
     L.gtb_submit_reads_multi.argtypes = [vp, C.c_int, abi.i32p, C.POINTER(abi.ReadBatch), C.POINTER(abi.SubmitStats)]
     L.gtb_accumulator_sizes.argtypes = [vp, C.c_int, abi.u32p, abi.u64p, abi.u64p]
     L.gtb_pool_finish.argtypes = [vp, C.c_int, C.POINTER(abi.Accumulators)]
+    L.gtb_pool_finish_multi.argtypes = [vp, C.c_int, abi.i32p, C.POINTER(abi.Accumulators)]
+    L.gtb_pool_reset_multi.argtypes = [vp, C.c_int, abi.i32p]
     L.gtb_debug_enable.argtypes = [vp, C.c_int]
     L.gtb_debug_seed_sizes.argtypes = [vp, C.c_int, abi.u64p, abi.u64p, abi.u64p]
     L.gtb_debug_seeds.argtypes = [vp, C.c_int, abi.u32p, abi.u32p, abi.u32p, C.POINTER(abi.Label)]
@@ -166,6 +168,26 @@ class Context:
         acc = abi.HostAccumulators(nb.value, ns.value, nc.value, self._samples[region_id])
         self._check(self.lib.gtb_pool_finish(self.h, region_id, C.byref(acc.view)))
         return acc
+
+    def alloc_accumulators(self, region_id: int) -> abi.HostAccumulators:
+        nb, ns, nc = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.gtb_accumulator_sizes(self.h, region_id, C.byref(nb), C.byref(ns), C.byref(nc)))
+        return abi.HostAccumulators(nb.value, ns.value, nc.value, self._samples[region_id])
+
+    def pool_finish_multi(self, region_ids: Sequence[int], out: Optional[List[abi.HostAccumulators]] = None):
+        """Accumulators of several regions with one stream synchronisation; `out` buffers are reused when given."""
+        n = len(region_ids)
+        if out is None:
+            out = [self.alloc_accumulators(r) for r in region_ids]
+        ids = (C.c_int32 * n)(*region_ids)
+        arr = (abi.Accumulators * n)(*[a.view for a in out])
+        self._check(self.lib.gtb_pool_finish_multi(self.h, n, ids, arr))
+        return out
+
+    def pool_reset_multi(self, region_ids: Sequence[int]) -> None:
+        n = len(region_ids)
+        ids = (C.c_int32 * n)(*region_ids)
+        self._check(self.lib.gtb_pool_reset_multi(self.h, n, ids))
 
     # -- debug taps
     def debug_enable(self, on: bool = True) -> None:

@@ -169,6 +169,9 @@ int gtb_pool_begin(gtb_ctx *ctx, int region_id, int n_samples);
 int gtb_submit_reads(gtb_ctx *ctx, int region_id, const gtb_read_batch *batch, gtb_submit_stats *stats);
 int gtb_accumulator_sizes(gtb_ctx *ctx, int region_id, uint32_t *n_bubbles, uint64_t *n_scores, uint64_t *n_cov);
 int gtb_pool_finish(gtb_ctx *ctx, int region_id, gtb_accumulators *out);
+/* Several regions with one stream synchronisation (outs[i] belongs to region_ids[i]); zero several pools. */
+int gtb_pool_finish_multi(gtb_ctx *ctx, int n, const int *region_ids, gtb_accumulators *outs);
+int gtb_pool_reset_multi(gtb_ctx *ctx, int n, const int *region_ids);
 
 /* Region-batched submission: regions[i] / batches[i] for i < n; one fused launch sequence for all. */
 int gtb_submit_reads_multi(gtb_ctx *ctx, int n, const int *region_ids, const gtb_read_batch *batches,

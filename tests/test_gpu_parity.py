@@ -97,3 +97,34 @@ def test_replay_accumulates_linearly(ctx):
             assert np.array_equal(a3[k], a1[k]), k
     finally:
         ctx.region_end(9)
+
+
+def test_full_config2_workload_matches_oracle(ctx, oracle_lib):
+    """BASELINE configs[1] at full size (1 Mb, 10k sites, 2e5 records, 20 regions, one region-batched submit):
+    accumulators of every region bit-identical to the oracle; PL/GT/GQ identical."""
+    import bench
+    ref, sites, gts, rs, regions, graphs, batches = bench.make_workload(0)
+    ids = list(range(200, 200 + len(graphs)))
+    for k, g in zip(ids, graphs):
+        ctx.region_begin(k, g)
+        ctx.pool_begin(k, 1)
+    try:
+        st = ctx.submit_multi(ids, batches)
+        assert st.n_records == 200000 and st.n_capacity_overflow == 0
+        accs = ctx.pool_finish_multi(ids)
+        n_scored = 0
+        for g, b, acc in zip(graphs, batches, accs):
+            h = oracle_lib.index_build(g)
+            r = oracle_lib.pool_run(g, h, 1, b, tap=False)
+            ref_acc = oracle_lib.result_accum(r, 1)
+            n_scored += oracle_lib.result_stats(r).n_pairs_scored
+            compare.compare_accum({k: v for k, v in ref_acc.as_dict().items() if k != "saturated"}, acc.as_dict(), "cuda-1Mb")
+            a, bb, cc = ctx.calls(acc)
+            a2, b2, c2 = oracle_lib.calls(ref_acc)
+            assert np.array_equal(a, a2) and np.array_equal(bb, b2) and np.array_equal(cc, c2)
+            oracle_lib.result_free(r)
+            oracle_lib.index_free(h)
+        assert st.n_pairs_scored == n_scored
+    finally:
+        for k in ids:
+            ctx.region_end(k)
