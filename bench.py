@@ -257,6 +257,8 @@ def main() -> None:
     n_reads = sum(len(b) for b in batches)
     config["reads_per_gpu"] = n_reads
     ctx = engine.Context(device=local_rank)
+    # inputs live in page-locked host memory (gtb_host_alloc), as a production caller would fill them
+    batches, pinned_arena = engine.pin_batches(batches)
     t0 = time.perf_counter()
     for k, g in enumerate(graphs):
         ctx.region_begin(k, g)

@@ -8,6 +8,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <functional>
 #include <thread>
 #include <cmath>
@@ -118,25 +120,52 @@ struct Region
   size_t accum_bytes = 0;
 };
 
+// Everything one in-flight (chunk of a) submit owns.  Slot 0 doubles as the "last batch" of the debug taps.
+struct BatchState
+{
+  DeviceBuffer d_batch, d_summaries, d_pool, d_counters, d_seedrecs, d_slow;
+  PinnedBuffer h_batch, h_counters;
+  LaunchParams P{};
+  uint32_t n_tasks = 0;
+  std::vector<int> regions;            // region ids of this chunk, in batch order
+  std::vector<uint32_t> unit_begin;    // per region: first unit index (size n+1)
+  std::vector<uint32_t> rec_begin;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // ev: 0 h2d start (copy stream), 1 h2d done (copy stream), 2 kernels start, 3 after probe, 4 after chain,
+  //     5 after slow, 6 after score, 7 after counters D2H
+  void release()
+  {
+    d_batch.release();
+    d_summaries.release();
+    d_pool.release();
+    d_counters.release();
+    d_seedrecs.release();
+    d_slow.release();
+    h_batch.release();
+    h_counters.release();
+    for (auto & e : ev)
+      if (e)
+        cudaEventDestroy(e);
+  }
+};
+constexpr int MAX_CHUNKS = 4;
+
 struct Ctx
 {
   int device = -1;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  BatchState bs[MAX_CHUNKS];
+  int n_chunks_last = 0;
   std::map<int, std::unique_ptr<Region>> regions;
   std::vector<int> slot_region; // slot -> region id (-1 free)
   DeviceBuffer d_regions;       // DevRegion table
   bool regions_dirty = true;
   // batch
-  DeviceBuffer d_batch, d_summaries, d_pool, d_counters, d_tap_counts, d_tap_pool, d_spill, d_seedrecs, d_slow;
-  PinnedBuffer h_batch, h_counters, h_accum;
-  LaunchParams last{};
+  DeviceBuffer d_tap_counts, d_tap_pool, d_spill;
+  PinnedBuffer h_stage, h_accum;
   bool have_last = false;
-  uint32_t last_n_tasks = 0;
   bool debug = false;
-  std::vector<int> last_regions; // region ids of the last submit, in batch order
-  std::vector<uint32_t> last_unit_begin; // per region of the last submit: first unit index (size n+1)
-  std::vector<uint32_t> last_rec_begin;
   float t_h2d = 0, t_align = 0, t_score = 0, t_d2h = 0, t_probe = 0, t_chain = 0, t_slow = 0;
   unsigned long long last_n_slow = 0;
   // nccl (loaded lazily with dlopen, see gtb_nccl.cpp part below)
@@ -193,27 +222,99 @@ int validate_graph(const gtb_graph_view * g)
   return 0;
 }
 
-// tiny fork-join helper for the host-side staging work (regions are independent)
+// Persistent fork-join pool for the host-side staging work (regions are independent jobs).
+class WorkPool
+{
+public:
+  WorkPool()
+  {
+    int const hw = (int)std::thread::hardware_concurrency();
+    n_workers_ = std::max(1, std::min(8, hw > 0 ? hw : 1)) - 1; // the caller thread works too
+    for (int t = 0; t < n_workers_; ++t)
+      threads_.emplace_back([this]() { worker(); });
+  }
+  ~WorkPool()
+  {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    for (auto & t : threads_)
+      t.join();
+  }
+  void run(int n, const std::function<void(int)> & fn)
+  {
+    if (n <= 0)
+      return;
+    if (n == 1 || n_workers_ == 0)
+    {
+      for (int i = 0; i < n; ++i)
+        fn(i);
+      return;
+    }
+    std::lock_guard<std::mutex> serial(run_m_);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      fn_ = &fn;
+      n_ = n;
+      next_.store(0);
+      pending_ = n_workers_;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    drain();
+    std::unique_lock<std::mutex> lk(m_);
+    done_cv_.wait(lk, [this]() { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+private:
+  void drain()
+  {
+    for (;;)
+    {
+      int const i = next_.fetch_add(1);
+      if (i >= n_)
+        break;
+      (*fn_)(i);
+    }
+  }
+  void worker()
+  {
+    unsigned long seen = 0;
+    for (;;)
+    {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&]() { return epoch_ != seen; });
+        seen = epoch_;
+        if (stop_)
+          return;
+      }
+      drain();
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        --pending_;
+      }
+      done_cv_.notify_one();
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex m_, run_m_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int)> * fn_ = nullptr;
+  std::atomic<int> next_{0};
+  int n_ = 0, n_workers_ = 0, pending_ = 0;
+  unsigned long epoch_ = 0;
+  bool stop_ = false;
+};
+
 void parallel_for(int n, const std::function<void(int)> & fn)
 {
-  int const hw = (int)std::thread::hardware_concurrency();
-  int const T = std::max(1, std::min({n, 8, hw > 0 ? hw : 1}));
-  if (T <= 1)
-  {
-    for (int i = 0; i < n; ++i)
-      fn(i);
-    return;
-  }
-  std::vector<std::thread> th;
-  th.reserve(T);
-  for (int t = 0; t < T; ++t)
-    th.emplace_back([&, t]()
-                    {
-                      for (int i = t; i < n; i += T)
-                        fn(i);
-                    });
-  for (auto & x : th)
-    x.join();
+  static WorkPool pool;
+  pool.run(n, fn);
 }
 
 template <typename T>
@@ -251,8 +352,11 @@ int gtb_create(int device_id, gtb_ctx ** out)
     e = cudaSetDevice(device_id);
     if (e == cudaSuccess)
       e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 8 && e == cudaSuccess; ++i)
-      e = cudaEventCreate(&c->ev[i]);
+    if (e == cudaSuccess)
+      e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < MAX_CHUNKS; ++k)
+      for (int i = 0; i < 8 && e == cudaSuccess; ++i)
+        e = cudaEventCreate(&c->bs[k].ev[i]);
     if (e != cudaSuccess)
     {
       delete c;
@@ -279,21 +383,15 @@ void gtb_destroy(gtb_ctx * ctx)
       kv.second->accum.release();
     }
     c->d_regions.release();
-    c->d_batch.release();
-    c->d_summaries.release();
-    c->d_pool.release();
-    c->d_counters.release();
+    for (auto & B : c->bs)
+      B.release();
     c->d_tap_counts.release();
     c->d_tap_pool.release();
     c->d_spill.release();
-    c->d_seedrecs.release();
-    c->d_slow.release();
-    c->h_batch.release();
-    c->h_counters.release();
+    c->h_stage.release();
     c->h_accum.release();
-    for (auto & e : c->ev)
-      if (e)
-        cudaEventDestroy(e);
+    if (c->copy_stream)
+      cudaStreamDestroy(c->copy_stream);
     if (c->stream)
       cudaStreamDestroy(c->stream);
   }
@@ -355,9 +453,9 @@ int gtb_region_begin(gtb_ctx * ctx, int region_id, const gtb_graph_view * g)
     size_t const o_labels = place<DevLabel>(off, R->index.labels.size());
     size_t const total = align_up(off, 256);
 
-    if (int rc = c->h_batch.reserve(total))
+    if (int rc = c->h_stage.reserve(total))
       return rc;
-    uint8_t * h = static_cast<uint8_t *>(c->h_batch.p);
+    uint8_t * h = static_cast<uint8_t *>(c->h_stage.p);
     memset(h, 0, total);
     auto put32 = [&](size_t o, const uint32_t * src, size_t n)
     {
@@ -552,92 +650,102 @@ int gtb_pool_begin(gtb_ctx * ctx, int region_id, int n_samples)
   return 0;
 }
 
-static int run_kernels(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
+// Enqueues the kernel sequence of one chunk on the compute stream (after its H2D copy has landed).
+static int launch_chunk(Ctx * c, BatchState & B)
 {
-  LaunchParams & P = c->last;
-  CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, sizeof(DevCounters), c->stream));
+  LaunchParams & P = B.P;
+  CUDA_TRY(cudaStreamWaitEvent(c->stream, B.ev[1], 0));
+  CUDA_TRY(cudaMemsetAsync(B.d_counters.p, 0, sizeof(DevCounters), c->stream));
   // orientations that are not aligned keep an all-zero summary (no paths)
   CUDA_TRY(cudaMemsetAsync(P.summaries, 0, (size_t)P.batch.n_units * 2 * sizeof(TaskSummary), c->stream));
   if (P.tap.list_count)
     CUDA_TRY(cudaMemsetAsync(P.tap.list_count, 0, (size_t)P.batch.n_units * 2 * (NLISTS * 2 + 1) * 4, c->stream));
-  CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+  CUDA_TRY(cudaEventRecord(B.ev[2], c->stream));
   launch_probe(P, c->stream);
-  CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+  CUDA_TRY(cudaEventRecord(B.ev[3], c->stream));
   launch_chain(P, c->stream);
-  CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
+  CUDA_TRY(cudaEventRecord(B.ev[4], c->stream));
   launch_slow(P, c->stream);
-  CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+  CUDA_TRY(cudaEventRecord(B.ev[5], c->stream));
   launch_score(P, c->stream);
-  CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
-  CUDA_TRY(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+  CUDA_TRY(cudaEventRecord(B.ev[6], c->stream));
+  CUDA_TRY(cudaMemcpyAsync(B.h_counters.p, B.d_counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaEventRecord(B.ev[7], c->stream));
+  return 0;
+}
+
+// After the stream has been synchronised: timings, counters, errors of all chunks of the last submit/replay.
+static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
+{
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaGetLastError());
   if (record_h2d)
-    cudaEventElapsedTime(&c->t_h2d, c->ev[0], c->ev[1]);
-  cudaEventElapsedTime(&c->t_align, c->ev[1], c->ev[2]);
-  cudaEventElapsedTime(&c->t_probe, c->ev[1], c->ev[5]);
-  cudaEventElapsedTime(&c->t_chain, c->ev[5], c->ev[6]);
-  cudaEventElapsedTime(&c->t_slow, c->ev[6], c->ev[2]);
-  cudaEventElapsedTime(&c->t_score, c->ev[2], c->ev[3]);
-  cudaEventElapsedTime(&c->t_d2h, c->ev[3], c->ev[4]);
-  DevCounters const * k = static_cast<DevCounters *>(c->h_counters.p);
-  c->last_n_slow = k->n_slow;
-  if (stats)
+    c->t_h2d = 0;
+  c->t_align = c->t_probe = c->t_chain = c->t_slow = c->t_score = c->t_d2h = 0;
+  c->last_n_slow = 0;
+  gtb_submit_stats st{};
+  unsigned long long n_overflow = 0, n_input_error = 0, reasons[12] = {0};
+  for (int k = 0; k < c->n_chunks_last; ++k)
   {
-    stats->n_records = P.batch.n_records;
-    stats->n_alignments = P.batch.n_units;
-    stats->n_oriented = P.n_active;
-    stats->n_pairs_scored = k->n_pairs_scored;
-    stats->n_singles_scored = k->n_singles_scored;
-    stats->n_capacity_overflow = k->n_overflow;
-    stats->kernel_launches = (P.n_active ? 3 : 0) + (P.batch.n_records ? 1 : 0);
+    BatchState & B = c->bs[k];
+    float t = 0;
+    if (record_h2d)
+    {
+      cudaEventElapsedTime(&t, B.ev[0], B.ev[1]);
+      c->t_h2d += t;
+    }
+    cudaEventElapsedTime(&t, B.ev[2], B.ev[3]);
+    c->t_probe += t;
+    cudaEventElapsedTime(&t, B.ev[3], B.ev[4]);
+    c->t_chain += t;
+    cudaEventElapsedTime(&t, B.ev[4], B.ev[5]);
+    c->t_slow += t;
+    cudaEventElapsedTime(&t, B.ev[5], B.ev[6]);
+    c->t_score += t;
+    cudaEventElapsedTime(&t, B.ev[6], B.ev[7]);
+    c->t_d2h += t;
+    DevCounters const * kc = static_cast<DevCounters *>(B.h_counters.p);
+    c->last_n_slow += kc->n_slow;
+    st.n_records += B.P.batch.n_records;
+    st.n_alignments += B.P.batch.n_units;
+    st.n_oriented += B.P.n_active;
+    st.n_pairs_scored += kc->n_pairs_scored;
+    st.n_singles_scored += kc->n_singles_scored;
+    st.n_capacity_overflow += kc->n_overflow;
+    st.kernel_launches += (B.P.n_active ? 3 : 0) + (B.P.batch.n_records ? 1 : 0);
+    n_overflow += kc->n_overflow;
+    n_input_error += kc->n_input_error;
+    for (int q = 0; q < 12; ++q)
+      reasons[q] += kc->reasons[q];
   }
-  if (k->n_input_error)
+  c->t_align = c->t_probe + c->t_chain + c->t_slow;
+  if (stats)
+    *stats = st;
+  if (n_input_error)
     return fail(GTB_ERR_INPUT, "two mates with the same IS_FIRST_IN_PAIR flag (the reference aborts here, "
                                "hts_parallel_reader.cpp:306-315)");
-  if (k->n_overflow)
+  if (n_overflow)
   {
     static const char * names[12] = {"refs", "vars", "paths", "locs", "labels", "cand_vars", "cands", "keys", "tap",
                                      "pool", "read_len", "-"};
     std::string why;
     for (int q = 0; q < 12; ++q)
-      if (k->reasons[q])
-        why += std::string(" ") + names[q] + "=" + std::to_string(k->reasons[q]);
-    return fail(GTB_ERR_CAPACITY, std::to_string(k->n_overflow) +
+      if (reasons[q])
+        why += std::string(" ") + names[q] + "=" + std::to_string(reasons[q]);
+    return fail(GTB_ERR_CAPACITY, std::to_string(n_overflow) +
                                     " read(s) exceeded a device working-set capacity (gtb_device.cuh):" + why);
   }
   return 0;
 }
 
-int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const gtb_read_batch * batches,
-                           gtb_submit_stats * stats)
+// Stages one chunk (regions [0, n) of the given arrays) into B's pinned buffer with host threads, reserves the
+// device buffers, enqueues ONE H2D copy on the copy stream and fills B.P.
+static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, const gtb_read_batch * batches,
+                       Region * const * regs, bool with_tap)
 {
-  auto * c = reinterpret_cast<Ctx *>(ctx);
-  if (!c || n <= 0 || !region_ids || !batches)
-    return fail(GTB_ERR_ARG, "bad arguments");
-  if (c->device < 0)
-    return fail(GTB_ERR_CUDA, "host-only context: the genotyping path needs a CUDA device (no CPU fallback)");
-  cudaSetDevice(c->device);
   size_t total = 0;
-  std::vector<Region *> regs(n);
   for (int i = 0; i < n; ++i)
-  {
-    auto it = c->regions.find(region_ids[i]);
-    if (it == c->regions.end())
-      return fail(GTB_ERR_STATE, "unknown region in submit");
-    if (!it->second->pool_open)
-      return fail(GTB_ERR_STATE, "gtb_pool_begin must precede gtb_submit_reads");
-    regs[i] = it->second.get();
-    if (batches[i].n_reads && batches[i].seq_stride != GTB_SEQ_STRIDE)
-      return fail(GTB_ERR_ARG, "seq_stride must be GTB_SEQ_STRIDE (76)");
     total += batches[i].n_reads;
-  }
-  if (total >= 0x7FFFFFFFull)
-    return fail(GTB_ERR_ARG, "batch too large");
-  if (int rc = upload_region_table(c))
-    return rc;
-
   // ---- staging layout (one pinned buffer, one H2D copy)
   size_t off = 0;
   size_t const o_seq4 = place<uint8_t>(off, total * GTB_SEQ_STRIDE);
@@ -655,14 +763,14 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   size_t const o_urec = place<int32_t>(off, total);
   size_t const o_active = place<uint32_t>(off, total * 2);
   size_t const bytes = align_up(off, 256);
-  if (int rc = c->h_batch.reserve(bytes))
+  if (int rc = B.h_batch.reserve(bytes))
     return rc;
-  uint8_t * h = static_cast<uint8_t *>(c->h_batch.p);
+  uint8_t * h = static_cast<uint8_t *>(B.h_batch.p);
   int32_t * h_unit = reinterpret_cast<int32_t *>(h + o_unit);
   int32_t * h_urec = reinterpret_cast<int32_t *>(h + o_urec);
   int32_t * h_mate = reinterpret_cast<int32_t *>(h + o_mate);
   uint16_t * h_region = reinterpret_cast<uint16_t *>(h + o_region);
-  c->last_regions.assign(region_ids, region_ids + n);
+  B.regions.assign(region_ids, region_ids + n);
   // ---- pass 1 (parallel over regions): alignment units per region (records that are not duplicates of a previous one)
   std::vector<size_t> rec_base(n + 1, 0);
   std::vector<uint32_t> unit_base(n + 1, 0), active_cnt(n, 0);
@@ -685,6 +793,27 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   uint32_t const n_units = unit_base[n];
   uint32_t * h_active = reinterpret_cast<uint32_t *>(h + o_active);
   std::atomic<int> err_code{0};
+  if (int rc = B.d_batch.reserve(bytes))
+    return rc;
+  // Bases are 3/4 of the bytes.  When the caller keeps them in pinned (page-locked) host memory -- gtb_host_alloc or
+  // cudaHostRegister -- they are DMA-ed straight from the caller's buffers while the small columns are staged.
+  bool direct_seq = n > 0;
+  for (int i = 0; i < n && direct_seq; ++i)
+    if (batches[i].n_reads)
+    {
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, batches[i].seq4) != cudaSuccess || at.type != cudaMemoryTypeHost)
+      {
+        cudaGetLastError();
+        direct_seq = false;
+      }
+    }
+  CUDA_TRY(cudaEventRecord(B.ev[0], c->copy_stream));
+  if (direct_seq)
+    for (int i = 0; i < n; ++i)
+      if (batches[i].n_reads)
+        CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(B.d_batch.p) + o_seq4 + rec_base[i] * GTB_SEQ_STRIDE, batches[i].seq4,
+                                 (size_t)batches[i].n_reads * GTB_SEQ_STRIDE, cudaMemcpyHostToDevice, c->copy_stream));
   // ---- pass 2 (parallel over regions): copy the columns, number the units, rebase mate links, list the read
   //      orientations that are aligned at all (align_read, src/typer/alignment.cpp:331-363: forward always; reverse
   //      complement unless unpaired or a properly oriented pair within 1200 bp)
@@ -694,7 +823,8 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
                  size_t const m = b.n_reads, base = rec_base[i];
                  if (m == 0)
                    return;
-                 memcpy(h + o_seq4 + base * GTB_SEQ_STRIDE, b.seq4, m * GTB_SEQ_STRIDE);
+                 if (!direct_seq)
+                   memcpy(h + o_seq4 + base * GTB_SEQ_STRIDE, b.seq4, m * GTB_SEQ_STRIDE);
                  memcpy(h + o_lseq + base * 2, b.lseq, m * 2);
                  memcpy(h + o_flag + base * 2, b.flag, m * 2);
                  memcpy(h + o_mapq + base, b.mapq, m);
@@ -774,43 +904,45 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   }
   // compact the per-region active lists
   uint32_t n_active = 0;
-  c->last_unit_begin.assign(1, 0);
-  c->last_rec_begin.assign(1, 0);
+  B.unit_begin.assign(1, 0);
+  B.rec_begin.assign(1, 0);
   for (int i = 0; i < n; ++i)
   {
     uint32_t * src = h_active + 2 * (size_t)unit_base[i];
     if (src != h_active + n_active && active_cnt[i])
       memmove(h_active + n_active, src, (size_t)active_cnt[i] * 4);
     n_active += active_cnt[i];
-    c->last_unit_begin.push_back(unit_base[i + 1]);
-    c->last_rec_begin.push_back((uint32_t)rec_base[i + 1]);
+    B.unit_begin.push_back(unit_base[i + 1]);
+    B.rec_begin.push_back((uint32_t)rec_base[i + 1]);
   }
 
   uint32_t const n_tasks = n_units * 2;
-  if (int rc = c->d_seedrecs.reserve((size_t)n_active * SEED_REC_BYTES + 64))
+  if (int rc = B.d_seedrecs.reserve((size_t)n_active * SEED_REC_BYTES + 64))
     return rc;
-  if (int rc = c->d_slow.reserve((size_t)n_active * 4 + 64))
+  if (int rc = B.d_slow.reserve((size_t)n_active * 4 + 64))
     return rc;
-  if (int rc = c->d_batch.reserve(bytes))
-    return rc;
-  if (int rc = c->d_summaries.reserve((size_t)n_tasks * sizeof(TaskSummary) + 16))
+  if (int rc = B.d_summaries.reserve((size_t)n_tasks * sizeof(TaskSummary) + 16))
     return rc;
   size_t const pool_words = (size_t)n_tasks * INLINE_WORDS + (size_t)n_units * 64 + 65536;
-  if (int rc = c->d_pool.reserve(pool_words * 4))
+  if (int rc = B.d_pool.reserve(pool_words * 4))
     return rc;
-  if (int rc = c->d_counters.reserve(sizeof(DevCounters)))
+  if (int rc = B.d_counters.reserve(sizeof(DevCounters)))
     return rc;
   if (int rc = c->d_spill.reserve(align_spill_bytes()))
     return rc;
-  if (int rc = c->h_counters.reserve(sizeof(DevCounters)))
+  if (int rc = B.h_counters.reserve(sizeof(DevCounters)))
     return rc;
 
-  CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-  CUDA_TRY(cudaMemcpyAsync(c->d_batch.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
+  // only the used prefix of the active list is copied (it is the last column)
+  size_t const copy_end = o_active + (size_t)n_active * 4;
+  size_t const copy_begin = direct_seq ? o_lseq : 0;
+  CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(B.d_batch.p) + copy_begin, h + copy_begin, copy_end - copy_begin,
+                           cudaMemcpyHostToDevice, c->copy_stream));
+  CUDA_TRY(cudaEventRecord(B.ev[1], c->copy_stream));
 
-  LaunchParams & P = c->last;
+  LaunchParams & P = B.P;
   memset(&P, 0, sizeof(P));
-  uint8_t * d = static_cast<uint8_t *>(c->d_batch.p);
+  uint8_t * d = static_cast<uint8_t *>(B.d_batch.p);
   P.regions = static_cast<const DevRegion *>(c->d_regions.p);
   P.batch.n_records = (uint32_t)total;
   P.batch.n_units = n_units;
@@ -827,16 +959,16 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   P.batch.mate = reinterpret_cast<const int32_t *>(d + o_mate);
   P.batch.unit = reinterpret_cast<const int32_t *>(d + o_unit);
   P.batch.unit_record = reinterpret_cast<const int32_t *>(d + o_urec);
-  P.summaries = static_cast<TaskSummary *>(c->d_summaries.p);
-  P.path_pool = static_cast<uint32_t *>(c->d_pool.p);
+  P.summaries = static_cast<TaskSummary *>(B.d_summaries.p);
+  P.path_pool = static_cast<uint32_t *>(B.d_pool.p);
   P.path_pool_cap = pool_words;
-  P.counters = static_cast<DevCounters *>(c->d_counters.p);
+  P.counters = static_cast<DevCounters *>(B.d_counters.p);
   P.cand_spill = c->d_spill.p;
   P.n_active = n_active;
   P.active_tasks = reinterpret_cast<const uint32_t *>(d + o_active);
-  P.seed_recs = c->d_seedrecs.p;
-  P.slow_tasks = static_cast<uint32_t *>(c->d_slow.p);
-  if (c->debug)
+  P.seed_recs = B.d_seedrecs.p;
+  P.slow_tasks = static_cast<uint32_t *>(B.d_slow.p);
+  if (with_tap)
   {
     size_t const tap_counts = (size_t)n_tasks * (NLISTS * 2 + 1) * 4;
     size_t const tap_labels = (size_t)n_tasks * 512 + 65536;
@@ -851,9 +983,74 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
     P.tap.pool = static_cast<DevLabel *>(c->d_tap_pool.p);
     P.tap.pool_cap = tap_labels;
   }
-  c->last_n_tasks = n_tasks;
+  B.n_tasks = n_tasks;
+  return 0;
+}
+
+int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const gtb_read_batch * batches,
+                           gtb_submit_stats * stats)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || n <= 0 || !region_ids || !batches)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  if (c->device < 0)
+    return fail(GTB_ERR_CUDA, "host-only context: the genotyping path needs a CUDA device (no CPU fallback)");
+  cudaSetDevice(c->device);
+  size_t total = 0;
+  std::vector<Region *> regs(n);
+  for (int i = 0; i < n; ++i)
+  {
+    auto it = c->regions.find(region_ids[i]);
+    if (it == c->regions.end())
+      return fail(GTB_ERR_STATE, "unknown region in submit");
+    if (!it->second->pool_open)
+      return fail(GTB_ERR_STATE, "gtb_pool_begin must precede gtb_submit_reads");
+    regs[i] = it->second.get();
+    if (batches[i].n_reads && batches[i].seq_stride != GTB_SEQ_STRIDE)
+      return fail(GTB_ERR_ARG, "seq_stride must be GTB_SEQ_STRIDE (76)");
+    total += batches[i].n_reads;
+  }
+  if (total >= 0x7FFFFFFFull)
+    return fail(GTB_ERR_ARG, "batch too large");
+  if (int rc = upload_region_table(c))
+    return rc;
+  c->have_last = false;
+
+  // ---- chunking: host staging of chunk k+1 overlaps the H2D copy and the kernels of chunk k.
+  //      Region boundaries are natural cut points (mate / duplicate links never cross regions).
+  int n_chunks = 1;
+  // (measured on B200/PCIe5: below a few million records chunking costs more in small-kernel inefficiency than
+  //  the overlap wins, so it only engages for very large submits)
+  if (!c->debug && n >= 2 && total >= 4000000)
+    n_chunks = std::min(n, MAX_CHUNKS);
+  std::vector<int> cut(n_chunks + 1, n);
+  cut[0] = 0;
+  {
+    size_t acc = 0;
+    int k = 1;
+    for (int i = 0; i < n && k < n_chunks; ++i)
+    {
+      acc += batches[i].n_reads;
+      if (acc * n_chunks >= total * k)
+      {
+        cut[k++] = i + 1;
+      }
+    }
+  }
+  for (int k = 1; k <= n_chunks; ++k)
+    cut[k] = std::max(cut[k], cut[k - 1]);
+  cut[n_chunks] = n;
+  c->n_chunks_last = n_chunks;
+  for (int k = 0; k < n_chunks; ++k)
+  {
+    int const b0 = cut[k], m = cut[k + 1] - cut[k];
+    if (int rc = stage_chunk(c, c->bs[k], m, region_ids + b0, batches + b0, regs.data() + b0, c->debug))
+      return rc;
+    if (int rc = launch_chunk(c, c->bs[k]))
+      return rc;
+  }
   c->have_last = true;
-  return run_kernels(c, stats, true);
+  return collect_chunks(c, stats, true);
 }
 
 int gtb_submit_reads(gtb_ctx * ctx, int region_id, const gtb_read_batch * batch, gtb_submit_stats * stats)
@@ -868,10 +1065,13 @@ int gtb_replay_last(gtb_ctx * ctx, gtb_submit_stats * stats)
   if (!c || !c->have_last)
     return fail(GTB_ERR_STATE, "no resident batch to replay");
   cudaSetDevice(c->device);
-  return run_kernels(c, stats, false);
+  for (int k = 0; k < c->n_chunks_last; ++k)
+    if (int rc = launch_chunk(c, c->bs[k]))
+      return rc;
+  return collect_chunks(c, stats, false);
 }
 
-// Device times (ms) of the last submit/replay measured with CUDA events on the library's stream.
+// Device times (ms) of the last submit/replay measured with CUDA events on the library's streams.
 int gtb_last_timing(gtb_ctx * ctx, float * h2d_ms, float * align_ms, float * score_ms, float * d2h_ms)
 {
   auto * c = reinterpret_cast<Ctx *>(ctx);
@@ -901,6 +1101,24 @@ int gtb_last_kernel_timing(gtb_ctx * ctx, float * probe_ms, float * chain_ms, fl
     *score_ms = c->t_score;
   if (n_slow)
     *n_slow = c->last_n_slow;
+  return 0;
+}
+
+// Page-locked host memory for callers that want their batch columns DMA-ed without an intermediate staging copy.
+int gtb_host_alloc(size_t bytes, void ** out)
+{
+  if (!out)
+    return fail(GTB_ERR_ARG, "null out");
+  cudaError_t const e = cudaMallocHost(out, bytes ? bytes : 1);
+  if (e != cudaSuccess)
+    return fail(GTB_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int gtb_host_free(void * p)
+{
+  if (p)
+    cudaFreeHost(p);
   return 0;
 }
 
@@ -1031,10 +1249,13 @@ int gtb_debug_enable(gtb_ctx * ctx, int on)
   return 0;
 }
 
+// debug taps look at chunk 0 (a submit made with gtb_debug_enable is never chunked)
 static int find_last_region(Ctx * c, int region_id)
 {
-  for (size_t i = 0; i < c->last_regions.size(); ++i)
-    if (c->last_regions[i] == region_id)
+  if (c->n_chunks_last != 1)
+    return -1;
+  for (size_t i = 0; i < c->bs[0].regions.size(); ++i)
+    if (c->bs[0].regions[i] == region_id)
       return (int)i;
   return -1;
 }
@@ -1043,14 +1264,14 @@ int gtb_debug_seed_sizes(gtb_ctx * ctx, int region_id, uint64_t * n_units, uint6
 {
   auto * c = reinterpret_cast<Ctx *>(ctx);
   int const k = c->have_last ? find_last_region(c, region_id) : -1;
-  if (k < 0 || !c->last.tap.list_count)
+  if (k < 0 || !c->bs[0].P.tap.list_count)
     return fail(GTB_ERR_STATE, "no debug tap for this region (gtb_debug_enable before submit)");
   cudaSetDevice(c->device);
-  uint32_t const u0 = c->last_unit_begin[k], u1 = c->last_unit_begin[k + 1];
+  uint32_t const u0 = c->bs[0].unit_begin[k], u1 = c->bs[0].unit_begin[k + 1];
   size_t const nt = (size_t)(u1 - u0) * 2;
   std::vector<uint32_t> counts(nt * NLISTS), nsl(nt);
-  CUDA_TRY(cudaMemcpy(counts.data(), c->last.tap.list_count + (size_t)u0 * 2 * NLISTS, counts.size() * 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(nsl.data(), c->last.tap.nslots + (size_t)u0 * 2, nsl.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(counts.data(), c->bs[0].P.tap.list_count + (size_t)u0 * 2 * NLISTS, counts.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(nsl.data(), c->bs[0].P.tap.nslots + (size_t)u0 * 2, nsl.size() * 4, cudaMemcpyDeviceToHost));
   uint64_t ns = 0, nl = 0;
   for (size_t t = 0; t < nt; ++t)
   {
@@ -1069,26 +1290,26 @@ int gtb_debug_seeds(gtb_ctx * ctx, int region_id, uint32_t * unit_record, uint32
 {
   auto * c = reinterpret_cast<Ctx *>(ctx);
   int const k = c->have_last ? find_last_region(c, region_id) : -1;
-  if (k < 0 || !c->last.tap.list_count)
+  if (k < 0 || !c->bs[0].P.tap.list_count)
     return fail(GTB_ERR_STATE, "no debug tap for this region");
   cudaSetDevice(c->device);
-  uint32_t const u0 = c->last_unit_begin[k], u1 = c->last_unit_begin[k + 1];
+  uint32_t const u0 = c->bs[0].unit_begin[k], u1 = c->bs[0].unit_begin[k + 1];
   size_t const nu = u1 - u0, nt = nu * 2;
   std::vector<uint32_t> counts(nt * NLISTS), offs(nt * NLISTS), nsl(nt);
   std::vector<int32_t> urec(nu);
-  CUDA_TRY(cudaMemcpy(counts.data(), c->last.tap.list_count + (size_t)u0 * 2 * NLISTS, counts.size() * 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(offs.data(), c->last.tap.list_off + (size_t)u0 * 2 * NLISTS, offs.size() * 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(nsl.data(), c->last.tap.nslots + (size_t)u0 * 2, nsl.size() * 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(urec.data(), c->last.batch.unit_record + u0, nu * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(counts.data(), c->bs[0].P.tap.list_count + (size_t)u0 * 2 * NLISTS, counts.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(offs.data(), c->bs[0].P.tap.list_off + (size_t)u0 * 2 * NLISTS, offs.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(nsl.data(), c->bs[0].P.tap.nslots + (size_t)u0 * 2, nsl.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(urec.data(), c->bs[0].P.batch.unit_record + u0, nu * 4, cudaMemcpyDeviceToHost));
   DevCounters k_host;
-  CUDA_TRY(cudaMemcpy(&k_host, c->d_counters.p, sizeof(k_host), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(&k_host, c->bs[0].d_counters.p, sizeof(k_host), cudaMemcpyDeviceToHost));
   std::vector<DevLabel> pool(k_host.dbg_label_words);
   if (!pool.empty())
-    CUDA_TRY(cudaMemcpy(pool.data(), c->last.tap.pool, pool.size() * sizeof(DevLabel), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(pool.data(), c->bs[0].P.tap.pool, pool.size() * sizeof(DevLabel), cudaMemcpyDeviceToHost));
   size_t si = 0, li = 0;
   for (size_t u = 0; u < nu; ++u)
   {
-    unit_record[u] = (uint32_t)(urec[u] - (int32_t)c->last_rec_begin[k]);
+    unit_record[u] = (uint32_t)(urec[u] - (int32_t)c->bs[0].rec_begin[k]);
     for (int o = 0; o < 2; ++o)
     {
       size_t const t = u * 2 + o;
@@ -1117,16 +1338,16 @@ int gtb_debug_seeds(gtb_ctx * ctx, int region_id, uint32_t * unit_record, uint32
 
 static int fetch_paths(Ctx * c, int k, std::vector<TaskSummary> & sums, std::vector<uint32_t> & pool)
 {
-  uint32_t const u0 = c->last_unit_begin[k], u1 = c->last_unit_begin[k + 1];
+  uint32_t const u0 = c->bs[0].unit_begin[k], u1 = c->bs[0].unit_begin[k + 1];
   sums.resize((size_t)(u1 - u0) * 2);
   if (!sums.empty())
-    CUDA_TRY(cudaMemcpy(sums.data(), c->last.summaries + (size_t)u0 * 2, sums.size() * sizeof(TaskSummary), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(sums.data(), c->bs[0].P.summaries + (size_t)u0 * 2, sums.size() * sizeof(TaskSummary), cudaMemcpyDeviceToHost));
   DevCounters k_host;
-  CUDA_TRY(cudaMemcpy(&k_host, c->d_counters.p, sizeof(k_host), cudaMemcpyDeviceToHost));
-  size_t const words = (size_t)c->last_n_tasks * INLINE_WORDS + k_host.path_words;
-  pool.resize(std::min<size_t>(words, c->last.path_pool_cap));
+  CUDA_TRY(cudaMemcpy(&k_host, c->bs[0].d_counters.p, sizeof(k_host), cudaMemcpyDeviceToHost));
+  size_t const words = (size_t)c->bs[0].n_tasks * INLINE_WORDS + k_host.path_words;
+  pool.resize(std::min<size_t>(words, c->bs[0].P.path_pool_cap));
   if (!pool.empty())
-    CUDA_TRY(cudaMemcpy(pool.data(), c->last.path_pool, pool.size() * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(pool.data(), c->bs[0].P.path_pool, pool.size() * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -22,7 +22,7 @@ EXPORTS = [
     "gtb_index_size", "gtb_index_export", "gtb_pool_begin", "gtb_submit_reads", "gtb_accumulator_sizes",
     "gtb_pool_finish", "gtb_pool_finish_multi", "gtb_pool_reset_multi", "gtb_submit_reads_multi", "gtb_debug_enable", "gtb_debug_seed_sizes", "gtb_debug_seeds",
     "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_replay_last",
-    "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators",
+    "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators",
 ]
 
 
@@ -71,11 +71,54 @@ def load_library() -> C.CDLL:
     L.gtb_last_timing.argtypes = [vp, fp, fp, fp, fp]
     L.gtb_last_kernel_timing.argtypes = [vp, fp, fp, fp, fp, abi.u64p]
     L.gtb_pool_reset.argtypes = [vp, C.c_int]
+    L.gtb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.gtb_host_free.argtypes = [vp]
     L.gtb_nccl_unique_id.argtypes = [abi.u8p]
     L.gtb_nccl_init.argtypes = [vp, C.c_int, C.c_int, abi.u8p]
     L.gtb_allreduce_accumulators.argtypes = [vp, C.c_int, vp]
     _lib = L
     return L
+
+
+class PinnedArena:
+    """Page-locked host memory from gtb_host_alloc, handed out as numpy arrays (freed with the arena)."""
+
+    def __init__(self, nbytes: int):
+        self.lib = load_library()
+        self.ptr = C.c_void_p()
+        rc = self.lib.gtb_host_alloc(nbytes, C.byref(self.ptr))
+        if rc != 0:
+            raise GtbError(rc, self.lib.gtb_last_error().decode())
+        self.nbytes = nbytes
+        self.used = 0
+
+    def take(self, arr: np.ndarray) -> np.ndarray:
+        """Copy of `arr` living in the arena."""
+        off = (self.used + 255) // 256 * 256
+        if off + arr.nbytes > self.nbytes:
+            raise MemoryError("pinned arena exhausted")
+        buf = (C.c_uint8 * arr.nbytes).from_address(self.ptr.value + off)
+        out = np.frombuffer(buf, dtype=arr.dtype).reshape(arr.shape)
+        out[...] = arr
+        self.used = off + arr.nbytes
+        return out
+
+    def close(self) -> None:
+        if self.ptr:
+            self.lib.gtb_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+def pin_batches(batches: Sequence[abi.HostBatch]) -> Tuple[List[abi.HostBatch], "PinnedArena"]:
+    """Re-homes the batch columns in page-locked memory (what a production caller fills directly)."""
+    total = sum(b.nbytes_h2d() + 16 * 256 for b in batches) + 4096
+    arena = PinnedArena(total)
+    out = []
+    for b in batches:
+        out.append(abi.HostBatch(arena.take(b.seq4), arena.take(b.lseq), arena.take(b.flag), arena.take(b.mapq),
+                                 arena.take(b.isize), arena.take(b.same_tid), arena.take(b.score_diff),
+                                 arena.take(b.clipped), arena.take(b.sample), arena.take(b.mate), arena.take(b.dup_of)))
+    return out, arena
 
 
 class Context:

@@ -202,6 +202,9 @@ int gtb_last_timing(gtb_ctx *ctx, float *h2d_ms, float *align_ms, float *score_m
 int gtb_last_kernel_timing(gtb_ctx *ctx, float *probe_ms, float *chain_ms, float *slow_ms, float *score_ms,
                            uint64_t *n_slow);
 int gtb_pool_reset(gtb_ctx *ctx, int region_id);
+/* Page-locked host memory: batch columns (seq4 above all) placed here are DMA-ed without a staging copy. */
+int gtb_host_alloc(size_t bytes, void **out);
+int gtb_host_free(void *p);
 
 /* NCCL bootstrap (libnccl is bound lazily with dlopen): rank 0 creates the 128-byte unique id, the caller
  * distributes it (e.g. torch.distributed.broadcast), every rank calls gtb_nccl_init. */

@@ -128,3 +128,22 @@ def test_full_config2_workload_matches_oracle(ctx, oracle_lib):
     finally:
         for k in ids:
             ctx.region_end(k)
+
+
+def test_pinned_inputs_take_the_direct_dma_path_with_equal_results(ctx):
+    """Columns in page-locked memory (gtb_host_alloc) skip the staging copy; results must not change."""
+    pre = ALL[1]
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    rd = gtba.load(pre + ".reads.gtba")
+    b = abi.batch_from_probe(rd)
+    ns = n_samples_of(rd)
+    pb, arena = engine.pin_batches([b])
+    ctx.region_begin(11, g)
+    try:
+        ctx.pool_begin(11, ns)
+        ctx.submit(11, pb[0])
+        acc = ctx.pool_finish(11)
+        compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), acc.as_dict(), "cuda-pinned")
+    finally:
+        ctx.region_end(11)
+        arena.close()
