@@ -360,3 +360,39 @@ def batch_from_probe(d: Dict[str, np.ndarray]) -> HostBatch:
     return HostBatch(seq4, lseq, d["flag"], d["mapq"], np.clip(d["isize"], -2**31, 2**31 - 1),
                      (d["tid"] == d["mtid"]).astype(np.uint8), d["score_diff"], np.zeros(n, np.uint8),
                      d["sample"], mate, dup)
+
+
+def shard_batch(batch: HostBatch, n_shards: int) -> List[HostBatch]:
+    """Splits one pool's records over `n_shards` GPUs for the "one sample on N GPUs" mode.
+    Records connected by a mate link or a duplicate link stay together (union-find), so every shard reproduces
+    exactly the alignments and pairings of the unsharded stream; accumulators are additive, so the shards' widened
+    accumulators sum (NCCL all-reduce) to the unsharded result."""
+    n = len(batch)
+    parent = np.arange(n)
+
+    def find(x: int) -> int:
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    for i in range(n):
+        for j in (int(batch.mate[i]), int(batch.dup_of[i])):
+            if j >= 0:
+                a, b = find(i), find(j)
+                if a != b:
+                    parent[max(a, b)] = min(a, b)
+    roots = np.array([find(i) for i in range(n)])
+    uniq, comp = np.unique(roots, return_inverse=True)
+    shard_of = comp % n_shards
+    out = []
+    for s in range(n_shards):
+        idx = np.nonzero(shard_of == s)[0]
+        remap = np.full(n, -1, np.int64)
+        remap[idx] = np.arange(len(idx))
+        mate = np.where(batch.mate[idx] >= 0, remap[np.maximum(batch.mate[idx], 0)], -1)
+        dup = np.where(batch.dup_of[idx] >= 0, remap[np.maximum(batch.dup_of[idx], 0)], -1)
+        out.append(HostBatch(batch.seq4[idx], batch.lseq[idx], batch.flag[idx], batch.mapq[idx], batch.isize[idx],
+                             batch.same_tid[idx], batch.score_diff[idx], batch.clipped[idx], batch.sample[idx],
+                             mate, dup))
+    return out

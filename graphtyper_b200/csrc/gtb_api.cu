@@ -451,6 +451,7 @@ int gtb_region_begin(gtb_ctx * ctx, int region_id, const gtb_graph_view * g)
     size_t const o_cov_off = place<uint32_t>(off, R->n_bubbles + 1);
     size_t const o_table = place<IndexSlot>(off, R->index.table.size());
     size_t const o_labels = place<DevLabel>(off, R->index.labels.size());
+    size_t const o_tags = place<uint8_t>(off, R->index.tags.size());
     size_t const total = align_up(off, 256);
 
     if (int rc = c->h_stage.reserve(total))
@@ -486,6 +487,7 @@ int gtb_region_begin(gtb_ctx * ctx, int region_id, const gtb_graph_view * g)
     put32(o_cov_off, R->cov_off.data(), R->n_bubbles + 1);
     memcpy(h + o_table, R->index.table.data(), R->index.table.size() * sizeof(IndexSlot));
     memcpy(h + o_labels, R->index.labels.data(), R->index.labels.size() * sizeof(DevLabel));
+    memcpy(h + o_tags, R->index.tags.data(), R->index.tags.size());
 
     if (int rc = R->arena.reserve(total))
       return rc;
@@ -526,6 +528,7 @@ int gtb_region_begin(gtb_ctx * ctx, int region_id, const gtb_graph_view * g)
     D.cov_off = reinterpret_cast<const uint32_t *>(d + o_cov_off);
     D.table = reinterpret_cast<const IndexSlot *>(d + o_table);
     D.labels = reinterpret_cast<const DevLabel *>(d + o_labels);
+    D.tags = d + o_tags;
 
     // slot in the device region table
     int slot = -1;
@@ -1101,6 +1104,22 @@ int gtb_last_kernel_timing(gtb_ctx * ctx, float * probe_ms, float * chain_ms, fl
     *score_ms = c->t_score;
   if (n_slow)
     *n_slow = c->last_n_slow;
+  return 0;
+}
+
+// Diagnostic counters of the last submit/replay (chunk 0): out[0..11] = why chain_kernel handed tasks to slow_kernel
+// (refs vars paths locs labels cand_vars cands keys tap pool read_len probe-flag), out[12..23] = slow_kernel overflows.
+int gtb_debug_counters(gtb_ctx * ctx, uint64_t * out24)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !c->have_last || !out24)
+    return fail(GTB_ERR_STATE, "no submit yet");
+  DevCounters const * k = static_cast<DevCounters *>(c->bs[0].h_counters.p);
+  for (int q = 0; q < 12; ++q)
+  {
+    out24[q] = k->fast_reasons[q];
+    out24[12 + q] = k->reasons[q];
+  }
   return 0;
 }
 

@@ -60,6 +60,7 @@ struct DevRegion
   const uint32_t * cov_off;      // [n_bubbles+1]
   // index
   const IndexSlot * table;
+  const uint8_t * tags;          // [table capacity] one-byte slot tags, 16 consecutive slots per 16-byte window
   const DevLabel * labels;
   // accumulators (widened; clamped on download)
   uint32_t * log_score;     // [score_off[NB] * NS]
@@ -123,6 +124,7 @@ struct DevCounters
   unsigned long long n_input_error;  // mates with equal IS_FIRST_IN_PAIR
   unsigned long long dbg_label_words; // bump cursor of the debug seed pool
   unsigned long long n_slow;         // tasks queued for slow_kernel
+  unsigned long long fast_reasons[12]; // why chain_kernel handed a task to slow_kernel (same codes; [11] = probe flag)
   unsigned long long reasons[12];    // overflow histogram: refs vars paths locs labels candv cands keys tap pool len -
 };
 

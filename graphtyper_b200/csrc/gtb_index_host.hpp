@@ -44,10 +44,12 @@ struct HostIndex
   std::vector<uint32_t> label_off; // [n_keys + 1]
   std::vector<gtb_label> labels;   // bucket order = reference insertion order
   std::vector<IndexSlot> table;    // open addressing, power-of-two capacity, load <= 0.5
+  std::vector<uint8_t> tags;       // one byte per slot: 0 = empty, else 1 + (hash & 0xFF) % 255 (probe prefilter)
   uint32_t table_mask = 0;
 };
 
 inline uint64_t hash_key(uint64_t k) { return k * 0x9E3779B97F4A7C15ull; }
+inline uint8_t tag_of_hash(uint64_t h) { return (uint8_t)(1u + (uint32_t)(h & 0xFFu) % 255u); }
 
 class IndexBuilder
 {
@@ -328,9 +330,10 @@ private:
     out.label_off.push_back((uint32_t)out.labels.size());
     // open-addressing table, load factor <= 0.5
     size_t cap = 16;
-    while (cap < out.keys.size() * 2 + 2)
+    while (cap < out.keys.size() * 4 + 2) // load factor <= 0.25: an unsuccessful lookup (the 96 neighbours) averages 1.4 probes
       cap <<= 1;
     out.table.assign(cap, IndexSlot{0, 0, 0});
+    out.tags.assign(cap, 0);
     out.table_mask = (uint32_t)(cap - 1);
     int shift = 64;
     for (size_t c = cap; c > 1; c >>= 1)
@@ -342,6 +345,7 @@ private:
       while (out.table[h].cnt != 0)
         h = (h + 1) & out.table_mask;
       out.table[h] = IndexSlot{k, out.label_off[i], out.label_off[i + 1] - out.label_off[i]};
+      out.tags[h] = tag_of_hash(hash_key(k));
     }
     tuples_.clear();
     tuples_.shrink_to_fit();

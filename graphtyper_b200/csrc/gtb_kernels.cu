@@ -165,13 +165,17 @@ struct GR
 };
 
 // ------------------------------------------------------------------------------------------------ phase A: seeds
-__device__ __forceinline__ bool probe(const DevRegion & R, uint64_t key, uint32_t & off, uint32_t & cnt)
+__device__ __forceinline__ uint32_t slot_of(const DevRegion & R, uint64_t key)
 {
-  uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> R.table_shift);
+  return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> R.table_shift);
+}
+
+// continues a linear-probing lookup whose first slot `s` (at index h) has already been loaded
+__device__ __forceinline__ bool probe_resolve(const DevRegion & R, uint64_t key, uint32_t h, uint4 s, uint32_t & off, uint32_t & cnt)
+{
   const uint4 * tab = reinterpret_cast<const uint4 *>(R.table);
   while (true)
   {
-    uint4 const s = __ldg(tab + h);
     if (s.w == 0)
       return false;
     uint64_t const k = (uint64_t)s.x | ((uint64_t)s.y << 32);
@@ -182,7 +186,15 @@ __device__ __forceinline__ bool probe(const DevRegion & R, uint64_t key, uint32_
       return true;
     }
     h = (h + 1) & R.table_mask;
+    s = __ldg(tab + h);
   }
+}
+
+__device__ __forceinline__ bool probe(const DevRegion & R, uint64_t key, uint32_t & off, uint32_t & cnt)
+{
+  uint32_t const h = slot_of(R, key);
+  uint4 const s = __ldg(reinterpret_cast<const uint4 *>(R.table) + h);
+  return probe_resolve(R, key, h, s, off, cnt);
 }
 
 // Appends the bucket references of `nk` keys (key k produced by keyfn(k)) to S.refs in key order, applying the
@@ -1449,14 +1461,29 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(LaunchParams P)
     {
       uint32_t total = 0;
       bool dropped = false;
-      for (int base = 0; base < 96; base += 32)
+      // memory-level parallelism: the first table slot of all three neighbour keys of this lane is requested
+      // before any of them is examined
+      const uint4 * tab = reinterpret_cast<const uint4 *>(R.table);
+      uint64_t nk[3];
+      uint32_t nh[3];
+      uint4 ns[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
       {
-        int const k = base + lane;
-        uint64_t const nk = key ^ ((uint64_t)(k % 3 + 1) << (2 * (k / 3)));
+        int const k = q * 32 + lane;
+        nk[q] = key ^ ((uint64_t)(k % 3 + 1) << (2 * (k / 3)));
+        nh[q] = slot_of(R, nk[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        ns[q] = __ldg(tab + nh[q]);
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+      {
         uint32_t off = 0, cnt = 0;
-        bool const found = probe(R, nk, off, cnt);
+        bool const found = probe_resolve(R, nk[q], nh[q], ns[q], off, cnt);
         unsigned const fm = __ballot_sync(FULL, found);
-        if (fm == 0)
+        if (fm == 0 || dropped)
           continue;
         uint32_t inc = found ? cnt : 0u;
 #pragma unroll
@@ -1469,7 +1496,7 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(LaunchParams P)
         if (__any_sync(FULL, found && (total + inc) > 75u)) // PHIndex::multi_get give-up rule (ph_index.cpp:84-89)
         {
           dropped = true;
-          break;
+          continue;
         }
         int const pos = nrefs + __popc(fm & ((1u << lane) - 1u));
         if (found)
@@ -1517,6 +1544,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) chain_kernel(LaunchParams P)
   uint32_t const w2 = reinterpret_cast<const uint32_t *>(recp)[2];
   if ((w2 >> 8) & 1u)
   {
+    atomicAdd(&P.counters->fast_reasons[11], 1ull); // marked by probe_kernel (IUPAC/N seed or > SEED_INLINE references)
     push_slow(P, task);
     return;
   }
@@ -1549,6 +1577,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS) chain_kernel(LaunchParams P)
   run_task(S, g, recp->refs, list_start, nslots, S.L);
   if (S.overflow)
   {
+    for (int q = 0; q < 12; ++q)
+      if ((S.overflow >> q) & 1u)
+        atomicAdd(&P.counters->fast_reasons[q], 1ull);
     push_slow(P, task);
     return;
   }

@@ -204,6 +204,8 @@ int gtb_last_kernel_timing(gtb_ctx *ctx, float *probe_ms, float *chain_ms, float
 int gtb_pool_reset(gtb_ctx *ctx, int region_id);
 /* Page-locked host memory: batch columns (seq4 above all) placed here are DMA-ed without a staging copy. */
 int gtb_host_alloc(size_t bytes, void **out);
+/* Diagnostics: out24[0..11] why chain_kernel re-queued tasks for slow_kernel, out24[12..23] slow_kernel overflows. */
+int gtb_debug_counters(gtb_ctx *ctx, uint64_t *out24);
 int gtb_host_free(void *p);
 
 /* NCCL bootstrap (libnccl is bound lazily with dlopen): rank 0 creates the 128-byte unique id, the caller
