@@ -1520,6 +1520,8 @@ struct NcclApi
   int (*CommInitRank)(void **, int, gtb_nccl_id, int) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*CommDestroy)(void *) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char * (*GetErrorString)(int) = nullptr;
   void * lib = nullptr;
 } g_nccl;
@@ -1542,6 +1544,8 @@ int load_nccl()
   g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(g_nccl.lib, "ncclAllReduce"));
   g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(g_nccl.lib, "ncclCommDestroy"));
   g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(g_nccl.lib, "ncclGetErrorString"));
+  g_nccl.GroupStart = reinterpret_cast<decltype(g_nccl.GroupStart)>(dlsym(g_nccl.lib, "ncclGroupStart"));
+  g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(dlsym(g_nccl.lib, "ncclGroupEnd"));
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
     return fail(GTB_ERR_NCCL, "libnccl lacks required symbols");
   return 0;
@@ -1581,33 +1585,56 @@ int gtb_nccl_init(gtb_ctx * ctx, int n_ranks, int rank, const uint8_t * id128)
 // Sum-reduce of the widened accumulators of one region over all ranks (additive: SURVEY.md section 8e).
 // The accumulator arena is laid out as uint32 [..] then uint64 [..] then uint32 read_strand; it is reduced as
 // three typed spans.  nccl_comm == NULL uses the communicator of gtb_nccl_init.
-int gtb_allreduce_accumulators(gtb_ctx * ctx, int region_id, void * nccl_comm)
+int gtb_allreduce_accumulators_multi(gtb_ctx * ctx, int n, const int * region_ids, void * nccl_comm)
 {
   auto * c = reinterpret_cast<Ctx *>(ctx);
-  auto it = c->regions.find(region_id);
-  if (it == c->regions.end() || !it->second->pool_open)
-    return fail(GTB_ERR_STATE, "unknown region / pool not open");
+  if (!c || n <= 0 || !region_ids)
+    return fail(GTB_ERR_ARG, "bad arguments");
   void * comm = nccl_comm ? nccl_comm : c->nccl_comm;
   if (!comm)
     return fail(GTB_ERR_STATE, "no NCCL communicator (gtb_nccl_init)");
   if (int rc = load_nccl())
     return rc;
-  Region & R = *it->second;
   cudaSetDevice(c->device);
-  uint8_t * base = static_cast<uint8_t *>(R.accum.p);
-  uint8_t * u64_begin = reinterpret_cast<uint8_t *>(R.dev.vs_clipped_reads);
-  uint8_t * rs_begin = reinterpret_cast<uint8_t *>(R.dev.read_strand);
-  uint8_t * end = base + R.accum_bytes;
-  // ncclUint32 = 3, ncclUint64 = 5, ncclSum = 0
-  int r = g_nccl.AllReduce(base, base, (size_t)(u64_begin - base) / 4, 3, 0, comm, c->stream);
-  if (r == 0)
-    r = g_nccl.AllReduce(u64_begin, u64_begin, (size_t)(rs_begin - u64_begin) / 8, 5, 0, comm, c->stream);
-  if (r == 0)
-    r = g_nccl.AllReduce(rs_begin, rs_begin, (size_t)(end - rs_begin) / 4, 3, 0, comm, c->stream);
+  std::vector<Region *> regs(n);
+  for (int i = 0; i < n; ++i)
+  {
+    auto it = c->regions.find(region_ids[i]);
+    if (it == c->regions.end() || !it->second->pool_open)
+      return fail(GTB_ERR_STATE, "unknown region / pool not open");
+    regs[i] = it->second.get();
+  }
+  // one NCCL group for all regions: three typed spans per accumulator arena (u32 | u64 | u32 read_strand)
+  int r = g_nccl.GroupStart ? g_nccl.GroupStart() : 0;
+  for (int i = 0; i < n && r == 0; ++i)
+  {
+    Region & R = *regs[i];
+    uint8_t * base = static_cast<uint8_t *>(R.accum.p);
+    uint8_t * u64_begin = reinterpret_cast<uint8_t *>(R.dev.vs_clipped_reads);
+    uint8_t * rs_begin = reinterpret_cast<uint8_t *>(R.dev.read_strand);
+    uint8_t * end = base + R.accum_bytes;
+    // ncclUint32 = 3, ncclUint64 = 5, ncclSum = 0
+    r = g_nccl.AllReduce(base, base, (size_t)(u64_begin - base) / 4, 3, 0, comm, c->stream);
+    if (r == 0)
+      r = g_nccl.AllReduce(u64_begin, u64_begin, (size_t)(rs_begin - u64_begin) / 8, 5, 0, comm, c->stream);
+    if (r == 0)
+      r = g_nccl.AllReduce(rs_begin, rs_begin, (size_t)(end - rs_begin) / 4, 3, 0, comm, c->stream);
+  }
+  if (g_nccl.GroupEnd)
+  {
+    int const r2 = g_nccl.GroupEnd();
+    if (r == 0)
+      r = r2;
+  }
   if (r != 0)
     return fail(GTB_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+int gtb_allreduce_accumulators(gtb_ctx * ctx, int region_id, void * nccl_comm)
+{
+  return gtb_allreduce_accumulators_multi(ctx, 1, &region_id, nccl_comm);
 }
 
 } // extern "C"

@@ -22,7 +22,7 @@ EXPORTS = [
     "gtb_index_size", "gtb_index_export", "gtb_pool_begin", "gtb_submit_reads", "gtb_accumulator_sizes",
     "gtb_pool_finish", "gtb_pool_finish_multi", "gtb_pool_reset_multi", "gtb_submit_reads_multi", "gtb_debug_enable", "gtb_debug_seed_sizes", "gtb_debug_seeds",
     "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_replay_last",
-    "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators",
+    "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators", "gtb_allreduce_accumulators_multi", "gtb_debug_counters",
 ]
 
 
@@ -76,6 +76,8 @@ def load_library() -> C.CDLL:
     L.gtb_nccl_unique_id.argtypes = [abi.u8p]
     L.gtb_nccl_init.argtypes = [vp, C.c_int, C.c_int, abi.u8p]
     L.gtb_allreduce_accumulators.argtypes = [vp, C.c_int, vp]
+    L.gtb_allreduce_accumulators_multi.argtypes = [vp, C.c_int, abi.i32p, vp]
+    L.gtb_debug_counters.argtypes = [vp, abi.u64p]
     _lib = L
     return L
 
@@ -283,3 +285,8 @@ class Context:
 
     def allreduce(self, region_id: int) -> None:
         self._check(self.lib.gtb_allreduce_accumulators(self.h, region_id, None))
+
+    def allreduce_multi(self, region_ids: Sequence[int]) -> None:
+        n = len(region_ids)
+        ids = (C.c_int32 * n)(*region_ids)
+        self._check(self.lib.gtb_allreduce_accumulators_multi(self.h, n, ids, None))

@@ -217,6 +217,8 @@ int gtb_nccl_init(gtb_ctx *ctx, int n_ranks, int rank, const uint8_t *id128);
  * (ncclComm_t passed as void*; all ranks call; result valid on every rank).  Used when ONE sample's reads
  * are split over GPUs; with sample sharding no collective is needed. */
 int gtb_allreduce_accumulators(gtb_ctx *ctx, int region_id, void *nccl_comm);
+/* Several regions in ONE NCCL group and one stream synchronisation. */
+int gtb_allreduce_accumulators_multi(gtb_ctx *ctx, int n, const int *region_ids, void *nccl_comm);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,39 @@
+"""Run under torchrun on N GPUs: one pool's records sharded over the ranks (abi.shard_batch), every rank accumulates
+its shard on its GPU, ONE grouped NCCL all-reduce, result compared bit-for-bit with the reference's golden accumulators."""
+import glob, os, sys
+import numpy as np
+import torch, torch.distributed as dist
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import compare
+from graphtyper_b200 import abi, engine, gtba
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+torch.cuda.set_device(lr)
+ctx = engine.Context(lr)
+uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{lr}")
+if rank == 0:
+    uid.copy_(torch.from_numpy(ctx.nccl_unique_id()))
+dist.broadcast(uid, 0)
+ctx.nccl_init(world, rank, uid.cpu().numpy())
+pres = sorted(p[:-len(".graph.gtba")] for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.graph.gtba")) +
+              glob.glob(os.path.join(ROOT, "tests", "data_local", "*.graph.gtba")))
+ok = True
+for k, pre in enumerate(pres):
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    rd = gtba.load(pre + ".reads.gtba")
+    ns = len(rd["sample_names"].tobytes().split(b"\n")) - 1
+    shard = abi.shard_batch(abi.batch_from_probe(rd), world)[rank]
+    ctx.region_begin(k, g); ctx.pool_begin(k, ns)
+    ctx.submit(k, shard)
+    ctx.allreduce_multi([k])
+    acc = ctx.pool_finish(k)
+    try:
+        compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), acc.as_dict(), f"rank{rank}")
+        if rank == 0: print("OK  ", os.path.basename(pre), "shard sizes", len(shard))
+    except AssertionError as e:
+        ok = False; print("FAIL", os.path.basename(pre), e)
+    ctx.region_end(k)
+dist.barrier()
+if rank == 0: print("multi-GPU sharded parity:", "PASS" if ok else "FAIL")
+dist.destroy_process_group()
