@@ -259,12 +259,12 @@ def main() -> None:
     ctx = engine.Context(device=local_rank)
     # inputs live in page-locked host memory (gtb_host_alloc), as a production caller would fill them
     batches, pinned_arena = engine.pin_batches(batches)
+    ids = list(range(len(graphs)))
     t0 = time.perf_counter()
-    for k, g in enumerate(graphs):
-        ctx.region_begin(k, g)
+    ctx.region_begin_multi(ids, graphs)  # host index builds in parallel threads, table built on the device
+    for k in ids:
         ctx.pool_begin(k, 1)
     t_region = time.perf_counter() - t0
-    ids = list(range(len(graphs)))
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:

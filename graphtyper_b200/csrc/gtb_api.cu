@@ -398,159 +398,192 @@ void gtb_destroy(gtb_ctx * ctx)
   delete c;
 }
 
-int gtb_region_begin(gtb_ctx * ctx, int region_id, const gtb_graph_view * g)
+// Uploads one prepared region: graph + labels + distinct k-mer list in ONE H2D copy, then the k-mer table is
+// built on the device (the 16-byte-slot table is 4-8x larger than the list it is built from).
+static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g)
+{
+  size_t off = 0;
+  size_t const o_ref_order = place<uint32_t>(off, g->n_ref);
+  size_t const o_ref_seq_off = place<uint32_t>(off, g->n_ref + 1);
+  size_t const o_ref_var_off = place<uint32_t>(off, g->n_ref + 1);
+  size_t const o_var_order = place<uint32_t>(off, g->n_var);
+  size_t const o_var_seq_off = place<uint32_t>(off, g->n_var + 1);
+  size_t const o_var_out_ref = place<uint32_t>(off, g->n_var);
+  size_t const o_seq = place<uint8_t>(off, g->seq_len + 16);
+  size_t const o_actual = place<uint32_t>(off, g->n_special);
+  size_t const o_rreach = place<uint32_t>(off, g->n_special);
+  size_t const o_sp_keys = place<uint32_t>(off, g->n_sp_keys);
+  size_t const o_sp_off = place<uint32_t>(off, g->n_sp_keys + 1);
+  size_t const n_sp_list = g->n_sp_keys ? g->sp_off[g->n_sp_keys] : 0;
+  size_t const o_sp_list = place<uint32_t>(off, n_sp_list);
+  size_t const o_bubble_order = place<uint32_t>(off, R.n_bubbles);
+  size_t const o_score_off = place<uint32_t>(off, R.n_bubbles + 1);
+  size_t const o_cov_off = place<uint32_t>(off, R.n_bubbles + 1);
+  size_t const o_labels = place<DevLabel>(off, R.index.labels.size());
+  size_t const o_uniq = place<IndexSlot>(off, R.index.uniq.size());
+  size_t const upload_bytes = align_up(off, 256);
+  size_t const o_table = place<IndexSlot>(off, R.index.table_cap); // device only
+  size_t const total = align_up(off, 256);
+
+  if (int rc = c->h_stage.reserve(upload_bytes))
+    return rc;
+  uint8_t * h = static_cast<uint8_t *>(c->h_stage.p);
+  auto put32 = [&](size_t o, const uint32_t * src, size_t n)
+  {
+    if (n)
+      memcpy(h + o, src, n * 4);
+  };
+  auto put64as32 = [&](size_t o, const uint64_t * src, size_t n)
+  {
+    uint32_t * d = reinterpret_cast<uint32_t *>(h + o);
+    for (size_t i = 0; i < n; ++i)
+      d[i] = (uint32_t)src[i];
+  };
+  put32(o_ref_order, g->ref_order, g->n_ref);
+  put64as32(o_ref_seq_off, g->ref_seq_off, g->n_ref + 1);
+  put32(o_ref_var_off, g->ref_var_off, g->n_ref + 1);
+  put32(o_var_order, g->var_order, g->n_var);
+  put64as32(o_var_seq_off, g->var_seq_off, g->n_var + 1);
+  put32(o_var_out_ref, g->var_out_ref, g->n_var);
+  memcpy(h + o_seq, g->seq, g->seq_len);
+  memset(h + o_seq + g->seq_len, 0, 16);
+  put32(o_actual, g->actual_poses, g->n_special);
+  put32(o_rreach, g->ref_reach_poses, g->n_special);
+  put32(o_sp_keys, g->sp_keys, g->n_sp_keys);
+  if (g->n_sp_keys)
+    put32(o_sp_off, g->sp_off, g->n_sp_keys + 1);
+  else
+    memset(h + o_sp_off, 0, 4);
+  put32(o_sp_list, g->sp_list, n_sp_list);
+  put32(o_bubble_order, R.bubble_order.data(), R.n_bubbles);
+  put32(o_score_off, R.score_off.data(), R.n_bubbles + 1);
+  put32(o_cov_off, R.cov_off.data(), R.n_bubbles + 1);
+  memcpy(h + o_labels, R.index.labels.data(), R.index.labels.size() * sizeof(DevLabel));
+  memcpy(h + o_uniq, R.index.uniq.data(), R.index.uniq.size() * sizeof(IndexSlot));
+
+  if (int rc = R.arena.reserve(total))
+    return rc;
+  uint8_t * d = static_cast<uint8_t *>(R.arena.p);
+  CUDA_TRY(cudaMemcpyAsync(d, h, upload_bytes, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemsetAsync(d + o_table, 0, (size_t)R.index.table_cap * sizeof(IndexSlot), c->stream));
+  launch_build_table(reinterpret_cast<const IndexSlot *>(d + o_uniq), (uint32_t)R.index.uniq.size(),
+                     reinterpret_cast<IndexSlot *>(d + o_table), R.index.table_mask, R.index.table_shift, c->stream);
+  CUDA_TRY(cudaStreamSynchronize(c->stream)); // h_stage is reused by the next region
+  CUDA_TRY(cudaGetLastError());
+
+  DevRegion & D = R.dev;
+  memset(&D, 0, sizeof(D));
+  D.n_ref = g->n_ref;
+  D.n_var = g->n_var;
+  D.n_special = g->n_special;
+  D.n_sp_keys = g->n_sp_keys;
+  D.is_sv = g->is_sv_graph ? 1u : 0u;
+  D.n_bubbles = R.n_bubbles;
+  D.n_samples = 0;
+  D.table_mask = R.index.table_mask;
+  D.table_shift = R.index.table_shift;
+  D.ref_order = reinterpret_cast<const uint32_t *>(d + o_ref_order);
+  D.ref_seq_off = reinterpret_cast<const uint32_t *>(d + o_ref_seq_off);
+  D.ref_var_off = reinterpret_cast<const uint32_t *>(d + o_ref_var_off);
+  D.var_order = reinterpret_cast<const uint32_t *>(d + o_var_order);
+  D.var_seq_off = reinterpret_cast<const uint32_t *>(d + o_var_seq_off);
+  D.var_out_ref = reinterpret_cast<const uint32_t *>(d + o_var_out_ref);
+  D.seq = d + o_seq;
+  D.actual_poses = reinterpret_cast<const uint32_t *>(d + o_actual);
+  D.ref_reach_poses = reinterpret_cast<const uint32_t *>(d + o_rreach);
+  D.sp_keys = reinterpret_cast<const uint32_t *>(d + o_sp_keys);
+  D.sp_off = reinterpret_cast<const uint32_t *>(d + o_sp_off);
+  D.sp_list = reinterpret_cast<const uint32_t *>(d + o_sp_list);
+  D.bubble_order = reinterpret_cast<const uint32_t *>(d + o_bubble_order);
+  D.score_off = reinterpret_cast<const uint32_t *>(d + o_score_off);
+  D.cov_off = reinterpret_cast<const uint32_t *>(d + o_cov_off);
+  D.table = reinterpret_cast<const IndexSlot *>(d + o_table);
+  D.labels = reinterpret_cast<const DevLabel *>(d + o_labels);
+
+  int slot = -1;
+  for (size_t s = 0; s < c->slot_region.size(); ++s)
+    if (c->slot_region[s] < 0)
+    {
+      slot = (int)s;
+      break;
+    }
+  if (slot < 0)
+  {
+    slot = (int)c->slot_region.size();
+    c->slot_region.push_back(-1);
+  }
+  if (slot > 0xFFFF)
+    return fail(GTB_ERR_CAPACITY, "more than 65536 resident regions");
+  c->slot_region[slot] = R.id;
+  R.slot = slot;
+  c->regions_dirty = true;
+  return 0;
+}
+
+// Several regions at once: the host index builds run in parallel (they are independent), uploads follow.
+int gtb_region_begin_multi(gtb_ctx * ctx, int n, const int * region_ids, const gtb_graph_view * graphs)
 {
   auto * c = reinterpret_cast<Ctx *>(ctx);
-  if (!c)
-    return fail(GTB_ERR_ARG, "null ctx");
-  if (c->regions.count(region_id))
-    return fail(GTB_ERR_STATE, "region id already in use");
-  if (int rc = validate_graph(g))
-    return rc;
-  auto R = std::make_unique<Region>();
-  R->id = region_id;
-  R->n_bubbles = g->n_ref - 1;
+  if (!c || n <= 0 || !region_ids || !graphs)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  for (int i = 0; i < n; ++i)
   {
-    IndexBuilder ib(*g);
-    const char * err = nullptr;
-    if (!ib.build(R->index, &err))
-      return fail(GTB_ERR_ARG, err ? err : "index build failed");
+    if (c->regions.count(region_ids[i]))
+      return fail(GTB_ERR_STATE, "region id already in use");
+    for (int j = 0; j < i; ++j)
+      if (region_ids[j] == region_ids[i])
+        return fail(GTB_ERR_ARG, "duplicate region id");
+    if (int rc = validate_graph(&graphs[i]))
+      return rc;
   }
-  R->score_off.assign(1, 0);
-  R->cov_off.assign(1, 0);
-  for (uint32_t b = 0; b < R->n_bubbles; ++b)
-  {
-    uint32_t const v0 = g->ref_var_off[b];
-    uint32_t const cnum = g->ref_var_off[b + 1] - v0;
-    R->bubble_order.push_back(g->var_order[v0]);
-    R->n_alleles.push_back(cnum);
-    R->score_off.push_back(R->score_off.back() + cnum * (cnum + 1) / 2);
-    R->cov_off.push_back(R->cov_off.back() + cnum);
-  }
-
+  std::vector<std::unique_ptr<Region>> regs(n);
+  std::vector<const char *> errs(n, nullptr);
+  parallel_for(n, [&](int i)
+               {
+                 const gtb_graph_view * g = &graphs[i];
+                 auto R = std::make_unique<Region>();
+                 R->id = region_ids[i];
+                 R->n_bubbles = g->n_ref - 1;
+                 IndexBuilder ib(*g);
+                 const char * err = nullptr;
+                 if (!ib.build(R->index, &err))
+                 {
+                   errs[i] = err ? err : "index build failed";
+                   return;
+                 }
+                 R->score_off.assign(1, 0);
+                 R->cov_off.assign(1, 0);
+                 for (uint32_t b = 0; b < R->n_bubbles; ++b)
+                 {
+                   uint32_t const v0 = g->ref_var_off[b];
+                   uint32_t const cnum = g->ref_var_off[b + 1] - v0;
+                   R->bubble_order.push_back(g->var_order[v0]);
+                   R->n_alleles.push_back(cnum);
+                   R->score_off.push_back(R->score_off.back() + cnum * (cnum + 1) / 2);
+                   R->cov_off.push_back(R->cov_off.back() + cnum);
+                 }
+                 regs[i] = std::move(R);
+               });
+  for (int i = 0; i < n; ++i)
+    if (errs[i])
+      return fail(GTB_ERR_ARG, errs[i]);
   if (c->device >= 0)
   {
     cudaSetDevice(c->device);
-    // ---- pack the arena
-    size_t off = 0;
-    size_t const o_ref_order = place<uint32_t>(off, g->n_ref);
-    size_t const o_ref_seq_off = place<uint32_t>(off, g->n_ref + 1);
-    size_t const o_ref_var_off = place<uint32_t>(off, g->n_ref + 1);
-    size_t const o_var_order = place<uint32_t>(off, g->n_var);
-    size_t const o_var_seq_off = place<uint32_t>(off, g->n_var + 1);
-    size_t const o_var_out_ref = place<uint32_t>(off, g->n_var);
-    size_t const o_seq = place<uint8_t>(off, g->seq_len + 16);
-    size_t const o_actual = place<uint32_t>(off, g->n_special);
-    size_t const o_rreach = place<uint32_t>(off, g->n_special);
-    size_t const o_sp_keys = place<uint32_t>(off, g->n_sp_keys);
-    size_t const o_sp_off = place<uint32_t>(off, g->n_sp_keys + 1);
-    size_t const n_sp_list = g->n_sp_keys ? g->sp_off[g->n_sp_keys] : 0;
-    size_t const o_sp_list = place<uint32_t>(off, n_sp_list);
-    size_t const o_bubble_order = place<uint32_t>(off, R->n_bubbles);
-    size_t const o_score_off = place<uint32_t>(off, R->n_bubbles + 1);
-    size_t const o_cov_off = place<uint32_t>(off, R->n_bubbles + 1);
-    size_t const o_table = place<IndexSlot>(off, R->index.table.size());
-    size_t const o_labels = place<DevLabel>(off, R->index.labels.size());
-    size_t const o_tags = place<uint8_t>(off, R->index.tags.size());
-    size_t const total = align_up(off, 256);
-
-    if (int rc = c->h_stage.reserve(total))
-      return rc;
-    uint8_t * h = static_cast<uint8_t *>(c->h_stage.p);
-    memset(h, 0, total);
-    auto put32 = [&](size_t o, const uint32_t * src, size_t n)
-    {
-      if (n)
-        memcpy(h + o, src, n * 4);
-    };
-    auto put64as32 = [&](size_t o, const uint64_t * src, size_t n)
-    {
-      uint32_t * d = reinterpret_cast<uint32_t *>(h + o);
-      for (size_t i = 0; i < n; ++i)
-        d[i] = (uint32_t)src[i];
-    };
-    put32(o_ref_order, g->ref_order, g->n_ref);
-    put64as32(o_ref_seq_off, g->ref_seq_off, g->n_ref + 1);
-    put32(o_ref_var_off, g->ref_var_off, g->n_ref + 1);
-    put32(o_var_order, g->var_order, g->n_var);
-    put64as32(o_var_seq_off, g->var_seq_off, g->n_var + 1);
-    put32(o_var_out_ref, g->var_out_ref, g->n_var);
-    memcpy(h + o_seq, g->seq, g->seq_len);
-    put32(o_actual, g->actual_poses, g->n_special);
-    put32(o_rreach, g->ref_reach_poses, g->n_special);
-    put32(o_sp_keys, g->sp_keys, g->n_sp_keys);
-    if (g->n_sp_keys)
-      put32(o_sp_off, g->sp_off, g->n_sp_keys + 1);
-    put32(o_sp_list, g->sp_list, n_sp_list);
-    put32(o_bubble_order, R->bubble_order.data(), R->n_bubbles);
-    put32(o_score_off, R->score_off.data(), R->n_bubbles + 1);
-    put32(o_cov_off, R->cov_off.data(), R->n_bubbles + 1);
-    memcpy(h + o_table, R->index.table.data(), R->index.table.size() * sizeof(IndexSlot));
-    memcpy(h + o_labels, R->index.labels.data(), R->index.labels.size() * sizeof(DevLabel));
-    memcpy(h + o_tags, R->index.tags.data(), R->index.tags.size());
-
-    if (int rc = R->arena.reserve(total))
-      return rc;
-    CUDA_TRY(cudaMemcpyAsync(R->arena.p, h, total, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-
-    uint8_t * d = static_cast<uint8_t *>(R->arena.p);
-    DevRegion & D = R->dev;
-    memset(&D, 0, sizeof(D));
-    D.n_ref = g->n_ref;
-    D.n_var = g->n_var;
-    D.n_special = g->n_special;
-    D.n_sp_keys = g->n_sp_keys;
-    D.is_sv = g->is_sv_graph ? 1u : 0u;
-    D.n_bubbles = R->n_bubbles;
-    D.n_samples = 0;
-    D.table_mask = R->index.table_mask;
-    {
-      int shift = 64;
-      for (size_t cap = R->index.table.size(); cap > 1; cap >>= 1)
-        --shift;
-      D.table_shift = shift;
-    }
-    D.ref_order = reinterpret_cast<const uint32_t *>(d + o_ref_order);
-    D.ref_seq_off = reinterpret_cast<const uint32_t *>(d + o_ref_seq_off);
-    D.ref_var_off = reinterpret_cast<const uint32_t *>(d + o_ref_var_off);
-    D.var_order = reinterpret_cast<const uint32_t *>(d + o_var_order);
-    D.var_seq_off = reinterpret_cast<const uint32_t *>(d + o_var_seq_off);
-    D.var_out_ref = reinterpret_cast<const uint32_t *>(d + o_var_out_ref);
-    D.seq = d + o_seq;
-    D.actual_poses = reinterpret_cast<const uint32_t *>(d + o_actual);
-    D.ref_reach_poses = reinterpret_cast<const uint32_t *>(d + o_rreach);
-    D.sp_keys = reinterpret_cast<const uint32_t *>(d + o_sp_keys);
-    D.sp_off = reinterpret_cast<const uint32_t *>(d + o_sp_off);
-    D.sp_list = reinterpret_cast<const uint32_t *>(d + o_sp_list);
-    D.bubble_order = reinterpret_cast<const uint32_t *>(d + o_bubble_order);
-    D.score_off = reinterpret_cast<const uint32_t *>(d + o_score_off);
-    D.cov_off = reinterpret_cast<const uint32_t *>(d + o_cov_off);
-    D.table = reinterpret_cast<const IndexSlot *>(d + o_table);
-    D.labels = reinterpret_cast<const DevLabel *>(d + o_labels);
-    D.tags = d + o_tags;
-
-    // slot in the device region table
-    int slot = -1;
-    for (size_t s = 0; s < c->slot_region.size(); ++s)
-      if (c->slot_region[s] < 0)
-      {
-        slot = (int)s;
-        break;
-      }
-    if (slot < 0)
-    {
-      slot = (int)c->slot_region.size();
-      c->slot_region.push_back(-1);
-    }
-    if (slot > 0xFFFF)
-      return fail(GTB_ERR_CAPACITY, "more than 65536 resident regions");
-    c->slot_region[slot] = region_id;
-    R->slot = slot;
-    c->regions_dirty = true;
+    for (int i = 0; i < n; ++i)
+      if (int rc = upload_region(c, *regs[i], &graphs[i]))
+        return rc;
   }
-  c->regions[region_id] = std::move(R);
+  for (int i = 0; i < n; ++i)
+    c->regions[region_ids[i]] = std::move(regs[i]);
   return 0;
+}
+
+int gtb_region_begin(gtb_ctx * ctx, int region_id, const gtb_graph_view * g)
+{
+  if (!ctx)
+    return fail(GTB_ERR_ARG, "null ctx");
+  return gtb_region_begin_multi(ctx, 1, &region_id, g);
 }
 
 int gtb_region_end(gtb_ctx * ctx, int region_id)
@@ -580,7 +613,7 @@ int gtb_index_size(gtb_ctx * ctx, int region_id, uint64_t * n_keys, uint64_t * n
   auto it = c->regions.find(region_id);
   if (it == c->regions.end())
     return fail(GTB_ERR_STATE, "unknown region");
-  *n_keys = it->second->index.keys.size();
+  *n_keys = it->second->index.n_keys;
   *n_labels = it->second->index.labels.size();
   return 0;
 }
@@ -591,10 +624,13 @@ int gtb_index_export(gtb_ctx * ctx, int region_id, uint64_t * keys, uint32_t * l
   auto it = c->regions.find(region_id);
   if (it == c->regions.end())
     return fail(GTB_ERR_STATE, "unknown region");
-  HostIndex const & ix = it->second->index;
-  memcpy(keys, ix.keys.data(), ix.keys.size() * 8);
-  memcpy(label_off, ix.label_off.data(), ix.label_off.size() * 4);
-  memcpy(labels, ix.labels.data(), ix.labels.size() * sizeof(gtb_label));
+  std::vector<uint64_t> k;
+  std::vector<uint32_t> lo;
+  std::vector<gtb_label> ll;
+  it->second->index.export_sorted(k, lo, ll);
+  memcpy(keys, k.data(), k.size() * 8);
+  memcpy(label_off, lo.data(), lo.size() * 4);
+  memcpy(labels, ll.data(), ll.size() * sizeof(gtb_label));
   return 0;
 }
 

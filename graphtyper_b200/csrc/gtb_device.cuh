@@ -60,7 +60,6 @@ struct DevRegion
   const uint32_t * cov_off;      // [n_bubbles+1]
   // index
   const IndexSlot * table;
-  const uint8_t * tags;          // [table capacity] one-byte slot tags, 16 consecutive slots per 16-byte window
   const DevLabel * labels;
   // accumulators (widened; clamped on download)
   uint32_t * log_score;     // [score_off[NB] * NS]
@@ -155,6 +154,7 @@ struct LaunchParams
 };
 
 // host launchers (gtb_kernels.cu)
+void launch_build_table(const IndexSlot * uniq, uint32_t n, IndexSlot * table, uint32_t mask, int shift, void * stream);
 void launch_probe(const LaunchParams & p, void * stream);
 void launch_chain(const LaunchParams & p, void * stream);
 void launch_slow(const LaunchParams & p, void * stream);

@@ -40,16 +40,35 @@ struct IndexSlot // 16-byte open-addressing slot; cnt == 0 means empty
 
 struct HostIndex
 {
-  std::vector<uint64_t> keys;      // ascending, unique
-  std::vector<uint32_t> label_off; // [n_keys + 1]
-  std::vector<gtb_label> labels;   // bucket order = reference insertion order
-  std::vector<IndexSlot> table;    // open addressing, power-of-two capacity, load <= 0.5
-  std::vector<uint8_t> tags;       // one byte per slot: 0 = empty, else 1 + (hash & 0xFF) % 255 (probe prefilter)
-  uint32_t table_mask = 0;
+  std::vector<gtb_label> labels;   // grouped by key (first-seen key order); bucket order = reference insertion order
+  std::vector<IndexSlot> uniq;     // one {key, label offset, label count} per distinct k-mer, first-seen order
+  uint64_t n_keys = 0;
+  // geometry of the DEVICE table (built on the device from `uniq`): power-of-two capacity, load <= 0.25
+  uint32_t table_cap = 16;
+  uint32_t table_mask = 15;
+  int table_shift = 60;
+
+  // PHIndex-style view for inspection / parity tests: keys ascending, labels concatenated in that order
+  void export_sorted(std::vector<uint64_t> & keys, std::vector<uint32_t> & label_off, std::vector<gtb_label> & out) const
+  {
+    std::vector<uint32_t> order(uniq.size());
+    for (uint32_t i = 0; i < order.size(); ++i)
+      order[i] = i;
+    std::sort(order.begin(), order.end(), [this](uint32_t a, uint32_t b) { return uniq[a].key < uniq[b].key; });
+    keys.clear();
+    label_off.assign(1, 0);
+    out.clear();
+    out.reserve(labels.size());
+    for (uint32_t i : order)
+    {
+      keys.push_back(uniq[i].key);
+      out.insert(out.end(), labels.begin() + uniq[i].off, labels.begin() + uniq[i].off + uniq[i].cnt);
+      label_off.push_back((uint32_t)out.size());
+    }
+  }
 };
 
 inline uint64_t hash_key(uint64_t k) { return k * 0x9E3779B97F4A7C15ull; }
-inline uint8_t tag_of_hash(uint64_t h) { return (uint8_t)(1u + (uint32_t)(h & 0xFFu) % 255u); }
 
 class IndexBuilder
 {
@@ -69,8 +88,30 @@ public:
     for (uint32_t r = 0; r < NR; ++r)
     {
       uint32_t const n = ref_len(r);
+      // A window that lies entirely inside this ref node is the only walk ending there: roll its key along the
+      // node instead of walking backwards (the bulk of all end positions).
+      const uint8_t * dna = ref_dna(r);
+      uint64_t key = 0;
+      uint32_t run = 0; // consecutive ACGT bases ending at d
       for (uint32_t d = 0; d < n; ++d)
-        enumerate_end(false, r, d);
+      {
+        int const c = code_of(dna[d]);
+        if (c < 0)
+        {
+          run = 0;
+          key = 0;
+          continue; // a non-ACGT base kills every walk through it
+        }
+        key = (key << 2) | (uint64_t)c;
+        ++run;
+        if (d >= 31)
+        {
+          if (run >= 32)
+            tuples_.push_back({key, {g_.ref_order[r] + d - 31, g_.ref_order[r] + d, GTB_INVALID_ID}});
+        }
+        else
+          enumerate_end(false, r, d);
+      }
       if (r + 1 < NR)
       {
         for (uint32_t v = g_.ref_var_off[r]; v < g_.ref_var_off[r + 1]; ++v)
@@ -91,10 +132,9 @@ public:
   }
 
 private:
-  struct Tuple
+  struct Tuple // in emission order (= the reference's insertion order)
   {
     uint64_t key;
-    uint32_t seq; // emission sequence number (stable bucket order)
     gtb_label label;
   };
 
@@ -111,7 +151,6 @@ private:
 
   const gtb_graph_view & g_;
   std::vector<Tuple> tuples_;
-  uint32_t seq_ = 0;
   bool bad_ = false;
   uint32_t end_pos_ = 0; // encoded end position of the current job
 
@@ -204,11 +243,11 @@ private:
       return;
     if (w.nvars == 0)
     {
-      tuples_.push_back({w.key, seq_++, {start_pos, end_pos_, GTB_INVALID_ID}});
+      tuples_.push_back({w.key, {start_pos, end_pos_, GTB_INVALID_ID}});
       return;
     }
     for (int i = w.nvars - 1; i >= 0; --i) // ascending var id = forward order
-      tuples_.push_back({w.key, seq_++, {start_pos, end_pos_, w.vars[i]}});
+      tuples_.push_back({w.key, {start_pos, end_pos_, w.vars[i]}});
   }
 
   // continue the walk backwards from the END of ref node r (all of r's bases are candidates)
@@ -311,42 +350,56 @@ private:
 
   void finish(HostIndex & out)
   {
-    // stable order by (key, emission sequence)
-    std::sort(tuples_.begin(), tuples_.end(),
-              [](const Tuple & a, const Tuple & b) { return a.key < b.key || (a.key == b.key && a.seq < b.seq); });
-    out.keys.clear();
-    out.label_off.clear();
-    out.labels.clear();
-    out.labels.reserve(tuples_.size());
-    for (size_t i = 0; i < tuples_.size(); ++i)
+    size_t const n = tuples_.size();
+    // host-side grouping table (load <= 0.5, values = index into out.uniq); no sort: the labels of one key keep
+    // their emission order by construction
+    size_t gcap = 16;
+    while (gcap < n * 2 + 2)
+      gcap <<= 1;
+    int gshift = 64;
+    for (size_t c = gcap; c > 1; c >>= 1)
+      --gshift;
+    std::vector<uint32_t> gtab(gcap, 0xFFFFFFFFu);
+    std::vector<uint32_t> bucket_of(n);
+    out.uniq.clear();
+    out.uniq.reserve(n);
+    for (size_t i = 0; i < n; ++i)
     {
-      if (i == 0 || tuples_[i].key != tuples_[i - 1].key)
+      uint64_t const k = tuples_[i].key;
+      size_t h = (size_t)(hash_key(k) >> gshift);
+      while (gtab[h] != 0xFFFFFFFFu && out.uniq[gtab[h]].key != k)
+        h = (h + 1) & (gcap - 1);
+      if (gtab[h] == 0xFFFFFFFFu)
       {
-        out.keys.push_back(tuples_[i].key);
-        out.label_off.push_back((uint32_t)out.labels.size());
+        gtab[h] = (uint32_t)out.uniq.size();
+        out.uniq.push_back(IndexSlot{k, 0, 0});
       }
-      out.labels.push_back(tuples_[i].label);
+      bucket_of[i] = gtab[h];
+      ++out.uniq[gtab[h]].cnt;
     }
-    out.label_off.push_back((uint32_t)out.labels.size());
-    // open-addressing table, load factor <= 0.5
+    out.n_keys = out.uniq.size();
+    uint32_t running = 0;
+    for (auto & u : out.uniq) // first-seen key order
+    {
+      u.off = running;
+      running += u.cnt;
+      u.cnt = 0; // reused as write cursor, restored below
+    }
+    out.labels.resize(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+      IndexSlot & u = out.uniq[bucket_of[i]];
+      out.labels[u.off + u.cnt++] = tuples_[i].label;
+    }
     size_t cap = 16;
-    while (cap < out.keys.size() * 4 + 2) // load factor <= 0.25: an unsuccessful lookup (the 96 neighbours) averages 1.4 probes
+    while (cap < n * 4 + 2) // load factor <= 0.25: an unsuccessful lookup (the 96 neighbours) averages ~1.2 probes
       cap <<= 1;
-    out.table.assign(cap, IndexSlot{0, 0, 0});
-    out.tags.assign(cap, 0);
+    out.table_cap = (uint32_t)cap;
     out.table_mask = (uint32_t)(cap - 1);
     int shift = 64;
     for (size_t c = cap; c > 1; c >>= 1)
       --shift;
-    for (size_t i = 0; i < out.keys.size(); ++i)
-    {
-      uint64_t const k = out.keys[i];
-      size_t h = (size_t)(hash_key(k) >> shift);
-      while (out.table[h].cnt != 0)
-        h = (h + 1) & out.table_mask;
-      out.table[h] = IndexSlot{k, out.label_off[i], out.label_off[i + 1] - out.label_off[i]};
-      out.tags[h] = tag_of_hash(hash_key(k));
-    }
+    out.table_shift = shift;
     tuples_.clear();
     tuples_.shrink_to_fit();
   }

@@ -2100,6 +2100,38 @@ __global__ void __launch_bounds__(128) score_kernel(LaunchParams P)
   }
 }
 
+// ================================================================================================ table build
+// Inserts the region's distinct k-mers {key, label offset, count} into the zero-initialised open-addressing table.
+// A slot is claimed by CAS on its (offset, count) word -- count == 0 means empty -- then the key is written;
+// lookups only happen in later kernels.
+__global__ void __launch_bounds__(256) build_table_kernel(const IndexSlot * uniq, uint32_t n, IndexSlot * table,
+                                                          uint32_t mask, int shift)
+{
+  uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  IndexSlot const u = uniq[i];
+  unsigned long long const val = (unsigned long long)u.off | ((unsigned long long)u.cnt << 32);
+  uint32_t h = (uint32_t)((u.key * 0x9E3779B97F4A7C15ull) >> shift);
+  while (true)
+  {
+    unsigned long long * w = reinterpret_cast<unsigned long long *>(&table[h]) + 1;
+    if (atomicCAS(w, 0ull, val) == 0ull)
+    {
+      table[h].key = u.key;
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+void launch_build_table(const IndexSlot * uniq, uint32_t n, IndexSlot * table, uint32_t mask, int shift, void * stream)
+{
+  if (n == 0)
+    return;
+  build_table_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(uniq, n, table, mask, shift);
+}
+
 // ================================================================================================ launchers
 static int g_align_blocks_per_sm = 0;
 

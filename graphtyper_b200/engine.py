@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgtb200.so")
 
 EXPORTS = [
-    "gtb_last_error", "gtb_version", "gtb_create", "gtb_destroy", "gtb_region_begin", "gtb_region_end",
+    "gtb_last_error", "gtb_version", "gtb_create", "gtb_destroy", "gtb_region_begin", "gtb_region_begin_multi", "gtb_region_end",
     "gtb_index_size", "gtb_index_export", "gtb_pool_begin", "gtb_submit_reads", "gtb_accumulator_sizes",
     "gtb_pool_finish", "gtb_pool_finish_multi", "gtb_pool_reset_multi", "gtb_submit_reads_multi", "gtb_debug_enable", "gtb_debug_seed_sizes", "gtb_debug_seeds",
     "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_replay_last",
@@ -50,6 +50,7 @@ def load_library() -> C.CDLL:
     L.gtb_destroy.argtypes = [vp]
     L.gtb_destroy.restype = None
     L.gtb_region_begin.argtypes = [vp, C.c_int, C.POINTER(abi.GraphView)]
+    L.gtb_region_begin_multi.argtypes = [vp, C.c_int, abi.i32p, C.POINTER(abi.GraphView)]
     L.gtb_region_end.argtypes = [vp, C.c_int]
     L.gtb_index_size.argtypes = [vp, C.c_int, abi.u64p, abi.u64p]
     L.gtb_index_export.argtypes = [vp, C.c_int, abi.u64p, abi.u32p, C.POINTER(abi.Label)]
@@ -153,6 +154,15 @@ class Context:
     def region_begin(self, region_id: int, graph: abi.HostGraph) -> None:
         self._check(self.lib.gtb_region_begin(self.h, region_id, C.byref(graph.view)))
         self._graphs[region_id] = graph
+
+    def region_begin_multi(self, region_ids: Sequence[int], graphs: Sequence[abi.HostGraph]) -> None:
+        """Host index builds of all regions run in parallel threads inside the library."""
+        n = len(region_ids)
+        ids = (C.c_int32 * n)(*region_ids)
+        arr = (abi.GraphView * n)(*[g.view for g in graphs])
+        self._check(self.lib.gtb_region_begin_multi(self.h, n, ids, arr))
+        for r, g in zip(region_ids, graphs):
+            self._graphs[r] = g
 
     def region_end(self, region_id: int) -> None:
         self._check(self.lib.gtb_region_end(self.h, region_id))

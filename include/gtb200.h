@@ -158,6 +158,8 @@ void gtb_destroy(gtb_ctx *ctx);
 /* Region: flatten + index build (host) + upload (device). Regions are identified by a small integer so
  * several regions can be resident and processed by ONE batched launch (region-batched mode). */
 int gtb_region_begin(gtb_ctx *ctx, int region_id, const gtb_graph_view *graph);
+/* Several regions at once: host index builds run in parallel threads, uploads follow. */
+int gtb_region_begin_multi(gtb_ctx *ctx, int n, const int *region_ids, const gtb_graph_view *graphs);
 int gtb_region_end(gtb_ctx *ctx, int region_id);
 
 /* Index inspection (parity with PHIndex contents): keys ascending, labels in bucket order. */
