@@ -260,8 +260,13 @@ def main() -> None:
     # inputs live in page-locked host memory (gtb_host_alloc), as a production caller would fill them
     batches, pinned_arena = engine.pin_batches(batches)
     ids = list(range(len(graphs)))
+    # region setup = host index build (parallel threads) + graph/label upload + on-device table build.
+    # First call pays one-time CUDA module/pinned-pool initialisation, so the steady-state figure is the second call.
+    ctx.region_begin_multi(ids, graphs)
+    for k in ids:
+        ctx.region_end(k)
     t0 = time.perf_counter()
-    ctx.region_begin_multi(ids, graphs)  # host index builds in parallel threads, table built on the device
+    ctx.region_begin_multi(ids, graphs)
     for k in ids:
         ctx.pool_begin(k, 1)
     t_region = time.perf_counter() - t0
@@ -375,6 +380,8 @@ def main() -> None:
             "kernels_ms": {**{nm: float(np.mean(v)) for nm, v in kt.items()},
                            "replay_call_wall_ms": float(np.mean(wall)) * 1e3, "slow_tasks": n_slow},
             "region_setup_s": t_region,
+            "e2e_incl_region_setup": {"value": total_reads / (e2e_t + t_region), "unit": "reads/s",
+                                      "note": "index build + graph upload + H2D + kernels + D2H for the whole 1 Mb"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "probe_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ},

@@ -44,7 +44,7 @@ class ReadBatch(C.Structure):
         ("n_reads", C.c_uint32), ("seq_stride", C.c_uint32),
         ("seq4", u8p), ("lseq", u16p), ("flag", u16p), ("mapq", u8p), ("isize", i32p),
         ("same_tid", u8p), ("score_diff", u8p), ("clipped", u8p), ("sample", i32p),
-        ("mate", i32p), ("dup_of", i32p),
+        ("mate", i32p), ("dup_of", i32p), ("leftover", u8p),
     ]
 
 
@@ -58,6 +58,7 @@ class Accumulators(C.Structure):
         ("vs_clipped_reads", u64p), ("vs_mapq_squared", u64p),
         ("pa_clipped_bp", u64p), ("pa_mapq_squared", u64p), ("pa_score_diff", u64p), ("pa_mismatches", u64p),
         ("read_strand", u32p),
+        ("depth_size", C.c_uint32), ("reference_offset", C.c_uint32), ("ref_depth", u16p),
     ]
 
 
@@ -126,7 +127,7 @@ class HostBatch:
     """Owns the arrays behind a ReadBatch."""
 
     def __init__(self, seq4, lseq, flag, mapq, isize, same_tid, score_diff, clipped, sample, mate, dup_of,
-                 seq_stride: int = SEQ_STRIDE):
+                 seq_stride: int = SEQ_STRIDE, leftover=None):
         n = len(lseq)
         self.seq4 = np.ascontiguousarray(seq4, dtype=np.uint8).reshape(n, seq_stride)
         self.lseq = np.ascontiguousarray(lseq, dtype=np.uint16)
@@ -139,6 +140,9 @@ class HostBatch:
         self.sample = np.ascontiguousarray(sample, dtype=np.int32)
         self.mate = np.ascontiguousarray(mate, dtype=np.int32)
         self.dup_of = np.ascontiguousarray(dup_of, dtype=np.int32)
+        if leftover is None:
+            leftover = compute_leftover(self.flag, self.mate)
+        self.leftover = np.ascontiguousarray(leftover, dtype=np.uint8)
         b = ReadBatch()
         b.n_reads = n
         b.seq_stride = seq_stride
@@ -153,6 +157,7 @@ class HostBatch:
         b.sample = _ptr(self.sample, i32p)
         b.mate = _ptr(self.mate, i32p)
         b.dup_of = _ptr(self.dup_of, i32p)
+        b.leftover = _ptr(self.leftover, u8p)
         self.view = b
 
     def __len__(self) -> int:
@@ -160,14 +165,16 @@ class HostBatch:
 
     def nbytes_h2d(self) -> int:
         return sum(x.nbytes for x in (self.seq4, self.lseq, self.flag, self.mapq, self.isize, self.same_tid,
-                                      self.score_diff, self.clipped, self.sample, self.mate, self.dup_of))
+                                      self.score_diff, self.clipped, self.sample, self.mate, self.dup_of,
+                                      self.leftover))
 
 
 class HostAccumulators:
     """Caller-owned accumulator buffers sized from (n_bubbles, n_scores, n_cov, n_samples)."""
 
-    def __init__(self, n_bubbles: int, n_scores: int, n_cov: int, n_samples: int):
+    def __init__(self, n_bubbles: int, n_scores: int, n_cov: int, n_samples: int, depth_size: int = 0):
         NB, NS = n_bubbles, n_samples
+        self.ref_depth = np.zeros(depth_size * NS, np.uint16)
         self.bubble_id = np.zeros(NB, np.uint32)
         self.n_alleles = np.zeros(NB, np.uint32)
         self.score_off = np.zeros(NB + 1, np.uint64)
@@ -190,7 +197,12 @@ class HostAccumulators:
         a.n_bubbles = NB
         a.n_samples = NS
         for name, typ in Accumulators._fields_[2:]:
+            if name in ("depth_size", "reference_offset"):
+                continue
             setattr(a, name, _ptr(getattr(self, name), typ))
+        a.depth_size = depth_size
+        if depth_size == 0:
+            a.ref_depth = C.cast(None, u16p)
         self.view = a
         self.n_samples = NS
         self.n_bubbles = NB
@@ -201,7 +213,10 @@ class HostAccumulators:
               "pa_mismatches", "read_strand"]
 
     def as_dict(self) -> Dict[str, np.ndarray]:
-        return {k: getattr(self, k) for k in self.ARRAYS}
+        d = {k: getattr(self, k) for k in self.ARRAYS}
+        if len(self.ref_depth):
+            d["ref_depth"] = self.ref_depth
+        return d
 
 
 # ----------------------------------------------------------------------------- read preparation (host)
@@ -232,6 +247,16 @@ def score_diff_from_tags(as_tag: np.ndarray, xs_tag: np.ndarray) -> np.ndarray:
     x = np.where(x == -1, 0, x)
     d = np.minimum(a - x, 255)
     return np.where(zero, 0, d).astype(np.uint8)
+
+
+def compute_leftover(flag: np.ndarray, mate: np.ndarray) -> np.ndarray:
+    """Paired records still waiting in the read-name map when the pool ends (only used on SV graphs,
+    hts_parallel_reader.cpp:719-772): paired, not the second arrival of a pair, never referenced as a mate."""
+    n = len(flag)
+    has_partner = np.zeros(n, bool)
+    m = mate[mate >= 0]
+    has_partner[m] = True
+    return (((flag & 1) != 0) & (mate < 0) & ~has_partner).astype(np.uint8)
 
 
 def compute_dup_of(pos: np.ndarray, lseq: np.ndarray, seq4: np.ndarray, tid: Optional[np.ndarray] = None) -> np.ndarray:

@@ -111,6 +111,7 @@ struct Region
   std::vector<uint32_t> bubble_order, n_alleles, score_off, cov_off;
   HostIndex index;
   uint32_t n_bubbles = 0;
+  uint32_t depth_size = 0, reference_offset = 0; // SV graphs only
   int n_samples = 0;
   bool pool_open = false;
   // device
@@ -499,6 +500,8 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g)
   D.cov_off = reinterpret_cast<const uint32_t *>(d + o_cov_off);
   D.table = reinterpret_cast<const IndexSlot *>(d + o_table);
   D.labels = reinterpret_cast<const DevLabel *>(d + o_labels);
+  D.depth_size = R.depth_size;
+  D.reference_offset = R.reference_offset;
 
   int slot = -1;
   for (size_t s = 0; s < c->slot_region.size(); ++s)
@@ -544,6 +547,14 @@ int gtb_region_begin_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
                  auto R = std::make_unique<Region>();
                  R->id = region_ids[i];
                  R->n_bubbles = g->n_ref - 1;
+                 if (g->is_sv_graph)
+                 {
+                   // ReferenceDepth: offset = first ref node order, size = graph.reference.size() (reference_depth.cpp:17-27)
+                   uint32_t const last = g->n_ref - 1;
+                   uint32_t const last_reach = g->ref_order[last] + (uint32_t)(g->ref_seq_off[last + 1] - g->ref_seq_off[last]) - 1;
+                   R->reference_offset = g->ref_order[0];
+                   R->depth_size = last_reach >= g->ref_order[0] ? last_reach - g->ref_order[0] + 1 : 0;
+                 }
                  IndexBuilder ib(*g);
                  const char * err = nullptr;
                  if (!ib.build(R->index, &err))
@@ -655,6 +666,7 @@ int gtb_pool_begin(gtb_ctx * ctx, int region_id, int n_samples)
   size_t const o_amb = place<uint32_t>(off, NB * NS);
   size_t const o_amba = place<uint32_t>(off, NB * NS);
   size_t const o_altpp = place<uint32_t>(off, NB * NS);
+  size_t const o_rdd = place<int>(off, R.depth_size ? ((size_t)R.depth_size + 1) * NS : 0);
   size_t const o_vcr = place<unsigned long long>(off, NB);
   size_t const o_vmq = place<unsigned long long>(off, NB);
   size_t const o_pcb = place<unsigned long long>(off, n_cov);
@@ -676,6 +688,7 @@ int gtb_pool_begin(gtb_ctx * ctx, int region_id, int n_samples)
   D.amb = reinterpret_cast<uint32_t *>(d + o_amb);
   D.amb_alt = reinterpret_cast<uint32_t *>(d + o_amba);
   D.alt_pp = reinterpret_cast<uint32_t *>(d + o_altpp);
+  D.ref_depth_delta = reinterpret_cast<int *>(d + o_rdd);
   D.vs_clipped_reads = reinterpret_cast<unsigned long long *>(d + o_vcr);
   D.vs_mapq_squared = reinterpret_cast<unsigned long long *>(d + o_vmq);
   D.pa_clipped_bp = reinterpret_cast<unsigned long long *>(d + o_pcb);
@@ -795,6 +808,7 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   size_t const o_same = place<uint8_t>(off, total);
   size_t const o_sd = place<uint8_t>(off, total);
   size_t const o_clip = place<uint8_t>(off, total);
+  size_t const o_left = place<uint8_t>(off, total);
   size_t const o_isize = place<int32_t>(off, total);
   size_t const o_sample = place<int32_t>(off, total);
   size_t const o_mate = place<int32_t>(off, total);
@@ -873,6 +887,10 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
                    memcpy(h + o_clip + base, b.clipped, m);
                  else
                    memset(h + o_clip + base, 0, m);
+                 if (b.leftover)
+                   memcpy(h + o_left + base, b.leftover, m);
+                 else
+                   memset(h + o_left + base, 0, m);
                  memcpy(h + o_isize + base * 4, b.isize, m * 4);
                  memcpy(h + o_sample + base * 4, b.sample, m * 4);
                  uint32_t u = unit_base[i];
@@ -993,6 +1011,7 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   P.batch.same_tid = d + o_same;
   P.batch.score_diff = d + o_sd;
   P.batch.clipped = d + o_clip;
+  P.batch.leftover = d + o_left;
   P.batch.isize = reinterpret_cast<const int32_t *>(d + o_isize);
   P.batch.sample = reinterpret_cast<const int32_t *>(d + o_sample);
   P.batch.mate = reinterpret_cast<const int32_t *>(d + o_mate);
@@ -1246,6 +1265,23 @@ static void convert_accumulators(Region const & R, const uint8_t * h, gtb_accumu
   memcpy(out->pa_score_diff, host_of(R.dev.pa_score_diff), n_cov * 8);
   memcpy(out->pa_mismatches, host_of(R.dev.pa_mismatches), n_cov * 8);
   memcpy(out->read_strand, host_of(R.dev.read_strand), n_cov * 16);
+  out->depth_size = R.depth_size;
+  out->reference_offset = R.reference_offset;
+  if (out->ref_depth && R.depth_size)
+  {
+    const int * delta = reinterpret_cast<const int *>(host_of(R.dev.ref_depth_delta));
+    for (uint32_t s = 0; s < NS; ++s)
+    {
+      long long run = 0;
+      const int * dl = delta + (size_t)s * ((size_t)R.depth_size + 1);
+      uint16_t * o = out->ref_depth + (size_t)s * R.depth_size;
+      for (uint32_t k = 0; k < R.depth_size; ++k)
+      {
+        run += dl[k];
+        o[k] = (uint16_t)std::min<long long>(std::max<long long>(run, 0), 0xFFFF);
+      }
+    }
+  }
 }
 
 // Downloads the accumulators of several regions with ONE stream synchronisation; conversion runs in parallel.
@@ -1274,6 +1310,19 @@ int gtb_pool_finish_multi(gtb_ctx * ctx, int n, const int * region_ids, gtb_accu
     CUDA_TRY(cudaMemcpyAsync(h + off[i], regs[i]->accum.p, regs[i]->accum_bytes, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   parallel_for(n, [&](int i) { convert_accumulators(*regs[i], h + off[i], &outs[i]); });
+  return 0;
+}
+
+int gtb_ref_depth_size(gtb_ctx * ctx, int region_id, uint32_t * depth_size, uint32_t * reference_offset)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  auto it = c->regions.find(region_id);
+  if (it == c->regions.end())
+    return fail(GTB_ERR_STATE, "unknown region");
+  if (depth_size)
+    *depth_size = it->second->depth_size;
+  if (reference_offset)
+    *reference_offset = it->second->reference_offset;
   return 0;
 }
 

@@ -75,6 +75,9 @@ struct DevRegion
   unsigned long long * pa_score_diff;
   unsigned long long * pa_mismatches;
   uint32_t * read_strand;                // [cov_off[NB] * 4]
+  // SV graphs: ReferenceDepth as a difference array per sample (prefix-summed on download), (depth_size + 1) ints each
+  int * ref_depth_delta;
+  uint32_t depth_size, reference_offset;
 };
 
 // Records of one submit (possibly several regions concatenated), SoA on the device.
@@ -94,6 +97,7 @@ struct DevBatch
   const int32_t * unit;        // alignment unit of each record
   const uint16_t * region;     // region slot of each record
   const int32_t * unit_record; // [n_units] record that defines the unit
+  const uint8_t * leftover;    // SV only: paired record whose mate never arrived
 };
 
 // Result of aligning one read orientation (GenotypePaths summary) -- 16 bytes.

@@ -1994,6 +1994,89 @@ __device__ bool push_scores(const LaunchParams & P, const DevRegion & R, const G
   return true;
 }
 
+// ReferenceDepth::add_genotype_paths (src/graph/reference_depth.cpp:114-203) on a per-sample difference array:
+// +1 at the first covered index, -1 one past the last; one path = its span, several paths = the union of their
+// (4-bp trimmed) spans.  Saturation (u16) is applied after the prefix sum on download.
+__device__ void add_ref_depth(const LaunchParams & P, const DevRegion & R, const Geno & geno, int sample)
+{
+  if (geno.s.npaths == 0 || geno.s.longest < 63)
+    return;
+  GR g(R);
+  long long const size = R.depth_size, offset = R.reference_offset;
+  int * delta = R.ref_depth_delta + (size_t)sample * (size_t)(size + 1);
+  const uint32_t * w = P.path_pool + geno.s.path_off;
+  long long const RL = geno.read_length;
+  if (geno.s.npaths == 1)
+  {
+    long long const sp = (long long)g.ref_reach_pos(w[0]) - (long long)(w[2] & 0xFFFFu);
+    long long const ep = (long long)g.ref_reach_pos(w[1]) + (RL - 1 - (long long)(w[2] >> 16));
+    long long const si = sp < offset ? 0 : sp - offset;
+    long long ei = ep > offset + size ? size : ep + 1 - offset;
+    if (si < size)
+    {
+      if (ei < si || ei > size)
+        ei = size; // the reference's iterator loop runs to the end of the track in that case
+      if (ei > si)
+      {
+        atomicAdd(delta + si, 1);
+        atomicAdd(delta + ei, -1);
+      }
+    }
+    return;
+  }
+  long long iv[MAXP][2];
+  int n = 0;
+  for (int pi = 0; pi < geno.s.npaths && n < MAXP; ++pi)
+  {
+    uint32_t const nvar = w[3] >> 16;
+    long long sp = (long long)g.ref_reach_pos(w[0]) - (long long)(w[2] & 0xFFFFu);
+    long long ep = (long long)g.ref_reach_pos(w[1]) + (RL - 1 - (long long)(w[2] >> 16));
+    w += PATH_HDR_WORDS + 2 * nvar;
+    if (ep - sp >= 50)
+    {
+      sp += 4;
+      ep -= 4;
+    }
+    if (ep < offset)
+      continue;
+    long long const si = sp < offset ? 0 : sp - offset;
+    long long ei = ep > offset + size ? size : ep + 1 - offset;
+    if (si >= size)
+      continue;
+    if (ei < si || ei > size)
+      ei = size;
+    if (ei <= si)
+      continue;
+    // insertion sort by start
+    int k = n++;
+    while (k > 0 && iv[k - 1][0] > si)
+    {
+      iv[k][0] = iv[k - 1][0];
+      iv[k][1] = iv[k - 1][1];
+      --k;
+    }
+    iv[k][0] = si;
+    iv[k][1] = ei;
+  }
+  if (n == 0)
+    return;
+  long long cs = iv[0][0], ce = iv[0][1];
+  for (int k = 1; k < n; ++k)
+  {
+    if (iv[k][0] <= ce)
+      ce = max(ce, iv[k][1]);
+    else
+    {
+      atomicAdd(delta + cs, 1);
+      atomicAdd(delta + ce, -1);
+      cs = iv[k][0];
+      ce = iv[k][1];
+    }
+  }
+  atomicAdd(delta + cs, 1);
+  atomicAdd(delta + ce, -1);
+}
+
 // GenotypePaths pair of one record as update_paths leaves it
 __device__ void make_genos(const LaunchParams & P, int rec, Geno & first, Geno & second)
 {
@@ -2061,6 +2144,11 @@ __global__ void __launch_bounds__(128) score_kernel(LaunchParams P)
     }
     if (s1 < 0)
       return;
+    if (R.is_sv) // hts_parallel_reader.cpp:321-326
+    {
+      add_ref_depth(P, R, g[s1], sample);
+      add_ref_depth(P, R, g[s2], sample);
+    }
     bool ok = true;
     if (geno_good(R, g[s1]))
       ok = push_scores(P, R, g[s1], sample) && ok;
@@ -2069,6 +2157,35 @@ __global__ void __launch_bounds__(128) score_kernel(LaunchParams P)
     if (!ok)
       atomicAdd(&P.counters->n_overflow, 1ull);
     atomicAdd(&P.counters->n_pairs_scored, 1ull);
+  }
+  else if (R.is_sv && P.batch.leftover[i])
+  {
+    // leftover mate at pool end (SV calling only, hts_parallel_reader.cpp:719-772): paired against a copy of itself
+    // with IS_FIRST_IN_PAIR and IS_SEQ_REVERSED toggled; the first-in-pair side of the better pairing is scored alone
+    Geno g[4];
+    make_genos(P, (int)i, g[0], g[1]);
+    if (((g[0].s.bits | g[1].s.bits) & TS_OVERFLOW) != 0)
+      return;
+    g[2] = g[0];
+    g[3] = g[1];
+    g[2].flags ^= (F_FIRST | F_REV);
+    g[3].flags ^= (F_FIRST | F_REV);
+    int arr[4] = {-1, -1, -1, -1};
+    for (int k = 0; k < 4; ++k)
+      arr[((g[k].flags & F_FIRST) != 0) + 2 * ((g[k].flags & F_REV) == 0)] = k;
+    if (arr[0] < 0 || arr[1] < 0 || arr[2] < 0 || arr[3] < 0)
+      return;
+    int const c = compare_pairs(g[arr[3]], g[arr[0]], g[arr[1]], g[arr[2]]);
+    int const s1 = c == 1 ? arr[3] : c == 2 ? arr[1] : -1;
+    if (s1 < 0)
+      return;
+    add_ref_depth(P, R, g[s1], sample);
+    if (geno_good(R, g[s1]))
+    {
+      if (!push_scores(P, R, g[s1], sample))
+        atomicAdd(&P.counters->n_overflow, 1ull);
+      atomicAdd(&P.counters->n_singles_scored, 1ull);
+    }
   }
   else if ((flag & F_PAIRED) == 0)
   {

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(HERE, "libgtb200.so")
 
 EXPORTS = [
     "gtb_last_error", "gtb_version", "gtb_create", "gtb_destroy", "gtb_region_begin", "gtb_region_begin_multi", "gtb_region_end",
-    "gtb_index_size", "gtb_index_export", "gtb_pool_begin", "gtb_submit_reads", "gtb_accumulator_sizes",
+    "gtb_index_size", "gtb_index_export", "gtb_pool_begin", "gtb_submit_reads", "gtb_accumulator_sizes", "gtb_ref_depth_size",
     "gtb_pool_finish", "gtb_pool_finish_multi", "gtb_pool_reset_multi", "gtb_submit_reads_multi", "gtb_debug_enable", "gtb_debug_seed_sizes", "gtb_debug_seeds",
     "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_replay_last",
     "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators", "gtb_allreduce_accumulators_multi", "gtb_debug_counters",
@@ -58,6 +58,7 @@ def load_library() -> C.CDLL:
     L.gtb_submit_reads.argtypes = [vp, C.c_int, C.POINTER(abi.ReadBatch), C.POINTER(abi.SubmitStats)]
     L.gtb_submit_reads_multi.argtypes = [vp, C.c_int, abi.i32p, C.POINTER(abi.ReadBatch), C.POINTER(abi.SubmitStats)]
     L.gtb_accumulator_sizes.argtypes = [vp, C.c_int, abi.u32p, abi.u64p, abi.u64p]
+    L.gtb_ref_depth_size.argtypes = [vp, C.c_int, abi.u32p, abi.u32p]
     L.gtb_pool_finish.argtypes = [vp, C.c_int, C.POINTER(abi.Accumulators)]
     L.gtb_pool_finish_multi.argtypes = [vp, C.c_int, abi.i32p, C.POINTER(abi.Accumulators)]
     L.gtb_pool_reset_multi.argtypes = [vp, C.c_int, abi.i32p]
@@ -218,16 +219,16 @@ class Context:
                 "n_slow_tasks": int(n.value)}
 
     def pool_finish(self, region_id: int) -> abi.HostAccumulators:
-        nb, ns, nc = C.c_uint32(), C.c_uint64(), C.c_uint64()
-        self._check(self.lib.gtb_accumulator_sizes(self.h, region_id, C.byref(nb), C.byref(ns), C.byref(nc)))
-        acc = abi.HostAccumulators(nb.value, ns.value, nc.value, self._samples[region_id])
+        acc = self.alloc_accumulators(region_id)
         self._check(self.lib.gtb_pool_finish(self.h, region_id, C.byref(acc.view)))
         return acc
 
     def alloc_accumulators(self, region_id: int) -> abi.HostAccumulators:
         nb, ns, nc = C.c_uint32(), C.c_uint64(), C.c_uint64()
         self._check(self.lib.gtb_accumulator_sizes(self.h, region_id, C.byref(nb), C.byref(ns), C.byref(nc)))
-        return abi.HostAccumulators(nb.value, ns.value, nc.value, self._samples[region_id])
+        ds, ro = C.c_uint32(), C.c_uint32()
+        self._check(self.lib.gtb_ref_depth_size(self.h, region_id, C.byref(ds), C.byref(ro)))
+        return abi.HostAccumulators(nb.value, ns.value, nc.value, self._samples[region_id], depth_size=ds.value)
 
     def pool_finish_multi(self, region_ids: Sequence[int], out: Optional[List[abi.HostAccumulators]] = None):
         """Accumulators of several regions with one stream synchronisation; `out` buffers are reused when given."""

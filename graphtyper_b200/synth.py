@@ -385,3 +385,57 @@ def write_dataset(ds: Dataset, out_dir: str, region_size: int = 50000) -> dict:
             sams.append(p)
         man["regions"].append({"begin": b, "end": e, "sams": sams})
     return man
+
+
+# ----------------------------------------------------------------------------- structural variants (genotype_sv)
+
+def make_sv_sites(ref: np.ndarray, n_sites: int, seed: int = 52, min_size: int = 50, max_size: int = 1000,
+                  margin: int = 1500, spacing: int = 1500, p_del: float = 0.6, p_ins: float = 0.25) -> List[Site]:
+    """Non-overlapping <DEL> / <INS> / <DUP> sites. `Site.ref`/`Site.alt` hold the resolved sequences (used to build
+    the sample haplotypes); write_sv_vcf() writes the symbolic records graphtyper's SV constructor parses
+    (INFO keys of src/graph/constructor.cpp:1301-1313)."""
+    rng = np.random.default_rng(seed)
+    L = len(ref)
+    n_slots = (L - 2 * margin) // (max_size + spacing)
+    if n_sites > n_slots:
+        raise ValueError("too many SV sites")
+    slots = np.sort(rng.choice(n_slots, size=n_sites, replace=False))
+    sites: List[Site] = []
+    for sl in slots.tolist():
+        p = margin + sl * (max_size + spacing) + int(rng.integers(0, spacing // 2))
+        size = int(rng.integers(min_size, max_size + 1))
+        anchor = bytes(ref[p - 1:p])
+        k = rng.random()
+        if k < p_del:
+            s = Site(p, bytes(ref[p - 1:p + size]), anchor)
+            s.sv = ("DEL", size, None)
+        elif k < p_del + p_ins:
+            ins = bytes(BASES[rng.integers(0, 4, size=size)])
+            s = Site(p, anchor, anchor + ins)
+            s.sv = ("INS", size, ins)
+        else:  # tandem duplication of the `size` bases that follow the anchor
+            dup = bytes(ref[p:p + size])
+            s = Site(p, anchor, anchor + dup)
+            s.sv = ("DUP", size, None)
+        sites.append(s)
+    return sites
+
+
+def write_sv_vcf(path: str, sites: List[Site], contig: str = "chr1", contig_len: int = 0) -> None:
+    with open(path, "w") as f:
+        f.write("##fileformat=VCFv4.2\n")
+        f.write(f"##contig=<ID={contig},length={contig_len}>\n")
+        for k, d in (("SVTYPE", "String"), ("SVSIZE", "Integer"), ("SVLEN", "Integer"), ("END", "Integer"),
+                     ("SEQ", "String")):
+            f.write(f'##INFO=<ID={k},Number=1,Type={d},Description="{k}">\n')
+        f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+        for s in sites:
+            typ, size, seq = s.sv
+            ref_base = s.ref[:1].decode()
+            if typ == "DEL":
+                info = f"SVTYPE=DEL;SVSIZE={size};SVLEN=-{size};END={s.pos + size}"
+            elif typ == "INS":
+                info = f"SVTYPE=INS;SVSIZE={size};SVLEN={size};END={s.pos};SEQ={seq.decode()}"
+            else:
+                info = f"SVTYPE=DUP;SVSIZE={size};SVLEN={size};END={s.pos + size}"
+            f.write(f"{contig}\t{s.pos}\t.\t{ref_base}\t<{typ}>\t.\t.\t{info}\n")

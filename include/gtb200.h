@@ -102,6 +102,8 @@ typedef struct gtb_read_batch {
                                  (read-name map semantics of genotype_only, hts_parallel_reader.cpp:270-337) */
   const int32_t *dup_of;      /* index of the record whose alignment is re-used (equal_pos_seq shortcut,
                                  hts_parallel_reader.cpp:666-684), else -1 */
+  const uint8_t *leftover;    /* SV graphs only, may be NULL: 1 = paired record whose mate never arrived in this pool
+                                 (processed alone at pool end, hts_parallel_reader.cpp:719-772) */
 } gtb_read_batch;
 
 /* Per-pool accumulators = VcfWriter::haplotypes[b].hap_samples[s] (+ var_stats), bubble-major:
@@ -133,6 +135,11 @@ typedef struct gtb_accumulators {
   uint64_t *pa_score_diff;
   uint64_t *pa_mismatches;
   uint32_t *read_strand;      /* [cov_off[n_bubbles] * 4]  r1_forward r1_reverse r2_forward r2_reverse */
+  /* SV graphs only (ReferenceDepth, src/graph/reference_depth.cpp:114-203): per-sample per-base depth of the
+   * graph-aligned reads over [reference_offset, reference_offset + depth_size); ref_depth may be NULL. */
+  uint32_t depth_size;
+  uint32_t reference_offset;
+  uint16_t *ref_depth;        /* [n_samples * depth_size] */
 } gtb_accumulators;
 
 /* Counters of one gtb_submit_reads call (diagnostics + bench bookkeeping). */
@@ -170,6 +177,8 @@ int gtb_index_export(gtb_ctx *ctx, int region_id, uint64_t *keys, uint32_t *labe
 int gtb_pool_begin(gtb_ctx *ctx, int region_id, int n_samples);
 int gtb_submit_reads(gtb_ctx *ctx, int region_id, const gtb_read_batch *batch, gtb_submit_stats *stats);
 int gtb_accumulator_sizes(gtb_ctx *ctx, int region_id, uint32_t *n_bubbles, uint64_t *n_scores, uint64_t *n_cov);
+/* SV graphs: length and first absolute position of the per-base reference depth track (0 for non-SV graphs). */
+int gtb_ref_depth_size(gtb_ctx *ctx, int region_id, uint32_t *depth_size, uint32_t *reference_offset);
 int gtb_pool_finish(gtb_ctx *ctx, int region_id, gtb_accumulators *out);
 /* Several regions with one stream synchronisation (outs[i] belongs to region_ids[i]); zero several pools. */
 int gtb_pool_finish_multi(gtb_ctx *ctx, int n, const int *region_ids, gtb_accumulators *outs);

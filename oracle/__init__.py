@@ -65,6 +65,7 @@ class Oracle:
         L.gto_result_stats.argtypes = [C.c_void_p, C.POINTER(abi.SubmitStats)]
         L.gto_result_accum_sizes.argtypes = [C.c_void_p, abi.u32p, abi.u64p, abi.u64p]
         L.gto_result_accum.argtypes = [C.c_void_p, C.POINTER(abi.Accumulators)]
+        L.gto_result_ref_depth_size.argtypes = [C.c_void_p, abi.u32p, abi.u32p]
         L.gto_result_seed_sizes.argtypes = [C.c_void_p, abi.u64p, abi.u64p, abi.u64p]
         L.gto_result_seeds.argtypes = [C.c_void_p, abi.u32p, abi.u32p, abi.u32p, C.POINTER(abi.Label)]
         L.gto_result_path_sizes.argtypes = [C.c_void_p, abi.u64p, abi.u64p, abi.u64p, abi.u64p]
@@ -112,7 +113,9 @@ class Oracle:
     def result_accum(self, r, n_samples: int):
         nb, ns, nc = C.c_uint32(), C.c_uint64(), C.c_uint64()
         self.lib.gto_result_accum_sizes(r, C.byref(nb), C.byref(ns), C.byref(nc))
-        acc = self.abi.HostAccumulators(nb.value, ns.value, nc.value, n_samples)
+        ds, ro = C.c_uint32(), C.c_uint32()
+        self.lib.gto_result_ref_depth_size(r, C.byref(ds), C.byref(ro))
+        acc = self.abi.HostAccumulators(nb.value, ns.value, nc.value, n_samples, depth_size=ds.value)
         self.lib.gto_result_accum(r, C.byref(acc.view))
         return acc
 

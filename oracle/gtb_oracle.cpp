@@ -1701,10 +1701,64 @@ void push_to_haplotype_scores(const G & g, Writer & w, const GenoPaths & geno, l
   }
 }
 
+// ------------------------------------------------------------------------------------------------ reference depth (A16)
+// src/graph/reference_depth.cpp:17-36,114-232
+struct RefDepth
+{
+  long offset = 0;
+  std::vector<std::vector<uint16_t>> depths;
+  long start_idx(long p) const { return p < offset ? 0 : p - offset; }
+  long end_idx(long e, long size) const { return e > offset + size ? size : e + 1 - offset; }
+
+  void add_genotype_paths(const G & g, const GenoPaths & geno, long sample)
+  {
+    if (sample >= (long)depths.size())
+      return;
+    if (geno.paths.empty() || geno.paths[0].size() < 63)
+      return;
+    auto & depth = depths[sample];
+    long const size = (long)depth.size();
+    if (geno.paths.size() == 1)
+    {
+      auto const & p = geno.paths[0];
+      long const sp = (long)g.get_ref_reach_pos(p.start) - p.rs;
+      long const ep = (long)g.get_ref_reach_pos(p.end) + ((long)geno.read_length - 1 - p.re);
+      long const si = start_idx(sp), ei = end_idx(ep, size);
+      if (si < size)
+        for (long k = si; k != ei && k != size; ++k)
+          ++depth[k]; // not saturating in the reference
+    }
+    else
+    {
+      std::set<long> local;
+      for (auto const & p : geno.paths)
+      {
+        long sp = (long)g.get_ref_reach_pos(p.start) - p.rs;
+        long ep = (long)g.get_ref_reach_pos(p.end) + ((long)geno.read_length - 1 - p.re);
+        if (ep - sp >= 50)
+        {
+          sp += 4;
+          ep -= 4;
+        }
+        if (ep < offset)
+          continue;
+        long const si = start_idx(sp), ei = end_idx(ep, size);
+        if (si < size)
+          for (long k = si; k != ei && k != size; ++k)
+            local.insert(k);
+      }
+      for (long k : local)
+        if (depth[k] < 0xFFFF)
+          ++depth[k];
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------ pool driver (A10)
 struct PoolResult
 {
   Writer w;
+  RefDepth rd;
   int n_samples = 0;
   // debug taps: units = non-duplicate records in batch order
   std::vector<uint32_t> unit_record;
@@ -1717,6 +1771,13 @@ int run_pool(const G & g, const Index & idx, int n_samples, const gtb_read_batch
 {
   R.w.init(g, n_samples);
   R.n_samples = n_samples;
+  bool const SV = g.v.is_sv_graph != 0;
+  if (SV && g.v.n_ref > 0)
+  {
+    R.rd.offset = g.v.ref_order[0];
+    long const size = (long)g.ref_reach(g.v.n_ref - 1) - (long)g.v.ref_order[0] + 1;
+    R.rd.depths.assign(n_samples, std::vector<uint16_t>(size, 0));
+  }
   uint32_t const n = b.n_reads;
   std::vector<int32_t> unit_of(n, -1);
   // per record: the pair<GenotypePaths, GenotypePaths> after update_paths, kept while waiting for the mate
@@ -1826,6 +1887,11 @@ int run_pool(const G & g, const Index & idx, int n_samples, const gtb_read_batch
         {
           s1->flags |= IS_PROPER_PAIR;
           s2->flags |= IS_PROPER_PAIR;
+          if (SV) // hts_parallel_reader.cpp:321-326
+          {
+            R.rd.add_genotype_paths(g, *s1, sample);
+            R.rd.add_genotype_paths(g, *s2, sample);
+          }
           // update_haplotype_scores_geno (pair), vcf_writer.cpp:143-250
           bool const g1 = are_genotype_paths_good(g, *s1), g2 = are_genotype_paths_good(g, *s2);
           if (g1)
@@ -1837,6 +1903,38 @@ int run_pool(const G & g, const Index & idx, int n_samples, const gtb_read_batch
       }
       is_waiting[m] = 0;
       waiting[m] = std::pair<GenoPaths, GenoPaths>();
+    }
+  }
+  // leftover mates (SV calling only), hts_parallel_reader.cpp:719-772
+  if (SV)
+  {
+    for (uint32_t i = 0; i < n; ++i)
+    {
+      if (!is_waiting[i] || !(b.leftover && b.leftover[i]))
+        continue;
+      auto & orig = waiting[i];
+      std::pair<GenoPaths, GenoPaths> copy(orig);
+      copy.first.flags ^= (IS_FIRST_IN_PAIR | IS_SEQ_REVERSED);
+      copy.second.flags ^= (IS_FIRST_IN_PAIR | IS_SEQ_REVERSED);
+      GenoPaths * arr[4] = {nullptr, nullptr, nullptr, nullptr};
+      auto get_index = [](uint16_t f) { return ((f & IS_FIRST_IN_PAIR) != 0) + 2 * ((f & IS_SEQ_REVERSED) == 0); };
+      arr[get_index(orig.first.flags)] = &orig.first;
+      arr[get_index(orig.second.flags)] = &orig.second;
+      arr[get_index(copy.first.flags)] = &copy.first;
+      arr[get_index(copy.second.flags)] = &copy.second;
+      if (!(arr[0] && arr[1] && arr[2] && arr[3]))
+        continue;
+      int const c = compare_pairs(*arr[3], *arr[0], *arr[1], *arr[2]);
+      GenoPaths * s1 = c == 1 ? arr[3] : c == 2 ? arr[1] : nullptr;
+      if (!s1)
+        continue;
+      s1->flags |= IS_PROPER_PAIR;
+      R.rd.add_genotype_paths(g, *s1, b.sample[i]);
+      if (are_genotype_paths_good(g, *s1))
+      {
+        push_to_haplotype_scores(g, R.w, *s1, b.sample[i]);
+        ++R.stats.n_singles_scored;
+      }
     }
   }
   R.stats.n_records = n;
@@ -1952,6 +2050,14 @@ int gto_result_accum(void * r, gtb_accumulators * out)
   uint32_t const NS = (uint32_t)R->n_samples;
   out->n_bubbles = NB;
   out->n_samples = NS;
+  if (out->ref_depth && !R->rd.depths.empty())
+  {
+    size_t const sz = R->rd.depths[0].size();
+    out->depth_size = (uint32_t)sz;
+    out->reference_offset = (uint32_t)R->rd.offset;
+    for (uint32_t s = 0; s < NS; ++s)
+      memcpy(out->ref_depth + (size_t)s * sz, R->rd.depths[s].data(), sz * 2);
+  }
   for (uint32_t b = 0; b <= NB; ++b)
   {
     out->score_off[b] = so[b];
@@ -1986,6 +2092,14 @@ int gto_result_accum(void * r, gtb_accumulators * out)
         out->read_strand[(co[b] + a) * 4 + k] = h.read_strand[(size_t)a * 4 + k];
     }
   }
+  return 0;
+}
+
+int gto_result_ref_depth_size(void * r, uint32_t * depth_size, uint32_t * reference_offset)
+{
+  auto * R = (PoolResult *)r;
+  *depth_size = R->rd.depths.empty() ? 0u : (uint32_t)R->rd.depths[0].size();
+  *reference_offset = (uint32_t)R->rd.offset;
   return 0;
 }
 

@@ -564,6 +564,37 @@ int main(int argc, char ** argv)
   }
   (void)have_prev;
 
+  // leftover mates: SV calling only -- restated driver of hts_parallel_reader.cpp:719-772 on the reference's functions
+  if (IS_SV)
+  {
+    auto process_leftovers = [&](long sample_i, long rg_i)
+    {
+      auto & map_gpaths = maps[rg_i];
+      for (auto read_it = map_gpaths.begin(); read_it != map_gpaths.end(); ++read_it)
+      {
+        std::pair<GenotypePaths, GenotypePaths> copy(read_it->second);
+        toggle_bit(copy.first.flags, IS_FIRST_IN_PAIR | IS_SEQ_REVERSED);
+        toggle_bit(copy.second.flags, IS_FIRST_IN_PAIR | IS_SEQ_REVERSED);
+        std::pair<GenotypePaths *, GenotypePaths *> better = get_better_paths(read_it->second, copy);
+        if (better.first)
+        {
+          reference_depth.add_genotype_paths(*better.first, sample_i);
+          writer.update_haplotype_scores_geno(*better.first, sample_i, nullptr);
+        }
+      }
+    };
+    for (long file_i = 0; file_i < static_cast<long>(hts_preader.hts_files.size()); ++file_i)
+    {
+      auto const & hts_f = hts_preader.hts_files[file_i];
+      if (hts_f.rg2sample_i.size() <= 1)
+        process_leftovers(hts_f.sample_index_offset, hts_f.rg_index_offset);
+      else
+        for (long rg_i = 0; rg_i < static_cast<long>(hts_f.rg2sample_i.size()); ++rg_i)
+          process_leftovers(hts_f.sample_index_offset + hts_f.rg2sample_i[rg_i], hts_f.rg_index_offset + rg_i);
+    }
+    maps.clear();
+  }
+
   {
     ArrayFile af;
     af.add("flag", r_flag);

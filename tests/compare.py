@@ -85,7 +85,8 @@ def probe_accum(d: dict) -> dict:
     num = d["hap_num"].astype(np.uint64)
     score_off = np.concatenate([[0], np.cumsum(num * (num + 1) // 2)]).astype(np.uint64)
     cov_off = np.concatenate([[0], np.cumsum(num)]).astype(np.uint64)
-    return {"bubble_id": d["hap_id"], "n_alleles": d["hap_num"], "score_off": score_off, "cov_off": cov_off,
+    extra = {"ref_depth": d["ref_depth"]} if "ref_depth" in d else {}
+    return {**extra, "bubble_id": d["hap_id"], "n_alleles": d["hap_num"], "score_off": score_off, "cov_off": cov_off,
             "log_score": d["log_score"], "gt_coverage": d["gt_cov"], "max_log_score": d["max_log_score"],
             "ambiguous_depth": d["amb"], "ambiguous_depth_alt": d["amb_alt"], "alt_proper_pair_depth": d["alt_pp"],
             "vs_clipped_reads": d["vs_clipped_reads"], "vs_mapq_squared": d["vs_mapq_sq"],

@@ -28,6 +28,14 @@ SMALL = {
                          lowmapq_rate=0.1, unpaired_rate=0.05, improper_rate=0.08, flip_rate=0.5), 50000),
     "mini_r100": (dict(length=6000, n_sites=40, n_samples=1, seed=31, coverage=20, err=0.004, read_len=100), 50000),
 }
+# structural-variant fixtures (genotype_sv flow, is_sv_graph = true): kwargs of the SV generator below
+SMALL_SV = {
+    "mini_sv": dict(length=16000, n_sites=3, n_samples=2, seed=61, coverage=14, max_size=400, orphan_rate=0.06),
+}
+BIG_SV = {
+    "sv30k": dict(length=30000, n_sites=6, n_samples=2, seed=71, coverage=20, max_size=600, orphan_rate=0.06),
+    "sv60k": dict(length=60000, n_sites=14, n_samples=3, seed=81, coverage=15, max_size=1000, orphan_rate=0.04),
+}
 BIG = {
     "r60k": (dict(length=60000, n_sites=600, n_samples=1, seed=11), 50000),
     "stress": (dict(length=30000, n_sites=600, n_samples=3, seed=21, coverage=20, err=0.01, n_rate=0.002,
@@ -55,12 +63,47 @@ def run(name: str, kwargs: dict, region_size: int, out_dir: str) -> None:
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def run_sv(name: str, kw: dict, out_dir: str) -> None:
+    """<DEL>/<INS>/<DUP> sites, reads from the carrier haplotypes, a fraction of mates dropped (they become the
+    'leftover' reads genotype_sv processes at pool end); probe run with --sv (is_sv_graph = true)."""
+    import numpy as np
+    tmp = tempfile.mkdtemp(prefix="gtb_golden_sv_")
+    try:
+        L = kw["length"]
+        ref = synth.make_reference(L, kw["seed"])
+        sites = synth.make_sv_sites(ref, kw["n_sites"], seed=kw["seed"] + 1, max_size=kw["max_size"], p_del=0.5, p_ins=0.3)
+        gts = synth.make_genotypes(len(sites), kw["n_samples"], kw["seed"] + 2)
+        fa = os.path.join(tmp, "ref.fa")
+        synth.write_fasta(fa, ref)
+        vcf = os.path.join(tmp, "sv.vcf")
+        synth.write_sv_vcf(vcf, sites, "chr1", L)
+        subprocess.run([os.path.join(BIN, "bgzip"), "-f", vcf], check=True)
+        subprocess.run([os.path.join(BIN, "tabix"), "-f", "-p", "vcf", vcf + ".gz"], check=True)
+        rng = np.random.default_rng(kw["seed"] + 3)
+        sams = []
+        for k in range(kw["n_samples"]):
+            rs = synth.simulate_reads(ref, sites, gts[k], f"SAMP{k + 1}", kw["seed"] + 10 + k, coverage=kw["coverage"],
+                                      err=0.004, lowmapq_rate=0.05)
+            keep = np.nonzero((rng.random(len(rs)) > kw["orphan_rate"]) & (rs.pos >= 0) & (rs.mpos >= 0))[0]
+            sam = os.path.join(tmp, f"s{k}.sam")
+            synth.write_sam(sam, rs.subset(keep), "chr1", L)
+            sams.append(sam)
+        pre = os.path.join(out_dir, f"{name}.r0")
+        subprocess.run([os.path.join(BIN, "gt_probe"), "--ref", fa, "--vcf", vcf + ".gz", "--region", f"chr1:1-{L}", "--sv",
+                        "--sams", ",".join(sams), "--out", pre], check=True, stderr=subprocess.DEVNULL)
+        print("wrote", pre, {s: os.path.getsize(pre + s) for s in (".graph.gtba", ".index.gtba", ".reads.gtba", ".accum.gtba")})
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main() -> None:
     big = "--big" in sys.argv
     out_dir = os.path.join(ROOT, "tests", "data_local" if big else "golden")
     os.makedirs(out_dir, exist_ok=True)
     for name, (kw, rs) in (BIG if big else SMALL).items():
         run(name, kw, rs, out_dir)
+    for name, kw in (BIG_SV if big else SMALL_SV).items():
+        run_sv(name, kw, out_dir)
 
 
 if __name__ == "__main__":
