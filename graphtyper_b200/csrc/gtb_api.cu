@@ -164,6 +164,7 @@ struct Ctx
   bool regions_dirty = true;
   // batch
   DeviceBuffer d_tap_counts, d_tap_pool, d_spill;
+  std::vector<DeviceBuffer> buffer_cache; // arenas / accumulators of ended regions, reused by the next regions
   PinnedBuffer h_stage, h_accum;
   bool have_last = false;
   bool debug = false;
@@ -174,6 +175,39 @@ struct Ctx
   void * nccl_comm = nullptr;
   int nccl_rank = 0, nccl_size = 1;
 };
+
+// Region arenas are recycled: cudaMalloc / cudaFree of ~10 MB blocks per region would otherwise dominate (and add
+// multi-millisecond jitter to) the per-region setup of a long run.
+int take_buffer(Ctx * c, DeviceBuffer & dst, size_t bytes)
+{
+  if (dst.cap >= bytes)
+    return 0;
+  dst.release();
+  int best = -1;
+  for (size_t i = 0; i < c->buffer_cache.size(); ++i)
+    if (c->buffer_cache[i].cap >= bytes && (best < 0 || c->buffer_cache[i].cap < c->buffer_cache[best].cap))
+      best = (int)i;
+  if (best >= 0)
+  {
+    dst = c->buffer_cache[best];
+    c->buffer_cache.erase(c->buffer_cache.begin() + best);
+    return 0;
+  }
+  return dst.reserve(bytes);
+}
+
+void give_buffer(Ctx * c, DeviceBuffer & b)
+{
+  if (b.p)
+  {
+    if (c->buffer_cache.size() < 256)
+      c->buffer_cache.push_back(b);
+    else
+      cudaFree(b.p);
+  }
+  b.p = nullptr;
+  b.cap = 0;
+}
 
 int upload_region_table(Ctx * c)
 {
@@ -384,6 +418,9 @@ void gtb_destroy(gtb_ctx * ctx)
       kv.second->accum.release();
     }
     c->d_regions.release();
+    for (auto & b : c->buffer_cache)
+      b.release();
+    c->buffer_cache.clear();
     for (auto & B : c->bs)
       B.release();
     c->d_tap_counts.release();
@@ -462,7 +499,7 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g)
   memcpy(h + o_labels, R.index.labels.data(), R.index.labels.size() * sizeof(DevLabel));
   memcpy(h + o_uniq, R.index.uniq.data(), R.index.uniq.size() * sizeof(IndexSlot));
 
-  if (int rc = R.arena.reserve(total))
+  if (int rc = take_buffer(c, R.arena, total))
     return rc;
   uint8_t * d = static_cast<uint8_t *>(R.arena.p);
   CUDA_TRY(cudaMemcpyAsync(d, h, upload_bytes, cudaMemcpyHostToDevice, c->stream));
@@ -607,8 +644,8 @@ int gtb_region_end(gtb_ctx * ctx, int region_id)
   {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    it->second->arena.release();
-    it->second->accum.release();
+    give_buffer(c, it->second->arena);
+    give_buffer(c, it->second->accum);
     if (it->second->slot >= 0)
       c->slot_region[it->second->slot] = -1;
     c->regions_dirty = true;
@@ -675,7 +712,7 @@ int gtb_pool_begin(gtb_ctx * ctx, int region_id, int n_samples)
   size_t const o_pmm = place<unsigned long long>(off, n_cov);
   size_t const o_rs = place<uint32_t>(off, n_cov * 4);
   size_t const total = align_up(off, 256);
-  if (int rc = R.accum.reserve(total))
+  if (int rc = take_buffer(c, R.accum, total))
     return rc;
   CUDA_TRY(cudaMemsetAsync(R.accum.p, 0, total, c->stream));
   R.accum_bytes = total;

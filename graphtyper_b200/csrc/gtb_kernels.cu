@@ -1534,7 +1534,7 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(LaunchParams P)
 // ================================================================================================ chain kernel
 // One THREAD per active task: phases B-D on a small per-thread working set (local memory).  Tasks that exceed a
 // small capacity, or that probe_kernel marked, are queued for slow_kernel.
-__global__ void __launch_bounds__(CHAIN_THREADS) chain_kernel(LaunchParams P)
+__global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(LaunchParams P)
 {
   uint32_t const t = blockIdx.x * CHAIN_THREADS + threadIdx.x;
   if (t >= P.n_active)
