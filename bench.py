@@ -40,6 +40,9 @@ ALGO_BYTES_PER_READ = 6468  # 100 read + 388 probes x 16 + 72 la
 LENGTH = 1_000_000
 N_SITES = 10_000
 REGION = 50_000
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE probe_kernel launch on this workload, from the committed ncu capture
+# profiles/r1_final_ncu_summary.txt (192.2 MB + 13.0 MB; cold L2).  Well below the algorithmic 1.29 GB: the tables are L2-resident.
+PROBE_DRAM_BYTES_PER_LAUNCH = 205_231_616
 
 
 def env_int(name: str, default: int) -> int:
@@ -386,7 +389,7 @@ def main() -> None:
             "e2e_incl_region_setup": {"value": total_reads / (e2e_t + t_region), "unit": "reads/s",
                                       "note": "index build + graph upload + H2D + kernels + D2H for the whole 1 Mb"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "probe_kernel", "peak_source": peak_src,
+                         "traffic": PROBE_DRAM_BYTES_PER_LAUNCH, "kernel": "probe_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ},
             "clocks": clocks,
         }

@@ -1625,6 +1625,189 @@ int gtb_calls_from_accumulators(const gtb_accumulators * acc, uint8_t * phred, u
   return 0;
 }
 
+// Variant::scan_calls (src/typer/variant.cpp:230-428) for every bubble of one pool (non-SV graphs)
+int gtb_scan_calls(const gtb_accumulators * acc, const uint8_t * phred, uint64_t * var, uint64_t * allele, double * ratio)
+{
+  if (!acc || !phred || !var || !allele || !ratio)
+    return fail(GTB_ERR_ARG, "null argument");
+  uint32_t const NB = acc->n_bubbles, NS = acc->n_samples;
+  memset(var, 0, (size_t)NB * 9 * 8);
+  memset(allele, 0, (size_t)acc->cov_off[NB] * 13 * 8);
+  for (uint64_t i = 0; i < acc->cov_off[NB]; ++i)
+    ratio[i] = 0.0;
+  for (uint32_t b = 0; b < NB; ++b)
+  {
+    uint64_t * V = var + (size_t)b * 9;
+    uint64_t const c0 = acc->cov_off[b];
+    uint32_t const cnum = acc->n_alleles[b];
+    uint64_t const tri = acc->score_off[b + 1] - acc->score_off[b];
+    auto A = [&](uint32_t a) { return allele + (c0 + a) * 13; };
+    V[1] += NS; // n_calls
+    for (uint32_t s = 0; s < NS; ++s)
+    {
+      const uint8_t * ph = phred + acc->score_off[b] * NS + (uint64_t)s * tri;
+      const uint16_t * cov = acc->gt_coverage + c0 * NS + (uint64_t)s * cnum;
+      uint8_t const amb = acc->ambiguous_depth[(uint64_t)b * NS + s];
+      uint8_t const altpp = acc->alt_proper_pair_depth[(uint64_t)b * NS + s];
+      // get_gt_call / get_gq (sample_call.cpp:78-131)
+      uint32_t g1 = 0, g2 = 0;
+      {
+        uint64_t i = 0;
+        bool done = false;
+        for (uint32_t y = 0; y < cnum && !done; ++y)
+          for (uint32_t x = 0; x <= y; ++x, ++i)
+            if (ph[i] == 0)
+            {
+              g1 = x;
+              g2 = y;
+              done = true;
+              break;
+            }
+      }
+      long gq;
+      {
+        bool seen = false, two = false;
+        uint8_t nl = 255;
+        for (uint64_t i = 0; i < tri; ++i)
+        {
+          if (ph[i] == 0)
+          {
+            if (seen)
+            {
+              two = true;
+              break;
+            }
+            seen = true;
+          }
+          else if (ph[i] < nl)
+            nl = ph[i];
+        }
+        gq = two ? 0 : nl;
+      }
+      auto lowest_phred_not_with = [&](uint32_t al) // sample_call.cpp:131-154
+      {
+        long i = 0;
+        uint8_t mn = 255;
+        for (long y = 0; y < (long)cnum; ++y)
+        {
+          if (y == (long)al)
+          {
+            i += y + 1;
+            continue;
+          }
+          for (long x = 0; x <= y; ++x, ++i)
+          {
+            if (x == (long)al)
+              continue;
+            if (ph[i] < mn)
+              mn = ph[i];
+          }
+        }
+        return mn;
+      };
+      if (tri > 0 && ph[0] > 0) // not homozygous reference
+      {
+        auto qd = [&](uint32_t al)
+        {
+          long const depth = std::min(10l, (long)cov[al] + (long)amb);
+          if (depth > 0)
+          {
+            A(al)[0] += (uint64_t)std::min(25l * depth, (long)lowest_phred_not_with(al));
+            A(al)[1] += (uint64_t)depth;
+          }
+        };
+        if (g1 > 0)
+          qd(g1);
+        if (g1 != g2)
+          qd(g2);
+      }
+      V[3] = std::max<uint64_t>(V[3], altpp); // MaxAltPP within the pool
+      uint64_t total_depth = 0;
+      for (uint32_t a = 0; a < cnum; ++a)
+        total_depth += cov[a];
+      for (uint32_t a = 1; a < cnum; ++a)
+      {
+        uint64_t * P = A(a);
+        P[8] = std::max<uint64_t>(P[8], cov[a]);
+        if (total_depth > 0)
+          ratio[c0 + a] = std::max(ratio[c0 + a], (double)cov[a] / (double)total_depth);
+        if (g1 == a || g2 == a)
+        {
+          if (g1 == g2)
+            ++P[7];
+          else
+            ++P[6];
+        }
+        else
+          ++P[5];
+      }
+      long const filter = gq >= 30 ? 0 : gq >= 20 ? 1 : gq >= 10 ? 2 : 3; // check_filter (sample_call.cpp:156-170)
+      bool nonzero = false;
+      for (uint64_t i = 0; i < tri; ++i)
+        nonzero = nonzero || ph[i] != 0;
+      if (nonzero)
+        ++V[0];
+      if (filter == 0)
+        ++V[2];
+      if (g1 != g2)
+      {
+        V[5] += cov[g1];
+        V[6] += cov[g2];
+        A(g1)[9] += cov[g1];
+        A(g1)[10] += total_depth - cov[g1];
+        A(g2)[9] += cov[g2];
+        A(g2)[10] += total_depth - cov[g2];
+      }
+      else
+      {
+        V[7] += cov[g1];
+        V[8] += total_depth - cov[g1];
+        A(g1)[11] += cov[g1];
+        A(g1)[12] += total_depth - cov[g1];
+      }
+      V[4] += total_depth + amb; // seqdepth += get_depth()
+      for (uint32_t a = 1; a < cnum; ++a)
+        A(a)[2] += cov[a];
+      ++A(g1)[3];
+      ++A(g2)[3];
+      if (filter == 0)
+      {
+        ++A(g1)[4];
+        ++A(g2)[4];
+      }
+    }
+  }
+  return 0;
+}
+
+// VarStats::add_stats (src/typer/var_stats.cpp:141-189) on the arrays of gtb_scan_calls: dst += src
+int gtb_merge_varstats(uint32_t n_bubbles, uint64_t n_alleles_total, uint64_t * var, uint64_t * allele, double * ratio,
+                       const uint64_t * var_src, const uint64_t * allele_src, const double * ratio_src)
+{
+  for (uint32_t b = 0; b < n_bubbles; ++b)
+    for (int k = 0; k < 9; ++k)
+    {
+      uint64_t & d = var[(size_t)b * 9 + k];
+      d += var_src[(size_t)b * 9 + k];
+      if (k == 3)
+        d &= 0xFFu; // uint8_t n_max_alt_proper_pairs is summed (not max-ed) in the reference and wraps
+    }
+  for (uint64_t a = 0; a < n_alleles_total; ++a)
+  {
+    for (int k = 0; k < 13; ++k)
+    {
+      uint64_t & d = allele[a * 13 + k];
+      uint64_t const sv = allele_src[a * 13 + k];
+      if (k == 8)
+        d = std::max(d, sv);
+      else
+        d += sv;
+    }
+    ratio[a] = std::max(ratio[a], ratio_src[a]);
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ multi-GPU reduce
 // NCCL is bound lazily (dlopen) so the library loads on hosts without it and never clashes with the NCCL copy
 // PyTorch bundles.  The communicator is created here from a unique id the caller distributes (e.g. with

@@ -21,7 +21,7 @@ EXPORTS = [
     "gtb_last_error", "gtb_version", "gtb_create", "gtb_destroy", "gtb_region_begin", "gtb_region_begin_multi", "gtb_region_end",
     "gtb_index_size", "gtb_index_export", "gtb_pool_begin", "gtb_submit_reads", "gtb_accumulator_sizes", "gtb_ref_depth_size",
     "gtb_pool_finish", "gtb_pool_finish_multi", "gtb_pool_reset_multi", "gtb_submit_reads_multi", "gtb_debug_enable", "gtb_debug_seed_sizes", "gtb_debug_seeds",
-    "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_replay_last",
+    "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_scan_calls", "gtb_merge_varstats", "gtb_replay_last",
     "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators", "gtb_allreduce_accumulators_multi", "gtb_debug_counters",
 ]
 
@@ -68,6 +68,9 @@ def load_library() -> C.CDLL:
     L.gtb_debug_path_sizes.argtypes = [vp, C.c_int, abi.u64p, abi.u64p, abi.u64p, abi.u64p]
     L.gtb_debug_paths.argtypes = [vp, C.c_int, abi.u32p, abi.u32p, abi.u32p, abi.u32p, abi.u32p, abi.u16p]
     L.gtb_calls_from_accumulators.argtypes = [C.POINTER(abi.Accumulators), abi.u8p, abi.u16p, abi.u8p]
+    dp = C.POINTER(C.c_double)
+    L.gtb_scan_calls.argtypes = [C.POINTER(abi.Accumulators), abi.u8p, abi.u64p, abi.u64p, dp]
+    L.gtb_merge_varstats.argtypes = [C.c_uint32, C.c_uint64, abi.u64p, abi.u64p, dp, abi.u64p, abi.u64p, dp]
     L.gtb_replay_last.argtypes = [vp, C.POINTER(abi.SubmitStats)]
     fp = C.POINTER(C.c_float)
     L.gtb_last_timing.argtypes = [vp, fp, fp, fp, fp]
@@ -283,6 +286,16 @@ class Context:
         self._check(self.lib.gtb_calls_from_accumulators(C.byref(acc.view), phred.ctypes.data_as(abi.u8p),
                                                          gt.ctypes.data_as(abi.u16p), gq.ctypes.data_as(abi.u8p)))
         return phred, gt, gq
+
+    def scan_calls(self, acc: abi.HostAccumulators, phred: np.ndarray):
+        """Variant::scan_calls summary of one pool: (var[NB,9], allele[n_cov,13], ratio[n_cov])."""
+        n_cov = int(acc.cov_off[-1])
+        var = np.zeros(acc.n_bubbles * 9, np.uint64)
+        allele = np.zeros(n_cov * 13, np.uint64)
+        ratio = np.zeros(n_cov, np.float64)
+        self._check(self.lib.gtb_scan_calls(C.byref(acc.view), phred.ctypes.data_as(abi.u8p), var.ctypes.data_as(abi.u64p),
+                                            allele.ctypes.data_as(abi.u64p), ratio.ctypes.data_as(C.POINTER(C.c_double))))
+        return var, allele, ratio
 
     # -- multi-GPU
     def nccl_unique_id(self) -> np.ndarray:

@@ -224,6 +224,17 @@ int gtb_host_free(void *p);
 int gtb_nccl_unique_id(uint8_t *id128);
 int gtb_nccl_init(gtb_ctx *ctx, int n_ranks, int rank, const uint8_t *id128);
 
+/* Per-pool variant summary = Variant::scan_calls (src/typer/variant.cpp:230-428) on the calls of one pool, and its
+ * cross-pool merge VarStats::add_stats (src/typer/var_stats.cpp:141-189: sums, except max for maximum_alt_support and
+ * its ratio; n_max_alt_proper_pairs is SUMMED there as a uint8, reproduced).  Layouts (row-major):
+ *   var[b][9]     n_genotyped n_calls n_passed_calls n_max_alt_proper_pairs seqdepth het_ad0 het_ad1 hom_ad0 hom_ad1
+ *   allele[a][13] qd_qual qd_depth total_depth ac pass_ac n_ref_ref n_ref_alt n_alt_alt maximum_alt_support
+ *                 het_multi0 het_multi1 hom_multi0 hom_multi1          (a runs over cov_off[b] + allele)
+ *   ratio[a]      maximum_alt_support_ratio */
+int gtb_scan_calls(const gtb_accumulators *acc, const uint8_t *phred, uint64_t *var, uint64_t *allele, double *ratio);
+int gtb_merge_varstats(uint32_t n_bubbles, uint64_t n_alleles_total, uint64_t *var, uint64_t *allele, double *ratio,
+                       const uint64_t *var_src, const uint64_t *allele_src, const double *ratio_src);
+
 /* Multi-GPU: sum-reduce widened accumulators of a region over an NCCL communicator supplied by the host
  * (ncclComm_t passed as void*; all ranks call; result valid on every rank).  Used when ONE sample's reads
  * are split over GPUs; with sample sharding no collective is needed. */

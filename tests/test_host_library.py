@@ -44,11 +44,18 @@ def test_host_finalisation_matches_reference(pre):
     acc = abi.HostAccumulators(nb, int(ref["score_off"][-1]), int(ref["cov_off"][-1]), ns)
     for k in ("n_alleles", "score_off", "cov_off", "log_score"):
         getattr(acc, k)[:] = ref[k]
+    for k in ("gt_coverage", "ambiguous_depth", "alt_proper_pair_depth"):
+        getattr(acc, k)[:] = ref[k]
     ctx = engine.Context(device=-1)
     ph, gt, gq = ctx.calls(acc)
     assert np.array_equal(ph, pa["call_phred"])
     assert np.array_equal(gt, pa["call_gt"])
     assert np.array_equal(gq, pa["call_gq"])
+    if "ref_depth" not in pa:  # Variant::scan_calls only runs for non-SV graphs (hts_parallel_reader.cpp:1019-1023)
+        var, allele, ratio = ctx.scan_calls(acc, ph)
+        assert np.array_equal(var, pa["stats_var"])
+        assert np.array_equal(allele, pa["stats_allele"])
+        assert np.array_equal(ratio, pa["stats_allele_ratio"])
     ctx.close()
 
 
