@@ -461,6 +461,7 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g)
   size_t const o_uniq = place<IndexSlot>(off, R.index.uniq.size());
   size_t const upload_bytes = align_up(off, 256);
   size_t const o_table = place<IndexSlot>(off, R.index.table_cap); // device only
+  size_t const o_bitmap = place<uint32_t>(off, (size_t)R.index.table_cap * 4 / 32 + 1); // device only, follows the table
   size_t const total = align_up(off, 256);
 
   if (int rc = c->h_stage.reserve(upload_bytes))
@@ -503,9 +504,10 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g)
     return rc;
   uint8_t * d = static_cast<uint8_t *>(R.arena.p);
   CUDA_TRY(cudaMemcpyAsync(d, h, upload_bytes, cudaMemcpyHostToDevice, c->stream));
-  CUDA_TRY(cudaMemsetAsync(d + o_table, 0, (size_t)R.index.table_cap * sizeof(IndexSlot), c->stream));
+  CUDA_TRY(cudaMemsetAsync(d + o_table, 0, total - o_table, c->stream)); // table + bitmap
   launch_build_table(reinterpret_cast<const IndexSlot *>(d + o_uniq), (uint32_t)R.index.uniq.size(),
-                     reinterpret_cast<IndexSlot *>(d + o_table), R.index.table_mask, R.index.table_shift, c->stream);
+                     reinterpret_cast<IndexSlot *>(d + o_table), R.index.table_mask, R.index.table_shift,
+                     reinterpret_cast<uint32_t *>(d + o_bitmap), c->stream);
   CUDA_TRY(cudaStreamSynchronize(c->stream)); // h_stage is reused by the next region
   CUDA_TRY(cudaGetLastError());
 
@@ -536,6 +538,7 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g)
   D.score_off = reinterpret_cast<const uint32_t *>(d + o_score_off);
   D.cov_off = reinterpret_cast<const uint32_t *>(d + o_cov_off);
   D.table = reinterpret_cast<const IndexSlot *>(d + o_table);
+  D.bitmap = reinterpret_cast<const uint32_t *>(d + o_bitmap);
   D.labels = reinterpret_cast<const DevLabel *>(d + o_labels);
   D.depth_size = R.depth_size;
   D.reference_offset = R.reference_offset;

@@ -61,6 +61,7 @@ struct DevRegion
   const uint32_t * cov_off;      // [n_bubbles+1]
   // index
   const IndexSlot * table;
+  const uint32_t * bitmap;       // presence bits, 4 per table slot: bit (hash >> (table_shift - 2))
   const DevLabel * labels;
   // accumulators (widened; clamped on download)
   uint32_t * log_score;     // [score_off[NB] * NS]
@@ -159,7 +160,8 @@ struct LaunchParams
 };
 
 // host launchers (gtb_kernels.cu)
-void launch_build_table(const IndexSlot * uniq, uint32_t n, IndexSlot * table, uint32_t mask, int shift, void * stream);
+void launch_build_table(const IndexSlot * uniq, uint32_t n, IndexSlot * table, uint32_t mask, int shift, uint32_t * bitmap,
+                        void * stream);
 void launch_probe(const LaunchParams & p, void * stream);
 void launch_chain(const LaunchParams & p, void * stream);
 void launch_slow(const LaunchParams & p, void * stream);

@@ -1423,6 +1423,14 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(LaunchParams P)
   int const nslots = 1 + (L - 32) / 31; // get_num_kmers (kmer_help_functions.cpp:10-17)
   int nrefs = 0;
   bool slow = false;
+  // XOR masks of this lane's three Hamming-1 neighbours: key index k = q*32 + lane flips base k/3 by (k%3 + 1)
+  uint64_t nmask[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+  {
+    int const k = q * 32 + lane;
+    nmask[q] = (uint64_t)(k % 3 + 1) << (2 * (k / 3));
+  }
   uint32_t cnts = 0, cnts_hi = 0; // 8 x 8-bit list counts
   for (int i = 0; i < nslots && !slow; ++i)
   {
@@ -1463,25 +1471,28 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(LaunchParams P)
       bool dropped = false;
       // memory-level parallelism: the first table slot of all three neighbour keys of this lane is requested
       // before any of them is examined
-      const uint4 * tab = reinterpret_cast<const uint4 *>(R.table);
+      // A presence bitmap (1 bit per 1/4 table slot, ~3 % occupied, small enough to live in L1/L2) answers the
+      // usual case -- neighbour absent -- with one 4-byte load and no probe loop; the table is only walked for the
+      // few keys whose bit is set.  All three bitmap words of a lane are requested before any is examined.
       uint64_t nk[3];
-      uint32_t nh[3];
-      uint4 ns[3];
+      uint64_t nhs[3];
+      uint32_t nw[3];
 #pragma unroll
       for (int q = 0; q < 3; ++q)
       {
-        int const k = q * 32 + lane;
-        nk[q] = key ^ ((uint64_t)(k % 3 + 1) << (2 * (k / 3)));
-        nh[q] = slot_of(R, nk[q]);
+        nk[q] = key ^ nmask[q];
+        nhs[q] = nk[q] * 0x9E3779B97F4A7C15ull;
       }
 #pragma unroll
       for (int q = 0; q < 3; ++q)
-        ns[q] = __ldg(tab + nh[q]);
+        nw[q] = __ldg(R.bitmap + (uint32_t)(nhs[q] >> (R.table_shift - 2 + 5)));
 #pragma unroll
       for (int q = 0; q < 3; ++q)
       {
         uint32_t off = 0, cnt = 0;
-        bool const found = probe_resolve(R, nk[q], nh[q], ns[q], off, cnt);
+        bool found = false;
+        if ((nw[q] >> ((uint32_t)(nhs[q] >> (R.table_shift - 2)) & 31u)) & 1u)
+          found = probe(R, nk[q], off, cnt);
         unsigned const fm = __ballot_sync(FULL, found);
         if (fm == 0 || dropped)
           continue;
@@ -2222,14 +2233,17 @@ __global__ void __launch_bounds__(128) score_kernel(LaunchParams P)
 // A slot is claimed by CAS on its (offset, count) word -- count == 0 means empty -- then the key is written;
 // lookups only happen in later kernels.
 __global__ void __launch_bounds__(256) build_table_kernel(const IndexSlot * uniq, uint32_t n, IndexSlot * table,
-                                                          uint32_t mask, int shift)
+                                                          uint32_t mask, int shift, uint32_t * bitmap)
 {
   uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
   IndexSlot const u = uniq[i];
   unsigned long long const val = (unsigned long long)u.off | ((unsigned long long)u.cnt << 32);
-  uint32_t h = (uint32_t)((u.key * 0x9E3779B97F4A7C15ull) >> shift);
+  uint64_t const hs = u.key * 0x9E3779B97F4A7C15ull;
+  uint32_t const bi = (uint32_t)(hs >> (shift - 2)); // presence bitmap: 4 bits per table slot
+  atomicOr(&bitmap[bi >> 5], 1u << (bi & 31u));
+  uint32_t h = (uint32_t)(hs >> shift);
   while (true)
   {
     unsigned long long * w = reinterpret_cast<unsigned long long *>(&table[h]) + 1;
@@ -2242,11 +2256,12 @@ __global__ void __launch_bounds__(256) build_table_kernel(const IndexSlot * uniq
   }
 }
 
-void launch_build_table(const IndexSlot * uniq, uint32_t n, IndexSlot * table, uint32_t mask, int shift, void * stream)
+void launch_build_table(const IndexSlot * uniq, uint32_t n, IndexSlot * table, uint32_t mask, int shift, uint32_t * bitmap,
+                        void * stream)
 {
   if (n == 0)
     return;
-  build_table_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(uniq, n, table, mask, shift);
+  build_table_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(uniq, n, table, mask, shift, bitmap);
 }
 
 // ================================================================================================ launchers
