@@ -26,7 +26,7 @@ constexpr int SEED_INLINE = 10;     // index bucket references handed from probe
 constexpr int SEED_REC_BYTES = 16 + 8 * SEED_INLINE;
 constexpr int PROBE_WARPS = 8;      // warps per block of probe_kernel
 constexpr int CHAIN_THREADS = 128;  // threads per block of chain_kernel
-constexpr int CHAIN_MIN_BLOCKS = 12; // -> <= 40 registers: all ~2e5 tasks of the bench workload resident in ONE wave
+constexpr int CHAIN_MIN_BLOCKS = 8;  // <= 64 registers per thread
 constexpr int MAX_TOUCH = 16; // bubbles touched by one read in the accumulate kernel
 using allele_mask_t = uint32_t; // allele set of one bubble on a path: bit a = allele a  (<= 32 alleles per bubble)
 constexpr int MAX_ALLELES = 32;

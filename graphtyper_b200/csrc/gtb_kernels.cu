@@ -102,6 +102,7 @@ struct SlowState : StateT<MAXP, MAXV, CAND_CAP, CAND_V, WL_CAP, MAXLOC>
   uint8_t seq[MAX_SEQ + 8]; // 4-bit codes in phase A, IUPAC characters afterwards
   Cand * cand_spill;        // this warp's global-memory extension of cands[] (CAND_SPILL entries)
   __device__ __forceinline__ uint8_t rd(int j) const { return seq[j]; }
+  __device__ __forceinline__ void prepare(int, int) {} // the whole read is already decoded in seq[]
   // candidate i of the bubble expansion: the first CAND_CAP live in shared memory, the (rare) rest in a per-warp
   // global scratch area, so that the reference's limit of 128 open candidates (+ one round of growth) fits
   __device__ __forceinline__ Cand & cand_at(int i) { return i < CAND_CAP ? cands[i] : cand_spill[i - CAND_CAP]; }
@@ -112,15 +113,21 @@ struct FastState : StateT<FAST_P, FAST_V, FAST_C, FAST_CV, FAST_WL, FAST_LOC>
   static constexpr int CAND_TOTAL = FAST_C;
   const uint8_t * s4; // packed 4-bit read
   int L, orient;
-  __device__ __forceinline__ uint8_t rd(int j) const
+  uint8_t buf[MAX_SEQ]; // IUPAC characters of the read window the current walk compares against
+  // decodes read bases [from, to) once; the comparison loops of a walk touch the same ~26-base tail several times
+  __device__ void prepare(int from, int to)
   {
-    int const src = orient ? (L - 1 - j) : j;
-    uint8_t const b = __ldg(s4 + (src >> 1));
-    uint8_t c = (src & 1) ? (b & 15) : (b >> 4);
-    if (orient)
-      c = comp4(c);
-    return iupac_char(c);
+    for (int j = from; j < to; ++j)
+    {
+      int const src = orient ? (L - 1 - j) : j;
+      uint8_t const b = __ldg(s4 + (src >> 1));
+      uint8_t c = (src & 1) ? (b & 15) : (b >> 4);
+      if (orient)
+        c = comp4(c);
+      buf[j] = iupac_char(c);
+    }
   }
+  __device__ __forceinline__ uint8_t rd(int j) const { return buf[j]; }
   __device__ __forceinline__ Cand & cand_at(int i) { return cands[i]; }
 };
 
@@ -1040,6 +1047,21 @@ __device__ void walk(W & S, const GR & g, uint32_t L, bool forward)
   if (S.npaths == 0 || psize(S.paths[0]) == L)
     return;
   // MAX_SEED_NUMBER_FOR_WALKING (256) / _ALLOWING_MISMATCHES (64) can never be reached with MAXP paths
+  {
+    // read window this walk can touch: [min read_end_index, L) forwards, [0, max read_start_index] backwards
+    int from = (int)L, to = 0;
+    for (int pi = 0; pi < S.npaths; ++pi)
+    {
+      if (forward && S.paths[pi].re != L - 1)
+        from = min(from, (int)S.paths[pi].re);
+      if (!forward && S.paths[pi].rs != 0)
+        to = max(to, (int)S.paths[pi].rs + 1);
+    }
+    if (forward)
+      S.prepare(from, (int)L);
+    else
+      S.prepare(0, to);
+  }
   uint32_t best_mm = 7;
   int nlists = 0;
   int committed = 0;

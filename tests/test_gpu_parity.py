@@ -147,3 +147,67 @@ def test_pinned_inputs_take_the_direct_dma_path_with_equal_results(ctx):
     finally:
         ctx.region_end(11)
         arena.close()
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def _plain_graph(length=400, seed=3):
+    """A region without any variant: a single ref node."""
+    from graphtyper_b200 import graph_build, synth
+    ref = synth.make_reference(length, seed)
+    return ref, graph_build.build_region_graph(ref, [], 1, length, pad=0)
+
+
+def _batch_from_seqs(seqs, flags, mates=None, lens=None):
+    n = len(seqs)
+    L = max(len(s) for s in seqs) if n else 0
+    arr = np.full((n, max(L, 1)), ord("A"), np.uint8)
+    for i, s in enumerate(seqs):
+        arr[i, :len(s)] = np.frombuffer(s, np.uint8)
+    seq4 = abi.pack_seq4(arr) if n else np.zeros((0, abi.SEQ_STRIDE), np.uint8)
+    lseq = np.array([len(s) for s in seqs] if lens is None else lens, np.uint16)
+    mate = np.full(n, -1, np.int32) if mates is None else np.array(mates, np.int32)
+    return abi.HostBatch(seq4, lseq, np.array(flags, np.uint16), np.full(n, 60, np.uint8), np.zeros(n, np.int32),
+                         np.ones(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.int32),
+                         mate, np.full(n, -1, np.int32))
+
+
+def test_empty_batch_and_variant_free_graph(ctx, oracle_lib):
+    ref, g = _plain_graph()
+    ctx.region_begin(21, g)
+    try:
+        ctx.pool_begin(21, 1)
+        st = ctx.submit(21, _batch_from_seqs([], []))
+        assert st.n_records == 0 and st.kernel_launches == 0
+        # ragged lengths incl. reads below the 63-bp limit and at the 151/152 maximum; no bubbles -> nothing to score
+        seqs = [bytes(ref[10:10 + n]) for n in (40, 62, 63, 100, 151, 152)]
+        st = ctx.submit(21, _batch_from_seqs(seqs, [0] * len(seqs)))
+        assert st.n_records == 6 and st.n_oriented == 4 and st.n_capacity_overflow == 0
+        ctx.debug_enable(True)
+        ctx.submit(21, _batch_from_seqs(seqs, [0] * len(seqs)))
+        paths = ctx.debug_paths(21)
+        ctx.debug_enable(False)
+        assert paths["gp_npaths"].tolist() == [0, 0, 0, 0, 1, 0, 1, 0, 1, 0, 1, 0]
+        assert paths["gp_longest"][4::2].tolist() == [63, 100, 151, 152]
+        acc = ctx.pool_finish(21)
+        assert acc.n_bubbles == 0 and len(acc.log_score) == 0
+    finally:
+        ctx.region_end(21)
+
+
+def test_input_errors_are_reported(ctx):
+    ref, g = _plain_graph()
+    ctx.region_begin(22, g)
+    try:
+        ctx.pool_begin(22, 1)
+        s = bytes(ref[20:170])
+        with pytest.raises(engine.GtbError) as e:  # both mates first-in-pair: the reference exits (hts_parallel_reader.cpp:306)
+            ctx.submit(22, _batch_from_seqs([s, s], [65, 65], mates=[-1, 0]))
+        assert e.value.code == -5
+        with pytest.raises(engine.GtbError) as e:  # longer than the 152-base device limit
+            ctx.submit(22, _batch_from_seqs([s], [0], lens=[153]))
+        assert e.value.code == -4
+        with pytest.raises(engine.GtbError) as e:  # forward mate reference
+            ctx.submit(22, _batch_from_seqs([s, s], [65, 129], mates=[1, -1]))
+        assert e.value.code == -1
+    finally:
+        ctx.region_end(22)
