@@ -14,6 +14,7 @@
 #include <thread>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -1117,10 +1118,18 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   // ---- chunking: host staging of chunk k+1 overlaps the H2D copy and the kernels of chunk k.
   //      Region boundaries are natural cut points (mate / duplicate links never cross regions).
   int n_chunks = 1;
-  // (measured on B200/PCIe5: below a few million records chunking costs more in small-kernel inefficiency than
-  //  the overlap wins, so it only engages for very large submits)
-  if (!c->debug && n >= 2 && total >= 4000000)
-    n_chunks = std::min(n, MAX_CHUNKS);
+  if (!c->debug && n >= 2)
+  {
+    // Chunks on two streams hide the H2D copy behind the previous chunk's kernels.  Measured on B200/PCIe5 with the
+    // 2e5-record step: 1 chunk 2.32 ms, 2 chunks 2.21 ms, 3 chunks 2.46 ms end to end (tools/chunk_sweep.sh) -- the split
+    // kernels lose what the overlap wins, so chunking only engages for multi-million-record submits.
+    // GTB_CHUNKS overrides (1..4).
+    static int const forced = []() { const char * e = getenv("GTB_CHUNKS"); return e ? atoi(e) : 0; }();
+    if (forced > 0)
+      n_chunks = std::min({n, MAX_CHUNKS, forced});
+    else if (total >= 4000000)
+      n_chunks = std::min(n, MAX_CHUNKS);
+  }
   std::vector<int> cut(n_chunks + 1, n);
   cut[0] = 0;
   {
