@@ -169,6 +169,7 @@ struct Ctx
   PinnedBuffer h_stage, h_accum;
   bool have_last = false;
   bool debug = false;
+  int forced_chunks = 0; // gtb_set_chunks / GTB_CHUNKS: 0 = automatic
   float t_h2d = 0, t_align = 0, t_score = 0, t_d2h = 0, t_probe = 0, t_chain = 0, t_slow = 0;
   unsigned long long last_n_slow = 0;
   // nccl (loaded lazily with dlopen, see gtb_nccl.cpp part below)
@@ -1124,7 +1125,8 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
     // 2e5-record step: 1 chunk 2.32 ms, 2 chunks 2.21 ms, 3 chunks 2.46 ms end to end (tools/chunk_sweep.sh) -- the split
     // kernels lose what the overlap wins, so chunking only engages for multi-million-record submits.
     // GTB_CHUNKS overrides (1..4).
-    static int const forced = []() { const char * e = getenv("GTB_CHUNKS"); return e ? atoi(e) : 0; }();
+    static int const env_forced = []() { const char * e = getenv("GTB_CHUNKS"); return e ? atoi(e) : 0; }();
+    int const forced = c->forced_chunks > 0 ? c->forced_chunks : env_forced;
     if (forced > 0)
       n_chunks = std::min({n, MAX_CHUNKS, forced});
     else if (total >= 4000000)
@@ -1224,6 +1226,16 @@ int gtb_debug_counters(gtb_ctx * ctx, uint64_t * out24)
     out24[q] = k->fast_reasons[q];
     out24[12 + q] = k->reasons[q];
   }
+  return 0;
+}
+
+// Forces the number of pipeline chunks of gtb_submit_reads_multi (1..4; 0 = automatic).
+int gtb_set_chunks(gtb_ctx * ctx, int n_chunks)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || n_chunks < 0 || n_chunks > MAX_CHUNKS)
+    return fail(GTB_ERR_ARG, "n_chunks must be 0..4");
+  c->forced_chunks = n_chunks;
   return 0;
 }
 

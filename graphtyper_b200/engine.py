@@ -22,7 +22,7 @@ EXPORTS = [
     "gtb_index_size", "gtb_index_export", "gtb_pool_begin", "gtb_submit_reads", "gtb_accumulator_sizes", "gtb_ref_depth_size",
     "gtb_pool_finish", "gtb_pool_finish_multi", "gtb_pool_reset_multi", "gtb_submit_reads_multi", "gtb_debug_enable", "gtb_debug_seed_sizes", "gtb_debug_seeds",
     "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_scan_calls", "gtb_merge_varstats", "gtb_replay_last",
-    "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators", "gtb_allreduce_accumulators_multi", "gtb_debug_counters",
+    "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_set_chunks", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators", "gtb_allreduce_accumulators_multi", "gtb_debug_counters",
 ]
 
 
@@ -76,6 +76,7 @@ def load_library() -> C.CDLL:
     L.gtb_last_timing.argtypes = [vp, fp, fp, fp, fp]
     L.gtb_last_kernel_timing.argtypes = [vp, fp, fp, fp, fp, abi.u64p]
     L.gtb_pool_reset.argtypes = [vp, C.c_int]
+    L.gtb_set_chunks.argtypes = [vp, C.c_int]
     L.gtb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.gtb_host_free.argtypes = [vp]
     L.gtb_nccl_unique_id.argtypes = [abi.u8p]
@@ -188,6 +189,9 @@ class Context:
     def pool_begin(self, region_id: int, n_samples: int) -> None:
         self._check(self.lib.gtb_pool_begin(self.h, region_id, n_samples))
         self._samples[region_id] = n_samples
+
+    def set_chunks(self, n: int) -> None:
+        self._check(self.lib.gtb_set_chunks(self.h, n))
 
     def pool_reset(self, region_id: int) -> None:
         self._check(self.lib.gtb_pool_reset(self.h, region_id))

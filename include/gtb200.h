@@ -213,6 +213,8 @@ int gtb_last_timing(gtb_ctx *ctx, float *h2d_ms, float *align_ms, float *score_m
 int gtb_last_kernel_timing(gtb_ctx *ctx, float *probe_ms, float *chain_ms, float *slow_ms, float *score_ms,
                            uint64_t *n_slow);
 int gtb_pool_reset(gtb_ctx *ctx, int region_id);
+/* Pipeline chunks of gtb_submit_reads_multi: staging of chunk k+1 overlaps copy + kernels of chunk k (0 = automatic). */
+int gtb_set_chunks(gtb_ctx *ctx, int n_chunks);
 /* Page-locked host memory: batch columns (seq4 above all) placed here are DMA-ed without a staging copy. */
 int gtb_host_alloc(size_t bytes, void **out);
 /* Diagnostics: out24[0..11] why chain_kernel re-queued tasks for slow_kernel, out24[12..23] slow_kernel overflows. */

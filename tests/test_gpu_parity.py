@@ -75,6 +75,37 @@ def test_region_batched_submit_equals_separate(ctx):
             ctx.region_end(100 + k)
 
 
+@pytest.mark.parametrize("n_chunks", [2, 3, 4])
+def test_chunked_pipeline_equals_golden(ctx, n_chunks):
+    """The double-buffered chunk pipeline (copy stream + compute stream) gives the same accumulators."""
+    pres = [p for p in ALL if "sv" not in os.path.basename(p)][:5]
+    graphs, batches, ns = [], [], []
+    ids = list(range(300, 300 + len(pres)))
+    for k, pre in zip(ids, pres):
+        graphs.append(abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba")))
+        rd = gtba.load(pre + ".reads.gtba")
+        batches.append(abi.batch_from_probe(rd))
+        ns.append(n_samples_of(rd))
+    ctx.region_begin_multi(ids, graphs)
+    try:
+        for k, n in zip(ids, ns):
+            ctx.pool_begin(k, n)
+        ctx.set_chunks(n_chunks)
+        st = ctx.submit_multi(ids, batches)
+        assert st.n_records == sum(len(b) for b in batches)
+        accs = ctx.pool_finish_multi(ids)
+        for pre, acc in zip(pres, accs):
+            compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), acc.as_dict(), f"chunks={n_chunks}")
+        # replaying a chunked batch doubles the sums
+        ctx.replay()
+        a2 = ctx.pool_finish(ids[0]).as_dict()
+        assert np.array_equal(a2["read_strand"].astype(np.int64), 2 * accs[0].as_dict()["read_strand"].astype(np.int64))
+    finally:
+        ctx.set_chunks(0)
+        for k in ids:
+            ctx.region_end(k)
+
+
 def test_replay_accumulates_linearly(ctx):
     """Size-independent property: accumulators are additive -- replaying the resident batch doubles every sum."""
     pre = ALL[0]
