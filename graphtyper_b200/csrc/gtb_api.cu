@@ -176,6 +176,13 @@ struct Ctx
   void * nccl_lib = nullptr;
   void * nccl_comm = nullptr;
   int nccl_rank = 0, nccl_size = 1;
+  // discovery re-alignment (gtb_sw_align_batch)
+  DeviceBuffer d_sw_in, d_sw_out, d_sw_bt;
+  PinnedBuffer h_sw;
+  SwParams sw_last{};
+  int sw_warps = 0;
+  cudaEvent_t sw_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float t_sw_kernel = 0, t_sw_h2d = 0, t_sw_d2h = 0;
 };
 
 // Region arenas are recycled: cudaMalloc / cudaFree of ~10 MB blocks per region would otherwise dominate (and add
@@ -430,6 +437,13 @@ void gtb_destroy(gtb_ctx * ctx)
     c->d_spill.release();
     c->h_stage.release();
     c->h_accum.release();
+    c->d_sw_in.release();
+    c->d_sw_out.release();
+    c->d_sw_bt.release();
+    c->h_sw.release();
+    for (auto & e : c->sw_ev)
+      if (e)
+        cudaEventDestroy(e);
     if (c->copy_stream)
       cudaStreamDestroy(c->copy_stream);
     if (c->stream)
@@ -1964,6 +1978,110 @@ int gtb_allreduce_accumulators_multi(gtb_ctx * ctx, int n, const int * region_id
 int gtb_allreduce_accumulators(gtb_ctx * ctx, int region_id, void * nccl_comm)
 {
   return gtb_allreduce_accumulators_multi(ctx, 1, &region_id, nccl_comm);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Discovery re-alignment: batch of (read, haplotype window) pairs through sw_kernel (gtb_sw.cu).
+int gtb_sw_align_batch(gtb_ctx * ctx, int n_pairs, const uint8_t * query, const int32_t * q_off,
+                       const uint8_t * database, const int32_t * d_off, gtb_sw_result * out)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || n_pairs < 0 || (n_pairs > 0 && (!query || !q_off || !database || !d_off || !out)))
+    return fail(GTB_ERR_ARG, "gtb_sw_align_batch: null argument");
+  if (n_pairs == 0)
+    return 0;
+  int max_db = 0;
+  for (int k = 0; k < n_pairs; ++k)
+  {
+    int const m = q_off[k + 1] - q_off[k], n = d_off[k + 1] - d_off[k];
+    if (m < 1 || m > GTB_SW_MAX_QUERY)
+      return fail(GTB_ERR_ARG, "gtb_sw_align_batch: query length must be 1.." + std::to_string(GTB_SW_MAX_QUERY));
+    if (n < 1 || n > GTB_SW_MAX_DATABASE)
+      return fail(GTB_ERR_ARG, "gtb_sw_align_batch: database length must be 1.." + std::to_string(GTB_SW_MAX_DATABASE));
+    max_db = std::max(max_db, n);
+  }
+  if (q_off[0] != 0 || d_off[0] != 0)
+    return fail(GTB_ERR_ARG, "gtb_sw_align_batch: offsets must start at 0");
+  cudaSetDevice(c->device);
+  for (auto & e : c->sw_ev)
+    if (!e)
+      CUDA_TRY(cudaEventCreate(&e));
+  if (!c->sw_warps)
+    c->sw_warps = sw_resident_warps();
+  size_t const qb = (size_t)q_off[n_pairs], db = (size_t)d_off[n_pairs], ob = (size_t)(n_pairs + 1) * 4;
+  size_t const o_q = 0, o_d = align_up(o_q + qb), o_qo = align_up(o_d + db), o_do = align_up(o_qo + ob);
+  size_t const in_bytes = align_up(o_do + ob);
+  max_db = (max_db + 63) / 64 * 64;
+  if (int rc = c->d_sw_in.reserve(in_bytes))
+    return rc;
+  if (int rc = c->d_sw_out.reserve((size_t)n_pairs * sizeof(gtb_sw_result)))
+    return rc;
+  if (int rc = c->d_sw_bt.reserve((size_t)c->sw_warps * (size_t)max_db * 128))
+    return rc;
+  size_t const out_bytes = (size_t)n_pairs * sizeof(gtb_sw_result);
+  if (int rc = c->h_sw.reserve(std::max(in_bytes, out_bytes)))
+    return rc;
+  uint8_t * h = static_cast<uint8_t *>(c->h_sw.p);
+  memcpy(h + o_q, query, qb);
+  memcpy(h + o_d, database, db);
+  memcpy(h + o_qo, q_off, ob);
+  memcpy(h + o_do, d_off, ob);
+  uint8_t * dv = static_cast<uint8_t *>(c->d_sw_in.p);
+  CUDA_TRY(cudaEventRecord(c->sw_ev[0], c->stream));
+  CUDA_TRY(cudaMemcpyAsync(dv, h, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaEventRecord(c->sw_ev[1], c->stream));
+  SwParams P{};
+  P.n_pairs = n_pairs;
+  P.max_db = max_db;
+  P.q = dv + o_q;
+  P.d = dv + o_d;
+  P.q_off = reinterpret_cast<const int32_t *>(dv + o_qo);
+  P.d_off = reinterpret_cast<const int32_t *>(dv + o_do);
+  P.out = static_cast<gtb_sw_result *>(c->d_sw_out.p);
+  P.bt = static_cast<uint32_t *>(c->d_sw_bt.p);
+  launch_sw(P, c->sw_warps, c->stream);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(c->sw_ev[2], c->stream));
+  // the input staging area is reused for the results once the H2D copy has been consumed (same stream => ordered)
+  CUDA_TRY(cudaMemcpyAsync(h, c->d_sw_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaEventRecord(c->sw_ev[3], c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  memcpy(out, h, out_bytes);
+  cudaEventElapsedTime(&c->t_sw_h2d, c->sw_ev[0], c->sw_ev[1]);
+  cudaEventElapsedTime(&c->t_sw_kernel, c->sw_ev[1], c->sw_ev[2]);
+  cudaEventElapsedTime(&c->t_sw_d2h, c->sw_ev[2], c->sw_ev[3]);
+  c->sw_last = P;
+  return 0;
+}
+
+int gtb_sw_replay_last(gtb_ctx * ctx)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || c->sw_last.n_pairs <= 0)
+    return fail(GTB_ERR_STATE, "gtb_sw_replay_last: no previous gtb_sw_align_batch");
+  cudaSetDevice(c->device);
+  CUDA_TRY(cudaEventRecord(c->sw_ev[1], c->stream));
+  launch_sw(c->sw_last, c->sw_warps, c->stream);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(c->sw_ev[2], c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->t_sw_kernel, c->sw_ev[1], c->sw_ev[2]);
+  return 0;
+}
+
+int gtb_sw_last_timing(gtb_ctx * ctx, float * kernel_ms, float * h2d_ms, float * d2h_ms)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c)
+    return fail(GTB_ERR_ARG, "null ctx");
+  if (kernel_ms)
+    *kernel_ms = c->t_sw_kernel;
+  if (h2d_ms)
+    *h2d_ms = c->t_sw_h2d;
+  if (d2h_ms)
+    *d2h_ms = c->t_sw_d2h;
+  return 0;
 }
 
 } // extern "C"

@@ -169,4 +169,19 @@ void launch_score(const LaunchParams & p, void * stream);
 int align_kernel_blocks_per_sm();
 size_t align_spill_bytes();
 
+// discovery re-alignment (gtb_sw.cu)
+struct SwParams
+{
+  int n_pairs;
+  int max_db;               // rows of backtrack scratch per warp
+  const uint8_t * q;
+  const int32_t * q_off;    // [n_pairs + 1]
+  const uint8_t * d;
+  const int32_t * d_off;    // [n_pairs + 1]
+  gtb_sw_result * out;
+  uint32_t * bt;            // [resident warps][max_db][32]
+};
+int sw_resident_warps();
+void launch_sw(const SwParams & p, int resident_warps, void * stream);
+
 } // namespace gtb

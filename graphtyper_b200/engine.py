@@ -23,6 +23,7 @@ EXPORTS = [
     "gtb_pool_finish", "gtb_pool_finish_multi", "gtb_pool_reset_multi", "gtb_submit_reads_multi", "gtb_debug_enable", "gtb_debug_seed_sizes", "gtb_debug_seeds",
     "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_scan_calls", "gtb_merge_varstats", "gtb_replay_last",
     "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_set_chunks", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators", "gtb_allreduce_accumulators_multi", "gtb_debug_counters",
+    "gtb_sw_align_batch", "gtb_sw_last_timing", "gtb_sw_replay_last",
 ]
 
 
@@ -84,6 +85,9 @@ def load_library() -> C.CDLL:
     L.gtb_allreduce_accumulators.argtypes = [vp, C.c_int, vp]
     L.gtb_allreduce_accumulators_multi.argtypes = [vp, C.c_int, abi.i32p, vp]
     L.gtb_debug_counters.argtypes = [vp, abi.u64p]
+    L.gtb_sw_align_batch.argtypes = [vp, C.c_int, abi.u8p, abi.i32p, abi.u8p, abi.i32p, C.c_void_p]
+    L.gtb_sw_last_timing.argtypes = [vp, fp, fp, fp]
+    L.gtb_sw_replay_last.argtypes = [vp]
     _lib = L
     return L
 
@@ -318,3 +322,41 @@ class Context:
         n = len(region_ids)
         ids = (C.c_int32 * n)(*region_ids)
         self._check(self.lib.gtb_allreduce_accumulators_multi(self.h, n, ids, None))
+
+    # -- discovery re-alignment
+    def sw_align(self, queries: Sequence[bytes], databases: Sequence[bytes]) -> np.ndarray:
+        """paw::pairwise_alignment + clipping of each (read, haplotype window) pair as realign_to_indels configures it
+        (src/typer/caller.cpp:1864-1870,2007).  Returns int32 [n, 5]: score, database_begin, database_end, clip_begin,
+        clip_end."""
+        q, q_off = pack_sequences(queries)
+        d, d_off = pack_sequences(databases)
+        return self.sw_align_packed(q, q_off, d, d_off)
+
+    def sw_align_packed(self, q: np.ndarray, q_off: np.ndarray, d: np.ndarray, d_off: np.ndarray) -> np.ndarray:
+        n = len(q_off) - 1
+        if len(d_off) - 1 != n:
+            raise ValueError("queries and databases differ in number")
+        out = np.zeros((n, 5), np.int32)
+        self._check(self.lib.gtb_sw_align_batch(self.h, n, q.ctypes.data_as(abi.u8p), q_off.ctypes.data_as(abi.i32p),
+                                                d.ctypes.data_as(abi.u8p), d_off.ctypes.data_as(abi.i32p),
+                                                out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def sw_replay(self) -> None:
+        self._check(self.lib.gtb_sw_replay_last(self.h))
+
+    def sw_last_timing(self) -> Dict[str, float]:
+        k, h, d = C.c_float(), C.c_float(), C.c_float()
+        self._check(self.lib.gtb_sw_last_timing(self.h, C.byref(k), C.byref(h), C.byref(d)))
+        return {"kernel_ms": k.value, "h2d_ms": h.value, "d2h_ms": d.value}
+
+
+def pack_sequences(seqs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    """Concatenates byte strings: (uint8 bases, int32 offsets[n+1])."""
+    off = np.zeros(len(seqs) + 1, np.int32)
+    if len(seqs):
+        np.cumsum([len(s) for s in seqs], out=off[1:])
+    buf = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy() if len(seqs) else np.zeros(0, np.uint8)
+    if buf.size == 0:
+        buf = np.zeros(1, np.uint8)
+    return buf, off

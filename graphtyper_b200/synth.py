@@ -439,3 +439,63 @@ def write_sv_vcf(path: str, sites: List[Site], contig: str = "chr1", contig_len:
             else:
                 info = f"SVTYPE=DUP;SVSIZE={size};SVLEN={size};END={s.pos + size}"
             f.write(f"{contig}\t{s.pos}\t.\t{ref_base}\t<{typ}>\t.\t.\t{info}\n")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# (read, haplotype window) pairs for the discovery re-alignment kernel (gtb_sw_align_batch)
+_ACGT = np.frombuffer(b"ACGT", np.uint8)
+
+
+def make_sw_pairs(n_pairs: int, seed: int = 1, min_db: int = 60, max_db: int = 520, max_query: int = 151,
+                  lowercase_rate: float = 0.03) -> Tuple[List[bytes], List[bytes]]:
+    """Seeded read/window pairs shaped like realign_to_indels' input (src/typer/caller.cpp:1930-2007: a read against
+    reference window +- 50..100 bp with one indel haplotype spliced in): the read is a fragment of the window with
+    substitutions, small indels, occasional N, overhangs past either window end (exercises clipping) and random
+    tails; windows sometimes hold N runs or lower-case bases."""
+    rng = np.random.default_rng(seed)
+
+    def mutate(s: bytes) -> bytes:
+        out = bytearray()
+        psub = rng.choice([0.0, 0.01, 0.03, 0.1])
+        pins = rng.choice([0, 0.003, 0.02])
+        pdel = rng.choice([0, 0.003, 0.02])
+        i = 0
+        while i < len(s):
+            r = rng.random()
+            if r < pdel:
+                i += int(rng.integers(1, 8))
+                continue
+            if r < pdel + pins:
+                out += bytes(_ACGT[rng.integers(0, 4, size=int(rng.integers(1, 8)))])
+            c = s[i]
+            if rng.random() < psub:
+                c = int(_ACGT[rng.integers(0, 4)])
+            if rng.random() < 0.002:
+                c = ord("N")
+            out.append(c)
+            i += 1
+        return bytes(out)
+
+    queries: List[bytes] = []
+    windows: List[bytes] = []
+    for _ in range(n_pairs):
+        n = int(rng.integers(min_db, max_db))
+        d = bytes(_ACGT[rng.integers(0, 4, size=n)])
+        length = int(rng.integers(20, max_query + 1))
+        st = int(rng.integers(-30, n - 10))
+        frag = d[max(st, 0):max(st, 0) + length]
+        if st < 0:
+            frag = bytes(_ACGT[rng.integers(0, 4, size=-st)]) + frag
+        if rng.random() < 0.2:
+            frag = frag + bytes(_ACGT[rng.integers(0, 4, size=int(rng.integers(1, 40)))])
+        q = mutate(frag)[:max_query]
+        if len(q) < 5:
+            q = frag[:20] + b"ACGTA"
+        if rng.random() < 0.05:
+            d = d[:n // 2] + b"N" * int(rng.integers(1, 5)) + d[n // 2:]
+        if rng.random() < lowercase_rate:
+            a = int(rng.integers(0, len(d)))
+            d = d[:a] + d[a:a + 20].lower() + d[a + 20:]
+        queries.append(q)
+        windows.append(d)
+    return queries, windows

@@ -244,6 +244,30 @@ int gtb_allreduce_accumulators(gtb_ctx *ctx, int region_id, void *nccl_comm);
 /* Several regions in ONE NCCL group and one stream synchronisation. */
 int gtb_allreduce_accumulators_multi(gtb_ctx *ctx, int n, const int *region_ids, void *nccl_comm);
 
+/* Discovery re-alignment.  Replaces paw::pairwise_alignment(read, haplotype window, opts)
+ * + AlignmentResults::get_database_begin_end + apply_clipping as realign_to_indels calls them
+ * (src/typer/caller.cpp:1864-1870 options, :2007 the call; paw/include/paw/align/pairwise_alignment.hpp:146-388):
+ * query global, database ends free, match 1 / mismatch 4 / gap open 7 / extend 1, clip 5.
+ * Pair k aligns query[q_off[k]..q_off[k+1]) (<= GTB_SW_MAX_QUERY bases, raw ASCII) against
+ * database[d_off[k]..d_off[k+1]) (<= GTB_SW_MAX_DATABASE).  Results are identical to paw's
+ * AlignmentResults::{score, database_begin, database_end, clip_begin, clip_end}. */
+#define GTB_SW_MAX_QUERY 160
+#define GTB_SW_MAX_DATABASE 2048
+typedef struct gtb_sw_result
+{
+  int32_t score;          /* after clipping (alignment_results.hpp:451-669) */
+  int32_t database_begin; /* alignment_results.hpp:392-447 */
+  int32_t database_end;
+  int32_t clip_begin;     /* query bases [clip_begin, clip_end) are kept */
+  int32_t clip_end;
+} gtb_sw_result;
+int gtb_sw_align_batch(gtb_ctx *ctx, int n_pairs, const uint8_t *query, const int32_t *q_off, const uint8_t *database,
+                       const int32_t *d_off, gtb_sw_result *out);
+/* Device time (ms, CUDA events) of the last gtb_sw_align_batch kernel, and of its copies. */
+int gtb_sw_last_timing(gtb_ctx *ctx, float *kernel_ms, float *h2d_ms, float *d2h_ms);
+/* Bench helper: re-runs the kernel of the last gtb_sw_align_batch on its device-resident inputs. */
+int gtb_sw_replay_last(gtb_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

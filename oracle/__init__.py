@@ -32,6 +32,18 @@ def build_oracle(force: bool = False) -> str:
     return LIB
 
 
+PAW_LIB = os.path.join(BUILD, "libpaw_oracle.so")
+
+
+def build_paw_oracle(force: bool = False) -> str:
+    src = os.path.join(HERE, "paw_oracle.cpp")
+    if not force and os.path.exists(PAW_LIB) and os.path.getmtime(PAW_LIB) >= os.path.getmtime(src):
+        return PAW_LIB
+    os.makedirs(BUILD, exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", PAW_LIB, src], check=True)
+    return PAW_LIB
+
+
 def build_reference(jobs: int = 8) -> Optional[str]:
     """Compiles the reference into oracle/_ref (only possible where /root/reference exists)."""
     if not os.path.isdir("/root/reference/src"):
@@ -151,3 +163,41 @@ class Oracle:
         self.lib.gto_calls_from_accumulators(C.byref(acc.view), phred.ctypes.data_as(a.u8p), gt.ctypes.data_as(a.u16p),
                                              gq.ctypes.data_as(a.u8p))
         return phred, gt, gq
+
+
+class PawOracle:
+    """Scalar restatement of paw::pairwise_alignment + clipping (oracle/paw_oracle.cpp)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(build_paw_oracle())
+        self.lib.gto_sw_align_batch.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.c_char_p,
+                                                C.POINTER(C.c_int32), C.c_void_p]
+
+    def align(self, queries, windows) -> np.ndarray:
+        """int32 [n, 5]: score, database_begin, database_end, clip_begin, clip_end."""
+        n = len(queries)
+        q_off = np.zeros(n + 1, np.int32)
+        d_off = np.zeros(n + 1, np.int32)
+        if n:
+            np.cumsum([len(q) for q in queries], out=q_off[1:])
+            np.cumsum([len(d) for d in windows], out=d_off[1:])
+        out = np.zeros((n, 5), np.int32)
+        self.lib.gto_sw_align_batch(n, b"".join(queries), q_off.ctypes.data_as(C.POINTER(C.c_int32)), b"".join(windows),
+                                    d_off.ctypes.data_as(C.POINTER(C.c_int32)), out.ctypes.data_as(C.c_void_p))
+        return out
+
+
+def paw_reference(queries, windows) -> Optional[np.ndarray]:
+    """The compiled, unmodified paw (oracle/_ref/bin/paw_probe) on the same pairs; None when it is not built."""
+    exe = ref_binary("paw_probe")
+    if exe is None:
+        return None
+    import tempfile
+    with tempfile.NamedTemporaryFile("wb", suffix=".tsv", delete=False) as f:
+        f.write(b"".join(q + b"\t" + d + b"\n" for q, d in zip(queries, windows)))
+        path = f.name
+    try:
+        txt = subprocess.run([exe, path], check=True, capture_output=True, text=True).stdout
+    finally:
+        os.unlink(path)
+    return np.array([[int(x) for x in line.split()] for line in txt.strip().split("\n")], np.int32).reshape(-1, 5)
