@@ -2007,17 +2007,16 @@ int gtb_sw_align_batch(gtb_ctx * ctx, int n_pairs, const uint8_t * query, const 
   for (auto & e : c->sw_ev)
     if (!e)
       CUDA_TRY(cudaEventCreate(&e));
-  if (!c->sw_warps)
-    c->sw_warps = sw_resident_warps();
   size_t const qb = (size_t)q_off[n_pairs], db = (size_t)d_off[n_pairs], ob = (size_t)(n_pairs + 1) * 4;
   size_t const o_q = 0, o_d = align_up(o_q + qb), o_qo = align_up(o_d + db), o_do = align_up(o_qo + ob);
   size_t const in_bytes = align_up(o_do + ob);
   max_db = (max_db + 63) / 64 * 64;
+  c->sw_warps = sw_resident_warps(max_db);
   if (int rc = c->d_sw_in.reserve(in_bytes))
     return rc;
   if (int rc = c->d_sw_out.reserve((size_t)n_pairs * sizeof(gtb_sw_result)))
     return rc;
-  if (int rc = c->d_sw_bt.reserve((size_t)c->sw_warps * (size_t)max_db * 128))
+  if (int rc = c->d_sw_bt.reserve((size_t)c->sw_warps * (size_t)(max_db + 5) * 128))
     return rc;
   size_t const out_bytes = (size_t)n_pairs * sizeof(gtb_sw_result);
   if (int rc = c->h_sw.reserve(std::max(in_bytes, out_bytes)))

@@ -179,9 +179,9 @@ struct SwParams
   const uint8_t * d;
   const int32_t * d_off;    // [n_pairs + 1]
   gtb_sw_result * out;
-  uint32_t * bt;            // [resident warps][max_db][32]
+  uint32_t * bt;            // [resident warps][max_db + 5][32]
 };
-int sw_resident_warps();
+int sw_resident_warps(int max_db);
 void launch_sw(const SwParams & p, int resident_warps, void * stream);
 
 } // namespace gtb

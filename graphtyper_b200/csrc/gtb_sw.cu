@@ -6,14 +6,18 @@
 // (alignment_results.hpp:392-447,451-669).  Results are bit-identical to paw: score, database_begin/end, clip_begin/end.
 //
 // One warp per (read, window) pair.  The DP runs as a 32-lane systolic wavefront: lane l owns query columns
-// 5l+1 .. 5l+5, at step s it computes database row s-l+1, and hands (H', E, H) of its last column to lane l+1 with one
-// shuffle per step.  Every cell is three fused max-add DPX operations (__viaddmax_s32 / __vibmax_s32) plus the
-// strict-greater predicates that define paw's four backtrack bits (del, ins, del_extend, ins_extend); the bits of a
-// lane's five cells are one 32-bit word per row (coalesced 128-byte row stores to a per-warp scratch).  The traceback
-// (clipping + begin/end) is executed redundantly by all lanes on rows staged eight at a time in shared memory.
+// c*l+1 .. c*l+c (c = ceil(read length / 32) <= 5, one template instance each), at step s it computes database row
+// s-l+1 and hands (H', E, H) of its last column to lane l+1 with three shuffles.  A cell is two fused add-max DPX
+// operations (VIADDMNMX: E and F), two VIMNMX and four funnel shifts that push the sign of (loser - winner) into the
+// row word -- exactly paw's strict-greater backtrack bits (ins_extend, del_extend, ins, del), no predicates, no
+// branches.  A lane's cells of one row are one 32-bit word; a row is one coalesced 128-byte store into the warp's
+// scratch slab.  The traceback (clipping + begin/end in one walk) is executed redundantly by all lanes on rows staged
+// 16 at a time in shared memory with cp.async, double-buffered so the next 16 rows are in flight while the current
+// ones are walked.  The resident-warp count is sized so that all slabs stay in L2 (sw_resident_warps below).
 // No tensor cores: this is min/max/add dynamic programming, not a contraction.
 
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "gtb_device.cuh"
@@ -23,7 +27,8 @@ namespace gtb
 constexpr int SW_CPL = 5;                 // query columns per lane
 constexpr int SW_MAX_Q = 32 * SW_CPL;     // 160 >= MAX_READ_LENGTH (151)
 constexpr int SW_WARPS = 4;               // warps per block
-constexpr int SW_ROWS_CACHED = 8;         // backtrack rows staged per refill
+constexpr int SW_MIN_BLOCKS = 8;          // 32 resident warps / SM
+constexpr int SW_ROWS_CACHED = 16;        // backtrack rows staged per refill
 constexpr int SW_NEG = -(1 << 28);
 
 namespace
@@ -31,21 +36,123 @@ namespace
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int MATCH = 1, MISMATCH = 4, GO = 7, GE = 1, CLIP = 5;
 
-__device__ __forceinline__ uint8_t db_upper(uint8_t c) // magic_function is case-insensitive (libsimdpp_utils.hpp:96-123)
-{
-  return (c == 'a' || c == 'c' || c == 'g' || c == 't') ? (uint8_t)(c - 32) : c;
-}
 __device__ __forceinline__ bool is_acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 } // namespace
 
-__global__ void __launch_bounds__(SW_WARPS * 32) sw_kernel(SwParams P)
+// DP phase with CPL query columns per lane (CPL = ceil(m / 32) keeps every lane busy for short reads).  Writes one
+// backtrack word per (row, lane) and returns H[n][m] to every lane.
+template <int CPL>
+__device__ __forceinline__ int sw_dp(const uint8_t * q, int m, int n, const uint8_t * sdb, uint32_t * bt, int lane)
 {
-  __shared__ uint32_t s_rows[SW_WARPS][SW_ROWS_CACHED][32];
+  int const c0 = lane * CPL; // columns c0+1 .. c0+CPL
+  // Columns past the read end carry a sentinel base that matches nothing: they are computed (no per-column branch)
+  // but never read -- the score comes from column m and the traceback never moves right of it.
+  int qc[CPL], gop[CPL];
+  int Hprev[CPL], Fprev[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+  {
+    int const j = c0 + c + 1;
+    // a query base matches the database base iff it is an upper-case A/C/G/T and the database base is the same letter
+    // in either case (alignment_cache.hpp:70-121, libsimdpp_utils.hpp:96-123); everything else matches nothing
+    qc[c] = (j <= m && is_acgt(q[j - 1])) ? (int)(q[j - 1] | 0x20) : 0x1FE;
+    gop[c] = j == m ? 0 : GO;        // right_column_free: trailing database bases cost nothing
+    Hprev[c] = -(GO + (j - 1) * GE); // initial row (alignment_options.hpp:282-299)
+    Fprev[c] = SW_NEG;
+  }
+  int Hleft_prev = lane == 0 ? 0 : -(GO + (c0 - 1) * GE); // H[0][c0]
+  int pub_Hp = 0, pub_E = SW_NEG, pub_H = 0;
+  int const last_lane = (m - 1) / CPL;
+  int const steps = n + last_lane;
+  bool const lane_on = c0 < m;
+  // database base of the row handled at the next step, fetched one step ahead of its use
+  int dc_next = (lane == 0) ? sdb[0] | 0x20 : 0;
+#pragma unroll 1 // five template variants + the traceback share the instruction cache: keep every loop body single
+  for (int s = 0; s < steps; ++s)
+  {
+    int rHp = __shfl_up_sync(FULL, pub_Hp, 1);
+    int rE = __shfl_up_sync(FULL, pub_E, 1);
+    int rH = __shfl_up_sync(FULL, pub_H, 1);
+    if (lane == 0) // column 0: leading database bases are free (left_column_free)
+    {
+      rHp = 0;
+      rE = SW_NEG;
+      rH = 0;
+    }
+    int const i = s - lane + 1;
+    int const dc = dc_next;
+    dc_next = sdb[min(max(i, 0), n - 1)] | 0x20; // row i + 1
+    if (i >= 1 && i <= n && lane_on)
+    {
+      int left_Hp = rHp, left_E = rE, diag_src = Hleft_prev;
+      // Backtrack bits are shifted in one at a time: (word << 1) | sign(difference) is a single funnel shift.  Per
+      // cell the order ins_extend, del_extend, ins, del reproduces paw's nibble (8,4,2,1); column c of this lane
+      // ends up in bits [4*(CPL-1-c), 4*(CPL-1-c)+3].  The strict-greater tie rules are paw's.
+      uint32_t word = 0;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c)
+      {
+        int const diag = diag_src + (qc[c] == dc ? MATCH : -MISMATCH);
+        int const hup = Hprev[c];
+        int const fopen = hup - gop[c];
+        int const eopen = left_Hp - GO;
+        // F = max(F_up - extend, open): extension strictly better <=> open - F_up + extend < 0
+        word = __funnelshift_l((uint32_t)(fopen - Fprev[c] + GE), word, 1);
+        int const f = __viaddmax_s32(Fprev[c], -GE, fopen);
+        word = __funnelshift_l((uint32_t)(eopen - left_E + GE), word, 1);
+        int const e = __viaddmax_s32(left_E, -GE, eopen);
+        word = __funnelshift_l((uint32_t)(diag - f), word, 1); // ins: f > diag
+        int const hp = max(diag, f);
+        word = __funnelshift_l((uint32_t)(hp - e), word, 1); // del: e > hp
+        int const h = max(hp, e);
+        diag_src = hup;
+        Hprev[c] = h;
+        Fprev[c] = f;
+        left_Hp = hp;
+        left_E = e;
+      }
+      pub_Hp = left_Hp;
+      pub_E = left_E;
+      pub_H = Hprev[CPL - 1];
+      Hleft_prev = rH;
+      bt[(size_t)(i - 1) * 32 + lane] = word;
+    }
+  }
+  int const cm = (m - 1) % CPL;
+  int hsel = Hprev[0];
+#pragma unroll
+  for (int c = 1; c < CPL; ++c)
+    if (cm == c)
+      hsel = Hprev[c];
+  return __shfl_sync(FULL, hsel, last_lane);
+}
+
+// Starts the asynchronous copy (LDGSTS) of backtrack rows top, top-1, ... top-SW_ROWS_CACHED+1 of this warp into one
+// shared-memory buffer; the traceback consumes one buffer while the next one is in flight.
+__device__ __forceinline__ void sw_stage_rows_async(uint32_t (*rows)[32], const uint32_t * bt, int top, int lane)
+{
+#pragma unroll
+  for (int k = 0; k < SW_ROWS_CACHED; ++k)
+    if (top - k >= 0)
+    {
+      unsigned const dst = (unsigned)__cvta_generic_to_shared(&rows[k][lane]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(bt + (size_t)(top - k) * 32 + lane) : "memory");
+    }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(SW_WARPS * 32, SW_MIN_BLOCKS) sw_kernel(SwParams P)
+{
+  __shared__ uint32_t s_rows[SW_WARPS][2][SW_ROWS_CACHED][32];
+  __shared__ uint8_t s_db[SW_WARPS][GTB_SW_MAX_DATABASE];
+  __shared__ uint8_t s_q[SW_WARPS][SW_MAX_Q];
   int const lane = threadIdx.x & 31;
   int const wib = threadIdx.x >> 5;
   int const warp_global = blockIdx.x * SW_WARPS + wib;
   int const total_warps = gridDim.x * SW_WARPS;
-  uint32_t * bt = P.bt + (size_t)warp_global * (size_t)P.max_db * 32;
+  // per-warp scratch slabs are max_db + 5 rows apart: a power-of-two stride would map every warp's row r to the same
+  // L2 sets
+  uint32_t * bt = P.bt + (size_t)warp_global * (size_t)(P.max_db + 5) * 32;
 
   for (int pair = warp_global; pair < P.n_pairs; pair += total_warps)
   {
@@ -53,87 +160,33 @@ __global__ void __launch_bounds__(SW_WARPS * 32) sw_kernel(SwParams P)
     const uint8_t * d = P.d + P.d_off[pair];
     int const m = P.q_off[pair + 1] - P.q_off[pair];
     int const n = P.d_off[pair + 1] - P.d_off[pair];
-    if (m <= 0 || m > SW_MAX_Q || n <= 0 || n > P.max_db)
+    if (m <= 0 || m > SW_MAX_Q || n <= 0 || n > P.max_db || n > GTB_SW_MAX_DATABASE)
     {
       if (lane == 0)
         P.out[pair] = gtb_sw_result{0, 0, 0, 0, -1}; // clip_end = -1 marks an unsupported size
       continue;
     }
-    int const c0 = lane * SW_CPL; // columns c0+1 .. c0+5
-    uint8_t qc[SW_CPL];
-    int Hprev[SW_CPL], Fprev[SW_CPL];
-#pragma unroll
-    for (int c = 0; c < SW_CPL; ++c)
+    // Stage both sequences of this pair in shared memory (the DP reads a database base per step, the traceback
+    // compares raw bases).
+    __syncwarp();
+    for (int k = lane; k < n; k += 32)
+      s_db[wib][k] = __ldg(d + k);
+    for (int k = lane; k < m; k += 32)
+      s_q[wib][k] = __ldg(q + k);
+    __syncwarp();
+    q = s_q[wib];
+    d = s_db[wib];
+    int const cpl = (m + 31) / 32;
+    int const cpl_inv = (65536 + cpl - 1) / cpl;
+    long score;
+    switch (cpl)
     {
-      int const j = c0 + c + 1;
-      qc[c] = j <= m ? q[j - 1] : (uint8_t)0;
-      Hprev[c] = -(GO + (j - 1) * GE); // initial row (alignment_options.hpp:282-299)
-      Fprev[c] = SW_NEG;
+    case 1: score = sw_dp<1>(q, m, n, d, bt, lane); break;
+    case 2: score = sw_dp<2>(q, m, n, d, bt, lane); break;
+    case 3: score = sw_dp<3>(q, m, n, d, bt, lane); break;
+    case 4: score = sw_dp<4>(q, m, n, d, bt, lane); break;
+    default: score = sw_dp<5>(q, m, n, d, bt, lane); break;
     }
-    int Hleft_prev = lane == 0 ? 0 : -(GO + (c0 - 1) * GE); // H[0][c0]
-    int pub_Hp = 0, pub_E = SW_NEG, pub_H = 0;
-    int const steps = n + 31;
-    for (int s = 0; s < steps; ++s)
-    {
-      int rHp = __shfl_up_sync(FULL, pub_Hp, 1);
-      int rE = __shfl_up_sync(FULL, pub_E, 1);
-      int rH = __shfl_up_sync(FULL, pub_H, 1);
-      if (lane == 0) // column 0: leading database bases are free (left_column_free)
-      {
-        rHp = 0;
-        rE = SW_NEG;
-        rH = 0;
-      }
-      int const i = s - lane + 1;
-      if (i >= 1 && i <= n && c0 < m)
-      {
-        uint8_t const dc = db_upper(__ldg(d + i - 1));
-        bool const dvalid = is_acgt(dc);
-        int left_Hp = rHp, left_E = rE, diag_src = Hleft_prev;
-        uint32_t word = 0;
-#pragma unroll
-        for (int c = 0; c < SW_CPL; ++c)
-        {
-          int const j = c0 + c + 1;
-          if (j <= m)
-          {
-            int const diag = diag_src + ((dvalid && qc[c] == dc) ? MATCH : -MISMATCH);
-            int const hup = Hprev[c];
-            int const fopen = (j == m) ? hup : hup - GO; // right_column_free
-            bool p;
-            // F = max(F_up - extend, open); ins_extend bit <=> extension strictly better
-            int const f = __vibmax_s32(fopen, Fprev[c] - GE, &p);
-            uint32_t bits = p ? 0u : 8u;
-            int const hp = __vibmax_s32(diag, f, &p);
-            bits |= p ? 0u : 2u;
-            int const e = __vibmax_s32(left_Hp - GO, left_E - GE, &p);
-            bits |= p ? 0u : 4u;
-            int const h = __vibmax_s32(hp, e, &p);
-            bits |= p ? 0u : 1u;
-            diag_src = hup;
-            Hprev[c] = h;
-            Fprev[c] = f;
-            left_Hp = hp;
-            left_E = e;
-            word |= bits << (4 * c);
-          }
-        }
-        pub_Hp = left_Hp;
-        pub_E = left_E;
-        // H of this lane's last column (only lanes whose last column is <= m feed a neighbour that is active)
-        pub_H = Hprev[SW_CPL - 1];
-        Hleft_prev = rH;
-        bt[(size_t)(i - 1) * 32 + lane] = word;
-      }
-    }
-    // DP score = H[n][m]
-    int const lm = (m - 1) / SW_CPL, cm = (m - 1) % SW_CPL;
-    int hsel = Hprev[0];
-#pragma unroll
-    for (int c = 1; c < SW_CPL; ++c)
-      if (cm == c)
-        hsel = Hprev[c];
-    long score = __shfl_sync(FULL, hsel, lm);
     __syncwarp();
 
     // ---- traceback: clipping (alignment_results.hpp:451-669) and database begin/end (:392-447) follow the same walk.
@@ -142,20 +195,26 @@ __global__ void __launch_bounds__(SW_WARPS * 32) sw_kernel(SwParams P)
     int res_first = 0, res_second = m, db_first = 0, db_second = n;
     {
       int i = n, j = m;
-      int cached_top = -1; // s_rows[k] holds row (cached_top - k)
+      // s_rows[wib][cur][k] holds row (cached_top - k); the other buffer is being filled with the SW_ROWS_CACHED rows
+      // below.  The walk only ever moves to the same or the previous row.
+      int cur = 0, cached_top = n - 1;
+      sw_stage_rows_async(s_rows[wib][0], bt, cached_top, lane);
+      sw_stage_rows_async(s_rows[wib][1], bt, cached_top - SW_ROWS_CACHED, lane);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncwarp();
       auto bits_at = [&](int row, int col) -> uint32_t
       {
-        if (cached_top < 0 || row > cached_top || row <= cached_top - SW_ROWS_CACHED)
+        if (row <= cached_top - SW_ROWS_CACHED)
         {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
           __syncwarp();
-#pragma unroll
-          for (int k = 0; k < SW_ROWS_CACHED; ++k)
-            s_rows[wib][k][lane] = (row - k) >= 0 ? bt[(size_t)(row - k) * 32 + lane] : 0u;
-          cached_top = row;
-          __syncwarp();
+          cached_top -= SW_ROWS_CACHED;
+          sw_stage_rows_async(s_rows[wib][cur], bt, cached_top - SW_ROWS_CACHED, lane);
+          cur ^= 1;
         }
-        uint32_t const w = s_rows[wib][cached_top - row][(col - 1) / SW_CPL];
-        return (w >> (4 * ((col - 1) % SW_CPL))) & 15u;
+        int const wl = ((col - 1) * cpl_inv) >> 16; // (col - 1) / cpl, exact for col <= 160
+        uint32_t const w = s_rows[wib][cur][cached_top - row][wl];
+        return (w >> (4 * (cpl - 1 - (col - 1 - wl * cpl)))) & 15u;
       };
       while (i > 0 || j > 0)
       {
@@ -228,6 +287,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32) sw_kernel(SwParams P)
         }
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0)
     {
       gtb_sw_result r;
@@ -242,15 +302,28 @@ __global__ void __launch_bounds__(SW_WARPS * 32) sw_kernel(SwParams P)
   }
 }
 
-int sw_resident_warps()
+// Resident warps for windows of up to max_db bases.  Every resident warp owns a backtrack slab of (max_db + 5) rows
+// x 128 B that is written once by the DP and read back by the traceback; measured on B200 the kernel is fastest when
+// all slabs together stay inside the L2 (12 warps / SM at 512-base windows, 116 MB of 126 MB) -- more warps spill the
+// slabs to HBM and lose more to the traceback's read latency than they gain in issue slots.
+int sw_resident_warps(int max_db)
 {
-  int dev = 0, sms = 148, nb = 0;
+  int dev = 0, sms = 148, nb = 0, l2 = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sw_kernel, SW_WARPS * 32, 0) != cudaSuccess || nb < 1)
     nb = 1;
-  if (nb > 4)
-    nb = 4; // 16 warps / SM: bounds the backtrack scratch (128 B per row per warp)
+  if (nb > SW_MIN_BLOCKS)
+    nb = SW_MIN_BLOCKS;
+  if (l2 > 0)
+  {
+    size_t const slab = (size_t)(max_db + 5) * 128;
+    int const fit = (int)((size_t)l2 * 95 / 100 / slab / (size_t)(sms * SW_WARPS));
+    nb = max(1, min(nb, fit));
+  }
+  if (const char * e = getenv("GTB_SW_BLOCKS")) // tuning knob: resident blocks per SM
+    nb = max(1, min(SW_MIN_BLOCKS, atoi(e)));
   return sms * nb * SW_WARPS;
 }
 

@@ -447,7 +447,7 @@ _ACGT = np.frombuffer(b"ACGT", np.uint8)
 
 
 def make_sw_pairs(n_pairs: int, seed: int = 1, min_db: int = 60, max_db: int = 520, max_query: int = 151,
-                  lowercase_rate: float = 0.03) -> Tuple[List[bytes], List[bytes]]:
+                  lowercase_rate: float = 0.03, min_query: int = 20) -> Tuple[List[bytes], List[bytes]]:
     """Seeded read/window pairs shaped like realign_to_indels' input (src/typer/caller.cpp:1930-2007: a read against
     reference window +- 50..100 bp with one indel haplotype spliced in): the read is a fragment of the window with
     substitutions, small indels, occasional N, overhangs past either window end (exercises clipping) and random
@@ -481,7 +481,7 @@ def make_sw_pairs(n_pairs: int, seed: int = 1, min_db: int = 60, max_db: int = 5
     for _ in range(n_pairs):
         n = int(rng.integers(min_db, max_db))
         d = bytes(_ACGT[rng.integers(0, 4, size=n)])
-        length = int(rng.integers(20, max_query + 1))
+        length = int(rng.integers(min_query, max_query + 1))
         st = int(rng.integers(-30, n - 10))
         frag = d[max(st, 0):max(st, 0) + length]
         if st < 0:

@@ -28,9 +28,10 @@ def main() -> None:
     ap.add_argument("--pairs", type=int, default=200000)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--cpu-sample", type=int, default=20000)
+    ap.add_argument("--min-query", type=int, default=20, help="shortest read (151 = every read full length)")
     a = ap.parse_args()
     base = 20000
-    q0, d0 = synth.make_sw_pairs(base, seed=3, min_db=400, max_db=520)
+    q0, d0 = synth.make_sw_pairs(base, seed=3, min_db=400, max_db=520, min_query=a.min_query)
     rep = (a.pairs + base - 1) // base
     q, d = (q0 * rep)[:a.pairs], (d0 * rep)[:a.pairs]
     qb, qo = engine.pack_sequences(q)
@@ -49,11 +50,12 @@ def main() -> None:
         ctx.sw_replay()
         ker.append(ctx.sw_last_timing()["kernel_ms"])
     k_ms = float(np.median(ker))
-    line = {"metric": "sw_pairs_per_s", "pairs": a.pairs, "kernel_ms": k_ms, "value": a.pairs / (k_ms * 1e-3),
+    line = {"metric": "sw_pairs_per_s", "pairs": a.pairs, "mean_query": float(np.diff(qo).mean()),
+            "mean_window": float(np.diff(do).mean()), "kernel_ms": k_ms, "value": a.pairs / (k_ms * 1e-3),
             "gcups": cells / (k_ms * 1e-3) / 1e9, "e2e": a.pairs / float(np.median(e2e)),
             "h2d_ms": tim["h2d_ms"], "d2h_ms": tim["d2h_ms"], "checksum": int(out[:, 0].astype(np.int64).sum())}
     exe = os.path.join(ROOT, "oracle", "_ref", "bin", "paw_probe")
-    if os.path.exists(exe):
+    if os.path.exists(exe) and a.cpu_sample > 0:
         n = min(a.cpu_sample, a.pairs)
         with tempfile.NamedTemporaryFile("wb", suffix=".tsv", delete=False) as f:
             f.write(b"".join(x + b"\t" + y + b"\n" for x, y in zip(q[:n], d[:n])))
