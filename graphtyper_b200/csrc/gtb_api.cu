@@ -116,7 +116,11 @@ struct Region
   int n_samples = 0;
   bool pool_open = false;
   // device
-  DeviceBuffer arena;   // graph + index
+  DeviceBuffer arena;   // graph + index (host-built index) or graph only (device-built index)
+  DeviceBuffer index_arena; // device-built index: labels + distinct k-mers + table + bitmap
+  bool dev_index = false;
+  uint64_t dev_n_keys = 0, dev_n_labels = 0;
+  IdxRegion idx{};      // graph pointers of the device index build
   DeviceBuffer accum;   // accumulators (allocated at pool_begin)
   DevRegion dev{};      // pointers into arena/accum
   size_t accum_bytes = 0;
@@ -176,6 +180,10 @@ struct Ctx
   void * nccl_lib = nullptr;
   void * nccl_comm = nullptr;
   int nccl_rank = 0, nccl_size = 1;
+  // device-side index build (gtb_set_index_build / GTB_INDEX_BUILD=host|device)
+  int index_build_device = 1;
+  DeviceBuffer d_idx_small, d_idx_jobs, d_idx_keys, d_idx_keys2, d_idx_labels, d_idx_idx, d_idx_idx2, d_idx_head, d_idx_temp;
+  PinnedBuffer h_idx_small;
   // discovery re-alignment (gtb_sw_align_batch)
   DeviceBuffer d_sw_in, d_sw_out, d_sw_bt;
   PinnedBuffer h_sw;
@@ -424,6 +432,7 @@ void gtb_destroy(gtb_ctx * ctx)
     for (auto & kv : c->regions)
     {
       kv.second->arena.release();
+      kv.second->index_arena.release();
       kv.second->accum.release();
     }
     c->d_regions.release();
@@ -437,6 +446,10 @@ void gtb_destroy(gtb_ctx * ctx)
     c->d_spill.release();
     c->h_stage.release();
     c->h_accum.release();
+    for (DeviceBuffer * b : {&c->d_idx_small, &c->d_idx_jobs, &c->d_idx_keys, &c->d_idx_keys2, &c->d_idx_labels, &c->d_idx_idx,
+                             &c->d_idx_idx2, &c->d_idx_head, &c->d_idx_temp})
+      b->release();
+    c->h_idx_small.release();
     c->d_sw_in.release();
     c->d_sw_out.release();
     c->d_sw_bt.release();
@@ -454,7 +467,7 @@ void gtb_destroy(gtb_ctx * ctx)
 
 // Uploads one prepared region: graph + labels + distinct k-mer list in ONE H2D copy, then the k-mer table is
 // built on the device (the 16-byte-slot table is 4-8x larger than the list it is built from).
-static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g)
+static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g, bool dev_index)
 {
   size_t off = 0;
   size_t const o_ref_order = place<uint32_t>(off, g->n_ref);
@@ -473,11 +486,21 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g)
   size_t const o_bubble_order = place<uint32_t>(off, R.n_bubbles);
   size_t const o_score_off = place<uint32_t>(off, R.n_bubbles + 1);
   size_t const o_cov_off = place<uint32_t>(off, R.n_bubbles + 1);
-  size_t const o_labels = place<DevLabel>(off, R.index.labels.size());
-  size_t const o_uniq = place<IndexSlot>(off, R.index.uniq.size());
+  // device index build: events + the sweep-order node table instead of a host-built index
+  bool const have_ev = dev_index && g->var_ev_off && g->var_aev_off && g->var_ev && g->var_aev;
+  size_t const n_ev = have_ev ? g->var_ev_off[g->n_var] : 0, n_aev = have_ev ? g->var_aev_off[g->n_var] : 0;
+  uint32_t const n_sweep = dev_index ? g->n_ref + g->n_var : 0;
+  size_t const o_ev_off = place<uint32_t>(off, have_ev ? g->n_var + 1 : 0);
+  size_t const o_aev_off = place<uint32_t>(off, have_ev ? g->n_var + 1 : 0);
+  size_t const o_ev = place<int64_t>(off, n_ev);
+  size_t const o_aev = place<int64_t>(off, n_aev);
+  size_t const o_sweep_node = place<uint32_t>(off, n_sweep);
+  size_t const o_sweep_off = place<uint32_t>(off, dev_index ? n_sweep + 1 : 0);
+  size_t const o_labels = place<DevLabel>(off, dev_index ? 0 : R.index.labels.size());
+  size_t const o_uniq = place<IndexSlot>(off, dev_index ? 0 : R.index.uniq.size());
   size_t const upload_bytes = align_up(off, 256);
-  size_t const o_table = place<IndexSlot>(off, R.index.table_cap); // device only
-  size_t const o_bitmap = place<uint32_t>(off, (size_t)R.index.table_cap * 4 / 32 + 1); // device only, follows the table
+  size_t const o_table = place<IndexSlot>(off, dev_index ? 0 : R.index.table_cap); // device only
+  size_t const o_bitmap = place<uint32_t>(off, dev_index ? 0 : (size_t)R.index.table_cap * 4 / 32 + 1); // follows the table
   size_t const total = align_up(off, 256);
 
   if (int rc = c->h_stage.reserve(upload_bytes))
@@ -513,17 +536,51 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g)
   put32(o_bubble_order, R.bubble_order.data(), R.n_bubbles);
   put32(o_score_off, R.score_off.data(), R.n_bubbles + 1);
   put32(o_cov_off, R.cov_off.data(), R.n_bubbles + 1);
-  memcpy(h + o_labels, R.index.labels.data(), R.index.labels.size() * sizeof(DevLabel));
-  memcpy(h + o_uniq, R.index.uniq.data(), R.index.uniq.size() * sizeof(IndexSlot));
+  uint32_t n_jobs = 0;
+  if (dev_index)
+  {
+    if (have_ev)
+    {
+      put32(o_ev_off, g->var_ev_off, g->n_var + 1);
+      put32(o_aev_off, g->var_aev_off, g->n_var + 1);
+      memcpy(h + o_ev, g->var_ev, n_ev * 8);
+      memcpy(h + o_aev, g->var_aev, n_aev * 8);
+    }
+    // sweep order of indexer.cpp:246-291: ref node r, then the alleles of bubble r in order
+    uint32_t * sn = reinterpret_cast<uint32_t *>(h + o_sweep_node);
+    uint32_t * so = reinterpret_cast<uint32_t *>(h + o_sweep_off);
+    uint32_t k = 0;
+    for (uint32_t r = 0; r < g->n_ref; ++r)
+    {
+      sn[k] = r;
+      so[k++] = n_jobs;
+      n_jobs += (uint32_t)(g->ref_seq_off[r + 1] - g->ref_seq_off[r]);
+      for (uint32_t v = g->ref_var_off[r]; v < g->ref_var_off[r + 1]; ++v)
+      {
+        sn[k] = v | 0x80000000u;
+        so[k++] = n_jobs;
+        n_jobs += (uint32_t)(g->var_seq_off[v + 1] - g->var_seq_off[v]);
+      }
+    }
+    so[k] = n_jobs;
+  }
+  else
+  {
+    memcpy(h + o_labels, R.index.labels.data(), R.index.labels.size() * sizeof(DevLabel));
+    memcpy(h + o_uniq, R.index.uniq.data(), R.index.uniq.size() * sizeof(IndexSlot));
+  }
 
   if (int rc = take_buffer(c, R.arena, total))
     return rc;
   uint8_t * d = static_cast<uint8_t *>(R.arena.p);
   CUDA_TRY(cudaMemcpyAsync(d, h, upload_bytes, cudaMemcpyHostToDevice, c->stream));
-  CUDA_TRY(cudaMemsetAsync(d + o_table, 0, total - o_table, c->stream)); // table + bitmap
-  launch_build_table(reinterpret_cast<const IndexSlot *>(d + o_uniq), (uint32_t)R.index.uniq.size(),
-                     reinterpret_cast<IndexSlot *>(d + o_table), R.index.table_mask, R.index.table_shift,
-                     reinterpret_cast<uint32_t *>(d + o_bitmap), c->stream);
+  if (!dev_index)
+  {
+    CUDA_TRY(cudaMemsetAsync(d + o_table, 0, total - o_table, c->stream)); // table + bitmap
+    launch_build_table(reinterpret_cast<const IndexSlot *>(d + o_uniq), (uint32_t)R.index.uniq.size(),
+                       reinterpret_cast<IndexSlot *>(d + o_table), R.index.table_mask, R.index.table_shift,
+                       reinterpret_cast<uint32_t *>(d + o_bitmap), c->stream);
+  }
   CUDA_TRY(cudaStreamSynchronize(c->stream)); // h_stage is reused by the next region
   CUDA_TRY(cudaGetLastError());
 
@@ -558,6 +615,36 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g)
   D.labels = reinterpret_cast<const DevLabel *>(d + o_labels);
   D.depth_size = R.depth_size;
   D.reference_offset = R.reference_offset;
+  R.dev_index = dev_index;
+  if (dev_index)
+  {
+    IdxRegion & X = R.idx;
+    memset(&X, 0, sizeof(X));
+    X.n_ref = g->n_ref;
+    X.n_var = g->n_var;
+    X.n_sp_keys = g->n_sp_keys;
+    X.n_sweep = n_sweep;
+    X.ref_order = D.ref_order;
+    X.ref_seq_off = D.ref_seq_off;
+    X.ref_var_off = D.ref_var_off;
+    X.var_order = D.var_order;
+    X.var_seq_off = D.var_seq_off;
+    X.var_out_ref = D.var_out_ref;
+    X.seq = D.seq;
+    X.sp_keys = D.sp_keys;
+    X.sp_off = D.sp_off;
+    X.sp_list = D.sp_list;
+    if (have_ev)
+    {
+      X.var_ev_off = reinterpret_cast<const uint32_t *>(d + o_ev_off);
+      X.var_aev_off = reinterpret_cast<const uint32_t *>(d + o_aev_off);
+      X.var_ev = reinterpret_cast<const int64_t *>(d + o_ev);
+      X.var_aev = reinterpret_cast<const int64_t *>(d + o_aev);
+    }
+    X.sweep_node = reinterpret_cast<const uint32_t *>(d + o_sweep_node);
+    X.sweep_job_off = reinterpret_cast<const uint32_t *>(d + o_sweep_off);
+    R.dev_n_labels = n_jobs; // number of END positions until the count pass has run
+  }
 
   int slot = -1;
   for (size_t s = 0; s < c->slot_region.size(); ++s)
@@ -579,7 +666,152 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g)
   return 0;
 }
 
-// Several regions at once: the host index builds run in parallel (they are independent), uploads follow.
+// Device-side index build of all regions of one gtb_region_begin_multi call (kernels: gtb_index_dev.cu).  Two stream
+// synchronisations: after the count pass (the label totals size the per-region index arenas) and at the end.
+static int build_indexes_on_device(Ctx * c, std::vector<std::unique_ptr<Region>> & regs)
+{
+  uint32_t const n = (uint32_t)regs.size();
+  std::vector<uint32_t> job_off(n + 1, 0);
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    uint64_t const next = (uint64_t)job_off[i] + regs[i]->dev_n_labels; // = END positions (set by upload_region)
+    if (next >= 0x7FFFFFFFull)
+      return fail(GTB_ERR_CAPACITY, "more than 2^31 graph bases in one gtb_region_begin_multi call");
+    job_off[i + 1] = (uint32_t)next;
+  }
+  uint32_t const total_jobs = job_off[n];
+  // small arrays: [IdxRegion x n][region_job_off n+1][region_tuple_off n+1][region_n_uniq n][err 1]
+  size_t so = 0;
+  size_t const o_desc = place<IdxRegion>(so, n);
+  size_t const o_rjo = place<uint32_t>(so, n + 1);
+  size_t const o_rto = place<uint32_t>(so, n + 1);
+  size_t const o_nu = place<uint32_t>(so, n);
+  size_t const o_err = place<uint32_t>(so, 1);
+  size_t const small_bytes = align_up(so, 256);
+  if (int rc = c->d_idx_small.reserve(small_bytes))
+    return rc;
+  if (int rc = c->h_idx_small.reserve(small_bytes))
+    return rc;
+  uint8_t * hs = static_cast<uint8_t *>(c->h_idx_small.p);
+  uint8_t * ds = static_cast<uint8_t *>(c->d_idx_small.p);
+  memset(hs, 0, small_bytes);
+  IdxRegion * hdesc = reinterpret_cast<IdxRegion *>(hs + o_desc);
+  for (uint32_t i = 0; i < n; ++i)
+    hdesc[i] = regs[i]->idx;
+  memcpy(hs + o_rjo, job_off.data(), (n + 1) * 4);
+  CUDA_TRY(cudaMemcpyAsync(ds, hs, small_bytes, cudaMemcpyHostToDevice, c->stream));
+  const IdxRegion * d_desc = reinterpret_cast<const IdxRegion *>(ds + o_desc);
+  const uint32_t * d_rjo = reinterpret_cast<const uint32_t *>(ds + o_rjo);
+  uint32_t * d_rto = reinterpret_cast<uint32_t *>(ds + o_rto);
+  uint32_t * d_nu = reinterpret_cast<uint32_t *>(ds + o_nu);
+  uint32_t * d_err = reinterpret_cast<uint32_t *>(ds + o_err);
+
+  // 1-2. count + scan
+  size_t const jobs_bytes = align_up((size_t)(total_jobs + 1) * 4);
+  if (int rc = c->d_idx_jobs.reserve(jobs_bytes * 2))
+    return rc;
+  uint32_t * d_cnt = static_cast<uint32_t *>(c->d_idx_jobs.p);
+  uint32_t * d_joff = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(c->d_idx_jobs.p) + jobs_bytes);
+  size_t scan_bytes = idx_scan_temp_bytes(total_jobs + 1);
+  if (int rc = c->d_idx_temp.reserve(scan_bytes))
+    return rc;
+  CUDA_TRY(cudaMemsetAsync(d_cnt + total_jobs, 0, 4, c->stream));
+  idx_launch_count(d_desc, n, d_rjo, total_jobs, d_cnt, d_err, c->stream);
+  if (idx_exclusive_scan(c->d_idx_temp.p, c->d_idx_temp.cap, d_cnt, d_joff, total_jobs + 1, c->stream))
+    return fail(GTB_ERR_CUDA, "index build: scan failed");
+  idx_launch_region_totals(d_joff, d_rjo, n, d_rto, c->stream);
+  CUDA_TRY(cudaMemcpyAsync(hs + o_rto, d_rto, (n + 1) * 4 + 0, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(hs + o_err, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  const uint32_t * rto = reinterpret_cast<const uint32_t *>(hs + o_rto);
+  if (*reinterpret_cast<const uint32_t *>(hs + o_err))
+    return fail(GTB_ERR_ARG, "index build: inconsistent graph view (special position table / more than 64 nested empty nodes)");
+  uint32_t const total = rto[n];
+
+  // per-region index arenas (labels, distinct k-mers, table, bitmap), geometry as in HostIndex
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    Region & R = *regs[i];
+    size_t const nl = rto[i + 1] - rto[i];
+    size_t cap = 16;
+    while (cap < nl * 4 + 2)
+      cap <<= 1;
+    int shift = 64;
+    for (size_t x = cap; x > 1; x >>= 1)
+      --shift;
+    size_t ao = 0;
+    size_t const o_labels = place<DevLabel>(ao, nl);
+    size_t const o_uniq = place<IndexSlot>(ao, nl);
+    size_t const o_table = place<IndexSlot>(ao, cap);
+    size_t const o_bitmap = place<uint32_t>(ao, cap * 4 / 32 + 1);
+    size_t const atotal = align_up(ao, 256);
+    if (int rc = take_buffer(c, R.index_arena, atotal))
+      return rc;
+    uint8_t * a = static_cast<uint8_t *>(R.index_arena.p);
+    CUDA_TRY(cudaMemsetAsync(a + o_table, 0, atotal - o_table, c->stream));
+    IdxRegion & X = hdesc[i];
+    X.labels = reinterpret_cast<DevLabel *>(a + o_labels);
+    X.uniq = reinterpret_cast<IndexSlot *>(a + o_uniq);
+    X.table = reinterpret_cast<IndexSlot *>(a + o_table);
+    X.bitmap = reinterpret_cast<uint32_t *>(a + o_bitmap);
+    X.table_mask = (uint32_t)(cap - 1);
+    X.table_shift = shift;
+    R.idx = X;
+    R.dev.table = X.table;
+    R.dev.bitmap = X.bitmap;
+    R.dev.labels = X.labels;
+    R.dev.table_mask = X.table_mask;
+    R.dev.table_shift = X.table_shift;
+    R.dev_n_labels = nl;
+    R.index.table_cap = (uint32_t)cap;
+    R.index.table_mask = X.table_mask;
+    R.index.table_shift = shift;
+  }
+  CUDA_TRY(cudaMemcpyAsync(ds + o_desc, hs + o_desc, n * sizeof(IdxRegion), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemsetAsync(d_nu, 0, n * 4, c->stream));
+  if (total)
+  {
+    // 3. emit  4. segmented stable sort  5-6. group + table
+    if (int rc = c->d_idx_keys.reserve((size_t)total * 8))
+      return rc;
+    if (int rc = c->d_idx_keys2.reserve((size_t)total * 8))
+      return rc;
+    if (int rc = c->d_idx_labels.reserve((size_t)total * sizeof(DevLabel)))
+      return rc;
+    if (int rc = c->d_idx_idx.reserve((size_t)total * 4))
+      return rc;
+    if (int rc = c->d_idx_idx2.reserve((size_t)total * 4))
+      return rc;
+    if (int rc = c->d_idx_head.reserve((size_t)total * 8))
+      return rc;
+    size_t const sort_bytes = idx_sort_temp_bytes(total, n);
+    scan_bytes = idx_scan_temp_bytes(total);
+    if (int rc = c->d_idx_temp.reserve(std::max(sort_bytes, scan_bytes)))
+      return rc;
+    uint64_t * k1 = static_cast<uint64_t *>(c->d_idx_keys.p);
+    uint64_t * k2 = static_cast<uint64_t *>(c->d_idx_keys2.p);
+    uint32_t * i1 = static_cast<uint32_t *>(c->d_idx_idx.p);
+    uint32_t * i2 = static_cast<uint32_t *>(c->d_idx_idx2.p);
+    DevLabel * le = static_cast<DevLabel *>(c->d_idx_labels.p);
+    uint32_t * head = static_cast<uint32_t *>(c->d_idx_head.p);
+    idx_launch_emit(d_desc, n, d_rjo, total_jobs, d_joff, k1, le, i1, d_err, c->stream);
+    if (idx_sort(c->d_idx_temp.p, c->d_idx_temp.cap, k1, k2, i1, i2, total, n, d_rto, c->stream))
+      return fail(GTB_ERR_CUDA, "index build: sort failed");
+    idx_launch_group(d_desc, k2, i2, le, head, head + total, c->d_idx_temp.p, c->d_idx_temp.cap, d_rto, n, total, d_nu, c->stream);
+  }
+  CUDA_TRY(cudaMemcpyAsync(hs + o_nu, d_nu, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  const uint32_t * nu = reinterpret_cast<const uint32_t *>(hs + o_nu);
+  for (uint32_t i = 0; i < n; ++i)
+    regs[i]->dev_n_keys = nu[i];
+  c->regions_dirty = true;
+  return 0;
+}
+
+// Several regions at once.  With a CUDA device the index of all regions is built on the device in one launch sequence
+// (gtb_set_index_build(ctx, 0) / GTB_INDEX_BUILD=host selects the host builder, whose builds run in parallel).
 int gtb_region_begin_multi(gtb_ctx * ctx, int n, const int * region_ids, const gtb_graph_view * graphs)
 {
   auto * c = reinterpret_cast<Ctx *>(ctx);
@@ -595,6 +827,11 @@ int gtb_region_begin_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
     if (int rc = validate_graph(&graphs[i]))
       return rc;
   }
+  static int const env_mode = []() {
+    const char * e = getenv("GTB_INDEX_BUILD");
+    return !e ? -1 : (strcmp(e, "host") == 0 ? 0 : 1);
+  }();
+  bool const dev_index = c->device >= 0 && (env_mode >= 0 ? env_mode == 1 : c->index_build_device != 0);
   std::vector<std::unique_ptr<Region>> regs(n);
   std::vector<const char *> errs(n, nullptr);
   parallel_for(n, [&](int i)
@@ -611,12 +848,15 @@ int gtb_region_begin_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
                    R->reference_offset = g->ref_order[0];
                    R->depth_size = last_reach >= g->ref_order[0] ? last_reach - g->ref_order[0] + 1 : 0;
                  }
-                 IndexBuilder ib(*g);
-                 const char * err = nullptr;
-                 if (!ib.build(R->index, &err))
+                 if (!dev_index)
                  {
-                   errs[i] = err ? err : "index build failed";
-                   return;
+                   IndexBuilder ib(*g);
+                   const char * err = nullptr;
+                   if (!ib.build(R->index, &err))
+                   {
+                     errs[i] = err ? err : "index build failed";
+                     return;
+                   }
                  }
                  R->score_off.assign(1, 0);
                  R->cov_off.assign(1, 0);
@@ -637,9 +877,24 @@ int gtb_region_begin_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   if (c->device >= 0)
   {
     cudaSetDevice(c->device);
-    for (int i = 0; i < n; ++i)
-      if (int rc = upload_region(c, *regs[i], &graphs[i]))
-        return rc;
+    int rc = 0;
+    for (int i = 0; i < n && !rc; ++i)
+      rc = upload_region(c, *regs[i], &graphs[i], dev_index);
+    if (!rc && dev_index)
+      rc = build_indexes_on_device(c, regs);
+    if (rc)
+    {
+      // undo: free slots and recycle the arenas of the regions that were already uploaded
+      for (int i = 0; i < n; ++i)
+      {
+        if (regs[i]->slot >= 0)
+          c->slot_region[regs[i]->slot] = -1;
+        give_buffer(c, regs[i]->arena);
+        give_buffer(c, regs[i]->index_arena);
+      }
+      c->regions_dirty = true;
+      return rc;
+    }
   }
   for (int i = 0; i < n; ++i)
     c->regions[region_ids[i]] = std::move(regs[i]);
@@ -664,6 +919,7 @@ int gtb_region_end(gtb_ctx * ctx, int region_id)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     give_buffer(c, it->second->arena);
+    give_buffer(c, it->second->index_arena);
     give_buffer(c, it->second->accum);
     if (it->second->slot >= 0)
       c->slot_region[it->second->slot] = -1;
@@ -680,6 +936,12 @@ int gtb_index_size(gtb_ctx * ctx, int region_id, uint64_t * n_keys, uint64_t * n
   auto it = c->regions.find(region_id);
   if (it == c->regions.end())
     return fail(GTB_ERR_STATE, "unknown region");
+  if (it->second->dev_index)
+  {
+    *n_keys = it->second->dev_n_keys;
+    *n_labels = it->second->dev_n_labels;
+    return 0;
+  }
   *n_keys = it->second->index.n_keys;
   *n_labels = it->second->index.labels.size();
   return 0;
@@ -691,6 +953,24 @@ int gtb_index_export(gtb_ctx * ctx, int region_id, uint64_t * keys, uint32_t * l
   auto it = c->regions.find(region_id);
   if (it == c->regions.end())
     return fail(GTB_ERR_STATE, "unknown region");
+  if (it->second->dev_index)
+  {
+    // the device-built index is already grouped by ascending k-mer
+    Region & R = *it->second;
+    cudaSetDevice(c->device);
+    std::vector<IndexSlot> u(R.dev_n_keys);
+    CUDA_TRY(cudaMemcpy(u.data(), R.idx.uniq, u.size() * sizeof(IndexSlot), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(labels, R.idx.labels, R.dev_n_labels * sizeof(gtb_label), cudaMemcpyDeviceToHost));
+    label_off[0] = 0;
+    for (size_t i = 0; i < u.size(); ++i)
+    {
+      keys[i] = u[i].key;
+      if (u[i].off != label_off[i])
+        return fail(GTB_ERR_STATE, "device index: distinct k-mer slots are not contiguous");
+      label_off[i + 1] = u[i].off + u[i].cnt;
+    }
+    return 0;
+  }
   std::vector<uint64_t> k;
   std::vector<uint32_t> lo;
   std::vector<gtb_label> ll;
@@ -1250,6 +1530,16 @@ int gtb_set_chunks(gtb_ctx * ctx, int n_chunks)
   if (!c || n_chunks < 0 || n_chunks > MAX_CHUNKS)
     return fail(GTB_ERR_ARG, "n_chunks must be 0..4");
   c->forced_chunks = n_chunks;
+  return 0;
+}
+
+// 1 (default): region indexes are built on the device; 0: by the host builder (gtb_index_host.hpp).
+int gtb_set_index_build(gtb_ctx * ctx, int on_device)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c)
+    return fail(GTB_ERR_ARG, "null ctx");
+  c->index_build_device = on_device ? 1 : 0;
   return 0;
 }
 

@@ -169,6 +169,49 @@ void launch_score(const LaunchParams & p, void * stream);
 int align_kernel_blocks_per_sm();
 size_t align_spill_bytes();
 
+// device-side index build (gtb_index_dev.cu): one descriptor per region of a gtb_region_begin_multi call
+struct IdxRegion
+{
+  uint32_t n_ref, n_var, n_sp_keys, n_sweep;
+  const uint32_t * ref_order;
+  const uint32_t * ref_seq_off;
+  const uint32_t * ref_var_off;
+  const uint32_t * var_order;
+  const uint32_t * var_seq_off;
+  const uint32_t * var_out_ref;
+  const uint8_t * seq;
+  const uint32_t * sp_keys;
+  const uint32_t * sp_off;
+  const uint32_t * sp_list;
+  const uint32_t * var_ev_off;  // null when the graph has no events
+  const int64_t * var_ev;
+  const uint32_t * var_aev_off;
+  const int64_t * var_aev;
+  const uint32_t * sweep_node;    // [n_sweep] (is_var << 31) | node id, in the reference's sweep order
+  const uint32_t * sweep_job_off; // [n_sweep + 1] first END position (= base) of each node
+  // outputs, in the region's index arena
+  DevLabel * labels;
+  IndexSlot * uniq;
+  IndexSlot * table;
+  uint32_t * bitmap;
+  uint32_t table_mask;
+  int table_shift;
+};
+void idx_launch_count(const IdxRegion * regions, uint32_t n_regions, const uint32_t * region_job_off, uint32_t total_jobs,
+                      uint32_t * job_cnt, uint32_t * err, void * stream);
+size_t idx_scan_temp_bytes(uint32_t n);
+int idx_exclusive_scan(void * temp, size_t temp_bytes, const uint32_t * in, uint32_t * out, uint32_t n, void * stream);
+void idx_launch_region_totals(const uint32_t * job_off, const uint32_t * region_job_off, uint32_t n_regions,
+                              uint32_t * region_tuple_off, void * stream);
+void idx_launch_emit(const IdxRegion * regions, uint32_t n_regions, const uint32_t * region_job_off, uint32_t total_jobs,
+                     const uint32_t * job_off, uint64_t * keys, DevLabel * labels, uint32_t * tuple_idx, uint32_t * err, void * stream);
+size_t idx_sort_temp_bytes(uint32_t total, uint32_t n_regions);
+int idx_sort(void * temp, size_t temp_bytes, const uint64_t * keys_in, uint64_t * keys_out, const uint32_t * idx_in, uint32_t * idx_out,
+             uint32_t total, uint32_t n_regions, const uint32_t * region_tuple_off, void * stream);
+void idx_launch_group(const IdxRegion * regions, const uint64_t * skeys, const uint32_t * sidx, const DevLabel * labels_emit,
+                      uint32_t * head, uint32_t * head_incl, void * scan_temp, size_t scan_temp_bytes, const uint32_t * region_tuple_off,
+                      uint32_t n_regions, uint32_t total, uint32_t * region_n_uniq, void * stream);
+
 // discovery re-alignment (gtb_sw.cu)
 struct SwParams
 {

@@ -23,7 +23,7 @@ EXPORTS = [
     "gtb_pool_finish", "gtb_pool_finish_multi", "gtb_pool_reset_multi", "gtb_submit_reads_multi", "gtb_debug_enable", "gtb_debug_seed_sizes", "gtb_debug_seeds",
     "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_scan_calls", "gtb_merge_varstats", "gtb_replay_last",
     "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_set_chunks", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators", "gtb_allreduce_accumulators_multi", "gtb_debug_counters",
-    "gtb_sw_align_batch", "gtb_sw_last_timing", "gtb_sw_replay_last",
+    "gtb_sw_align_batch", "gtb_sw_last_timing", "gtb_sw_replay_last", "gtb_set_index_build",
 ]
 
 
@@ -88,6 +88,7 @@ def load_library() -> C.CDLL:
     L.gtb_sw_align_batch.argtypes = [vp, C.c_int, abi.u8p, abi.i32p, abi.u8p, abi.i32p, C.c_void_p]
     L.gtb_sw_last_timing.argtypes = [vp, fp, fp, fp]
     L.gtb_sw_replay_last.argtypes = [vp]
+    L.gtb_set_index_build.argtypes = [vp, C.c_int]
     _lib = L
     return L
 
@@ -193,6 +194,10 @@ class Context:
     def pool_begin(self, region_id: int, n_samples: int) -> None:
         self._check(self.lib.gtb_pool_begin(self.h, region_id, n_samples))
         self._samples[region_id] = n_samples
+
+    def set_index_build(self, on_device: bool) -> None:
+        """Device-side (default) or host-side construction of the region k-mer indexes."""
+        self._check(self.lib.gtb_set_index_build(self.h, 1 if on_device else 0))
 
     def set_chunks(self, n: int) -> None:
         self._check(self.lib.gtb_set_chunks(self.h, n))

@@ -215,6 +215,10 @@ int gtb_last_kernel_timing(gtb_ctx *ctx, float *probe_ms, float *chain_ms, float
 int gtb_pool_reset(gtb_ctx *ctx, int region_id);
 /* Pipeline chunks of gtb_submit_reads_multi: staging of chunk k+1 overlaps copy + kernels of chunk k (0 = automatic). */
 int gtb_set_chunks(gtb_ctx *ctx, int n_chunks);
+/* Where gtb_region_begin(_multi) builds the k-mer index (replaces index_graph, src/index/indexer.cpp:246-291):
+ * 1 (default with a CUDA device) = on the device, all regions of a call in one launch sequence; 0 = host builder.
+ * Both produce the same index (keys, labels, bucket order).  Environment override: GTB_INDEX_BUILD=host|device. */
+int gtb_set_index_build(gtb_ctx *ctx, int on_device);
 /* Page-locked host memory: batch columns (seq4 above all) placed here are DMA-ed without a staging copy. */
 int gtb_host_alloc(size_t bytes, void **out);
 /* Diagnostics: out24[0..11] why chain_kernel re-queued tasks for slow_kernel, out24[12..23] slow_kernel overflows. */

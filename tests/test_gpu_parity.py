@@ -242,3 +242,46 @@ def test_input_errors_are_reported(ctx):
         assert e.value.code == -1
     finally:
         ctx.region_end(22)
+
+
+def test_device_index_build_equals_host_builder_and_reference(ctx):
+    """N2: the index built on the device (default) equals the host builder's and the reference's golden index -- keys,
+    label lists and bucket order -- one region at a time and all regions of a call in one launch sequence."""
+    pres = ALL
+    graphs = [abi.HostGraph.from_gtba(gtba.load(p + ".graph.gtba")) for p in pres]
+    ids = list(range(100, 100 + len(pres)))
+    ctx.set_index_build(True)
+    ctx.region_begin_multi(ids, graphs)
+    dev = [ctx.index_export(i) for i in ids]
+    for i in ids:
+        ctx.region_end(i)
+    ctx.set_index_build(False)
+    try:
+        ctx.region_begin_multi(ids, graphs)
+        host = [ctx.index_export(i) for i in ids]
+        for i in ids:
+            ctx.region_end(i)
+    finally:
+        ctx.set_index_build(True)
+    for pre, d, h in zip(pres, dev, host):
+        compare.compare_index(gtba.load(pre + ".index.gtba"), d)
+        for k in ("keys", "label_off", "labels"):
+            assert np.array_equal(d[k], h[k]), (pre, k)
+
+
+def test_host_built_index_still_drives_the_kernels(ctx):
+    pre = ALL[0]
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    rd = gtba.load(pre + ".reads.gtba")
+    b = abi.batch_from_probe(rd)
+    pa = gtba.load(pre + ".accum.gtba")
+    ctx.set_index_build(False)
+    try:
+        ctx.region_begin(7, g)
+        ctx.pool_begin(7, n_samples_of(rd))
+        ctx.submit(7, b)
+        acc = ctx.pool_finish(7)
+        compare.compare_accum(compare.probe_accum(pa), acc.as_dict(), "cuda/host-index")
+    finally:
+        ctx.set_index_build(True)
+        ctx.region_end(7)
