@@ -34,6 +34,15 @@ class Site:
     pos: int  # 1-based VCF POS
     ref: bytes
     alt: bytes
+    more_alts: Tuple[bytes, ...] = ()  # further ALT alleles of a multi-allelic record (allele index 2, 3, ...)
+    info: str = "."                    # VCF INFO (GT_ID / GT_ANTI_HAPLOTYPE events, constructor.cpp:1540-1590)
+
+    def allele(self, a: int) -> bytes:
+        return self.ref if a == 0 else (self.alt if a == 1 else self.more_alts[a - 2])
+
+    @property
+    def n_alleles(self) -> int:
+        return 2 + len(self.more_alts)
 
 
 @dataclasses.dataclass
@@ -96,6 +105,83 @@ def make_sites(ref: np.ndarray, n_sites: int, seed: int = 12, grid: int = 12, ma
     return sites
 
 
+def make_sites_complex(ref: np.ndarray, n_sites: int, seed: int = 12, grid: int = 24, margin: int = 200) -> List[Site]:
+    """Sites that exercise what the biallelic generator cannot: multi-allelic SNPs and indels (bubbles with 3-4 alleles),
+    records overlapping an earlier deletion, adjacent records (empty reference nodes between bubbles) and haplotype
+    events (INFO GT_ID / GT_ANTI_HAPLOTYPE -> VarNode::events / anti_events, used by the index build,
+    src/index/indexer.cpp:114-131).  n_sites counts anchor positions; companions add more records."""
+    rng = np.random.default_rng(seed)
+    L = len(ref)
+    first = (margin // grid + 1) * grid
+    last = ((L - margin) // grid) * grid
+    grid_pos = np.arange(first, last, grid)
+    if n_sites > len(grid_pos):
+        raise ValueError("too many sites for the grid")
+    chosen = np.sort(rng.choice(grid_pos, size=n_sites, replace=False))
+    sites: List[Site] = []
+    event_id = 0
+
+    def other(base: int, k: int) -> List[bytes]:
+        alts = [b for b in b"ACGT" if b != base]
+        order = rng.permutation(3)[:k]
+        return [bytes([alts[int(i)]]) for i in order]
+
+    def rand_seq(n: int) -> bytes:
+        return bytes(BASES[rng.integers(0, 4, size=n)])
+
+    for p in chosen.tolist():
+        r = int(ref[p - 1])
+        k = rng.random()
+        if k < 0.25:  # multi-allelic SNP
+            a = other(r, int(rng.integers(2, 4)))
+            sites.append(Site(p, bytes([r]), a[0], tuple(a[1:])))
+        elif k < 0.35:  # two insertions of different length at one anchor
+            i1, i2 = rand_seq(int(rng.integers(1, 4))), rand_seq(int(rng.integers(4, 8)))
+            sites.append(Site(p, bytes([r]), bytes([r]) + i1, (bytes([r]) + i2,)))
+        elif k < 0.43:  # deletion and a shorter deletion / SNP in one record
+            n = int(rng.integers(3, 7))
+            refa = bytes(ref[p - 1:p + n])
+            snp = bytearray(refa)
+            snp[-1] = other(snp[-1], 1)[0][0]
+            sites.append(Site(p, refa, bytes([r]), (refa[:2], bytes(snp))))
+        elif k < 0.53:  # deletion, then a separate SNP record inside the deleted span
+            n = int(rng.integers(3, 7))
+            sites.append(Site(p, bytes(ref[p - 1:p + n]), bytes([r])))
+            q = p + int(rng.integers(1, n + 1))
+            sites.append(Site(q, bytes([int(ref[q - 1])]), other(int(ref[q - 1]), 1)[0]))
+        elif k < 0.63:  # adjacent SNP records
+            sites.append(Site(p, bytes([r]), other(r, 1)[0]))
+            sites.append(Site(p + 1, bytes([int(ref[p])]), other(int(ref[p]), 1)[0]))
+        elif k < 0.78:  # event pair within one k-mer: the later alt may not follow the earlier alt (or the reverse order)
+            event_id += 1
+            q = p + int(rng.integers(2, 12))
+            first_info, second_info = (f"GT_ANTI_HAPLOTYPE={event_id}", f"GT_ID={event_id}")
+            if rng.random() < 0.3:
+                first_info, second_info = second_info, first_info
+            sites.append(Site(p, bytes([r]), other(r, 1)[0], (), first_info))
+            sites.append(Site(q, bytes([int(ref[q - 1])]), other(int(ref[q - 1]), 1)[0], (), second_info))
+        elif k < 0.9:
+            sites.append(Site(p, bytes([r]), other(r, 1)[0]))
+        else:
+            n = int(rng.integers(1, 7))
+            if rng.random() < 0.5:
+                sites.append(Site(p, bytes(ref[p - 1:p + n]), bytes([r])))
+            else:
+                sites.append(Site(p, bytes([r]), bytes([r]) + rand_seq(n)))
+    sites.sort(key=lambda s: s.pos)
+    return sites
+
+
+def make_genotypes_complex(sites: List[Site], n_samples: int, seed: int = 13) -> np.ndarray:
+    """[n_samples, n_sites, 2] allele indices, uniform over each site's alleles (reference twice as likely)."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n_samples, len(sites), 2), dtype=np.int8)
+    for i, s in enumerate(sites):
+        choices = [0] + list(range(s.n_alleles))
+        out[:, i, :] = rng.choice(choices, size=(n_samples, 2))
+    return out
+
+
 def make_genotypes(n_sites: int, n_samples: int, seed: int = 13) -> np.ndarray:
     """[n_samples, n_sites, 2] allele indices; uniform over {0/0, 0/1, 0/1, 1/1}, hets randomly phased."""
     rng = np.random.default_rng(seed)
@@ -117,9 +203,11 @@ def build_haplotype(ref: np.ndarray, sites: List[Site], alleles: np.ndarray) -> 
         if not a:
             continue
         p0 = s.pos - 1
+        if p0 < cur:
+            continue  # overlapped by an allele already applied (complex fixtures: a deletion spanning a later record)
         pieces.append(ref[cur:p0])
         pos_pieces.append(np.arange(cur, p0, dtype=np.int64))
-        alt = np.frombuffer(s.alt, dtype=np.uint8)
+        alt = np.frombuffer(s.allele(int(a)), dtype=np.uint8)
         pieces.append(alt)
         pp = np.full(len(alt), -1, dtype=np.int64)
         n_al = min(len(s.ref), len(alt))  # anchor (and SNP base) stay aligned
@@ -293,7 +381,8 @@ def write_vcf(path: str, sites: List[Site], contig: str = "chr1", contig_len: in
             hdr += "\tFORMAT\t" + "\t".join(samples)
         f.write(hdr + "\n")
         for i, s in enumerate(sites):
-            line = f"{contig}\t{s.pos}\t.\t{s.ref.decode()}\t{s.alt.decode()}\t.\t.\t."
+            alts = ",".join(a.decode() for a in (s.alt,) + tuple(s.more_alts))
+            line = f"{contig}\t{s.pos}\t.\t{s.ref.decode()}\t{alts}\t.\t.\t{s.info}"
             if samples:
                 line += "\tGT\t" + "\t".join(f"{int(gts[k, i, 0])}/{int(gts[k, i, 1])}" for k in range(len(samples)))
             f.write(line + "\n")
@@ -337,10 +426,15 @@ class Dataset:
 
 def make_dataset(length: int, n_sites: int, n_samples: int = 1, seed: int = 11, coverage: float = 30.0,
                  err: float = 0.002, n_rate: float = 0.0, lowmapq_rate: float = 0.0, unpaired_rate: float = 0.0,
-                 improper_rate: float = 0.0, flip_rate: float = 0.0, read_len: int = 150) -> Dataset:
+                 improper_rate: float = 0.0, flip_rate: float = 0.0, read_len: int = 150,
+                 complex_sites: bool = False) -> Dataset:
     ref = make_reference(length, seed)
-    sites = make_sites(ref, n_sites, seed + 1)
-    gts = make_genotypes(n_sites, n_samples, seed + 2)
+    if complex_sites:
+        sites = make_sites_complex(ref, n_sites, seed + 1)
+        gts = make_genotypes_complex(sites, n_samples, seed + 2)
+    else:
+        sites = make_sites(ref, n_sites, seed + 1)
+        gts = make_genotypes(n_sites, n_samples, seed + 2)
     samples = [f"SAMP{k + 1}" for k in range(n_samples)]
     reads = [simulate_reads(ref, sites, gts[k], samples[k], seed + 100 + k, coverage=coverage, err=err,
                             n_rate=n_rate, lowmapq_rate=lowmapq_rate, unpaired_rate=unpaired_rate,

@@ -27,6 +27,8 @@ SMALL = {
     "mini_stress": (dict(length=8000, n_sites=160, n_samples=3, seed=21, coverage=12, err=0.01, n_rate=0.002,
                          lowmapq_rate=0.1, unpaired_rate=0.05, improper_rate=0.08, flip_rate=0.5), 50000),
     "mini_r100": (dict(length=6000, n_sites=40, n_samples=1, seed=31, coverage=20, err=0.004, read_len=100), 50000),
+    # multi-allelic bubbles, overlapping / adjacent records, GT_ID / GT_ANTI_HAPLOTYPE events
+    "mini_complex": (dict(length=7000, n_sites=90, n_samples=2, seed=91, coverage=14, err=0.004, complex_sites=True), 50000),
 }
 # structural-variant fixtures (genotype_sv flow, is_sv_graph = true): kwargs of the SV generator below
 SMALL_SV = {
@@ -42,6 +44,8 @@ BIG = {
                     lowmapq_rate=0.1, unpaired_rate=0.05, improper_rate=0.08, flip_rate=0.5), 50000),
     "r100": (dict(length=20000, n_sites=150, n_samples=1, seed=31, coverage=25, err=0.004, read_len=100), 50000),
     "dense": (dict(length=20000, n_sites=1200, n_samples=2, seed=41, coverage=20, err=0.006, n_rate=0.001), 50000),
+    "complex": (dict(length=40000, n_sites=700, n_samples=3, seed=93, coverage=18, err=0.005, n_rate=0.0005,
+                     complex_sites=True), 50000),
 }
 
 
@@ -98,12 +102,15 @@ def run_sv(name: str, kw: dict, out_dir: str) -> None:
 
 def main() -> None:
     big = "--big" in sys.argv
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
     out_dir = os.path.join(ROOT, "tests", "data_local" if big else "golden")
     os.makedirs(out_dir, exist_ok=True)
     for name, (kw, rs) in (BIG if big else SMALL).items():
-        run(name, kw, rs, out_dir)
+        if not only or name in only:
+            run(name, kw, rs, out_dir)
     for name, kw in (BIG_SV if big else SMALL_SV).items():
-        run_sv(name, kw, out_dir)
+        if not only or name in only:
+            run_sv(name, kw, out_dir)
 
 
 if __name__ == "__main__":
