@@ -160,6 +160,17 @@ def make_sites_complex(ref: np.ndarray, n_sites: int, seed: int = 12, grid: int 
                 first_info, second_info = second_info, first_info
             sites.append(Site(p, bytes([r]), other(r, 1)[0], (), first_info))
             sites.append(Site(q, bytes([int(ref[q - 1])]), other(int(ref[q - 1]), 1)[0], (), second_info))
+        elif k < 0.83:  # STR-like site: many insertion alleles (5-14 alts) -> the 181-combination limit of the index
+            n_alt = int(rng.integers(5, 15))
+            unit = rand_seq(int(rng.integers(1, 4)))
+            alts = []
+            for j in range(n_alt):
+                a = bytes([r]) + unit * (j + 1)
+                if rng.random() < 0.4:
+                    a = a + rand_seq(1)
+                if a not in alts:
+                    alts.append(a)
+            sites.append(Site(p, bytes([r]), alts[0], tuple(alts[1:])))
         elif k < 0.9:
             sites.append(Site(p, bytes([r]), other(r, 1)[0]))
         else:
