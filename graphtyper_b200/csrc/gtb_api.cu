@@ -168,7 +168,7 @@ struct Ctx
   DeviceBuffer d_regions;       // DevRegion table
   bool regions_dirty = true;
   // batch
-  DeviceBuffer d_tap_counts, d_tap_pool, d_spill;
+  DeviceBuffer d_tap_counts, d_tap_pool, d_spill, d_huge;
   std::vector<DeviceBuffer> buffer_cache; // arenas / accumulators of ended regions, reused by the next regions
   PinnedBuffer h_stage, h_accum;
   bool have_last = false;
@@ -444,6 +444,7 @@ void gtb_destroy(gtb_ctx * ctx)
     c->d_tap_counts.release();
     c->d_tap_pool.release();
     c->d_spill.release();
+    c->d_huge.release();
     c->h_stage.release();
     c->h_accum.release();
     for (DeviceBuffer * b : {&c->d_idx_small, &c->d_idx_jobs, &c->d_idx_keys, &c->d_idx_keys2, &c->d_idx_labels, &c->d_idx_idx,
@@ -1104,7 +1105,7 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     n_overflow += kc->n_overflow;
     n_input_error += kc->n_input_error;
     for (int q = 0; q < 12; ++q)
-      reasons[q] += kc->reasons[q];
+      reasons[q] += kc->final_reasons[q];
   }
   c->t_align = c->t_probe + c->t_chain + c->t_slow;
   if (stats)
@@ -1312,7 +1313,7 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   uint32_t const n_tasks = n_units * 2;
   if (int rc = B.d_seedrecs.reserve((size_t)n_active * SEED_REC_BYTES + 64))
     return rc;
-  if (int rc = B.d_slow.reserve((size_t)n_active * 4 + 64))
+  if (int rc = B.d_slow.reserve((size_t)n_active * 8 + 128))
     return rc;
   if (int rc = B.d_summaries.reserve((size_t)n_tasks * sizeof(TaskSummary) + 16))
     return rc;
@@ -1320,6 +1321,8 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   if (int rc = B.d_pool.reserve(pool_words * 4))
     return rc;
   if (int rc = B.d_counters.reserve(sizeof(DevCounters)))
+    return rc;
+  if (int rc = c->d_huge.reserve(huge_state_bytes()))
     return rc;
   if (int rc = c->d_spill.reserve(align_spill_bytes()))
     return rc;
@@ -1362,6 +1365,8 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   P.active_tasks = reinterpret_cast<const uint32_t *>(d + o_active);
   P.seed_recs = B.d_seedrecs.p;
   P.slow_tasks = static_cast<uint32_t *>(B.d_slow.p);
+  P.huge_tasks = P.slow_tasks + n_active + 16;
+  P.huge_states = c->d_huge.p;
   if (with_tap)
   {
     size_t const tap_counts = (size_t)n_tasks * (NLISTS * 2 + 1) * 4;

@@ -20,6 +20,10 @@ constexpr int CAND_V = 16;    // var nodes per candidate
 constexpr int MAXLOC = 8;     // graph locations of a position (reference limit: 256)
 constexpr int WL_CAP = 96;    // labels staged by one walk_read_starts/ends call
 constexpr int MAX_SEQ = 152;  // bases per read (GTB_SEQ_STRIDE * 2)
+// huge_kernel (third tier, one warp per task, working set in a per-warp global-memory slab): the reference's own limits.
+// 512 paths (walks stop above 256, constants.hpp.in:43), 48 bubbles per path, 640 open candidates (reference: 128 + one
+// round of growth), 40 locations of a position (<= 32 alleles per bubble + the reference node), 2048 staged labels.
+constexpr int HUGE_P = 512, HUGE_V = 48, HUGE_C = 640, HUGE_CV = 48, HUGE_WL = 2048, HUGE_LOC = 40, HUGE_REFS = 2048;
 // chain_kernel (one thread per read orientation, working set in local memory) -- small capacities, overflow -> slow_kernel
 constexpr int FAST_P = 6, FAST_V = 8, FAST_C = 6, FAST_CV = 8, FAST_WL = 12, FAST_LOC = 4;
 constexpr int SEED_INLINE = 10;     // index bucket references handed from probe_kernel to chain_kernel per task
@@ -27,7 +31,7 @@ constexpr int SEED_REC_BYTES = 16 + 8 * SEED_INLINE;
 constexpr int PROBE_WARPS = 8;      // warps per block of probe_kernel
 constexpr int CHAIN_THREADS = 128;  // threads per block of chain_kernel
 constexpr int CHAIN_MIN_BLOCKS = 8;  // <= 64 registers per thread
-constexpr int MAX_TOUCH = 16; // bubbles touched by one read in the accumulate kernel
+constexpr int MAX_TOUCH = 48; // bubbles touched by one read in the accumulate kernel (= HUGE_V)
 using allele_mask_t = uint32_t; // allele set of one bubble on a path: bit a = allele a  (<= 32 alleles per bubble)
 constexpr int MAX_ALLELES = 32;
 
@@ -130,7 +134,9 @@ struct DevCounters
   unsigned long long dbg_label_words; // bump cursor of the debug seed pool
   unsigned long long n_slow;         // tasks queued for slow_kernel
   unsigned long long fast_reasons[12]; // why chain_kernel handed a task to slow_kernel (same codes; [11] = probe flag)
-  unsigned long long reasons[12];    // overflow histogram: refs vars paths locs labels candv cands keys tap pool len -
+  unsigned long long reasons[12];    // why slow_kernel handed a task to huge_kernel: refs vars paths locs labels candv cands keys tap pool len -
+  unsigned long long n_huge;         // tasks queued for huge_kernel
+  unsigned long long final_reasons[12]; // capacity overflows nothing could hold (reported as GTB_ERR_CAPACITY)
 };
 
 // Debug tap of the seed stage: per task, per list (slot*2 + ham): count and offset into a label pool
@@ -157,6 +163,8 @@ struct LaunchParams
   const uint32_t * active_tasks; // [n_active] task id = unit * 2 + orientation
   void * seed_recs;             // [n_active] SeedRec
   uint32_t * slow_tasks;        // [n_active] queue filled by chain_kernel
+  uint32_t * huge_tasks;        // [n_active] queue filled by slow_kernel
+  void * huge_states;           // [SM count] HugeState slabs
 };
 
 // host launchers (gtb_kernels.cu)
@@ -168,6 +176,7 @@ void launch_slow(const LaunchParams & p, void * stream);
 void launch_score(const LaunchParams & p, void * stream);
 int align_kernel_blocks_per_sm();
 size_t align_spill_bytes();
+size_t huge_state_bytes();
 
 // device-side index build (gtb_index_dev.cu): one descriptor per region of a gtb_region_begin_multi call
 struct IdxRegion

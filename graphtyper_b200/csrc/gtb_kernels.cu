@@ -94,19 +94,27 @@ struct StateT
   uint32_t overflow;
 };
 
-struct SlowState : StateT<MAXP, MAXV, CAND_CAP, CAND_V, WL_CAP, MAXLOC>
+// Warp-per-task working set: SlowState lives in shared memory (13 KB), HugeState in a per-warp global-memory slab with
+// the reference's own limits as capacities (third tier, for reads the shared-memory state cannot hold).
+template <int P_, int V_, int C_, int CV_, int WL_, int LOC_, int SPILL_, int REFS_>
+struct WarpStateT : StateT<P_, V_, C_, CV_, WL_, LOC_>
 {
-  static constexpr int CAND_TOTAL = CAND_CAP + CAND_SPILL;
-  uint2 refs[REF_CAP];
+  using Base = StateT<P_, V_, C_, CV_, WL_, LOC_>;
+  using Cand = typename Base::Cand;
+  static constexpr int CAND_TOTAL = C_ + SPILL_;
+  static constexpr int REFCAP = REFS_;
+  uint2 refs[REFS_];
   uint16_t list_start[NLISTS + 1];
   uint8_t seq[MAX_SEQ + 8]; // 4-bit codes in phase A, IUPAC characters afterwards
-  Cand * cand_spill;        // this warp's global-memory extension of cands[] (CAND_SPILL entries)
+  Cand * cand_spill;        // this warp's global-memory extension of cands[] (SPILL_ entries)
   __device__ __forceinline__ uint8_t rd(int j) const { return seq[j]; }
   __device__ __forceinline__ void prepare(int, int) {} // the whole read is already decoded in seq[]
-  // candidate i of the bubble expansion: the first CAND_CAP live in shared memory, the (rare) rest in a per-warp
+  // candidate i of the bubble expansion: the first C_ live in the state itself, the (rare) rest in a per-warp
   // global scratch area, so that the reference's limit of 128 open candidates (+ one round of growth) fits
-  __device__ __forceinline__ Cand & cand_at(int i) { return i < CAND_CAP ? cands[i] : cand_spill[i - CAND_CAP]; }
+  __device__ __forceinline__ Cand & cand_at(int i) { return (SPILL_ == 0 || i < C_) ? this->cands[i] : cand_spill[i - C_]; }
 };
+using SlowState = WarpStateT<MAXP, MAXV, CAND_CAP, CAND_V, WL_CAP, MAXLOC, CAND_SPILL, REF_CAP>;
+using HugeState = WarpStateT<HUGE_P, HUGE_V, HUGE_C, HUGE_CV, HUGE_WL, HUGE_LOC, 0, HUGE_REFS>;
 
 struct FastState : StateT<FAST_P, FAST_V, FAST_C, FAST_CV, FAST_WL, FAST_LOC>
 {
@@ -131,7 +139,6 @@ struct FastState : StateT<FAST_P, FAST_V, FAST_C, FAST_CV, FAST_WL, FAST_LOC>
   __device__ __forceinline__ Cand & cand_at(int i) { return cands[i]; }
 };
 
-using WS = SlowState;
 
 __device__ __constant__ char IUPAC_CHAR[17] = "UACMGRSVTWYHKDBN";
 
@@ -206,8 +213,8 @@ __device__ __forceinline__ bool probe(const DevRegion & R, uint64_t key, uint32_
 
 // Appends the bucket references of `nk` keys (key k produced by keyfn(k)) to S.refs in key order, applying the
 // "more than 75 labels while probing several keys => give the slot up" rule of PHIndex::multi_get.
-template <typename KeyFn>
-__device__ void query_list(WS & S, const DevRegion & R, KeyFn keyfn, int nk, bool multi, int lane, int & nrefs)
+template <class WST, typename KeyFn>
+__device__ void query_list(WST & S, const DevRegion & R, KeyFn keyfn, int nk, bool multi, int lane, int & nrefs)
 {
   int const start = nrefs;
   uint32_t total = 0;
@@ -235,14 +242,14 @@ __device__ void query_list(WS & S, const DevRegion & R, KeyFn keyfn, int nk, boo
     }
     unsigned const fm = __ballot_sync(FULL, found);
     int const pos = nrefs + __popc(fm & ((1u << lane) - 1u));
-    if (found && pos < REF_CAP)
+    if (found && pos < WST::REFCAP)
       S.refs[pos] = make_uint2(off, cnt);
     nrefs += __popc(fm);
     total += __shfl_sync(FULL, inc, 31);
   }
   if (dropped)
     nrefs = start;
-  if (nrefs > REF_CAP)
+  if (nrefs > WST::REFCAP)
   {
     if (lane == 0)
       S.overflow |= OV_REFS;
@@ -1046,7 +1053,11 @@ __device__ void walk(W & S, const GR & g, uint32_t L, bool forward)
 {
   if (S.npaths == 0 || psize(S.paths[0]) == L)
     return;
-  // MAX_SEED_NUMBER_FOR_WALKING (256) / _ALLOWING_MISMATCHES (64) can never be reached with MAXP paths
+  // MAX_SEED_NUMBER_FOR_WALKING (256): no walk at all; MAX_SEED_NUMBER_ALLOWING_MISMATCHES (64): exact matches only
+  // (genotype_paths.cpp:488-492,560-564; constants.hpp.in:42-43).  Only the huge tier can hold that many paths.
+  if (W::MAXP > 256 && S.npaths > 256)
+    return;
+  bool const exact_only = W::MAXP > 64 && S.npaths > 64;
   {
     // read window this walk can touch: [min read_end_index, L) forwards, [0, max read_start_index] backwards
     int from = (int)L, to = 0;
@@ -1089,7 +1100,7 @@ __device__ void walk(W & S, const GR & g, uint32_t L, bool forward)
     }
     if (nloc == 0)
       continue;
-    uint32_t mm = min(2u + klen / 11u, best_mm);
+    uint32_t mm = exact_only ? 0u : min(2u + klen / 11u, best_mm);
     // iterative_dfs (graph.cpp:1703-1754)
     int const pend0 = committed;
     int pend1 = committed;
@@ -1620,22 +1631,19 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(
 }
 
 // ================================================================================================ slow kernel
-// One warp per queued task, big shared-memory working set, lane 0 runs the scalar logic.  Handles seeds with
-// IUPAC/N bases (key expansion, type_conversions.cpp:207-266) and everything chain_kernel's capacities cannot hold.
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) slow_kernel(LaunchParams P)
+// One warp per queued task, lane 0 runs the scalar logic.  Handles seeds with IUPAC/N bases (key expansion,
+// type_conversions.cpp:207-266) and everything the previous tier's capacities cannot hold.  Two instances:
+//   slow_kernel : SlowState in shared memory; a task that still overflows is queued for huge_kernel
+//   huge_kernel : HugeState in a per-warp global slab, capacities = the reference's own limits; an overflow here is final
+template <class WST, bool LAST>
+__device__ void warp_tier(const LaunchParams & P, WST & S, int lane, uint32_t warp_global, uint32_t total_warps,
+                          const uint32_t * queue, uint32_t n_queued)
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  WS * all = reinterpret_cast<WS *>(smem_raw);
-  int const lane = threadIdx.x & 31;
-  int const wib = threadIdx.x >> 5;
-  WS & S = all[wib];
-  int const total_warps = gridDim.x * WARPS_PER_BLOCK;
-  uint32_t const n_slow = (uint32_t)P.counters->n_slow;
   uint32_t const n_tasks = P.batch.n_units * 2;
 
-  for (uint32_t si = blockIdx.x * WARPS_PER_BLOCK + wib; si < n_slow; si += total_warps)
+  for (uint32_t si = warp_global; si < n_queued; si += total_warps)
   {
-    uint32_t const task = P.slow_tasks[si];
+    uint32_t const task = queue[si];
     uint32_t const unit = task >> 1;
     int const orient = task & 1;
     int const rec = P.batch.unit_record[unit];
@@ -1657,7 +1665,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) slow_kernel(LaunchParams
       if (lane == 0)
       {
         S.overflow = 0;
-        S.cand_spill = static_cast<WS::Cand *>(P.cand_spill) + (size_t)(blockIdx.x * WARPS_PER_BLOCK + wib) * CAND_SPILL;
+        S.cand_spill = LAST ? nullptr : reinterpret_cast<typename WST::Cand *>(P.cand_spill) + (size_t)warp_global * CAND_SPILL;
         S.npaths = 0;
         S.npp = 0;
         S.longest = 0;
@@ -1693,7 +1701,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) slow_kernel(LaunchParams
         int nk = 0;
         if (lane == 0)
         {
-          nk = expand_keys(S.seq + 31 * i, keys, (int)(sizeof(WS::Path) * MAXP * 2 / sizeof(uint64_t)));
+          nk = expand_keys(S.seq + 31 * i, keys, (int)(sizeof(typename WST::Path) * WST::MAXP * 2 / sizeof(uint64_t)));
           if (nk < 0)
           {
             S.overflow |= OV_KEYS;
@@ -1710,7 +1718,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) slow_kernel(LaunchParams
         __syncwarp();
         // a slot without a unique exact key gets no Hamming-1 keys: the same keys are queried again
         int const cnt = nrefs - before;
-        if (nrefs + cnt > REF_CAP)
+        if (nrefs + cnt > WST::REFCAP)
         {
           if (lane == 0)
             S.overflow |= OV_REFS;
@@ -1737,7 +1745,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) slow_kernel(LaunchParams
       if (P.tap.list_count && !write_seed_tap(P, R, task, S.refs, S.list_start, nslots))
         S.overflow |= OV_TAP;
       run_task(S, g, S.refs, S.list_start, nslots, L);
-      if (S.overflow)
+      if (S.overflow && !LAST && !(S.overflow & (OV_TAP | OV_LEN)))
+      {
+        // the next tier has room for it
+        for (int q = 0; q < 12; ++q)
+          if ((S.overflow >> q) & 1u)
+            atomicAdd(&P.counters->reasons[q], 1ull);
+        unsigned long long const hi = atomicAdd(&P.counters->n_huge, 1ull);
+        P.huge_tasks[hi] = task;
+      }
+      else if (S.overflow)
       {
         TaskSummary sum;
         sum.npaths = 0;
@@ -1751,13 +1768,32 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) slow_kernel(LaunchParams
         atomicAdd(&P.counters->n_overflow, 1ull);
         for (int q = 0; q < 12; ++q)
           if ((S.overflow >> q) & 1u)
-            atomicAdd(&P.counters->reasons[q], 1ull);
+            atomicAdd(&P.counters->final_reasons[q], 1ull);
       }
       else
         write_result(S, g, P, task, n_tasks);
     }
     __syncwarp();
   }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) slow_kernel(LaunchParams P)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SlowState * all = reinterpret_cast<SlowState *>(smem_raw);
+  int const wib = threadIdx.x >> 5;
+  warp_tier<SlowState, false>(P, all[wib], threadIdx.x & 31, blockIdx.x * WARPS_PER_BLOCK + wib, gridDim.x * WARPS_PER_BLOCK,
+                              P.slow_tasks, (uint32_t)P.counters->n_slow);
+}
+
+// One warp per block (grid = SM count); exits at once when slow_kernel queued nothing, which is the normal case.
+__global__ void __launch_bounds__(32) huge_kernel(LaunchParams P)
+{
+  uint32_t const n = (uint32_t)P.counters->n_huge;
+  if (n == 0)
+    return;
+  HugeState & S = reinterpret_cast<HugeState *>(P.huge_states)[blockIdx.x];
+  warp_tier<HugeState, true>(P, S, threadIdx.x, blockIdx.x, gridDim.x, P.huge_tasks, n);
 }
 
 // ================================================================================================ score kernel
@@ -2057,6 +2093,68 @@ __device__ void add_ref_depth(const LaunchParams & P, const DevRegion & R, const
     }
     return;
   }
+  if (geno.s.npaths > MAXP)
+  {
+    // (huge tier) more paths than the sorted-interval buffer holds: union by repeated sweeps over the path records, no
+    // storage.  Any exact decomposition of the union gives the same difference array.
+    auto for_each_interval = [&](auto && fn) {
+      const uint32_t * v = w;
+      for (int pi = 0; pi < geno.s.npaths; ++pi)
+      {
+        uint32_t const nvar = v[3] >> 16;
+        long long sp = (long long)g.ref_reach_pos(v[0]) - (long long)(v[2] & 0xFFFFu);
+        long long ep = (long long)g.ref_reach_pos(v[1]) + (RL - 1 - (long long)(v[2] >> 16));
+        v += PATH_HDR_WORDS + 2 * nvar;
+        if (ep - sp >= 50)
+        {
+          sp += 4;
+          ep -= 4;
+        }
+        if (ep < offset)
+          continue;
+        long long const si = sp < offset ? 0 : sp - offset;
+        long long ei = ep > offset + size ? size : ep + 1 - offset;
+        if (si >= size)
+          continue;
+        if (ei < si || ei > size)
+          ei = size;
+        if (ei > si)
+          fn(si, ei);
+      }
+    };
+    long long done = -1; // every index < done is handled
+    for (;;)
+    {
+      long long cs = -1, ce = -1;
+      for_each_interval([&](long long si, long long ei) {
+        if (ei <= done)
+          return;
+        si = max(si, done);
+        if (cs < 0 || si < cs)
+        {
+          cs = si;
+          ce = ei;
+        }
+      });
+      if (cs < 0)
+        return;
+      bool grew = true;
+      while (grew)
+      {
+        grew = false;
+        for_each_interval([&](long long si, long long ei) {
+          if (si <= ce && ei > ce)
+          {
+            ce = ei;
+            grew = true;
+          }
+        });
+      }
+      atomicAdd(delta + cs, 1);
+      atomicAdd(delta + ce, -1);
+      done = ce;
+    }
+  }
   long long iv[MAXP][2];
   int n = 0;
   for (int pi = 0; pi < geno.s.npaths && n < MAXP; ++pi)
@@ -2293,7 +2391,7 @@ int align_kernel_blocks_per_sm()
 {
   if (g_align_blocks_per_sm == 0)
   {
-    size_t const smem = sizeof(WS) * WARPS_PER_BLOCK;
+    size_t const smem = sizeof(SlowState) * WARPS_PER_BLOCK;
     cudaFuncSetAttribute(slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, slow_kernel, WARPS_PER_BLOCK * 32, smem) != cudaSuccess || nb < 1)
@@ -2318,7 +2416,7 @@ static int sm_count()
 
 size_t align_spill_bytes()
 {
-  return (size_t)sm_count() * align_kernel_blocks_per_sm() * WARPS_PER_BLOCK * CAND_SPILL * sizeof(WS::Cand);
+  return (size_t)sm_count() * align_kernel_blocks_per_sm() * WARPS_PER_BLOCK * CAND_SPILL * sizeof(SlowState::Cand);
 }
 
 void launch_probe(const LaunchParams & p, void * stream)
@@ -2342,10 +2440,13 @@ void launch_slow(const LaunchParams & p, void * stream)
 {
   if (p.n_active == 0)
     return;
-  size_t const smem = sizeof(WS) * WARPS_PER_BLOCK;
+  size_t const smem = sizeof(SlowState) * WARPS_PER_BLOCK;
   uint32_t const grid = (uint32_t)(sm_count() * align_kernel_blocks_per_sm());
   slow_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(p);
+  huge_kernel<<<(uint32_t)sm_count(), 32, 0, (cudaStream_t)stream>>>(p);
 }
+
+size_t huge_state_bytes() { return (size_t)sm_count() * sizeof(HugeState); }
 
 void launch_score(const LaunchParams & p, void * stream)
 {

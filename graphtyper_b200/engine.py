@@ -265,6 +265,12 @@ class Context:
     def debug_enable(self, on: bool = True) -> None:
         self._check(self.lib.gtb_debug_enable(self.h, 1 if on else 0))
 
+    def debug_counters(self) -> List[int]:
+        """[0..11] why chain_kernel re-queued tasks for slow_kernel, [12..23] why slow_kernel re-queued for huge_kernel."""
+        out = (C.c_uint64 * 24)()
+        self._check(self.lib.gtb_debug_counters(self.h, out))
+        return [int(x) for x in out]
+
     def debug_seeds(self, region_id: int) -> Dict[str, np.ndarray]:
         nu, ns, nl = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._check(self.lib.gtb_debug_seed_sizes(self.h, region_id, C.byref(nu), C.byref(ns), C.byref(nl)))

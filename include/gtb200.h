@@ -221,7 +221,8 @@ int gtb_set_chunks(gtb_ctx *ctx, int n_chunks);
 int gtb_set_index_build(gtb_ctx *ctx, int on_device);
 /* Page-locked host memory: batch columns (seq4 above all) placed here are DMA-ed without a staging copy. */
 int gtb_host_alloc(size_t bytes, void **out);
-/* Diagnostics: out24[0..11] why chain_kernel re-queued tasks for slow_kernel, out24[12..23] slow_kernel overflows. */
+/* Diagnostics: out24[0..11] why chain_kernel re-queued tasks for slow_kernel, out24[12..23] why slow_kernel re-queued
+ * tasks for huge_kernel (codes: refs vars paths locs labels candv cands keys tap pool len probe-flag). */
 int gtb_debug_counters(gtb_ctx *ctx, uint64_t *out24);
 int gtb_host_free(void *p);
 

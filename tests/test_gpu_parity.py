@@ -285,3 +285,23 @@ def test_host_built_index_still_drives_the_kernels(ctx):
     finally:
         ctx.set_index_build(True)
         ctx.region_end(7)
+
+
+def test_huge_tier_takes_what_the_shared_memory_state_cannot_hold(ctx):
+    """Reads on 15-allele bubbles need more locations / paths than slow_kernel's 13 KB shared-memory state holds: they are
+    re-queued for huge_kernel (global-memory state, the reference's own limits) instead of failing, and the result is
+    still the reference's (test_cuda_matches_reference covers the equality on this fixture)."""
+    pre = [p for p in ALL if os.path.basename(p).startswith("mini_complex")][0]
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    rd = gtba.load(pre + ".reads.gtba")
+    ctx.region_begin(7, g)
+    try:
+        ctx.pool_begin(7, n_samples_of(rd))
+        st = ctx.submit(7, abi.batch_from_probe(rd))
+        assert st.n_capacity_overflow == 0
+        cnt = ctx.debug_counters()
+        assert sum(cnt[12:24]) > 0, "expected slow_kernel -> huge_kernel re-queues on this fixture"
+        acc = ctx.pool_finish(7)
+        compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), acc.as_dict(), "cuda/huge")
+    finally:
+        ctx.region_end(7)
