@@ -1101,7 +1101,7 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     st.n_pairs_scored += kc->n_pairs_scored;
     st.n_singles_scored += kc->n_singles_scored;
     st.n_capacity_overflow += kc->n_overflow;
-    st.kernel_launches += (B.P.n_active ? 3 : 0) + (B.P.batch.n_records ? 1 : 0);
+    st.kernel_launches += (B.P.n_active ? 4 : 0) + (B.P.batch.n_records ? 1 : 0); // probe, chain, slow, huge + score
     n_overflow += kc->n_overflow;
     n_input_error += kc->n_input_error;
     for (int q = 0; q < 12; ++q)
