@@ -42,7 +42,7 @@ N_SITES = 10_000
 REGION = 50_000
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE probe_kernel launch on this workload, from the committed ncu capture
 # profiles/r1_final_ncu_summary.txt (192.2 MB + 13.0 MB; cold L2).  Well below the algorithmic 1.29 GB: the tables are L2-resident.
-PROBE_DRAM_BYTES_PER_LAUNCH = 205_231_616
+PROBE_DRAM_BYTES_PER_LAUNCH = 150_882_048  # ncu dram__bytes_read.sum + dram__bytes_write.sum of one probe_kernel launch (profiles/r1b_ncu_summary.txt)
 
 
 def env_int(name: str, default: int) -> int:
@@ -324,9 +324,13 @@ def main() -> None:
         e2e_times.append(time.perf_counter() - t)
     e2e_t = float(np.mean(e2e_times))
 
-    # ---- device-resident: replay the batch already in HBM, CUDA-event time of the two kernels
+    # ---- device-resident: replay the batch already in HBM, CUDA-event time of the kernels.  With nothing to copy there
+    #      is nothing to overlap, so the batch is resident as ONE launch sequence (the e2e steps above use the library's
+    #      automatic 2-chunk copy/compute pipeline).
+    ctx.set_chunks(1)
     reset()
     ctx.submit_multi(ids, batches)
+    ctx.set_chunks(0)
     for _ in range(max(3, args.warmup)):
         reset()
         ctx.replay()

@@ -406,6 +406,7 @@ int gtb_create(int device_id, gtb_ctx ** out)
       e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess)
       e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+
     for (int k = 0; k < MAX_CHUNKS; ++k)
       for (int i = 0; i < 8 && e == cudaSuccess; ++i)
         e = cudaEventCreate(&c->bs[k].ev[i]);
@@ -460,6 +461,7 @@ void gtb_destroy(gtb_ctx * ctx)
         cudaEventDestroy(e);
     if (c->copy_stream)
       cudaStreamDestroy(c->copy_stream);
+
     if (c->stream)
       cudaStreamDestroy(c->stream);
   }
@@ -784,7 +786,7 @@ static int build_indexes_on_device(Ctx * c, std::vector<std::unique_ptr<Region>>
       return rc;
     if (int rc = c->d_idx_idx2.reserve((size_t)total * 4))
       return rc;
-    if (int rc = c->d_idx_head.reserve((size_t)total * 8))
+    if (int rc = c->d_idx_head.reserve((size_t)total * 16)) // head flags + inclusive scan; before that: the sort's aux arrays
       return rc;
     size_t const sort_bytes = idx_sort_temp_bytes(total, n);
     scan_bytes = idx_scan_temp_bytes(total);
@@ -797,7 +799,7 @@ static int build_indexes_on_device(Ctx * c, std::vector<std::unique_ptr<Region>>
     DevLabel * le = static_cast<DevLabel *>(c->d_idx_labels.p);
     uint32_t * head = static_cast<uint32_t *>(c->d_idx_head.p);
     idx_launch_emit(d_desc, n, d_rjo, total_jobs, d_joff, k1, le, i1, d_err, c->stream);
-    if (idx_sort(c->d_idx_temp.p, c->d_idx_temp.cap, k1, k2, i1, i2, total, n, d_rto, c->stream))
+    if (idx_sort(c->d_idx_temp.p, c->d_idx_temp.cap, k1, k2, i1, i2, head, total, n, d_rto, c->stream))
       return fail(GTB_ERR_CUDA, "index build: sort failed");
     idx_launch_group(d_desc, k2, i2, le, head, head + total, c->d_idx_temp.p, c->d_idx_temp.cap, d_rto, n, total, d_nu, c->stream);
   }
@@ -1054,12 +1056,16 @@ static int launch_chunk(Ctx * c, BatchState & B)
   CUDA_TRY(cudaEventRecord(B.ev[3], c->stream));
   launch_chain(P, c->stream);
   CUDA_TRY(cudaEventRecord(B.ev[4], c->stream));
-  launch_slow(P, c->stream);
-  CUDA_TRY(cudaEventRecord(B.ev[5], c->stream));
-  launch_score(P, c->stream);
-  CUDA_TRY(cudaEventRecord(B.ev[6], c->stream));
-  CUDA_TRY(cudaMemcpyAsync(B.h_counters.p, B.d_counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaEventRecord(B.ev[7], c->stream));
+  // (Running slow/huge/score of chunk k on a third stream, concurrently with probe/chain of chunk k+1, was measured and
+  // rejected: slow_kernel is one long single-lane task per warp, and sharing the SM schedulers with a 70 %-issue-bound
+  // probe_kernel stretches it from 0.1 ms to 0.5 ms.)
+  cudaStream_t const ts = c->stream;
+  launch_slow(P, ts);
+  CUDA_TRY(cudaEventRecord(B.ev[5], ts));
+  launch_score(P, ts);
+  CUDA_TRY(cudaEventRecord(B.ev[6], ts));
+  CUDA_TRY(cudaMemcpyAsync(B.h_counters.p, B.d_counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, ts));
+  CUDA_TRY(cudaEventRecord(B.ev[7], ts));
   return 0;
 }
 
@@ -1420,16 +1426,18 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   int n_chunks = 1;
   if (!c->debug && n >= 2)
   {
-    // Chunks on two streams hide the H2D copy behind the previous chunk's kernels.  Measured on B200/PCIe5 with the
-    // 2e5-record step: 1 chunk 2.32 ms, 2 chunks 2.21 ms, 3 chunks 2.46 ms end to end (tools/chunk_sweep.sh) -- the split
-    // kernels lose what the overlap wins, so chunking only engages for multi-million-record submits.
-    // GTB_CHUNKS overrides (1..4).
+    // Two chunks on two streams hide half of the H2D copy behind the first chunk's kernels.  Measured on B200/PCIe5 with
+    // the 2e5-record step (tools/chunk_sweep.sh): 1 chunk 2.36-2.43 ms, 2 chunks 2.12-2.17 ms, 3 chunks 2.15-2.44 ms,
+    // 4 chunks 2.35 ms end to end -- every chunk pays slow_kernel's fixed ~0.1 ms latency again, so more chunks lose what
+    // the overlap wins.  gtb_set_chunks / GTB_CHUNKS override (1..4).
     static int const env_forced = []() { const char * e = getenv("GTB_CHUNKS"); return e ? atoi(e) : 0; }();
     int const forced = c->forced_chunks > 0 ? c->forced_chunks : env_forced;
     if (forced > 0)
       n_chunks = std::min({n, MAX_CHUNKS, forced});
     else if (total >= 4000000)
       n_chunks = std::min(n, MAX_CHUNKS);
+    else if (total >= 65536)
+      n_chunks = 2;
   }
   std::vector<int> cut(n_chunks + 1, n);
   cut[0] = 0;

@@ -215,7 +215,7 @@ void idx_launch_region_totals(const uint32_t * job_off, const uint32_t * region_
 void idx_launch_emit(const IdxRegion * regions, uint32_t n_regions, const uint32_t * region_job_off, uint32_t total_jobs,
                      const uint32_t * job_off, uint64_t * keys, DevLabel * labels, uint32_t * tuple_idx, uint32_t * err, void * stream);
 size_t idx_sort_temp_bytes(uint32_t total, uint32_t n_regions);
-int idx_sort(void * temp, size_t temp_bytes, const uint64_t * keys_in, uint64_t * keys_out, const uint32_t * idx_in, uint32_t * idx_out,
+int idx_sort(void * temp, size_t temp_bytes, uint64_t * keys_a, uint64_t * keys_b, uint32_t * idx_a, uint32_t * idx_b, uint32_t * aux,
              uint32_t total, uint32_t n_regions, const uint32_t * region_tuple_off, void * stream);
 void idx_launch_group(const IdxRegion * regions, const uint64_t * skeys, const uint32_t * sidx, const DevLabel * labels_emit,
                       uint32_t * head, uint32_t * head_incl, void * scan_temp, size_t scan_temp_bytes, const uint32_t * region_tuple_off,
