@@ -68,6 +68,51 @@ class SubmitStats(C.Structure):
                 ("n_capacity_overflow", C.c_uint64), ("kernel_launches", C.c_uint64)]
 
 
+class Connection(C.Structure):
+    _fields_ = [("sample", C.c_uint32), ("hap1", C.c_uint16), ("allele1", C.c_uint16), ("hap2", C.c_uint16),
+                ("allele2", C.c_uint16), ("count", C.c_uint32)]
+
+
+class PhaseSupportEntry(C.Structure):
+    _fields_ = [("hap1", C.c_uint16), ("allele1", C.c_uint16), ("hap2", C.c_uint16), ("allele2", C.c_uint16),
+                ("flags", C.c_int8), ("pad", C.c_uint8 * 7)]
+
+
+CONNECTION_DTYPE = np.dtype([("sample", np.uint32), ("hap1", np.uint16), ("allele1", np.uint16), ("hap2", np.uint16),
+                             ("allele2", np.uint16), ("count", np.uint32)])
+PHASE_DTYPE = np.dtype([("hap1", np.uint16), ("allele1", np.uint16), ("hap2", np.uint16), ("allele2", np.uint16),
+                        ("flags", np.int8), ("pad", np.uint8, (7,))])
+assert CONNECTION_DTYPE.itemsize == C.sizeof(Connection) == 16 and PHASE_DTYPE.itemsize == C.sizeof(PhaseSupportEntry) == 16
+
+
+def connections_as_table(c: np.ndarray) -> np.ndarray:
+    """uint32 [n, 6]: sample hap1 allele1 hap2 allele2 count."""
+    return np.stack([c[k].astype(np.uint32) for k in ("sample", "hap1", "allele1", "hap2", "allele2", "count")], axis=1) \
+        if len(c) else np.zeros((0, 6), np.uint32)
+
+
+def phase_as_table(p: np.ndarray) -> np.ndarray:
+    """uint32 [n, 5]: hap1 allele1 hap2 allele2 flags."""
+    return np.stack([p[k].astype(np.uint32) for k in ("hap1", "allele1", "hap2", "allele2", "flags")], axis=1) \
+        if len(p) else np.zeros((0, 5), np.uint32)
+
+
+def phase_support(lib, fn_name: str, acc, conn: np.ndarray) -> np.ndarray:
+    """Calls <lib>.<fn_name>(acc, n_conn, conn, &n, out) with the count-then-fill protocol."""
+    fn = getattr(lib, fn_name)
+    fn.argtypes = [C.POINTER(Accumulators), C.c_uint64, C.c_void_p, u64p, C.c_void_p]
+    conn = np.ascontiguousarray(conn, dtype=CONNECTION_DTYPE)
+    n = C.c_uint64(0)
+    rc = fn(C.byref(acc.view), len(conn), conn.ctypes.data, C.byref(n), None)
+    if rc:
+        raise RuntimeError(f"{fn_name} rc={rc}")
+    out = np.zeros(n.value, PHASE_DTYPE)
+    rc = fn(C.byref(acc.view), len(conn), conn.ctypes.data, C.byref(n), out.ctypes.data)
+    if rc:
+        raise RuntimeError(f"{fn_name} rc={rc}")
+    return out
+
+
 def _ptr(a: Optional[np.ndarray], typ):
     if a is None:
         return C.cast(None, typ)

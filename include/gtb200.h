@@ -242,6 +242,34 @@ int gtb_scan_calls(const gtb_accumulators *acc, const uint8_t *phred, uint64_t *
 int gtb_merge_varstats(uint32_t n_bubbles, uint64_t n_alleles_total, uint64_t *var, uint64_t *allele, double *ratio,
                        const uint64_t *var_src, const uint64_t *allele_src, const double *ratio_src);
 
+/* Phasing connections = HapSample::connections (include/graphtyper/graph/haplotype.hpp:42): for every read / read pair that
+ * explains alleles of several bubbles, support counts between (bubble hap1, allele1) and a LATER bubble's (hap2, allele2),
+ * as VcfWriter::push_to_haplotype_scores builds them (src/typer/vcf_writer.cpp:587-637: weight 6/(n1*n2) inside one read)
+ * and update_haplotype_scores_geno merges them over the two mates (vcf_writer.cpp:186-249: +1 per cross-mate pair).
+ * The reference only consumes them when is_writing_hap (discovery iterations, hts_parallel_reader.cpp:782), so they are OFF
+ * by default; gtb_set_connections(ctx, 1) applies to pools begun afterwards.  Counts are uint16 in the reference (wrap
+ * around at 65536, reproduced).  hap = bubble index within the region (the reference's uint16 haplotype index). */
+typedef struct gtb_connection {
+  uint32_t sample;
+  uint16_t hap1, allele1, hap2, allele2;
+  uint32_t count;
+} gtb_connection;
+int gtb_set_connections(gtb_ctx *ctx, int on);
+/* After gtb_pool_finish: number of non-zero entries, then the entries sorted by (sample, hap1, allele1, hap2, allele2). */
+int gtb_connections_size(gtb_ctx *ctx, int region_id, uint64_t *n);
+int gtb_connections(gtb_ctx *ctx, int region_id, gtb_connection *out);
+/* The phase-support map `ph` the pool derives from connections + allele coverage when is_writing_hap
+ * (src/utilities/hts_parallel_reader.cpp:782-893): for bubbles less than 100 bp apart, per pair of ALT alleles, the OR over
+ * samples of IS_ANY_HAP_SUPPORT (1) / IS_ANY_ANTI_HAP_SUPPORT (2) (constants.hpp.in:56-57).  Pure host function.
+ * Call with out == NULL to get the count; entries sorted by (hap1, allele1, hap2, allele2). */
+typedef struct gtb_phase_support_entry {
+  uint16_t hap1, allele1, hap2, allele2;
+  int8_t flags;
+  uint8_t pad[7];
+} gtb_phase_support_entry;
+int gtb_phase_support(const gtb_accumulators *acc, uint64_t n_conn, const gtb_connection *conn, uint64_t *n_out,
+                      gtb_phase_support_entry *out);
+
 /* Multi-GPU: sum-reduce widened accumulators of a region over an NCCL communicator supplied by the host
  * (ncclComm_t passed as void*; all ranks call; result valid on every rank).  Used when ONE sample's reads
  * are split over GPUs; with sample sharding no collective is needed. */

@@ -83,6 +83,10 @@ class Oracle:
         L.gto_result_path_sizes.argtypes = [C.c_void_p, abi.u64p, abi.u64p, abi.u64p, abi.u64p]
         L.gto_result_paths.argtypes = [C.c_void_p, abi.u32p, abi.u32p, abi.u32p, abi.u32p, abi.u32p, abi.u16p]
         L.gto_calls_from_accumulators.argtypes = [C.POINTER(abi.Accumulators), abi.u8p, abi.u16p, abi.u8p]
+        L.gto_set_connections.argtypes = [C.c_int]
+        L.gto_set_connections.restype = None
+        L.gto_result_connections_size.argtypes = [C.c_void_p, abi.u64p]
+        L.gto_result_connections.argtypes = [C.c_void_p, C.c_void_p]
 
     # -- index
     def index_build(self, graph) -> C.c_void_p:
@@ -154,6 +158,20 @@ class Oracle:
                                   out["p_fields"].ctypes.data_as(a.u32p), out["v_order"].ctypes.data_as(a.u32p),
                                   out["v_nnum"].ctypes.data_as(a.u32p), out["v_nums"].ctypes.data_as(a.u16p))
         return out
+
+    def set_connections(self, on: bool) -> None:
+        """Phasing connections (vcf_writer.cpp:587-637) in the following pool_run calls."""
+        self.lib.gto_set_connections(1 if on else 0)
+
+    def result_connections(self, r) -> np.ndarray:
+        n = C.c_uint64()
+        self.lib.gto_result_connections_size(r, C.byref(n))
+        out = np.zeros(n.value, self.abi.CONNECTION_DTYPE)
+        self.lib.gto_result_connections(r, out.ctypes.data)
+        return out
+
+    def phase_support(self, acc, conn: np.ndarray) -> np.ndarray:
+        return self.abi.phase_support(self.lib, "gto_phase_support", acc, conn)
 
     def calls(self, acc):
         phred = np.zeros(len(acc.log_score), np.uint8)

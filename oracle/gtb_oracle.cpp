@@ -14,6 +14,8 @@
 // Each function cites the reference file:line it follows (paths relative to /root/reference).
 
 #include <algorithm>
+#include <array>
+#include <numeric>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -1510,10 +1512,26 @@ struct Hap
   }
 };
 
+// push_to_haplotype_scores' return value (vcf_writer.cpp:502-519): (hap, allele) -> list of (later hap, allele)
+using HapAllele = std::pair<uint16_t, uint16_t>;
+using ConnMap = std::map<HapAllele, std::vector<HapAllele>>;
+
 struct Writer
 {
   std::vector<Hap> haps;
   std::vector<uint32_t> hap_orders; // ascending bubble orders for id2hap (vcf_writer.cpp:84)
+  // HapSample::connections (haplotype.hpp:42) of all samples as one sparse map:
+  // (sample, hap1, allele1, hap2, allele2) -> uint16 support count
+  bool conn_on = false;
+  std::map<std::array<uint32_t, 5>, uint16_t> conn;
+
+  // "add new connections to hap_samples" (vcf_writer.cpp:119-140, 229-249)
+  void add_connections(ConnMap const & merged, long pn)
+  {
+    for (auto const & kv : merged)
+      for (auto const & to : kv.second)
+        ++conn[{(uint32_t)pn, kv.first.first, kv.first.second, to.first, to.second}];
+  }
 
   void init(const G & g, int n_samples) // graph.cpp:680-702, haplotype.cpp:122-147
   {
@@ -1566,9 +1584,11 @@ bool are_genotype_paths_good(const G & g, const GenoPaths & geno)
   return true;
 }
 
-// vcf_writer.cpp:503-676 (connections omitted: only consumed when is_writing_hap, hts_parallel_reader.cpp:782)
-void push_to_haplotype_scores(const G & g, Writer & w, const GenoPaths & geno, long pn)
+// vcf_writer.cpp:503-676; the returned connections are only built when Writer::conn_on (they are consumed when
+// is_writing_hap, hts_parallel_reader.cpp:782)
+ConnMap push_to_haplotype_scores(const G & g, Writer & w, const GenoPaths & geno, long pn)
 {
+  ConnMap new_connections;
   int const clipped_bp = (int)geno.read_length - (int)geno.longest;
   bool const fully_aligned = clipped_bp == 0;
   bool const non_unique = !geno.all_paths_unique(g);
@@ -1601,6 +1621,32 @@ void push_to_haplotype_scores(const G & g, Writer & w, const GenoPaths & geno, l
       }
     }
   }
+
+  // "check connections" (vcf_writer.cpp:587-637)
+  if (w.conn_on)
+    for (auto it = recent.begin(); it != recent.end(); ++it)
+    {
+      Hap const & h1 = w.haps[it->first];
+      long const n1 = (long)h1.explains.size();
+      if (n1 == 0 || n1 > 64)
+        continue;
+      for (uint64_t b1 : h1.explains) // ascending alleles, as the b1 counter loop visits them
+      {
+        auto & conn = new_connections[{(uint16_t)it->first, (uint16_t)b1}];
+        for (auto it2 = std::next(it); it2 != recent.end(); ++it2)
+        {
+          Hap const & h2 = w.haps[it2->first];
+          long const n2 = (long)h2.explains.size();
+          if (n2 == 0 || n2 > 64)
+            continue;
+          long const weight = n1 * n2;
+          long const repeat = weight >= 3 ? 6 / weight : 1;
+          for (uint64_t b2 : h2.explains)
+            for (long r = 0; r < repeat; ++r)
+              conn.push_back({(uint16_t)it2->first, (uint16_t)b2});
+        }
+      }
+    }
 
   for (auto const & kv : recent)
   {
@@ -1699,6 +1745,46 @@ void push_to_haplotype_scores(const G & g, Writer & w, const GenoPaths & geno, l
     h.coverage = NO_COVERAGE;
     h.explains.clear();
   }
+  return new_connections;
+}
+
+// VcfWriter::update_haplotype_scores_geno, single read (vcf_writer.cpp:88-141); the caller has checked are_genotype_paths_good
+void update_scores_single(const G & g, Writer & w, const GenoPaths & geno, long pn)
+{
+  ConnMap const con1 = push_to_haplotype_scores(g, w, geno, pn);
+  if (w.conn_on)
+    w.add_connections(con1, pn);
+}
+
+// VcfWriter::update_haplotype_scores_geno, read pair (vcf_writer.cpp:143-250)
+void update_scores_pair(const G & g, Writer & w, const GenoPaths & geno1, const GenoPaths & geno2, long pn)
+{
+  ConnMap con1, con2;
+  if (are_genotype_paths_good(g, geno1))
+    con1 = push_to_haplotype_scores(g, w, geno1, pn);
+  if (are_genotype_paths_good(g, geno2))
+    con2 = push_to_haplotype_scores(g, w, geno2, pn);
+  if (!w.conn_on || (con1.empty() && con2.empty()))
+    return;
+  ConnMap merged;
+  for (auto const & kv1 : con1) // :191-208
+  {
+    auto & dst = merged[kv1.first];
+    dst = kv1.second;
+    for (auto const & kv2 : con2)
+      if (kv2.first.first > kv1.first.first)
+        dst.push_back(kv2.first);
+  }
+  for (auto const & kv2 : con2) // :211-226
+  {
+    auto ins = merged.insert(kv2);
+    if (!ins.second)
+      ins.first->second.insert(ins.first->second.end(), kv2.second.begin(), kv2.second.end());
+    for (auto const & kv1 : con1)
+      if (kv1.first.first > kv2.first.first)
+        ins.first->second.push_back(kv1.first);
+  }
+  w.add_connections(merged, pn);
 }
 
 // ------------------------------------------------------------------------------------------------ reference depth (A16)
@@ -1767,9 +1853,12 @@ struct PoolResult
 };
 
 // hts_parallel_reader.cpp:245-338 (+ alignment.cpp:365-449,557-622)
+bool g_connections = false; // gto_set_connections
+
 int run_pool(const G & g, const Index & idx, int n_samples, const gtb_read_batch & b, PoolResult & R, bool tap)
 {
   R.w.init(g, n_samples);
+  R.w.conn_on = g_connections;
   R.n_samples = n_samples;
   bool const SV = g.v.is_sv_graph != 0;
   if (SV && g.v.n_ref > 0)
@@ -1842,7 +1931,7 @@ int run_pool(const G & g, const Index & idx, int n_samples, const gtb_read_batch
           sel->score_diff = b.score_diff[i];
           if (are_genotype_paths_good(g, *sel)) // vcf_writer.cpp:88-141
           {
-            push_to_haplotype_scores(g, R.w, *sel, sample);
+            update_scores_single(g, R.w, *sel, sample);
             ++R.stats.n_singles_scored;
           }
         }
@@ -1893,11 +1982,7 @@ int run_pool(const G & g, const Index & idx, int n_samples, const gtb_read_batch
             R.rd.add_genotype_paths(g, *s2, sample);
           }
           // update_haplotype_scores_geno (pair), vcf_writer.cpp:143-250
-          bool const g1 = are_genotype_paths_good(g, *s1), g2 = are_genotype_paths_good(g, *s2);
-          if (g1)
-            push_to_haplotype_scores(g, R.w, *s1, sample);
-          if (g2)
-            push_to_haplotype_scores(g, R.w, *s2, sample);
+          update_scores_pair(g, R.w, *s1, *s2, sample);
           ++R.stats.n_pairs_scored;
         }
       }
@@ -1932,7 +2017,7 @@ int run_pool(const G & g, const Index & idx, int n_samples, const gtb_read_batch
       R.rd.add_genotype_paths(g, *s1, b.sample[i]);
       if (are_genotype_paths_good(g, *s1))
       {
-        push_to_haplotype_scores(g, R.w, *s1, b.sample[i]);
+        update_scores_single(g, R.w, *s1, b.sample[i]);
         ++R.stats.n_singles_scored;
       }
     }
@@ -2205,6 +2290,122 @@ int gto_result_paths(void * r, uint32_t * gp_npaths, uint32_t * gp_longest, uint
         }
       }
     }
+  return 0;
+}
+
+void gto_set_connections(int on) { g_connections = on != 0; }
+
+int gto_result_connections_size(void * r, uint64_t * n)
+{
+  uint64_t k = 0;
+  for (auto const & kv : ((PoolResult *)r)->w.conn)
+    if (kv.second != 0)
+      ++k;
+  *n = k;
+  return 0;
+}
+
+int gto_result_connections(void * r, gtb_connection * out)
+{
+  for (auto const & kv : ((PoolResult *)r)->w.conn)
+    if (kv.second != 0)
+    {
+      out->sample = kv.first[0];
+      out->hap1 = (uint16_t)kv.first[1];
+      out->allele1 = (uint16_t)kv.first[2];
+      out->hap2 = (uint16_t)kv.first[3];
+      out->allele2 = (uint16_t)kv.first[4];
+      out->count = kv.second;
+      ++out;
+    }
+  return 0;
+}
+
+// the `ph` block of parallel_reader_genotype_only (hts_parallel_reader.cpp:782-893)
+int gto_phase_support(const gtb_accumulators * acc, uint64_t n_conn, const gtb_connection * conn, uint64_t * n_out,
+                      gtb_phase_support_entry * out)
+{
+  long const NB = acc->n_bubbles, NS = acc->n_samples;
+  // hap_samples[s].connections[cov1] : hap2 -> vector<uint16_t>(hap2.gt.num)
+  std::map<std::array<uint32_t, 4>, std::vector<uint16_t>> C;
+  for (uint64_t i = 0; i < n_conn; ++i)
+  {
+    auto & v = C[{conn[i].sample, conn[i].hap1, conn[i].allele1, conn[i].hap2}];
+    if (v.empty())
+      v.assign(acc->n_alleles[conn[i].hap2], 0);
+    v[conn[i].allele2] = (uint16_t)conn[i].count;
+  }
+  std::map<std::pair<HapAllele, HapAllele>, int8_t> ph;
+  for (long ps1 = 0; ps1 < NB - 1; ++ps1)
+  {
+    long const order1 = acc->bubble_id[ps1];
+    long const num1 = acc->n_alleles[ps1];
+    for (long ps2 = ps1 + 1; ps2 < NB; ++ps2)
+    {
+      long const order2 = acc->bubble_id[ps2];
+      long const num2 = acc->n_alleles[ps2];
+      if (order2 >= order1 + 100)
+        break;
+      for (long s = 0; s < NS; ++s)
+      {
+        const uint16_t * cov1v = acc->gt_coverage + acc->cov_off[ps1] * NS + s * num1;
+        const uint16_t * cov2v = acc->gt_coverage + acc->cov_off[ps2] * NS + s * num2;
+        double const sum1 = std::accumulate(cov1v, cov1v + num1, 0.0), sum2 = std::accumulate(cov2v, cov2v + num2, 0.0);
+        for (long cov1 = 1; cov1 < num1; ++cov1)
+        {
+          auto f = C.find({(uint32_t)s, (uint32_t)ps1, (uint32_t)cov1, (uint32_t)(uint16_t)ps2});
+          if (f == C.end())
+            continue;
+          bool const clearly1 = cov1v[cov1] >= 4 || ((double)cov1v[cov1] / sum1) >= 0.28;
+          bool const not1 = cov1v[cov1] <= 2 || ((double)cov1v[cov1] / sum1) < 0.22;
+          std::vector<uint16_t> const & support_vec = f->second;
+          long const total_support = std::accumulate(support_vec.begin(), support_vec.end(), 0l);
+          for (long cov2 = 1; cov2 < (long)support_vec.size(); ++cov2)
+          {
+            double const support = (double)support_vec[cov2];
+            int8_t is_good = 0;
+            bool const clearly2 = cov2v[cov2] >= 4 || ((double)cov2v[cov2] / sum2) >= 0.28;
+            bool const not2 = cov2v[cov2] <= 2 || ((double)cov2v[cov2] / sum2) < 0.22;
+            if (not1 && not2)
+              continue;
+            if ((not1 && clearly2) || (not2 && clearly1))
+              is_good = 2;
+            else
+            {
+              if (total_support <= 2)
+                continue;
+              if (clearly1 && clearly2 && support / (double)total_support > 0.78)
+                is_good = 1;
+              else if (support / (double)total_support < 0.22)
+                is_good = 2;
+              else
+                continue;
+            }
+            ph[{{(uint16_t)ps1, (uint16_t)cov1}, {(uint16_t)ps2, (uint16_t)cov2}}] |= is_good;
+          }
+        }
+      }
+    }
+  }
+  if (out)
+  {
+    if (*n_out < ph.size())
+    {
+      g_err = "phase support output too small";
+      return GTB_ERR_ARG;
+    }
+    for (auto const & kv : ph)
+    {
+      memset(out, 0, sizeof(*out));
+      out->hap1 = kv.first.first.first;
+      out->allele1 = kv.first.first.second;
+      out->hap2 = kv.first.second.first;
+      out->allele2 = kv.first.second.second;
+      out->flags = kv.second;
+      ++out;
+    }
+  }
+  *n_out = ph.size();
   return 0;
 }
 

@@ -20,6 +20,7 @@
 // (0 unsigned, 1 signed, 2 float), u64 count, raw little-endian data padded to 8 bytes.
 
 #include <algorithm>
+#include <array>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -706,6 +707,55 @@ int main(int argc, char ** argv)
       std::vector<uint64_t> rdm = {(uint64_t)reference_depth.reference_offset,
                                    (uint64_t)(reference_depth.depths.empty() ? 0 : reference_depth.depths[0].size())};
       af.add("ref_depth_meta", rdm);
+    }
+
+    // ---- phasing connections: hap_samples[s].connections[b1][hap2][b2] (vcf_writer.cpp:119-140,229-249), non-zero
+    //      counts as sorted (sample, hap1, b1, hap2, b2) tuples
+    {
+      std::vector<std::array<uint32_t, 5>> keys;
+      std::map<std::array<uint32_t, 5>, uint16_t> sorted;
+      for (uint32_t h1 = 0; h1 < writer.haplotypes.size(); ++h1)
+        for (long s = 0; s < NS; ++s)
+        {
+          auto const & conn_vec = writer.haplotypes[h1].hap_samples[s].connections;
+          for (uint32_t b1 = 0; b1 < conn_vec.size(); ++b1)
+            for (auto const & kv : conn_vec[b1])
+              for (uint32_t b2 = 0; b2 < kv.second.size(); ++b2)
+                if (kv.second[b2] != 0)
+                  sorted[{(uint32_t)s, h1, b1, (uint32_t)kv.first, b2}] = kv.second[b2];
+        }
+      std::vector<uint32_t> conn_tuples;
+      std::vector<uint16_t> conn_counts;
+      for (auto const & kv : sorted)
+      {
+        conn_tuples.insert(conn_tuples.end(), kv.first.begin(), kv.first.end());
+        conn_counts.push_back(kv.second);
+      }
+      af.add("conn_tuples", conn_tuples);
+      af.add("conn_counts", conn_counts);
+    }
+
+    // ---- the phase-support map `ph` exactly as the reference derives it: a second, independent pass that calls the
+    //      reference's own pool function with is_writing_hap = true (hts_parallel_reader.cpp:458,782-893)
+    if (!IS_SV)
+    {
+      std::vector<std::map<std::pair<uint16_t, uint16_t>, std::map<std::pair<uint16_t, uint16_t>, int8_t>>> ph_vec(1);
+      std::string out_path, tmp_dir = out + ".phtmp", reference_fn = "", reg = ".";
+      std::vector<double> avg_cov(sams.size(), -1.0);
+      std::string const cmd = "mkdir -p '" + tmp_dir + "'";
+      if (system(cmd.c_str()) != 0)
+        return 3;
+      parallel_reader_genotype_only(0, &out_path, &sams, &avg_cov, &tmp_dir, &reference_fn, &reg, &ph_index, nullptr, &ph_vec,
+                                    true, true, nullptr);
+      std::string const rm = "rm -rf '" + tmp_dir + "'";
+      if (system(rm.c_str()) != 0)
+        return 3;
+      std::vector<uint32_t> ph_tuples; // ps1 cov1 ps2 cov2 flags
+      for (auto const & a : ph_vec[0])
+        for (auto const & b : a.second)
+          ph_tuples.insert(ph_tuples.end(), {(uint32_t)a.first.first, (uint32_t)a.first.second, (uint32_t)b.first.first,
+                                             (uint32_t)b.first.second, (uint32_t)(uint8_t)b.second});
+      af.add("ph_tuples", ph_tuples);
     }
 
     // ---- pool finalisation: SampleCall + VarStats (vcf.cpp:1507, variant.cpp:230)

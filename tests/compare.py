@@ -103,3 +103,16 @@ def compare_accum(ref: dict, got: dict, what: str = "") -> None:
             bad = np.nonzero(a[:n].astype(np.uint64) != b[:n].astype(np.uint64))[0]
             raise AssertionError(f"{what} accumulators.{k} differ: shapes {a.shape} vs {b.shape}; "
                                  f"{len(bad)} mismatches, first at {bad[:5]}: {a[bad[:5]]} vs {b[bad[:5]]}")
+
+
+def probe_connections(d: dict) -> np.ndarray:
+    """Golden HapSample::connections -> uint32 [n, 6] rows (sample hap1 allele1 hap2 allele2 count), sorted."""
+    return np.concatenate([d["conn_tuples"].reshape(-1, 5).astype(np.uint32),
+                           d["conn_counts"].astype(np.uint32)[:, None]], axis=1)
+
+
+def compare_connections(ref: np.ndarray, got: np.ndarray, what: str = "") -> None:
+    if ref.shape != got.shape or not np.array_equal(ref, got):
+        rs, gs = {tuple(r) for r in ref.tolist()}, {tuple(r) for r in got.tolist()}
+        raise AssertionError(f"{what} connections differ: {len(ref)} vs {len(got)} entries; "
+                             f"missing {sorted(rs - gs)[:5]} extra {sorted(gs - rs)[:5]}")

@@ -41,6 +41,43 @@ def test_oracle_matches_reference(pre, oracle_lib):
     O.index_free(h)
 
 
+@pytest.mark.parametrize("pre", SMALL, ids=[os.path.basename(p) for p in SMALL])
+def test_oracle_connections_and_phase_support_match_reference(pre, oracle_lib):
+    """HapSample::connections (vcf_writer.cpp:88-250,587-637) and the `ph` map the reference's own pool function
+    derives with is_writing_hap (hts_parallel_reader.cpp:782-893)."""
+    O = oracle_lib
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    h = O.index_build(g)
+    rd = gtba.load(pre + ".reads.gtba")
+    ns = n_samples_of(rd)
+    O.set_connections(True)
+    try:
+        r = O.pool_run(g, h, ns, abi.batch_from_probe(rd), tap=False)
+    finally:
+        O.set_connections(False)
+    pa = gtba.load(pre + ".accum.gtba")
+    conn = O.result_connections(r)
+    compare.compare_connections(compare.probe_connections(pa), abi.connections_as_table(conn), "oracle")
+    acc = O.result_accum(r, ns)
+    compare.compare_accum(compare.probe_accum(pa), acc.as_dict(), "oracle+conn")
+    if "ph_tuples" in pa:
+        got = abi.phase_as_table(O.phase_support(acc, conn))
+        assert np.array_equal(pa["ph_tuples"].reshape(-1, 5).astype(np.uint32), got)
+    O.result_free(r)
+    O.index_free(h)
+
+
+def test_golden_fixtures_exercise_connections():
+    n_conn = n_ph = 0
+    for pre in SMALL:
+        pa = gtba.load(pre + ".accum.gtba")
+        n_conn += len(pa["conn_counts"])
+        n_ph += len(pa.get("ph_tuples", [])) // 5
+        if "ph_tuples" in pa and len(pa["ph_tuples"]):
+            assert set(np.unique(pa["ph_tuples"].reshape(-1, 5)[:, 4])) <= {1, 2, 3}
+    assert n_conn > 5000 and n_ph > 300
+
+
 def test_kmer_codec_known_answers(oracle_lib):
     """Known answers of the reference's own unit tests for the k-mer codec
     (test/utilities/test_kmer_help_functions.cpp, test/utilities/test_utilities.cpp:123-162):
