@@ -124,6 +124,10 @@ struct Region
   DeviceBuffer accum;   // accumulators (allocated at pool_begin)
   DevRegion dev{};      // pointers into arena/accum
   size_t accum_bytes = 0;
+  // phasing connections (gtb_set_connections): open-addressing table keys[cap] | vals[cap] | state[4]
+  DeviceBuffer conn;
+  uint32_t conn_cap = 0;   // slots (power of two), 0 = off for this pool
+  uint64_t conn_used = 0;  // occupied slots after the last submit (read back with the submit's counters)
 };
 
 // Everything one in-flight (chunk of a) submit owns.  Slot 0 doubles as the "last batch" of the debug taps.
@@ -136,6 +140,7 @@ struct BatchState
   std::vector<int> regions;            // region ids of this chunk, in batch order
   std::vector<uint32_t> unit_begin;    // per region: first unit index (size n+1)
   std::vector<uint32_t> rec_begin;
+  bool with_conn = false;              // some region of this chunk collects phasing connections
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // ev: 0 h2d start (copy stream), 1 h2d done (copy stream), 2 kernels start, 3 after probe, 4 after chain,
   //     5 after slow, 6 after score, 7 after counters D2H
@@ -174,6 +179,8 @@ struct Ctx
   bool have_last = false;
   bool debug = false;
   int forced_chunks = 0; // gtb_set_chunks / GTB_CHUNKS: 0 = automatic
+  int connections = 0;   // gtb_set_connections: 0 off, otherwise table slots reserved per submitted record
+  PinnedBuffer h_conn_state;
   float t_h2d = 0, t_align = 0, t_score = 0, t_d2h = 0, t_probe = 0, t_chain = 0, t_slow = 0;
   unsigned long long last_n_slow = 0;
   // nccl (loaded lazily with dlopen, see gtb_nccl.cpp part below)
@@ -369,6 +376,50 @@ void parallel_for(int n, const std::function<void(int)> & fn)
   pool.run(n, fn);
 }
 
+// ---- phasing-connection table of one pool
+size_t conn_table_bytes(uint32_t cap) { return (size_t)cap * 12 + 16; }
+
+int conn_alloc(Ctx * c, Region & R, uint32_t cap)
+{
+  if (int rc = take_buffer(c, R.conn, conn_table_bytes(cap)))
+    return rc;
+  CUDA_TRY(cudaMemsetAsync(R.conn.p, 0, conn_table_bytes(cap), c->stream));
+  uint8_t * d = static_cast<uint8_t *>(R.conn.p);
+  R.dev.conn_keys = reinterpret_cast<unsigned long long *>(d);
+  R.dev.conn_vals = reinterpret_cast<uint32_t *>(d + (size_t)cap * 8);
+  R.dev.conn_state = reinterpret_cast<uint32_t *>(d + (size_t)cap * 12);
+  R.dev.conn_mask = cap - 1;
+  R.conn_cap = cap;
+  c->regions_dirty = true;
+  return 0;
+}
+
+// Keeps the table at most half full after `n_new` more records (c->connections slots budgeted per record; an insert that
+// still finds the table full raises GTB_ERR_CAPACITY after the submit).  Growth = new zeroed table + re-insert on the device.
+int conn_reserve(Ctx * c, Region & R, uint64_t n_new)
+{
+  if (!R.conn_cap)
+    return 0;
+  uint64_t const need = (R.conn_used + (uint64_t)c->connections * n_new) * 2;
+  if (need <= R.conn_cap)
+    return 0;
+  uint64_t ncap = R.conn_cap;
+  while (ncap < need)
+    ncap <<= 1;
+  if (ncap > (1ull << 30))
+    return fail(GTB_ERR_CAPACITY, "phasing-connection table would exceed 2^30 slots");
+  DeviceBuffer old = R.conn;
+  DevRegion const old_dev = R.dev;
+  uint32_t const old_cap = R.conn_cap;
+  R.conn = DeviceBuffer();
+  if (int rc = conn_alloc(c, R, (uint32_t)ncap))
+    return rc;
+  launch_conn_rehash(old_dev.conn_keys, old_dev.conn_vals, old_cap, R.dev, c->stream);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  give_buffer(c, old);
+  return 0;
+}
+
 template <typename T>
 size_t place(size_t & off, size_t count)
 {
@@ -435,6 +486,7 @@ void gtb_destroy(gtb_ctx * ctx)
       kv.second->arena.release();
       kv.second->index_arena.release();
       kv.second->accum.release();
+      kv.second->conn.release();
     }
     c->d_regions.release();
     for (auto & b : c->buffer_cache)
@@ -448,6 +500,7 @@ void gtb_destroy(gtb_ctx * ctx)
     c->d_huge.release();
     c->h_stage.release();
     c->h_accum.release();
+    c->h_conn_state.release();
     for (DeviceBuffer * b : {&c->d_idx_small, &c->d_idx_jobs, &c->d_idx_keys, &c->d_idx_keys2, &c->d_idx_labels, &c->d_idx_idx,
                              &c->d_idx_idx2, &c->d_idx_head, &c->d_idx_temp})
       b->release();
@@ -924,6 +977,7 @@ int gtb_region_end(gtb_ctx * ctx, int region_id)
     give_buffer(c, it->second->arena);
     give_buffer(c, it->second->index_arena);
     give_buffer(c, it->second->accum);
+    give_buffer(c, it->second->conn);
     if (it->second->slot >= 0)
       c->slot_region[it->second->slot] = -1;
     c->regions_dirty = true;
@@ -1038,6 +1092,20 @@ int gtb_pool_begin(gtb_ctx * ctx, int region_id, int n_samples)
   R.n_samples = n_samples;
   R.pool_open = true;
   c->regions_dirty = true;
+  D.conn_keys = nullptr;
+  D.conn_vals = nullptr;
+  D.conn_state = nullptr;
+  D.conn_mask = 0;
+  R.conn_cap = 0;
+  R.conn_used = 0;
+  if (c->connections)
+  {
+    if (NB > CONN_MAX_BUBBLES || NS > CONN_MAX_SAMPLES)
+      return fail(GTB_ERR_CAPACITY, "phasing connections need <= 65536 bubbles per region (the reference's uint16 haplotype "
+                                    "index, vcf_writer.cpp:502) and <= 2^21 samples per pool");
+    if (int rc = conn_alloc(c, R, 1u << 16))
+      return rc;
+  }
   return 0;
 }
 
@@ -1062,7 +1130,7 @@ static int launch_chunk(Ctx * c, BatchState & B)
   cudaStream_t const ts = c->stream;
   launch_slow(P, ts);
   CUDA_TRY(cudaEventRecord(B.ev[5], ts));
-  launch_score(P, ts);
+  launch_score(P, B.with_conn, ts);
   CUDA_TRY(cudaEventRecord(B.ev[6], ts));
   CUDA_TRY(cudaMemcpyAsync(B.h_counters.p, B.d_counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, ts));
   CUDA_TRY(cudaEventRecord(B.ev[7], ts));
@@ -1392,6 +1460,36 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   return 0;
 }
 
+// After a submit: occupancy + overflow flag of every connection table it touched (one small D2H each, one synchronisation).
+static int conn_check(Ctx * c, int n, Region * const * regs)
+{
+  int m = 0;
+  for (int i = 0; i < n; ++i)
+    m += regs[i]->conn_cap != 0;
+  if (m == 0)
+    return 0;
+  if (int rc = c->h_conn_state.reserve((size_t)m * 8))
+    return rc;
+  uint32_t * h = static_cast<uint32_t *>(c->h_conn_state.p);
+  int k = 0;
+  for (int i = 0; i < n; ++i)
+    if (regs[i]->conn_cap)
+      CUDA_TRY(cudaMemcpyAsync(h + 2 * k++, regs[i]->dev.conn_state, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  k = 0;
+  bool full = false;
+  for (int i = 0; i < n; ++i)
+    if (regs[i]->conn_cap)
+    {
+      regs[i]->conn_used = h[2 * k];
+      full = full || h[2 * k + 1] != 0;
+      ++k;
+    }
+  if (full)
+    return fail(GTB_ERR_CAPACITY, "phasing-connection table full: raise the per-record budget with gtb_set_connections(ctx, n)");
+  return 0;
+}
+
 int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const gtb_read_batch * batches,
                            gtb_submit_stats * stats)
 {
@@ -1417,6 +1515,9 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   }
   if (total >= 0x7FFFFFFFull)
     return fail(GTB_ERR_ARG, "batch too large");
+  for (int i = 0; i < n; ++i)
+    if (int rc = conn_reserve(c, *regs[i], batches[i].n_reads))
+      return rc;
   if (int rc = upload_region_table(c))
     return rc;
   c->have_last = false;
@@ -1462,11 +1563,16 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
     int const b0 = cut[k], m = cut[k + 1] - cut[k];
     if (int rc = stage_chunk(c, c->bs[k], m, region_ids + b0, batches + b0, regs.data() + b0, c->debug))
       return rc;
+    c->bs[k].with_conn = false;
+    for (int i = b0; i < b0 + m; ++i)
+      c->bs[k].with_conn = c->bs[k].with_conn || regs[i]->conn_cap != 0;
     if (int rc = launch_chunk(c, c->bs[k]))
       return rc;
   }
   c->have_last = true;
-  return collect_chunks(c, stats, true);
+  if (int rc = collect_chunks(c, stats, true))
+    return rc;
+  return conn_check(c, n, regs.data());
 }
 
 int gtb_submit_reads(gtb_ctx * ctx, int region_id, const gtb_read_batch * batch, gtb_submit_stats * stats)
@@ -1583,6 +1689,9 @@ int gtb_pool_reset(gtb_ctx * ctx, int region_id)
     return fail(GTB_ERR_STATE, "unknown region / pool not open");
   cudaSetDevice(c->device);
   CUDA_TRY(cudaMemsetAsync(it->second->accum.p, 0, it->second->accum_bytes, c->stream));
+  if (it->second->conn_cap)
+    CUDA_TRY(cudaMemsetAsync(it->second->conn.p, 0, conn_table_bytes(it->second->conn_cap), c->stream));
+  it->second->conn_used = 0;
   return 0;
 }
 
@@ -1720,7 +1829,191 @@ int gtb_pool_reset_multi(gtb_ctx * ctx, int n, const int * region_ids)
     if (it == c->regions.end() || !it->second->pool_open)
       return fail(GTB_ERR_STATE, "unknown region / pool not open");
     CUDA_TRY(cudaMemsetAsync(it->second->accum.p, 0, it->second->accum_bytes, c->stream));
+    if (it->second->conn_cap)
+      CUDA_TRY(cudaMemsetAsync(it->second->conn.p, 0, conn_table_bytes(it->second->conn_cap), c->stream));
+    it->second->conn_used = 0;
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ phasing connections
+int gtb_set_connections(gtb_ctx * ctx, int on)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || on < 0)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  c->connections = on == 1 ? 16 : on; // table slots budgeted per submitted record
+  return 0;
+}
+
+// Compacts the pool's table on the device, downloads the entries and sorts them by key (= by sample, hap1, allele1, hap2,
+// allele2).  Counts are reported modulo 2^16 like the reference's uint16 counters; entries that are 0 modulo 2^16 are dropped.
+static int conn_fetch(Ctx * c, Region & R, std::vector<gtb_connection> & out)
+{
+  out.clear();
+  if (!R.conn_cap)
+    return 0;
+  cudaSetDevice(c->device);
+  uint32_t st[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(st, R.dev.conn_state, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  uint32_t const n = st[0];
+  if (n == 0)
+    return 0;
+  DeviceBuffer d;
+  if (int rc = take_buffer(c, d, (size_t)n * 12 + 16))
+    return rc;
+  uint8_t * dp = static_cast<uint8_t *>(d.p);
+  auto * d_keys = reinterpret_cast<unsigned long long *>(dp);
+  auto * d_vals = reinterpret_cast<uint32_t *>(dp + (size_t)n * 8);
+  auto * d_n = reinterpret_cast<uint32_t *>(dp + (size_t)n * 12);
+  CUDA_TRY(cudaMemsetAsync(d_n, 0, 4, c->stream));
+  launch_conn_compact(R.dev, d_keys, d_vals, d_n, c->stream);
+  std::vector<unsigned long long> keys(n);
+  std::vector<uint32_t> vals(n);
+  CUDA_TRY(cudaMemcpyAsync(keys.data(), d_keys, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(vals.data(), d_vals, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  give_buffer(c, d);
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; ++i)
+    order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+  out.reserve(n);
+  for (uint32_t i : order)
+  {
+    uint32_t const cnt = vals[i] & 0xFFFFu;
+    if (cnt == 0)
+      continue;
+    unsigned long long const k = keys[i];
+    gtb_connection e;
+    e.sample = (uint32_t)((k >> 42) & 0x1FFFFFu);
+    e.hap1 = (uint16_t)((k >> 26) & 0xFFFFu);
+    e.allele1 = (uint16_t)((k >> 21) & 0x1Fu);
+    e.hap2 = (uint16_t)((k >> 5) & 0xFFFFu);
+    e.allele2 = (uint16_t)(k & 0x1Fu);
+    e.count = cnt;
+    out.push_back(e);
+  }
+  return 0;
+}
+
+int gtb_connections_size(gtb_ctx * ctx, int region_id, uint64_t * n)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !n)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  auto it = c->regions.find(region_id);
+  if (it == c->regions.end() || !it->second->pool_open)
+    return fail(GTB_ERR_STATE, "unknown region / pool not open");
+  if (c->device < 0)
+    return fail(GTB_ERR_CUDA, "host-only context");
+  std::vector<gtb_connection> v;
+  if (int rc = conn_fetch(c, *it->second, v))
+    return rc;
+  *n = v.size();
+  return 0;
+}
+
+int gtb_connections(gtb_ctx * ctx, int region_id, gtb_connection * out)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !out)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  auto it = c->regions.find(region_id);
+  if (it == c->regions.end() || !it->second->pool_open)
+    return fail(GTB_ERR_STATE, "unknown region / pool not open");
+  if (c->device < 0)
+    return fail(GTB_ERR_CUDA, "host-only context");
+  std::vector<gtb_connection> v;
+  if (int rc = conn_fetch(c, *it->second, v))
+    return rc;
+  if (!v.empty())
+    memcpy(out, v.data(), v.size() * sizeof(gtb_connection));
+  return 0;
+}
+
+// `ph` of parallel_reader_genotype_only (hts_parallel_reader.cpp:782-893).  The connection entries arrive sorted by
+// (sample, hap1, allele1, hap2, allele2), so the support vector of (sample, hap1, allele1) -> hap2 is one contiguous run;
+// runs are visited once and looked at only when the two bubbles are < 100 bp apart.
+int gtb_phase_support(const gtb_accumulators * acc, uint64_t n_conn, const gtb_connection * conn, uint64_t * n_out,
+                      gtb_phase_support_entry * out)
+{
+  if (!acc || !n_out || (n_conn && !conn))
+    return fail(GTB_ERR_ARG, "bad arguments");
+  uint64_t const NS = acc->n_samples;
+  uint32_t const NB = acc->n_bubbles;
+  std::map<uint64_t, int8_t> ph; // hap1 << 48 | allele1 << 32 | hap2 << 16 | allele2
+  auto seen = [&](uint32_t b, uint64_t s, uint32_t a, bool & clearly, bool & not_seen) {
+    uint32_t const num = acc->n_alleles[b];
+    const uint16_t * cv = acc->gt_coverage + acc->cov_off[b] * NS + s * num;
+    double total = 0.0;
+    for (uint32_t k = 0; k < num; ++k)
+      total += cv[k];
+    double const frac = (double)cv[a] / total;
+    clearly = cv[a] >= 4 || frac >= 0.28;
+    not_seen = cv[a] <= 2 || frac < 0.22;
+  };
+  for (uint64_t i = 0; i < n_conn;)
+  {
+    gtb_connection const & f = conn[i];
+    uint64_t j = i;
+    long total_support = 0;
+    while (j < n_conn && conn[j].sample == f.sample && conn[j].hap1 == f.hap1 && conn[j].allele1 == f.allele1 &&
+           conn[j].hap2 == f.hap2)
+      total_support += (long)conn[j++].count;
+    if (f.hap1 >= NB || f.hap2 >= NB || f.sample >= NS || f.allele1 >= acc->n_alleles[f.hap1])
+      return fail(GTB_ERR_ARG, "connection entry out of range");
+    bool const near = f.hap2 > f.hap1 && (long long)acc->bubble_id[f.hap2] < (long long)acc->bubble_id[f.hap1] + 100;
+    // the reference's ps2 loop stops at the FIRST bubble >= 100 bp away; bubble ids are non-decreasing, so "near" is the same set
+    if (near && f.allele1 >= 1)
+    {
+      bool clearly1, not1;
+      seen(f.hap1, f.sample, f.allele1, clearly1, not1);
+      uint32_t const num2 = acc->n_alleles[f.hap2];
+      uint64_t r = i;
+      for (uint32_t a2 = 1; a2 < num2; ++a2)
+      {
+        while (r < j && conn[r].allele2 < a2)
+          ++r;
+        double const support = (r < j && conn[r].allele2 == a2) ? (double)conn[r].count : 0.0;
+        bool clearly2, not2;
+        seen(f.hap2, f.sample, a2, clearly2, not2);
+        int8_t flag = 0;
+        if (not1 && not2)
+          continue;
+        if ((not1 && clearly2) || (not2 && clearly1))
+          flag = 2; // IS_ANY_ANTI_HAP_SUPPORT
+        else if (total_support <= 2)
+          continue;
+        else if (clearly1 && clearly2 && support / (double)total_support > 0.78)
+          flag = 1; // IS_ANY_HAP_SUPPORT
+        else if (support / (double)total_support < 0.22)
+          flag = 2;
+        else
+          continue;
+        ph[((uint64_t)f.hap1 << 48) | ((uint64_t)f.allele1 << 32) | ((uint64_t)f.hap2 << 16) | a2] |= flag;
+      }
+    }
+    i = j;
+  }
+  if (out)
+  {
+    if (*n_out < ph.size())
+      return fail(GTB_ERR_ARG, "phase support output too small");
+    for (auto const & kv : ph)
+    {
+      memset(out, 0, sizeof(*out));
+      out->hap1 = (uint16_t)(kv.first >> 48);
+      out->allele1 = (uint16_t)(kv.first >> 32);
+      out->hap2 = (uint16_t)(kv.first >> 16);
+      out->allele2 = (uint16_t)kv.first;
+      out->flags = kv.second;
+      ++out;
+    }
+  }
+  *n_out = ph.size();
   return 0;
 }
 

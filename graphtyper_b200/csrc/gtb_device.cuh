@@ -84,7 +84,16 @@ struct DevRegion
   // SV graphs: ReferenceDepth as a difference array per sample (prefix-summed on download), (depth_size + 1) ints each
   int * ref_depth_delta;
   uint32_t depth_size, reference_offset;
+  // phasing connections (HapSample::connections, haplotype.hpp:42) of all samples of the pool: one open-addressing table,
+  // key = CONN_OCCUPIED | sample << 42 | hap1 << 26 | allele1 << 21 | hap2 << 5 | allele2 (so key order = the order the
+  // entries are reported in), value = widened support count.  conn_mask == 0: connections are off.
+  unsigned long long * conn_keys; // [conn_mask + 1], 0 = empty
+  uint32_t * conn_vals;           // [conn_mask + 1]
+  uint32_t * conn_state;          // [0] occupied slots, [1] set when an insert found the table full
+  uint32_t conn_mask, pad1;
 };
+constexpr unsigned long long CONN_OCCUPIED = 1ull << 63;
+constexpr uint32_t CONN_MAX_SAMPLES = 1u << 21, CONN_MAX_BUBBLES = 1u << 16;
 
 // Records of one submit (possibly several regions concatenated), SoA on the device.
 struct DevBatch
@@ -173,7 +182,11 @@ void launch_build_table(const IndexSlot * uniq, uint32_t n, IndexSlot * table, u
 void launch_probe(const LaunchParams & p, void * stream);
 void launch_chain(const LaunchParams & p, void * stream);
 void launch_slow(const LaunchParams & p, void * stream);
-void launch_score(const LaunchParams & p, void * stream);
+void launch_score(const LaunchParams & p, bool with_connections, void * stream);
+// connection table maintenance: re-insert every entry of (keys, vals)[0..n_slots) into R's (larger, zeroed) table;
+// compact the non-empty entries of R's table into (out_keys, out_vals), count in *out_n
+void launch_conn_rehash(const unsigned long long * keys, const uint32_t * vals, uint32_t n_slots, const DevRegion & R, void * stream);
+void launch_conn_compact(const DevRegion & R, unsigned long long * out_keys, uint32_t * out_vals, uint32_t * out_n, void * stream);
 int align_kernel_blocks_per_sm();
 size_t align_spill_bytes();
 size_t huge_state_bytes();

@@ -1907,8 +1907,77 @@ __device__ __forceinline__ void add_coverage(uint16_t & coverage, uint16_t c) //
     coverage = (coverage == 0 || c == 0) ? MULTI_REF_COVERAGE : MULTI_ALT_COVERAGE;
 }
 
+// ---- phasing connections (vcf_writer.cpp:587-637 inside one read, :186-249 across the two mates)
+__device__ __forceinline__ unsigned long long conn_key(int sample, uint32_t hap1, uint32_t a1, uint32_t hap2, uint32_t a2)
+{
+  return CONN_OCCUPIED | ((unsigned long long)(uint32_t)sample << 42) | ((unsigned long long)hap1 << 26) |
+         ((unsigned long long)a1 << 21) | ((unsigned long long)hap2 << 5) | (unsigned long long)a2;
+}
+
+__device__ void conn_insert(const DevRegion & R, unsigned long long key, uint32_t inc)
+{
+  uint32_t const mask = R.conn_mask;
+  uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & mask;
+  for (uint32_t n = 0; n <= mask; ++n)
+  {
+    unsigned long long cur = R.conn_keys[h];
+    if (cur == 0)
+    {
+      cur = atomicCAS(&R.conn_keys[h], 0ull, key);
+      if (cur == 0)
+      {
+        atomicAdd(&R.conn_state[0], 1u);
+        cur = key;
+      }
+    }
+    if (cur == key)
+    {
+      atomicAdd(&R.conn_vals[h], inc);
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+  atomicExch(&R.conn_state[1], 1u); // table full: reported as GTB_ERR_CAPACITY by the host
+}
+
+// every allele pair of two touched bubbles, oriented from the earlier bubble to the later one
+__device__ void conn_add_pairs(const DevRegion & R, int sample, uint32_t hap_a, allele_mask_t Ea, uint32_t hap_b, allele_mask_t Eb,
+                               uint32_t inc)
+{
+  if (hap_a == hap_b || inc == 0)
+    return;
+  if (hap_a > hap_b)
+  {
+    uint32_t const th = hap_a;
+    hap_a = hap_b;
+    hap_b = th;
+    allele_mask_t const te = Ea;
+    Ea = Eb;
+    Eb = te;
+  }
+  for (allele_mask_t m1 = Ea; m1; m1 &= m1 - 1)
+    for (allele_mask_t m2 = Eb; m2; m2 &= m2 - 1)
+      conn_insert(R, conn_key(sample, hap_a, (uint32_t)__ffs((int)m1) - 1, hap_b, (uint32_t)__ffs((int)m2) - 1), inc);
+}
+
+// (bubble, explained alleles) of one scored read: the keys of the reference's new_connections map
+struct TouchList
+{
+  int n;
+  uint32_t hap[MAX_TOUCH];
+  allele_mask_t expl[MAX_TOUCH];
+};
+
+// the cross-mate part of update_haplotype_scores_geno's merge: +1 for every (key of mate 1, key of mate 2) on different bubbles
+__device__ void conn_merge_mates(const DevRegion & R, int sample, const TouchList & a, const TouchList & b)
+{
+  for (int i = 0; i < a.n; ++i)
+    for (int j = 0; j < b.n; ++j)
+      conn_add_pairs(R, sample, a.hap[i], a.expl[i], b.hap[j], b.expl[j], 1u);
+}
+
 // push_to_haplotype_scores (vcf_writer.cpp:503-676) + explain_to_score / coverage_to_gts / *_to_stats
-__device__ bool push_scores(const LaunchParams & P, const DevRegion & R, const Geno & geno, int sample)
+__device__ bool push_scores(const LaunchParams & P, const DevRegion & R, const Geno & geno, int sample, TouchList * touched = nullptr)
 {
   GR g(R);
   int const clipped_bp = (int)geno.read_length - (int)geno.s.longest;
@@ -1975,6 +2044,21 @@ __device__ bool push_scores(const LaunchParams & P, const DevRegion & R, const G
       }
     }
     w += 2 * nvar;
+  }
+
+  if (touched) // "check connections": weight n1*n2, a pair of uniquely explained bubbles counts once, 3 <= weight <= 6 -> 6/weight
+  {
+    touched->n = nt;
+    for (int i = 0; i < nt; ++i)
+    {
+      touched->hap[i] = t_hap[i];
+      touched->expl[i] = t_expl[i];
+      for (int j = i + 1; j < nt; ++j)
+      {
+        uint32_t const weight = (uint32_t)__popc(t_expl[i]) * (uint32_t)__popc(t_expl[j]);
+        conn_add_pairs(R, sample, t_hap[i], t_expl[i], t_hap[j], t_expl[j], weight >= 3u ? 6u / weight : 1u);
+      }
+    }
   }
 
   uint32_t const NS = R.n_samples;
@@ -2233,6 +2317,8 @@ __device__ void make_genos(const LaunchParams & P, int rec, Geno & first, Geno &
 }
 } // namespace
 
+// CONN: also build the phasing connections (regions whose conn_mask is 0 skip them at run time)
+template <bool CONN>
 __global__ void __launch_bounds__(128) score_kernel(LaunchParams P)
 {
   uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2242,6 +2328,7 @@ __global__ void __launch_bounds__(128) score_kernel(LaunchParams P)
   int32_t const m = P.batch.mate[i];
   const DevRegion & R = P.regions[P.batch.region[i]];
   int const sample = P.batch.sample[i];
+  bool const conn = CONN && R.conn_mask != 0;
 
   if (m >= 0)
   {
@@ -2281,10 +2368,24 @@ __global__ void __launch_bounds__(128) score_kernel(LaunchParams P)
       add_ref_depth(P, R, g[s2], sample);
     }
     bool ok = true;
-    if (geno_good(R, g[s1]))
-      ok = push_scores(P, R, g[s1], sample) && ok;
-    if (geno_good(R, g[s2]))
-      ok = push_scores(P, R, g[s2], sample) && ok;
+    if (CONN && conn)
+    {
+      TouchList k1, k2;
+      k1.n = k2.n = 0;
+      if (geno_good(R, g[s1]))
+        ok = push_scores(P, R, g[s1], sample, &k1) && ok;
+      if (geno_good(R, g[s2]))
+        ok = push_scores(P, R, g[s2], sample, &k2) && ok;
+      if (ok)
+        conn_merge_mates(R, sample, k1, k2);
+    }
+    else
+    {
+      if (geno_good(R, g[s1]))
+        ok = push_scores(P, R, g[s1], sample) && ok;
+      if (geno_good(R, g[s2]))
+        ok = push_scores(P, R, g[s2], sample) && ok;
+    }
     if (!ok)
       atomicAdd(&P.counters->n_overflow, 1ull);
     atomicAdd(&P.counters->n_pairs_scored, 1ull);
@@ -2313,7 +2414,8 @@ __global__ void __launch_bounds__(128) score_kernel(LaunchParams P)
     add_ref_depth(P, R, g[s1], sample);
     if (geno_good(R, g[s1]))
     {
-      if (!push_scores(P, R, g[s1], sample))
+      TouchList k1;
+      if (!push_scores(P, R, g[s1], sample, (CONN && conn) ? &k1 : nullptr))
         atomicAdd(&P.counters->n_overflow, 1ull);
       atomicAdd(&P.counters->n_singles_scored, 1ull);
     }
@@ -2341,11 +2443,32 @@ __global__ void __launch_bounds__(128) score_kernel(LaunchParams P)
       sel.flags |= F_MAPQ_BAD; // the unpaired path does set IS_MAPQ_BAD on the flipped orientation (alignment.cpp:419)
     if (geno_good(R, sel))
     {
-      if (!push_scores(P, R, sel, sample))
+      TouchList k1;
+      if (!push_scores(P, R, sel, sample, (CONN && conn) ? &k1 : nullptr))
         atomicAdd(&P.counters->n_overflow, 1ull);
       atomicAdd(&P.counters->n_singles_scored, 1ull);
     }
   }
+}
+
+// ================================================================================================ connection table upkeep
+__global__ void __launch_bounds__(256) conn_rehash_kernel(const unsigned long long * keys, const uint32_t * vals, uint32_t n_slots,
+                                                          DevRegion R)
+{
+  uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_slots && keys[i] != 0)
+    conn_insert(R, keys[i], vals[i]);
+}
+
+__global__ void __launch_bounds__(256) conn_compact_kernel(DevRegion R, unsigned long long * out_keys, uint32_t * out_vals,
+                                                           uint32_t * out_n)
+{
+  uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > R.conn_mask || R.conn_keys[i] == 0)
+    return;
+  uint32_t const o = atomicAdd(out_n, 1u);
+  out_keys[o] = R.conn_keys[i];
+  out_vals[o] = R.conn_vals[i];
 }
 
 // ================================================================================================ table build
@@ -2448,12 +2571,27 @@ void launch_slow(const LaunchParams & p, void * stream)
 
 size_t huge_state_bytes() { return (size_t)sm_count() * sizeof(HugeState); }
 
-void launch_score(const LaunchParams & p, void * stream)
+void launch_score(const LaunchParams & p, bool with_connections, void * stream)
 {
   if (p.batch.n_records == 0)
     return;
   uint32_t const grid = (p.batch.n_records + 127) / 128;
-  score_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+  if (with_connections)
+    score_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+  else
+    score_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+}
+
+void launch_conn_rehash(const unsigned long long * keys, const uint32_t * vals, uint32_t n_slots, const DevRegion & R, void * stream)
+{
+  if (n_slots)
+    conn_rehash_kernel<<<(n_slots + 255) / 256, 256, 0, (cudaStream_t)stream>>>(keys, vals, n_slots, R);
+}
+
+void launch_conn_compact(const DevRegion & R, unsigned long long * out_keys, uint32_t * out_vals, uint32_t * out_n, void * stream)
+{
+  if (R.conn_mask)
+    conn_compact_kernel<<<(R.conn_mask + 256) / 256, 256, 0, (cudaStream_t)stream>>>(R, out_keys, out_vals, out_n);
 }
 
 } // namespace gtb

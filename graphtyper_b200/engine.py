@@ -24,6 +24,7 @@ EXPORTS = [
     "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_scan_calls", "gtb_merge_varstats", "gtb_replay_last",
     "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_set_chunks", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators", "gtb_allreduce_accumulators_multi", "gtb_debug_counters",
     "gtb_sw_align_batch", "gtb_sw_last_timing", "gtb_sw_replay_last", "gtb_set_index_build",
+    "gtb_set_connections", "gtb_connections_size", "gtb_connections", "gtb_phase_support",
 ]
 
 
@@ -89,6 +90,9 @@ def load_library() -> C.CDLL:
     L.gtb_sw_last_timing.argtypes = [vp, fp, fp, fp]
     L.gtb_sw_replay_last.argtypes = [vp]
     L.gtb_set_index_build.argtypes = [vp, C.c_int]
+    L.gtb_set_connections.argtypes = [vp, C.c_int]
+    L.gtb_connections_size.argtypes = [vp, C.c_int, abi.u64p]
+    L.gtb_connections.argtypes = [vp, C.c_int, C.c_void_p]
     _lib = L
     return L
 
@@ -198,6 +202,23 @@ class Context:
     def set_index_build(self, on_device: bool) -> None:
         """Device-side (default) or host-side construction of the region k-mer indexes."""
         self._check(self.lib.gtb_set_index_build(self.h, 1 if on_device else 0))
+
+    def set_connections(self, on: int = 1) -> None:
+        """Phasing connections (HapSample::connections) for pools begun afterwards; `on` > 1 = table slots per record."""
+        self._check(self.lib.gtb_set_connections(self.h, int(on)))
+
+    def connections(self, region_id: int) -> np.ndarray:
+        """Structured array (abi.CONNECTION_DTYPE) sorted by (sample, hap1, allele1, hap2, allele2)."""
+        n = C.c_uint64()
+        self._check(self.lib.gtb_connections_size(self.h, region_id, C.byref(n)))
+        out = np.zeros(n.value, abi.CONNECTION_DTYPE)
+        if n.value:
+            self._check(self.lib.gtb_connections(self.h, region_id, out.ctypes.data))
+        return out
+
+    def phase_support(self, acc: abi.HostAccumulators, conn: np.ndarray) -> np.ndarray:
+        """The `ph` map (hts_parallel_reader.cpp:782-893) as a structured array (abi.PHASE_DTYPE); pure host function."""
+        return abi.phase_support(self.lib, "gtb_phase_support", acc, conn)
 
     def set_chunks(self, n: int) -> None:
         self._check(self.lib.gtb_set_chunks(self.h, n))

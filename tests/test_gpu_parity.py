@@ -53,6 +53,62 @@ def test_cuda_matches_reference(pre, ctx):
         ctx.region_end(7)
 
 
+@pytest.mark.parametrize("pre", ALL, ids=[os.path.basename(p) for p in ALL])
+def test_cuda_connections_match_reference(pre, ctx):
+    """Phasing connections (HapSample::connections) built by score_kernel<true> and the derived `ph` map against the
+    compiled reference; the accumulators must not change when connections are collected."""
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    rd = gtba.load(pre + ".reads.gtba")
+    b = abi.batch_from_probe(rd)
+    ns = n_samples_of(rd)
+    pa = gtba.load(pre + ".accum.gtba")
+    ctx.region_begin(9, g)
+    ctx.set_connections(1)
+    try:
+        ctx.pool_begin(9, ns)
+        ctx.submit(9, b)
+        acc = ctx.pool_finish(9)
+        conn = ctx.connections(9)
+        compare.compare_connections(compare.probe_connections(pa), abi.connections_as_table(conn), "cuda")
+        compare.compare_accum(compare.probe_accum(pa), acc.as_dict(), "cuda+conn")
+        if "ph_tuples" in pa:
+            got = abi.phase_as_table(ctx.phase_support(acc, conn))
+            assert np.array_equal(pa["ph_tuples"].reshape(-1, 5).astype(np.uint32), got)
+        # reset clears the table; a second pass gives the same entries (idempotence of reset + submit)
+        ctx.pool_reset(9)
+        ctx.submit(9, b)
+        assert np.array_equal(abi.connections_as_table(ctx.connections(9)), abi.connections_as_table(conn))
+    finally:
+        ctx.set_connections(0)
+        ctx.region_end(9)
+
+
+def test_connection_table_grows_and_replay_doubles(ctx):
+    """A 2-slots-per-record budget forces table growth (re-insert on the device) between submits; the result is unchanged.
+    Replaying the resident batch (the last shard) only ever adds counts (monotonicity)."""
+    pre = [p for p in ALL if os.path.basename(p) in ("stress.r0", "mini_stress.r0")][-1]
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    rd = gtba.load(pre + ".reads.gtba")
+    b = abi.batch_from_probe(rd)
+    ns = n_samples_of(rd)
+    pa = gtba.load(pre + ".accum.gtba")
+    want = compare.probe_connections(pa)
+    ctx.region_begin(9, g)
+    ctx.set_connections(2)
+    try:
+        ctx.pool_begin(9, ns)
+        for shard in abi.shard_batch(b, 3):  # three submits into the same pool: the table grows between them
+            ctx.submit(9, shard)
+        got = abi.connections_as_table(ctx.connections(9))
+        compare.compare_connections(want, got, "cuda small budget")
+        ctx.replay()
+        again = abi.connections_as_table(ctx.connections(9))
+        assert np.array_equal(again[:, :5], got[:, :5]) and (again[:, 5] >= got[:, 5]).all() and again[:, 5].sum() > got[:, 5].sum()
+    finally:
+        ctx.set_connections(0)
+        ctx.region_end(9)
+
+
 def test_region_batched_submit_equals_separate(ctx):
     """Several regions in ONE launch give the same accumulators as one launch per region."""
     pres = ALL[:3]

@@ -59,6 +59,27 @@ def test_host_finalisation_matches_reference(pre):
     ctx.close()
 
 
+@pytest.mark.parametrize("pre", SMALL, ids=[os.path.basename(p) for p in SMALL])
+def test_host_phase_support_matches_reference(pre):
+    """gtb_phase_support (pure host function) on the reference's own connections + coverage = the reference's `ph` map."""
+    pa = gtba.load(pre + ".accum.gtba")
+    if "ph_tuples" not in pa:
+        pytest.skip("SV fixture: the reference never writes haplotypes for SV graphs")
+    ref = compare.probe_accum(pa)
+    ns, nb = int(pa["meta"][0]), int(pa["meta"][1])
+    acc = abi.HostAccumulators(nb, int(ref["score_off"][-1]), int(ref["cov_off"][-1]), ns)
+    for k in ("bubble_id", "n_alleles", "score_off", "cov_off", "gt_coverage"):
+        getattr(acc, k)[:] = ref[k]
+    tab = compare.probe_connections(pa)
+    conn = np.zeros(len(tab), abi.CONNECTION_DTYPE)
+    for j, k in enumerate(("sample", "hap1", "allele1", "hap2", "allele2", "count")):
+        conn[k] = tab[:, j]
+    ctx = engine.Context(device=-1)
+    got = abi.phase_as_table(ctx.phase_support(acc, conn))
+    assert np.array_equal(pa["ph_tuples"].reshape(-1, 5).astype(np.uint32), got)
+    ctx.close()
+
+
 def test_no_cpu_fallback():
     ctx = engine.Context(device=-1)
     g = abi.HostGraph.from_gtba(gtba.load(SMALL[0] + ".graph.gtba"))
