@@ -133,7 +133,7 @@ struct Region
 // Everything one in-flight (chunk of a) submit owns.  Slot 0 doubles as the "last batch" of the debug taps.
 struct BatchState
 {
-  DeviceBuffer d_batch, d_summaries, d_pool, d_counters, d_seedrecs, d_slow;
+  DeviceBuffer d_batch, d_summaries, d_pool, d_counters, d_seedrecs, d_slow, d_task_times;
   PinnedBuffer h_batch, h_counters;
   LaunchParams P{};
   uint32_t n_tasks = 0;
@@ -141,9 +141,10 @@ struct BatchState
   std::vector<uint32_t> unit_begin;    // per region: first unit index (size n+1)
   std::vector<uint32_t> rec_begin;
   bool with_conn = false;              // some region of this chunk collects phasing connections
+  cudaStream_t stream = nullptr;       // probe + chain of this chunk (chunks run concurrently, each on its own stream)
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  // ev: 0 h2d start (copy stream), 1 h2d done (copy stream), 2 kernels start, 3 after probe, 4 after chain,
-  //     5 after slow, 6 after score, 7 after counters D2H
+  // ev: 0 h2d start (copy stream), 1 h2d done (copy stream), 2 kernels start, 3 after probe, 4 after chain (chunk stream),
+  //     5 before score, 6 after score, 7 after counters D2H (main stream)
   void release()
   {
     d_batch.release();
@@ -151,15 +152,17 @@ struct BatchState
     d_pool.release();
     d_counters.release();
     d_seedrecs.release();
+    d_task_times.release();
     d_slow.release();
     h_batch.release();
     h_counters.release();
     for (auto & e : ev)
       if (e)
         cudaEventDestroy(e);
+    if (stream)
+      cudaStreamDestroy(stream);
   }
 };
-constexpr int MAX_CHUNKS = 4;
 
 struct Ctx
 {
@@ -179,6 +182,8 @@ struct Ctx
   bool have_last = false;
   bool debug = false;
   int forced_chunks = 0; // gtb_set_chunks / GTB_CHUNKS: 0 = automatic
+  cudaEvent_t ev_slow[3] = {nullptr, nullptr, nullptr}; // [0],[1] around slow_kernel + huge_kernel (main stream);
+                                                        // [2] main-stream position when a submit / replay starts
   int connections = 0;   // gtb_set_connections: 0 off, otherwise table slots reserved per submitted record
   PinnedBuffer h_conn_state;
   float t_h2d = 0, t_align = 0, t_score = 0, t_d2h = 0, t_probe = 0, t_chain = 0, t_slow = 0;
@@ -459,8 +464,14 @@ int gtb_create(int device_id, gtb_ctx ** out)
       e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
 
     for (int k = 0; k < MAX_CHUNKS; ++k)
+    {
       for (int i = 0; i < 8 && e == cudaSuccess; ++i)
         e = cudaEventCreate(&c->bs[k].ev[i]);
+      if (e == cudaSuccess)
+        e = cudaStreamCreateWithFlags(&c->bs[k].stream, cudaStreamNonBlocking);
+    }
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i)
+      e = cudaEventCreate(&c->ev_slow[i]);
     if (e != cudaSuccess)
     {
       delete c;
@@ -510,6 +521,9 @@ void gtb_destroy(gtb_ctx * ctx)
     c->d_sw_bt.release();
     c->h_sw.release();
     for (auto & e : c->sw_ev)
+      if (e)
+        cudaEventDestroy(e);
+    for (auto & e : c->ev_slow)
       if (e)
         cudaEventDestroy(e);
     if (c->copy_stream)
@@ -1109,31 +1123,52 @@ int gtb_pool_begin(gtb_ctx * ctx, int region_id, int n_samples)
   return 0;
 }
 
-// Enqueues the kernel sequence of one chunk on the compute stream (after its H2D copy has landed).
-static int launch_chunk(Ctx * c, BatchState & B)
+// Front half of one chunk on the chunk's own stream, as soon as its H2D copy has landed: probe + chain.  The chunks of a
+// submit run concurrently -- chain_kernel is bound by the latency of its longest task (~0.25 ms whatever the chunk size),
+// so a chunk's chain overlaps the next chunk's copy and probe instead of queueing behind them.
+static int launch_front(Ctx * c, BatchState & B, cudaEvent_t after)
 {
   LaunchParams & P = B.P;
-  CUDA_TRY(cudaStreamWaitEvent(c->stream, B.ev[1], 0));
-  CUDA_TRY(cudaMemsetAsync(B.d_counters.p, 0, sizeof(DevCounters), c->stream));
+  cudaStream_t const s = B.stream;
+  CUDA_TRY(cudaStreamWaitEvent(s, after, 0)); // everything queued on the main stream before this submit
+  CUDA_TRY(cudaStreamWaitEvent(s, B.ev[1], 0));
+  CUDA_TRY(cudaMemsetAsync(B.d_counters.p, 0, sizeof(DevCounters), s));
   // orientations that are not aligned keep an all-zero summary (no paths)
-  CUDA_TRY(cudaMemsetAsync(P.summaries, 0, (size_t)P.batch.n_units * 2 * sizeof(TaskSummary), c->stream));
+  CUDA_TRY(cudaMemsetAsync(P.summaries, 0, (size_t)P.batch.n_units * 2 * sizeof(TaskSummary), s));
   if (P.tap.list_count)
-    CUDA_TRY(cudaMemsetAsync(P.tap.list_count, 0, (size_t)P.batch.n_units * 2 * (NLISTS * 2 + 1) * 4, c->stream));
-  CUDA_TRY(cudaEventRecord(B.ev[2], c->stream));
-  launch_probe(P, c->stream);
-  CUDA_TRY(cudaEventRecord(B.ev[3], c->stream));
-  launch_chain(P, c->stream);
-  CUDA_TRY(cudaEventRecord(B.ev[4], c->stream));
-  // (Running slow/huge/score of chunk k on a third stream, concurrently with probe/chain of chunk k+1, was measured and
-  // rejected: slow_kernel is one long single-lane task per warp, and sharing the SM schedulers with a 70 %-issue-bound
-  // probe_kernel stretches it from 0.1 ms to 0.5 ms.)
+    CUDA_TRY(cudaMemsetAsync(P.tap.list_count, 0, (size_t)P.batch.n_units * 2 * (NLISTS * 2 + 1) * 4, s));
+  CUDA_TRY(cudaEventRecord(B.ev[2], s));
+  launch_probe(P, s);
+  CUDA_TRY(cudaEventRecord(B.ev[3], s));
+  launch_chain(P, s);
+  CUDA_TRY(cudaEventRecord(B.ev[4], s));
+  return 0;
+}
+
+// Back half of all chunks on the main stream: ONE slow_kernel + huge_kernel launch over every chunk's queue (a launch costs
+// the latency of its slowest single-lane task, ~0.1 ms, however many chunks feed it), then score + counters per chunk.
+static int launch_back(Ctx * c, int n_chunks)
+{
   cudaStream_t const ts = c->stream;
-  launch_slow(P, ts);
-  CUDA_TRY(cudaEventRecord(B.ev[5], ts));
-  launch_score(P, B.with_conn, ts);
-  CUDA_TRY(cudaEventRecord(B.ev[6], ts));
-  CUDA_TRY(cudaMemcpyAsync(B.h_counters.p, B.d_counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, ts));
-  CUDA_TRY(cudaEventRecord(B.ev[7], ts));
+  MultiLaunch M;
+  M.n = n_chunks;
+  for (int k = 0; k < n_chunks; ++k)
+  {
+    CUDA_TRY(cudaStreamWaitEvent(ts, c->bs[k].ev[4], 0));
+    M.p[k] = c->bs[k].P;
+  }
+  CUDA_TRY(cudaEventRecord(c->ev_slow[0], ts));
+  launch_slow(M, ts);
+  CUDA_TRY(cudaEventRecord(c->ev_slow[1], ts));
+  for (int k = 0; k < n_chunks; ++k)
+  {
+    BatchState & B = c->bs[k];
+    CUDA_TRY(cudaEventRecord(B.ev[5], ts));
+    launch_score(B.P, B.with_conn, ts);
+    CUDA_TRY(cudaEventRecord(B.ev[6], ts));
+    CUDA_TRY(cudaMemcpyAsync(B.h_counters.p, B.d_counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, ts));
+    CUDA_TRY(cudaEventRecord(B.ev[7], ts));
+  }
   return 0;
 }
 
@@ -1161,13 +1196,27 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     c->t_probe += t;
     cudaEventElapsedTime(&t, B.ev[3], B.ev[4]);
     c->t_chain += t;
-    cudaEventElapsedTime(&t, B.ev[4], B.ev[5]);
-    c->t_slow += t;
     cudaEventElapsedTime(&t, B.ev[5], B.ev[6]);
     c->t_score += t;
     cudaEventElapsedTime(&t, B.ev[6], B.ev[7]);
     c->t_d2h += t;
     DevCounters const * kc = static_cast<DevCounters *>(B.h_counters.p);
+    if (B.P.task_times && k == 0)
+      if (const char * fn = getenv("GTB_TASK_TIMES"))
+      {
+        std::vector<unsigned long long> tt((size_t)B.P.n_active * 2);
+        std::vector<uint32_t> at(B.P.n_active);
+        cudaMemcpy(tt.data(), B.P.task_times, tt.size() * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(at.data(), B.P.active_tasks, at.size() * 4, cudaMemcpyDeviceToHost);
+        if (FILE * f = fopen(fn, "wb"))
+        {
+          uint64_t const n = B.P.n_active;
+          fwrite(&n, 8, 1, f);
+          fwrite(tt.data(), 8, tt.size(), f);
+          fwrite(at.data(), 4, at.size(), f);
+          fclose(f);
+        }
+      }
     c->last_n_slow += kc->n_slow;
     st.n_records += B.P.batch.n_records;
     st.n_alignments += B.P.batch.n_units;
@@ -1175,11 +1224,17 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     st.n_pairs_scored += kc->n_pairs_scored;
     st.n_singles_scored += kc->n_singles_scored;
     st.n_capacity_overflow += kc->n_overflow;
-    st.kernel_launches += (B.P.n_active ? 4 : 0) + (B.P.batch.n_records ? 1 : 0); // probe, chain, slow, huge + score
+    st.kernel_launches += (B.P.n_active ? 2 : 0) + (B.P.batch.n_records ? 1 : 0); // probe, chain + score
     n_overflow += kc->n_overflow;
     n_input_error += kc->n_input_error;
     for (int q = 0; q < 12; ++q)
       reasons[q] += kc->final_reasons[q];
+  }
+  {
+    float t = 0;
+    cudaEventElapsedTime(&t, c->ev_slow[0], c->ev_slow[1]);
+    c->t_slow = t;
+    st.kernel_launches += st.n_oriented ? 2 : 0; // slow_kernel + huge_kernel, once per submit
   }
   c->t_align = c->t_probe + c->t_chain + c->t_slow;
   if (stats)
@@ -1438,6 +1493,13 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   P.n_active = n_active;
   P.active_tasks = reinterpret_cast<const uint32_t *>(d + o_active);
   P.seed_recs = B.d_seedrecs.p;
+  P.task_times = nullptr;
+  if (getenv("GTB_TASK_TIMES")) // profiling aid: per-task start/end times of chain_kernel, dumped by collect_chunks
+  {
+    if (int rc = B.d_task_times.reserve((size_t)n_active * 16 + 16))
+      return rc;
+    P.task_times = static_cast<unsigned long long *>(B.d_task_times.p);
+  }
   P.slow_tasks = static_cast<uint32_t *>(B.d_slow.p);
   P.huge_tasks = P.slow_tasks + n_active + 16;
   P.huge_states = c->d_huge.p;
@@ -1535,10 +1597,8 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
     int const forced = c->forced_chunks > 0 ? c->forced_chunks : env_forced;
     if (forced > 0)
       n_chunks = std::min({n, MAX_CHUNKS, forced});
-    else if (total >= 4000000)
-      n_chunks = std::min(n, MAX_CHUNKS);
     else if (total >= 65536)
-      n_chunks = 2;
+      n_chunks = std::min(n, 3);
   }
   std::vector<int> cut(n_chunks + 1, n);
   cut[0] = 0;
@@ -1558,6 +1618,7 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
     cut[k] = std::max(cut[k], cut[k - 1]);
   cut[n_chunks] = n;
   c->n_chunks_last = n_chunks;
+  CUDA_TRY(cudaEventRecord(c->ev_slow[2], c->stream)); // the chunk streams start after everything queued so far (resets)
   for (int k = 0; k < n_chunks; ++k)
   {
     int const b0 = cut[k], m = cut[k + 1] - cut[k];
@@ -1566,9 +1627,11 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
     c->bs[k].with_conn = false;
     for (int i = b0; i < b0 + m; ++i)
       c->bs[k].with_conn = c->bs[k].with_conn || regs[i]->conn_cap != 0;
-    if (int rc = launch_chunk(c, c->bs[k]))
+    if (int rc = launch_front(c, c->bs[k], c->ev_slow[2]))
       return rc;
   }
+  if (int rc = launch_back(c, n_chunks))
+    return rc;
   c->have_last = true;
   if (int rc = collect_chunks(c, stats, true))
     return rc;
@@ -1587,9 +1650,12 @@ int gtb_replay_last(gtb_ctx * ctx, gtb_submit_stats * stats)
   if (!c || !c->have_last)
     return fail(GTB_ERR_STATE, "no resident batch to replay");
   cudaSetDevice(c->device);
+  CUDA_TRY(cudaEventRecord(c->ev_slow[2], c->stream)); // orders the chunk streams after earlier main-stream work
   for (int k = 0; k < c->n_chunks_last; ++k)
-    if (int rc = launch_chunk(c, c->bs[k]))
+    if (int rc = launch_front(c, c->bs[k], c->ev_slow[2]))
       return rc;
+  if (int rc = launch_back(c, c->n_chunks_last))
+    return rc;
   return collect_chunks(c, stats, false);
 }
 
@@ -1647,7 +1713,7 @@ int gtb_set_chunks(gtb_ctx * ctx, int n_chunks)
 {
   auto * c = reinterpret_cast<Ctx *>(ctx);
   if (!c || n_chunks < 0 || n_chunks > MAX_CHUNKS)
-    return fail(GTB_ERR_ARG, "n_chunks must be 0..4");
+    return fail(GTB_ERR_ARG, "n_chunks must be 0..8");
   c->forced_chunks = n_chunks;
   return 0;
 }

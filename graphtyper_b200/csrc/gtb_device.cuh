@@ -29,8 +29,14 @@ constexpr int FAST_P = 6, FAST_V = 8, FAST_C = 6, FAST_CV = 8, FAST_WL = 12, FAS
 constexpr int SEED_INLINE = 10;     // index bucket references handed from probe_kernel to chain_kernel per task
 constexpr int SEED_REC_BYTES = 16 + 8 * SEED_INLINE;
 constexpr int PROBE_WARPS = 8;      // warps per block of probe_kernel
-constexpr int CHAIN_THREADS = 128;  // threads per block of chain_kernel
-constexpr int CHAIN_MIN_BLOCKS = 8;  // <= 64 registers per thread
+#ifndef GTB_CHAIN_THREADS
+#define GTB_CHAIN_THREADS 128
+#endif
+#ifndef GTB_CHAIN_MIN_BLOCKS
+#define GTB_CHAIN_MIN_BLOCKS 8
+#endif
+constexpr int CHAIN_THREADS = GTB_CHAIN_THREADS;     // threads per block of chain_kernel
+constexpr int CHAIN_MIN_BLOCKS = GTB_CHAIN_MIN_BLOCKS; // 8 x 128 -> <= 64 registers per thread
 constexpr int MAX_TOUCH = 48; // bubbles touched by one read in the accumulate kernel (= HUGE_V)
 using allele_mask_t = uint32_t; // allele set of one bubble on a path: bit a = allele a  (<= 32 alleles per bubble)
 constexpr int MAX_ALLELES = 32;
@@ -174,14 +180,26 @@ struct LaunchParams
   uint32_t * slow_tasks;        // [n_active] queue filled by chain_kernel
   uint32_t * huge_tasks;        // [n_active] queue filled by slow_kernel
   void * huge_states;           // [SM count] HugeState slabs
+  unsigned long long * task_times; // profiling aid (GTB_TASK_TIMES=file): [n_active][2] globaltimer ns at start / end of
+                                   // each chain_kernel task; nullptr normally
 };
+
+// The chunks of one submit (gtb_submit_reads_multi pipelines copy and compute chunk by chunk); slow_kernel / huge_kernel
+// serve the queues of all of them in one launch.
+constexpr int MAX_CHUNKS = 8;
+struct MultiLaunch
+{
+  int n;
+  LaunchParams p[MAX_CHUNKS];
+};
+static_assert(sizeof(MultiLaunch) <= 4000, "MultiLaunch is passed as a kernel parameter");
 
 // host launchers (gtb_kernels.cu)
 void launch_build_table(const IndexSlot * uniq, uint32_t n, IndexSlot * table, uint32_t mask, int shift, uint32_t * bitmap,
                         void * stream);
 void launch_probe(const LaunchParams & p, void * stream);
 void launch_chain(const LaunchParams & p, void * stream);
-void launch_slow(const LaunchParams & p, void * stream);
+void launch_slow(const MultiLaunch & m, void * stream);
 void launch_score(const LaunchParams & p, bool with_connections, void * stream);
 // connection table maintenance: re-insert every entry of (keys, vals)[0..n_slots) into R's (larger, zeroed) table;
 // compact the non-empty entries of R's table into (out_keys, out_vals), count in *out_n

@@ -61,6 +61,21 @@ __device__ __forceinline__ uint8_t iupac_char(uint8_t c)
 //   SlowState : big capacities, lives in shared memory, one warp per task (lane 0 runs the scalar logic)
 //   FastState : small capacities, lives in per-thread local memory, one THREAD per task (32 tasks per warp);
 //               a task that exceeds a small capacity is re-run by the slow kernel.
+// 4 consecutive bytes from an arbitrary address: two aligned 32-bit loads + funnel shift.  May touch up to 7 bytes past
+// p -- the graph sequence array and the read buffers are padded for that.
+__device__ __forceinline__ uint32_t ld4_global(const uint8_t * p)
+{
+  uintptr_t const a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t * w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+  return __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3u) * 8u);
+}
+
+__device__ __forceinline__ uint32_t ld4_state(const uint8_t * base, int j) // base is 4-byte aligned (state member)
+{
+  const uint32_t * w = reinterpret_cast<const uint32_t *>(base) + (j >> 2);
+  return __funnelshift_r(w[0], w[1], (uint32_t)(j & 3) * 8u);
+}
+
 template <int P_, int V_, int C_, int CV_, int WL_, int LOC_>
 struct StateT
 {
@@ -105,9 +120,10 @@ struct WarpStateT : StateT<P_, V_, C_, CV_, WL_, LOC_>
   static constexpr int REFCAP = REFS_;
   uint2 refs[REFS_];
   uint16_t list_start[NLISTS + 1];
-  uint8_t seq[MAX_SEQ + 8]; // 4-bit codes in phase A, IUPAC characters afterwards
+  alignas(4) uint8_t seq[MAX_SEQ + 8]; // 4-bit codes in phase A, IUPAC characters afterwards
   Cand * cand_spill;        // this warp's global-memory extension of cands[] (SPILL_ entries)
   __device__ __forceinline__ uint8_t rd(int j) const { return seq[j]; }
+  __device__ __forceinline__ uint32_t rd4(int j) const { return ld4_state(seq, j); }
   __device__ __forceinline__ void prepare(int, int) {} // the whole read is already decoded in seq[]
   // candidate i of the bubble expansion: the first C_ live in the state itself, the (rare) rest in a per-warp
   // global scratch area, so that the reference's limit of 128 open candidates (+ one round of growth) fits
@@ -121,7 +137,7 @@ struct FastState : StateT<FAST_P, FAST_V, FAST_C, FAST_CV, FAST_WL, FAST_LOC>
   static constexpr int CAND_TOTAL = FAST_C;
   const uint8_t * s4; // packed 4-bit read
   int L, orient;
-  uint8_t buf[MAX_SEQ]; // IUPAC characters of the read window the current walk compares against
+  alignas(4) uint8_t buf[MAX_SEQ + 8]; // IUPAC characters of the read window the current walk compares against
   // decodes read bases [from, to) once; the comparison loops of a walk touch the same ~26-base tail several times
   __device__ void prepare(int from, int to)
   {
@@ -136,6 +152,7 @@ struct FastState : StateT<FAST_P, FAST_V, FAST_C, FAST_CV, FAST_WL, FAST_LOC>
     }
   }
   __device__ __forceinline__ uint8_t rd(int j) const { return buf[j]; }
+  __device__ __forceinline__ uint32_t rd4(int j) const { return ld4_state(buf, j); }
   __device__ __forceinline__ Cand & cand_at(int i) { return cands[i]; }
 };
 
@@ -305,6 +322,25 @@ __device__ int expand_keys(const uint8_t * codes, uint64_t * keys, int cap)
 template <class PathT>
 __device__ __forceinline__ uint32_t psize(const PathT & p) { return (uint32_t)p.re - p.rs + 1u; }
 
+// Path assignment that moves the header and only the nvar live (order, mask) entries: the working sets sit in local /
+// shared / global memory, and a whole-struct copy moves all MAXV slots (typical paths cross 0-2 bubbles)
+template <class PathT>
+__device__ __forceinline__ void copy_path(PathT & dst, const PathT & src)
+{
+  dst.start = src.start;
+  dst.end = src.end;
+  dst.rs = src.rs;
+  dst.re = src.re;
+  dst.mm = src.mm;
+  int const n = src.nvar;
+  dst.nvar = (uint16_t)n;
+  for (int i = 0; i < n; ++i)
+  {
+    dst.order[i] = src.order[i];
+    dst.mask[i] = src.mask[i];
+  }
+}
+
 template <class W>
 __device__ void merge_with_current(W & S, const GR & g, typename W::Path & p, const DevLabel & l) // path.cpp:105-129
 {
@@ -362,7 +398,7 @@ __device__ void pp_add_label(W & S, const GR & g, const DevLabel & l, uint16_t r
 template <class W>
 __device__ bool merge_paths(W & S, const typename W::Path & p1, const typename W::Path & p2, typename W::Path & out)
 {
-  out = p2;
+  copy_path(out, p2);
   for (int i = 0; i < p1.nvar; ++i)
   {
     bool found = false;
@@ -401,7 +437,7 @@ __device__ void push_path(W & S, const typename W::Path & p)
     S.overflow |= OV_PATHS;
     return;
   }
-  S.paths[S.npaths++] = p;
+  copy_path(S.paths[S.npaths++], p);
 }
 
 // second half of add_next_kmer_labels (genotype_paths.cpp:308-351): S.pp holds the grouped new labels
@@ -416,7 +452,7 @@ __device__ void add_next(W & S, uint32_t rs)
     if (S.paths[i].re != rs)
       continue;
     bool once = false;
-    S.op = S.paths[i];
+    copy_path(S.op, S.paths[i]);
     for (int j = 0; j < S.npp; ++j)
     {
       if (S.op.end != S.pp[j].start)
@@ -429,7 +465,7 @@ __device__ void add_next(W & S, uint32_t rs)
       else
       {
         S.longest = max(psize(S.np), S.longest);
-        S.paths[i] = S.np;
+        copy_path(S.paths[i], S.np);
         once = true;
       }
     }
@@ -454,7 +490,7 @@ __device__ void add_prev(W & S, uint32_t re)
     if (S.paths[i].rs != re)
       continue;
     bool once = false;
-    S.op = S.paths[i];
+    copy_path(S.op, S.paths[i]);
     for (int j = 0; j < S.npp; ++j)
     {
       if (S.pp[j].end != S.op.start)
@@ -467,7 +503,7 @@ __device__ void add_prev(W & S, uint32_t re)
       else
       {
         S.longest = max(psize(S.np), S.longest);
-        S.paths[i] = S.np;
+        copy_path(S.paths[i], S.np);
         once = true;
       }
     }
@@ -491,7 +527,7 @@ __device__ void remove_short_paths(W & S) // genotype_paths.cpp:824-834
     if (psize(S.paths[i]) >= S.longest)
     {
       if (w != i)
-        S.paths[w] = S.paths[i];
+        copy_path(S.paths[w], S.paths[i]);
       ++w;
     }
   S.npaths = w;
@@ -526,41 +562,52 @@ __device__ bool path_is_reference(const PathT & p)
 }
 
 // ------------------------------------------------------------------------------------------------ phase C: graph walk
+// mismatches between read[r0 + i] and dna[i], i < m, by the reference's per-base rule (graph_utils.hpp:7-69: 'N' on either
+// side matches, '<' / '>' in the graph rejects = BIGMM).  Four bases per step: equal words need no further look (a read
+// never holds '<' or '>', so a graph tag always differs); a word that differs somewhere goes through the per-base rule.
+template <class W>
+__device__ uint32_t cmp_range(const W & S, int r0, const uint8_t * dna, uint32_t m)
+{
+  uint32_t mm = 0;
+  for (uint32_t i = 0; i < m; i += 4)
+  {
+    uint32_t const g = ld4_global(dna + i), r = S.rd4(r0 + (int)i);
+    uint32_t const rem = m - i;
+    uint32_t x = g ^ r;
+    if (rem < 4)
+      x &= (1u << (8 * rem)) - 1u;
+    if (x == 0)
+      continue;
+    uint32_t const nb = rem < 4 ? rem : 4u;
+    for (uint32_t k = 0; k < nb; ++k)
+    {
+      uint32_t const gc = (g >> (8 * k)) & 0xFFu, rc = (r >> (8 * k)) & 0xFFu;
+      if (gc == '>' || gc == '<')
+        return BIGMM;
+      mm += (gc != rc && rc != 'N' && gc != 'N');
+    }
+  }
+  return mm;
+}
+
 // mismatches between read[koff + have + i] and dna[i] (graph_utils.hpp:7-37); BIGMM when the graph has '<' or '>'
 template <class W>
 __device__ uint32_t cmp_fwd(const W & S, int koff, uint32_t RL, uint32_t have, const uint8_t * dna, uint32_t n)
 {
   if (have >= RL)
     return 0;
-  uint32_t const m = min(n, RL - have);
-  uint32_t mm = 0;
-  int const r0 = koff + (int)have;
-  for (uint32_t i = 0; i < m; ++i)
-  {
-    uint8_t const gc = dna[i], rc = S.rd(r0 + (int)i);
-    if (gc == '>' || gc == '<')
-      return BIGMM;
-    mm += (gc != rc && rc != 'N' && gc != 'N');
-  }
-  return mm;
+  return cmp_range(S, koff + (int)have, dna, min(n, RL - have));
 }
 
-// backward: the k-mer is read[0 .. RL), the candidate already covers its last `have` bases (graph_utils.hpp:39-69)
+// backward: the k-mer is read[0 .. RL), the candidate already covers its last `have` bases (graph_utils.hpp:39-69):
+// dna[n-1-i] against read[RL-1-have-i] for i < m, i.e. the last m bases of dna against read[RL-have-m .. RL-have)
 template <class W>
 __device__ uint32_t cmp_bwd(const W & S, uint32_t RL, uint32_t have, const uint8_t * dna, uint32_t n)
 {
   if (have >= RL)
     return 0;
   uint32_t const m = min(n, RL - have);
-  uint32_t mm = 0;
-  for (uint32_t i = 0; i < m; ++i)
-  {
-    uint8_t const gc = dna[n - 1 - i], rc = S.rd((int)(RL - 1 - have - i));
-    if (gc == '>' || gc == '<')
-      return BIGMM;
-    mm += (gc != rc && rc != 'N' && gc != 'N');
-  }
-  return mm;
+  return cmp_range(S, (int)(RL - have - m), dna + (n - m), m);
 }
 
 // Graph::get_locations_of_a_position (graph.cpp:931-1029,1154-1185) -> S.locs; returns count
@@ -1259,7 +1306,7 @@ __device__ void run_task(W & S, const GR & g, const uint2 * refs, const uint16_t
       if (S.paths[i].mm <= mn)
       {
         if (w != i)
-          S.paths[w] = S.paths[i];
+          copy_path(S.paths[w], S.paths[i]);
         ++w;
       }
     S.npaths = w;
@@ -1271,7 +1318,7 @@ __device__ void run_task(W & S, const GR & g, const uint2 * refs, const uint16_t
       if (g.ref_reach_pos(S.paths[i].start) != g.ref_reach_pos(S.paths[i].end))
       {
         if (w != i)
-          S.paths[w] = S.paths[i];
+          copy_path(S.paths[w], S.paths[i]);
         ++w;
       }
     S.npaths = w;
@@ -1293,7 +1340,7 @@ __device__ void run_task(W & S, const GR & g, const uint2 * refs, const uint16_t
         if (path_is_reference(S.paths[i]))
         {
           if (w != i)
-            S.paths[w] = S.paths[i];
+            copy_path(S.paths[w], S.paths[i]);
           ++w;
         }
       S.npaths = w;
@@ -1586,6 +1633,26 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(
   uint32_t const task = P.active_tasks[t];
   const SeedRec * recp = reinterpret_cast<const SeedRec *>(P.seed_recs) + t;
   uint32_t const w2 = reinterpret_cast<const uint32_t *>(recp)[2];
+  struct TaskTimer // profiling aid, see LaunchParams::task_times
+  {
+    unsigned long long * p;
+    __device__ static unsigned long long now()
+    {
+      unsigned long long v;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+      return v;
+    }
+    __device__ TaskTimer(unsigned long long * q) : p(q)
+    {
+      if (p)
+        p[0] = now();
+    }
+    __device__ ~TaskTimer()
+    {
+      if (p)
+        p[1] = now();
+    }
+  } timer(P.task_times ? P.task_times + 2 * (size_t)t : nullptr);
   if ((w2 >> 8) & 1u)
   {
     atomicAdd(&P.counters->fast_reasons[11], 1ull); // marked by probe_kernel (IUPAC/N seed or > SEED_INLINE references)
@@ -1635,13 +1702,15 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(
 // type_conversions.cpp:207-266) and everything the previous tier's capacities cannot hold.  Two instances:
 //   slow_kernel : SlowState in shared memory; a task that still overflows is queued for huge_kernel
 //   huge_kernel : HugeState in a per-warp global slab, capacities = the reference's own limits; an overflow here is final
+// `first` = first queue index of this warp (the queues of several chunks are dealt round-robin over the grid's warps),
+// `warp_global` = the warp's own index, which owns the global scratch slabs.
 template <class WST, bool LAST>
-__device__ void warp_tier(const LaunchParams & P, WST & S, int lane, uint32_t warp_global, uint32_t total_warps,
+__device__ void warp_tier(const LaunchParams & P, WST & S, int lane, uint32_t first, uint32_t warp_global, uint32_t total_warps,
                           const uint32_t * queue, uint32_t n_queued)
 {
   uint32_t const n_tasks = P.batch.n_units * 2;
 
-  for (uint32_t si = warp_global; si < n_queued; si += total_warps)
+  for (uint32_t si = first; si < n_queued; si += total_warps)
   {
     uint32_t const task = queue[si];
     uint32_t const unit = task >> 1;
@@ -1777,23 +1846,40 @@ __device__ void warp_tier(const LaunchParams & P, WST & S, int lane, uint32_t wa
   }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) slow_kernel(LaunchParams P)
+// The queues of all chunks of one submit are served by ONE launch: slow tasks are few (tens per 10^5 reads) and each is a
+// long single-lane job, so a launch costs the latency of its slowest task no matter how many chunks feed it.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) slow_kernel(const __grid_constant__ MultiLaunch M)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SlowState * all = reinterpret_cast<SlowState *>(smem_raw);
   int const wib = threadIdx.x >> 5;
-  warp_tier<SlowState, false>(P, all[wib], threadIdx.x & 31, blockIdx.x * WARPS_PER_BLOCK + wib, gridDim.x * WARPS_PER_BLOCK,
-                              P.slow_tasks, (uint32_t)P.counters->n_slow);
+  uint32_t const warp = blockIdx.x * WARPS_PER_BLOCK + wib, total = gridDim.x * WARPS_PER_BLOCK;
+  uint32_t base = 0;
+  for (int c = 0; c < M.n; ++c)
+  {
+    uint32_t const n = (uint32_t)M.p[c].counters->n_slow;
+    if (n)
+      warp_tier<SlowState, false>(M.p[c], all[wib], threadIdx.x & 31, (warp + total - base % total) % total, warp, total,
+                                  M.p[c].slow_tasks, n);
+    base += n;
+  }
 }
 
 // One warp per block (grid = SM count); exits at once when slow_kernel queued nothing, which is the normal case.
-__global__ void __launch_bounds__(32) huge_kernel(LaunchParams P)
+__global__ void __launch_bounds__(32) huge_kernel(const __grid_constant__ MultiLaunch M)
 {
-  uint32_t const n = (uint32_t)P.counters->n_huge;
-  if (n == 0)
-    return;
-  HugeState & S = reinterpret_cast<HugeState *>(P.huge_states)[blockIdx.x];
-  warp_tier<HugeState, true>(P, S, threadIdx.x, blockIdx.x, gridDim.x, P.huge_tasks, n);
+  uint32_t base = 0;
+  for (int c = 0; c < M.n; ++c)
+  {
+    uint32_t const n = (uint32_t)M.p[c].counters->n_huge;
+    if (n)
+    {
+      HugeState & S = reinterpret_cast<HugeState *>(M.p[c].huge_states)[blockIdx.x];
+      warp_tier<HugeState, true>(M.p[c], S, threadIdx.x, (blockIdx.x + gridDim.x - base % gridDim.x) % gridDim.x, blockIdx.x,
+                                 gridDim.x, M.p[c].huge_tasks, n);
+    }
+    base += n;
+  }
 }
 
 // ================================================================================================ score kernel
@@ -2559,14 +2645,17 @@ void launch_chain(const LaunchParams & p, void * stream)
 }
 
 // persistent grid (a multiple of the SM count); the number of queued tasks is read on the device
-void launch_slow(const LaunchParams & p, void * stream)
+void launch_slow(const MultiLaunch & m, void * stream)
 {
-  if (p.n_active == 0)
+  bool any = false;
+  for (int c = 0; c < m.n; ++c)
+    any = any || m.p[c].n_active != 0;
+  if (!any)
     return;
   size_t const smem = sizeof(SlowState) * WARPS_PER_BLOCK;
   uint32_t const grid = (uint32_t)(sm_count() * align_kernel_blocks_per_sm());
-  slow_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(p);
-  huge_kernel<<<(uint32_t)sm_count(), 32, 0, (cudaStream_t)stream>>>(p);
+  slow_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(m);
+  huge_kernel<<<(uint32_t)sm_count(), 32, 0, (cudaStream_t)stream>>>(m);
 }
 
 size_t huge_state_bytes() { return (size_t)sm_count() * sizeof(HugeState); }

@@ -15,7 +15,7 @@ import numpy as np
 from . import abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgtb200.so")
+LIB_PATH = os.environ.get("GTB_LIB") or os.path.join(HERE, "libgtb200.so")  # GTB_LIB: tuning builds (tools/)
 
 EXPORTS = [
     "gtb_last_error", "gtb_version", "gtb_create", "gtb_destroy", "gtb_region_begin", "gtb_region_begin_multi", "gtb_region_end",

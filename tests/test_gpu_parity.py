@@ -131,10 +131,10 @@ def test_region_batched_submit_equals_separate(ctx):
             ctx.region_end(100 + k)
 
 
-@pytest.mark.parametrize("n_chunks", [2, 3, 4])
+@pytest.mark.parametrize("n_chunks", [2, 3, 4, 8])
 def test_chunked_pipeline_equals_golden(ctx, n_chunks):
     """The double-buffered chunk pipeline (copy stream + compute stream) gives the same accumulators."""
-    pres = [p for p in ALL if "sv" not in os.path.basename(p)][:5]
+    pres = [p for p in ALL if "sv" not in os.path.basename(p)][:9]
     graphs, batches, ns = [], [], []
     ids = list(range(300, 300 + len(pres)))
     for k, pre in zip(ids, pres):

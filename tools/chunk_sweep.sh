@@ -1,6 +1,6 @@
 #!/bin/bash
 # e2e vs number of pipeline chunks (GTB_CHUNKS) on the bench workload
-for c in 1 2 3 4; do
+for c in 1 2 3 4 6 8; do
   GTB_CHUNKS=$c python bench.py --no-cpu-baseline 2>&1 | tail -1 | GTB_C=$c python -c "
 import sys, json, os
 d = json.loads(sys.stdin.read())
