@@ -338,7 +338,7 @@ def main() -> None:
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev_ms, align_ms, score_ms, wall = [], [], [], []
-    kt = {"probe_kernel": [], "chain_kernel": [], "slow_kernel": [], "score_kernel": []}
+    kt = {"prep_kernels": [], "probe_kernel": [], "chain_kernel": [], "slow_kernel": [], "score_kernel": []}
     n_slow = 0
     t_all0 = time.perf_counter()
     for _ in range(args.steps):

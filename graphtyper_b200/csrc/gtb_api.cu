@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <functional>
@@ -141,10 +142,13 @@ struct BatchState
   std::vector<uint32_t> unit_begin;    // per region: first unit index (size n+1)
   std::vector<uint32_t> rec_begin;
   bool with_conn = false;              // some region of this chunk collects phasing connections
+  PrepParams prep{};                   // device-side batch preparation of this chunk
+  DeviceBuffer d_scan_temp;
+  size_t scan_temp_bytes = 0;
   cudaStream_t stream = nullptr;       // probe + chain of this chunk (chunks run concurrently, each on its own stream)
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  // ev: 0 h2d start (copy stream), 1 h2d done (copy stream), 2 kernels start, 3 after probe, 4 after chain (chunk stream),
-  //     5 before score, 6 after score, 7 after counters D2H (main stream)
+  // ev: 0 h2d start (copy stream), 1 h2d done (copy stream), 2 kernels start, 3 after prep + probe, 4 after chain,
+  //     5 after the first score pass, 6 after the batch preparation (chunk stream), 7 after counters D2H (main stream)
   void release()
   {
     d_batch.release();
@@ -153,6 +157,7 @@ struct BatchState
     d_counters.release();
     d_seedrecs.release();
     d_task_times.release();
+    d_scan_temp.release();
     d_slow.release();
     h_batch.release();
     h_counters.release();
@@ -169,6 +174,8 @@ struct Ctx
   int device = -1;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream2 = nullptr; // second H2D queue: per-region copies of < 1 MB do not reach PCIe peak one at a time
+  cudaEvent_t ev_copy2 = nullptr;
   BatchState bs[MAX_CHUNKS];
   int n_chunks_last = 0;
   std::map<int, std::unique_ptr<Region>> regions;
@@ -178,15 +185,18 @@ struct Ctx
   // batch
   DeviceBuffer d_tap_counts, d_tap_pool, d_spill, d_huge;
   std::vector<DeviceBuffer> buffer_cache; // arenas / accumulators of ended regions, reused by the next regions
-  PinnedBuffer h_stage, h_accum;
+  PinnedBuffer h_stage, h_accum, h_segments;
+  DeviceBuffer d_segments, d_gather;
+  int segments_flip = 0;
   bool have_last = false;
   bool debug = false;
   int forced_chunks = 0; // gtb_set_chunks / GTB_CHUNKS: 0 = automatic
-  cudaEvent_t ev_slow[3] = {nullptr, nullptr, nullptr}; // [0],[1] around slow_kernel + huge_kernel (main stream);
-                                                        // [2] main-stream position when a submit / replay starts
+  cudaEvent_t ev_slow[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // [0],[1] around slow_kernel + huge_kernel (main stream);
+                                                        // [2] main-stream position when a submit / replay starts;
+                                                        // [4], [3] around the second score pass
   int connections = 0;   // gtb_set_connections: 0 off, otherwise table slots reserved per submitted record
   PinnedBuffer h_conn_state;
-  float t_h2d = 0, t_align = 0, t_score = 0, t_d2h = 0, t_probe = 0, t_chain = 0, t_slow = 0;
+  float t_h2d = 0, t_align = 0, t_score = 0, t_d2h = 0, t_probe = 0, t_chain = 0, t_slow = 0, t_total = 0, t_prep = 0;
   unsigned long long last_n_slow = 0;
   // nccl (loaded lazily with dlopen, see gtb_nccl.cpp part below)
   void * nccl_lib = nullptr;
@@ -381,6 +391,32 @@ void parallel_for(int n, const std::function<void(int)> & fn)
   pool.run(n, fn);
 }
 
+// Segment table of a gather / zero launch: staged in pinned memory, copied on the main stream.  Tables alternate between
+// two pinned halves so that the previous call's (asynchronous) copy is never overwritten while still in flight.
+template <typename F>
+int upload_segments(Ctx * c, int n, F make, unsigned long long & max_bytes)
+{
+  size_t const bytes = (size_t)n * sizeof(Segment);
+  if (c->h_segments.cap < 2 * bytes)
+  {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (int rc = c->h_segments.reserve(2 * bytes))
+      return rc;
+  }
+  if (int rc = c->d_segments.reserve(bytes))
+    return rc;
+  c->segments_flip ^= 1;
+  Segment * h = reinterpret_cast<Segment *>(static_cast<uint8_t *>(c->h_segments.p) + (c->segments_flip ? c->h_segments.cap / 2 / 16 * 16 : 0));
+  max_bytes = 0;
+  for (int i = 0; i < n; ++i)
+  {
+    h[i] = make(i);
+    max_bytes = std::max(max_bytes, h[i].bytes);
+  }
+  CUDA_TRY(cudaMemcpyAsync(c->d_segments.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
 // ---- phasing-connection table of one pool
 size_t conn_table_bytes(uint32_t cap) { return (size_t)cap * 12 + 16; }
 
@@ -462,6 +498,10 @@ int gtb_create(int device_id, gtb_ctx ** out)
       e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess)
       e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+      e = cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+      e = cudaEventCreateWithFlags(&c->ev_copy2, cudaEventDisableTiming);
 
     for (int k = 0; k < MAX_CHUNKS; ++k)
     {
@@ -470,7 +510,7 @@ int gtb_create(int device_id, gtb_ctx ** out)
       if (e == cudaSuccess)
         e = cudaStreamCreateWithFlags(&c->bs[k].stream, cudaStreamNonBlocking);
     }
-    for (int i = 0; i < 3 && e == cudaSuccess; ++i)
+    for (int i = 0; i < 5 && e == cudaSuccess; ++i)
       e = cudaEventCreate(&c->ev_slow[i]);
     if (e != cudaSuccess)
     {
@@ -512,6 +552,9 @@ void gtb_destroy(gtb_ctx * ctx)
     c->h_stage.release();
     c->h_accum.release();
     c->h_conn_state.release();
+    c->h_segments.release();
+    c->d_segments.release();
+    c->d_gather.release();
     for (DeviceBuffer * b : {&c->d_idx_small, &c->d_idx_jobs, &c->d_idx_keys, &c->d_idx_keys2, &c->d_idx_labels, &c->d_idx_idx,
                              &c->d_idx_idx2, &c->d_idx_head, &c->d_idx_temp})
       b->release();
@@ -528,6 +571,10 @@ void gtb_destroy(gtb_ctx * ctx)
         cudaEventDestroy(e);
     if (c->copy_stream)
       cudaStreamDestroy(c->copy_stream);
+    if (c->copy_stream2)
+      cudaStreamDestroy(c->copy_stream2);
+    if (c->ev_copy2)
+      cudaEventDestroy(c->ev_copy2);
 
     if (c->stream)
       cudaStreamDestroy(c->stream);
@@ -1134,14 +1181,24 @@ static int launch_front(Ctx * c, BatchState & B, cudaEvent_t after)
   CUDA_TRY(cudaStreamWaitEvent(s, B.ev[1], 0));
   CUDA_TRY(cudaMemsetAsync(B.d_counters.p, 0, sizeof(DevCounters), s));
   // orientations that are not aligned keep an all-zero summary (no paths)
-  CUDA_TRY(cudaMemsetAsync(P.summaries, 0, (size_t)P.batch.n_units * 2 * sizeof(TaskSummary), s));
+  CUDA_TRY(cudaMemsetAsync(P.summaries, 0, (size_t)P.batch.n_units * 2 * (sizeof(TaskSummary) + 1), s)); // + pending[]
   if (P.tap.list_count)
     CUDA_TRY(cudaMemsetAsync(P.tap.list_count, 0, (size_t)P.batch.n_units * 2 * (NLISTS * 2 + 1) * 4, s));
   CUDA_TRY(cudaEventRecord(B.ev[2], s));
+  // batch preparation: units, aligned orientations, link checks (exclusive scan of (is_unit << 32 | orientations))
+  launch_prep_flags(B.prep, s);
+  if (B.prep.n_records)
+    if (exclusive_scan64(B.d_scan_temp.p, B.scan_temp_bytes, B.prep.scan, B.prep.scan, B.prep.n_records, s) != 0)
+      return fail(GTB_ERR_CUDA, "prefix scan of the batch preparation failed");
+  launch_prep_fill(B.prep, s);
+  CUDA_TRY(cudaEventRecord(B.ev[6], s));
   launch_probe(P, s);
   CUDA_TRY(cudaEventRecord(B.ev[3], s));
   launch_chain(P, s);
   CUDA_TRY(cudaEventRecord(B.ev[4], s));
+  // first score pass: every record whose tasks chain_kernel finished (all but a few dozen per 10^5)
+  launch_score(P, B.with_conn, s);
+  CUDA_TRY(cudaEventRecord(B.ev[5], s));
   return 0;
 }
 
@@ -1152,20 +1209,24 @@ static int launch_back(Ctx * c, int n_chunks)
   cudaStream_t const ts = c->stream;
   MultiLaunch M;
   M.n = n_chunks;
+  bool with_conn[MAX_CHUNKS];
   for (int k = 0; k < n_chunks; ++k)
   {
-    CUDA_TRY(cudaStreamWaitEvent(ts, c->bs[k].ev[4], 0));
+    // after the chunk's first score pass, not beside it: slow_kernel's tasks are long single-lane jobs, and sharing the SM
+    // schedulers with a full score_kernel stretches them (measured 0.09 -> 0.17 ms; the score pass 0.07 -> 0.19 ms)
+    CUDA_TRY(cudaStreamWaitEvent(ts, c->bs[k].ev[5], 0));
     M.p[k] = c->bs[k].P;
+    with_conn[k] = c->bs[k].with_conn;
   }
   CUDA_TRY(cudaEventRecord(c->ev_slow[0], ts));
   launch_slow(M, ts);
   CUDA_TRY(cudaEventRecord(c->ev_slow[1], ts));
+  CUDA_TRY(cudaEventRecord(c->ev_slow[4], ts));
+  launch_score_deferred(M, with_conn, ts); // second score pass: the records that waited for slow_kernel / huge_kernel
+  CUDA_TRY(cudaEventRecord(c->ev_slow[3], ts));
   for (int k = 0; k < n_chunks; ++k)
   {
     BatchState & B = c->bs[k];
-    CUDA_TRY(cudaEventRecord(B.ev[5], ts));
-    launch_score(B.P, B.with_conn, ts);
-    CUDA_TRY(cudaEventRecord(B.ev[6], ts));
     CUDA_TRY(cudaMemcpyAsync(B.h_counters.p, B.d_counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, ts));
     CUDA_TRY(cudaEventRecord(B.ev[7], ts));
   }
@@ -1177,12 +1238,27 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
 {
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaGetLastError());
+  if (c->debug && c->n_chunks_last == 1 && c->bs[0].unit_begin.empty())
+  {
+    // debug taps address units per region: first unit of region i = unit of its first record
+    BatchState & B = c->bs[0];
+    size_t const nr = B.rec_begin.size() - 1;
+    std::vector<int32_t> unit(B.P.batch.n_records);
+    if (!unit.empty())
+      CUDA_TRY(cudaMemcpy(unit.data(), B.P.batch.unit, unit.size() * 4, cudaMemcpyDeviceToHost));
+    DevCounters kc0{};
+    CUDA_TRY(cudaMemcpy(&kc0, B.d_counters.p, sizeof(kc0), cudaMemcpyDeviceToHost));
+    B.unit_begin.assign(nr + 1, kc0.n_units);
+    for (size_t i = nr; i-- > 0;)
+      B.unit_begin[i] = B.rec_begin[i] < B.rec_begin[i + 1] ? (uint32_t)unit[B.rec_begin[i]] : B.unit_begin[i + 1];
+  }
   if (record_h2d)
     c->t_h2d = 0;
-  c->t_align = c->t_probe = c->t_chain = c->t_slow = c->t_score = c->t_d2h = 0;
+  c->t_align = c->t_prep = c->t_probe = c->t_chain = c->t_slow = c->t_score = c->t_d2h = 0;
   c->last_n_slow = 0;
   gtb_submit_stats st{};
   unsigned long long n_overflow = 0, n_input_error = 0, reasons[12] = {0};
+  uint32_t input_bits = 0;
   for (int k = 0; k < c->n_chunks_last; ++k)
   {
     BatchState & B = c->bs[k];
@@ -1192,25 +1268,25 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
       cudaEventElapsedTime(&t, B.ev[0], B.ev[1]);
       c->t_h2d += t;
     }
-    cudaEventElapsedTime(&t, B.ev[2], B.ev[3]);
+    cudaEventElapsedTime(&t, B.ev[2], B.ev[6]);
+    c->t_prep += t;
+    cudaEventElapsedTime(&t, B.ev[6], B.ev[3]);
     c->t_probe += t;
     cudaEventElapsedTime(&t, B.ev[3], B.ev[4]);
     c->t_chain += t;
-    cudaEventElapsedTime(&t, B.ev[5], B.ev[6]);
+    cudaEventElapsedTime(&t, B.ev[4], B.ev[5]);
     c->t_score += t;
-    cudaEventElapsedTime(&t, B.ev[6], B.ev[7]);
-    c->t_d2h += t;
     DevCounters const * kc = static_cast<DevCounters *>(B.h_counters.p);
     if (B.P.task_times && k == 0)
       if (const char * fn = getenv("GTB_TASK_TIMES"))
       {
-        std::vector<unsigned long long> tt((size_t)B.P.n_active * 2);
-        std::vector<uint32_t> at(B.P.n_active);
+        std::vector<unsigned long long> tt((size_t)kc->n_active * 2);
+        std::vector<uint32_t> at(kc->n_active);
         cudaMemcpy(tt.data(), B.P.task_times, tt.size() * 8, cudaMemcpyDeviceToHost);
         cudaMemcpy(at.data(), B.P.active_tasks, at.size() * 4, cudaMemcpyDeviceToHost);
         if (FILE * f = fopen(fn, "wb"))
         {
-          uint64_t const n = B.P.n_active;
+          uint64_t const n = kc->n_active;
           fwrite(&n, 8, 1, f);
           fwrite(tt.data(), 8, tt.size(), f);
           fwrite(at.data(), 4, at.size(), f);
@@ -1219,12 +1295,13 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
       }
     c->last_n_slow += kc->n_slow;
     st.n_records += B.P.batch.n_records;
-    st.n_alignments += B.P.batch.n_units;
-    st.n_oriented += B.P.n_active;
+    st.n_alignments += kc->n_units;
+    st.n_oriented += kc->n_active;
+    input_bits |= kc->input_bits;
     st.n_pairs_scored += kc->n_pairs_scored;
     st.n_singles_scored += kc->n_singles_scored;
     st.n_capacity_overflow += kc->n_overflow;
-    st.kernel_launches += (B.P.n_active ? 2 : 0) + (B.P.batch.n_records ? 1 : 0); // probe, chain + score
+    st.kernel_launches += B.P.batch.n_records ? 6 : 0; // prep_flags, scan (1 kernel at these sizes), prep_fill, probe, chain, score
     n_overflow += kc->n_overflow;
     n_input_error += kc->n_input_error;
     for (int q = 0; q < 12; ++q)
@@ -1234,11 +1311,26 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     float t = 0;
     cudaEventElapsedTime(&t, c->ev_slow[0], c->ev_slow[1]);
     c->t_slow = t;
-    st.kernel_launches += st.n_oriented ? 2 : 0; // slow_kernel + huge_kernel, once per submit
+    cudaEventElapsedTime(&t, c->ev_slow[4], c->ev_slow[3]);
+    c->t_score += t; // second pass
+    cudaEventElapsedTime(&t, c->ev_slow[3], c->bs[c->n_chunks_last - 1].ev[7]);
+    c->t_d2h = t;
+    cudaEventElapsedTime(&t, c->bs[0].ev[2], c->ev_slow[3]);
+    c->t_total = t; // device span of the whole launch sequence (slow_kernel overlaps the first score pass)
+    st.kernel_launches += st.n_records ? 3 : 0; // slow_kernel, huge_kernel, second score pass: once per submit
   }
-  c->t_align = c->t_probe + c->t_chain + c->t_slow;
+  c->t_align = c->t_prep + c->t_probe + c->t_chain;
   if (stats)
     *stats = st;
+  // input the batch-preparation kernels rejected (the offending links were cut / values replaced before the other kernels ran)
+  if (input_bits & PREP_ERR_SAMPLE)
+    return fail(GTB_ERR_ARG, "sample index out of range");
+  if (input_bits & PREP_ERR_DUP)
+    return fail(GTB_ERR_ARG, "dup_of must reference an earlier record of the same batch");
+  if (input_bits & PREP_ERR_MATE)
+    return fail(GTB_ERR_ARG, "mate must reference an earlier record of the same batch");
+  if (input_bits & PREP_ERR_LEN)
+    return fail(GTB_ERR_CAPACITY, "read longer than 152 bases (reference MAX_READ_LENGTH is 151)");
   if (n_input_error)
     return fail(GTB_ERR_INPUT, "two mates with the same IS_FIRST_IN_PAIR flag (the reference aborts here, "
                                "hts_parallel_reader.cpp:306-315)");
@@ -1256,15 +1348,18 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
   return 0;
 }
 
-// Stages one chunk (regions [0, n) of the given arrays) into B's pinned buffer with host threads, reserves the
-// device buffers, enqueues ONE H2D copy on the copy stream and fills B.P.
+// Stages one chunk (regions [0, n) of the given arrays): the bases are DMA-ed straight from the caller's buffers when those
+// are page-locked, the small columns are gathered into B's pinned buffer by the host pool (plain copies in blocks of 8192
+// records; mate / duplicate links are rebased to chunk-global indices on the way) and follow in ONE H2D copy.  Everything
+// that needs a look at each record -- alignment units, the list of aligned orientations, link validation -- happens on the
+// device (prep_flags_kernel -> scan -> prep_fill_kernel, launch_front).
 static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, const gtb_read_batch * batches,
                        Region * const * regs, bool with_tap)
 {
   size_t total = 0;
   for (int i = 0; i < n; ++i)
     total += batches[i].n_reads;
-  // ---- staging layout (one pinned buffer, one H2D copy)
+  // ---- layout: [seq4] [columns copied from the host ...] [columns produced on the device ...]
   size_t off = 0;
   size_t const o_seq4 = place<uint8_t>(off, total * GTB_SEQ_STRIDE);
   size_t const o_lseq = place<uint16_t>(off, total);
@@ -1278,40 +1373,22 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   size_t const o_isize = place<int32_t>(off, total);
   size_t const o_sample = place<int32_t>(off, total);
   size_t const o_mate = place<int32_t>(off, total);
+  size_t const o_dup = place<int32_t>(off, total);
+  size_t const copy_end = off;
   size_t const o_unit = place<int32_t>(off, total);
   size_t const o_urec = place<int32_t>(off, total);
   size_t const o_active = place<uint32_t>(off, total * 2);
+  size_t const o_scan = place<unsigned long long>(off, total);
   size_t const bytes = align_up(off, 256);
-  if (int rc = B.h_batch.reserve(bytes))
+  if (int rc = B.h_batch.reserve(align_up(copy_end, 256)))
     return rc;
   uint8_t * h = static_cast<uint8_t *>(B.h_batch.p);
-  int32_t * h_unit = reinterpret_cast<int32_t *>(h + o_unit);
-  int32_t * h_urec = reinterpret_cast<int32_t *>(h + o_urec);
-  int32_t * h_mate = reinterpret_cast<int32_t *>(h + o_mate);
-  uint16_t * h_region = reinterpret_cast<uint16_t *>(h + o_region);
   B.regions.assign(region_ids, region_ids + n);
-  // ---- pass 1 (parallel over regions): alignment units per region (records that are not duplicates of a previous one)
   std::vector<size_t> rec_base(n + 1, 0);
-  std::vector<uint32_t> unit_base(n + 1, 0), active_cnt(n, 0);
   for (int i = 0; i < n; ++i)
     rec_base[i + 1] = rec_base[i] + batches[i].n_reads;
-  parallel_for(n, [&](int i)
-               {
-                 gtb_read_batch const & b = batches[i];
-                 uint32_t cnt = b.n_reads;
-                 if (b.dup_of)
-                 {
-                   cnt = 0;
-                   for (uint32_t k = 0; k < b.n_reads; ++k)
-                     cnt += b.dup_of[k] < 0;
-                 }
-                 unit_base[i + 1] = cnt;
-               });
-  for (int i = 0; i < n; ++i)
-    unit_base[i + 1] += unit_base[i];
-  uint32_t const n_units = unit_base[n];
-  uint32_t * h_active = reinterpret_cast<uint32_t *>(h + o_active);
-  std::atomic<int> err_code{0};
+  B.rec_begin.assign(rec_base.begin(), rec_base.end());
+  B.unit_begin.clear(); // filled after the kernels when the debug taps are on
   if (int rc = B.d_batch.reserve(bytes))
     return rc;
   // Bases are 3/4 of the bytes.  When the caller keeps them in pinned (page-locked) host memory -- gtb_host_alloc or
@@ -1328,123 +1405,95 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
       }
     }
   CUDA_TRY(cudaEventRecord(B.ev[0], c->copy_stream));
+  static int const n_copy_streams = []() { const char * e = getenv("GTB_COPY_STREAMS"); return e ? atoi(e) : 2; }();
   if (direct_seq)
+  {
+    bool used2 = false;
+    if (n_copy_streams > 1)
+    {
+      CUDA_TRY(cudaEventRecord(c->ev_copy2, c->copy_stream)); // keep the two queues in step chunk by chunk
+      CUDA_TRY(cudaStreamWaitEvent(c->copy_stream2, c->ev_copy2, 0));
+    }
     for (int i = 0; i < n; ++i)
       if (batches[i].n_reads)
+      {
+        bool const second = n_copy_streams > 1 && (i & 1);
+        used2 = used2 || second;
         CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(B.d_batch.p) + o_seq4 + rec_base[i] * GTB_SEQ_STRIDE, batches[i].seq4,
-                                 (size_t)batches[i].n_reads * GTB_SEQ_STRIDE, cudaMemcpyHostToDevice, c->copy_stream));
-  // ---- pass 2 (parallel over regions): copy the columns, number the units, rebase mate links, list the read
-  //      orientations that are aligned at all (align_read, src/typer/alignment.cpp:331-363: forward always; reverse
-  //      complement unless unpaired or a properly oriented pair within 1200 bp)
-  parallel_for(n, [&](int i)
-               {
-                 gtb_read_batch const & b = batches[i];
-                 size_t const m = b.n_reads, base = rec_base[i];
-                 if (m == 0)
-                   return;
-                 if (!direct_seq)
-                   memcpy(h + o_seq4 + base * GTB_SEQ_STRIDE, b.seq4, m * GTB_SEQ_STRIDE);
-                 memcpy(h + o_lseq + base * 2, b.lseq, m * 2);
-                 memcpy(h + o_flag + base * 2, b.flag, m * 2);
-                 memcpy(h + o_mapq + base, b.mapq, m);
-                 memcpy(h + o_same + base, b.same_tid, m);
-                 memcpy(h + o_sd + base, b.score_diff, m);
-                 if (b.clipped)
-                   memcpy(h + o_clip + base, b.clipped, m);
-                 else
-                   memset(h + o_clip + base, 0, m);
-                 if (b.leftover)
-                   memcpy(h + o_left + base, b.leftover, m);
-                 else
-                   memset(h + o_left + base, 0, m);
-                 memcpy(h + o_isize + base * 4, b.isize, m * 4);
-                 memcpy(h + o_sample + base * 4, b.sample, m * 4);
-                 uint32_t u = unit_base[i];
-                 uint32_t * act = h_active + 2 * (size_t)unit_base[i];
-                 uint32_t na = 0;
-                 uint16_t const slot = (uint16_t)regs[i]->slot;
-                 int const ns = regs[i]->n_samples;
-                 for (size_t k = 0; k < m; ++k)
-                 {
-                   h_region[base + k] = slot;
-                   if (b.sample[k] < 0 || b.sample[k] >= ns)
-                   {
-                     err_code = 1;
-                     return;
-                   }
-                   int32_t const d = b.dup_of ? b.dup_of[k] : -1;
-                   if (d < 0)
-                   {
-                     h_unit[base + k] = (int32_t)u;
-                     h_urec[u] = (int32_t)(base + k);
-                     uint16_t const L = b.lseq[k], flag = b.flag[k];
-                     if (L > (uint16_t)MAX_SEQ)
-                     {
-                       err_code = 4;
-                       return;
-                     }
-                     if (L >= 63) // hard restriction of align_read (2 * K - 1)
-                     {
-                       act[na++] = u * 2;
-                       bool const fwd_only = (flag & 1u) == 0 || (b.same_tid[k] && b.isize[k] > -1200 && b.isize[k] < 1200 &&
-                                                                 (((flag & 16u) != 0) != ((flag & 32u) != 0)));
-                       if (!fwd_only)
-                         act[na++] = u * 2 + 1;
-                     }
-                     ++u;
-                   }
-                   else
-                   {
-                     if ((size_t)d >= k)
-                     {
-                       err_code = 2;
-                       return;
-                     }
-                     h_unit[base + k] = h_unit[base + d];
-                   }
-                   int32_t const mt = b.mate ? b.mate[k] : -1;
-                   if (mt >= 0 && (size_t)mt >= k)
-                   {
-                     err_code = 3;
-                     return;
-                   }
-                   h_mate[base + k] = mt < 0 ? -1 : (int32_t)(base + mt);
-                 }
-                 active_cnt[i] = na;
-               });
-  switch (err_code.load())
-  {
-  case 1:
-    return fail(GTB_ERR_ARG, "sample index out of range");
-  case 2:
-    return fail(GTB_ERR_ARG, "dup_of must reference an earlier record of the same batch");
-  case 3:
-    return fail(GTB_ERR_ARG, "mate must reference an earlier record of the same batch");
-  case 4:
-    return fail(GTB_ERR_CAPACITY, "read longer than 152 bases (reference MAX_READ_LENGTH is 151)");
-  default:
-    break;
+                                 (size_t)batches[i].n_reads * GTB_SEQ_STRIDE, cudaMemcpyHostToDevice,
+                                 second ? c->copy_stream2 : c->copy_stream));
+      }
+    if (used2)
+    {
+      CUDA_TRY(cudaEventRecord(c->ev_copy2, c->copy_stream2));
+      CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_copy2, 0));
+    }
   }
-  // compact the per-region active lists
-  uint32_t n_active = 0;
-  B.unit_begin.assign(1, 0);
-  B.rec_begin.assign(1, 0);
+  // ---- gather the small columns: independent blocks of records, so the pool is busy whatever the number of regions
+  struct Block
+  {
+    int region;
+    uint32_t k0, k1;
+  };
+  std::vector<Block> blocks;
+  constexpr uint32_t BLOCK = 8192;
   for (int i = 0; i < n; ++i)
-  {
-    uint32_t * src = h_active + 2 * (size_t)unit_base[i];
-    if (src != h_active + n_active && active_cnt[i])
-      memmove(h_active + n_active, src, (size_t)active_cnt[i] * 4);
-    n_active += active_cnt[i];
-    B.unit_begin.push_back(unit_base[i + 1]);
-    B.rec_begin.push_back((uint32_t)rec_base[i + 1]);
-  }
+    for (uint32_t k0 = 0; k0 < batches[i].n_reads; k0 += BLOCK)
+      blocks.push_back({i, k0, std::min<uint32_t>(k0 + BLOCK, batches[i].n_reads)});
+  parallel_for((int)blocks.size(), [&](int bi)
+               {
+                 Block const & blk = blocks[bi];
+                 gtb_read_batch const & b = batches[blk.region];
+                 size_t const k0 = blk.k0, m = blk.k1 - blk.k0, base = rec_base[blk.region], at = base + k0;
+                 if (!direct_seq)
+                   memcpy(h + o_seq4 + at * GTB_SEQ_STRIDE, b.seq4 + k0 * GTB_SEQ_STRIDE, m * GTB_SEQ_STRIDE);
+                 memcpy(h + o_lseq + at * 2, b.lseq + k0, m * 2);
+                 memcpy(h + o_flag + at * 2, b.flag + k0, m * 2);
+                 memcpy(h + o_mapq + at, b.mapq + k0, m);
+                 memcpy(h + o_same + at, b.same_tid + k0, m);
+                 memcpy(h + o_sd + at, b.score_diff + k0, m);
+                 if (b.clipped)
+                   memcpy(h + o_clip + at, b.clipped + k0, m);
+                 else
+                   memset(h + o_clip + at, 0, m);
+                 if (b.leftover)
+                   memcpy(h + o_left + at, b.leftover + k0, m);
+                 else
+                   memset(h + o_left + at, 0, m);
+                 memcpy(h + o_isize + at * 4, b.isize + k0, m * 4);
+                 memcpy(h + o_sample + at * 4, b.sample + k0, m * 4);
+                 uint16_t * h_region = reinterpret_cast<uint16_t *>(h + o_region) + at;
+                 int32_t * h_mate = reinterpret_cast<int32_t *>(h + o_mate) + at;
+                 int32_t * h_dup = reinterpret_cast<int32_t *>(h + o_dup) + at;
+                 uint16_t const slot = (uint16_t)regs[blk.region]->slot;
+                 int32_t const rb = (int32_t)base;
+                 for (size_t k = 0; k < m; ++k)
+                   h_region[k] = slot;
+                 // links are batch-local; a link at or beyond its own record stays >= its chunk-global index and is
+                 // reported by prep_flags_kernel
+                 if (b.mate)
+                   for (size_t k = 0; k < m; ++k)
+                     h_mate[k] = b.mate[k0 + k] < 0 ? -1 : rb + b.mate[k0 + k];
+                 else
+                   for (size_t k = 0; k < m; ++k)
+                     h_mate[k] = -1;
+                 if (b.dup_of)
+                   for (size_t k = 0; k < m; ++k)
+                     h_dup[k] = b.dup_of[k0 + k] < 0 ? -1 : rb + b.dup_of[k0 + k];
+                 else
+                   for (size_t k = 0; k < m; ++k)
+                     h_dup[k] = -1;
+               });
 
+  // upper bounds: every record its own unit, both orientations aligned; the exact counts are produced on the device
+  uint32_t const n_units = (uint32_t)total;
+  uint32_t const n_active = (uint32_t)total * 2;
   uint32_t const n_tasks = n_units * 2;
   if (int rc = B.d_seedrecs.reserve((size_t)n_active * SEED_REC_BYTES + 64))
     return rc;
-  if (int rc = B.d_slow.reserve((size_t)n_active * 8 + 128))
+  if (int rc = B.d_slow.reserve((size_t)n_active * 8 + 128 + total * 4))
     return rc;
-  if (int rc = B.d_summaries.reserve((size_t)n_tasks * sizeof(TaskSummary) + 16))
+  if (int rc = B.d_summaries.reserve((size_t)n_tasks * (sizeof(TaskSummary) + 1) + 16))
     return rc;
   size_t const pool_words = (size_t)n_tasks * INLINE_WORDS + (size_t)n_units * 64 + 65536;
   if (int rc = B.d_pool.reserve(pool_words * 4))
@@ -1457,12 +1506,14 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
     return rc;
   if (int rc = B.h_counters.reserve(sizeof(DevCounters)))
     return rc;
+  B.scan_temp_bytes = scan64_temp_bytes((uint32_t)std::max<size_t>(total, 1));
+  if (int rc = B.d_scan_temp.reserve(B.scan_temp_bytes + 16))
+    return rc;
 
-  // only the used prefix of the active list is copied (it is the last column)
-  size_t const copy_end = o_active + (size_t)n_active * 4;
   size_t const copy_begin = direct_seq ? o_lseq : 0;
-  CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(B.d_batch.p) + copy_begin, h + copy_begin, copy_end - copy_begin,
-                           cudaMemcpyHostToDevice, c->copy_stream));
+  if (copy_end > copy_begin)
+    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(B.d_batch.p) + copy_begin, h + copy_begin, copy_end - copy_begin,
+                             cudaMemcpyHostToDevice, c->copy_stream));
   CUDA_TRY(cudaEventRecord(B.ev[1], c->copy_stream));
 
   LaunchParams & P = B.P;
@@ -1493,6 +1544,25 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   P.n_active = n_active;
   P.active_tasks = reinterpret_cast<const uint32_t *>(d + o_active);
   P.seed_recs = B.d_seedrecs.p;
+  {
+    PrepParams & Q = B.prep;
+    memset(&Q, 0, sizeof(Q));
+    Q.n_records = (uint32_t)total;
+    Q.dup_of = reinterpret_cast<const int32_t *>(d + o_dup);
+    Q.mate = reinterpret_cast<int32_t *>(d + o_mate);
+    Q.sample = reinterpret_cast<int32_t *>(d + o_sample);
+    Q.lseq = P.batch.lseq;
+    Q.flag = P.batch.flag;
+    Q.same_tid = P.batch.same_tid;
+    Q.isize = P.batch.isize;
+    Q.region = P.batch.region;
+    Q.regions = P.regions;
+    Q.scan = reinterpret_cast<unsigned long long *>(d + o_scan);
+    Q.unit = reinterpret_cast<int32_t *>(d + o_unit);
+    Q.unit_record = reinterpret_cast<int32_t *>(d + o_urec);
+    Q.active = reinterpret_cast<uint32_t *>(d + o_active);
+    Q.counters = P.counters;
+  }
   P.task_times = nullptr;
   if (getenv("GTB_TASK_TIMES")) // profiling aid: per-task start/end times of chain_kernel, dumped by collect_chunks
   {
@@ -1502,6 +1572,8 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   }
   P.slow_tasks = static_cast<uint32_t *>(B.d_slow.p);
   P.huge_tasks = P.slow_tasks + n_active + 16;
+  P.deferred = P.huge_tasks + n_active + 16;
+  P.pending = reinterpret_cast<uint8_t *>(P.summaries + n_tasks);
   P.huge_states = c->d_huge.p;
   if (with_tap)
   {
@@ -1598,7 +1670,7 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
     if (forced > 0)
       n_chunks = std::min({n, MAX_CHUNKS, forced});
     else if (total >= 65536)
-      n_chunks = std::min(n, 3);
+      n_chunks = std::min(n, 4);
   }
   std::vector<int> cut(n_chunks + 1, n);
   cut[0] = 0;
@@ -1618,6 +1690,10 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
     cut[k] = std::max(cut[k], cut[k - 1]);
   cut[n_chunks] = n;
   c->n_chunks_last = n_chunks;
+  static bool const trace = getenv("GTB_TRACE") != nullptr; // host-side timeline of a submit (profiling aid)
+  auto const t_begin = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
+  std::string tr;
   CUDA_TRY(cudaEventRecord(c->ev_slow[2], c->stream)); // the chunk streams start after everything queued so far (resets)
   for (int k = 0; k < n_chunks; ++k)
   {
@@ -1627,14 +1703,24 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
     c->bs[k].with_conn = false;
     for (int i = b0; i < b0 + m; ++i)
       c->bs[k].with_conn = c->bs[k].with_conn || regs[i]->conn_cap != 0;
+    if (trace)
+      tr += " staged" + std::to_string(k) + "=" + std::to_string((int)since());
     if (int rc = launch_front(c, c->bs[k], c->ev_slow[2]))
       return rc;
+    if (trace)
+      tr += " front" + std::to_string(k) + "=" + std::to_string((int)since());
   }
   if (int rc = launch_back(c, n_chunks))
     return rc;
+  if (trace)
+    tr += " back=" + std::to_string((int)since());
   c->have_last = true;
-  if (int rc = collect_chunks(c, stats, true))
-    return rc;
+  int const rc_collect = collect_chunks(c, stats, true);
+  if (trace)
+    fprintf(stderr, "[gtb trace us]%s synced=%d | dev: h2d %.0f prep %.0f probe %.0f chain %.0f slow %.0f score %.0f\n", tr.c_str(), (int)since(),
+            c->t_h2d * 1e3, c->t_prep * 1e3, c->t_probe * 1e3, c->t_chain * 1e3, c->t_slow * 1e3, c->t_score * 1e3);
+  if (rc_collect)
+    return rc_collect;
   return conn_check(c, n, regs.data());
 }
 
@@ -1668,7 +1754,8 @@ int gtb_last_timing(gtb_ctx * ctx, float * h2d_ms, float * align_ms, float * sco
   if (align_ms)
     *align_ms = c->t_align;
   if (score_ms)
-    *score_ms = c->t_score;
+    *score_ms = c->t_total - c->t_align; // everything after chain_kernel as a span: slow/huge beside the first score pass,
+                                         // then the second pass -- so align_ms + score_ms = device time of the launch sequence
   if (d2h_ms)
     *d2h_ms = c->t_d2h;
   return 0;
@@ -1689,6 +1776,16 @@ int gtb_last_kernel_timing(gtb_ctx * ctx, float * probe_ms, float * chain_ms, fl
     *score_ms = c->t_score;
   if (n_slow)
     *n_slow = c->last_n_slow;
+  return 0;
+}
+
+// Device time (ms) of the batch-preparation kernels (units, aligned orientations, link checks) of the last submit/replay.
+int gtb_last_prep_timing(gtb_ctx * ctx, float * prep_ms)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !prep_ms)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  *prep_ms = c->t_prep;
   return 0;
 }
 
@@ -1859,9 +1956,21 @@ int gtb_pool_finish_multi(gtb_ctx * ctx, int n, const int * region_ids, gtb_accu
   if (int rc = c->h_accum.reserve(off[n]))
     return rc;
   uint8_t * h = static_cast<uint8_t *>(c->h_accum.p);
-  for (int i = 0; i < n; ++i)
-    CUDA_TRY(cudaMemcpyAsync(h + off[i], regs[i]->accum.p, regs[i]->accum_bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (n == 1)
+    CUDA_TRY(cudaMemcpyAsync(h, regs[0]->accum.p, regs[0]->accum_bytes, cudaMemcpyDeviceToHost, c->stream));
+  else
+  {
+    // one gather kernel + ONE D2H copy instead of a small (latency-bound) copy per region
+    if (int rc = c->d_gather.reserve(off[n]))
+      return rc;
+    unsigned long long max_bytes = 0;
+    if (int rc = upload_segments(c, n, [&](int i) { return Segment{regs[i]->accum.p, off[i], regs[i]->accum_bytes}; }, max_bytes))
+      return rc;
+    launch_gather_segments(static_cast<const Segment *>(c->d_segments.p), n, max_bytes, c->d_gather.p, c->stream);
+    CUDA_TRY(cudaMemcpyAsync(h, c->d_gather.p, off[n], cudaMemcpyDeviceToHost, c->stream));
+  }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
   parallel_for(n, [&](int i) { convert_accumulators(*regs[i], h + off[i], &outs[i]); });
   return 0;
 }
@@ -1889,16 +1998,27 @@ int gtb_pool_reset_multi(gtb_ctx * ctx, int n, const int * region_ids)
 {
   auto * c = reinterpret_cast<Ctx *>(ctx);
   cudaSetDevice(c->device);
+  std::vector<Region *> regs(n);
   for (int i = 0; i < n; ++i)
   {
     auto it = c->regions.find(region_ids[i]);
     if (it == c->regions.end() || !it->second->pool_open)
       return fail(GTB_ERR_STATE, "unknown region / pool not open");
-    CUDA_TRY(cudaMemsetAsync(it->second->accum.p, 0, it->second->accum_bytes, c->stream));
-    if (it->second->conn_cap)
-      CUDA_TRY(cudaMemsetAsync(it->second->conn.p, 0, conn_table_bytes(it->second->conn_cap), c->stream));
-    it->second->conn_used = 0;
+    regs[i] = it->second.get();
+    if (regs[i]->conn_cap)
+      CUDA_TRY(cudaMemsetAsync(regs[i]->conn.p, 0, conn_table_bytes(regs[i]->conn_cap), c->stream));
+    regs[i]->conn_used = 0;
   }
+  if (n <= 2)
+  {
+    for (int i = 0; i < n; ++i)
+      CUDA_TRY(cudaMemsetAsync(regs[i]->accum.p, 0, regs[i]->accum_bytes, c->stream));
+    return 0;
+  }
+  unsigned long long max_bytes = 0; // one launch for all regions instead of one memset each
+  if (int rc = upload_segments(c, n, [&](int i) { return Segment{regs[i]->accum.p, 0, regs[i]->accum_bytes}; }, max_bytes))
+    return rc;
+  launch_zero_segments(static_cast<const Segment *>(c->d_segments.p), n, max_bytes, c->stream);
   return 0;
 }
 

@@ -104,7 +104,7 @@ constexpr uint32_t CONN_MAX_SAMPLES = 1u << 21, CONN_MAX_BUBBLES = 1u << 16;
 // Records of one submit (possibly several regions concatenated), SoA on the device.
 struct DevBatch
 {
-  uint32_t n_records, n_units;
+  uint32_t n_records, n_units; // n_units: upper bound (= n_records) used for sizing; exact count in counters->n_units
   const uint8_t * seq4;     // [n * GTB_SEQ_STRIDE]
   const uint16_t * lseq;
   const uint16_t * flag;
@@ -152,7 +152,38 @@ struct DevCounters
   unsigned long long reasons[12];    // why slow_kernel handed a task to huge_kernel: refs vars paths locs labels candv cands keys tap pool len -
   unsigned long long n_huge;         // tasks queued for huge_kernel
   unsigned long long final_reasons[12]; // capacity overflows nothing could hold (reported as GTB_ERR_CAPACITY)
+  // written by the batch-preparation kernels (prep_*): alignment units and aligned read orientations of this chunk, and
+  // what is wrong with the input (PREP_ERR_* bits)
+  uint32_t n_units, n_active, input_bits, n_deferred;
 };
+constexpr uint32_t PREP_ERR_SAMPLE = 1, PREP_ERR_DUP = 2, PREP_ERR_MATE = 4, PREP_ERR_LEN = 8;
+
+// Batch preparation on the device (the per-record part of what genotype_only's caller does, hts_parallel_reader.cpp:655-708):
+// alignment units (records that are not duplicates of an earlier one), the list of read orientations align_read aligns at
+// all (alignment.cpp:331-363), link validation.
+struct PrepParams
+{
+  uint32_t n_records;
+  const int32_t * dup_of;       // batch-global index of the record whose alignment is re-used, or -1
+  int32_t * mate;               // in/out: a link that does not point to an earlier record is cut (and reported)
+  int32_t * sample;             // in/out: out of range -> 0 (and reported)
+  const uint16_t * lseq;
+  const uint16_t * flag;
+  const uint8_t * same_tid;
+  const int32_t * isize;
+  const uint16_t * region;
+  const DevRegion * regions;
+  unsigned long long * scan;    // [n_records] (is_unit << 32 | orientations) -> exclusive prefix sums, in place
+  int32_t * unit;               // out [n_records]
+  int32_t * unit_record;        // out [n_units]
+  uint32_t * active;            // out [n_active]
+  DevCounters * counters;
+};
+void launch_prep_flags(const PrepParams & p, void * stream);
+void launch_prep_fill(const PrepParams & p, void * stream);
+size_t scan64_temp_bytes(uint32_t n);
+int exclusive_scan64(void * temp, size_t temp_bytes, const unsigned long long * in, unsigned long long * out, uint32_t n,
+                     void * stream);
 
 // Debug tap of the seed stage: per task, per list (slot*2 + ham): count and offset into a label pool
 struct DevSeedTap
@@ -174,12 +205,16 @@ struct LaunchParams
   DevCounters * counters;
   DevSeedTap tap; // tap.list_count == nullptr when disabled
   void * cand_spill; // per-resident-warp global extension of the bubble-expansion candidate list
-  uint32_t n_active;            // read orientations that are actually aligned (align_read, alignment.cpp:331-363)
-  const uint32_t * active_tasks; // [n_active] task id = unit * 2 + orientation
+  uint32_t n_active;            // UPPER BOUND (grid / buffer sizing) of the read orientations that are actually aligned
+                                // (align_read, alignment.cpp:331-363); the exact count is counters->n_active (prep kernels)
+  const uint32_t * active_tasks; // [counters->n_active] task id = unit * 2 + orientation
   void * seed_recs;             // [n_active] SeedRec
   uint32_t * slow_tasks;        // [n_active] queue filled by chain_kernel
   uint32_t * huge_tasks;        // [n_active] queue filled by slow_kernel
   void * huge_states;           // [SM count] HugeState slabs
+  uint8_t * pending;            // [n_units * 2] set by chain_kernel for tasks it hands to slow_kernel; never cleared by the
+                                // slower tiers, so the first score pass can read it while they run
+  uint32_t * deferred;          // [n_records] records the first score pass left for the second (some task pending)
   unsigned long long * task_times; // profiling aid (GTB_TASK_TIMES=file): [n_active][2] globaltimer ns at start / end of
                                    // each chain_kernel task; nullptr normally
 };
@@ -200,7 +235,20 @@ void launch_build_table(const IndexSlot * uniq, uint32_t n, IndexSlot * table, u
 void launch_probe(const LaunchParams & p, void * stream);
 void launch_chain(const LaunchParams & p, void * stream);
 void launch_slow(const MultiLaunch & m, void * stream);
+// first pass: every record of one chunk whose tasks are all computed by chain_kernel; records with a task still queued for
+// slow_kernel are listed in p.deferred.  Second pass (after slow_kernel / huge_kernel): the deferred records of all chunks.
 void launch_score(const LaunchParams & p, bool with_connections, void * stream);
+void launch_score_deferred(const MultiLaunch & m, const bool * with_connections, void * stream);
+// Many small buffers in one launch: copy every segment to dst + dst_off (gather before ONE D2H) or zero it.
+// Pointers and sizes are multiples of 16 bytes.
+struct Segment
+{
+  void * ptr;
+  unsigned long long dst_off;
+  unsigned long long bytes;
+};
+void launch_gather_segments(const Segment * seg, int n, unsigned long long max_bytes, void * dst, void * stream);
+void launch_zero_segments(const Segment * seg, int n, unsigned long long max_bytes, void * stream);
 // connection table maintenance: re-insert every entry of (keys, vals)[0..n_slots) into R's (larger, zeroed) table;
 // compact the non-empty entries of R's table into (out_keys, out_vals), count in *out_n
 void launch_conn_rehash(const unsigned long long * keys, const uint32_t * vals, uint32_t n_slots, const DevRegion & R, void * stream);

@@ -496,6 +496,19 @@ int idx_exclusive_scan(void * temp, size_t temp_bytes, const uint32_t * in, uint
   return (int)cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, (int)n, (cudaStream_t)stream);
 }
 
+size_t scan64_temp_bytes(uint32_t n)
+{
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)n);
+  return bytes;
+}
+
+int exclusive_scan64(void * temp, size_t temp_bytes, const unsigned long long * in, unsigned long long * out, uint32_t n,
+                     void * stream)
+{
+  return (int)cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, (int)n, (cudaStream_t)stream);
+}
+
 int idx_inclusive_scan(void * temp, size_t temp_bytes, const uint32_t * in, uint32_t * out, uint32_t n, void * stream)
 {
   return (int)cub::DeviceScan::InclusiveSum(temp, temp_bytes, in, out, (int)n, (cudaStream_t)stream);

@@ -1463,10 +1463,110 @@ static_assert(sizeof(SeedRec) == SEED_REC_BYTES, "SeedRec layout");
 
 __device__ __forceinline__ void push_slow(const LaunchParams & P, uint32_t task)
 {
+  P.pending[task] = 1;
   unsigned long long const i = atomicAdd(&P.counters->n_slow, 1ull);
   P.slow_tasks[i] = task;
 }
 } // namespace
+
+// ================================================================================================ batch preparation
+namespace
+{
+// orientations align_read aligns for a unit record: none below 2K-1 bases; forward only for unpaired reads and for properly
+// oriented pairs within 1200 bp; else both (alignment.cpp:343-360)
+__device__ __forceinline__ uint32_t orientations_of(const PrepParams & p, uint32_t k)
+{
+  uint32_t const L = p.lseq[k];
+  if (L < 63u || L > (uint32_t)MAX_SEQ)
+    return 0;
+  uint32_t const flag = p.flag[k];
+  int32_t const isz = p.isize[k];
+  bool const fwd_only = (flag & 1u) == 0 || (p.same_tid[k] && isz > -1200 && isz < 1200 && (((flag & 16u) != 0) != ((flag & 32u) != 0)));
+  return fwd_only ? 1u : 2u;
+}
+} // namespace
+
+__global__ void __launch_bounds__(256) prep_flags_kernel(PrepParams p)
+{
+  uint32_t const k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p.n_records)
+    return;
+  uint32_t err = 0;
+  int32_t const d = p.dup_of[k];
+  bool is_unit = d < 0;
+  if (d >= (int32_t)k)
+  {
+    err |= PREP_ERR_DUP;
+    is_unit = true;
+  }
+  if (p.lseq[k] > (uint16_t)MAX_SEQ)
+    err |= PREP_ERR_LEN;
+  int32_t const s = p.sample[k];
+  if (s < 0 || s >= (int32_t)p.regions[p.region[k]].n_samples)
+  {
+    err |= PREP_ERR_SAMPLE;
+    p.sample[k] = 0;
+  }
+  if (p.mate[k] >= (int32_t)k)
+  {
+    err |= PREP_ERR_MATE;
+    p.mate[k] = -1;
+  }
+  if (err)
+    atomicOr(&p.counters->input_bits, err);
+  p.scan[k] = is_unit ? ((1ull << 32) | orientations_of(p, k)) : 0ull;
+}
+
+__global__ void __launch_bounds__(256) prep_fill_kernel(PrepParams p)
+{
+  uint32_t const k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p.n_records)
+    return;
+  int32_t const d = p.dup_of[k];
+  bool const is_unit = d < 0 || d >= (int32_t)k;
+  unsigned long long const v = p.scan[k];
+  uint32_t const u = (uint32_t)(v >> 32), a = (uint32_t)v;
+  uint32_t n_or = 0;
+  if (is_unit)
+  {
+    n_or = orientations_of(p, k);
+    p.unit[k] = (int32_t)u;
+    p.unit_record[u] = (int32_t)k;
+    if (n_or >= 1)
+      p.active[a] = u * 2;
+    if (n_or == 2)
+      p.active[a + 1] = u * 2 + 1;
+  }
+  else
+  {
+    int32_t r = d; // the record whose alignment is re-used may itself re-use an earlier one
+    for (;;)
+    {
+      int32_t const dd = p.dup_of[r];
+      if (dd < 0 || dd >= r)
+        break;
+      r = dd;
+    }
+    p.unit[k] = (int32_t)(p.scan[r] >> 32);
+  }
+  if (k == p.n_records - 1)
+  {
+    p.counters->n_units = u + (is_unit ? 1u : 0u);
+    p.counters->n_active = a + n_or;
+  }
+}
+
+void launch_prep_flags(const PrepParams & p, void * stream)
+{
+  if (p.n_records)
+    prep_flags_kernel<<<(p.n_records + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+}
+
+void launch_prep_fill(const PrepParams & p, void * stream)
+{
+  if (p.n_records)
+    prep_fill_kernel<<<(p.n_records + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+}
 
 // ================================================================================================ probe kernel
 // One warp per active task; phase A only.  Tiny shared state -> high occupancy; all lanes busy.
@@ -1477,7 +1577,7 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(LaunchParams P)
   int const lane = threadIdx.x & 31;
   int const wib = threadIdx.x >> 5;
   uint32_t const t = blockIdx.x * PROBE_WARPS + wib;
-  if (t >= P.n_active)
+  if (t >= P.counters->n_active)
     return;
   uint32_t const task = P.active_tasks[t];
   uint32_t const unit = task >> 1;
@@ -1628,7 +1728,7 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(LaunchParams P)
 __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(LaunchParams P)
 {
   uint32_t const t = blockIdx.x * CHAIN_THREADS + threadIdx.x;
-  if (t >= P.n_active)
+  if (t >= P.counters->n_active)
     return;
   uint32_t const task = P.active_tasks[t];
   const SeedRec * recp = reinterpret_cast<const SeedRec *>(P.seed_recs) + t;
@@ -2405,11 +2505,57 @@ __device__ void make_genos(const LaunchParams & P, int rec, Geno & first, Geno &
 
 // CONN: also build the phasing connections (regions whose conn_mask is 0 skip them at run time)
 template <bool CONN>
+__device__ void score_record(const LaunchParams & P, uint32_t i);
+
+// first pass: one thread per record of a chunk
+template <bool CONN>
 __global__ void __launch_bounds__(128) score_kernel(LaunchParams P)
 {
   uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.batch.n_records)
     return;
+  {
+    // anything this record needs still queued for the slower tiers?  (own alignment unit, and the mate's)
+    int const u = P.batch.unit[i];
+    int32_t const m = P.batch.mate[i];
+    uint32_t pend = (uint32_t)P.pending[2 * u] | (uint32_t)P.pending[2 * u + 1];
+    if (m >= 0)
+    {
+      int const um = P.batch.unit[m];
+      pend |= (uint32_t)P.pending[2 * um] | (uint32_t)P.pending[2 * um + 1];
+    }
+    if (pend)
+    {
+      P.deferred[atomicAdd(&P.counters->n_deferred, 1u)] = i;
+      return;
+    }
+  }
+  score_record<CONN>(P, i);
+}
+
+// second pass: the deferred records of all chunks of a submit, after slow_kernel and huge_kernel
+template <bool CONN>
+__global__ void __launch_bounds__(128) score_deferred_kernel(const __grid_constant__ MultiLaunch M, uint32_t conn_chunks)
+{
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int c = 0; c < M.n; ++c)
+  {
+    uint32_t const n = M.p[c].counters->n_deferred;
+    if (j < n)
+    {
+      if (CONN && ((conn_chunks >> c) & 1u))
+        score_record<true>(M.p[c], M.p[c].deferred[j]);
+      else
+        score_record<false>(M.p[c], M.p[c].deferred[j]);
+      return;
+    }
+    j -= n;
+  }
+}
+
+template <bool CONN>
+__device__ void score_record(const LaunchParams & P, uint32_t const i)
+{
   uint16_t const flag = P.batch.flag[i];
   int32_t const m = P.batch.mate[i];
   const DevRegion & R = P.regions[P.batch.region[i]];
@@ -2535,6 +2681,45 @@ __global__ void __launch_bounds__(128) score_kernel(LaunchParams P)
       atomicAdd(&P.counters->n_singles_scored, 1ull);
     }
   }
+}
+
+// ================================================================================================ segment gather / zero
+__global__ void __launch_bounds__(256) gather_segments_kernel(const Segment * seg, uint8_t * dst)
+{
+  Segment const sg = seg[blockIdx.y];
+  const uint4 * src = static_cast<const uint4 *>(sg.ptr);
+  uint4 * out = reinterpret_cast<uint4 *>(dst + sg.dst_off);
+  size_t const n = sg.bytes / 16;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) zero_segments_kernel(const Segment * seg)
+{
+  Segment const sg = seg[blockIdx.y];
+  uint4 * out = static_cast<uint4 *>(sg.ptr);
+  size_t const n = sg.bytes / 16;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = make_uint4(0, 0, 0, 0);
+}
+
+static dim3 segment_grid(int n, unsigned long long max_bytes)
+{
+  unsigned long long const per_block = 256ull * 16 * 4; // four 16-byte words per thread
+  unsigned const gx = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>((max_bytes + per_block - 1) / per_block, 1), 1024);
+  return dim3(gx, (unsigned)n, 1);
+}
+
+void launch_gather_segments(const Segment * seg, int n, unsigned long long max_bytes, void * dst, void * stream)
+{
+  if (n > 0)
+    gather_segments_kernel<<<segment_grid(n, max_bytes), 256, 0, (cudaStream_t)stream>>>(seg, static_cast<uint8_t *>(dst));
+}
+
+void launch_zero_segments(const Segment * seg, int n, unsigned long long max_bytes, void * stream)
+{
+  if (n > 0)
+    zero_segments_kernel<<<segment_grid(n, max_bytes), 256, 0, (cudaStream_t)stream>>>(seg);
 }
 
 // ================================================================================================ connection table upkeep
@@ -2669,6 +2854,26 @@ void launch_score(const LaunchParams & p, bool with_connections, void * stream)
     score_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
   else
     score_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+}
+
+void launch_score_deferred(const MultiLaunch & m, const bool * with_connections, void * stream)
+{
+  // grid bound: slow tasks are rare; the kernel reads the exact counts on the device.  One block per 128 records of the
+  // largest plausible backlog (1/64 of the records, at least 4 blocks); a backlog beyond that is handled by more passes.
+  uint32_t total = 0, conn_chunks = 0;
+  for (int c = 0; c < m.n; ++c)
+  {
+    total += m.p[c].batch.n_records;
+    if (with_connections[c])
+      conn_chunks |= 1u << c;
+  }
+  if (total == 0)
+    return;
+  uint32_t const grid = (total + 127) / 128;
+  if (conn_chunks)
+    score_deferred_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(m, conn_chunks);
+  else
+    score_deferred_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(m, conn_chunks);
 }
 
 void launch_conn_rehash(const unsigned long long * keys, const uint32_t * vals, uint32_t n_slots, const DevRegion & R, void * stream)

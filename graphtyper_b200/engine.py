@@ -24,7 +24,7 @@ EXPORTS = [
     "gtb_debug_path_sizes", "gtb_debug_paths", "gtb_calls_from_accumulators", "gtb_scan_calls", "gtb_merge_varstats", "gtb_replay_last",
     "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_set_chunks", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators", "gtb_allreduce_accumulators_multi", "gtb_debug_counters",
     "gtb_sw_align_batch", "gtb_sw_last_timing", "gtb_sw_replay_last", "gtb_set_index_build",
-    "gtb_set_connections", "gtb_connections_size", "gtb_connections", "gtb_phase_support",
+    "gtb_set_connections", "gtb_connections_size", "gtb_connections", "gtb_phase_support", "gtb_last_prep_timing",
 ]
 
 
@@ -90,6 +90,7 @@ def load_library() -> C.CDLL:
     L.gtb_sw_last_timing.argtypes = [vp, fp, fp, fp]
     L.gtb_sw_replay_last.argtypes = [vp]
     L.gtb_set_index_build.argtypes = [vp, C.c_int]
+    L.gtb_last_prep_timing.argtypes = [vp, fp]
     L.gtb_set_connections.argtypes = [vp, C.c_int]
     L.gtb_connections_size.argtypes = [vp, C.c_int, abi.u64p]
     L.gtb_connections.argtypes = [vp, C.c_int, C.c_void_p]
@@ -252,8 +253,10 @@ class Context:
     def last_kernel_timing(self) -> Dict[str, float]:
         a, b, c, d, n = C.c_float(), C.c_float(), C.c_float(), C.c_float(), C.c_uint64()
         self._check(self.lib.gtb_last_kernel_timing(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(n)))
-        return {"probe_kernel": a.value, "chain_kernel": b.value, "slow_kernel": c.value, "score_kernel": d.value,
-                "n_slow_tasks": int(n.value)}
+        p = C.c_float()
+        self._check(self.lib.gtb_last_prep_timing(self.h, C.byref(p)))
+        return {"prep_kernels": p.value, "probe_kernel": a.value, "chain_kernel": b.value, "slow_kernel": c.value,
+                "score_kernel": d.value, "n_slow_tasks": int(n.value)}
 
     def pool_finish(self, region_id: int) -> abi.HostAccumulators:
         acc = self.alloc_accumulators(region_id)

@@ -210,8 +210,14 @@ int gtb_calls_from_accumulators(const gtb_accumulators *acc, uint8_t *phred /*[n
  * submit/replay from CUDA events on the library's stream; zero a region's accumulators. */
 int gtb_replay_last(gtb_ctx *ctx, gtb_submit_stats *stats);
 int gtb_last_timing(gtb_ctx *ctx, float *h2d_ms, float *align_ms, float *score_ms, float *d2h_ms);
+/* align_ms = batch preparation + probe_kernel + chain_kernel; score_ms = everything after chain_kernel measured as ONE span
+ * (slow_kernel / huge_kernel run beside the first score pass, then the second pass), so align_ms + score_ms is the device
+ * time of the launch sequence when the submit was a single chunk. */
 int gtb_last_kernel_timing(gtb_ctx *ctx, float *probe_ms, float *chain_ms, float *slow_ms, float *score_ms,
                            uint64_t *n_slow);
+/* Device time (ms) of the batch-preparation kernels of the last submit/replay: alignment units of the duplicate-read
+ * shortcut (hts_parallel_reader.cpp:666-684), the orientations align_read aligns (alignment.cpp:343-360), link checks. */
+int gtb_last_prep_timing(gtb_ctx *ctx, float *prep_ms);
 int gtb_pool_reset(gtb_ctx *ctx, int region_id);
 /* Pipeline chunks of gtb_submit_reads_multi: staging of chunk k+1 overlaps copy + kernels of chunk k (0 = automatic). */
 int gtb_set_chunks(gtb_ctx *ctx, int n_chunks);
