@@ -196,7 +196,7 @@ struct Ctx
                                                         // [4], [3] around the second score pass
   int connections = 0;   // gtb_set_connections: 0 off, otherwise table slots reserved per submitted record
   PinnedBuffer h_conn_state;
-  float t_h2d = 0, t_align = 0, t_score = 0, t_d2h = 0, t_probe = 0, t_chain = 0, t_slow = 0, t_total = 0, t_prep = 0;
+  float t_h2d = 0, t_align = 0, t_score = 0, t_d2h = 0, t_probe = 0, t_chain = 0, t_slow = 0, t_total = 0, t_prep = 0, t_score0 = 0, t_score1 = 0;
   unsigned long long last_n_slow = 0;
   // nccl (loaded lazily with dlopen, see gtb_nccl.cpp part below)
   void * nccl_lib = nullptr;
@@ -495,6 +495,10 @@ int gtb_create(int device_id, gtb_ctx ** out)
     }
     e = cudaSetDevice(device_id);
     if (e == cudaSuccess)
+      e = (cudaError_t)upload_hash_tables_kernels();
+    if (e == cudaSuccess)
+      e = (cudaError_t)upload_hash_tables_index();
+    if (e == cudaSuccess)
       e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess)
       e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
@@ -603,6 +607,20 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g, bool dev
   size_t const o_bubble_order = place<uint32_t>(off, R.n_bubbles);
   size_t const o_score_off = place<uint32_t>(off, R.n_bubbles + 1);
   size_t const o_cov_off = place<uint32_t>(off, R.n_bubbles + 1);
+  // id2hap (vcf_writer.cpp:84) as a direct table: bubble index by (var order - first bubble order); the score kernels would
+  // otherwise binary-search bubble_order for every bubble of every path (9 dependent loads)
+  uint32_t hap_base = 0, hap_span = 0;
+  if (R.n_bubbles > 0 && R.n_bubbles < 0xFFFFu)
+  {
+    uint32_t const lo = *std::min_element(R.bubble_order.begin(), R.bubble_order.end());
+    uint32_t const hi = *std::max_element(R.bubble_order.begin(), R.bubble_order.end());
+    if ((uint64_t)hi - lo < (1ull << 24))
+    {
+      hap_base = lo;
+      hap_span = hi - lo + 1;
+    }
+  }
+  size_t const o_hap = place<uint16_t>(off, hap_span);
   // device index build: events + the sweep-order node table instead of a host-built index
   bool const have_ev = dev_index && g->var_ev_off && g->var_aev_off && g->var_ev && g->var_aev;
   size_t const n_ev = have_ev ? g->var_ev_off[g->n_var] : 0, n_aev = have_ev ? g->var_aev_off[g->n_var] : 0;
@@ -653,6 +671,13 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g, bool dev
   put32(o_bubble_order, R.bubble_order.data(), R.n_bubbles);
   put32(o_score_off, R.score_off.data(), R.n_bubbles + 1);
   put32(o_cov_off, R.cov_off.data(), R.n_bubbles + 1);
+  if (hap_span)
+  {
+    uint16_t * tab = reinterpret_cast<uint16_t *>(h + o_hap);
+    memset(tab, 0xFF, (size_t)hap_span * 2);
+    for (uint32_t b = 0; b < R.n_bubbles; ++b)
+      tab[R.bubble_order[b] - hap_base] = (uint16_t)b; // ascending b: on duplicate orders the last bubble wins, like id2hap
+  }
   uint32_t n_jobs = 0;
   if (dev_index)
   {
@@ -725,6 +750,9 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g, bool dev
   D.sp_off = reinterpret_cast<const uint32_t *>(d + o_sp_off);
   D.sp_list = reinterpret_cast<const uint32_t *>(d + o_sp_list);
   D.bubble_order = reinterpret_cast<const uint32_t *>(d + o_bubble_order);
+  D.hap_of_order = hap_span ? reinterpret_cast<const uint16_t *>(d + o_hap) : nullptr;
+  D.hap_base = hap_base;
+  D.hap_span = hap_span;
   D.score_off = reinterpret_cast<const uint32_t *>(d + o_score_off);
   D.cov_off = reinterpret_cast<const uint32_t *>(d + o_cov_off);
   D.table = reinterpret_cast<const IndexSlot *>(d + o_table);
@@ -1196,8 +1224,12 @@ static int launch_front(Ctx * c, BatchState & B, cudaEvent_t after)
   CUDA_TRY(cudaEventRecord(B.ev[3], s));
   launch_chain(P, s);
   CUDA_TRY(cudaEventRecord(B.ev[4], s));
-  // first score pass: every record whose tasks chain_kernel finished (all but a few dozen per 10^5)
-  launch_score(P, B.with_conn, s);
+  // Several chunks: a first score pass right away for every record whose tasks chain_kernel finished (all but a few dozen
+  // per 10^5), so that only the last chunk's pass is on the critical path; the rest waits for slow_kernel (second pass).
+  // One chunk: nothing to overlap -- slow_kernel first, then ONE score pass over everything (launch_back).
+  P.defer = c->n_chunks_last > 1 ? 1u : 0u;
+  if (P.defer)
+    launch_score(P, B.with_conn, s);
   CUDA_TRY(cudaEventRecord(B.ev[5], s));
   return 0;
 }
@@ -1222,7 +1254,10 @@ static int launch_back(Ctx * c, int n_chunks)
   launch_slow(M, ts);
   CUDA_TRY(cudaEventRecord(c->ev_slow[1], ts));
   CUDA_TRY(cudaEventRecord(c->ev_slow[4], ts));
-  launch_score_deferred(M, with_conn, ts); // second score pass: the records that waited for slow_kernel / huge_kernel
+  if (n_chunks > 1)
+    launch_score_deferred(M, with_conn, ts); // second score pass: the records that waited for slow_kernel / huge_kernel
+  else
+    launch_score(c->bs[0].P, with_conn[0], ts);
   CUDA_TRY(cudaEventRecord(c->ev_slow[3], ts));
   for (int k = 0; k < n_chunks; ++k)
   {
@@ -1301,7 +1336,7 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     st.n_pairs_scored += kc->n_pairs_scored;
     st.n_singles_scored += kc->n_singles_scored;
     st.n_capacity_overflow += kc->n_overflow;
-    st.kernel_launches += B.P.batch.n_records ? 6 : 0; // prep_flags, scan (1 kernel at these sizes), prep_fill, probe, chain, score
+    st.kernel_launches += B.P.batch.n_records ? 5 + (c->n_chunks_last > 1 ? 1 : 0) : 0; // prep_flags, scan, prep_fill, probe, chain (+ first score pass)
     n_overflow += kc->n_overflow;
     n_input_error += kc->n_input_error;
     for (int q = 0; q < 12; ++q)
@@ -1311,8 +1346,10 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     float t = 0;
     cudaEventElapsedTime(&t, c->ev_slow[0], c->ev_slow[1]);
     c->t_slow = t;
+    c->t_score0 = c->t_score;
     cudaEventElapsedTime(&t, c->ev_slow[4], c->ev_slow[3]);
     c->t_score += t; // second pass
+    c->t_score1 = t;
     cudaEventElapsedTime(&t, c->ev_slow[3], c->bs[c->n_chunks_last - 1].ev[7]);
     c->t_d2h = t;
     cudaEventElapsedTime(&t, c->bs[0].ev[2], c->ev_slow[3]);
@@ -1717,8 +1754,9 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   c->have_last = true;
   int const rc_collect = collect_chunks(c, stats, true);
   if (trace)
-    fprintf(stderr, "[gtb trace us]%s synced=%d | dev: h2d %.0f prep %.0f probe %.0f chain %.0f slow %.0f score %.0f\n", tr.c_str(), (int)since(),
-            c->t_h2d * 1e3, c->t_prep * 1e3, c->t_probe * 1e3, c->t_chain * 1e3, c->t_slow * 1e3, c->t_score * 1e3);
+    fprintf(stderr, "[gtb trace us]%s synced=%d | dev: h2d %.0f prep %.0f probe %.0f chain %.0f score0 %.0f slow %.0f score1 %.0f total %.0f\n",
+            tr.c_str(), (int)since(), c->t_h2d * 1e3, c->t_prep * 1e3, c->t_probe * 1e3, c->t_chain * 1e3, c->t_score0 * 1e3,
+            c->t_slow * 1e3, c->t_score1 * 1e3, c->t_total * 1e3);
   if (rc_collect)
     return rc_collect;
   return conn_check(c, n, regs.data());

@@ -28,7 +28,10 @@ constexpr int HUGE_P = 512, HUGE_V = 48, HUGE_C = 640, HUGE_CV = 48, HUGE_WL = 2
 constexpr int FAST_P = 6, FAST_V = 8, FAST_C = 6, FAST_CV = 8, FAST_WL = 12, FAST_LOC = 4;
 constexpr int SEED_INLINE = 10;     // index bucket references handed from probe_kernel to chain_kernel per task
 constexpr int SEED_REC_BYTES = 16 + 8 * SEED_INLINE;
-constexpr int PROBE_WARPS = 8;      // warps per block of probe_kernel
+#ifndef GTB_PROBE_WARPS
+#define GTB_PROBE_WARPS 8
+#endif
+constexpr int PROBE_WARPS = GTB_PROBE_WARPS; // warps per block of probe_kernel
 #ifndef GTB_CHAIN_THREADS
 #define GTB_CHAIN_THREADS 128
 #endif
@@ -40,6 +43,55 @@ constexpr int CHAIN_MIN_BLOCKS = GTB_CHAIN_MIN_BLOCKS; // 8 x 128 -> <= 64 regis
 constexpr int MAX_TOUCH = 48; // bubbles touched by one read in the accumulate kernel (= HUGE_V)
 using allele_mask_t = uint32_t; // allele set of one bubble on a path: bit a = allele a  (<= 32 alleles per bubble)
 constexpr int MAX_ALLELES = 32;
+
+// ---- hash of the k-mer table: GF(2)-linear, h(x) = XOR of basis[i] over the set bits i of x (32-bit result; table slot =
+// top log2(capacity) bits, presence-bitmap bit = top log2(capacity) + 2 bits).  Linearity is what the probe kernel lives on:
+// h(key ^ m) = h(key) ^ h(m), so the 96 Hamming-1 neighbours of a seed cost one XOR each with per-lane constants h(m), and
+// h(key) itself is the XOR-reduction of one per-lane word per base.  With a pseudo-random basis the family is universal,
+// which is all open addressing at load <= 0.25 asks for.  Full keys are hashed by byte tables (8 lookups).
+struct HashTables
+{
+  uint32_t basis[64];
+  uint32_t tab[8 * 256]; // tab[j * 256 + b] = hash of byte value b at byte position j
+};
+inline const HashTables & hash_tables()
+{
+  static const HashTables T = []() {
+    HashTables t{};
+    uint64_t x = 0x6A09E667F3BCC909ull; // splitmix64 stream
+    for (int i = 0; i < 64; ++i)
+    {
+      x += 0x9E3779B97F4A7C15ull;
+      uint64_t z = x;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z ^= z >> 31;
+      t.basis[i] = (uint32_t)(z >> 32);
+    }
+    for (int j = 0; j < 8; ++j)
+      for (int b = 0; b < 256; ++b)
+      {
+        uint32_t h = 0;
+        for (int i = 0; i < 8; ++i)
+          if ((b >> i) & 1)
+            h ^= t.basis[8 * j + i];
+        t.tab[j * 256 + b] = h;
+      }
+    return t;
+  }();
+  return T;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t hash32_tab(const uint32_t * T, uint64_t k)
+{
+  uint32_t const lo = (uint32_t)k, hi = (uint32_t)(k >> 32);
+  return T[lo & 255u] ^ T[256 + ((lo >> 8) & 255u)] ^ T[512 + ((lo >> 16) & 255u)] ^ T[768 + (lo >> 24)] ^ T[1024 + (hi & 255u)] ^
+         T[1280 + ((hi >> 8) & 255u)] ^ T[1536 + ((hi >> 16) & 255u)] ^ T[1792 + (hi >> 24)];
+}
+#endif
+// every translation unit with kernels keeps its own device copy of the tables (no relocatable device code); called by gtb_create
+int upload_hash_tables_kernels();
+int upload_hash_tables_index();
 
 struct DevLabel
 {
@@ -53,7 +105,7 @@ struct DevRegion
   // graph (include/gtb200.h: gtb_graph_view)
   uint32_t n_ref, n_var, n_special, n_sp_keys;
   uint32_t is_sv, n_bubbles, n_samples, table_mask;
-  int table_shift, pad0;
+  int table_shift, pad0; // table_shift = 32 - log2(table capacity): slot = hash32 >> table_shift
   const uint32_t * ref_order;
   const uint32_t * ref_seq_off; // [n_ref+1]
   const uint32_t * ref_var_off; // [n_ref+1]
@@ -67,6 +119,8 @@ struct DevRegion
   const uint32_t * sp_off;
   const uint32_t * sp_list;
   const uint32_t * bubble_order; // [n_bubbles] order of bubble b's var nodes (Genotype::id)
+  const uint16_t * hap_of_order; // [hap_span] bubble index by (order - hap_base), 0xFFFF = none; nullptr = search bubble_order
+  uint32_t hap_base, hap_span;
   const uint32_t * score_off;    // [n_bubbles+1]
   const uint32_t * cov_off;      // [n_bubbles+1]
   // index
@@ -215,6 +269,7 @@ struct LaunchParams
   uint8_t * pending;            // [n_units * 2] set by chain_kernel for tasks it hands to slow_kernel; never cleared by the
                                 // slower tiers, so the first score pass can read it while they run
   uint32_t * deferred;          // [n_records] records the first score pass left for the second (some task pending)
+  uint32_t defer;               // 1: score_kernel runs before slow_kernel and defers; 0: it runs after and scores everything
   unsigned long long * task_times; // profiling aid (GTB_TASK_TIMES=file): [n_active][2] globaltimer ns at start / end of
                                    // each chain_kernel task; nullptr normally
 };

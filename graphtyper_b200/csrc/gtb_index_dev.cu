@@ -24,6 +24,13 @@
 
 namespace gtb
 {
+__device__ uint32_t g_hash_tab_idx[8 * 256]; // this translation unit's copy of HashTables::tab (gtb_device.cuh)
+
+int upload_hash_tables_index()
+{
+  return (int)cudaMemcpyToSymbol(g_hash_tab_idx, hash_tables().tab, sizeof(uint32_t) * 8 * 256);
+}
+
 namespace
 {
 constexpr int IDX_MAX_FRAMES = 64;
@@ -454,10 +461,10 @@ __global__ void __launch_bounds__(256) idx_table_kernel(const IdxRegion * region
   s.cnt -= s.off;
   G.uniq[u].cnt = s.cnt;
   unsigned long long const val = (unsigned long long)s.off | ((unsigned long long)s.cnt << 32);
-  uint64_t const hs = s.key * 0x9E3779B97F4A7C15ull;
-  uint32_t const bi = (uint32_t)(hs >> (G.table_shift - 2)); // presence bitmap: 4 bits per table slot
+  uint32_t const hs = hash32_tab(g_hash_tab_idx, s.key);
+  uint32_t const bi = hs >> (G.table_shift - 34); // presence bitmap: 4 bits per table slot
   atomicOr(&G.bitmap[bi >> 5], 1u << (bi & 31u));
-  uint32_t h = (uint32_t)(hs >> G.table_shift);
+  uint32_t h = hs >> (G.table_shift - 32);
   while (true)
   {
     unsigned long long * w = reinterpret_cast<unsigned long long *>(&G.table[h]) + 1;

@@ -27,6 +27,17 @@
 
 namespace gtb
 {
+__device__ uint32_t g_hash_tab[8 * 256]; // this translation unit's copies of HashTables (gtb_device.cuh)
+__constant__ uint32_t c_hash_basis[64];
+
+int upload_hash_tables_kernels()
+{
+  cudaError_t e = cudaMemcpyToSymbol(g_hash_tab, hash_tables().tab, sizeof(uint32_t) * 8 * 256);
+  if (e == cudaSuccess)
+    e = cudaMemcpyToSymbol(c_hash_basis, hash_tables().basis, sizeof(uint32_t) * 64);
+  return (int)e;
+}
+
 namespace
 {
 constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -198,7 +209,7 @@ struct GR
 // ------------------------------------------------------------------------------------------------ phase A: seeds
 __device__ __forceinline__ uint32_t slot_of(const DevRegion & R, uint64_t key)
 {
-  return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> R.table_shift);
+  return hash32_tab(g_hash_tab, key) >> (R.table_shift - 32);
 }
 
 // continues a linear-probing lookup whose first slot `s` (at index h) has already been loaded
@@ -1569,114 +1580,264 @@ void launch_prep_fill(const PrepParams & p, void * stream)
 }
 
 // ================================================================================================ probe kernel
-// One warp per active task; phase A only.  Tiny shared state -> high occupancy; all lanes busy.
-__global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(LaunchParams P)
+// Phase A only: seed keys -> index bucket references (PHIndex::get / multi_get, ph_index.cpp:24-107).
+//
+// One persistent block per SM (32 warps, one warp per task at a time).  A task asks for 4 x (1 + 96) keys, and 95+ of the
+// 96 Hamming-1 neighbours of a seed are absent from the index; answering "absent" from global memory costs one L1
+// wavefront per lane (every lane hits a different line), and ncu showed exactly that as the limiter (388 scattered 4-byte
+// gathers per task, L1TEX tag stage ~70 % busy, issue slots idle).  So the presence filter of the region a block works on
+// lives in SHARED memory (<= 128 KiB: the region's presence bitmap OR-folded to 2^20 bits, ~6 % of the bits set for a 50 kb
+// region); a block walks its contiguous share of the task list region by region (tasks arrive grouped by region) and
+// re-stages the filter when the region changes.  Only keys whose filter bit is set go to the table in HBM/L2: the exact key
+// + ~6 neighbours per slot, compacted in key order onto lanes 0..n-1 so the table is walked once per slot.  Regions whose
+// bitmap would have to be folded more than 4x (more than ~2.6e5 distinct k-mers) keep probing the global bitmap.
+//
+// The table hash is GF(2)-linear (gtb_device.cuh): hash(key) is one __reduce_xor_sync over per-lane words, the hash of a
+// neighbour one XOR with a per-lane constant.  PHIndex::multi_get's ">75 labels => drop the slot" rule is a warp scan over
+// the compacted hits.
+constexpr int PROBE_BLOCK_WARPS = 32;
+constexpr uint32_t FILTER_LOG2_BITS = 20; // 128 KiB
+constexpr uint32_t FILTER_WORDS = 1u << (FILTER_LOG2_BITS - 5);
+constexpr int FILTER_MAX_FOLD = 2;        // log2: the bitmap is folded at most 4x
+
+namespace
 {
-  __shared__ uint8_t s_codes[PROBE_WARPS][MAX_SEQ + 8];
-  __shared__ uint2 s_refs[PROBE_WARPS][SEED_INLINE];
+__device__ __forceinline__ uint32_t or_fold2(uint32_t x) // bit j of the result = bit 2j | bit 2j+1 of x (16 result bits)
+{
+  x = (x | (x >> 1)) & 0x55555555u;
+  x = (x | (x >> 1)) & 0x33333333u;
+  x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+  x = (x | (x >> 4)) & 0x00FF00FFu;
+  x = (x | (x >> 8)) & 0x0000FFFFu;
+  return x;
+}
+} // namespace
+
+__global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(LaunchParams P)
+{
+  extern __shared__ __align__(16) uint32_t s_filter[]; // FILTER_WORDS
+  __shared__ uint16_t s_cand[PROBE_BLOCK_WARPS][4 * 97 + 4]; // candidates of a task, slot-major and in key order:
+                                                             // slot << 8 | (0 = the exact key, 1 + k = neighbour k = bb * 3 + j)
+  __shared__ uint2 s_key[PROBE_BLOCK_WARPS][MAX_SLOTS];      // seed keys (lo, hi) of the task a warp works on
+  __shared__ uint32_t s_kh[PROBE_BLOCK_WARPS][MAX_SLOTS];    // and their hashes
+  __shared__ uint2 s_refs[PROBE_BLOCK_WARPS][SEED_INLINE];
+  __shared__ uint32_t s_hm[96];                        // hashes of the 96 neighbour masks
+  __shared__ uint32_t s_seg_end;
   int const lane = threadIdx.x & 31;
   int const wib = threadIdx.x >> 5;
-  uint32_t const t = blockIdx.x * PROBE_WARPS + wib;
-  if (t >= P.counters->n_active)
-    return;
-  uint32_t const task = P.active_tasks[t];
-  uint32_t const unit = task >> 1;
-  int const orient = task & 1;
-  int const rec = P.batch.unit_record[unit];
-  int const L = P.batch.lseq[rec];
-  const DevRegion & R = P.regions[P.batch.region[rec]];
-  uint8_t * codes = s_codes[wib];
+  uint32_t const lt = (1u << lane) - 1u;
+  uint16_t * cand = s_cand[wib];
   uint2 * refs = s_refs[wib];
-  {
-    const uint8_t * s4 = P.batch.seq4 + (size_t)rec * GTB_SEQ_STRIDE;
-    for (int j = lane; j < L; j += 32)
-    {
-      int const src = orient ? (L - 1 - j) : j;
-      uint8_t const byte = __ldg(s4 + (src >> 1));
-      uint8_t c = (src & 1) ? (byte & 15) : (byte >> 4);
-      if (orient)
-        c = comp4(c);
-      codes[j] = c;
-    }
-  }
-  __syncwarp();
-  int const nslots = 1 + (L - 32) / 31; // get_num_kmers (kmer_help_functions.cpp:10-17)
-  int nrefs = 0;
-  bool slow = false;
-  // XOR masks of this lane's three Hamming-1 neighbours: key index k = q*32 + lane flips base k/3 by (k%3 + 1)
-  uint64_t nmask[3];
+  uint32_t const n_active = P.counters->n_active;
+  // Per lane, task-independent:
+  //   hm[q]   hash of the XOR mask of this lane's q-th Hamming-1 neighbour: key index k = q*32 + lane flips base k/3 by (k%3 + 1)
+  //   hb[v]   hash of base value v at this lane's position of the key (base `lane` of a seed sits at bits 2(31-lane))
+  uint32_t hm[3], hb[4];
 #pragma unroll
   for (int q = 0; q < 3; ++q)
   {
     int const k = q * 32 + lane;
-    nmask[q] = (uint64_t)(k % 3 + 1) << (2 * (k / 3));
+    int const bb = k / 3, j = k % 3 + 1;
+    hm[q] = ((j & 1) ? c_hash_basis[2 * bb] : 0u) ^ ((j & 2) ? c_hash_basis[2 * bb + 1] : 0u);
+    asm volatile("" : "+r"(hm[q])); // opaque: keep it in a register instead of re-deriving it inside the task loop
   }
-  uint32_t cnts = 0, cnts_hi = 0; // 8 x 8-bit list counts
-  for (int i = 0; i < nslots && !slow; ++i)
+  hb[0] = 0;
+  hb[1] = c_hash_basis[2 * (31 - lane)];
+  hb[2] = c_hash_basis[2 * (31 - lane) + 1];
+  hb[3] = hb[1] ^ hb[2];
+  asm volatile("" : "+r"(hb[1]), "+r"(hb[2]), "+r"(hb[3]));
+  if (threadIdx.x < 96)
   {
-    uint8_t const c = codes[31 * i + lane];
-    if (!__all_sync(FULL, __popc((unsigned)c) == 1))
+    int const k = threadIdx.x, bb = k / 3, j = k % 3 + 1;
+    s_hm[k] = ((j & 1) ? c_hash_basis[2 * bb] : 0u) ^ ((j & 2) ? c_hash_basis[2 * bb + 1] : 0u);
+  }
+
+  // this block's contiguous share of the task list
+  uint32_t const t_begin = (uint32_t)(((unsigned long long)n_active * blockIdx.x) / gridDim.x);
+  uint32_t const t_end = (uint32_t)(((unsigned long long)n_active * (blockIdx.x + 1)) / gridDim.x);
+  auto region_of = [&](uint32_t t) { return (uint32_t)P.batch.region[P.batch.unit_record[P.active_tasks[t] >> 1]]; };
+
+  for (uint32_t seg = t_begin; seg < t_end;)
+  {
+    // ---- segment = the run of tasks of one region starting at seg (tasks are grouped by region, in batch order)
+    uint32_t const slot = region_of(seg);
+    __syncthreads(); // every warp is done with the previous segment (filter, s_seg_end)
+    if (threadIdx.x == 0)
+      s_seg_end = t_end;
+    __syncthreads();
+    for (uint32_t t = seg + 1 + threadIdx.x; t < t_end; t += blockDim.x)
     {
-      slow = true; // IUPAC / N in a seed: key expansion runs in the slow kernel
-      break;
+      bool const differs = region_of(t) != slot;
+      if (differs)
+        atomicMin(&s_seg_end, t);
+      if (__any_sync(__activemask(), differs))
+        break; // later strides only find later positions
     }
-    uint64_t const val = (uint64_t)(__ffs((int)c) - 1) << (2 * (31 - lane));
-    uint32_t const lo = __reduce_or_sync(FULL, (uint32_t)val);
-    uint32_t const hi = __reduce_or_sync(FULL, (uint32_t)(val >> 32));
-    uint64_t const key = (uint64_t)lo | ((uint64_t)hi << 32);
-    // exact key (lane 0 probes) + the 96 Hamming-1 neighbours in key order bb*3 + j (type_conversions.cpp:272-288)
-    int before = nrefs;
+    const DevRegion & R = P.regions[slot];
+    int const log2cap = 64 - R.table_shift;
+    int const fold = log2cap + 2 - (int)FILTER_LOG2_BITS; // log2 of (bitmap bits / filter bits); <= 0: bitmap fits as it is
+    bool const use_filter = fold <= FILTER_MAX_FOLD;
+    if (use_filter)
     {
-      uint32_t off = 0, cnt = 0;
-      bool f = false;
-      if (lane == 0)
-        f = probe(R, key, off, cnt);
-      f = __shfl_sync(FULL, (int)f, 0) != 0;
-      if (f)
+      if (fold <= 0)
       {
-        if (nrefs < SEED_INLINE)
-        {
-          if (lane == 0)
-            refs[nrefs] = make_uint2(off, cnt);
-        }
-        else
-          slow = true;
-        ++nrefs;
+        uint32_t const words = 1u << (log2cap + 2 - 5);
+        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x)
+          s_filter[w] = __ldg(R.bitmap + w);
       }
+      else if (fold == 1)
+        for (uint32_t w = threadIdx.x; w < FILTER_WORDS; w += blockDim.x)
+        {
+          uint2 const v = __ldg(reinterpret_cast<const uint2 *>(R.bitmap) + w);
+          s_filter[w] = or_fold2(v.x) | (or_fold2(v.y) << 16);
+        }
+      else
+        for (uint32_t w = threadIdx.x; w < FILTER_WORDS; w += blockDim.x)
+        {
+          uint4 const v = __ldg(reinterpret_cast<const uint4 *>(R.bitmap) + w);
+          uint32_t const a = or_fold2(v.x) | (or_fold2(v.y) << 16), b2 = or_fold2(v.z) | (or_fold2(v.w) << 16);
+          s_filter[w] = or_fold2(a) | (or_fold2(b2) << 16);
+        }
     }
-    uint32_t const c0 = (uint32_t)(nrefs - before);
-    before = nrefs;
+    __syncthreads();
+    uint32_t const seg_end = s_seg_end;
+    int const bshift = R.table_shift - 34 + (use_filter && fold > 0 ? fold : 0); // hash -> presence bit index
+    int const tshift = R.table_shift - 32;                                        // hash -> table slot
+    const uint4 * const table = reinterpret_cast<const uint4 *>(R.table);
+    const uint32_t * const bitmap = R.bitmap;
+
+    // per-warp software pipeline over its tasks: the task id / record / length of the NEXT task are requested while the
+    // current one is processed (a dependent chain of three global loads otherwise opens every task)
+    uint32_t t = seg + wib;
+    uint32_t nx_task = t < seg_end ? P.active_tasks[t] : 0u;
+    int nx_rec = t < seg_end ? P.batch.unit_record[nx_task >> 1] : 0;
+    int nx_L = t < seg_end ? P.batch.lseq[nx_rec] : 0;
+    for (; t < seg_end; t += PROBE_BLOCK_WARPS)
     {
+      uint32_t const task = nx_task;
+      int const orient = task & 1;
+      int const rec = nx_rec;
+      uint32_t const t_next = t + PROBE_BLOCK_WARPS;
+      if (t_next < seg_end)
+        nx_task = P.active_tasks[t_next];
+      int const L = nx_L;
+      int const nslots = 1 + (L - 32) / 31; // get_num_kmers (kmer_help_functions.cpp:10-17)
+      // this lane's base of every seed slot, straight from the 4-bit BAM bytes (slot i covers read[31 i .. 31 i + 31])
+      uint32_t code[MAX_SLOTS];
+      {
+        const uint8_t * s4 = P.batch.seq4 + (size_t)rec * GTB_SEQ_STRIDE;
+#pragma unroll
+        for (int i = 0; i < MAX_SLOTS; ++i)
+        {
+          code[i] = 1;
+          if (i < nslots)
+          {
+            int const pos = 31 * i + lane;
+            int const src = orient ? (L - 1 - pos) : pos;
+            uint32_t const byte = __ldg(s4 + (src >> 1));
+            uint32_t c = (src & 1) ? (byte & 15u) : (byte >> 4);
+            if (orient)
+              c = comp4((uint8_t)c);
+            code[i] = c;
+          }
+        }
+      }
+      if (t_next < seg_end)
+        nx_rec = P.batch.unit_record[nx_task >> 1];
+
+      // ---- phase 1, all slots: key, key hash, presence bits of the 96 neighbours, candidate list (slot-major, key order)
+      int n_ok = 0;       // slots with pure ACGT seeds, processed here
+      bool slow = false;  // IUPAC / N in a seed: key expansion runs in the slow kernel
+      int nc[MAX_SLOTS], cstart[MAX_SLOTS];
+      int total_c = 0;
+#pragma unroll
+      for (int i = 0; i < MAX_SLOTS; ++i)
+      {
+        nc[i] = 0;
+        cstart[i] = total_c;
+        if (i >= nslots || slow)
+          continue;
+        uint32_t const c = code[i];
+        if (!__all_sync(FULL, __popc(c) == 1))
+        {
+          slow = true;
+          continue;
+        }
+        n_ok = i + 1;
+        uint32_t const v = (uint32_t)__ffs((int)c) - 1u; // A0 C1 G2 T3
+        uint32_t const kh = __reduce_xor_sync(FULL, v == 0 ? 0u : v == 1 ? hb[1] : v == 2 ? hb[2] : hb[3]);
+        uint32_t nb[3], nw[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+        {
+          nb[q] = (kh ^ hm[q]) >> bshift;
+          nw[q] = use_filter ? s_filter[nb[q] >> 5] : __ldg(bitmap + (nb[q] >> 5));
+        }
+        uint64_t const val = (uint64_t)v << (2 * (31 - lane));
+        uint32_t const lo = __reduce_or_sync(FULL, (uint32_t)val);
+        uint32_t const hi = __reduce_or_sync(FULL, (uint32_t)(val >> 32));
+        bool const f0 = (nw[0] >> (nb[0] & 31u)) & 1u, f1 = (nw[1] >> (nb[1] & 31u)) & 1u, f2 = (nw[2] >> (nb[2] & 31u)) & 1u;
+        uint32_t const m0 = __ballot_sync(FULL, f0), m1 = __ballot_sync(FULL, f1), m2 = __ballot_sync(FULL, f2);
+        int const n0 = __popc(m0), n1 = __popc(m1), n2 = __popc(m2);
+        nc[i] = 1 + n0 + n1 + n2; // candidate 0 = the exact key
+        uint16_t * cl = cand + total_c;
+        uint16_t const tag = (uint16_t)(i << 8);
+        if (lane == 0)
+        {
+          cl[0] = tag;
+          s_key[wib][i] = make_uint2(lo, hi);
+          s_kh[wib][i] = kh;
+        }
+        if (f0)
+          cl[1 + __popc(m0 & lt)] = (uint16_t)(tag | (1 + lane));
+        if (f1)
+          cl[1 + n0 + __popc(m1 & lt)] = (uint16_t)(tag | (33 + lane));
+        if (f2)
+          cl[1 + n0 + n1 + __popc(m2 & lt)] = (uint16_t)(tag | (65 + lane));
+        total_c += nc[i];
+      }
+      __syncwarp();
+
+      // ---- phase 2 + 3: walk the table for the candidates, then settle the slots in order
+      // resolve(g): candidate g of the task's list
+      auto resolve = [&](int g, bool & found, uint32_t & off, uint32_t & cnt) {
+        uint32_t const e = cand[g];
+        uint32_t const i = e >> 8, kc = e & 255u;
+        uint2 const kk = s_key[wib][i];
+        uint64_t ck = (uint64_t)kk.x | ((uint64_t)kk.y << 32);
+        uint32_t ch = s_kh[wib][i];
+        if (kc)
+        {
+          uint32_t const k = kc - 1u;
+          uint32_t const bb = (k * 171u) >> 9; // k / 3 for k < 96
+          ck ^= (uint64_t)(k - 3u * bb + 1u) << (2u * bb);
+          ch ^= s_hm[k];
+        }
+        uint32_t h = ch >> tshift;
+        uint4 sl = __ldg(table + h);
+        while (sl.w != 0) // linear probing; count == 0 marks an empty slot
+        {
+          if (((uint64_t)sl.x | ((uint64_t)sl.y << 32)) == ck)
+          {
+            found = true;
+            off = sl.z;
+            cnt = sl.w;
+            break;
+          }
+          h = (h + 1) & R.table_mask;
+          sl = __ldg(table + h);
+        }
+      };
+      int nrefs = 0;
+      uint32_t cnts = 0, cnts_hi = 0; // 8 x 8-bit list counts
+      // per-slot state while its neighbour hits are absorbed round by round
       uint32_t total = 0;
       bool dropped = false;
-      // memory-level parallelism: the first table slot of all three neighbour keys of this lane is requested
-      // before any of them is examined
-      // A presence bitmap (1 bit per 1/4 table slot, ~3 % occupied, small enough to live in L1/L2) answers the
-      // usual case -- neighbour absent -- with one 4-byte load and no probe loop; the table is only walked for the
-      // few keys whose bit is set.  All three bitmap words of a lane are requested before any is examined.
-      uint64_t nk[3];
-      uint64_t nhs[3];
-      uint32_t nw[3];
-#pragma unroll
-      for (int q = 0; q < 3; ++q)
-      {
-        nk[q] = key ^ nmask[q];
-        nhs[q] = nk[q] * 0x9E3779B97F4A7C15ull;
-      }
-#pragma unroll
-      for (int q = 0; q < 3; ++q)
-        nw[q] = __ldg(R.bitmap + (uint32_t)(nhs[q] >> (R.table_shift - 2 + 5)));
-#pragma unroll
-      for (int q = 0; q < 3; ++q)
-      {
-        uint32_t off = 0, cnt = 0;
-        bool found = false;
-        if ((nw[q] >> ((uint32_t)(nhs[q] >> (R.table_shift - 2)) & 31u)) & 1u)
-          found = probe(R, nk[q], off, cnt);
-        unsigned const fm = __ballot_sync(FULL, found);
+      auto absorb = [&](bool hit, uint32_t off, uint32_t cnt) { // hit: this lane holds a found NEIGHBOUR of the current slot
+        unsigned const fm = __ballot_sync(FULL, hit);
         if (fm == 0 || dropped)
-          continue;
-        uint32_t inc = found ? cnt : 0u;
+          return;
+        uint32_t inc = hit ? cnt : 0u;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1)
         {
@@ -1684,42 +1845,111 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(LaunchParams P)
           if (lane >= d)
             inc += tt;
         }
-        if (__any_sync(FULL, found && (total + inc) > 75u)) // PHIndex::multi_get give-up rule (ph_index.cpp:84-89)
+        if (__any_sync(FULL, hit && (total + inc) > 75u)) // PHIndex::multi_get give-up rule (ph_index.cpp:84-89)
         {
           dropped = true;
-          continue;
+          return;
         }
-        int const pos = nrefs + __popc(fm & ((1u << lane) - 1u));
-        if (found)
-        {
-          if (pos < SEED_INLINE)
-            refs[pos] = make_uint2(off, cnt);
-        }
+        int const pos = nrefs + __popc(fm & lt);
+        if (hit && pos < SEED_INLINE)
+          refs[pos] = make_uint2(off, cnt);
         nrefs += __popc(fm);
         total += __shfl_sync(FULL, inc, 31);
+      };
+      auto exact_hit = [&](uint32_t off, uint32_t cnt, int src_lane, uint32_t & c0) { // exact-match list: 1 key, never dropped
+        if (nrefs < SEED_INLINE)
+        {
+          if (lane == src_lane)
+            refs[nrefs] = make_uint2(off, cnt);
+        }
+        else
+          slow = true;
+        ++nrefs;
+        c0 = 1;
+      };
+      auto close_slot = [&](int i, uint32_t c0, int before) {
+        if (dropped)
+          nrefs = before;
+        if (nrefs > SEED_INLINE)
+          slow = true;
+        uint32_t const c1 = (uint32_t)(nrefs - before);
+        if (i < 2)
+          cnts |= (c0 << (16 * i)) | (c1 << (16 * i + 8));
+        else
+          cnts_hi |= (c0 << (16 * (i - 2))) | (c1 << (16 * (i - 2) + 8));
+      };
+
+      if (total_c <= 32)
+      {
+        // the usual case: every candidate of every slot in ONE round of table walks (one memory latency per task, not per slot)
+        bool found = false;
+        uint32_t off = 0, cnt = 0;
+        if (lane < total_c)
+          resolve(lane, found, off, cnt);
+#pragma unroll
+        for (int i = 0; i < MAX_SLOTS; ++i)
+        {
+          if (i >= n_ok || slow)
+            continue;
+          int const a = cstart[i];
+          uint32_t c0 = 0;
+          if (__shfl_sync(FULL, (int)found, a))
+            exact_hit(off, cnt, a, c0);
+          int const before = nrefs;
+          total = 0;
+          dropped = false;
+          absorb(found && lane > a && lane < a + nc[i], off, cnt);
+          close_slot(i, c0, before);
+        }
       }
-      if (dropped)
-        nrefs = before;
-      if (nrefs > SEED_INLINE)
-        slow = true;
+      else
+      {
+#pragma unroll
+        for (int i = 0; i < MAX_SLOTS; ++i)
+        {
+          if (i >= n_ok || slow)
+            continue;
+          uint32_t c0 = 0;
+          int before = nrefs;
+          total = 0;
+          dropped = false;
+          for (int base = 0; base < nc[i]; base += 32)
+          {
+            int const ci = base + lane;
+            bool found = false;
+            uint32_t off = 0, cnt = 0;
+            if (ci < nc[i])
+              resolve(cstart[i] + ci, found, off, cnt);
+            if (base == 0)
+            {
+              if (__shfl_sync(FULL, (int)found, 0))
+                exact_hit(off, cnt, 0, c0);
+              before = nrefs;
+              if (lane == 0)
+                found = false;
+            }
+            absorb(found, off, cnt);
+          }
+          close_slot(i, c0, before);
+        }
+      }
+      if (t_next < seg_end)
+        nx_L = P.batch.lseq[nx_rec];
+      __syncwarp();
+      SeedRec * out = reinterpret_cast<SeedRec *>(P.seed_recs) + t;
+      if (lane == 0)
+      {
+        uint32_t * w = reinterpret_cast<uint32_t *>(out);
+        w[0] = cnts;
+        w[1] = cnts_hi;
+        w[2] = (uint32_t)nslots | ((slow ? 1u : 0u) << 8);
+      }
+      if (!slow && lane < nrefs)
+        out->refs[lane] = refs[lane];
+      __syncwarp();
     }
-    uint32_t const c1 = (uint32_t)(nrefs - before);
-    if (i < 2)
-      cnts |= (c0 << (16 * i)) | (c1 << (16 * i + 8));
-    else
-      cnts_hi |= (c0 << (16 * (i - 2))) | (c1 << (16 * (i - 2) + 8));
+    seg = seg_end;
   }
-  __syncwarp();
-  SeedRec * out = reinterpret_cast<SeedRec *>(P.seed_recs) + t;
-  if (lane == 0)
-  {
-    uint32_t * w = reinterpret_cast<uint32_t *>(out);
-    w[0] = cnts;
-    w[1] = cnts_hi;
-    w[2] = (uint32_t)nslots | ((slow ? 1u : 0u) << 8);
-  }
-  if (!slow && lane < nrefs)
-    out->refs[lane] = refs[lane];
 }
 
 // ================================================================================================ chain kernel
@@ -2190,17 +2420,23 @@ __device__ bool push_scores(const LaunchParams & P, const DevRegion & R, const G
       allele_mask_t const mask = (allele_mask_t)w[2 * k + 1];
       if (mask == 0)
         continue;
-      // id2hap (vcf_writer.cpp:84): bubble index of this var order
-      int lo = 0, hi = (int)R.n_bubbles;
-      while (lo < hi)
+      // id2hap (vcf_writer.cpp:84): bubble index of this var order -- direct table, binary search as the fallback
+      uint32_t hap = 0xFFFFu;
+      if (R.hap_of_order && order - R.hap_base < R.hap_span)
+        hap = R.hap_of_order[order - R.hap_base];
+      if (hap == 0xFFFFu)
       {
-        int const mid = (lo + hi) >> 1;
-        if (R.bubble_order[mid] <= order)
-          lo = mid + 1;
-        else
-          hi = mid;
+        int lo = 0, hi = (int)R.n_bubbles;
+        while (lo < hi)
+        {
+          int const mid = (lo + hi) >> 1;
+          if (R.bubble_order[mid] <= order)
+            lo = mid + 1;
+          else
+            hi = mid;
+        }
+        hap = (uint32_t)(lo - 1);
       }
-      uint32_t const hap = (uint32_t)(lo - 1);
       int t = -1;
       for (int q = 0; q < nt; ++q)
         if (t_hap[q] == hap)
@@ -2514,6 +2750,7 @@ __global__ void __launch_bounds__(128) score_kernel(LaunchParams P)
   uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.batch.n_records)
     return;
+  if (P.defer)
   {
     // anything this record needs still queued for the slower tiers?  (own alignment unit, and the mate's)
     int const u = P.batch.unit[i];
@@ -2754,10 +2991,10 @@ __global__ void __launch_bounds__(256) build_table_kernel(const IndexSlot * uniq
     return;
   IndexSlot const u = uniq[i];
   unsigned long long const val = (unsigned long long)u.off | ((unsigned long long)u.cnt << 32);
-  uint64_t const hs = u.key * 0x9E3779B97F4A7C15ull;
-  uint32_t const bi = (uint32_t)(hs >> (shift - 2)); // presence bitmap: 4 bits per table slot
+  uint32_t const hs = hash32_tab(g_hash_tab, u.key);
+  uint32_t const bi = hs >> (shift - 34); // presence bitmap: 4 bits per table slot
   atomicOr(&bitmap[bi >> 5], 1u << (bi & 31u));
-  uint32_t h = (uint32_t)(hs >> shift);
+  uint32_t h = hs >> (shift - 32);
   while (true)
   {
     unsigned long long * w = reinterpret_cast<unsigned long long *>(&table[h]) + 1;
@@ -2817,8 +3054,17 @@ void launch_probe(const LaunchParams & p, void * stream)
 {
   if (p.n_active == 0)
     return;
-  uint32_t const grid = (p.n_active + PROBE_WARPS - 1) / PROBE_WARPS;
-  probe_kernel<<<grid, PROBE_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  // one persistent block per SM (p.n_active is an upper bound; the exact count is read on the device); small batches
+  // get fewer blocks so that a block still has a few hundred tasks to amortise staging its region's filter
+  static bool attr_set = false;
+  if (!attr_set)
+  {
+    cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_WORDS * 4));
+    attr_set = true;
+  }
+  uint32_t const want = (p.n_active + 255) / 256;
+  uint32_t const grid = std::max(1u, std::min(want, (uint32_t)sm_count()));
+  probe_kernel<<<grid, PROBE_BLOCK_WARPS * 32, FILTER_WORDS * 4, (cudaStream_t)stream>>>(p);
 }
 
 void launch_chain(const LaunchParams & p, void * stream)
