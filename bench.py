@@ -41,9 +41,9 @@ LENGTH = 1_000_000
 N_SITES = 10_000
 REGION = 50_000
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE probe_kernel launch on this workload, from the committed ncu capture
-# profiles/r1_final_ncu_summary.txt (192.2 MB + 13.0 MB; cold L2).  Well below the algorithmic 1.29 GB: the tables are L2-resident.
-PROBE_DRAM_BYTES_PER_LAUNCH = 150_882_048  # ncu dram__bytes_read.sum + dram__bytes_write.sum of one probe_kernel launch (profiles/r1b_ncu_summary.txt)
-
+# profiles/r1c_ncu_summary.txt (223.9 MB + 13.2 MB; cold L2).  Well below the algorithmic 1.29 GB: "absent" -- the fate of 95+
+# of the 96 Hamming-1 neighbours of a seed -- is answered from the presence filter in shared memory, and the tables are L2-resident.
+PROBE_DRAM_BYTES_PER_LAUNCH = 237_096_704
 
 def env_int(name: str, default: int) -> int:
     try:
@@ -229,7 +229,9 @@ def main() -> None:
     metric = "reads/sec genotyped (150bp, 1Mb/10k-var graph)"
     config = {"workload": "configs[1]: 1 Mb synthetic region, 10k SNP/indel graph, 1 sample 30x 150 bp reads "
                           "(2e5 records, 20 x 50 kb regions, region-batched)",
-              "reads_per_gpu": None, "regions": LENGTH // REGION, "l2": "flushed between timed iterations (256 MiB write)"}
+              "reads_per_gpu": None, "regions": LENGTH // REGION, "l2": "flushed between timed iterations (256 MiB write)",
+              "value_path": "device-resident replay, one launch sequence (prep, probe, chain, slow, huge, score)",
+              "e2e_path": "gtb_pool_reset_multi + gtb_submit_reads_multi (4 concurrent chunks) + gtb_pool_finish_multi, pinned host buffers"}
 
     if args.impl == "reference":
         if rank != 0:

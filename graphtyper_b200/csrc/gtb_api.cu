@@ -1222,6 +1222,7 @@ static int launch_front(Ctx * c, BatchState & B, cudaEvent_t after)
   CUDA_TRY(cudaEventRecord(B.ev[6], s));
   launch_probe(P, s);
   CUDA_TRY(cudaEventRecord(B.ev[3], s));
+  launch_chain_order(P, s);
   launch_chain(P, s);
   CUDA_TRY(cudaEventRecord(B.ev[4], s));
   // Several chunks: a first score pass right away for every record whose tasks chain_kernel finished (all but a few dozen
@@ -1336,7 +1337,8 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     st.n_pairs_scored += kc->n_pairs_scored;
     st.n_singles_scored += kc->n_singles_scored;
     st.n_capacity_overflow += kc->n_overflow;
-    st.kernel_launches += B.P.batch.n_records ? 5 + (c->n_chunks_last > 1 ? 1 : 0) : 0; // prep_flags, scan, prep_fill, probe, chain (+ first score pass)
+    // prep_flags, scan, prep_fill, probe, chain (+ the two task-order kernels) (+ first score pass)
+    st.kernel_launches += B.P.batch.n_records ? 5 + (B.P.chain_order ? 2 : 0) + (c->n_chunks_last > 1 ? 1 : 0) : 0;
     n_overflow += kc->n_overflow;
     n_input_error += kc->n_input_error;
     for (int q = 0; q < 12; ++q)
@@ -1528,7 +1530,11 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   uint32_t const n_tasks = n_units * 2;
   if (int rc = B.d_seedrecs.reserve((size_t)n_active * SEED_REC_BYTES + 64))
     return rc;
-  if (int rc = B.d_slow.reserve((size_t)n_active * 8 + 128 + total * 4))
+  // Heavy-first, class-by-class task order for chain_kernel (chain_order_kernels): measured on the bench workload and NOT a
+  // win (0.352 -> 0.373 ms incl. the two ordering kernels: warp time is dominated by memory latency of each thread's own
+  // dependent chain, not by divergence between label-count classes), so it is opt-in (GTB_CHAIN_SORT=1) for experiments.
+  static bool const chain_sort = []() { const char * e = getenv("GTB_CHAIN_SORT"); return e ? atoi(e) != 0 : false; }();
+  if (int rc = B.d_slow.reserve((size_t)n_active * 8 + 128 + total * 4 + (chain_sort ? (size_t)n_active * 5 + 64 : 0)))
     return rc;
   if (int rc = B.d_summaries.reserve((size_t)n_tasks * (sizeof(TaskSummary) + 1) + 16))
     return rc;
@@ -1610,6 +1616,11 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   P.slow_tasks = static_cast<uint32_t *>(B.d_slow.p);
   P.huge_tasks = P.slow_tasks + n_active + 16;
   P.deferred = P.huge_tasks + n_active + 16;
+  if (chain_sort && !with_tap) // (the debug taps address seed records by task position; keep the natural order there)
+  {
+    P.chain_order = P.deferred + total;
+    P.chain_bin = reinterpret_cast<uint8_t *>(P.chain_order + n_active + 8);
+  }
   P.pending = reinterpret_cast<uint8_t *>(P.summaries + n_tasks);
   P.huge_states = c->d_huge.p;
   if (with_tap)

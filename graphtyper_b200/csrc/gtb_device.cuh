@@ -209,6 +209,8 @@ struct DevCounters
   // written by the batch-preparation kernels (prep_*): alignment units and aligned read orientations of this chunk, and
   // what is wrong with the input (PREP_ERR_* bits)
   uint32_t n_units, n_active, input_bits, n_deferred;
+  // cost classes of the chain_kernel tasks (probe_kernel counts, chain_order_kernels turn them into a heavy-first task order)
+  uint32_t chain_bins[16], chain_cursor[16];
 };
 constexpr uint32_t PREP_ERR_SAMPLE = 1, PREP_ERR_DUP = 2, PREP_ERR_MATE = 4, PREP_ERR_LEN = 8;
 
@@ -269,6 +271,8 @@ struct LaunchParams
   uint8_t * pending;            // [n_units * 2] set by chain_kernel for tasks it hands to slow_kernel; never cleared by the
                                 // slower tiers, so the first score pass can read it while they run
   uint32_t * deferred;          // [n_records] records the first score pass left for the second (some task pending)
+  uint8_t * chain_bin;          // [n_active] cost class of each task (labels handed over by probe_kernel, capped at 15)
+  uint32_t * chain_order;       // [n_active] task positions, heaviest class first; nullptr = natural order
   uint32_t defer;               // 1: score_kernel runs before slow_kernel and defers; 0: it runs after and scores everything
   unsigned long long * task_times; // profiling aid (GTB_TASK_TIMES=file): [n_active][2] globaltimer ns at start / end of
                                    // each chain_kernel task; nullptr normally
@@ -289,6 +293,7 @@ void launch_build_table(const IndexSlot * uniq, uint32_t n, IndexSlot * table, u
                         void * stream);
 void launch_probe(const LaunchParams & p, void * stream);
 void launch_chain(const LaunchParams & p, void * stream);
+void launch_chain_order(const LaunchParams & p, void * stream); // fills p.chain_order from p.chain_bin / counters->chain_bins
 void launch_slow(const MultiLaunch & m, void * stream);
 // first pass: every record of one chunk whose tasks are all computed by chain_kernel; records with a task still queued for
 // slow_kernel are listed in p.deferred.  Second pass (after slow_kernel / huge_kernel): the deferred records of all chunks.

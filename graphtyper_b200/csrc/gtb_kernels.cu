@@ -1623,9 +1623,12 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
   __shared__ uint2 s_refs[PROBE_BLOCK_WARPS][SEED_INLINE];
   __shared__ uint32_t s_hm[96];                        // hashes of the 96 neighbour masks
   __shared__ uint32_t s_seg_end;
+  __shared__ uint32_t s_bins[16];                            // cost classes of this block's tasks (see chain_order_kernels)
   int const lane = threadIdx.x & 31;
   int const wib = threadIdx.x >> 5;
   uint32_t const lt = (1u << lane) - 1u;
+  if (threadIdx.x < 16)
+    s_bins[threadIdx.x] = 0;
   uint16_t * cand = s_cand[wib];
   uint2 * refs = s_refs[wib];
   uint32_t const n_active = P.counters->n_active;
@@ -1946,10 +1949,66 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
       }
       if (!slow && lane < nrefs)
         out->refs[lane] = refs[lane];
+      if (P.chain_bin)
+      {
+        // cost class for chain_kernel's task order: labels handed over (tasks for slow_kernel cost chain_kernel nothing)
+        uint32_t const labels = __reduce_add_sync(FULL, (!slow && lane < nrefs) ? refs[lane].y : 0u);
+        if (lane == 0)
+        {
+          uint32_t const bin = slow ? 0u : min(labels, 15u);
+          P.chain_bin[t] = (uint8_t)bin;
+          atomicAdd(&s_bins[bin], 1u);
+        }
+      }
       __syncwarp();
     }
     seg = seg_end;
   }
+  __syncthreads();
+  if (P.chain_bin && threadIdx.x < 16 && s_bins[threadIdx.x])
+    atomicAdd(&P.counters->chain_bins[threadIdx.x], s_bins[threadIdx.x]);
+}
+
+// ================================================================================================ chain task order
+// chain_kernel runs one THREAD per task, and a warp takes as long as the union of its threads' control paths.  Tasks are
+// therefore issued heaviest cost class first and class by class: warps are (nearly) homogeneous, and the long tasks start
+// at once instead of at the end of the grid.  Counting sort: histogram (probe_kernel) -> bases -> scatter.
+__global__ void chain_order_bases_kernel(DevCounters * c)
+{
+  if (threadIdx.x == 0)
+  {
+    uint32_t base = 0;
+    for (int b = 15; b >= 0; --b)
+    {
+      c->chain_cursor[b] = base;
+      base += c->chain_bins[b];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) chain_order_scatter_kernel(LaunchParams P)
+{
+  uint32_t const t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool const valid = t < P.counters->n_active;
+  uint32_t const bin = valid ? P.chain_bin[t] : 16u;
+  unsigned const peers = __match_any_sync(FULL, bin);
+  if (!valid)
+    return;
+  int const lane = threadIdx.x & 31;
+  int const leader = __ffs((int)peers) - 1;
+  uint32_t base = 0;
+  if (lane == leader)
+    base = atomicAdd(&P.counters->chain_cursor[bin], (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  P.chain_order[base + __popc(peers & ((1u << lane) - 1u))] = t;
+}
+
+void launch_chain_order(const LaunchParams & p, void * stream)
+{
+  if (p.n_active == 0 || !p.chain_order)
+    return;
+  chain_order_bases_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p.counters);
+  chain_order_scatter_kernel<<<(p.n_active + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
 }
 
 // ================================================================================================ chain kernel
@@ -1957,9 +2016,10 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
 // small capacity, or that probe_kernel marked, are queued for slow_kernel.
 __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(LaunchParams P)
 {
-  uint32_t const t = blockIdx.x * CHAIN_THREADS + threadIdx.x;
-  if (t >= P.counters->n_active)
+  uint32_t const gt = blockIdx.x * CHAIN_THREADS + threadIdx.x;
+  if (gt >= P.counters->n_active)
     return;
+  uint32_t const t = P.chain_order ? P.chain_order[gt] : gt; // heaviest cost class first (chain_order_kernels)
   uint32_t const task = P.active_tasks[t];
   const SeedRec * recp = reinterpret_cast<const SeedRec *>(P.seed_recs) + t;
   uint32_t const w2 = reinterpret_cast<const uint32_t *>(recp)[2];
@@ -1982,7 +2042,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(
       if (p)
         p[1] = now();
     }
-  } timer(P.task_times ? P.task_times + 2 * (size_t)t : nullptr);
+  } timer(P.task_times ? P.task_times + 2 * (size_t)gt : nullptr);
   if ((w2 >> 8) & 1u)
   {
     atomicAdd(&P.counters->fast_reasons[11], 1ull); // marked by probe_kernel (IUPAC/N seed or > SEED_INLINE references)
