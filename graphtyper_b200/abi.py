@@ -113,6 +113,56 @@ def phase_support(lib, fn_name: str, acc, conn: np.ndarray) -> np.ndarray:
     return out
 
 
+class BamCore(C.Structure):
+    _fields_ = [("pos", C.c_int64), ("mpos", C.c_int64), ("isize", C.c_int64), ("tid", C.c_int32), ("mtid", C.c_int32),
+                ("l_qseq", C.c_int32), ("n_cigar", C.c_uint32), ("flag", C.c_uint16), ("l_qname", C.c_uint16),
+                ("mapq", C.c_uint8), ("reserved", C.c_uint8 * 3)]
+
+
+BAM_CORE_DTYPE = np.dtype([("pos", np.int64), ("mpos", np.int64), ("isize", np.int64), ("tid", np.int32), ("mtid", np.int32),
+                           ("l_qseq", np.int32), ("n_cigar", np.uint32), ("flag", np.uint16), ("l_qname", np.uint16),
+                           ("mapq", np.uint8), ("reserved", np.uint8, (3,))])
+assert BAM_CORE_DTYPE.itemsize == C.sizeof(BamCore) == 48
+
+
+class BamBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("reserved", C.c_uint32), ("core", C.c_void_p), ("data", u8p), ("data_off", u64p),
+                ("sample", i32p), ("rg", i32p)]
+
+
+class HostBamBatch:
+    """Owns the arrays behind a BamBatch: records as htslib holds them (core fields + bam1_t::data)."""
+
+    def __init__(self, core: np.ndarray, data: np.ndarray, data_off: np.ndarray, sample: np.ndarray, rg: np.ndarray):
+        self.core = np.ascontiguousarray(core, dtype=BAM_CORE_DTYPE)
+        self.data = np.ascontiguousarray(data, dtype=np.uint8)
+        self.data_off = np.ascontiguousarray(data_off, dtype=np.uint64)
+        self.sample = np.ascontiguousarray(sample, dtype=np.int32)
+        self.rg = np.ascontiguousarray(rg, dtype=np.int32)
+        v = BamBatch()
+        v.n_reads = len(self.core)
+        v.core = self.core.ctypes.data
+        v.data = _ptr(self.data, u8p)
+        v.data_off = _ptr(self.data_off, u64p)
+        v.sample = _ptr(self.sample, i32p)
+        v.rg = _ptr(self.rg, i32p)
+        self.view = v
+
+    def __len__(self) -> int:
+        return len(self.core)
+
+    @classmethod
+    def from_probe(cls, d: Dict[str, np.ndarray]) -> "HostBamBatch":
+        """From the records dumped by oracle/_ref/bin/gt_probe (<out>.reads.gtba: bam_data / bam_off + core columns)."""
+        n = len(d["flag"])
+        core = np.zeros(n, BAM_CORE_DTYPE)
+        core["pos"], core["mpos"], core["isize"] = d["pos"], d["mpos"], d["isize"]
+        core["tid"], core["mtid"], core["l_qseq"] = d["tid"], d["mtid"], d["lseq"]
+        core["n_cigar"] = np.diff(d["cigar_off"].astype(np.int64))
+        core["flag"], core["l_qname"], core["mapq"] = d["flag"], d["bam_lqname"], d["mapq"]
+        return cls(core, d["bam_data"], d["bam_off"], d["sample"], d["rg"])
+
+
 def _ptr(a: Optional[np.ndarray], typ):
     if a is None:
         return C.cast(None, typ)

@@ -248,6 +248,41 @@ int gtb_scan_calls(const gtb_accumulators *acc, const uint8_t *phred, uint64_t *
 int gtb_merge_varstats(uint32_t n_bubbles, uint64_t n_alleles_total, uint64_t *var, uint64_t *allele, double *ratio,
                        const uint64_t *var_src, const uint64_t *allele_src, const double *ratio_src);
 
+/* Record-parsing entry (SURVEY.md section 8f, N3 -- first step: everything genotype_only's caller derives per record moves
+ * to the device; BGZF inflate and the k-way merge stay in htslib).  The shim hands over the records of one pool in merge
+ * order (after the flag filter, hts_parallel_reader.cpp:655-663, and for SV graphs is_good_read, :528-568) as htslib holds
+ * them: the core fields below (bam1_core_t, htslib/sam.h) + bam1_t::data (qname | cigar | seq | qual | aux), concatenated.
+ * On the device: 4-bit bases, lengths, flags, MAPQ, insert size, AS-XS exactly as get_score_diff walks the aux block
+ * (src/typer/alignment.cpp:140-325), the duplicate shortcut equal_pos_seq (include/graphtyper/utilities/hts_utils.hpp:110-128,
+ * hts_parallel_reader.cpp:666-684), mate pairing with the read-name map semantics of genotype_only (:270-337: a record whose
+ * name waits in its read group's map pairs with it -- paired flag or not --, otherwise a paired record waits, an unpaired one
+ * is scored alone) by sorting 64-bit (read group, name) hashes and verifying the names, and for SV graphs the leftover mates
+ * (:719-772).  Then the same kernels as gtb_submit_reads.  All records of a pool must come in ONE call (mates pair within it). */
+typedef struct gtb_bam_core {
+  int64_t pos, mpos, isize;   /* core.pos, core.mpos, core.isize */
+  int32_t tid, mtid;
+  int32_t l_qseq;
+  uint32_t n_cigar;
+  uint16_t flag;
+  uint16_t l_qname;           /* core.l_qname: includes the NUL terminator and htslib's padding NULs */
+  uint8_t mapq;               /* core.qual */
+  uint8_t reserved[3];
+} gtb_bam_core;
+typedef struct gtb_bam_batch {
+  uint32_t n_reads;
+  uint32_t reserved;
+  const gtb_bam_core *core;   /* [n_reads] */
+  const uint8_t *data;        /* bam1_t::data of every record, back to back */
+  const uint64_t *data_off;   /* [n_reads + 1] */
+  const int32_t *sample;      /* [n_reads] sample index within the pool (HtsParallelReader::get_sample_and_rg_index) */
+  const int32_t *rg;          /* [n_reads] read-group index: one read-name map per read group */
+} gtb_bam_batch;
+int gtb_submit_bam_records(gtb_ctx *ctx, int region_id, const gtb_bam_batch *batch, gtb_submit_stats *stats);
+/* Debug/parity tap: the per-record columns the device derived in the last gtb_submit_bam_records call (any pointer may be NULL). */
+int gtb_debug_bam_columns(gtb_ctx *ctx, uint32_t n_reads, uint8_t *seq4 /*[n*GTB_SEQ_STRIDE]*/, uint16_t *lseq, uint16_t *flag,
+                          uint8_t *mapq, int32_t *isize, uint8_t *same_tid, uint8_t *score_diff, int32_t *mate, int32_t *dup_of,
+                          uint8_t *leftover);
+
 /* Phasing connections = HapSample::connections (include/graphtyper/graph/haplotype.hpp:42): for every read / read pair that
  * explains alleles of several bubbles, support counts between (bubble hap1, allele1) and a LATER bubble's (hap2, allele2),
  * as VcfWriter::push_to_haplotype_scores builds them (src/typer/vcf_writer.cpp:587-637: weight 6/(n1*n2) inside one read)

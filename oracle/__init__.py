@@ -83,6 +83,8 @@ class Oracle:
         L.gto_result_path_sizes.argtypes = [C.c_void_p, abi.u64p, abi.u64p, abi.u64p, abi.u64p]
         L.gto_result_paths.argtypes = [C.c_void_p, abi.u32p, abi.u32p, abi.u32p, abi.u32p, abi.u32p, abi.u16p]
         L.gto_calls_from_accumulators.argtypes = [C.POINTER(abi.Accumulators), abi.u8p, abi.u16p, abi.u8p]
+        L.gto_parse_bam.argtypes = [C.POINTER(abi.BamBatch), C.c_int, abi.u8p, abi.u16p, abi.u16p, abi.u8p, abi.i32p, abi.u8p,
+                                    abi.u8p, abi.i32p, abi.i32p, abi.u8p]
         L.gto_set_connections.argtypes = [C.c_int]
         L.gto_set_connections.restype = None
         L.gto_result_connections_size.argtypes = [C.c_void_p, abi.u64p]
@@ -158,6 +160,22 @@ class Oracle:
                                   out["p_fields"].ctypes.data_as(a.u32p), out["v_order"].ctypes.data_as(a.u32p),
                                   out["v_nnum"].ctypes.data_as(a.u32p), out["v_nums"].ctypes.data_as(a.u16p))
         return out
+
+    def parse_bam(self, bam, is_sv: bool = False):
+        """Records (abi.HostBamBatch) -> abi.HostBatch with every derived column (score_diff, mate, dup_of, leftover)."""
+        a = self.abi
+        n = len(bam)
+        seq4 = np.zeros((n, a.SEQ_STRIDE), np.uint8)
+        lseq, flag = np.zeros(n, np.uint16), np.zeros(n, np.uint16)
+        mapq, same, sd, left = (np.zeros(n, np.uint8) for _ in range(4))
+        isize, mate, dup = (np.zeros(n, np.int32) for _ in range(3))
+        rc = self.lib.gto_parse_bam(C.byref(bam.view), 1 if is_sv else 0, seq4.ctypes.data_as(a.u8p), lseq.ctypes.data_as(a.u16p),
+                                    flag.ctypes.data_as(a.u16p), mapq.ctypes.data_as(a.u8p), isize.ctypes.data_as(a.i32p),
+                                    same.ctypes.data_as(a.u8p), sd.ctypes.data_as(a.u8p), mate.ctypes.data_as(a.i32p),
+                                    dup.ctypes.data_as(a.i32p), left.ctypes.data_as(a.u8p))
+        if rc:
+            raise RuntimeError(f"oracle parse_bam rc={rc}: {self.lib.gto_last_error().decode()}")
+        return a.HostBatch(seq4, lseq, flag, mapq, isize, same, sd, np.zeros(n, np.uint8), bam.sample, mate, dup, leftover=left)
 
     def set_connections(self, on: bool) -> None:
         """Phasing connections (vcf_writer.cpp:587-637) in the following pool_run calls."""

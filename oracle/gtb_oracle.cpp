@@ -2293,6 +2293,116 @@ int gto_result_paths(void * r, uint32_t * gp_npaths, uint32_t * gp_longest, uint
   return 0;
 }
 
+// ---- record parsing (N3): what genotype_only's caller derives per record, restated on the CPU
+// get_score_diff (src/typer/alignment.cpp:140-325): walk of the aux block; AS / XS of integer type, anything but
+// A Z c C s S i I f ends the walk
+static uint8_t oracle_score_diff(const uint8_t * it, long l_aux)
+{
+  long i = 0;
+  int64_t as = -1, xs = -1;
+  while (i < l_aux)
+  {
+    i += 3;
+    char const type = (char)it[i - 1];
+    bool const s_tag = it[i - 2] == 'S';
+    bool const is_as = s_tag && it[i - 3] == 'A', is_xs = s_tag && it[i - 3] == 'X';
+    int64_t num = 0;
+    bool have = false;
+    switch (type)
+    {
+    case 'A':
+      ++i;
+      break;
+    case 'Z':
+      while (it[i] != '\0' && it[i] != '\n')
+        ++i;
+      ++i;
+      break;
+    case 'c': { int8_t v; memcpy(&v, it + i, 1); num = v; have = true; i += 1; break; }
+    case 'C': { uint8_t v; memcpy(&v, it + i, 1); num = v; have = true; i += 1; break; }
+    case 's': { int16_t v; memcpy(&v, it + i, 2); num = v; have = true; i += 2; break; }
+    case 'S': { uint16_t v; memcpy(&v, it + i, 2); num = v; have = true; i += 2; break; }
+    case 'i': { int32_t v; memcpy(&v, it + i, 4); num = v; have = true; i += 4; break; }
+    case 'I': { uint32_t v; memcpy(&v, it + i, 4); num = v; have = true; i += 4; break; }
+    case 'f':
+      i += 4;
+      break;
+    default:
+      i = l_aux;
+      break;
+    }
+    if (have && is_as)
+      as = num;
+    else if (have && is_xs)
+      xs = num;
+  }
+  if (as == -1 || as < xs)
+    return 0;
+  if (xs == -1)
+    xs = 0;
+  long const diff = (long)(as - xs);
+  return diff < 255 ? (uint8_t)diff : 255;
+}
+
+// Fills the gtb_read_batch columns (caller-allocated, n_reads entries; seq4 zero-initialised with stride GTB_SEQ_STRIDE)
+int gto_parse_bam(const gtb_bam_batch * b, int is_sv, uint8_t * seq4, uint16_t * lseq, uint16_t * flag, uint8_t * mapq,
+                  int32_t * isize, uint8_t * same_tid, uint8_t * score_diff, int32_t * mate, int32_t * dup_of, uint8_t * leftover)
+{
+  uint32_t const n = b->n_reads;
+  std::vector<std::unordered_map<std::string, int32_t>> maps; // one read-name map per read group (hts_parallel_reader.cpp:270-337)
+  int32_t prev = -1;                                          // last record that was not a duplicate (:666-684)
+  for (uint32_t k = 0; k < n; ++k)
+  {
+    gtb_bam_core const & c = b->core[k];
+    const uint8_t * d = b->data + b->data_off[k];
+    long const l_data = (long)(b->data_off[k + 1] - b->data_off[k]);
+    long const o_seq = (long)c.l_qname + 4l * c.n_cigar, n_seq = (c.l_qseq + 1l) / 2l, o_aux = o_seq + n_seq + c.l_qseq;
+    if (c.l_qseq < 0 || c.l_qseq > (int32_t)(2 * GTB_SEQ_STRIDE) || o_aux > l_data)
+    {
+      g_err = "malformed record";
+      return GTB_ERR_ARG;
+    }
+    memcpy(seq4 + (size_t)k * GTB_SEQ_STRIDE, d + o_seq, (size_t)n_seq);
+    lseq[k] = (uint16_t)c.l_qseq;
+    flag[k] = c.flag;
+    mapq[k] = c.mapq;
+    isize[k] = (int32_t)std::max<int64_t>(std::min<int64_t>(c.isize, INT32_MAX), INT32_MIN);
+    same_tid[k] = c.tid == c.mtid;
+    score_diff[k] = oracle_score_diff(d + o_aux, l_data - o_aux);
+    leftover[k] = 0;
+    // duplicate shortcut: equal_pos_seq against the last non-duplicate record (hts_utils.hpp:110-128)
+    dup_of[k] = -1;
+    if (prev >= 0)
+    {
+      gtb_bam_core const & p = b->core[prev];
+      if (p.tid == c.tid && p.pos == c.pos && p.l_qseq == c.l_qseq &&
+          memcmp(seq4 + (size_t)prev * GTB_SEQ_STRIDE, seq4 + (size_t)k * GTB_SEQ_STRIDE, (size_t)n_seq) == 0)
+        dup_of[k] = prev;
+    }
+    if (dup_of[k] < 0)
+      prev = (int32_t)k;
+    // read-name map
+    if ((size_t)b->rg[k] >= maps.size())
+      maps.resize((size_t)b->rg[k] + 1);
+    auto & m = maps[b->rg[k]];
+    std::string const name(reinterpret_cast<const char *>(d));
+    auto it = m.find(name);
+    mate[k] = -1;
+    if (it != m.end())
+    {
+      mate[k] = it->second;
+      m.erase(it);
+    }
+    else if (c.flag & IS_PAIRED)
+      m[name] = (int32_t)k;
+  }
+  if (is_sv) // whatever still waits at the end of the pool is processed alone (hts_parallel_reader.cpp:719-772)
+    for (auto const & m : maps)
+      for (auto const & kv : m)
+        leftover[kv.second] = 1;
+  return 0;
+}
+
 void gto_set_connections(int on) { g_connections = on != 0; }
 
 int gto_result_connections_size(void * r, uint64_t * n)

@@ -466,6 +466,11 @@ int main(int argc, char ** argv)
   std::vector<uint8_t> r_names;
   std::vector<uint32_t> r_cigar;
   std::vector<uint8_t> r_score_diff_first; // score_diff as set by update_paths on geno.first
+  // the records themselves as htslib holds them: bam1_t::data (qname | cigar | seq | qual | aux) + the core fields the
+  // columns above do not carry -- input of the record-parsing path (gtb_submit_bam_records)
+  std::vector<uint8_t> r_bam_data;
+  std::vector<uint64_t> r_bam_off(1, 0);
+  std::vector<uint32_t> r_lqname;
   PathDump pd;
   SeedDump sd0, sd1;
 
@@ -502,6 +507,9 @@ int main(int argc, char ** argv)
     uint32_t * cg = bam_get_cigar(b);
     r_cigar.insert(r_cigar.end(), cg, cg + c.n_cigar);
     r_cigar_off.push_back(r_cigar.size());
+    r_bam_data.insert(r_bam_data.end(), b->data, b->data + b->l_data);
+    r_bam_off.push_back(r_bam_data.size());
+    r_lqname.push_back(c.l_qname);
     // AS-XS exactly as the reference computes it: run update_paths on a scratch pair
     std::pair<GenotypePaths, GenotypePaths> scratch =
       std::make_pair(GenotypePaths(c.flag, c.l_qseq), GenotypePaths(c.flag, c.l_qseq));
@@ -617,6 +625,9 @@ int main(int argc, char ** argv)
     af.add("cigar", r_cigar);
     af.add("cigar_off", r_cigar_off);
     af.add("score_diff", r_score_diff_first);
+    af.add("bam_data", r_bam_data);
+    af.add("bam_off", r_bam_off);
+    af.add("bam_lqname", r_lqname);
     pd.write(af, "");
     af.add("s0_nslots", sd0.nslots);
     af.add("s0_nlabels", sd0.nlabels);

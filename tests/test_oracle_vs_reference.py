@@ -67,6 +67,63 @@ def test_oracle_connections_and_phase_support_match_reference(pre, oracle_lib):
     O.index_free(h)
 
 
+@pytest.mark.parametrize("pre", SMALL, ids=[os.path.basename(p) for p in SMALL])
+def test_oracle_record_parsing_matches_reference(pre, oracle_lib):
+    """The per-record columns derived from raw records (htslib's core fields + bam1_t::data dumped by the probe) equal what
+    the reference's own loop produced: AS-XS of update_paths / get_score_diff, the duplicate shortcut of the pool loop, and
+    the mate links implied by its read-name maps (checked through the accumulators of a full oracle pool run)."""
+    O = oracle_lib
+    rd = gtba.load(pre + ".reads.gtba")
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    bam = abi.HostBamBatch.from_probe(rd)
+    b = O.parse_bam(bam, is_sv=g.is_sv_graph)
+    want = abi.batch_from_probe(rd)
+    assert np.array_equal(b.score_diff, rd["score_diff"])
+    assert np.array_equal(b.dup_of >= 0, rd["isdup"] != 0)
+    for k in ("seq4", "lseq", "flag", "mapq", "isize", "same_tid", "dup_of", "mate", "leftover"):
+        assert np.array_equal(getattr(b, k), getattr(want, k)), k
+    ns = n_samples_of(rd)
+    h = O.index_build(g)
+    r = O.pool_run(g, h, ns, b, tap=False)
+    compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), O.result_accum(r, ns).as_dict(), "oracle(bam)")
+    O.result_free(r)
+    O.index_free(h)
+
+
+def test_record_parsing_corner_cases(oracle_lib):
+    """Aux walks get_score_diff handles in its own way, and the read-name map's treatment of unpaired records."""
+    O = oracle_lib
+
+    def rec(name, flag, aux, seq=b"\x11" * 32, lq=64):
+        qn = name + b"\0"
+        qn += b"\0" * ((4 - len(qn) % 4) % 4)
+        return dict(data=qn + seq + b"I" * lq + aux, l_qname=len(qn), flag=flag, lq=lq)
+
+    recs = [
+        rec(b"a", 0x41, b"ASC\x64XSC\x0a"),                       # AS 100, XS 10 -> 90
+        rec(b"a", 0x00, b"NMC\x01ASc\xfb"),                       # unpaired, name waits -> pairs anyway; AS -5 (signed), no XS -> 0
+        rec(b"b", 0x41, b"RGZgrp\0ASs\x2c\x01XSS\x05\x00"),       # Z string skipped; AS 300, XS 5 -> 255 (saturates)
+        rec(b"b", 0x81, b"XSC\x05"),                               # no AS -> 0
+        rec(b"c", 0x41, b"ASC\x32BXc\x01XSC\x28"),                 # other tags of integer type are stepped over; 50 - 40
+        rec(b"c", 0x81, b"ZZB\x01ASC\x10"),                        # type 'B' ends the walk before AS -> 0
+        rec(b"d", 0x41, b"ASC\x05XSC\x09"),                        # AS < XS -> 0; never gets a mate
+    ]
+    n = len(recs)
+    core = np.zeros(n, abi.BAM_CORE_DTYPE)
+    off = np.zeros(n + 1, np.uint64)
+    data = b""
+    for i, r in enumerate(recs):
+        core["l_qseq"][i], core["flag"][i], core["l_qname"][i], core["pos"][i] = r["lq"], r["flag"], r["l_qname"], 100 + i
+        data += r["data"]
+        off[i + 1] = len(data)
+    bam = abi.HostBamBatch(core, np.frombuffer(data, np.uint8), off, np.zeros(n, np.int32), np.zeros(n, np.int32))
+    b = O.parse_bam(bam, is_sv=True)
+    assert b.score_diff.tolist() == [90, 0, 255, 0, 0x32 - 0x28, 0, 0]
+    assert b.mate.tolist() == [-1, 0, -1, 2, -1, 4, -1]
+    assert b.leftover.tolist() == [0, 0, 0, 0, 0, 0, 1]
+    assert (b.dup_of == -1).all()
+
+
 def test_golden_fixtures_exercise_connections():
     n_conn = n_ph = 0
     for pre in SMALL:
