@@ -143,6 +143,9 @@ struct BatchState
   std::vector<uint32_t> rec_begin;
   bool with_conn = false;              // some region of this chunk collects phasing connections
   PrepParams prep{};                   // device-side batch preparation of this chunk
+  BamParams bam{};                     // record parsing (gtb_submit_bam_records); bam.n == 0: columns came from the host
+  DeviceBuffer d_bam, d_bam_sort;
+  size_t bam_sort_bytes = 0;
   DeviceBuffer d_scan_temp;
   size_t scan_temp_bytes = 0;
   cudaStream_t stream = nullptr;       // probe + chain of this chunk (chunks run concurrently, each on its own stream)
@@ -158,6 +161,8 @@ struct BatchState
     d_seedrecs.release();
     d_task_times.release();
     d_scan_temp.release();
+    d_bam.release();
+    d_bam_sort.release();
     d_slow.release();
     h_batch.release();
     h_counters.release();
@@ -1213,6 +1218,9 @@ static int launch_front(Ctx * c, BatchState & B, cudaEvent_t after)
   if (P.tap.list_count)
     CUDA_TRY(cudaMemsetAsync(P.tap.list_count, 0, (size_t)P.batch.n_units * 2 * (NLISTS * 2 + 1) * 4, s));
   CUDA_TRY(cudaEventRecord(B.ev[2], s));
+  if (B.bam.n) // record parsing: the chunk's columns from raw htslib records
+    if (launch_bam_parse(B.bam, B.d_bam_sort.p, B.bam_sort_bytes, s) != 0)
+      return fail(GTB_ERR_CUDA, "radix sort of the read-name hashes failed");
   // batch preparation: units, aligned orientations, link checks (exclusive scan of (is_unit << 32 | orientations))
   launch_prep_flags(B.prep, s);
   if (B.prep.n_records)
@@ -1339,6 +1347,7 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     st.n_capacity_overflow += kc->n_overflow;
     // prep_flags, scan, prep_fill, probe, chain (+ the two task-order kernels) (+ first score pass)
     st.kernel_launches += B.P.batch.n_records ? 5 + (B.P.chain_order ? 2 : 0) + (c->n_chunks_last > 1 ? 1 : 0) : 0;
+    st.kernel_launches += B.bam.n ? 7 : 0; // parse, seq, dup, radix sort (3 kernels at these sizes), mate
     n_overflow += kc->n_overflow;
     n_input_error += kc->n_input_error;
     for (int q = 0; q < 12; ++q)
@@ -1370,6 +1379,11 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     return fail(GTB_ERR_ARG, "mate must reference an earlier record of the same batch");
   if (input_bits & PREP_ERR_LEN)
     return fail(GTB_ERR_CAPACITY, "read longer than 152 bases (reference MAX_READ_LENGTH is 151)");
+  if (input_bits & PREP_ERR_RECORD)
+    return fail(GTB_ERR_ARG, "malformed record: qname + cigar + seq + qual do not fit its data block");
+  if (input_bits & PREP_ERR_COLLISION)
+    return fail(GTB_ERR_INPUT, "two different read names share one 64-bit hash (nothing was mis-paired; resubmit through "
+                               "gtb_submit_reads with host-side mate links)");
   if (n_input_error)
     return fail(GTB_ERR_INPUT, "two mates with the same IS_FIRST_IN_PAIR flag (the reference aborts here, "
                                "hts_parallel_reader.cpp:306-315)");
@@ -1387,6 +1401,38 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
   return 0;
 }
 
+// Device layout of one chunk's record columns: [seq4] [columns that arrive from the host or from the record parser ...]
+// [columns produced by the batch-preparation kernels ...]
+struct ChunkLayout
+{
+  size_t o_seq4, o_lseq, o_flag, o_region, o_mapq, o_same, o_sd, o_clip, o_left, o_isize, o_sample, o_mate, o_dup, copy_end;
+  size_t o_unit, o_urec, o_active, o_scan, bytes;
+  explicit ChunkLayout(size_t total)
+  {
+    size_t off = 0;
+    o_seq4 = place<uint8_t>(off, total * GTB_SEQ_STRIDE);
+    o_lseq = place<uint16_t>(off, total);
+    o_flag = place<uint16_t>(off, total);
+    o_region = place<uint16_t>(off, total);
+    o_mapq = place<uint8_t>(off, total);
+    o_same = place<uint8_t>(off, total);
+    o_sd = place<uint8_t>(off, total);
+    o_clip = place<uint8_t>(off, total);
+    o_left = place<uint8_t>(off, total);
+    o_isize = place<int32_t>(off, total);
+    o_sample = place<int32_t>(off, total);
+    o_mate = place<int32_t>(off, total);
+    o_dup = place<int32_t>(off, total);
+    copy_end = off;
+    o_unit = place<int32_t>(off, total);
+    o_urec = place<int32_t>(off, total);
+    o_active = place<uint32_t>(off, total * 2);
+    o_scan = place<unsigned long long>(off, total);
+    bytes = align_up(off, 256);
+  }
+};
+static int bind_chunk(Ctx * c, BatchState & B, ChunkLayout const & Lo, size_t total, bool with_tap);
+
 // Stages one chunk (regions [0, n) of the given arrays): the bases are DMA-ed straight from the caller's buffers when those
 // are page-locked, the small columns are gathered into B's pinned buffer by the host pool (plain copies in blocks of 8192
 // records; mate / duplicate links are rebased to chunk-global indices on the way) and follow in ONE H2D copy.  Everything
@@ -1398,27 +1444,10 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   size_t total = 0;
   for (int i = 0; i < n; ++i)
     total += batches[i].n_reads;
-  // ---- layout: [seq4] [columns copied from the host ...] [columns produced on the device ...]
-  size_t off = 0;
-  size_t const o_seq4 = place<uint8_t>(off, total * GTB_SEQ_STRIDE);
-  size_t const o_lseq = place<uint16_t>(off, total);
-  size_t const o_flag = place<uint16_t>(off, total);
-  size_t const o_region = place<uint16_t>(off, total);
-  size_t const o_mapq = place<uint8_t>(off, total);
-  size_t const o_same = place<uint8_t>(off, total);
-  size_t const o_sd = place<uint8_t>(off, total);
-  size_t const o_clip = place<uint8_t>(off, total);
-  size_t const o_left = place<uint8_t>(off, total);
-  size_t const o_isize = place<int32_t>(off, total);
-  size_t const o_sample = place<int32_t>(off, total);
-  size_t const o_mate = place<int32_t>(off, total);
-  size_t const o_dup = place<int32_t>(off, total);
-  size_t const copy_end = off;
-  size_t const o_unit = place<int32_t>(off, total);
-  size_t const o_urec = place<int32_t>(off, total);
-  size_t const o_active = place<uint32_t>(off, total * 2);
-  size_t const o_scan = place<unsigned long long>(off, total);
-  size_t const bytes = align_up(off, 256);
+  ChunkLayout const Lo(total);
+  size_t const o_seq4 = Lo.o_seq4, o_lseq = Lo.o_lseq, o_flag = Lo.o_flag, o_region = Lo.o_region, o_mapq = Lo.o_mapq,
+               o_same = Lo.o_same, o_sd = Lo.o_sd, o_clip = Lo.o_clip, o_left = Lo.o_left, o_isize = Lo.o_isize,
+               o_sample = Lo.o_sample, o_mate = Lo.o_mate, o_dup = Lo.o_dup, copy_end = Lo.copy_end, bytes = Lo.bytes;
   if (int rc = B.h_batch.reserve(align_up(copy_end, 256)))
     return rc;
   uint8_t * h = static_cast<uint8_t *>(B.h_batch.p);
@@ -1524,6 +1553,23 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
                      h_dup[k] = -1;
                });
 
+  size_t const copy_begin = direct_seq ? o_lseq : 0;
+  if (copy_end > copy_begin)
+    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(B.d_batch.p) + copy_begin, h + copy_begin, copy_end - copy_begin,
+                             cudaMemcpyHostToDevice, c->copy_stream));
+  CUDA_TRY(cudaEventRecord(B.ev[1], c->copy_stream));
+
+  B.bam.n = 0;
+  return bind_chunk(c, B, Lo, total, with_tap);
+}
+
+// Reserves the per-chunk device buffers and points B.P / B.prep at the chunk's columns.
+static int bind_chunk(Ctx * c, BatchState & B, ChunkLayout const & Lo, size_t total, bool with_tap)
+{
+  size_t const o_seq4 = Lo.o_seq4, o_lseq = Lo.o_lseq, o_flag = Lo.o_flag, o_region = Lo.o_region, o_mapq = Lo.o_mapq,
+               o_same = Lo.o_same, o_sd = Lo.o_sd, o_clip = Lo.o_clip, o_left = Lo.o_left, o_isize = Lo.o_isize,
+               o_sample = Lo.o_sample, o_mate = Lo.o_mate, o_dup = Lo.o_dup, o_unit = Lo.o_unit, o_urec = Lo.o_urec,
+               o_active = Lo.o_active, o_scan = Lo.o_scan;
   // upper bounds: every record its own unit, both orientations aligned; the exact counts are produced on the device
   uint32_t const n_units = (uint32_t)total;
   uint32_t const n_active = (uint32_t)total * 2;
@@ -1552,12 +1598,6 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   B.scan_temp_bytes = scan64_temp_bytes((uint32_t)std::max<size_t>(total, 1));
   if (int rc = B.d_scan_temp.reserve(B.scan_temp_bytes + 16))
     return rc;
-
-  size_t const copy_begin = direct_seq ? o_lseq : 0;
-  if (copy_end > copy_begin)
-    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(B.d_batch.p) + copy_begin, h + copy_begin, copy_end - copy_begin,
-                             cudaMemcpyHostToDevice, c->copy_stream));
-  CUDA_TRY(cudaEventRecord(B.ev[1], c->copy_stream));
 
   LaunchParams & P = B.P;
   memset(&P, 0, sizeof(P));
@@ -1771,6 +1811,151 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   if (rc_collect)
     return rc_collect;
   return conn_check(c, n, regs.data());
+}
+
+// Records of one pool as htslib holds them -> parsed, paired and de-duplicated on the device, then the same kernels as
+// gtb_submit_reads (one chunk: the mates of a pool pair within one call).
+int gtb_submit_bam_records(gtb_ctx * ctx, int region_id, const gtb_bam_batch * batch, gtb_submit_stats * stats)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !batch)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  if (c->device < 0)
+    return fail(GTB_ERR_CUDA, "host-only context: the genotyping path needs a CUDA device (no CPU fallback)");
+  auto it = c->regions.find(region_id);
+  if (it == c->regions.end())
+    return fail(GTB_ERR_STATE, "unknown region in submit");
+  Region & R = *it->second;
+  if (!R.pool_open)
+    return fail(GTB_ERR_STATE, "gtb_pool_begin must precede gtb_submit_bam_records");
+  size_t const total = batch->n_reads;
+  if (total >= 0x7FFFFFFFull)
+    return fail(GTB_ERR_ARG, "batch too large");
+  if (total && (!batch->core || !batch->data || !batch->data_off || !batch->sample || !batch->rg))
+    return fail(GTB_ERR_ARG, "record batch has null arrays");
+  size_t const n_data = total ? (size_t)batch->data_off[total] : 0;
+  if (total && batch->data_off[0] != 0)
+    return fail(GTB_ERR_ARG, "data_off[0] must be 0");
+  cudaSetDevice(c->device);
+  if (int rc = conn_reserve(c, R, total))
+    return rc;
+  if (int rc = upload_region_table(c))
+    return rc;
+  c->have_last = false;
+  c->n_chunks_last = 1;
+  BatchState & B = c->bs[0];
+  ChunkLayout const Lo(total);
+  if (int rc = B.d_batch.reserve(Lo.bytes))
+    return rc;
+  B.regions.assign(1, region_id);
+  B.rec_begin.assign({0u, (uint32_t)total});
+  B.unit_begin.clear();
+  // raw records + sort buffers: [core][data_off][rg][hash][hash sorted][idx][idx sorted][data]
+  size_t off = 0;
+  size_t const o_core = place<gtb_bam_core>(off, total);
+  size_t const o_doff = place<unsigned long long>(off, total + 1);
+  size_t const o_rg = place<int32_t>(off, total);
+  size_t const o_hash = place<unsigned long long>(off, total);
+  size_t const o_hash2 = place<unsigned long long>(off, total);
+  size_t const o_idx = place<uint32_t>(off, total);
+  size_t const o_idx2 = place<uint32_t>(off, total);
+  size_t const o_data = place<uint8_t>(off, n_data + 16);
+  if (int rc = B.d_bam.reserve(align_up(off, 256)))
+    return rc;
+  B.bam_sort_bytes = bam_sort_temp_bytes((uint32_t)std::max<size_t>(total, 1));
+  if (int rc = B.d_bam_sort.reserve(B.bam_sort_bytes + 16))
+    return rc;
+  uint8_t * r = static_cast<uint8_t *>(B.d_bam.p);
+  uint8_t * d = static_cast<uint8_t *>(B.d_batch.p);
+  CUDA_TRY(cudaEventRecord(c->ev_slow[2], c->stream));
+  CUDA_TRY(cudaEventRecord(B.ev[0], c->copy_stream));
+  if (total)
+  {
+    CUDA_TRY(cudaMemcpyAsync(r + o_core, batch->core, total * sizeof(gtb_bam_core), cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(r + o_doff, batch->data_off, (total + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(r + o_rg, batch->rg, total * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(r + o_data, batch->data, n_data, cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(d + Lo.o_sample, batch->sample, total * 4, cudaMemcpyHostToDevice, c->copy_stream));
+  }
+  CUDA_TRY(cudaEventRecord(B.ev[1], c->copy_stream));
+  if (int rc = bind_chunk(c, B, Lo, total, c->debug))
+    return rc;
+  BamParams & Q = B.bam;
+  memset(&Q, 0, sizeof(Q));
+  Q.n = (uint32_t)total;
+  Q.region_slot = (uint16_t)R.slot;
+  Q.is_sv = R.dev.is_sv ? 1 : 0;
+  Q.core = reinterpret_cast<const gtb_bam_core *>(r + o_core);
+  Q.data = r + o_data;
+  Q.data_off = reinterpret_cast<const unsigned long long *>(r + o_doff);
+  Q.rg = reinterpret_cast<const int32_t *>(r + o_rg);
+  Q.seq4 = d + Lo.o_seq4;
+  Q.lseq = reinterpret_cast<uint16_t *>(d + Lo.o_lseq);
+  Q.flag = reinterpret_cast<uint16_t *>(d + Lo.o_flag);
+  Q.region = reinterpret_cast<uint16_t *>(d + Lo.o_region);
+  Q.mapq = d + Lo.o_mapq;
+  Q.same_tid = d + Lo.o_same;
+  Q.score_diff = d + Lo.o_sd;
+  Q.clipped = d + Lo.o_clip;
+  Q.leftover = d + Lo.o_left;
+  Q.isize = reinterpret_cast<int32_t *>(d + Lo.o_isize);
+  Q.mate = reinterpret_cast<int32_t *>(d + Lo.o_mate);
+  Q.dup_of = reinterpret_cast<int32_t *>(d + Lo.o_dup);
+  Q.name_hash = reinterpret_cast<unsigned long long *>(r + o_hash);
+  Q.name_hash_sorted = reinterpret_cast<unsigned long long *>(r + o_hash2);
+  Q.idx = reinterpret_cast<uint32_t *>(r + o_idx);
+  Q.idx_sorted = reinterpret_cast<uint32_t *>(r + o_idx2);
+  Q.counters = B.P.counters;
+  B.with_conn = R.conn_cap != 0;
+  if (int rc = launch_front(c, B, c->ev_slow[2]))
+    return rc;
+  if (int rc = launch_back(c, 1))
+    return rc;
+  c->have_last = true;
+  if (int rc = collect_chunks(c, stats, true))
+    return rc;
+  Region * rp = &R;
+  return conn_check(c, 1, &rp);
+}
+
+// The per-record columns the device derived in the last gtb_submit_bam_records (duplicate links resolved to the record whose
+// alignment is re-used, as the reference's `prev` pointer would have it).
+int gtb_debug_bam_columns(gtb_ctx * ctx, uint32_t n_reads, uint8_t * seq4, uint16_t * lseq, uint16_t * flag, uint8_t * mapq,
+                          int32_t * isize, uint8_t * same_tid, uint8_t * score_diff, int32_t * mate, int32_t * dup_of,
+                          uint8_t * leftover)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !c->have_last || c->bs[0].bam.n == 0 || c->bs[0].bam.n != n_reads)
+    return fail(GTB_ERR_STATE, "the last submit was not a gtb_submit_bam_records call of that size");
+  cudaSetDevice(c->device);
+  BamParams const & Q = c->bs[0].bam;
+  size_t const n = n_reads;
+  if (seq4)
+    CUDA_TRY(cudaMemcpy(seq4, Q.seq4, n * GTB_SEQ_STRIDE, cudaMemcpyDeviceToHost));
+  if (lseq)
+    CUDA_TRY(cudaMemcpy(lseq, Q.lseq, n * 2, cudaMemcpyDeviceToHost));
+  if (flag)
+    CUDA_TRY(cudaMemcpy(flag, Q.flag, n * 2, cudaMemcpyDeviceToHost));
+  if (mapq)
+    CUDA_TRY(cudaMemcpy(mapq, Q.mapq, n, cudaMemcpyDeviceToHost));
+  if (isize)
+    CUDA_TRY(cudaMemcpy(isize, Q.isize, n * 4, cudaMemcpyDeviceToHost));
+  if (same_tid)
+    CUDA_TRY(cudaMemcpy(same_tid, Q.same_tid, n, cudaMemcpyDeviceToHost));
+  if (score_diff)
+    CUDA_TRY(cudaMemcpy(score_diff, Q.score_diff, n, cudaMemcpyDeviceToHost));
+  if (mate)
+    CUDA_TRY(cudaMemcpy(mate, Q.mate, n * 4, cudaMemcpyDeviceToHost));
+  if (leftover)
+    CUDA_TRY(cudaMemcpy(leftover, Q.leftover, n, cudaMemcpyDeviceToHost));
+  if (dup_of)
+  {
+    CUDA_TRY(cudaMemcpy(dup_of, Q.dup_of, n * 4, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < n; ++k) // the device links each duplicate to its predecessor; roots are earlier, already final
+      if (dup_of[k] >= 0 && dup_of[dup_of[k]] >= 0)
+        dup_of[k] = dup_of[dup_of[k]];
+  }
+  return 0;
 }
 
 int gtb_submit_reads(gtb_ctx * ctx, int region_id, const gtb_read_batch * batch, gtb_submit_stats * stats)

@@ -212,7 +212,39 @@ struct DevCounters
   // cost classes of the chain_kernel tasks (probe_kernel counts, chain_order_kernels turn them into a heavy-first task order)
   uint32_t chain_bins[16], chain_cursor[16];
 };
-constexpr uint32_t PREP_ERR_SAMPLE = 1, PREP_ERR_DUP = 2, PREP_ERR_MATE = 4, PREP_ERR_LEN = 8;
+constexpr uint32_t PREP_ERR_SAMPLE = 1, PREP_ERR_DUP = 2, PREP_ERR_MATE = 4, PREP_ERR_LEN = 8, PREP_ERR_RECORD = 16,
+                   PREP_ERR_COLLISION = 32;
+
+// Record parsing on the device (gtb_bam.cu): raw htslib records of one pool -> the chunk's record columns
+struct BamParams
+{
+  uint32_t n;
+  uint16_t region_slot;
+  uint16_t is_sv;
+  const gtb_bam_core * core;
+  const uint8_t * data;
+  const unsigned long long * data_off; // [n + 1]
+  const int32_t * rg;
+  uint8_t * seq4;
+  uint16_t * lseq;
+  uint16_t * flag;
+  uint16_t * region;
+  uint8_t * mapq;
+  uint8_t * same_tid;
+  uint8_t * score_diff;
+  uint8_t * clipped;
+  uint8_t * leftover;
+  int32_t * isize;
+  int32_t * mate;
+  int32_t * dup_of;
+  unsigned long long * name_hash;        // [n] hash of (read group, read name)
+  unsigned long long * name_hash_sorted; // [n]
+  uint32_t * idx;                        // [n] 0 .. n-1
+  uint32_t * idx_sorted;                 // [n]
+  DevCounters * counters;
+};
+size_t bam_sort_temp_bytes(uint32_t n);
+int launch_bam_parse(const BamParams & p, void * sort_temp, size_t sort_temp_bytes, void * stream);
 
 // Batch preparation on the device (the per-record part of what genotype_only's caller does, hts_parallel_reader.cpp:655-708):
 // alignment units (records that are not duplicates of an earlier one), the list of read orientations align_read aligns at

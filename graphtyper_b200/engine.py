@@ -25,6 +25,7 @@ EXPORTS = [
     "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_set_chunks", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators", "gtb_allreduce_accumulators_multi", "gtb_debug_counters",
     "gtb_sw_align_batch", "gtb_sw_last_timing", "gtb_sw_replay_last", "gtb_set_index_build",
     "gtb_set_connections", "gtb_connections_size", "gtb_connections", "gtb_phase_support", "gtb_last_prep_timing",
+    "gtb_submit_bam_records", "gtb_debug_bam_columns",
 ]
 
 
@@ -91,6 +92,9 @@ def load_library() -> C.CDLL:
     L.gtb_sw_replay_last.argtypes = [vp]
     L.gtb_set_index_build.argtypes = [vp, C.c_int]
     L.gtb_last_prep_timing.argtypes = [vp, fp]
+    L.gtb_submit_bam_records.argtypes = [vp, C.c_int, C.POINTER(abi.BamBatch), C.POINTER(abi.SubmitStats)]
+    L.gtb_debug_bam_columns.argtypes = [vp, C.c_uint32, abi.u8p, abi.u16p, abi.u16p, abi.u8p, abi.i32p, abi.u8p, abi.u8p, abi.i32p,
+                                        abi.i32p, abi.u8p]
     L.gtb_set_connections.argtypes = [vp, C.c_int]
     L.gtb_connections_size.argtypes = [vp, C.c_int, abi.u64p]
     L.gtb_connections.argtypes = [vp, C.c_int, C.c_void_p]
@@ -239,6 +243,26 @@ class Context:
         st = abi.SubmitStats()
         self._check(self.lib.gtb_submit_reads_multi(self.h, n, ids, arr, C.byref(st)))
         return st
+
+    def submit_bam(self, region_id: int, bam: abi.HostBamBatch) -> abi.SubmitStats:
+        """Raw htslib records of one pool (abi.HostBamBatch): parsed, paired and de-duplicated on the device."""
+        st = abi.SubmitStats()
+        self._check(self.lib.gtb_submit_bam_records(self.h, region_id, C.byref(bam.view), C.byref(st)))
+        return st
+
+    def debug_bam_columns(self, n: int) -> Dict[str, np.ndarray]:
+        """Per-record columns the device derived in the last submit_bam (parity tap)."""
+        out = {"seq4": np.zeros((n, abi.SEQ_STRIDE), np.uint8), "lseq": np.zeros(n, np.uint16), "flag": np.zeros(n, np.uint16),
+               "mapq": np.zeros(n, np.uint8), "isize": np.zeros(n, np.int32), "same_tid": np.zeros(n, np.uint8),
+               "score_diff": np.zeros(n, np.uint8), "mate": np.zeros(n, np.int32), "dup_of": np.zeros(n, np.int32),
+               "leftover": np.zeros(n, np.uint8)}
+        a = abi
+        self._check(self.lib.gtb_debug_bam_columns(
+            self.h, n, out["seq4"].ctypes.data_as(a.u8p), out["lseq"].ctypes.data_as(a.u16p), out["flag"].ctypes.data_as(a.u16p),
+            out["mapq"].ctypes.data_as(a.u8p), out["isize"].ctypes.data_as(a.i32p), out["same_tid"].ctypes.data_as(a.u8p),
+            out["score_diff"].ctypes.data_as(a.u8p), out["mate"].ctypes.data_as(a.i32p), out["dup_of"].ctypes.data_as(a.i32p),
+            out["leftover"].ctypes.data_as(a.u8p)))
+        return out
 
     def replay(self) -> abi.SubmitStats:
         st = abi.SubmitStats()

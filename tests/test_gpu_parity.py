@@ -83,6 +83,57 @@ def test_cuda_connections_match_reference(pre, ctx):
         ctx.region_end(9)
 
 
+@pytest.mark.parametrize("pre", ALL, ids=[os.path.basename(p) for p in ALL])
+def test_cuda_record_parsing_matches_reference(pre, ctx, oracle_lib):
+    """gtb_submit_bam_records: raw htslib records (as the probe dumped them from the reference's own loop) are parsed,
+    de-duplicated and paired on the device; the derived columns equal the reference's (score_diff, duplicates) and the
+    oracle's (mates, leftovers), and the accumulators equal the golden ones."""
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    rd = gtba.load(pre + ".reads.gtba")
+    bam = abi.HostBamBatch.from_probe(rd)
+    ns = n_samples_of(rd)
+    want = oracle_lib.parse_bam(bam, is_sv=g.is_sv_graph)
+    ctx.region_begin(11, g)
+    try:
+        ctx.pool_begin(11, ns)
+        st = ctx.submit_bam(11, bam)
+        assert st.n_records == len(bam) and st.n_capacity_overflow == 0
+        assert st.n_alignments == int((rd["isdup"] == 0).sum())
+        col = ctx.debug_bam_columns(len(bam))
+        assert np.array_equal(col["score_diff"], rd["score_diff"])
+        assert np.array_equal(col["dup_of"] >= 0, rd["isdup"] != 0)
+        for k in ("seq4", "lseq", "flag", "mapq", "isize", "same_tid", "score_diff", "mate", "dup_of", "leftover"):
+            assert np.array_equal(col[k], getattr(want, k)), k
+        acc = ctx.pool_finish(11)
+        compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), acc.as_dict(), "cuda(bam)")
+    finally:
+        ctx.region_end(11)
+
+
+def test_record_parsing_rejects_bad_records(ctx):
+    _ref, g = _plain_graph()
+    ctx.region_begin(12, g)
+    try:
+        ctx.pool_begin(12, 1)
+
+        def one(l_qseq, data, l_qname=4):
+            core = np.zeros(1, abi.BAM_CORE_DTYPE)
+            core["l_qseq"], core["l_qname"] = l_qseq, l_qname
+            return abi.HostBamBatch(core, np.frombuffer(data, np.uint8), np.array([0, len(data)], np.uint64), np.zeros(1, np.int32),
+                                    np.zeros(1, np.int32))
+        with pytest.raises(engine.GtbError) as e:   # sequence + qualities do not fit the data block
+            ctx.submit_bam(12, one(100, b"r1\0\0" + b"\x11" * 20))
+        assert e.value.code == -1
+        with pytest.raises(engine.GtbError) as e:   # longer than the reference's MAX_READ_LENGTH
+            ctx.submit_bam(12, one(200, b"r1\0\0" + b"\x11" * 100 + b"I" * 200))
+        assert e.value.code == -4
+        st = ctx.submit_bam(12, abi.HostBamBatch(np.zeros(0, abi.BAM_CORE_DTYPE), np.zeros(0, np.uint8), np.zeros(1, np.uint64),
+                                                 np.zeros(0, np.int32), np.zeros(0, np.int32)))
+        assert st.n_records == 0
+    finally:
+        ctx.region_end(12)
+
+
 def test_connection_table_grows_and_replay_doubles(ctx):
     """A 2-slots-per-record budget forces table growth (re-insert on the device) between submits; the result is unchanged.
     Replaying the resident batch (the last shard) only ever adds counts (monotonicity)."""

@@ -6,4 +6,4 @@ cd "$(dirname "$0")/.."
 name=$1; shift
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared "$@" \
   -o graphtyper_b200/libgtb200_$name.so graphtyper_b200/csrc/gtb_api.cu graphtyper_b200/csrc/gtb_kernels.cu \
-  graphtyper_b200/csrc/gtb_sw.cu graphtyper_b200/csrc/gtb_index_dev.cu -lcudart -ldl 2>&1 | grep -i "error" || true
+  graphtyper_b200/csrc/gtb_sw.cu graphtyper_b200/csrc/gtb_index_dev.cu graphtyper_b200/csrc/gtb_bam.cu -lcudart -ldl 2>&1 | grep -i "error" || true
