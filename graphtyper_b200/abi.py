@@ -441,6 +441,63 @@ def batch_from_readsets(readsets: Sequence, region_idx: Optional[Sequence[np.nda
                      np.ones(n, np.uint8), sd, np.zeros(n, np.uint8), cat["sample"], mate, dup)
 
 
+def bam_batch_from_readsets(readsets: Sequence, region_idx: Optional[Sequence[np.ndarray]] = None,
+                            flag_filter: int = 3840) -> "HostBamBatch":
+    """The same pool as batch_from_readsets (same records, same merge order), but as raw records the way htslib holds them
+    after reading the SAM/BAM written by synth.write_sam: qname (NUL + padding to 4) | cigar | 4-bit seq | qual | aux
+    (RG:Z, AS, XS with the smallest integer type that fits, like sam_parse1)."""
+    import re
+    cols = {k: [] for k in ("pos", "mpos", "flag", "mapq", "isize", "seq", "as", "xs", "sample", "name", "cig")}
+    names: List[bytes] = []
+    for s, rs in enumerate(readsets):
+        idx = np.arange(len(rs)) if region_idx is None else region_idx[s]
+        idx = idx[(rs.flag[idx] & flag_filter) == 0]
+        for k, v in (("pos", rs.pos), ("mpos", rs.mpos), ("flag", rs.flag), ("mapq", rs.mapq), ("isize", rs.isize), ("seq", rs.seq),
+                     ("as", rs.as_tag), ("xs", rs.xs_tag)):
+            cols[k].append(v[idx])
+        cols["sample"].append(np.full(len(idx), s, np.int32))
+        cols["name"].append(np.arange(len(names), len(names) + len(idx)))
+        cols["cig"].append(np.arange(len(names), len(names) + len(idx)))
+        names += [(f"{rs.name_prefix}{int(rs.name_id[i])}".encode(), rs.cigar[i], rs.sample.encode()) for i in idx]
+    cat = {k: np.concatenate(v) for k, v in cols.items()}
+    n = len(cat["pos"])
+    L = cat["seq"].shape[1] if n else 0
+    seq4 = pack_seq4(cat["seq"]) if n else np.zeros((0, SEQ_STRIDE), np.uint8)
+    order = merge_order(cat["pos"], np.full(n, L), seq4, cat["sample"]) if n else np.zeros(0, np.int64)
+    ops = {c: i for i, c in enumerate("MIDNSHP=X")}
+
+    def int_tag(tag: bytes, v: int) -> bytes:
+        if 0 <= v < 256:
+            return tag + b"C" + int(v).to_bytes(1, "little")
+        if -128 <= v < 0:
+            return tag + b"c" + int(v).to_bytes(1, "little", signed=True)
+        if 0 <= v < 65536:
+            return tag + b"S" + int(v).to_bytes(2, "little")
+        return tag + b"i" + int(v).to_bytes(4, "little", signed=True)
+
+    core = np.zeros(n, BAM_CORE_DTYPE)
+    off = np.zeros(n + 1, np.uint64)
+    parts: List[bytes] = []
+    nb = (L + 1) // 2
+    for j, o in enumerate(order):
+        qn, cigar, sample = names[cat["name"][o]]
+        q = qn + b"\0"
+        q += b"\0" * ((4 - len(q) % 4) % 4)
+        cg = b"".join(((int(m) << 4) | ops[c]).to_bytes(4, "little") for m, c in re.findall(r"(\d+)([MIDNSHP=X])", cigar))
+        aux = b"RGZ" + sample + b"\0" + int_tag(b"AS", int(cat["as"][o]))
+        if cat["xs"][o] >= 0:
+            aux += int_tag(b"XS", int(cat["xs"][o]))
+        rec = q + cg + seq4[o, :nb].tobytes() + b"\x28" * L + aux
+        parts.append(rec)
+        off[j + 1] = off[j] + len(rec)
+        core["l_qname"][j], core["n_cigar"][j] = len(q), len(cg) // 4
+    for k, src in (("pos", "pos"), ("mpos", "mpos"), ("isize", "isize"), ("flag", "flag"), ("mapq", "mapq")):
+        core[k] = cat[src][order]
+    core["l_qseq"] = L
+    return HostBamBatch(core, np.frombuffer(b"".join(parts), np.uint8), off, cat["sample"][order], np.zeros(n, np.int32)
+                        if len(readsets) == 1 else cat["sample"][order])
+
+
 def merge_order(pos: np.ndarray, lseq: np.ndarray, seq4: np.ndarray, file_index: np.ndarray) -> np.ndarray:
     """Order of HtsParallelReader's heap merge: ascending (tid,) pos, l_qseq, sequence bytes; equal records keep
     heap order.  Within one file same-position records are std::sort-ed descending and popped from the back

@@ -1813,32 +1813,41 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   return conn_check(c, n, regs.data());
 }
 
-// Records of one pool as htslib holds them -> parsed, paired and de-duplicated on the device, then the same kernels as
-// gtb_submit_reads (one chunk: the mates of a pool pair within one call).
-int gtb_submit_bam_records(gtb_ctx * ctx, int region_id, const gtb_bam_batch * batch, gtb_submit_stats * stats)
+// Records of one pool per region as htslib holds them -> parsed, paired and de-duplicated on the device, then the same
+// kernels as gtb_submit_reads_multi (one chunk: the mates of a pool pair within one call).
+int gtb_submit_bam_records_multi(gtb_ctx * ctx, int n, const int * region_ids, const gtb_bam_batch * batches, gtb_submit_stats * stats)
 {
   auto * c = reinterpret_cast<Ctx *>(ctx);
-  if (!c || !batch)
+  if (!c || n <= 0 || !region_ids || !batches)
     return fail(GTB_ERR_ARG, "bad arguments");
   if (c->device < 0)
     return fail(GTB_ERR_CUDA, "host-only context: the genotyping path needs a CUDA device (no CPU fallback)");
-  auto it = c->regions.find(region_id);
-  if (it == c->regions.end())
-    return fail(GTB_ERR_STATE, "unknown region in submit");
-  Region & R = *it->second;
-  if (!R.pool_open)
-    return fail(GTB_ERR_STATE, "gtb_pool_begin must precede gtb_submit_bam_records");
-  size_t const total = batch->n_reads;
-  if (total >= 0x7FFFFFFFull)
-    return fail(GTB_ERR_ARG, "batch too large");
-  if (total && (!batch->core || !batch->data || !batch->data_off || !batch->sample || !batch->rg))
-    return fail(GTB_ERR_ARG, "record batch has null arrays");
-  size_t const n_data = total ? (size_t)batch->data_off[total] : 0;
-  if (total && batch->data_off[0] != 0)
-    return fail(GTB_ERR_ARG, "data_off[0] must be 0");
+  std::vector<Region *> regs(n);
+  std::vector<uint32_t> rec_begin(n + 1, 0);
+  std::vector<unsigned long long> data_base(n + 1, 0);
+  for (int i = 0; i < n; ++i)
+  {
+    auto it = c->regions.find(region_ids[i]);
+    if (it == c->regions.end())
+      return fail(GTB_ERR_STATE, "unknown region in submit");
+    if (!it->second->pool_open)
+      return fail(GTB_ERR_STATE, "gtb_pool_begin must precede gtb_submit_bam_records");
+    regs[i] = it->second.get();
+    gtb_bam_batch const & b = batches[i];
+    if (b.n_reads && (!b.core || !b.data || !b.data_off || !b.sample || !b.rg))
+      return fail(GTB_ERR_ARG, "record batch has null arrays");
+    if (b.n_reads && b.data_off[0] != 0)
+      return fail(GTB_ERR_ARG, "data_off[0] must be 0");
+    if ((unsigned long long)rec_begin[i] + b.n_reads >= 0x7FFFFFFFull)
+      return fail(GTB_ERR_ARG, "batch too large");
+    rec_begin[i + 1] = rec_begin[i] + b.n_reads;
+    data_base[i + 1] = data_base[i] + (b.n_reads ? b.data_off[b.n_reads] : 0);
+  }
+  size_t const total = rec_begin[n], n_data = (size_t)data_base[n];
   cudaSetDevice(c->device);
-  if (int rc = conn_reserve(c, R, total))
-    return rc;
+  for (int i = 0; i < n; ++i)
+    if (int rc = conn_reserve(c, *regs[i], batches[i].n_reads))
+      return rc;
   if (int rc = upload_region_table(c))
     return rc;
   c->have_last = false;
@@ -1847,35 +1856,50 @@ int gtb_submit_bam_records(gtb_ctx * ctx, int region_id, const gtb_bam_batch * b
   ChunkLayout const Lo(total);
   if (int rc = B.d_batch.reserve(Lo.bytes))
     return rc;
-  B.regions.assign(1, region_id);
-  B.rec_begin.assign({0u, (uint32_t)total});
+  B.regions.assign(region_ids, region_ids + n);
+  B.rec_begin = rec_begin;
   B.unit_begin.clear();
-  // raw records + sort buffers: [core][data_off][rg][hash][hash sorted][idx][idx sorted][data]
+  // raw records + tables + sort buffers
   size_t off = 0;
   size_t const o_core = place<gtb_bam_core>(off, total);
-  size_t const o_doff = place<unsigned long long>(off, total + 1);
+  size_t const o_doff = place<unsigned long long>(off, total + n);
   size_t const o_rg = place<int32_t>(off, total);
   size_t const o_hash = place<unsigned long long>(off, total);
   size_t const o_hash2 = place<unsigned long long>(off, total);
   size_t const o_idx = place<uint32_t>(off, total);
   size_t const o_idx2 = place<uint32_t>(off, total);
+  size_t const o_tab = place<unsigned long long>(off, (size_t)n * 3 + 4); // data_base[n] | rec_begin[n + 1] | slots[n]
   size_t const o_data = place<uint8_t>(off, n_data + 16);
   if (int rc = B.d_bam.reserve(align_up(off, 256)))
     return rc;
   B.bam_sort_bytes = bam_sort_temp_bytes((uint32_t)std::max<size_t>(total, 1));
   if (int rc = B.d_bam_sort.reserve(B.bam_sort_bytes + 16))
     return rc;
+  // small tables through the chunk's pinned staging buffer
+  size_t const tab_bytes = (size_t)n * 8 + (size_t)(n + 1) * 4 + (size_t)n * 2;
+  if (int rc = B.h_batch.reserve(align_up(tab_bytes, 256)))
+    return rc;
+  uint8_t * ht = static_cast<uint8_t *>(B.h_batch.p);
+  memcpy(ht, data_base.data(), (size_t)n * 8);
+  memcpy(ht + (size_t)n * 8, rec_begin.data(), (size_t)(n + 1) * 4);
+  for (int i = 0; i < n; ++i)
+    reinterpret_cast<uint16_t *>(ht + (size_t)n * 8 + (size_t)(n + 1) * 4)[i] = (uint16_t)regs[i]->slot;
   uint8_t * r = static_cast<uint8_t *>(B.d_bam.p);
   uint8_t * d = static_cast<uint8_t *>(B.d_batch.p);
   CUDA_TRY(cudaEventRecord(c->ev_slow[2], c->stream));
   CUDA_TRY(cudaEventRecord(B.ev[0], c->copy_stream));
-  if (total)
+  CUDA_TRY(cudaMemcpyAsync(r + o_tab, ht, tab_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  for (int i = 0; i < n; ++i)
   {
-    CUDA_TRY(cudaMemcpyAsync(r + o_core, batch->core, total * sizeof(gtb_bam_core), cudaMemcpyHostToDevice, c->copy_stream));
-    CUDA_TRY(cudaMemcpyAsync(r + o_doff, batch->data_off, (total + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
-    CUDA_TRY(cudaMemcpyAsync(r + o_rg, batch->rg, total * 4, cudaMemcpyHostToDevice, c->copy_stream));
-    CUDA_TRY(cudaMemcpyAsync(r + o_data, batch->data, n_data, cudaMemcpyHostToDevice, c->copy_stream));
-    CUDA_TRY(cudaMemcpyAsync(d + Lo.o_sample, batch->sample, total * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    gtb_bam_batch const & b = batches[i];
+    size_t const m = b.n_reads, at = rec_begin[i];
+    if (m == 0)
+      continue;
+    CUDA_TRY(cudaMemcpyAsync(r + o_core + at * sizeof(gtb_bam_core), b.core, m * sizeof(gtb_bam_core), cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(r + o_doff + (at + i) * 8, b.data_off, (m + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(r + o_rg + at * 4, b.rg, m * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(r + o_data + data_base[i], b.data, (size_t)b.data_off[m], cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(d + Lo.o_sample + at * 4, b.sample, m * 4, cudaMemcpyHostToDevice, c->copy_stream));
   }
   CUDA_TRY(cudaEventRecord(B.ev[1], c->copy_stream));
   if (int rc = bind_chunk(c, B, Lo, total, c->debug))
@@ -1883,8 +1907,11 @@ int gtb_submit_bam_records(gtb_ctx * ctx, int region_id, const gtb_bam_batch * b
   BamParams & Q = B.bam;
   memset(&Q, 0, sizeof(Q));
   Q.n = (uint32_t)total;
-  Q.region_slot = (uint16_t)R.slot;
-  Q.is_sv = R.dev.is_sv ? 1 : 0;
+  Q.n_regions = (uint32_t)n;
+  Q.data_base = reinterpret_cast<const unsigned long long *>(r + o_tab);
+  Q.rec_begin = reinterpret_cast<const uint32_t *>(r + o_tab + (size_t)n * 8);
+  Q.slots = reinterpret_cast<const uint16_t *>(r + o_tab + (size_t)n * 8 + (size_t)(n + 1) * 4);
+  Q.regions = B.P.regions;
   Q.core = reinterpret_cast<const gtb_bam_core *>(r + o_core);
   Q.data = r + o_data;
   Q.data_off = reinterpret_cast<const unsigned long long *>(r + o_doff);
@@ -1906,7 +1933,9 @@ int gtb_submit_bam_records(gtb_ctx * ctx, int region_id, const gtb_bam_batch * b
   Q.idx = reinterpret_cast<uint32_t *>(r + o_idx);
   Q.idx_sorted = reinterpret_cast<uint32_t *>(r + o_idx2);
   Q.counters = B.P.counters;
-  B.with_conn = R.conn_cap != 0;
+  B.with_conn = false;
+  for (int i = 0; i < n; ++i)
+    B.with_conn = B.with_conn || regs[i]->conn_cap != 0;
   if (int rc = launch_front(c, B, c->ev_slow[2]))
     return rc;
   if (int rc = launch_back(c, 1))
@@ -1914,8 +1943,12 @@ int gtb_submit_bam_records(gtb_ctx * ctx, int region_id, const gtb_bam_batch * b
   c->have_last = true;
   if (int rc = collect_chunks(c, stats, true))
     return rc;
-  Region * rp = &R;
-  return conn_check(c, 1, &rp);
+  return conn_check(c, n, regs.data());
+}
+
+int gtb_submit_bam_records(gtb_ctx * ctx, int region_id, const gtb_bam_batch * batch, gtb_submit_stats * stats)
+{
+  return gtb_submit_bam_records_multi(ctx, 1, &region_id, batch, stats);
 }
 
 // The per-record columns the device derived in the last gtb_submit_bam_records (duplicate links resolved to the record whose

@@ -98,6 +98,28 @@ __device__ uint8_t score_diff_of(const uint8_t * it, long l_aux)
   return diff < 255 ? (uint8_t)diff : (uint8_t)255;
 }
 
+// region of record k (records of a region are contiguous) and the bounds of its data block
+struct RecLoc
+{
+  uint32_t reg;
+  unsigned long long o0, o1;
+};
+__device__ __forceinline__ RecLoc locate(const BamParams & p, uint32_t k)
+{
+  uint32_t lo = 0, hi = p.n_regions; // last region with rec_begin <= k
+  while (hi - lo > 1)
+  {
+    uint32_t const mid = (lo + hi) >> 1;
+    if (p.rec_begin[mid] <= k)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  const unsigned long long * off = p.data_off + p.rec_begin[lo] + lo + (k - p.rec_begin[lo]);
+  unsigned long long const base = p.data_base[lo];
+  return RecLoc{lo, base + off[0], base + off[1]};
+}
+
 __device__ __forceinline__ bool record_ok(const gtb_bam_core & c, unsigned long long l_data)
 {
   if (c.l_qseq < 0 || c.l_qname == 0)
@@ -112,7 +134,8 @@ __global__ void __launch_bounds__(256) bam_parse_kernel(BamParams p)
   if (k >= p.n)
     return;
   gtb_bam_core const c = p.core[k];
-  unsigned long long const o0 = p.data_off[k], o1 = p.data_off[k + 1];
+  RecLoc const loc = locate(p, k);
+  unsigned long long const o0 = loc.o0, o1 = loc.o1;
   bool ok = o1 >= o0 && record_ok(c, o1 - o0);
   if (ok && c.l_qseq > MAX_SEQ)
   {
@@ -121,7 +144,7 @@ __global__ void __launch_bounds__(256) bam_parse_kernel(BamParams p)
   }
   else if (!ok)
     atomicOr(&p.counters->input_bits, PREP_ERR_RECORD);
-  p.region[k] = p.region_slot;
+  p.region[k] = p.slots[loc.reg];
   p.clipped[k] = 0; // clipped_count() returns a bool, so "> 3" is never true in the reference (alignment.cpp:105-138)
   p.leftover[k] = 0;
   p.mate[k] = -1;
@@ -147,8 +170,8 @@ __global__ void __launch_bounds__(256) bam_parse_kernel(BamParams p)
   p.same_tid[k] = c.tid == c.mtid;
   unsigned long long const o_aux = (unsigned long long)c.l_qname + 4ull * c.n_cigar + (unsigned long long)(c.l_qseq + 1) / 2 + (unsigned long long)c.l_qseq;
   p.score_diff[k] = score_diff_of(d + o_aux, (long)((o1 - o0) - o_aux));
-  // FNV-1a over (read group, name up to the NUL), finished with a 64-bit mix
-  unsigned long long h = 0xCBF29CE484222325ull ^ (unsigned long long)(uint32_t)p.rg[k];
+  // FNV-1a over (region, read group, name up to the NUL), finished with a 64-bit mix
+  unsigned long long h = 0xCBF29CE484222325ull ^ (unsigned long long)(uint32_t)p.rg[k] ^ ((unsigned long long)loc.reg << 32);
   h *= 0x100000001B3ull;
   for (uint32_t j = 0; j < c.l_qname && d[j] != 0; ++j)
   {
@@ -169,7 +192,7 @@ __global__ void __launch_bounds__(256) bam_seq_kernel(BamParams p)
     return;
   uint32_t const L = p.lseq[k]; // 0 for a rejected record
   uint32_t const nb = (L + 1) / 2;
-  const uint8_t * src = p.data + p.data_off[k] + p.core[k].l_qname + 4ull * p.core[k].n_cigar;
+  const uint8_t * src = p.data + locate(p, k).o0 + p.core[k].l_qname + 4ull * p.core[k].n_cigar;
   uint8_t * dst = p.seq4 + (size_t)k * GTB_SEQ_STRIDE;
   for (uint32_t j = lane; j < GTB_SEQ_STRIDE; j += 32)
     dst[j] = j < nb ? src[j] : (uint8_t)0;
@@ -184,7 +207,8 @@ __global__ void __launch_bounds__(256) bam_dup_kernel(BamParams p)
   if (k > 0 && p.lseq[k] != 0)
   {
     gtb_bam_core const a = p.core[k - 1], b = p.core[k];
-    if (a.tid == b.tid && a.pos == b.pos && a.l_qseq == b.l_qseq && p.lseq[k - 1] != 0)
+    if (a.tid == b.tid && a.pos == b.pos && a.l_qseq == b.l_qseq && p.lseq[k - 1] != 0 && p.region[k - 1] == p.region[k] &&
+        locate(p, k).reg == locate(p, k - 1).reg) // the shortcut never crosses a pool
     {
       // rows are zero-padded to the stride, so whole-row equality = equality of the (l_qseq + 1) / 2 sequence bytes;
       // a row is 76 bytes = 19 words and starts 4-byte aligned
@@ -209,7 +233,8 @@ __global__ void __launch_bounds__(128) bam_mate_kernel(BamParams p)
   if (q0 > 0 && p.name_hash_sorted[q0 - 1] == key)
     return; // not the head of its run
   uint32_t const head = p.idx_sorted[q0];
-  const uint8_t * hname = p.data + p.data_off[head];
+  RecLoc const hloc = locate(p, head);
+  const uint8_t * hname = p.data + hloc.o0;
   int32_t const hrg = p.rg[head];
   int32_t waiting = -1;
   for (uint32_t q = q0; q < p.n && p.name_hash_sorted[q] == key; ++q)
@@ -217,8 +242,9 @@ __global__ void __launch_bounds__(128) bam_mate_kernel(BamParams p)
     uint32_t const r = p.idx_sorted[q]; // ascending within the run: the sort is stable
     if (q != q0)
     {
-      const uint8_t * name = p.data + p.data_off[r];
-      bool same = p.rg[r] == hrg;
+      RecLoc const rloc = locate(p, r);
+      const uint8_t * name = p.data + rloc.o0;
+      bool same = p.rg[r] == hrg && rloc.reg == hloc.reg;
       for (uint32_t j = 0; same; ++j)
       {
         same = name[j] == hname[j];
@@ -239,7 +265,7 @@ __global__ void __launch_bounds__(128) bam_mate_kernel(BamParams p)
     else if (p.flag[r] & 1u)
       waiting = (int32_t)r;
   }
-  if (waiting >= 0 && p.is_sv)
+  if (waiting >= 0 && p.regions[p.slots[hloc.reg]].is_sv)
     p.leftover[waiting] = 1;
 }
 } // namespace

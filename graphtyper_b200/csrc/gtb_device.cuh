@@ -218,12 +218,15 @@ constexpr uint32_t PREP_ERR_SAMPLE = 1, PREP_ERR_DUP = 2, PREP_ERR_MATE = 4, PRE
 // Record parsing on the device (gtb_bam.cu): raw htslib records of one pool -> the chunk's record columns
 struct BamParams
 {
-  uint32_t n;
-  uint16_t region_slot;
-  uint16_t is_sv;
-  const gtb_bam_core * core;
+  uint32_t n;                          // records of all regions of the call, concatenated
+  uint32_t n_regions;
+  const uint32_t * rec_begin;          // [n_regions + 1] first record of each region
+  const uint16_t * slots;              // [n_regions] device region slot
+  const unsigned long long * data_base; // [n_regions] where each region's data block starts in `data`
+  const DevRegion * regions;
+  const gtb_bam_core * core;           // [n]
   const uint8_t * data;
-  const unsigned long long * data_off; // [n + 1]
+  const unsigned long long * data_off; // region r: its (n_r + 1) region-relative offsets start at rec_begin[r] + r
   const int32_t * rg;
   uint8_t * seq4;
   uint16_t * lseq;

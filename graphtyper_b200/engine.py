@@ -25,7 +25,7 @@ EXPORTS = [
     "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_set_chunks", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators", "gtb_allreduce_accumulators_multi", "gtb_debug_counters",
     "gtb_sw_align_batch", "gtb_sw_last_timing", "gtb_sw_replay_last", "gtb_set_index_build",
     "gtb_set_connections", "gtb_connections_size", "gtb_connections", "gtb_phase_support", "gtb_last_prep_timing",
-    "gtb_submit_bam_records", "gtb_debug_bam_columns",
+    "gtb_submit_bam_records", "gtb_submit_bam_records_multi", "gtb_debug_bam_columns",
 ]
 
 
@@ -93,6 +93,7 @@ def load_library() -> C.CDLL:
     L.gtb_set_index_build.argtypes = [vp, C.c_int]
     L.gtb_last_prep_timing.argtypes = [vp, fp]
     L.gtb_submit_bam_records.argtypes = [vp, C.c_int, C.POINTER(abi.BamBatch), C.POINTER(abi.SubmitStats)]
+    L.gtb_submit_bam_records_multi.argtypes = [vp, C.c_int, abi.i32p, C.POINTER(abi.BamBatch), C.POINTER(abi.SubmitStats)]
     L.gtb_debug_bam_columns.argtypes = [vp, C.c_uint32, abi.u8p, abi.u16p, abi.u16p, abi.u8p, abi.i32p, abi.u8p, abi.u8p, abi.i32p,
                                         abi.i32p, abi.u8p]
     L.gtb_set_connections.argtypes = [vp, C.c_int]
@@ -141,6 +142,14 @@ def pin_batches(batches: Sequence[abi.HostBatch]) -> Tuple[List[abi.HostBatch], 
                                  arena.take(b.isize), arena.take(b.same_tid), arena.take(b.score_diff),
                                  arena.take(b.clipped), arena.take(b.sample), arena.take(b.mate), arena.take(b.dup_of)))
     return out, arena
+
+
+def pin_bam_batches(bams: Sequence[abi.HostBamBatch]) -> Tuple[List[abi.HostBamBatch], "PinnedArena"]:
+    """Raw-record batches re-homed in page-locked memory."""
+    total = sum(b.core.nbytes + b.data.nbytes + b.data_off.nbytes + b.sample.nbytes + b.rg.nbytes + 8 * 256 for b in bams) + 4096
+    arena = PinnedArena(total)
+    return [abi.HostBamBatch(arena.take(b.core), arena.take(b.data), arena.take(b.data_off), arena.take(b.sample), arena.take(b.rg))
+            for b in bams], arena
 
 
 class Context:
@@ -248,6 +257,14 @@ class Context:
         """Raw htslib records of one pool (abi.HostBamBatch): parsed, paired and de-duplicated on the device."""
         st = abi.SubmitStats()
         self._check(self.lib.gtb_submit_bam_records(self.h, region_id, C.byref(bam.view), C.byref(st)))
+        return st
+
+    def submit_bam_multi(self, region_ids: Sequence[int], bams: Sequence[abi.HostBamBatch]) -> abi.SubmitStats:
+        n = len(region_ids)
+        ids = (C.c_int32 * n)(*region_ids)
+        arr = (abi.BamBatch * n)(*[b.view for b in bams])
+        st = abi.SubmitStats()
+        self._check(self.lib.gtb_submit_bam_records_multi(self.h, n, ids, arr, C.byref(st)))
         return st
 
     def debug_bam_columns(self, n: int) -> Dict[str, np.ndarray]:

@@ -278,6 +278,10 @@ typedef struct gtb_bam_batch {
   const int32_t *rg;          /* [n_reads] read-group index: one read-name map per read group */
 } gtb_bam_batch;
 int gtb_submit_bam_records(gtb_ctx *ctx, int region_id, const gtb_bam_batch *batch, gtb_submit_stats *stats);
+/* Several regions' pools in one launch sequence (region_ids[i] / batches[i]); pairing and the duplicate shortcut never cross
+ * a pool.  gtb_debug_bam_columns then addresses the concatenation of the batches. */
+int gtb_submit_bam_records_multi(gtb_ctx *ctx, int n, const int *region_ids, const gtb_bam_batch *batches,
+                                 gtb_submit_stats *stats);
 /* Debug/parity tap: the per-record columns the device derived in the last gtb_submit_bam_records call (any pointer may be NULL). */
 int gtb_debug_bam_columns(gtb_ctx *ctx, uint32_t n_reads, uint8_t *seq4 /*[n*GTB_SEQ_STRIDE]*/, uint16_t *lseq, uint16_t *flag,
                           uint8_t *mapq, int32_t *isize, uint8_t *same_tid, uint8_t *score_diff, int32_t *mate, int32_t *dup_of,

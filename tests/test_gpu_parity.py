@@ -110,6 +110,48 @@ def test_cuda_record_parsing_matches_reference(pre, ctx, oracle_lib):
         ctx.region_end(11)
 
 
+def test_record_parsing_of_several_pools_in_one_call(ctx):
+    """gtb_submit_bam_records_multi: pairing and the duplicate shortcut stay inside each pool; same accumulators as one call
+    per region.  Also: records built from the synthetic generator (abi.bam_batch_from_readsets) give the same accumulators as
+    the column batch of the same pool (abi.batch_from_readsets)."""
+    pres = [p for p in ALL if os.path.basename(p).startswith("mini_") or os.path.basename(p).startswith("tiny")]
+    ids = list(range(400, 400 + len(pres)))
+    graphs, bams, ns = [], [], []
+    for pre in pres:
+        graphs.append(abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba")))
+        rd = gtba.load(pre + ".reads.gtba")
+        bams.append(abi.HostBamBatch.from_probe(rd))
+        ns.append(n_samples_of(rd))
+    ctx.region_begin_multi(ids, graphs)
+    try:
+        for k, n in zip(ids, ns):
+            ctx.pool_begin(k, n)
+        st = ctx.submit_bam_multi(ids, bams)
+        assert st.n_records == sum(len(b) for b in bams)
+        for pre, acc in zip(pres, ctx.pool_finish_multi(ids)):
+            compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), acc.as_dict(), "cuda(bam multi) " + pre)
+    finally:
+        for k in ids:
+            ctx.region_end(k)
+    from graphtyper_b200 import graph_build, synth
+    ds = synth.make_dataset(length=6000, n_sites=60, n_samples=2, seed=77, coverage=10, err=0.005, unpaired_rate=0.05)
+    g = graph_build.build_region_graph(ds.ref, ds.sites, 1, 6000, pad=0)
+    cols = abi.batch_from_readsets(ds.reads)
+    bam = abi.bam_batch_from_readsets(ds.reads)
+    ctx.region_begin(450, g)
+    try:
+        ctx.pool_begin(450, 2)
+        ctx.submit(450, cols)
+        a = ctx.pool_finish(450).as_dict()
+        ctx.pool_reset(450)
+        ctx.submit_bam(450, bam)
+        b = ctx.pool_finish(450).as_dict()
+        compare.compare_accum(a, b, "columns vs records")
+        assert a["read_strand"].sum() > 0
+    finally:
+        ctx.region_end(450)
+
+
 def test_record_parsing_rejects_bad_records(ctx):
     _ref, g = _plain_graph()
     ctx.region_begin(12, g)
