@@ -1,10 +1,11 @@
 // gtb_api.cu -- C-ABI entry points (include/gtb200.h) and host orchestration (product code).
 //
-// Host responsibilities (the reference keeps these on the host too): graph flattening checks, k-mer index
-// construction (gtb_index_host.hpp), packing one region into a single device arena, batching records
-// (alignment units for the duplicate-read shortcut, mate links), kernel launches on a private stream,
-// accumulator download + saturation, PHRED conversion.  There is NO CPU fallback for the compute path: without
-// a usable CUDA device gtb_create(device >= 0) fails and every compute entry point returns GTB_ERR_CUDA.
+// Host responsibilities: graph flattening checks, packing one region into a single device arena (the k-mer index itself is
+// built on the device, gtb_index_dev.cu; the host builder of gtb_index_host.hpp is the alternative), gathering the record
+// columns of a submit into pinned staging (plain copies -- alignment units, aligned orientations and link checks are derived
+// on the device), chunking and stream orchestration, accumulator download + saturation, PHRED conversion, the phase-support
+// map.  There is NO CPU fallback for the compute path: without a usable CUDA device gtb_create(device >= 0) fails and every
+// compute entry point returns GTB_ERR_CUDA.
 
 #include <algorithm>
 #include <atomic>

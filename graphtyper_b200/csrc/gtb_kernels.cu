@@ -1,23 +1,29 @@
 // gtb_kernels.cu -- sm_100a kernels of the read -> graph genotyping path (product code).
 //
-//   align_kernel : one warp per (alignment unit, read orientation).
-//       A. unpack the 4-bit read, build the 32-mer seed keys (warp reduce), probe the region's open-addressed
-//          k-mer table for the exact key and its 96 Hamming-1 neighbours, lanes probing different keys
-//          (replaces to_uint64_vec / query_index / PHIndex::multi_get, src/utilities/type_conversions.cpp:207-288,
-//          src/utilities/kmer_help_functions.cpp:51-119, src/index/ph_index.cpp:66-107);
+// One launch sequence per chunk of a submit:
+//   prep_flags_kernel / prep_fill_kernel (+ a 64-bit scan): alignment units of the duplicate-read shortcut, the list of read
+//       orientations align_read aligns at all (alignment.cpp:343-360), link checks -- the per-record part of the pool loop
+//       (hts_parallel_reader.cpp:655-708).
+//   probe_kernel : phase A, one persistent block per SM, one warp per (alignment unit, read orientation) at a time: the
+//       32-mer seed keys and their GF(2)-linear hashes (warp reduces), the 96 Hamming-1 neighbours per seed against the
+//       region's presence filter in SHARED memory, the few keys that pass against the open-addressed k-mer table
+//       (replaces to_uint64_vec / query_index / PHIndex::multi_get, src/utilities/type_conversions.cpp:207-288,
+//       src/utilities/kmer_help_functions.cpp:51-119, src/index/ph_index.cpp:66-107).
+//   chain_kernel (one thread per task, working set in local memory) / slow_kernel (one warp per task, shared memory) /
+//   huge_kernel (one warp per task, global slab) -- three capacity tiers of the same templated code:
 //       B. chain the seed labels into paths (GenotypePaths::add_next_kmer_labels, src/typer/genotype_paths.cpp:294-352,
 //          Path merge src/typer/path.cpp:38-82);
 //       C. extend both read ends through the bubble graph under the shrinking mismatch budget
 //          (walk_read_starts/ends genotype_paths.cpp:483-621, Graph::get_locations_of_a_position graph.cpp:931-1185,
 //          get_labels_forward/backward graph.cpp:1187-1701, count_mismatches graph_utils.hpp:7-69);
 //       D. apply the path filters (alignment.cpp:68-87) and write a compact GenotypePaths record.
-//   score_kernel : one thread per record: mate/orientation selection (get_better_paths alignment.cpp:557-622,
-//       compare_pair_of_genotype_paths genotype_paths.cpp:943-1169), read acceptance (vcf_writer.cpp:28-60) and the
-//       integer likelihood / depth / stat accumulation (vcf_writer.cpp:503-676, haplotype.cpp:180-585) as atomics
-//       into widened per-bubble per-sample accumulators.
+//   score_kernel / score_deferred_kernel : one thread per record: mate/orientation selection (get_better_paths
+//       alignment.cpp:557-622, compare_pair_of_genotype_paths genotype_paths.cpp:943-1169), read acceptance
+//       (vcf_writer.cpp:28-60) and the integer likelihood / depth / stat accumulation (vcf_writer.cpp:503-676,
+//       haplotype.cpp:180-585) as atomics into widened per-bubble per-sample accumulators; optionally the phasing
+//       connections (vcf_writer.cpp:88-250,587-637) into the pool's open-addressing table.
+//   gather_segments_kernel / zero_segments_kernel, conn_rehash_kernel / conn_compact_kernel, build_table_kernel: upkeep.
 //
-// The working set of a read lives in shared memory (one WS per warp); phases B-D are data-dependent scalar
-// logic executed by lane 0 while phase A (the memory-bound part: ~388 table probes per read) uses all lanes.
 // Order-sensitive semantics of the reference (bucket order, path order, candidate order) are preserved.
 
 #include <cstdio>
