@@ -308,6 +308,8 @@ struct LaunchParams
   uint32_t * deferred;          // [n_records] records the first score pass left for the second (some task pending)
   uint8_t * chain_bin;          // [n_active] cost class of each task (labels handed over by probe_kernel, capped at 15)
   uint32_t * chain_order;       // [n_active] task positions, heaviest class first; nullptr = natural order
+  int filter_max_fold;          // probe_kernel: fold the presence bitmap into shared memory up to 2^this times (default
+                                // FILTER_MAX_FOLD; < 0 = always probe the global bitmap) -- GTB_PROBE_FILTER_FOLD, tests
   uint32_t defer;               // 1: score_kernel runs before slow_kernel and defers; 0: it runs after and scores everything
   unsigned long long * task_times; // profiling aid (GTB_TASK_TIMES=file): [n_active][2] globaltimer ns at start / end of
                                    // each chain_kernel task; nullptr normally

@@ -27,6 +27,7 @@
 // Order-sensitive semantics of the reference (bucket order, path order, candidate order) are preserved.
 
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "gtb_device.cuh"
@@ -1685,7 +1686,7 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
     const DevRegion & R = P.regions[slot];
     int const log2cap = 64 - R.table_shift;
     int const fold = log2cap + 2 - (int)FILTER_LOG2_BITS; // log2 of (bitmap bits / filter bits); <= 0: bitmap fits as it is
-    bool const use_filter = fold <= FILTER_MAX_FOLD;
+    bool const use_filter = fold <= P.filter_max_fold;
     if (use_filter)
     {
       if (fold <= 0)
@@ -3130,7 +3131,10 @@ void launch_probe(const LaunchParams & p, void * stream)
   }
   uint32_t const want = (p.n_active + 255) / 256;
   uint32_t const grid = std::max(1u, std::min(want, (uint32_t)sm_count()));
-  probe_kernel<<<grid, PROBE_BLOCK_WARPS * 32, FILTER_WORDS * 4, (cudaStream_t)stream>>>(p);
+  LaunchParams q = p;
+  const char * e = getenv("GTB_PROBE_FILTER_FOLD"); // tests: -1 forces the global-bitmap path on every region
+  q.filter_max_fold = e ? std::min(atoi(e), FILTER_MAX_FOLD) : FILTER_MAX_FOLD;
+  probe_kernel<<<grid, PROBE_BLOCK_WARPS * 32, FILTER_WORDS * 4, (cudaStream_t)stream>>>(q);
 }
 
 void launch_chain(const LaunchParams & p, void * stream)

@@ -310,6 +310,55 @@ def test_full_config2_workload_matches_oracle(ctx, oracle_lib):
             ctx.region_end(k)
 
 
+def _large_region_case(length, n_sites, seed, coverage):
+    from graphtyper_b200 import graph_build, synth
+    ref = synth.make_reference(length, seed)
+    sites = synth.make_sites(ref, n_sites, seed + 1)
+    gts = synth.make_genotypes(n_sites, 1, seed + 2)
+    rs = synth.simulate_reads(ref, sites, gts[0], "SAMP1", seed + 3, coverage=coverage)
+    g = graph_build.build_region_graph(ref, sites, 1, length, pad=0)
+    return g, abi.batch_from_readsets([rs])
+
+
+@pytest.mark.parametrize("length,n_sites,expect_log2cap", [(150_000, 1500, 20), (420_000, 3000, 21)],
+                         ids=["fold4_shared_filter", "global_bitmap"])
+def test_probe_paths_of_large_regions_match_oracle(ctx, oracle_lib, length, n_sites, expect_log2cap):
+    """probe_kernel stages a region's presence bitmap in shared memory folded 1x / 2x / 4x and falls back to the global
+    bitmap beyond that (more than ~2.6e5 distinct k-mers, e.g. the 1.2 Mb regions of genotype_sv).  The fixtures only reach
+    the 1x / 2x cases; here one region per remaining case, against the oracle."""
+    g, b = _large_region_case(length, n_sites, seed=301 + expect_log2cap, coverage=4)
+    h = oracle_lib.index_build(g)
+    n_keys = len(oracle_lib.index_export(h)["keys"])
+    assert (1 << (expect_log2cap - 1)) < 4 * n_keys + 2 <= (1 << expect_log2cap), n_keys   # table capacity = load <= 0.25
+    r = oracle_lib.pool_run(g, h, 1, b, tap=False)
+    want = {k: v for k, v in oracle_lib.result_accum(r, 1).as_dict().items() if k != "saturated"}
+    ctx.region_begin(30, g)
+    try:
+        ctx.pool_begin(30, 1)
+        st = ctx.submit(30, b)
+        assert st.n_capacity_overflow == 0 and st.n_pairs_scored == oracle_lib.result_stats(r).n_pairs_scored
+        compare.compare_accum(want, ctx.pool_finish(30).as_dict(), "large region")
+    finally:
+        ctx.region_end(30)
+        oracle_lib.result_free(r)
+        oracle_lib.index_free(h)
+
+
+def test_probe_global_bitmap_path_on_fixtures(ctx, monkeypatch):
+    """The same fixtures with the shared-memory filter switched off: every region probes the global bitmap."""
+    monkeypatch.setenv("GTB_PROBE_FILTER_FOLD", "-1")
+    for pre in ALL[:6]:
+        g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+        rd = gtba.load(pre + ".reads.gtba")
+        ctx.region_begin(31, g)
+        try:
+            ctx.pool_begin(31, n_samples_of(rd))
+            ctx.submit(31, abi.batch_from_probe(rd))
+            compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), ctx.pool_finish(31).as_dict(), "global bitmap")
+        finally:
+            ctx.region_end(31)
+
+
 def test_pinned_inputs_take_the_direct_dma_path_with_equal_results(ctx):
     """Columns in page-locked memory (gtb_host_alloc) skip the staging copy; results must not change."""
     pre = ALL[1]
