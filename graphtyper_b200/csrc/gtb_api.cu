@@ -21,6 +21,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -2476,6 +2477,50 @@ int gtb_phase_support(const gtb_accumulators * acc, uint64_t n_conn, const gtb_c
     }
   }
   *n_out = ph.size();
+  return 0;
+}
+
+// Two sorted connection lists of the same pool (e.g. from two ranks that each saw a share of the reads) -> one.
+int gtb_merge_connections(uint64_t n_a, const gtb_connection * a, uint64_t n_b, const gtb_connection * b, uint64_t * n_out,
+                          gtb_connection * out)
+{
+  if (!n_out || (n_a && !a) || (n_b && !b))
+    return fail(GTB_ERR_ARG, "bad arguments");
+  auto key = [](const gtb_connection & c) {
+    return std::make_tuple(c.sample, c.hap1, c.allele1, c.hap2, c.allele2);
+  };
+  uint64_t i = 0, j = 0, n = 0;
+  uint64_t const cap = *n_out;
+  auto emit = [&](gtb_connection c) -> bool {
+    c.count &= 0xFFFFu;
+    if (c.count == 0)
+      return true;
+    if (out)
+    {
+      if (n >= cap)
+        return false;
+      out[n] = c;
+    }
+    ++n;
+    return true;
+  };
+  bool ok = true;
+  while (ok && (i < n_a || j < n_b))
+  {
+    if (j >= n_b || (i < n_a && key(a[i]) < key(b[j])))
+      ok = emit(a[i++]);
+    else if (i >= n_a || key(b[j]) < key(a[i]))
+      ok = emit(b[j++]);
+    else
+    {
+      gtb_connection c = a[i++];
+      c.count += b[j++].count;
+      ok = emit(c);
+    }
+  }
+  if (!ok)
+    return fail(GTB_ERR_ARG, "merged connection output too small");
+  *n_out = n;
   return 0;
 }
 

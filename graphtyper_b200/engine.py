@@ -25,7 +25,7 @@ EXPORTS = [
     "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_set_chunks", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators", "gtb_allreduce_accumulators_multi", "gtb_debug_counters",
     "gtb_sw_align_batch", "gtb_sw_last_timing", "gtb_sw_replay_last", "gtb_set_index_build",
     "gtb_set_connections", "gtb_connections_size", "gtb_connections", "gtb_phase_support", "gtb_last_prep_timing",
-    "gtb_submit_bam_records", "gtb_submit_bam_records_multi", "gtb_debug_bam_columns",
+    "gtb_submit_bam_records", "gtb_submit_bam_records_multi", "gtb_debug_bam_columns", "gtb_merge_connections",
 ]
 
 
@@ -233,6 +233,18 @@ class Context:
     def phase_support(self, acc: abi.HostAccumulators, conn: np.ndarray) -> np.ndarray:
         """The `ph` map (hts_parallel_reader.cpp:782-893) as a structured array (abi.PHASE_DTYPE); pure host function."""
         return abi.phase_support(self.lib, "gtb_phase_support", acc, conn)
+
+    def merge_connections(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        """Sum of two sorted connection lists of one pool (read-sharded ranks); pure host function."""
+        fn = self.lib.gtb_merge_connections
+        fn.argtypes = [C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, abi.u64p, C.c_void_p]
+        a = np.ascontiguousarray(a, dtype=abi.CONNECTION_DTYPE)
+        b = np.ascontiguousarray(b, dtype=abi.CONNECTION_DTYPE)
+        n = C.c_uint64(0)
+        self._check(fn(len(a), a.ctypes.data, len(b), b.ctypes.data, C.byref(n), None))
+        out = np.zeros(n.value, abi.CONNECTION_DTYPE)
+        self._check(fn(len(a), a.ctypes.data, len(b), b.ctypes.data, C.byref(n), out.ctypes.data))
+        return out
 
     def set_chunks(self, n: int) -> None:
         self._check(self.lib.gtb_set_chunks(self.h, n))

@@ -314,6 +314,11 @@ typedef struct gtb_phase_support_entry {
 } gtb_phase_support_entry;
 int gtb_phase_support(const gtb_accumulators *acc, uint64_t n_conn, const gtb_connection *conn, uint64_t *n_out,
                       gtb_phase_support_entry *out);
+/* Read-sharded multi-GPU runs (one sample's reads split over ranks): the ranks' connection lists of the same pool are
+ * additive (every entry comes from one read or read pair, and mates stay together).  Merges two sorted lists into one
+ * sorted list, counts added modulo 2^16 like the reference's uint16 counters; out == NULL returns the size in *n_out. */
+int gtb_merge_connections(uint64_t n_a, const gtb_connection *a, uint64_t n_b, const gtb_connection *b, uint64_t *n_out,
+                          gtb_connection *out);
 
 /* Multi-GPU: sum-reduce widened accumulators of a region over an NCCL communicator supplied by the host
  * (ncclComm_t passed as void*; all ranks call; result valid on every rank).  Used when ONE sample's reads

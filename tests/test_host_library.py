@@ -80,6 +80,38 @@ def test_host_phase_support_matches_reference(pre):
     ctx.close()
 
 
+def test_sharded_connections_merge_to_unsharded(oracle_lib):
+    """Additivity of the phasing connections under read sharding (mates and duplicate groups stay together,
+    abi.shard_batch): the shards' lists, merged by gtb_merge_connections, equal the unsharded list -- and the reference's."""
+    pre = [p for p in SMALL if "mini_stress" in p][0]
+    O = oracle_lib
+    g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+    rd = gtba.load(pre + ".reads.gtba")
+    ns = len(rd["sample_names"].tobytes().split(b"\n")) - 1
+    h = O.index_build(g)
+    ctx = engine.Context(device=-1)
+    O.set_connections(True)
+    try:
+        merged = np.zeros(0, abi.CONNECTION_DTYPE)
+        for shard in abi.shard_batch(abi.batch_from_probe(rd), 3):
+            r = O.pool_run(g, h, ns, shard, tap=False)
+            merged = ctx.merge_connections(merged, O.result_connections(r))
+            O.result_free(r)
+    finally:
+        O.set_connections(False)
+        O.index_free(h)
+    want = compare.probe_connections(gtba.load(pre + ".accum.gtba"))
+    compare.compare_connections(want, abi.connections_as_table(merged), "merged shards")
+    # counters wrap at 2^16 like the reference's uint16: 0xFFFF + 1 disappears, 0xFFFF + 3 becomes 2
+    one = np.zeros(2, abi.CONNECTION_DTYPE)
+    one["hap2"], one["allele2"], one["count"] = [1, 2], [0, 1], [0xFFFF, 0xFFFF]
+    two = one.copy()
+    two["count"] = [1, 3]
+    out = ctx.merge_connections(one, two)
+    assert abi.connections_as_table(out).tolist() == [[0, 0, 0, 2, 1, 2]]
+    ctx.close()
+
+
 def test_no_cpu_fallback():
     ctx = engine.Context(device=-1)
     g = abi.HostGraph.from_gtba(gtba.load(SMALL[0] + ".graph.gtba"))
