@@ -2767,6 +2767,29 @@ int gtb_calls_from_accumulators(const gtb_accumulators * acc, uint8_t * phred, u
 }
 
 // Variant::scan_calls (src/typer/variant.cpp:230-428) for every bubble of one pool (non-SV graphs)
+int gtb_sample_depths(const gtb_accumulators * acc, uint16_t * ref_total_depth, uint16_t * alt_total_depth)
+{
+  if (!acc || !ref_total_depth || !alt_total_depth)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  uint64_t const NS = acc->n_samples;
+  for (uint32_t b = 0; b < acc->n_bubbles; ++b)
+  {
+    uint32_t const cnum = acc->n_alleles[b];
+    for (uint64_t s = 0; s < NS; ++s)
+    {
+      const uint16_t * cov = acc->gt_coverage + acc->cov_off[b] * NS + s * cnum;
+      uint64_t const i = (uint64_t)b * NS + s;
+      uint32_t const amb = acc->ambiguous_depth[i], amb_alt = acc->ambiguous_depth_alt[i];
+      uint32_t alt = amb;
+      for (uint32_t a = 1; a < cnum; ++a)
+        alt += cov[a];
+      ref_total_depth[i] = (uint16_t)std::min<uint32_t>(0xFFFFu, (uint32_t)cov[0] + amb - amb_alt);
+      alt_total_depth[i] = (uint16_t)std::min<uint32_t>(0xFFFFu, alt);
+    }
+  }
+  return 0;
+}
+
 int gtb_scan_calls(const gtb_accumulators * acc, const uint8_t * phred, uint64_t * var, uint64_t * allele, double * ratio)
 {
   if (!acc || !phred || !var || !allele || !ratio)

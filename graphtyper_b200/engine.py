@@ -25,7 +25,7 @@ EXPORTS = [
     "gtb_last_timing", "gtb_last_kernel_timing", "gtb_pool_reset", "gtb_set_chunks", "gtb_host_alloc", "gtb_host_free", "gtb_nccl_unique_id", "gtb_nccl_init", "gtb_allreduce_accumulators", "gtb_allreduce_accumulators_multi", "gtb_debug_counters",
     "gtb_sw_align_batch", "gtb_sw_last_timing", "gtb_sw_replay_last", "gtb_set_index_build",
     "gtb_set_connections", "gtb_connections_size", "gtb_connections", "gtb_phase_support", "gtb_last_prep_timing",
-    "gtb_submit_bam_records", "gtb_submit_bam_records_multi", "gtb_debug_bam_columns", "gtb_merge_connections",
+    "gtb_submit_bam_records", "gtb_submit_bam_records_multi", "gtb_debug_bam_columns", "gtb_merge_connections", "gtb_sample_depths",
 ]
 
 
@@ -382,6 +382,15 @@ class Context:
         self._check(self.lib.gtb_calls_from_accumulators(C.byref(acc.view), phred.ctypes.data_as(abi.u8p),
                                                          gt.ctypes.data_as(abi.u16p), gq.ctypes.data_as(abi.u8p)))
         return phred, gt, gq
+
+    def sample_depths(self, acc: abi.HostAccumulators):
+        """SampleCall::ref_total_depth / alt_total_depth per bubble x sample (sample_call.cpp:34-61)."""
+        fn = self.lib.gtb_sample_depths
+        fn.argtypes = [C.POINTER(abi.Accumulators), abi.u16p, abi.u16p]
+        n = acc.n_bubbles * acc.n_samples
+        r, a = np.zeros(n, np.uint16), np.zeros(n, np.uint16)
+        self._check(fn(C.byref(acc.view), r.ctypes.data_as(abi.u16p), a.ctypes.data_as(abi.u16p)))
+        return r, a
 
     def scan_calls(self, acc: abi.HostAccumulators, phred: np.ndarray):
         """Variant::scan_calls summary of one pool: (var[NB,9], allele[n_cov,13], ratio[n_cov])."""

@@ -206,6 +206,13 @@ int gtb_debug_paths(gtb_ctx *ctx, int region_id, uint32_t *gp_npaths /*[n_units*
 int gtb_calls_from_accumulators(const gtb_accumulators *acc, uint8_t *phred /*[n_scores*n_samples]*/,
                                 uint16_t *gt /*[n_bubbles*n_samples*2]*/, uint8_t *gq /*[n_bubbles*n_samples]*/);
 
+/* The remaining SampleCall fields (SampleCall ctor, src/typer/sample_call.cpp:34-61): per bubble x sample
+ *   ref_total_depth = min(0xFFFF, coverage[0] + ambiguous_depth - ambiguous_depth_alt)
+ *   alt_total_depth = min(0xFFFF, sum(coverage[1..]) + ambiguous_depth)
+ * (coverage = gt_coverage, AD; ambiguous_depth = MD; alt_proper_pair_depth = PP are the accumulators themselves). */
+int gtb_sample_depths(const gtb_accumulators *acc, uint16_t *ref_total_depth /*[n_bubbles*n_samples]*/,
+                      uint16_t *alt_total_depth /*[n_bubbles*n_samples]*/);
+
 /* Bench/ops helpers: re-run the kernels on the batch already resident in HBM; device times (ms) of the last
  * submit/replay from CUDA events on the library's stream; zero a region's accumulators. */
 int gtb_replay_last(gtb_ctx *ctx, gtb_submit_stats *stats);

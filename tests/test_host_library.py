@@ -44,9 +44,14 @@ def test_host_finalisation_matches_reference(pre):
     acc = abi.HostAccumulators(nb, int(ref["score_off"][-1]), int(ref["cov_off"][-1]), ns)
     for k in ("n_alleles", "score_off", "cov_off", "log_score"):
         getattr(acc, k)[:] = ref[k]
-    for k in ("gt_coverage", "ambiguous_depth", "alt_proper_pair_depth"):
+    for k in ("gt_coverage", "ambiguous_depth", "ambiguous_depth_alt", "alt_proper_pair_depth"):
         getattr(acc, k)[:] = ref[k]
     ctx = engine.Context(device=-1)
+    # the SampleCall of every bubble x sample: AD / MD / PP are the accumulators, RA-style totals derived (sample_call.cpp:34-61)
+    assert np.array_equal(pa["call_cov"], ref["gt_coverage"])
+    assert np.array_equal(pa["call_amb"], ref["ambiguous_depth"]) and np.array_equal(pa["call_altpp"], ref["alt_proper_pair_depth"])
+    ref_total, alt_total = ctx.sample_depths(acc)
+    assert np.array_equal(ref_total, pa["call_ref_total"]) and np.array_equal(alt_total, pa["call_alt_total"])
     ph, gt, gq = ctx.calls(acc)
     assert np.array_equal(ph, pa["call_phred"])
     assert np.array_equal(gt, pa["call_gt"])
