@@ -265,7 +265,7 @@ def main() -> None:
     # inputs live in page-locked host memory (gtb_host_alloc), as a production caller would fill them
     batches, pinned_arena = engine.pin_batches(batches)
     ids = list(range(len(graphs)))
-    # region setup = host index build (parallel threads) + graph/label upload + on-device table build.
+    # region setup = graph upload + index build on the device (enumerate, radix sorts, table) for all 20 regions.
     # First call pays one-time CUDA module/pinned-pool initialisation, so the steady-state figure is the second call.
     setup_times = []
     for rep in range(5):

@@ -162,10 +162,11 @@ const char *gtb_version(void);
 int gtb_create(int device_id, gtb_ctx **out);
 void gtb_destroy(gtb_ctx *ctx);
 
-/* Region: flatten + index build (host) + upload (device). Regions are identified by a small integer so
+/* Region: graph upload + index build (device by default, gtb_set_index_build). Regions are identified by a small integer so
  * several regions can be resident and processed by ONE batched launch (region-batched mode). */
 int gtb_region_begin(gtb_ctx *ctx, int region_id, const gtb_graph_view *graph);
-/* Several regions at once: host index builds run in parallel threads, uploads follow. */
+/* Several regions at once: ONE launch sequence builds all their indexes on the device (or, with the host builder,
+ * the builds run in parallel threads and the uploads follow). */
 int gtb_region_begin_multi(gtb_ctx *ctx, int n, const int *region_ids, const gtb_graph_view *graphs);
 int gtb_region_end(gtb_ctx *ctx, int region_id);
 
