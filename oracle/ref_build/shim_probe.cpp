@@ -3,8 +3,10 @@
 //   1. construct_graph (reference) -> gtb_shim::flatten -> gtb_region_begin on a host-only context (host index builder)
 //      -> gtb_index_export, compared key by key and label by label (bucket order included) with index_graph (reference);
 //   2. the pool's records gathered by gtb_shim::Records through the reference's own HtsParallelReader + flag filter;
-//   3. the compute entry points refuse to run without a device (no CPU fallback).
-// Prints "SHIM PASS ..." or the first difference.
+//   3. the compute entry points refuse to run without a device (no CPU fallback);
+//   4. with --gpu (on the GPU box): region + pool + records through the C ABI on the device, every HapSample and per-bubble
+//      statistic compared with the reference's own pool loop (genotype_only + VcfWriter) run in the same process.
+// Prints "SHIM PASS ..." (and "SHIM GPU PASS ...") or the first difference.
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -22,7 +24,148 @@
 #include <graphtyper/utilities/logging.hpp>
 #include <graphtyper/utilities/options.hpp>
 
+#include <graphtyper/graph/reference_depth.hpp>
+#include <graphtyper/typer/genotype_paths.hpp>
+#include <graphtyper/typer/primers.hpp>
+#include <graphtyper/typer/vcf_writer.hpp>
+#include <graphtyper/utilities/hts_utils.hpp>
+
+#include <seqan/sequence.h>
+
 #include "../../integration/gtb_shim.hpp"
+
+namespace gyper
+{
+// defined with external linkage in src/utilities/hts_parallel_reader.cpp:245 (not declared in a header)
+void genotype_only(HtsParallelReader const & hts_preader,
+                   VcfWriter & writer,
+                   ReferenceDepth & reference_depth,
+                   std::vector<std::unordered_map<std::string, std::pair<GenotypePaths, GenotypePaths>>> & maps,
+                   std::pair<GenotypePaths, GenotypePaths> & prev_paths,
+                   PHIndex const & ph_index,
+                   Primers const * primers,
+                   HtsRecord const & hts_rec,
+                   seqan::IupacString & seq,
+                   seqan::IupacString & rseq,
+                   bool update_prev_paths,
+                   bool const IS_SV_CALLING);
+} // namespace gyper
+
+namespace
+{
+// 4. (--gpu) the whole path through the shim on the device against the reference's own pool loop, in this process:
+// every HapSample (log_score, gt_coverage, max_log_score, ambiguous / alt proper-pair depths) and the per-bubble statistics
+int compare_with_reference_loop(std::vector<std::string> const & sams, gyper::PHIndex const & ph_index, gtb_shim::FlatGraph const & fg,
+                                gtb_bam_batch const & batch)
+{
+  using namespace gyper;
+  Options const & opts = *Options::const_instance();
+  // reference: driver of hts_parallel_reader.cpp:655-708 on the reference's own functions (same as gt_probe.cpp)
+  HtsParallelReader reader;
+  reader.open(sams, "", ".");
+  VcfWriter writer(opts.split_var_threshold - 1);
+  writer.set_samples(reader.get_samples());
+  ReferenceDepth reference_depth;
+  std::vector<std::unordered_map<std::string, std::pair<GenotypePaths, GenotypePaths>>> maps(reader.get_num_rg());
+  std::pair<GenotypePaths, GenotypePaths> prev_paths;
+  HtsRecord prev, curr;
+  seqan::IupacString seq, rseq;
+  bool done = !reader.read_record(prev);
+  while (!done && (prev.record->core.flag & opts.sam_flag_filter) != 0u)
+    done = !reader.read_record(prev);
+  if (!done)
+  {
+    genotype_only(reader, writer, reference_depth, maps, prev_paths, ph_index, nullptr, prev, seq, rseq, true, false);
+    while (reader.read_record(curr))
+    {
+      if ((curr.record->core.flag & opts.sam_flag_filter) != 0u)
+        continue;
+      if (equal_pos_seq(prev.record, curr.record))
+        genotype_only(reader, writer, reference_depth, maps, prev_paths, ph_index, nullptr, curr, seq, rseq, false, false);
+      else
+      {
+        genotype_only(reader, writer, reference_depth, maps, prev_paths, ph_index, nullptr, curr, seq, rseq, true, false);
+        reader.move_record(prev, curr);
+      }
+    }
+  }
+  // device: region + pool + records through the C ABI
+  int const NS = (int)writer.pns.size();
+  gtb_ctx * ctx = nullptr;
+  gtb_shim::die(gtb_create(0, &ctx));
+  gtb_shim::die(gtb_region_begin(ctx, 0, &fg.view));
+  gtb_shim::die(gtb_pool_begin(ctx, 0, NS));
+  gtb_submit_stats st{};
+  gtb_shim::die(gtb_submit_bam_records(ctx, 0, &batch, &st));
+  uint32_t nb = 0;
+  uint64_t n_scores = 0, n_cov = 0;
+  gtb_shim::die(gtb_accumulator_sizes(ctx, 0, &nb, &n_scores, &n_cov));
+  std::vector<uint32_t> bubble_id(nb), n_alleles(nb), saturated((size_t)nb * NS), read_strand(n_cov * 4);
+  std::vector<uint64_t> score_off(nb + 1), cov_off(nb + 1), vs_cr(nb), vs_mq(nb), pa_cb(n_cov), pa_mq(n_cov), pa_sd(n_cov), pa_mm(n_cov);
+  std::vector<uint16_t> log_score(n_scores * NS), gt_cov(n_cov * NS), max_ls((size_t)nb * NS);
+  std::vector<uint8_t> amb((size_t)nb * NS), amb_alt((size_t)nb * NS), alt_pp((size_t)nb * NS);
+  gtb_accumulators acc{};
+  acc.bubble_id = bubble_id.data();
+  acc.n_alleles = n_alleles.data();
+  acc.score_off = score_off.data();
+  acc.cov_off = cov_off.data();
+  acc.log_score = log_score.data();
+  acc.gt_coverage = gt_cov.data();
+  acc.max_log_score = max_ls.data();
+  acc.ambiguous_depth = amb.data();
+  acc.ambiguous_depth_alt = amb_alt.data();
+  acc.alt_proper_pair_depth = alt_pp.data();
+  acc.saturated = saturated.data();
+  acc.vs_clipped_reads = vs_cr.data();
+  acc.vs_mapq_squared = vs_mq.data();
+  acc.pa_clipped_bp = pa_cb.data();
+  acc.pa_mapq_squared = pa_mq.data();
+  acc.pa_score_diff = pa_sd.data();
+  acc.pa_mismatches = pa_mm.data();
+  acc.read_strand = read_strand.data();
+  gtb_shim::die(gtb_pool_finish(ctx, 0, &acc));
+  gtb_destroy(ctx);
+  if (writer.haplotypes.size() != nb)
+  {
+    printf("SHIM GPU FAIL: %zu haplotypes in the reference, %u bubbles on the device\n", writer.haplotypes.size(), nb);
+    return 1;
+  }
+  for (uint32_t b = 0; b < nb; ++b)
+  {
+    Haplotype const & hap = writer.haplotypes[b];
+    uint64_t const tri = score_off[b + 1] - score_off[b], cnum = cov_off[b + 1] - cov_off[b];
+    bool ok = hap.gt.id == bubble_id[b] && hap.gt.num == n_alleles[b] && hap.var_stats.clipped_reads == vs_cr[b] &&
+              hap.var_stats.mapq_squared == vs_mq[b];
+    for (int s = 0; ok && s < NS; ++s)
+    {
+      auto const & hs = hap.hap_samples[s];
+      ok = hs.log_score.size() == tri && hs.gt_coverage.size() == cnum &&
+           memcmp(hs.log_score.data(), log_score.data() + score_off[b] * NS + s * tri, tri * 2) == 0 &&
+           memcmp(hs.gt_coverage.data(), gt_cov.data() + cov_off[b] * NS + s * cnum, cnum * 2) == 0 &&
+           hs.max_log_score == max_ls[(size_t)b * NS + s] && hs.get_ambiguous_depth() == amb[(size_t)b * NS + s] &&
+           hs.get_ambiguous_depth_alt() == amb_alt[(size_t)b * NS + s] &&
+           hs.get_alt_proper_pair_depth() == alt_pp[(size_t)b * NS + s];
+    }
+    for (uint64_t a = 0; ok && a < cnum; ++a)
+    {
+      auto const & pa = hap.var_stats.per_allele[a];
+      auto const & rs = hap.var_stats.read_strand[a];
+      uint64_t const i = cov_off[b] + a;
+      ok = pa.clipped_bp == pa_cb[i] && pa.mapq_squared == pa_mq[i] && pa.score_diff == pa_sd[i] && pa.mismatches == pa_mm[i] &&
+           rs.r1_forward == read_strand[i * 4] && rs.r1_reverse == read_strand[i * 4 + 1] && rs.r2_forward == read_strand[i * 4 + 2] &&
+           rs.r2_reverse == read_strand[i * 4 + 3];
+    }
+    if (!ok)
+    {
+      printf("SHIM GPU FAIL: bubble %u differs from the reference's haplotype\n", b);
+      return 1;
+    }
+  }
+  printf("SHIM GPU PASS bubbles=%u samples=%d records=%llu pairs_scored=%llu\n", nb, NS, (unsigned long long)st.n_records,
+         (unsigned long long)st.n_pairs_scored);
+  return 0;
+}
+} // namespace
 
 int main(int argc, char ** argv)
 {
@@ -112,6 +255,9 @@ int main(int argc, char ** argv)
     return 1;
   }
   gtb_destroy(ctx);
+  if (argc > 5 && std::string(argv[5]) == "--gpu")
+    if (int rc = compare_with_reference_loop(sams, ref_index, fg, batch))
+      return rc;
   printf("SHIM PASS keys=%llu labels=%llu records=%u data_bytes=%llu samples=%ld\n", (unsigned long long)n_keys,
          (unsigned long long)n_labels, batch.n_reads, (unsigned long long)recs.data.size(), reader.get_num_samples());
   return 0;

@@ -35,3 +35,25 @@ def test_shim_flattens_and_indexes_like_the_reference(kw):
         assert int(fields["keys"]) > 1000 and int(fields["records"]) > 100 and int(fields["samples"]) == kw["n_samples"]
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(EXE is None or oracle.ref_binary("bgzip") is None, reason="compiled reference not present")
+def test_shim_genotypes_like_the_reference_in_one_process():
+    """The drop-in, end to end: the reference's graph and records go through the shim and the C ABI to the GPU, and every
+    HapSample / per-bubble statistic that comes back equals what the reference's own genotype_only + VcfWriter loop produced
+    in the same process."""
+    kw = dict(length=8000, n_sites=160, n_samples=3, seed=21, coverage=12, err=0.01, n_rate=0.002, lowmapq_rate=0.1,
+              unpaired_rate=0.05, improper_rate=0.08, flip_rate=0.5)
+    tmp = tempfile.mkdtemp(prefix="gtb_shim_gpu_")
+    try:
+        ds = synth.make_dataset(**kw)
+        man = synth.write_dataset(ds, tmp, region_size=50000)
+        subprocess.run([oracle.ref_binary("bgzip"), "-f", "-k", man["vcf"]], check=True)
+        subprocess.run([oracle.ref_binary("tabix"), "-f", "-p", "vcf", man["vcf"] + ".gz"], check=True)
+        reg = man["regions"][0]
+        out = subprocess.run([EXE, man["fasta"], man["vcf"] + ".gz", f"{man['contig']}:{reg['begin']}-{reg['end']}",
+                              ",".join(reg["sams"]), "--gpu"], capture_output=True, text=True, cwd=tmp)
+        assert out.returncode == 0 and "SHIM GPU PASS" in out.stdout and "SHIM PASS" in out.stdout, out.stdout + out.stderr
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
