@@ -3123,11 +3123,17 @@ void launch_probe(const LaunchParams & p, void * stream)
     return;
   // one persistent block per SM (p.n_active is an upper bound; the exact count is read on the device); small batches
   // get fewer blocks so that a block still has a few hundred tasks to amortise staging its region's filter
-  static bool attr_set = false;
-  if (!attr_set)
   {
-    cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_WORDS * 4));
-    attr_set = true;
+    // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev])
+    {
+      cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_WORDS * 4));
+      if (dev >= 0 && dev < 64)
+        attr_set[dev] = true;
+    }
   }
   uint32_t const want = (p.n_active + 255) / 256;
   uint32_t const grid = std::max(1u, std::min(want, (uint32_t)sm_count()));
@@ -3155,6 +3161,18 @@ void launch_slow(const MultiLaunch & m, void * stream)
     return;
   size_t const smem = sizeof(SlowState) * WARPS_PER_BLOCK;
   uint32_t const grid = (uint32_t)(sm_count() * align_kernel_blocks_per_sm());
+  {
+    // > 48 KB of dynamic shared memory is a per-device opt-in (align_kernel_blocks_per_sm() sets it on the first device only)
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev])
+    {
+      cudaFuncSetAttribute(slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (dev >= 0 && dev < 64)
+        attr_set[dev] = true;
+    }
+  }
   slow_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(m);
   huge_kernel<<<(uint32_t)sm_count(), 32, 0, (cudaStream_t)stream>>>(m);
 }
