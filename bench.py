@@ -358,6 +358,7 @@ def main() -> None:
         for nm in kt:
             kt[nm].append(k[nm])
         n_slow = k["n_slow_tasks"]
+        chain_t = ctx.last_chain_timing()
     barrier()
     t_all = time.perf_counter() - t_all0
     clocks = sampler.stop()
@@ -390,7 +391,7 @@ def main() -> None:
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_t * 1e3},
             "gpu_launches": int(st.kernel_launches) * args.steps,
             "kernels_ms": {**{nm: float(np.mean(v)) for nm, v in kt.items()},
-                           "replay_call_wall_ms": float(np.mean(wall)) * 1e3, "slow_tasks": n_slow},
+                           "replay_call_wall_ms": float(np.mean(wall)) * 1e3, "slow_tasks": n_slow, "chain_tiers": chain_t},
             "region_setup_s": t_region,
             "e2e_incl_region_setup": {"value": total_reads / (e2e_t + t_region), "unit": "reads/s",
                                       "note": "index build + graph upload + H2D + kernels + D2H for the whole 1 Mb"},

@@ -151,9 +151,10 @@ struct BatchState
   DeviceBuffer d_scan_temp;
   size_t scan_temp_bytes = 0;
   cudaStream_t stream = nullptr;       // probe + chain of this chunk (chunks run concurrently, each on its own stream)
-  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  // ev: 0 h2d start (copy stream), 1 h2d done (copy stream), 2 kernels start, 3 after prep + probe, 4 after chain,
-  //     5 after the first score pass, 6 after the batch preparation (chunk stream), 7 after counters D2H (main stream)
+  cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // ev: 0 h2d start (copy stream), 1 h2d done (copy stream), 2 kernels start, 3 after prep + probe, 4 after both chain tiers,
+  //     5 after the first score pass, 6 after the batch preparation (chunk stream), 7 after counters D2H (main stream),
+  //     8 between chain_kernel and chain_general_kernel
   void release()
   {
     d_batch.release();
@@ -204,7 +205,9 @@ struct Ctx
   int connections = 0;   // gtb_set_connections: 0 off, otherwise table slots reserved per submitted record
   PinnedBuffer h_conn_state;
   float t_h2d = 0, t_align = 0, t_score = 0, t_d2h = 0, t_probe = 0, t_chain = 0, t_slow = 0, t_total = 0, t_prep = 0, t_score0 = 0, t_score1 = 0;
-  unsigned long long last_n_slow = 0;
+  unsigned long long last_n_slow = 0, last_n_gen = 0, last_n_active = 0, t0_reasons[16] = {0};
+  float t_chain_fast = 0;
+  int gen_lanes = 8; // chain_general_kernel: tasks per warp (GTB_GEN_LANES)
   // nccl (loaded lazily with dlopen, see gtb_nccl.cpp part below)
   void * nccl_lib = nullptr;
   void * nccl_comm = nullptr;
@@ -500,6 +503,8 @@ int gtb_create(int device_id, gtb_ctx ** out)
                                   (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range") +
                                   " (the compute path has no CPU fallback)");
     }
+    if (const char * gl = getenv("GTB_GEN_LANES"))
+      c->gen_lanes = std::max(1, std::min(32, atoi(gl)));
     e = cudaSetDevice(device_id);
     if (e == cudaSuccess)
       e = (cudaError_t)upload_hash_tables_kernels();
@@ -516,7 +521,7 @@ int gtb_create(int device_id, gtb_ctx ** out)
 
     for (int k = 0; k < MAX_CHUNKS; ++k)
     {
-      for (int i = 0; i < 8 && e == cudaSuccess; ++i)
+      for (int i = 0; i < 9 && e == cudaSuccess; ++i)
         e = cudaEventCreate(&c->bs[k].ev[i]);
       if (e == cudaSuccess)
         e = cudaStreamCreateWithFlags(&c->bs[k].stream, cudaStreamNonBlocking);
@@ -628,6 +633,11 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g, bool dev
     }
   }
   size_t const o_hap = place<uint16_t>(off, hap_span);
+  // allele number of every var node, and "last ref node at or before a position" per 16 positions (chain kernels)
+  size_t const o_var_num = place<uint8_t>(off, g->n_var);
+  uint32_t const pos_base = g->ref_order[0];
+  uint32_t const n_pos_bucket = ((g->ref_order[g->n_ref - 1] - pos_base) >> 4) + 1;
+  size_t const o_pos_bucket = place<uint32_t>(off, n_pos_bucket);
   // device index build: events + the sweep-order node table instead of a host-built index
   bool const have_ev = dev_index && g->var_ev_off && g->var_aev_off && g->var_ev && g->var_aev;
   size_t const n_ev = have_ev ? g->var_ev_off[g->n_var] : 0, n_aev = have_ev ? g->var_aev_off[g->n_var] : 0;
@@ -684,6 +694,21 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g, bool dev
     memset(tab, 0xFF, (size_t)hap_span * 2);
     for (uint32_t b = 0; b < R.n_bubbles; ++b)
       tab[R.bubble_order[b] - hap_base] = (uint16_t)b; // ascending b: on duplicate orders the last bubble wins, like id2hap
+  }
+  {
+    uint8_t * vn = h + o_var_num;
+    for (uint32_t r = 0; r + 1 < g->n_ref; ++r)
+      for (uint32_t v = g->ref_var_off[r]; v < g->ref_var_off[r + 1]; ++v)
+        vn[v] = (uint8_t)(v - g->ref_var_off[r]);
+    uint32_t * pb = reinterpret_cast<uint32_t *>(h + o_pos_bucket);
+    uint32_t r = 0;
+    for (uint32_t b = 0; b < n_pos_bucket; ++b)
+    {
+      uint32_t const pos = pos_base + 16u * b;
+      while (r + 1 < g->n_ref && g->ref_order[r + 1] <= pos)
+        ++r;
+      pb[b] = r;
+    }
   }
   uint32_t n_jobs = 0;
   if (dev_index)
@@ -760,6 +785,10 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g, bool dev
   D.hap_of_order = hap_span ? reinterpret_cast<const uint16_t *>(d + o_hap) : nullptr;
   D.hap_base = hap_base;
   D.hap_span = hap_span;
+  D.var_num = d + o_var_num;
+  D.pos_bucket = reinterpret_cast<const uint32_t *>(d + o_pos_bucket);
+  D.pos_base = pos_base;
+  D.n_pos_bucket = n_pos_bucket;
   D.score_off = reinterpret_cast<const uint32_t *>(d + o_score_off);
   D.cov_off = reinterpret_cast<const uint32_t *>(d + o_cov_off);
   D.table = reinterpret_cast<const IndexSlot *>(d + o_table);
@@ -1232,8 +1261,9 @@ static int launch_front(Ctx * c, BatchState & B, cudaEvent_t after)
   CUDA_TRY(cudaEventRecord(B.ev[6], s));
   launch_probe(P, s);
   CUDA_TRY(cudaEventRecord(B.ev[3], s));
-  launch_chain_order(P, s);
   launch_chain(P, s);
+  CUDA_TRY(cudaEventRecord(B.ev[8], s));
+  launch_chain_general(P, s);
   CUDA_TRY(cudaEventRecord(B.ev[4], s));
   // Several chunks: a first score pass right away for every record whose tasks chain_kernel finished (all but a few dozen
   // per 10^5), so that only the last chunk's pass is on the critical path; the rest waits for slow_kernel (second pass).
@@ -1300,8 +1330,11 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
   }
   if (record_h2d)
     c->t_h2d = 0;
-  c->t_align = c->t_prep = c->t_probe = c->t_chain = c->t_slow = c->t_score = c->t_d2h = 0;
-  c->last_n_slow = 0;
+  c->t_align = c->t_prep = c->t_probe = c->t_chain = c->t_chain_fast = c->t_slow = c->t_score = c->t_d2h = 0;
+  c->last_n_slow = c->last_n_gen = c->last_n_active = 0;
+  for (auto & q : c->t0_reasons)
+    q = 0;
+  auto kc_of = [](BatchState & B) { return static_cast<DevCounters const *>(B.h_counters.p); };
   gtb_submit_stats st{};
   unsigned long long n_overflow = 0, n_input_error = 0, reasons[12] = {0};
   uint32_t input_bits = 0;
@@ -1320,6 +1353,11 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     c->t_probe += t;
     cudaEventElapsedTime(&t, B.ev[3], B.ev[4]);
     c->t_chain += t;
+    cudaEventElapsedTime(&t, B.ev[3], B.ev[8]);
+    c->t_chain_fast += t;
+    c->last_n_gen += kc_of(B)->n_gen;
+    for (int q = 0; q < 16; ++q)
+      c->t0_reasons[q] += kc_of(B)->t0_reasons[q];
     cudaEventElapsedTime(&t, B.ev[4], B.ev[5]);
     c->t_score += t;
     DevCounters const * kc = static_cast<DevCounters *>(B.h_counters.p);
@@ -1340,6 +1378,7 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
         }
       }
     c->last_n_slow += kc->n_slow;
+    c->last_n_active += kc->n_active;
     st.n_records += B.P.batch.n_records;
     st.n_alignments += kc->n_units;
     st.n_oriented += kc->n_active;
@@ -1347,8 +1386,8 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     st.n_pairs_scored += kc->n_pairs_scored;
     st.n_singles_scored += kc->n_singles_scored;
     st.n_capacity_overflow += kc->n_overflow;
-    // prep_flags, scan, prep_fill, probe, chain (+ the two task-order kernels) (+ first score pass)
-    st.kernel_launches += B.P.batch.n_records ? 5 + (B.P.chain_order ? 2 : 0) + (c->n_chunks_last > 1 ? 1 : 0) : 0;
+    // prep_flags, scan, prep_fill, probe, chain, chain_general (+ first score pass)
+    st.kernel_launches += B.P.batch.n_records ? 6 + (c->n_chunks_last > 1 ? 1 : 0) : 0;
     st.kernel_launches += B.bam.n ? 7 : 0; // parse, seq, dup, radix sort (3 kernels at these sizes), mate
     n_overflow += kc->n_overflow;
     n_input_error += kc->n_input_error;
@@ -1578,11 +1617,8 @@ static int bind_chunk(Ctx * c, BatchState & B, ChunkLayout const & Lo, size_t to
   uint32_t const n_tasks = n_units * 2;
   if (int rc = B.d_seedrecs.reserve((size_t)n_active * SEED_REC_BYTES + 64))
     return rc;
-  // Heavy-first, class-by-class task order for chain_kernel (chain_order_kernels): measured on the bench workload and NOT a
-  // win (0.352 -> 0.373 ms incl. the two ordering kernels: warp time is dominated by memory latency of each thread's own
-  // dependent chain, not by divergence between label-count classes), so it is opt-in (GTB_CHAIN_SORT=1) for experiments.
-  static bool const chain_sort = []() { const char * e = getenv("GTB_CHAIN_SORT"); return e ? atoi(e) != 0 : false; }();
-  if (int rc = B.d_slow.reserve((size_t)n_active * 8 + 128 + total * 4 + (chain_sort ? (size_t)n_active * 5 + 64 : 0)))
+  // queues: slow_tasks | huge_tasks | deferred records | gen_tasks
+  if (int rc = B.d_slow.reserve((size_t)n_active * 12 + 256 + total * 4))
     return rc;
   if (int rc = B.d_summaries.reserve((size_t)n_tasks * (sizeof(TaskSummary) + 1) + 16))
     return rc;
@@ -1658,11 +1694,8 @@ static int bind_chunk(Ctx * c, BatchState & B, ChunkLayout const & Lo, size_t to
   P.slow_tasks = static_cast<uint32_t *>(B.d_slow.p);
   P.huge_tasks = P.slow_tasks + n_active + 16;
   P.deferred = P.huge_tasks + n_active + 16;
-  if (chain_sort && !with_tap) // (the debug taps address seed records by task position; keep the natural order there)
-  {
-    P.chain_order = P.deferred + total;
-    P.chain_bin = reinterpret_cast<uint8_t *>(P.chain_order + n_active + 8);
-  }
+  P.gen_tasks = P.deferred + total + 16;
+  P.gen_lanes = (uint32_t)c->gen_lanes;
   P.pending = reinterpret_cast<uint8_t *>(P.summaries + n_tasks);
   P.huge_states = c->d_huge.p;
   if (with_tap)
@@ -2068,6 +2101,26 @@ int gtb_last_prep_timing(gtb_ctx * ctx, float * prep_ms)
 
 // Diagnostic counters of the last submit/replay (chunk 0): out[0..11] = why chain_kernel handed tasks to slow_kernel
 // (refs vars paths locs labels cand_vars cands keys tap pool read_len probe-flag), out[12..23] = slow_kernel overflows.
+int gtb_last_chain_timing(gtb_ctx * ctx, float * fast_ms, float * general_ms, uint64_t * n_tasks, uint64_t * n_general,
+                          uint64_t * reasons16)
+{
+  Ctx * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c)
+    return fail(GTB_ERR_ARG, "null context");
+  if (fast_ms)
+    *fast_ms = c->t_chain_fast;
+  if (general_ms)
+    *general_ms = c->t_chain - c->t_chain_fast;
+  if (n_tasks)
+    *n_tasks = c->last_n_active;
+  if (n_general)
+    *n_general = c->last_n_gen;
+  if (reasons16)
+    for (int q = 0; q < 16; ++q)
+      reasons16[q] = c->t0_reasons[q];
+  return 0;
+}
+
 int gtb_debug_counters(gtb_ctx * ctx, uint64_t * out24)
 {
   auto * c = reinterpret_cast<Ctx *>(ctx);

@@ -36,10 +36,10 @@ constexpr int PROBE_WARPS = GTB_PROBE_WARPS; // warps per block of probe_kernel
 #define GTB_CHAIN_THREADS 128
 #endif
 #ifndef GTB_CHAIN_MIN_BLOCKS
-#define GTB_CHAIN_MIN_BLOCKS 8
+#define GTB_CHAIN_MIN_BLOCKS 4
 #endif
 constexpr int CHAIN_THREADS = GTB_CHAIN_THREADS;     // threads per block of chain_kernel
-constexpr int CHAIN_MIN_BLOCKS = GTB_CHAIN_MIN_BLOCKS; // 8 x 128 -> <= 64 registers per thread
+constexpr int CHAIN_MIN_BLOCKS = GTB_CHAIN_MIN_BLOCKS; // chain_kernel (fast tier): 4 x 128 threads x 364 B of shared memory per SM
 constexpr int MAX_TOUCH = 48; // bubbles touched by one read in the accumulate kernel (= HUGE_V)
 using allele_mask_t = uint32_t; // allele set of one bubble on a path: bit a = allele a  (<= 32 alleles per bubble)
 constexpr int MAX_ALLELES = 32;
@@ -121,6 +121,9 @@ struct DevRegion
   const uint32_t * bubble_order; // [n_bubbles] order of bubble b's var nodes (Genotype::id)
   const uint16_t * hap_of_order; // [hap_span] bubble index by (order - hap_base), 0xFFFF = none; nullptr = search bubble_order
   uint32_t hap_base, hap_span;
+  const uint8_t * var_num;       // [n_var] allele number of a var node within its bubble (graph.cpp:341-345)
+  const uint32_t * pos_bucket;   // [n_pos_bucket] last ref node whose order <= pos_base + 16 * bucket (0 when none): replaces the
+  uint32_t pos_base, n_pos_bucket; // binary search of Graph::get_locations_of_a_position by one load + a short scan
   const uint32_t * score_off;    // [n_bubbles+1]
   const uint32_t * cov_off;      // [n_bubbles+1]
   // index
@@ -209,9 +212,13 @@ struct DevCounters
   // written by the batch-preparation kernels (prep_*): alignment units and aligned read orientations of this chunk, and
   // what is wrong with the input (PREP_ERR_* bits)
   uint32_t n_units, n_active, input_bits, n_deferred;
-  // cost classes of the chain_kernel tasks (probe_kernel counts, chain_order_kernels turn them into a heavy-first task order)
-  uint32_t chain_bins[16], chain_cursor[16];
+  // chain_kernel (fast tier) -> chain_general_kernel: queue length, why (T0_* codes), and how many it finished itself
+  uint32_t n_gen, n_fast_done;
+  unsigned long long t0_reasons[16];
 };
+// why the fast tier handed a task to the general tier
+constexpr int T0_SV = 0, T0_LABELS = 1, T0_VARS = 2, T0_MULTI = 3, T0_SURVIVORS = 4, T0_NO_CHAIN = 5, T0_END_IN_BUBBLE = 6,
+              T0_WALK_CAP = 7, T0_WALK_MULTI = 8, T0_SPECIAL = 9, T0_POOL = 10;
 constexpr uint32_t PREP_ERR_SAMPLE = 1, PREP_ERR_DUP = 2, PREP_ERR_MATE = 4, PREP_ERR_LEN = 8, PREP_ERR_RECORD = 16,
                    PREP_ERR_COLLISION = 32;
 
@@ -306,8 +313,8 @@ struct LaunchParams
   uint8_t * pending;            // [n_units * 2] set by chain_kernel for tasks it hands to slow_kernel; never cleared by the
                                 // slower tiers, so the first score pass can read it while they run
   uint32_t * deferred;          // [n_records] records the first score pass left for the second (some task pending)
-  uint8_t * chain_bin;          // [n_active] cost class of each task (labels handed over by probe_kernel, capped at 15)
-  uint32_t * chain_order;       // [n_active] task positions, heaviest class first; nullptr = natural order
+  uint32_t * gen_tasks;         // [n_active] positions (in active_tasks) chain_kernel left for chain_general_kernel
+  uint32_t gen_lanes;           // chain_general_kernel: tasks per warp (1..32; fewer = less divergence serialisation)
   int filter_max_fold;          // probe_kernel: fold the presence bitmap into shared memory up to 2^this times (default
                                 // FILTER_MAX_FOLD; < 0 = always probe the global bitmap) -- GTB_PROBE_FILTER_FOLD, tests
   uint32_t defer;               // 1: score_kernel runs before slow_kernel and defers; 0: it runs after and scores everything
@@ -329,8 +336,8 @@ static_assert(sizeof(MultiLaunch) <= 4000, "MultiLaunch is passed as a kernel pa
 void launch_build_table(const IndexSlot * uniq, uint32_t n, IndexSlot * table, uint32_t mask, int shift, uint32_t * bitmap,
                         void * stream);
 void launch_probe(const LaunchParams & p, void * stream);
-void launch_chain(const LaunchParams & p, void * stream);
-void launch_chain_order(const LaunchParams & p, void * stream); // fills p.chain_order from p.chain_bin / counters->chain_bins
+void launch_chain(const LaunchParams & p, void * stream);         // fast tier, one thread per task
+void launch_chain_general(const LaunchParams & p, void * stream); // general tier over the queue chain_kernel filled
 void launch_slow(const MultiLaunch & m, void * stream);
 // first pass: every record of one chunk whose tasks are all computed by chain_kernel; records with a task still queued for
 // slow_kernel are listed in p.deferred.  Second pass (after slow_kernel / huge_kernel): the deferred records of all chunks.

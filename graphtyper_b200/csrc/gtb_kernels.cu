@@ -188,7 +188,7 @@ struct GR
   __device__ const uint8_t * var_dna(uint32_t v) const { return R.seq + R.var_seq_off[v]; }
   __device__ uint32_t ref_reach(uint32_t r) const { return R.ref_order[r] + ref_len(r) - 1; }
   __device__ uint32_t var_reach(uint32_t v) const { return R.var_order[v] + var_len(v) - 1; }
-  __device__ uint32_t variant_num(uint32_t v) const { return v - R.ref_var_off[R.var_out_ref[v] - 1]; }
+  __device__ uint32_t variant_num(uint32_t v) const { return R.var_num[v]; }
   __device__ uint32_t bubble_ref_reach(uint32_t v) const { return var_reach(R.ref_var_off[R.var_out_ref[v] - 1]); }
   __device__ bool is_special(uint32_t p) const { return p >= SPECIAL_START && (p - SPECIAL_START) < R.n_special; }
   __device__ uint32_t ref_reach_pos(uint32_t p) const { return is_special(p) ? R.ref_reach_poses[p - SPECIAL_START] : p; }
@@ -212,6 +212,31 @@ struct GR
     return R.sp_list[R.sp_off[lo] + idx];
   }
 };
+
+// last ref node whose order <= pos (callers make sure pos >= ref_order[0])
+__device__ __forceinline__ uint32_t last_ref_le(const DevRegion & R, uint32_t pos)
+{
+  if (R.pos_bucket)
+  {
+    uint32_t b = (pos - R.pos_base) >> 4;
+    if (b >= R.n_pos_bucket)
+      b = R.n_pos_bucket - 1;
+    uint32_t r = R.pos_bucket[b];
+    while (r + 1 < R.n_ref && R.ref_order[r + 1] <= pos)
+      ++r;
+    return r;
+  }
+  int lo = 1, hi = (int)R.n_ref;
+  while (lo < hi)
+  {
+    int const mid = (lo + hi) >> 1;
+    if (R.ref_order[mid] <= pos)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return (uint32_t)(lo - 1);
+}
 
 // ------------------------------------------------------------------------------------------------ phase A: seeds
 __device__ __forceinline__ uint32_t slot_of(const DevRegion & R, uint64_t key)
@@ -644,17 +669,7 @@ __device__ int get_locations(W & S, const GR & g, uint32_t pos, const typename W
     S.locs[0] = Loc{'R', 0u, R.ref_order[0], pos - R.ref_order[0]};
     return 1;
   }
-  // rr = last ref node whose order <= pos
-  int lo = 1, hi = (int)R.n_ref;
-  while (lo < hi)
-  {
-    int const mid = (lo + hi) >> 1;
-    if (R.ref_order[mid] <= pos)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  int rr = lo - 1;
+  int rr = (int)last_ref_le(R, pos); // last ref node whose order <= pos
   if (pos < R.ref_order[rr] + g.ref_len(rr))
   {
     if (!sp)
@@ -1630,12 +1645,9 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
   __shared__ uint2 s_refs[PROBE_BLOCK_WARPS][SEED_INLINE];
   __shared__ uint32_t s_hm[96];                        // hashes of the 96 neighbour masks
   __shared__ uint32_t s_seg_end;
-  __shared__ uint32_t s_bins[16];                            // cost classes of this block's tasks (see chain_order_kernels)
   int const lane = threadIdx.x & 31;
   int const wib = threadIdx.x >> 5;
   uint32_t const lt = (1u << lane) - 1u;
-  if (threadIdx.x < 16)
-    s_bins[threadIdx.x] = 0;
   uint16_t * cand = s_cand[wib];
   uint2 * refs = s_refs[wib];
   uint32_t const n_active = P.counters->n_active;
@@ -1956,77 +1968,575 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
       }
       if (!slow && lane < nrefs)
         out->refs[lane] = refs[lane];
-      if (P.chain_bin)
-      {
-        // cost class for chain_kernel's task order: labels handed over (tasks for slow_kernel cost chain_kernel nothing)
-        uint32_t const labels = __reduce_add_sync(FULL, (!slow && lane < nrefs) ? refs[lane].y : 0u);
-        if (lane == 0)
-        {
-          uint32_t const bin = slow ? 0u : min(labels, 15u);
-          P.chain_bin[t] = (uint8_t)bin;
-          atomicAdd(&s_bins[bin], 1u);
-        }
-      }
       __syncwarp();
     }
     seg = seg_end;
   }
-  __syncthreads();
-  if (P.chain_bin && threadIdx.x < 16 && s_bins[threadIdx.x])
-    atomicAdd(&P.counters->chain_bins[threadIdx.x], s_bins[threadIdx.x]);
 }
 
-// ================================================================================================ chain task order
-// chain_kernel runs one THREAD per task, and a warp takes as long as the union of its threads' control paths.  Tasks are
-// therefore issued heaviest cost class first and class by class: warps are (nearly) homogeneous, and the long tasks start
-// at once instead of at the end of the grid.  Counting sort: histogram (probe_kernel) -> bases -> scatter.
-__global__ void chain_order_bases_kernel(DevCounters * c)
+// ================================================================================================ chain kernel (fast tier)
+// One THREAD per active task, working set in registers + 364 bytes of shared memory -- no local memory.
+//
+// What makes a small working set enough: in add_next_kmer_labels (genotype_paths.cpp:294-352) every existing path evolves
+// on its own -- it is compared with the new label groups, replaced in place by its first successful merge, and only a
+// SECOND success or an unmatched group appends a new path.  Paths therefore form a forest rooted at unmatched groups, the
+// order of the survivors is the order of their roots, and remove_short_paths (alignment.cpp:68) keeps the paths of maximal
+// size only.  A path that chains all seed slots (read_start_index 0 .. read_end_index 31 * nslots) can only be rooted at a
+// group of slot 0 (exact list, then Hamming-1 list); as soon as one exists, everything rooted at a later slot is shorter
+// and is removed before the read ends are walked, whatever it did in between.  So the tier follows the slot-0 roots ONE AT
+// A TIME through the later slots (a path that would split in two hands the task to the general tier), keeps at most two
+// full chains, walks their common tail with the general tier's own labels_forward on a small shared-memory candidate list,
+// merges the walked labels back (a path only ever sees the groups of a list whose read_start_index equals its
+// read_end_index) and applies the filters of alignment.cpp:73-87 to the one or two paths that are left.  Everything it
+// cannot hold -- SV graphs, more than 8 seed labels, more than 4 bubbles on a path, a split, more than two full chains or
+// none, a chain end inside a bubble or at a special position, a walk beyond 4 candidates -- goes to chain_general_kernel
+// through a queue, which runs the unrestricted code on the compacted rest.
+namespace
 {
-  if (threadIdx.x == 0)
+constexpr int FT_LAB = 8, FT_V = 4, FT_SURV = 2;
+constexpr int FT_PATH_WORDS = 5 + 2 * FT_V;
+
+struct FPath // registers; loops over order[] / mask[] are fully unrolled
+{
+  uint32_t start, end, mm, nvar, re;
+  uint32_t order[FT_V], mask[FT_V];
+};
+
+__device__ __forceinline__ void fp_store(uint32_t * w, const FPath & p)
+{
+  w[0] = p.start;
+  w[1] = p.end;
+  w[2] = p.mm;
+  w[3] = p.nvar;
+  w[4] = p.re;
+#pragma unroll
+  for (int i = 0; i < FT_V; ++i)
   {
-    uint32_t base = 0;
-    for (int b = 15; b >= 0; --b)
-    {
-      c->chain_cursor[b] = base;
-      base += c->chain_bins[b];
-    }
+    w[5 + i] = p.order[i];
+    w[5 + FT_V + i] = p.mask[i];
   }
 }
 
-__global__ void __launch_bounds__(256) chain_order_scatter_kernel(LaunchParams P)
+__device__ __forceinline__ void fp_load(FPath & p, const uint32_t * w)
 {
-  uint32_t const t = blockIdx.x * blockDim.x + threadIdx.x;
-  bool const valid = t < P.counters->n_active;
-  uint32_t const bin = valid ? P.chain_bin[t] : 16u;
-  unsigned const peers = __match_any_sync(FULL, bin);
-  if (!valid)
-    return;
-  int const lane = threadIdx.x & 31;
-  int const leader = __ffs((int)peers) - 1;
-  uint32_t base = 0;
-  if (lane == leader)
-    base = atomicAdd(&P.counters->chain_cursor[bin], (uint32_t)__popc(peers));
-  base = __shfl_sync(peers, base, leader);
-  P.chain_order[base + __popc(peers & ((1u << lane) - 1u))] = t;
+  p.start = w[0];
+  p.end = w[1];
+  p.mm = w[2];
+  p.nvar = w[3];
+  p.re = w[4];
+#pragma unroll
+  for (int i = 0; i < FT_V; ++i)
+  {
+    p.order[i] = w[5 + i];
+    p.mask[i] = w[5 + FT_V + i];
+  }
 }
 
-void launch_chain_order(const LaunchParams & p, void * stream)
+// Path::merge_with_current for one label (path.cpp:105-129): OR into the bubble's allele set or append the bubble
+__device__ __forceinline__ bool fp_add_var(FPath & p, uint32_t order, uint32_t bit)
 {
-  if (p.n_active == 0 || !p.chain_order)
-    return;
-  chain_order_bases_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p.counters);
-  chain_order_scatter_kernel<<<(p.n_active + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+  bool found = false;
+#pragma unroll
+  for (int i = 0; i < FT_V; ++i)
+    if ((uint32_t)i < p.nvar && p.order[i] == order)
+    {
+      p.mask[i] |= bit;
+      found = true;
+    }
+  if (found)
+    return true;
+  if (p.nvar >= (uint32_t)FT_V)
+    return false;
+#pragma unroll
+  for (int i = 0; i < FT_V; ++i)
+    if ((uint32_t)i == p.nvar)
+    {
+      p.order[i] = order;
+      p.mask[i] = bit;
+    }
+  ++p.nvar;
+  return true;
 }
 
-// ================================================================================================ chain kernel
-// One THREAD per active task: phases B-D on a small per-thread working set (local memory).  Tasks that exceed a
-// small capacity, or that probe_kernel marked, are queued for slow_kernel.
+// Path(p1 = P, p2 = the group already in `out`) (path.cpp:38-82): 1 merged, 0 empty allele intersection, -1 too many bubbles
+__device__ __forceinline__ int fp_merge_into(const FPath & P, FPath & out)
+{
+#pragma unroll
+  for (int i = 0; i < FT_V; ++i)
+    if ((uint32_t)i < P.nvar)
+    {
+      bool found = false, empty = false;
+#pragma unroll
+      for (int j = 0; j < FT_V; ++j)
+        if ((uint32_t)j < out.nvar && out.order[j] == P.order[i])
+        {
+          out.mask[j] &= P.mask[i];
+          empty = empty || out.mask[j] == 0;
+          found = true;
+        }
+      if (empty)
+        return 0;
+      if (!found)
+      {
+        if (out.nvar >= (uint32_t)FT_V)
+          return -1;
+#pragma unroll
+        for (int j = 0; j < FT_V; ++j)
+          if ((uint32_t)j == out.nvar)
+          {
+            out.order[j] = P.order[i];
+            out.mask[j] = P.mask[i];
+          }
+        ++out.nvar;
+      }
+    }
+  out.start = P.start;
+  out.mm += P.mm;
+  return 1;
+}
+
+// candidate list / walked labels / decoded read tail of one task, in shared memory (interface of labels_forward)
+struct TinyWalk
+{
+  static constexpr int CAND_TOTAL = 4, CANDV = 3, WLCAP = 8;
+  struct Cand
+  {
+    uint32_t len, pos, mm, nvar;
+    uint32_t vars[CANDV];
+  };
+  Cand cands[CAND_TOTAL];
+  DevLabel wl[WLCAP];
+  uint32_t tail[10]; // IUPAC characters of read[tail0 ..), padded for ld4_state
+  uint32_t overflow;
+  int tail0;
+  __device__ __forceinline__ uint32_t rd4(int j) const { return ld4_state(reinterpret_cast<const uint8_t *>(tail), j - tail0); }
+  __device__ __forceinline__ Cand & cand_at(int i) { return cands[i]; }
+};
+constexpr int FT_LAB_WORDS = FT_LAB * 5;           // start, end, var, bubble order, allele number | list << 8
+constexpr int FT_SCRATCH_WORDS = 2 * SEED_INLINE;  // the task's bucket references, then one FPath during chaining
+constexpr int FT_UNION_WORDS = (int)(sizeof(TinyWalk) / 4) > FT_LAB_WORDS + FT_SCRATCH_WORDS ? (int)(sizeof(TinyWalk) / 4)
+                                                                                              : FT_LAB_WORDS + FT_SCRATCH_WORDS;
+constexpr int FT_WORDS = (FT_UNION_WORDS + FT_SURV * FT_PATH_WORDS) | 1; // odd stride: threads of a warp hit distinct banks
+static_assert(FT_SCRATCH_WORDS >= FT_PATH_WORDS, "scratch holds one FPath");
+static_assert(sizeof(TinyWalk) % 4 == 0, "TinyWalk is made of 32-bit words");
+
+} // namespace
+
 __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(LaunchParams P)
 {
-  uint32_t const gt = blockIdx.x * CHAIN_THREADS + threadIdx.x;
-  if (gt >= P.counters->n_active)
+  __shared__ uint32_t sm_all[CHAIN_THREADS * FT_WORDS];
+  uint32_t const t = blockIdx.x * CHAIN_THREADS + threadIdx.x;
+  if (t >= P.counters->n_active)
     return;
-  uint32_t const t = P.chain_order ? P.chain_order[gt] : gt; // heaviest cost class first (chain_order_kernels)
+  uint32_t const task = P.active_tasks[t];
+  const SeedRec * recp = reinterpret_cast<const SeedRec *>(P.seed_recs) + t;
+  uint4 const hdr = *reinterpret_cast<const uint4 *>(recp);
+  if ((hdr.z >> 8) & 1u)
+  {
+    atomicAdd(&P.counters->fast_reasons[11], 1ull); // marked by probe_kernel (IUPAC/N seed or > SEED_INLINE references)
+    push_slow(P, task);
+    return;
+  }
+  auto to_general = [&](int why) {
+    atomicAdd(&P.counters->t0_reasons[why], 1ull);
+    P.gen_tasks[atomicAdd(&P.counters->n_gen, 1u)] = t;
+  };
+  uint32_t const unit = task >> 1;
+  int const rec = P.batch.unit_record[unit];
+  const DevRegion & R = P.regions[P.batch.region[rec]];
+  int const L = P.batch.lseq[rec];
+  int const nslots = (int)(hdr.z & 0xFFu);
+  auto list_count = [&](int l) { return (int)(((l < 4 ? hdr.x : hdr.y) >> (8 * (l & 3))) & 0xFFu); };
+  if (P.tap.list_count)
+  {
+    uint16_t list_start[NLISTS + 1];
+    list_start[0] = 0;
+    for (int l = 0; l < NLISTS; ++l)
+      list_start[l + 1] = (uint16_t)(list_start[l] + list_count(l));
+    write_seed_tap(P, R, task, recp->refs, list_start, nslots);
+  }
+  if (R.is_sv)
+    return to_general(T0_SV);
+
+  uint32_t * const sm = sm_all + threadIdx.x * FT_WORDS;
+  uint32_t * const lab = sm;                      // [FT_LAB][5]
+  uint32_t * const scratch = sm + FT_LAB_WORDS;   // bucket references, later one FPath
+  uint32_t * const surv = sm + FT_UNION_WORDS;    // [FT_SURV][FT_PATH_WORDS]
+
+  // ---- stage: bucket references -> labels -> (bubble order, allele number) of every label, each step as independent loads
+  int nrefs = 0;
+#pragma unroll
+  for (int l = 0; l < NLISTS; ++l)
+    nrefs += list_count(l);
+  {
+    const uint4 * rp = reinterpret_cast<const uint4 *>(recp) + 1;
+#pragma unroll
+    for (int q = 0; q < SEED_INLINE / 2; ++q)
+      if (2 * q < nrefs)
+      {
+        uint4 const v = rp[q];
+        scratch[4 * q] = v.x;
+        scratch[4 * q + 1] = v.y;
+        scratch[4 * q + 2] = v.z;
+        scratch[4 * q + 3] = v.w;
+      }
+  }
+  int T = 0;
+  {
+    int l = 0, in_list = 0;
+    bool over = false;
+#pragma unroll
+    for (int k = 0; k < SEED_INLINE; ++k)
+      if (k < nrefs && !over)
+      {
+        while (in_list >= list_count(l)) // the list reference k belongs to
+        {
+          ++l;
+          in_list = 0;
+        }
+        ++in_list;
+        uint32_t const off = scratch[2 * k], cnt = scratch[2 * k + 1];
+        if (T + (int)cnt > FT_LAB)
+          over = true;
+        else
+          for (uint32_t q = 0; q < cnt; ++q, ++T)
+          {
+            DevLabel const lb = R.labels[off + q];
+            lab[5 * T] = lb.start;
+            lab[5 * T + 1] = lb.end;
+            lab[5 * T + 2] = lb.var;
+            lab[5 * T + 4] = (uint32_t)l << 8;
+          }
+      }
+    if (over)
+      return to_general(T0_LABELS);
+  }
+#pragma unroll
+  for (int j = 0; j < FT_LAB; ++j)
+    if (j < T)
+    {
+      uint32_t const v = lab[5 * j + 2];
+      if (v != INVALID)
+      {
+        lab[5 * j + 3] = R.var_order[v];
+        lab[5 * j + 4] |= R.var_num[v];
+      }
+    }
+  // "all k-mers extremely common" (alignment.cpp:35-49) cannot hold here: every exact list has fewer than 512 labels
+
+  // ---- chain the slot-0 roots through the later slots
+  auto lab_list = [&](int j) { return (int)(lab[5 * j + 4] >> 8); };
+  auto is_head = [&](int j) { // first label of its (start, end) group within its list (find_all_nonduplicated_paths)
+    int const l = lab_list(j);
+    for (int i = j - 1; i >= 0 && lab_list(i) == l; --i)
+      if (lab[5 * i] == lab[5 * j] && lab[5 * i + 1] == lab[5 * j + 1])
+        return false;
+    return true;
+  };
+  auto build_group = [&](int h, FPath & G) { // the group headed by label h; false: more than FT_V bubbles
+    int const l = lab_list(h);
+    G.start = lab[5 * h];
+    G.end = lab[5 * h + 1];
+    G.nvar = 0;
+    G.mm = (uint32_t)(l & 1);
+    G.re = (uint32_t)(31 * (l >> 1) + 31);
+#pragma unroll
+    for (int i = 0; i < FT_V; ++i)
+      G.order[i] = G.mask[i] = 0;
+    for (int j = h; j < T && lab_list(j) == l; ++j)
+      if (lab[5 * j] == G.start && lab[5 * j + 1] == G.end && lab[5 * j + 2] != INVALID)
+        if (!fp_add_var(G, lab[5 * j + 3], 1u << (lab[5 * j + 4] & 0xFFu)))
+          return false;
+    return true;
+  };
+  uint32_t const re_full = (uint32_t)(31 * nslots);
+  int ns = 0;
+  for (int h = 0; h < T && lab_list(h) < 2; ++h)
+  {
+    if (!is_head(h))
+      continue;
+    FPath Pth;
+    if (!build_group(h, Pth))
+      return to_general(T0_VARS);
+    for (int l = 2; l < 2 * nslots; ++l)
+    {
+      if (Pth.re != (uint32_t)(31 * (l >> 1)))
+        continue;
+      int nm = 0;
+      for (int j = 0; j < T; ++j)
+      {
+        if (lab_list(j) != l || lab[5 * j] != Pth.end || !is_head(j))
+          continue;
+        FPath M;
+        if (!build_group(j, M))
+          return to_general(T0_VARS);
+        int const r = fp_merge_into(Pth, M);
+        if (r < 0)
+          return to_general(T0_VARS);
+        if (r == 1)
+        {
+          if (nm == 0)
+            fp_store(scratch, M);
+          ++nm;
+        }
+      }
+      if (nm >= 2)
+        return to_general(T0_MULTI); // the path splits
+      if (nm == 1)
+        fp_load(Pth, scratch);
+    }
+    if (Pth.re == re_full)
+    {
+      if (ns == FT_SURV)
+        return to_general(T0_SURVIVORS);
+      fp_store(surv + ns * FT_PATH_WORDS, Pth);
+      ++ns;
+    }
+  }
+  if (ns == 0)
+    return to_general(T0_NO_CHAIN); // no full chain: shorter paths compete, the general tier sorts that out
+
+  // ---- walk_read_ends over the full chains (walk_read_starts has nothing to do: read_start_index is 0 everywhere)
+  GR g(R);
+  if (re_full != (uint32_t)(L - 1))
+  {
+    TinyWalk & W = *reinterpret_cast<TinyWalk *>(sm); // the labels are no longer needed
+    {
+      const uint8_t * s4 = P.batch.seq4 + (size_t)rec * GTB_SEQ_STRIDE;
+      int const orient = task & 1;
+      W.tail0 = (int)re_full;
+      uint32_t word = 0;
+      int n = 0;
+      for (int j = (int)re_full; j < L; ++j, ++n)
+      {
+        int const src = orient ? (L - 1 - j) : j;
+        uint8_t const b = __ldg(s4 + (src >> 1));
+        uint8_t c = (src & 1) ? (b & 15) : (b >> 4);
+        if (orient)
+          c = comp4(c);
+        word |= (uint32_t)iupac_char(c) << (8 * (n & 3));
+        if ((n & 3) == 3)
+        {
+          W.tail[n >> 2] = word;
+          word = 0;
+        }
+      }
+      W.tail[n >> 2] = word;
+      W.tail[(n >> 2) + 1] = 0;
+    }
+    uint32_t const klen = (uint32_t)L - re_full;
+    uint32_t best_mm = 7;
+    int nlists = 0, committed = 0;
+    int list_start[FT_SURV + 1];
+    list_start[0] = 0;
+    for (int pi = 0; pi < ns; ++pi)
+    {
+      uint32_t const endpos = surv[pi * FT_PATH_WORDS + 1];
+      if (g.is_special(endpos))
+        return to_general(T0_SPECIAL);
+      if (endpos < R.ref_order[0])
+        continue; // no location
+      uint32_t rr = 0;
+      if (R.n_ref > 1)
+      {
+        rr = last_ref_le(R, endpos);
+        if (endpos >= R.ref_order[rr] + g.ref_len(rr))
+          return to_general(T0_END_IN_BUBBLE);
+      }
+      Loc const loc{'R', rr, R.ref_order[rr], endpos - R.ref_order[rr]};
+      uint32_t const mm = min(2u + klen / 11u, best_mm);
+      uint32_t m2 = mm;
+      int t1 = committed;
+      W.overflow = 0;
+      labels_forward(W, g, loc, (int)re_full, klen, m2, t1);
+      if (W.overflow)
+        return to_general(T0_WALK_CAP);
+      if (t1 > committed)
+      {
+        // one location: its labels are the path's labels, at m2 <= mm mismatches
+        if (m2 < best_mm)
+        {
+          int const cnt = t1 - committed;
+          for (int k = 0; k < cnt; ++k)
+            W.wl[k] = W.wl[committed + k];
+          nlists = 1;
+          list_start[1] = cnt;
+          best_mm = m2;
+          committed = cnt;
+        }
+        else // m2 == best_mm
+        {
+          list_start[++nlists] = t1;
+          committed = t1;
+        }
+      }
+    }
+    // the walked labels of each list, grouped by (start, end), against every chain that still ends at the seed boundary
+    for (int l = 0; l < nlists; ++l)
+      for (int pi = 0; pi < ns; ++pi)
+      {
+        uint32_t * const pw = surv + pi * FT_PATH_WORDS;
+        if (pw[4] != re_full)
+          continue;
+        FPath Pth;
+        fp_load(Pth, pw);
+        int nm = 0;
+        for (int h = list_start[l]; h < list_start[l + 1]; ++h)
+        {
+          uint32_t const gs = W.wl[h].start, ge = W.wl[h].end;
+          bool head = true;
+          for (int i = list_start[l]; i < h; ++i)
+            head = head && !(W.wl[i].start == gs && W.wl[i].end == ge);
+          if (!head || gs != Pth.end)
+            continue;
+          FPath M;
+          M.start = gs;
+          M.end = ge;
+          M.nvar = 0;
+          M.mm = best_mm;
+          M.re = (uint32_t)(L - 1);
+#pragma unroll
+          for (int i = 0; i < FT_V; ++i)
+            M.order[i] = M.mask[i] = 0;
+          bool ok = true;
+          for (int j = h; j < list_start[l + 1]; ++j)
+            if (W.wl[j].start == gs && W.wl[j].end == ge && W.wl[j].var != INVALID)
+            {
+              uint32_t const v = W.wl[j].var;
+              ok = ok && fp_add_var(M, R.var_order[v], 1u << R.var_num[v]);
+            }
+          if (!ok)
+            return to_general(T0_VARS);
+          int const r = fp_merge_into(Pth, M);
+          if (r < 0)
+            return to_general(T0_VARS);
+          if (r == 1)
+          {
+            if (nm == 0)
+              fp_store(pw, M);
+            ++nm;
+          }
+        }
+        if (nm >= 2)
+          return to_general(T0_WALK_MULTI);
+      }
+  }
+
+  // ---- filters (alignment.cpp:73-87) over the one or two chains; unmatched walk groups became paths of at most 31 bases
+  //      and fall to the first remove_short_paths
+  FPath A, B;
+  fp_load(A, surv);
+  bool keepA = true, keepB = ns > 1;
+  if (keepB)
+    fp_load(B, surv + FT_PATH_WORDS);
+  else
+    B = A;
+  {
+    uint32_t const longest = max(A.re, keepB ? B.re : 0u); // read_start_index is 0: size = re + 1
+    keepA = A.re >= longest;
+    keepB = keepB && B.re >= longest;
+    uint32_t mn = 10; // remove_paths_with_too_many_mismatches (genotype_paths.cpp:360-380)
+    if (keepA)
+      mn = min(mn, A.mm);
+    if (keepB)
+      mn = min(mn, B.mm);
+    keepA = keepA && A.mm <= mn;
+    keepB = keepB && B.mm <= mn;
+    if (keepA && keepB)
+    {
+      // remove_non_ref_paths_when_read_matches_ref (genotype_paths.cpp:460-474) when !all_paths_unique (:219-231)
+      bool const uniq = !(g.ref_reach_pos(A.start) != g.ref_reach_pos(B.start) && g.ref_reach_pos(A.end) != g.ref_reach_pos(B.end));
+      if (!uniq)
+      {
+        bool refA = true, refB = true;
+#pragma unroll
+        for (int i = 0; i < FT_V; ++i)
+        {
+          refA = refA && !((uint32_t)i < A.nvar && (A.mask[i] & 1u) == 0);
+          refB = refB && !((uint32_t)i < B.nvar && (B.mask[i] & 1u) == 0);
+        }
+        if (refA || refB)
+        {
+          keepA = refA;
+          keepB = refB;
+        }
+      }
+    }
+    // (update_longest_path_size + remove_short_paths again: both chains already have the same size when both are left)
+  }
+  if (!keepA)
+  {
+    A = B;
+    keepA = keepB;
+    keepB = false;
+  }
+
+  // ---- result record (same layout as write_result)
+  TaskSummary sum;
+  sum.npaths = (uint16_t)((keepA ? 1 : 0) + (keepB ? 1 : 0));
+  sum.longest = 0;
+  sum.mm0 = 0;
+  sum.altcalls = 0;
+  sum.bits = TS_ALL_UNIQUE | TS_COMPUTED;
+  sum.pad = 0;
+  sum.path_off = task * INLINE_WORDS;
+  if (keepA)
+  {
+    sum.longest = (uint16_t)(A.re + 1);
+    sum.mm0 = (uint16_t)A.mm;
+    if (keepB && g.ref_reach_pos(A.start) != g.ref_reach_pos(B.start) && g.ref_reach_pos(A.end) != g.ref_reach_pos(B.end))
+      sum.bits &= ~TS_ALL_UNIQUE;
+    uint32_t alt = 0, words = PATH_HDR_WORDS + 2 * A.nvar + (keepB ? PATH_HDR_WORDS + 2 * B.nvar : 0u);
+#pragma unroll
+    for (int i = 0; i < FT_V; ++i)
+    {
+      alt += ((uint32_t)i < A.nvar && (A.mask[i] & 1u) == 0) ? 1u : 0u;
+      alt += (keepB && (uint32_t)i < B.nvar && (B.mask[i] & 1u) == 0) ? 1u : 0u;
+    }
+    sum.altcalls = (uint16_t)alt;
+    unsigned long long off = (unsigned long long)task * INLINE_WORDS;
+    if (words > (uint32_t)INLINE_WORDS)
+    {
+      off = (unsigned long long)P.batch.n_units * 2 * INLINE_WORDS + atomicAdd(&P.counters->path_words, (unsigned long long)words);
+      if (off + words > P.path_pool_cap)
+        return to_general(T0_POOL); // the general tier reports the exhausted pool
+    }
+    sum.path_off = (uint32_t)off;
+    uint32_t * w = P.path_pool + off;
+    auto put = [&](const FPath & p) {
+      *w++ = p.start;
+      *w++ = p.end;
+      *w++ = p.re << 16; // read_start_index 0
+      *w++ = p.mm | (p.nvar << 16);
+#pragma unroll
+      for (int i = 0; i < FT_V; ++i)
+        if ((uint32_t)i < p.nvar)
+        {
+          *w++ = p.order[i];
+          *w++ = p.mask[i];
+        }
+    };
+    put(A);
+    if (keepB)
+      put(B);
+  }
+  P.summaries[task] = sum;
+}
+
+// ================================================================================================ chain kernel (general tier)
+// The tasks chain_kernel queued, one THREAD per task: phases B-D on a per-thread working set in local memory (6 paths x 8
+// bubbles).  Only `gen_lanes` lanes of a warp take a task: a warp takes as long as the union of its lanes' control paths,
+// and the queue holds the irregular reads.  Tasks that exceed a capacity here are queued for slow_kernel.
+__global__ void __launch_bounds__(CHAIN_THREADS, 8) chain_general_kernel(LaunchParams P)
+{
+  uint32_t const lanes = P.gen_lanes;
+  uint32_t const lane = threadIdx.x & 31u;
+  if (lane >= lanes)
+    return;
+  uint32_t const gt = ((blockIdx.x * CHAIN_THREADS + threadIdx.x) >> 5) * lanes + lane;
+  if (gt >= P.counters->n_gen)
+    return;
+  uint32_t const t = P.gen_tasks[gt];
   uint32_t const task = P.active_tasks[t];
   const SeedRec * recp = reinterpret_cast<const SeedRec *>(P.seed_recs) + t;
   uint32_t const w2 = reinterpret_cast<const uint32_t *>(recp)[2];
@@ -2050,12 +2560,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(
         p[1] = now();
     }
   } timer(P.task_times ? P.task_times + 2 * (size_t)gt : nullptr);
-  if ((w2 >> 8) & 1u)
-  {
-    atomicAdd(&P.counters->fast_reasons[11], 1ull); // marked by probe_kernel (IUPAC/N seed or > SEED_INLINE references)
-    push_slow(P, task);
-    return;
-  }
   uint32_t const unit = task >> 1;
   int const rec = P.batch.unit_record[unit];
   const DevRegion & R = P.regions[P.batch.region[rec]];
@@ -2080,9 +2584,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(
       list_start[l + 1] = (uint16_t)(list_start[l] + c);
     }
   }
-  if (P.tap.list_count)
-    write_seed_tap(P, R, task, recp->refs, list_start, nslots);
-  run_task(S, g, recp->refs, list_start, nslots, S.L);
+  run_task(S, g, recp->refs, list_start, nslots, S.L); // (the seed tap was written by chain_kernel)
   if (S.overflow)
   {
     for (int q = 0; q < 12; ++q)
@@ -3149,6 +3651,19 @@ void launch_chain(const LaunchParams & p, void * stream)
     return;
   uint32_t const grid = (p.n_active + CHAIN_THREADS - 1) / CHAIN_THREADS;
   chain_kernel<<<grid, CHAIN_THREADS, 0, (cudaStream_t)stream>>>(p);
+}
+
+// Grid for the upper bound of queued tasks (the exact count is read on the device; blocks beyond it return at once).
+void launch_chain_general(const LaunchParams & p, void * stream)
+{
+  if (p.n_active == 0)
+    return;
+  uint32_t const lanes = std::max(1u, std::min(32u, p.gen_lanes));
+  uint32_t const warps = (p.n_active + lanes - 1) / lanes;
+  uint32_t const grid = (warps + CHAIN_THREADS / 32 - 1) / (CHAIN_THREADS / 32);
+  LaunchParams q = p;
+  q.gen_lanes = lanes;
+  chain_general_kernel<<<grid, CHAIN_THREADS, 0, (cudaStream_t)stream>>>(q);
 }
 
 // persistent grid (a multiple of the SM count); the number of queued tasks is read on the device

@@ -26,6 +26,7 @@ EXPORTS = [
     "gtb_sw_align_batch", "gtb_sw_last_timing", "gtb_sw_replay_last", "gtb_set_index_build",
     "gtb_set_connections", "gtb_connections_size", "gtb_connections", "gtb_phase_support", "gtb_last_prep_timing",
     "gtb_submit_bam_records", "gtb_submit_bam_records_multi", "gtb_debug_bam_columns", "gtb_merge_connections", "gtb_sample_depths",
+    "gtb_last_chain_timing",
 ]
 
 
@@ -92,6 +93,7 @@ def load_library() -> C.CDLL:
     L.gtb_sw_replay_last.argtypes = [vp]
     L.gtb_set_index_build.argtypes = [vp, C.c_int]
     L.gtb_last_prep_timing.argtypes = [vp, fp]
+    L.gtb_last_chain_timing.argtypes = [vp, fp, fp, abi.u64p, abi.u64p, abi.u64p]
     L.gtb_submit_bam_records.argtypes = [vp, C.c_int, C.POINTER(abi.BamBatch), C.POINTER(abi.SubmitStats)]
     L.gtb_submit_bam_records_multi.argtypes = [vp, C.c_int, abi.i32p, C.POINTER(abi.BamBatch), C.POINTER(abi.SubmitStats)]
     L.gtb_debug_bam_columns.argtypes = [vp, C.c_uint32, abi.u8p, abi.u16p, abi.u16p, abi.u8p, abi.i32p, abi.u8p, abi.u8p, abi.i32p,
@@ -310,6 +312,18 @@ class Context:
         self._check(self.lib.gtb_last_prep_timing(self.h, C.byref(p)))
         return {"prep_kernels": p.value, "probe_kernel": a.value, "chain_kernel": b.value, "slow_kernel": c.value,
                 "score_kernel": d.value, "n_slow_tasks": int(n.value)}
+
+    T0_REASONS = ["sv_graph", "labels>8", "bubbles>4", "path_splits", "chains>2", "no_full_chain", "end_in_bubble",
+                  "walk_capacity", "walk_splits", "special_pos", "path_pool"]
+
+    def last_chain_timing(self) -> Dict[str, object]:
+        """The two tiers of the chaining stage in the last submit/replay (gtb_last_chain_timing)."""
+        f, g = C.c_float(), C.c_float()
+        n, ng = C.c_uint64(), C.c_uint64()
+        r = np.zeros(16, dtype=np.uint64)
+        self._check(self.lib.gtb_last_chain_timing(self.h, C.byref(f), C.byref(g), C.byref(n), C.byref(ng), abi._ptr(r, abi.u64p)))
+        return {"chain_kernel": f.value, "chain_general_kernel": g.value, "tasks": int(n.value), "general_tasks": int(ng.value),
+                "general_reasons": {k: int(v) for k, v in zip(self.T0_REASONS, r) if v}}
 
     def pool_finish(self, region_id: int) -> abi.HostAccumulators:
         acc = self.alloc_accumulators(region_id)

@@ -223,6 +223,13 @@ int gtb_last_timing(gtb_ctx *ctx, float *h2d_ms, float *align_ms, float *score_m
  * time of the launch sequence when the submit was a single chunk. */
 int gtb_last_kernel_timing(gtb_ctx *ctx, float *probe_ms, float *chain_ms, float *slow_ms, float *score_ms,
                            uint64_t *n_slow);
+/* The two tiers of the chaining / end-extension stage in the last submit/replay: device time (ms) of chain_kernel (fast tier,
+ * one thread per read orientation, registers + shared memory) and of chain_general_kernel (the tasks the fast tier queued),
+ * the number of read orientations aligned, how many of them went to the general tier and why (reasons16: SV graph, > 8 seed
+ * labels, > 4 bubbles on a path, path splits, > 2 full chains, no full chain, chain end inside a bubble, walk capacity, walk
+ * splits, special position, path pool; the rest unused).  Any pointer may be NULL. */
+int gtb_last_chain_timing(gtb_ctx *ctx, float *fast_ms, float *general_ms, uint64_t *n_tasks, uint64_t *n_general,
+                          uint64_t *reasons16);
 /* Device time (ms) of the batch-preparation kernels of the last submit/replay: alignment units of the duplicate-read
  * shortcut (hts_parallel_reader.cpp:666-684), the orientations align_read aligns (alignment.cpp:343-360), link checks. */
 int gtb_last_prep_timing(gtb_ctx *ctx, float *prep_ms);
