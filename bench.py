@@ -329,7 +329,8 @@ def main() -> None:
     # ---- device-resident: replay the batch already in HBM, CUDA-event time of the kernels.  With nothing to copy there
     #      is nothing to overlap, so the batch is resident as ONE launch sequence (the e2e steps above use the library's
     #      automatic 2-chunk copy/compute pipeline).
-    ctx.set_chunks(1)
+    replay_chunks = env_int("GTB_BENCH_REPLAY_CHUNKS", 0)  # 0 = the library's automatic choice (4 concurrent chunks)
+    ctx.set_chunks(replay_chunks)
     reset()
     ctx.submit_multi(ids, batches)
     ctx.set_chunks(0)

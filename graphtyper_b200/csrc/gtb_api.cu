@@ -151,10 +151,12 @@ struct BatchState
   DeviceBuffer d_scan_temp;
   size_t scan_temp_bytes = 0;
   cudaStream_t stream = nullptr;       // probe + chain of this chunk (chunks run concurrently, each on its own stream)
-  cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t stream_gen = nullptr, stream_slow = nullptr; // chain_general_kernel / first slow_kernel launch beside the first score pass
+  cudaEvent_t ev[13] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // ev: 0 h2d start (copy stream), 1 h2d done (copy stream), 2 kernels start, 3 after prep + probe, 4 after both chain tiers,
   //     5 after the first score pass, 6 after the batch preparation (chunk stream), 7 after counters D2H (main stream),
-  //     8 between chain_kernel and chain_general_kernel
+  //     8 after chain_kernel; 9 / 10 around chain_general_kernel (stream_gen); 11 / 12 around the first slow_kernel launch
+  //     (stream_slow)
   void release()
   {
     d_batch.release();
@@ -174,6 +176,10 @@ struct BatchState
         cudaEventDestroy(e);
     if (stream)
       cudaStreamDestroy(stream);
+    if (stream_gen)
+      cudaStreamDestroy(stream_gen);
+    if (stream_slow)
+      cudaStreamDestroy(stream_slow);
   }
 };
 
@@ -521,10 +527,14 @@ int gtb_create(int device_id, gtb_ctx ** out)
 
     for (int k = 0; k < MAX_CHUNKS; ++k)
     {
-      for (int i = 0; i < 9 && e == cudaSuccess; ++i)
+      for (int i = 0; i < 13 && e == cudaSuccess; ++i)
         e = cudaEventCreate(&c->bs[k].ev[i]);
       if (e == cudaSuccess)
         e = cudaStreamCreateWithFlags(&c->bs[k].stream, cudaStreamNonBlocking);
+      if (e == cudaSuccess)
+        e = cudaStreamCreateWithFlags(&c->bs[k].stream_gen, cudaStreamNonBlocking);
+      if (e == cudaSuccess)
+        e = cudaStreamCreateWithFlags(&c->bs[k].stream_slow, cudaStreamNonBlocking);
     }
     for (int i = 0; i < 5 && e == cudaSuccess; ++i)
       e = cudaEventCreate(&c->ev_slow[i]);
@@ -1261,17 +1271,29 @@ static int launch_front(Ctx * c, BatchState & B, cudaEvent_t after)
   CUDA_TRY(cudaEventRecord(B.ev[6], s));
   launch_probe(P, s);
   CUDA_TRY(cudaEventRecord(B.ev[3], s));
+  // chain_kernel finishes ~95 % of the read orientations itself.  The rest runs beside the first score pass, on side
+  // streams: chain_general_kernel over the queue of irregular reads, and slow_kernel over the tasks probe_kernel marked
+  // (IUPAC / N seeds); both are long single-thread jobs that leave most issue slots free.  Records with a task in one of the
+  // queues (pending[], written by chain_kernel only) wait for the second score pass (launch_back).
+  P.defer = 1u;
   launch_chain(P, s);
   CUDA_TRY(cudaEventRecord(B.ev[8], s));
-  launch_chain_general(P, s);
-  CUDA_TRY(cudaEventRecord(B.ev[4], s));
-  // Several chunks: a first score pass right away for every record whose tasks chain_kernel finished (all but a few dozen
-  // per 10^5), so that only the last chunk's pass is on the critical path; the rest waits for slow_kernel (second pass).
-  // One chunk: nothing to overlap -- slow_kernel first, then ONE score pass over everything (launch_back).
-  P.defer = c->n_chunks_last > 1 ? 1u : 0u;
-  if (P.defer)
-    launch_score(P, B.with_conn, s);
+  CUDA_TRY(cudaStreamWaitEvent(B.stream_gen, B.ev[8], 0));
+  CUDA_TRY(cudaEventRecord(B.ev[9], B.stream_gen));
+  launch_chain_general(P, B.stream_gen);
+  CUDA_TRY(cudaEventRecord(B.ev[10], B.stream_gen));
+  CUDA_TRY(cudaStreamWaitEvent(B.stream_slow, B.ev[8], 0));
+  CUDA_TRY(cudaEventRecord(B.ev[11], B.stream_slow));
+  {
+    MultiLaunch M;
+    M.n = 1;
+    M.p[0] = P;
+    launch_slow(M, 0, B.stream_slow);
+  }
+  CUDA_TRY(cudaEventRecord(B.ev[12], B.stream_slow));
+  launch_score(P, B.with_conn, s);
   CUDA_TRY(cudaEventRecord(B.ev[5], s));
+  CUDA_TRY(cudaEventRecord(B.ev[4], s));
   return 0;
 }
 
@@ -1285,20 +1307,18 @@ static int launch_back(Ctx * c, int n_chunks)
   bool with_conn[MAX_CHUNKS];
   for (int k = 0; k < n_chunks; ++k)
   {
-    // after the chunk's first score pass, not beside it: slow_kernel's tasks are long single-lane jobs, and sharing the SM
-    // schedulers with a full score_kernel stretches them (measured 0.09 -> 0.17 ms; the score pass 0.07 -> 0.19 ms)
+    // the chunk's first score pass, its chain_general_kernel and its first slow_kernel launch
     CUDA_TRY(cudaStreamWaitEvent(ts, c->bs[k].ev[5], 0));
+    CUDA_TRY(cudaStreamWaitEvent(ts, c->bs[k].ev[10], 0));
+    CUDA_TRY(cudaStreamWaitEvent(ts, c->bs[k].ev[12], 0));
     M.p[k] = c->bs[k].P;
     with_conn[k] = c->bs[k].with_conn;
   }
   CUDA_TRY(cudaEventRecord(c->ev_slow[0], ts));
-  launch_slow(M, ts);
+  launch_slow(M, 1, ts); // what chain_general_kernel re-queued (normally nothing), then huge_kernel
   CUDA_TRY(cudaEventRecord(c->ev_slow[1], ts));
   CUDA_TRY(cudaEventRecord(c->ev_slow[4], ts));
-  if (n_chunks > 1)
-    launch_score_deferred(M, with_conn, ts); // second score pass: the records that waited for slow_kernel / huge_kernel
-  else
-    launch_score(c->bs[0].P, with_conn[0], ts);
+  launch_score_deferred(M, with_conn, ts); // second score pass: the records that waited for the slower tiers
   CUDA_TRY(cudaEventRecord(c->ev_slow[3], ts));
   for (int k = 0; k < n_chunks; ++k)
   {
@@ -1351,33 +1371,36 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     c->t_prep += t;
     cudaEventElapsedTime(&t, B.ev[6], B.ev[3]);
     c->t_probe += t;
-    cudaEventElapsedTime(&t, B.ev[3], B.ev[4]);
-    c->t_chain += t;
     cudaEventElapsedTime(&t, B.ev[3], B.ev[8]);
     c->t_chain_fast += t;
+    c->t_chain += t;
+    cudaEventElapsedTime(&t, B.ev[9], B.ev[10]);
+    c->t_chain += t; // (chain_general_kernel runs beside the first score pass)
+    cudaEventElapsedTime(&t, B.ev[11], B.ev[12]);
+    c->t_slow += t;
+    cudaEventElapsedTime(&t, B.ev[8], B.ev[5]);
+    c->t_score += t;
     c->last_n_gen += kc_of(B)->n_gen;
     for (int q = 0; q < 16; ++q)
       c->t0_reasons[q] += kc_of(B)->t0_reasons[q];
-    cudaEventElapsedTime(&t, B.ev[4], B.ev[5]);
-    c->t_score += t;
     DevCounters const * kc = static_cast<DevCounters *>(B.h_counters.p);
     if (B.P.task_times && k == 0)
       if (const char * fn = getenv("GTB_TASK_TIMES"))
       {
-        std::vector<unsigned long long> tt((size_t)kc->n_active * 2);
-        std::vector<uint32_t> at(kc->n_active);
+        std::vector<unsigned long long> tt((size_t)kc->n_gen * 2); // tasks of chain_general_kernel, in queue order
+        std::vector<uint32_t> at(kc->n_gen);
         cudaMemcpy(tt.data(), B.P.task_times, tt.size() * 8, cudaMemcpyDeviceToHost);
-        cudaMemcpy(at.data(), B.P.active_tasks, at.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(at.data(), B.P.gen_tasks, at.size() * 4, cudaMemcpyDeviceToHost);
         if (FILE * f = fopen(fn, "wb"))
         {
-          uint64_t const n = kc->n_active;
+          uint64_t const n = kc->n_gen;
           fwrite(&n, 8, 1, f);
           fwrite(tt.data(), 8, tt.size(), f);
           fwrite(at.data(), 4, at.size(), f);
           fclose(f);
         }
       }
-    c->last_n_slow += kc->n_slow;
+    c->last_n_slow += kc->n_slow + kc->n_slow2;
     c->last_n_active += kc->n_active;
     st.n_records += B.P.batch.n_records;
     st.n_alignments += kc->n_units;
@@ -1386,8 +1409,8 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     st.n_pairs_scored += kc->n_pairs_scored;
     st.n_singles_scored += kc->n_singles_scored;
     st.n_capacity_overflow += kc->n_overflow;
-    // prep_flags, scan, prep_fill, probe, chain, chain_general (+ first score pass)
-    st.kernel_launches += B.P.batch.n_records ? 6 + (c->n_chunks_last > 1 ? 1 : 0) : 0;
+    // prep_flags, scan, prep_fill, probe, chain, chain_general, slow (first launch), first score pass
+    st.kernel_launches += B.P.batch.n_records ? 8 : 0;
     st.kernel_launches += B.bam.n ? 7 : 0; // parse, seq, dup, radix sort (3 kernels at these sizes), mate
     n_overflow += kc->n_overflow;
     n_input_error += kc->n_input_error;
@@ -1397,7 +1420,7 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
   {
     float t = 0;
     cudaEventElapsedTime(&t, c->ev_slow[0], c->ev_slow[1]);
-    c->t_slow = t;
+    c->t_slow += t;
     c->t_score0 = c->t_score;
     cudaEventElapsedTime(&t, c->ev_slow[4], c->ev_slow[3]);
     c->t_score += t; // second pass
@@ -1408,7 +1431,7 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     c->t_total = t; // device span of the whole launch sequence (slow_kernel overlaps the first score pass)
     st.kernel_launches += st.n_records ? 3 : 0; // slow_kernel, huge_kernel, second score pass: once per submit
   }
-  c->t_align = c->t_prep + c->t_probe + c->t_chain;
+  c->t_align = c->t_prep + c->t_probe + c->t_chain_fast; // everything later overlaps: reported as one span (gtb_last_timing)
   if (stats)
     *stats = st;
   // input the batch-preparation kernels rejected (the offending links were cut / values replaced before the other kernels ran)
@@ -1615,10 +1638,10 @@ static int bind_chunk(Ctx * c, BatchState & B, ChunkLayout const & Lo, size_t to
   uint32_t const n_units = (uint32_t)total;
   uint32_t const n_active = (uint32_t)total * 2;
   uint32_t const n_tasks = n_units * 2;
-  if (int rc = B.d_seedrecs.reserve((size_t)n_active * SEED_REC_BYTES + 64))
+  if (int rc = B.d_seedrecs.reserve(align_up((size_t)n_active * SEED_REC_BYTES + 64) + (size_t)n_active * LAB_REC_BYTES))
     return rc;
-  // queues: slow_tasks | huge_tasks | deferred records | gen_tasks
-  if (int rc = B.d_slow.reserve((size_t)n_active * 12 + 256 + total * 4))
+  // queues: slow_tasks | huge_tasks | deferred records | gen_tasks | slow2_tasks
+  if (int rc = B.d_slow.reserve((size_t)n_active * 16 + 512 + total * 4))
     return rc;
   if (int rc = B.d_summaries.reserve((size_t)n_tasks * (sizeof(TaskSummary) + 1) + 16))
     return rc;
@@ -1665,6 +1688,7 @@ static int bind_chunk(Ctx * c, BatchState & B, ChunkLayout const & Lo, size_t to
   P.n_active = n_active;
   P.active_tasks = reinterpret_cast<const uint32_t *>(d + o_active);
   P.seed_recs = B.d_seedrecs.p;
+  P.lab_recs = static_cast<uint8_t *>(B.d_seedrecs.p) + align_up((size_t)n_active * SEED_REC_BYTES + 64);
   {
     PrepParams & Q = B.prep;
     memset(&Q, 0, sizeof(Q));
@@ -1695,6 +1719,7 @@ static int bind_chunk(Ctx * c, BatchState & B, ChunkLayout const & Lo, size_t to
   P.huge_tasks = P.slow_tasks + n_active + 16;
   P.deferred = P.huge_tasks + n_active + 16;
   P.gen_tasks = P.deferred + total + 16;
+  P.slow2_tasks = P.gen_tasks + n_active + 16;
   P.gen_lanes = (uint32_t)c->gen_lanes;
   P.pending = reinterpret_cast<uint8_t *>(P.summaries + n_tasks);
   P.huge_states = c->d_huge.p;

@@ -28,6 +28,12 @@ constexpr int HUGE_P = 512, HUGE_V = 48, HUGE_C = 640, HUGE_CV = 48, HUGE_WL = 2
 constexpr int FAST_P = 6, FAST_V = 8, FAST_C = 6, FAST_CV = 8, FAST_WL = 12, FAST_LOC = 4;
 constexpr int SEED_INLINE = 10;     // index bucket references handed from probe_kernel to chain_kernel per task
 constexpr int SEED_REC_BYTES = 16 + 8 * SEED_INLINE;
+// Label record handed from probe_kernel to chain_kernel (fast tier): 16-byte header {labels per list (4 bits each), number of
+// labels (0xFF: more than FT_LAB, the general tier's business) | nslots << 8 | needs-slow-kernel << 16, 0, 0}, then the seed
+// labels of all lists in PHIndex::multi_get order, 16 bytes each: start, end, bubble order, allele number | list << 8 |
+// has-variant << 16.
+constexpr int FT_LAB = 14;
+constexpr int LAB_REC_BYTES = 16 + 16 * FT_LAB;
 #ifndef GTB_PROBE_WARPS
 #define GTB_PROBE_WARPS 8
 #endif
@@ -36,7 +42,7 @@ constexpr int PROBE_WARPS = GTB_PROBE_WARPS; // warps per block of probe_kernel
 #define GTB_CHAIN_THREADS 128
 #endif
 #ifndef GTB_CHAIN_MIN_BLOCKS
-#define GTB_CHAIN_MIN_BLOCKS 4
+#define GTB_CHAIN_MIN_BLOCKS 5
 #endif
 constexpr int CHAIN_THREADS = GTB_CHAIN_THREADS;     // threads per block of chain_kernel
 constexpr int CHAIN_MIN_BLOCKS = GTB_CHAIN_MIN_BLOCKS; // chain_kernel (fast tier): 4 x 128 threads x 364 B of shared memory per SM
@@ -213,7 +219,7 @@ struct DevCounters
   // what is wrong with the input (PREP_ERR_* bits)
   uint32_t n_units, n_active, input_bits, n_deferred;
   // chain_kernel (fast tier) -> chain_general_kernel: queue length, why (T0_* codes), and how many it finished itself
-  uint32_t n_gen, n_fast_done;
+  uint32_t n_gen, n_slow2; // n_slow2: tasks chain_general_kernel queued for the second slow_kernel launch
   unsigned long long t0_reasons[16];
 };
 // why the fast tier handed a task to the general tier
@@ -307,7 +313,9 @@ struct LaunchParams
                                 // (align_read, alignment.cpp:331-363); the exact count is counters->n_active (prep kernels)
   const uint32_t * active_tasks; // [counters->n_active] task id = unit * 2 + orientation
   void * seed_recs;             // [n_active] SeedRec
-  uint32_t * slow_tasks;        // [n_active] queue filled by chain_kernel
+  void * lab_recs;              // [n_active] label records (LAB_REC_BYTES each)
+  uint32_t * slow_tasks;        // [n_active] queue filled by chain_kernel (tasks probe_kernel marked: IUPAC/N seeds, many references)
+  uint32_t * slow2_tasks;       // [n_active] queue filled by chain_general_kernel (capacity overflows)
   uint32_t * huge_tasks;        // [n_active] queue filled by slow_kernel
   void * huge_states;           // [SM count] HugeState slabs
   uint8_t * pending;            // [n_units * 2] set by chain_kernel for tasks it hands to slow_kernel; never cleared by the
@@ -338,7 +346,9 @@ void launch_build_table(const IndexSlot * uniq, uint32_t n, IndexSlot * table, u
 void launch_probe(const LaunchParams & p, void * stream);
 void launch_chain(const LaunchParams & p, void * stream);         // fast tier, one thread per task
 void launch_chain_general(const LaunchParams & p, void * stream); // general tier over the queue chain_kernel filled
-void launch_slow(const MultiLaunch & m, void * stream);
+// which = 0: the queues chain_kernel filled (slow_kernel only, beside chain_general_kernel); 1: the queues chain_general_kernel
+// filled, then huge_kernel over everything both slow_kernel launches re-queued
+void launch_slow(const MultiLaunch & m, int which, void * stream);
 // first pass: every record of one chunk whose tasks are all computed by chain_kernel; records with a task still queued for
 // slow_kernel are listed in p.deferred.  Second pass (after slow_kernel / huge_kernel): the deferred records of all chunks.
 void launch_score(const LaunchParams & p, bool with_connections, void * stream);

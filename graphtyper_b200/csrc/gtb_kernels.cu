@@ -29,6 +29,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
+#include <type_traits>
 
 #include "gtb_device.cuh"
 
@@ -1500,6 +1501,11 @@ __device__ __forceinline__ void push_slow(const LaunchParams & P, uint32_t task)
   unsigned long long const i = atomicAdd(&P.counters->n_slow, 1ull);
   P.slow_tasks[i] = task;
 }
+__device__ __forceinline__ void push_slow2(const LaunchParams & P, uint32_t task) // from chain_general_kernel
+{
+  P.pending[task] = 1;
+  P.slow2_tasks[atomicAdd(&P.counters->n_slow2, 1u)] = task;
+}
 } // namespace
 
 // ================================================================================================ batch preparation
@@ -1643,6 +1649,7 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
   __shared__ uint2 s_key[PROBE_BLOCK_WARPS][MAX_SLOTS];      // seed keys (lo, hi) of the task a warp works on
   __shared__ uint32_t s_kh[PROBE_BLOCK_WARPS][MAX_SLOTS];    // and their hashes
   __shared__ uint2 s_refs[PROBE_BLOCK_WARPS][SEED_INLINE];
+  __shared__ uint8_t s_reflist[PROBE_BLOCK_WARPS][SEED_INLINE + 2]; // seed list (slot * 2 + ham) of every reference
   __shared__ uint32_t s_hm[96];                        // hashes of the 96 neighbour masks
   __shared__ uint32_t s_seg_end;
   int const lane = threadIdx.x & 31;
@@ -1650,6 +1657,7 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
   uint32_t const lt = (1u << lane) - 1u;
   uint16_t * cand = s_cand[wib];
   uint2 * refs = s_refs[wib];
+  uint8_t * reflist = s_reflist[wib];
   uint32_t const n_active = P.counters->n_active;
   // Per lane, task-independent:
   //   hm[q]   hash of the XOR mask of this lane's q-th Hamming-1 neighbour: key index k = q*32 + lane flips base k/3 by (k%3 + 1)
@@ -1855,7 +1863,7 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
       // per-slot state while its neighbour hits are absorbed round by round
       uint32_t total = 0;
       bool dropped = false;
-      auto absorb = [&](bool hit, uint32_t off, uint32_t cnt) { // hit: this lane holds a found NEIGHBOUR of the current slot
+      auto absorb = [&](int i, bool hit, uint32_t off, uint32_t cnt) { // hit: this lane holds a found NEIGHBOUR of slot i
         unsigned const fm = __ballot_sync(FULL, hit);
         if (fm == 0 || dropped)
           return;
@@ -1874,15 +1882,21 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
         }
         int const pos = nrefs + __popc(fm & lt);
         if (hit && pos < SEED_INLINE)
+        {
           refs[pos] = make_uint2(off, cnt);
+          reflist[pos] = (uint8_t)(2 * i + 1);
+        }
         nrefs += __popc(fm);
         total += __shfl_sync(FULL, inc, 31);
       };
-      auto exact_hit = [&](uint32_t off, uint32_t cnt, int src_lane, uint32_t & c0) { // exact-match list: 1 key, never dropped
+      auto exact_hit = [&](int i, uint32_t off, uint32_t cnt, int src_lane, uint32_t & c0) { // exact-match list: 1 key, never dropped
         if (nrefs < SEED_INLINE)
         {
           if (lane == src_lane)
+          {
             refs[nrefs] = make_uint2(off, cnt);
+            reflist[nrefs] = (uint8_t)(2 * i);
+          }
         }
         else
           slow = true;
@@ -1916,11 +1930,11 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
           int const a = cstart[i];
           uint32_t c0 = 0;
           if (__shfl_sync(FULL, (int)found, a))
-            exact_hit(off, cnt, a, c0);
+            exact_hit(i, off, cnt, a, c0);
           int const before = nrefs;
           total = 0;
           dropped = false;
-          absorb(found && lane > a && lane < a + nc[i], off, cnt);
+          absorb(i, found && lane > a && lane < a + nc[i], off, cnt);
           close_slot(i, c0, before);
         }
       }
@@ -1945,12 +1959,12 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
             if (base == 0)
             {
               if (__shfl_sync(FULL, (int)found, 0))
-                exact_hit(off, cnt, 0, c0);
+                exact_hit(i, off, cnt, 0, c0);
               before = nrefs;
               if (lane == 0)
                 found = false;
             }
-            absorb(found, off, cnt);
+            absorb(i, found, off, cnt);
           }
           close_slot(i, c0, before);
         }
@@ -1968,6 +1982,42 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
       }
       if (!slow && lane < nrefs)
         out->refs[lane] = refs[lane];
+      // label record for chain_kernel: the labels themselves with the bubble order / allele number of their var node, one
+      // reference per lane (a bucket holds one or two labels)
+      {
+        uint4 * lrec = reinterpret_cast<uint4 *>(static_cast<uint8_t *>(P.lab_recs) + (size_t)t * LAB_REC_BYTES);
+        bool const mine = !slow && lane < nrefs;
+        uint2 const rf = mine ? refs[lane] : make_uint2(0u, 0u);
+        uint32_t const li = mine ? reflist[lane] : 0u;
+        uint32_t inc = rf.y;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) // references sit in lanes 0 .. SEED_INLINE - 1
+        {
+          uint32_t const tt = __shfl_up_sync(FULL, inc, d);
+          if (lane >= d)
+            inc += tt;
+        }
+        uint32_t const T = __shfl_sync(FULL, inc, SEED_INLINE - 1);
+        bool const fits = !slow && T <= (uint32_t)FT_LAB;
+        uint32_t const lcnt = __reduce_add_sync(FULL, fits ? rf.y << (4 * li) : 0u);
+        if (fits)
+        {
+          uint32_t o = inc - rf.y;
+          for (uint32_t q = 0; q < rf.y; ++q, ++o)
+          {
+            DevLabel const lb = R.labels[rf.x + q];
+            uint32_t order = 0, meta = li << 8;
+            if (lb.var != INVALID)
+            {
+              order = R.var_order[lb.var];
+              meta |= (uint32_t)R.var_num[lb.var] | (1u << 16);
+            }
+            lrec[1 + o] = make_uint4(lb.start, lb.end, order, meta);
+          }
+        }
+        if (lane == 0)
+          lrec[0] = make_uint4(lcnt, (fits ? T : 0xFFu) | ((uint32_t)nslots << 8) | ((slow ? 1u : 0u) << 16), 0u, 0u);
+      }
       __syncwarp();
     }
     seg = seg_end;
@@ -1993,14 +2043,25 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
 // through a queue, which runs the unrestricted code on the compacted rest.
 namespace
 {
-constexpr int FT_LAB = 8, FT_V = 4, FT_SURV = 2;
+constexpr int FT_V = 4, FT_SURV = 2;
 constexpr int FT_PATH_WORDS = 5 + 2 * FT_V;
 
-struct FPath // registers; loops over order[] / mask[] are fully unrolled
+struct FPath // registers: order[] / mask[] are only ever indexed with compile-time constants (for_v)
 {
   uint32_t start, end, mm, nvar, re;
   uint32_t order[FT_V], mask[FT_V];
 };
+
+// f(integral_constant<int, 0>) ... f(integral_constant<int, FT_V - 1>): the index is a constant in the source, so the
+// arrays are split into registers whatever the loop unroller decides
+template <int I = 0, class F>
+__device__ __forceinline__ void for_v(F && f)
+{
+  f(std::integral_constant<int, I>{});
+  if constexpr (I + 1 < FT_V)
+    for_v<I + 1>(f);
+}
+#define FT_I (decltype(ic)::value)
 
 __device__ __forceinline__ void fp_store(uint32_t * w, const FPath & p)
 {
@@ -2009,12 +2070,10 @@ __device__ __forceinline__ void fp_store(uint32_t * w, const FPath & p)
   w[2] = p.mm;
   w[3] = p.nvar;
   w[4] = p.re;
-#pragma unroll
-  for (int i = 0; i < FT_V; ++i)
-  {
-    w[5 + i] = p.order[i];
-    w[5 + FT_V + i] = p.mask[i];
-  }
+  for_v([&](auto ic) {
+    w[5 + FT_I] = p.order[FT_I];
+    w[5 + FT_V + FT_I] = p.mask[FT_I];
+  });
 }
 
 __device__ __forceinline__ void fp_load(FPath & p, const uint32_t * w)
@@ -2024,36 +2083,34 @@ __device__ __forceinline__ void fp_load(FPath & p, const uint32_t * w)
   p.mm = w[2];
   p.nvar = w[3];
   p.re = w[4];
-#pragma unroll
-  for (int i = 0; i < FT_V; ++i)
-  {
-    p.order[i] = w[5 + i];
-    p.mask[i] = w[5 + FT_V + i];
-  }
+  for_v([&](auto ic) {
+    p.order[FT_I] = w[5 + FT_I];
+    p.mask[FT_I] = w[5 + FT_V + FT_I];
+  });
 }
 
 // Path::merge_with_current for one label (path.cpp:105-129): OR into the bubble's allele set or append the bubble
 __device__ __forceinline__ bool fp_add_var(FPath & p, uint32_t order, uint32_t bit)
 {
   bool found = false;
-#pragma unroll
-  for (int i = 0; i < FT_V; ++i)
-    if ((uint32_t)i < p.nvar && p.order[i] == order)
+  for_v([&](auto ic) {
+    if ((uint32_t)FT_I < p.nvar && p.order[FT_I] == order)
     {
-      p.mask[i] |= bit;
+      p.mask[FT_I] |= bit;
       found = true;
     }
+  });
   if (found)
     return true;
   if (p.nvar >= (uint32_t)FT_V)
     return false;
-#pragma unroll
-  for (int i = 0; i < FT_V; ++i)
-    if ((uint32_t)i == p.nvar)
+  for_v([&](auto ic) {
+    if ((uint32_t)FT_I == p.nvar)
     {
-      p.order[i] = order;
-      p.mask[i] = bit;
+      p.order[FT_I] = order;
+      p.mask[FT_I] = bit;
     }
+  });
   ++p.nvar;
   return true;
 }
@@ -2061,44 +2118,63 @@ __device__ __forceinline__ bool fp_add_var(FPath & p, uint32_t order, uint32_t b
 // Path(p1 = P, p2 = the group already in `out`) (path.cpp:38-82): 1 merged, 0 empty allele intersection, -1 too many bubbles
 __device__ __forceinline__ int fp_merge_into(const FPath & P, FPath & out)
 {
-#pragma unroll
-  for (int i = 0; i < FT_V; ++i)
-    if ((uint32_t)i < P.nvar)
+  int status = 1;
+  if (out.nvar == 0) // the usual seed: no bubble inside the k-mer -- the merged path keeps P's bubbles
+  {
+    for_v([&](auto ic) {
+      out.order[FT_I] = P.order[FT_I];
+      out.mask[FT_I] = P.mask[FT_I];
+    });
+    out.nvar = P.nvar;
+  }
+  else if (P.nvar != 0)
+  for_v([&](auto ic) {
+    if ((uint32_t)FT_I < P.nvar && status == 1)
     {
+      uint32_t const po = P.order[FT_I], pm = P.mask[FT_I];
       bool found = false, empty = false;
-#pragma unroll
-      for (int j = 0; j < FT_V; ++j)
-        if ((uint32_t)j < out.nvar && out.order[j] == P.order[i])
+      for_v([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        if ((uint32_t)J < out.nvar && out.order[J] == po)
         {
-          out.mask[j] &= P.mask[i];
-          empty = empty || out.mask[j] == 0;
+          out.mask[J] &= pm;
+          empty = empty || out.mask[J] == 0;
           found = true;
         }
+      });
       if (empty)
-        return 0;
-      if (!found)
+        status = 0;
+      else if (!found)
       {
         if (out.nvar >= (uint32_t)FT_V)
-          return -1;
-#pragma unroll
-        for (int j = 0; j < FT_V; ++j)
-          if ((uint32_t)j == out.nvar)
-          {
-            out.order[j] = P.order[i];
-            out.mask[j] = P.mask[i];
-          }
-        ++out.nvar;
+          status = -1;
+        else
+        {
+          for_v([&](auto jc) {
+            constexpr int J = decltype(jc)::value;
+            if ((uint32_t)J == out.nvar)
+            {
+              out.order[J] = po;
+              out.mask[J] = pm;
+            }
+          });
+          ++out.nvar;
+        }
       }
     }
-  out.start = P.start;
-  out.mm += P.mm;
-  return 1;
+  });
+  if (status == 1)
+  {
+    out.start = P.start;
+    out.mm += P.mm;
+  }
+  return status;
 }
 
 // candidate list / walked labels / decoded read tail of one task, in shared memory (interface of labels_forward)
 struct TinyWalk
 {
-  static constexpr int CAND_TOTAL = 4, CANDV = 3, WLCAP = 8;
+  static constexpr int CAND_TOTAL = 4, CANDV = 3, WLCAP = 6;
   struct Cand
   {
     uint32_t len, pos, mm, nvar;
@@ -2106,32 +2182,64 @@ struct TinyWalk
   };
   Cand cands[CAND_TOTAL];
   DevLabel wl[WLCAP];
-  uint32_t tail[10]; // IUPAC characters of read[tail0 ..), padded for ld4_state
+  uint32_t tail[9]; // IUPAC characters of read[tail0 ..) (at most 31), padded for ld4_state
   uint32_t overflow;
   int tail0;
   __device__ __forceinline__ uint32_t rd4(int j) const { return ld4_state(reinterpret_cast<const uint8_t *>(tail), j - tail0); }
   __device__ __forceinline__ Cand & cand_at(int i) { return cands[i]; }
 };
-constexpr int FT_LAB_WORDS = FT_LAB * 5;           // start, end, var, bubble order, allele number | list << 8
-constexpr int FT_SCRATCH_WORDS = 2 * SEED_INLINE;  // the task's bucket references, then one FPath during chaining
-constexpr int FT_UNION_WORDS = (int)(sizeof(TinyWalk) / 4) > FT_LAB_WORDS + FT_SCRATCH_WORDS ? (int)(sizeof(TinyWalk) / 4)
-                                                                                              : FT_LAB_WORDS + FT_SCRATCH_WORDS;
+// per-thread shared memory: [ seed labels (4 words each, as probe_kernel wrote them) | later the TinyWalk ] [ full chains ]
+constexpr int FT_LAB_WORDS = FT_LAB * 4;
+constexpr int FT_UNION_WORDS = (int)(sizeof(TinyWalk) / 4) > FT_LAB_WORDS ? (int)(sizeof(TinyWalk) / 4) : FT_LAB_WORDS;
 constexpr int FT_WORDS = (FT_UNION_WORDS + FT_SURV * FT_PATH_WORDS) | 1; // odd stride: threads of a warp hit distinct banks
-static_assert(FT_SCRATCH_WORDS >= FT_PATH_WORDS, "scratch holds one FPath");
 static_assert(sizeof(TinyWalk) % 4 == 0, "TinyWalk is made of 32-bit words");
-
+static_assert(FT_LAB <= 15, "labels per list are counted in 4 bits");
+constexpr uint32_t LAB_HAS_VAR = 1u << 16;
+// seed labels of one task in shared memory, 4 words each (see FT_LAB_WORDS)
+__device__ __forceinline__ void group_init(FPath & G, const uint32_t * lab, int j, int l)
+{
+  G.start = lab[4 * j];
+  G.end = lab[4 * j + 1];
+  G.nvar = 0;
+  G.mm = (uint32_t)(l & 1);
+  G.re = (uint32_t)(31 * (l >> 1) + 31);
+  for_v([&](auto ic) { G.order[FT_I] = G.mask[FT_I] = 0; });
+}
+// Path::merge_with_current with label j; false: more than FT_V bubbles
+__device__ __forceinline__ bool group_add(FPath & G, const uint32_t * lab, int j)
+{
+  uint32_t const meta = lab[4 * j + 3];
+  return (meta & LAB_HAS_VAR) == 0 || fp_add_var(G, lab[4 * j + 2], 1u << (meta & 0xFFu));
+}
+// first label of its (start, end) group within its list [j0, ..) (find_all_nonduplicated_paths, genotype_paths.cpp:32-66)
+__device__ __forceinline__ bool is_head(const uint32_t * lab, int j, int j0)
+{
+  for (int i = j0; i < j; ++i)
+    if (lab[4 * i] == lab[4 * j] && lab[4 * i + 1] == lab[4 * j + 1])
+      return false;
+  return true;
+}
+// the whole group headed by label h of list l = [.., jend)
+__device__ __forceinline__ bool build_group(FPath & G, const uint32_t * lab, int h, int jend, int l)
+{
+  group_init(G, lab, h, l);
+  for (int j = h; j < jend; ++j)
+    if (lab[4 * j] == G.start && lab[4 * j + 1] == G.end && !group_add(G, lab, j))
+      return false;
+  return true;
+}
 } // namespace
 
 __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(LaunchParams P)
 {
-  __shared__ uint32_t sm_all[CHAIN_THREADS * FT_WORDS];
+  extern __shared__ __align__(16) uint32_t sm_all[]; // CHAIN_THREADS * FT_WORDS
   uint32_t const t = blockIdx.x * CHAIN_THREADS + threadIdx.x;
   if (t >= P.counters->n_active)
     return;
   uint32_t const task = P.active_tasks[t];
-  const SeedRec * recp = reinterpret_cast<const SeedRec *>(P.seed_recs) + t;
-  uint4 const hdr = *reinterpret_cast<const uint4 *>(recp);
-  if ((hdr.z >> 8) & 1u)
+  const uint4 * const lrec = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.lab_recs) + (size_t)t * LAB_REC_BYTES);
+  uint4 const hdr = lrec[0]; // labels per list (4 bits each) | number of labels, nslots, slow flag
+  if ((hdr.y >> 16) & 1u)
   {
     atomicAdd(&P.counters->fast_reasons[11], 1ull); // marked by probe_kernel (IUPAC/N seed or > SEED_INLINE references)
     push_slow(P, task);
@@ -2140,150 +2248,117 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(
   auto to_general = [&](int why) {
     atomicAdd(&P.counters->t0_reasons[why], 1ull);
     P.gen_tasks[atomicAdd(&P.counters->n_gen, 1u)] = t;
+    if (P.defer)
+      P.pending[task] = 1; // the first score pass runs beside chain_general_kernel and leaves this read's records alone
   };
   uint32_t const unit = task >> 1;
   int const rec = P.batch.unit_record[unit];
   const DevRegion & R = P.regions[P.batch.region[rec]];
   int const L = P.batch.lseq[rec];
-  int const nslots = (int)(hdr.z & 0xFFu);
-  auto list_count = [&](int l) { return (int)(((l < 4 ? hdr.x : hdr.y) >> (8 * (l & 3))) & 0xFFu); };
+  int const nslots = (int)((hdr.y >> 8) & 0xFFu);
   if (P.tap.list_count)
   {
+    const SeedRec * recp = reinterpret_cast<const SeedRec *>(P.seed_recs) + t;
+    uint32_t const c_lo = reinterpret_cast<const uint32_t *>(recp)[0], c_hi = reinterpret_cast<const uint32_t *>(recp)[1];
     uint16_t list_start[NLISTS + 1];
     list_start[0] = 0;
     for (int l = 0; l < NLISTS; ++l)
-      list_start[l + 1] = (uint16_t)(list_start[l] + list_count(l));
+      list_start[l + 1] = (uint16_t)(list_start[l] + (((l < 4 ? c_lo : c_hi) >> (8 * (l & 3))) & 0xFFu));
     write_seed_tap(P, R, task, recp->refs, list_start, nslots);
   }
   if (R.is_sv)
     return to_general(T0_SV);
+  int const T = (int)(hdr.y & 0xFFu);
+  if (T > FT_LAB)
+    return to_general(T0_LABELS);
 
   uint32_t * const sm = sm_all + threadIdx.x * FT_WORDS;
-  uint32_t * const lab = sm;                      // [FT_LAB][5]
-  uint32_t * const scratch = sm + FT_LAB_WORDS;   // bucket references, later one FPath
-  uint32_t * const surv = sm + FT_UNION_WORDS;    // [FT_SURV][FT_PATH_WORDS]
-
-  // ---- stage: bucket references -> labels -> (bubble order, allele number) of every label, each step as independent loads
-  int nrefs = 0;
-#pragma unroll
-  for (int l = 0; l < NLISTS; ++l)
-    nrefs += list_count(l);
-  {
-    const uint4 * rp = reinterpret_cast<const uint4 *>(recp) + 1;
-#pragma unroll
-    for (int q = 0; q < SEED_INLINE / 2; ++q)
-      if (2 * q < nrefs)
-      {
-        uint4 const v = rp[q];
-        scratch[4 * q] = v.x;
-        scratch[4 * q + 1] = v.y;
-        scratch[4 * q + 2] = v.z;
-        scratch[4 * q + 3] = v.w;
-      }
-  }
-  int T = 0;
-  {
-    int l = 0, in_list = 0;
-    bool over = false;
-#pragma unroll
-    for (int k = 0; k < SEED_INLINE; ++k)
-      if (k < nrefs && !over)
-      {
-        while (in_list >= list_count(l)) // the list reference k belongs to
-        {
-          ++l;
-          in_list = 0;
-        }
-        ++in_list;
-        uint32_t const off = scratch[2 * k], cnt = scratch[2 * k + 1];
-        if (T + (int)cnt > FT_LAB)
-          over = true;
-        else
-          for (uint32_t q = 0; q < cnt; ++q, ++T)
-          {
-            DevLabel const lb = R.labels[off + q];
-            lab[5 * T] = lb.start;
-            lab[5 * T + 1] = lb.end;
-            lab[5 * T + 2] = lb.var;
-            lab[5 * T + 4] = (uint32_t)l << 8;
-          }
-      }
-    if (over)
-      return to_general(T0_LABELS);
-  }
+  uint32_t * const lab = sm;                   // [FT_LAB][4]
+  uint32_t * const surv = sm + FT_UNION_WORDS; // [FT_SURV][FT_PATH_WORDS]
+  uint32_t const lcnt = hdr.x;
 #pragma unroll
   for (int j = 0; j < FT_LAB; ++j)
     if (j < T)
     {
-      uint32_t const v = lab[5 * j + 2];
-      if (v != INVALID)
-      {
-        lab[5 * j + 3] = R.var_order[v];
-        lab[5 * j + 4] |= R.var_num[v];
-      }
+      uint4 const v = lrec[1 + j];
+      lab[4 * j] = v.x;
+      lab[4 * j + 1] = v.y;
+      lab[4 * j + 2] = v.z;
+      lab[4 * j + 3] = v.w;
     }
   // "all k-mers extremely common" (alignment.cpp:35-49) cannot hold here: every exact list has fewer than 512 labels
 
   // ---- chain the slot-0 roots through the later slots
-  auto lab_list = [&](int j) { return (int)(lab[5 * j + 4] >> 8); };
-  auto is_head = [&](int j) { // first label of its (start, end) group within its list (find_all_nonduplicated_paths)
-    int const l = lab_list(j);
-    for (int i = j - 1; i >= 0 && lab_list(i) == l; --i)
-      if (lab[5 * i] == lab[5 * j] && lab[5 * i + 1] == lab[5 * j + 1])
-        return false;
-    return true;
-  };
-  auto build_group = [&](int h, FPath & G) { // the group headed by label h; false: more than FT_V bubbles
-    int const l = lab_list(h);
-    G.start = lab[5 * h];
-    G.end = lab[5 * h + 1];
-    G.nvar = 0;
-    G.mm = (uint32_t)(l & 1);
-    G.re = (uint32_t)(31 * (l >> 1) + 31);
-#pragma unroll
-    for (int i = 0; i < FT_V; ++i)
-      G.order[i] = G.mask[i] = 0;
-    for (int j = h; j < T && lab_list(j) == l; ++j)
-      if (lab[5 * j] == G.start && lab[5 * j + 1] == G.end && lab[5 * j + 2] != INVALID)
-        if (!fp_add_var(G, lab[5 * j + 3], 1u << (lab[5 * j + 4] & 0xFFu)))
-          return false;
-    return true;
-  };
+  auto lc = [&](int l) { return (int)((lcnt >> (4 * l)) & 15u); };
   uint32_t const re_full = (uint32_t)(31 * nslots);
+  int const n0 = lc(0), n01 = n0 + lc(1);
   int ns = 0;
-  for (int h = 0; h < T && lab_list(h) < 2; ++h)
+  for (int h = 0; h < n01; ++h)
   {
-    if (!is_head(h))
+    int const l0 = h < n0 ? 0 : 1, j00 = l0 ? n0 : 0, j01 = l0 ? n01 : n0;
+    if (!is_head(lab, h, j00))
       continue;
     FPath Pth;
-    if (!build_group(h, Pth))
+    if (!build_group(Pth, lab, h, j01, l0))
       return to_general(T0_VARS);
+    int j0 = n01;
     for (int l = 2; l < 2 * nslots; ++l)
     {
-      if (Pth.re != (uint32_t)(31 * (l >> 1)))
-        continue;
-      int nm = 0;
-      for (int j = 0; j < T; ++j)
+      int const cnt = lc(l), jend = j0 + cnt;
+      if (cnt != 0 && Pth.re == (uint32_t)(31 * (l >> 1)))
       {
-        if (lab_list(j) != l || lab[5 * j] != Pth.end || !is_head(j))
-          continue;
+        // the usual list holds one group that continues the path: collect it in one pass
         FPath M;
-        if (!build_group(j, M))
-          return to_general(T0_VARS);
-        int const r = fp_merge_into(Pth, M);
-        if (r < 0)
-          return to_general(T0_VARS);
-        if (r == 1)
+        bool found = false, other = false;
+        for (int j = j0; j < jend; ++j)
         {
-          if (nm == 0)
-            fp_store(scratch, M);
-          ++nm;
+          if (lab[4 * j] != Pth.end)
+            continue;
+          if (!found)
+          {
+            group_init(M, lab, j, l);
+            found = true;
+          }
+          else if (lab[4 * j + 1] != M.end)
+          {
+            other = true;
+            continue;
+          }
+          if (!group_add(M, lab, j))
+            return to_general(T0_VARS);
+        }
+        if (other)
+        {
+          // several candidate groups: every one is tried against the path as it was; a second success would split it
+          int nm = 0, hsel = -1;
+          for (int j = j0; j < jend; ++j)
+          {
+            if (lab[4 * j] != Pth.end || !is_head(lab, j, j0))
+              continue;
+            if (!build_group(M, lab, j, jend, l))
+              return to_general(T0_VARS);
+            int const r = fp_merge_into(Pth, M);
+            if (r < 0)
+              return to_general(T0_VARS);
+            if (r == 1 && nm++ == 0)
+              hsel = j;
+          }
+          if (nm >= 2)
+            return to_general(T0_MULTI);
+          found = nm == 1;
+          if (found)
+            build_group(M, lab, hsel, jend, l);
+        }
+        if (found)
+        {
+          int const r = fp_merge_into(Pth, M);
+          if (r < 0)
+            return to_general(T0_VARS);
+          if (r == 1)
+            Pth = M;
         }
       }
-      if (nm >= 2)
-        return to_general(T0_MULTI); // the path splits
-      if (nm == 1)
-        fp_load(Pth, scratch);
+      j0 = jend;
     }
     if (Pth.re == re_full)
     {
@@ -2329,45 +2404,104 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(
     int nlists = 0, committed = 0;
     int list_start[FT_SURV + 1];
     list_start[0] = 0;
+    bool first_in_ref = false;
     for (int pi = 0; pi < ns; ++pi)
     {
-      uint32_t const endpos = surv[pi * FT_PATH_WORDS + 1];
+      const uint32_t * const pw = surv + pi * FT_PATH_WORDS;
+      uint32_t const endpos = pw[1];
       if (g.is_special(endpos))
         return to_general(T0_SPECIAL);
       if (endpos < R.ref_order[0])
         continue; // no location
-      uint32_t rr = 0;
-      if (R.n_ref > 1)
+      // A second chain that ends at the same position inside a ref node walks the same tail from the same location under a
+      // budget that the first walk already lowered to its own result: it finds the same labels again (or nothing again), and
+      // a second list of the same groups changes no path -- whoever could merge with them already has.
+      if (pi > 0 && first_in_ref && endpos == surv[1])
+        continue;
+      // Graph::get_locations_of_a_position (graph.cpp:931-1029): the ref node holding the position, else every var node
+      // holding it that the path allows, bubble by bubble backwards (PADDING 1000); each location is walked as it is found
+      int rr = R.n_ref > 1 ? (int)last_ref_le(R, endpos) : 0;
+      bool const in_ref = R.n_ref == 1 || endpos < R.ref_order[rr] + g.ref_len(rr);
+      if (pi == 0)
+        first_in_ref = in_ref;
+      uint32_t v_it = in_ref ? 0u : R.ref_var_off[rr];
+      uint32_t mm = min(2u + klen / 11u, best_mm);
+      int const pend0 = committed;
+      int pend1 = committed;
+      for (;;) // iterative_dfs over the locations (graph.cpp:1703-1754)
       {
-        rr = last_ref_le(R, endpos);
-        if (endpos >= R.ref_order[rr] + g.ref_len(rr))
-          return to_general(T0_END_IN_BUBBLE);
-      }
-      Loc const loc{'R', rr, R.ref_order[rr], endpos - R.ref_order[rr]};
-      uint32_t const mm = min(2u + klen / 11u, best_mm);
-      uint32_t m2 = mm;
-      int t1 = committed;
-      W.overflow = 0;
-      labels_forward(W, g, loc, (int)re_full, klen, m2, t1);
-      if (W.overflow)
-        return to_general(T0_WALK_CAP);
-      if (t1 > committed)
-      {
-        // one location: its labels are the path's labels, at m2 <= mm mismatches
-        if (m2 < best_mm)
+        Loc loc;
+        if (in_ref)
+          loc = Loc{'R', (uint32_t)rr, R.ref_order[rr], endpos - R.ref_order[rr]};
+        else
         {
-          int const cnt = t1 - committed;
+          bool have = false;
+          while (rr >= 0 && (long long)g.ref_reach(rr) + 1000 > (long long)endpos && !have)
+          {
+            uint32_t const vb = R.ref_var_off[rr], ve = R.ref_var_off[rr + 1];
+            for (; v_it < ve && !have; ++v_it)
+            {
+              uint32_t const vo = R.var_order[v_it];
+              if (endpos < vo || endpos > g.var_reach(v_it))
+                continue;
+              uint32_t allowed = 0; // the path's allele set of this bubble (a bubble the path does not hold gives no location)
+              for (uint32_t k = 0; k < pw[3]; ++k)
+                if (pw[5 + k] == vo)
+                  allowed = pw[5 + FT_V + k];
+              if ((allowed >> (v_it - vb)) & 1u)
+              {
+                loc = Loc{'V', v_it, vo, endpos - vo};
+                have = true;
+              }
+            }
+            if (!have)
+            {
+              --rr;
+              if (rr >= 0)
+                v_it = R.ref_var_off[rr];
+            }
+          }
+          if (!have)
+            break;
+        }
+        uint32_t m2 = mm;
+        int t1 = pend1;
+        W.overflow = 0;
+        labels_forward(W, g, loc, (int)re_full, klen, m2, t1);
+        if (W.overflow)
+          return to_general(T0_WALK_CAP);
+        if (t1 > pend1)
+        {
+          if (m2 < mm)
+          {
+            mm = m2;
+            int const cnt = t1 - pend1;
+            for (int k = 0; k < cnt; ++k)
+              W.wl[pend0 + k] = W.wl[pend1 + k];
+            pend1 = pend0 + cnt;
+          }
+          else if (m2 == mm)
+            pend1 = t1;
+        }
+        if (in_ref)
+          break;
+      }
+      if (pend1 > pend0)
+      {
+        if (mm < best_mm)
+        {
+          int const cnt = pend1 - pend0;
           for (int k = 0; k < cnt; ++k)
-            W.wl[k] = W.wl[committed + k];
+            W.wl[k] = W.wl[pend0 + k];
           nlists = 1;
           list_start[1] = cnt;
-          best_mm = m2;
+          best_mm = mm;
           committed = cnt;
         }
-        else // m2 == best_mm
+        else if (mm == best_mm)
         {
-          list_start[++nlists] = t1;
-          committed = t1;
+          list_start[++nlists] = pend1;
+          committed = pend1;
         }
       }
     }
@@ -2395,9 +2529,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(
           M.nvar = 0;
           M.mm = best_mm;
           M.re = (uint32_t)(L - 1);
-#pragma unroll
-          for (int i = 0; i < FT_V; ++i)
-            M.order[i] = M.mask[i] = 0;
+          for_v([&](auto ic) { M.order[FT_I] = M.mask[FT_I] = 0; });
           bool ok = true;
           for (int j = h; j < list_start[l + 1]; ++j)
             if (W.wl[j].start == gs && W.wl[j].end == ge && W.wl[j].var != INVALID)
@@ -2427,10 +2559,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(
   FPath A, B;
   fp_load(A, surv);
   bool keepA = true, keepB = ns > 1;
-  if (keepB)
-    fp_load(B, surv + FT_PATH_WORDS);
-  else
-    B = A;
+  fp_load(B, surv + (keepB ? FT_PATH_WORDS : 0));
   {
     uint32_t const longest = max(A.re, keepB ? B.re : 0u); // read_start_index is 0: size = re + 1
     keepA = A.re >= longest;
@@ -2449,12 +2578,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(
       if (!uniq)
       {
         bool refA = true, refB = true;
-#pragma unroll
-        for (int i = 0; i < FT_V; ++i)
-        {
-          refA = refA && !((uint32_t)i < A.nvar && (A.mask[i] & 1u) == 0);
-          refB = refB && !((uint32_t)i < B.nvar && (B.mask[i] & 1u) == 0);
-        }
+        for_v([&](auto ic) {
+          refA = refA && !((uint32_t)FT_I < A.nvar && (A.mask[FT_I] & 1u) == 0);
+          refB = refB && !((uint32_t)FT_I < B.nvar && (B.mask[FT_I] & 1u) == 0);
+        });
         if (refA || refB)
         {
           keepA = refA;
@@ -2464,61 +2591,70 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_BLOCKS) chain_kernel(
     }
     // (update_longest_path_size + remove_short_paths again: both chains already have the same size when both are left)
   }
-  if (!keepA)
+  bool const two = keepA && keepB;
+  if (!keepA) // the first path left is path 0
   {
-    A = B;
-    keepA = keepB;
-    keepB = false;
+    A.start = B.start;
+    A.end = B.end;
+    A.mm = B.mm;
+    A.nvar = B.nvar;
+    A.re = B.re;
+    for_v([&](auto ic) {
+      A.order[FT_I] = B.order[FT_I];
+      A.mask[FT_I] = B.mask[FT_I];
+    });
   }
+  bool const any = keepA || keepB;
 
-  // ---- result record (same layout as write_result)
+  // ---- result record (same layout as write_result); two paths of at most 4 bubbles always fit the inline words
+  static_assert(FT_SURV * (PATH_HDR_WORDS + 2 * FT_V) <= INLINE_WORDS, "fast-tier results are inline");
   TaskSummary sum;
-  sum.npaths = (uint16_t)((keepA ? 1 : 0) + (keepB ? 1 : 0));
+  sum.npaths = (uint16_t)(two ? 2 : any ? 1 : 0);
   sum.longest = 0;
   sum.mm0 = 0;
   sum.altcalls = 0;
   sum.bits = TS_ALL_UNIQUE | TS_COMPUTED;
   sum.pad = 0;
   sum.path_off = task * INLINE_WORDS;
-  if (keepA)
+  if (any)
   {
     sum.longest = (uint16_t)(A.re + 1);
     sum.mm0 = (uint16_t)A.mm;
-    if (keepB && g.ref_reach_pos(A.start) != g.ref_reach_pos(B.start) && g.ref_reach_pos(A.end) != g.ref_reach_pos(B.end))
+    if (two && g.ref_reach_pos(A.start) != g.ref_reach_pos(B.start) && g.ref_reach_pos(A.end) != g.ref_reach_pos(B.end))
       sum.bits &= ~TS_ALL_UNIQUE;
-    uint32_t alt = 0, words = PATH_HDR_WORDS + 2 * A.nvar + (keepB ? PATH_HDR_WORDS + 2 * B.nvar : 0u);
-#pragma unroll
-    for (int i = 0; i < FT_V; ++i)
-    {
-      alt += ((uint32_t)i < A.nvar && (A.mask[i] & 1u) == 0) ? 1u : 0u;
-      alt += (keepB && (uint32_t)i < B.nvar && (B.mask[i] & 1u) == 0) ? 1u : 0u;
-    }
+    uint32_t alt = 0;
+    for_v([&](auto ic) {
+      alt += ((uint32_t)FT_I < A.nvar && (A.mask[FT_I] & 1u) == 0) ? 1u : 0u;
+      alt += (two && (uint32_t)FT_I < B.nvar && (B.mask[FT_I] & 1u) == 0) ? 1u : 0u;
+    });
     sum.altcalls = (uint16_t)alt;
-    unsigned long long off = (unsigned long long)task * INLINE_WORDS;
-    if (words > (uint32_t)INLINE_WORDS)
+    uint32_t * w = P.path_pool + (size_t)task * INLINE_WORDS;
+    w[0] = A.start;
+    w[1] = A.end;
+    w[2] = A.re << 16; // read_start_index 0
+    w[3] = A.mm | (A.nvar << 16);
+    for_v([&](auto ic) {
+      if ((uint32_t)FT_I < A.nvar)
+      {
+        w[4 + 2 * FT_I] = A.order[FT_I];
+        w[5 + 2 * FT_I] = A.mask[FT_I];
+      }
+    });
+    if (two)
     {
-      off = (unsigned long long)P.batch.n_units * 2 * INLINE_WORDS + atomicAdd(&P.counters->path_words, (unsigned long long)words);
-      if (off + words > P.path_pool_cap)
-        return to_general(T0_POOL); // the general tier reports the exhausted pool
-    }
-    sum.path_off = (uint32_t)off;
-    uint32_t * w = P.path_pool + off;
-    auto put = [&](const FPath & p) {
-      *w++ = p.start;
-      *w++ = p.end;
-      *w++ = p.re << 16; // read_start_index 0
-      *w++ = p.mm | (p.nvar << 16);
-#pragma unroll
-      for (int i = 0; i < FT_V; ++i)
-        if ((uint32_t)i < p.nvar)
+      w += PATH_HDR_WORDS + 2 * A.nvar;
+      w[0] = B.start;
+      w[1] = B.end;
+      w[2] = B.re << 16;
+      w[3] = B.mm | (B.nvar << 16);
+      for_v([&](auto ic) {
+        if ((uint32_t)FT_I < B.nvar)
         {
-          *w++ = p.order[i];
-          *w++ = p.mask[i];
+          w[4 + 2 * FT_I] = B.order[FT_I];
+          w[5 + 2 * FT_I] = B.mask[FT_I];
         }
-    };
-    put(A);
-    if (keepB)
-      put(B);
+      });
+    }
   }
   P.summaries[task] = sum;
 }
@@ -2590,7 +2726,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 8) chain_general_kernel(LaunchP
     for (int q = 0; q < 12; ++q)
       if ((S.overflow >> q) & 1u)
         atomicAdd(&P.counters->fast_reasons[q], 1ull);
-    push_slow(P, task);
+    push_slow2(P, task);
     return;
   }
   write_result(S, g, P, task, P.batch.n_units * 2);
@@ -2747,7 +2883,7 @@ __device__ void warp_tier(const LaunchParams & P, WST & S, int lane, uint32_t fi
 
 // The queues of all chunks of one submit are served by ONE launch: slow tasks are few (tens per 10^5 reads) and each is a
 // long single-lane job, so a launch costs the latency of its slowest task no matter how many chunks feed it.
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) slow_kernel(const __grid_constant__ MultiLaunch M)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) slow_kernel(const __grid_constant__ MultiLaunch M, int which)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SlowState * all = reinterpret_cast<SlowState *>(smem_raw);
@@ -2756,10 +2892,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) slow_kernel(const __grid
   uint32_t base = 0;
   for (int c = 0; c < M.n; ++c)
   {
-    uint32_t const n = (uint32_t)M.p[c].counters->n_slow;
+    uint32_t const n = which ? M.p[c].counters->n_slow2 : (uint32_t)M.p[c].counters->n_slow;
     if (n)
       warp_tier<SlowState, false>(M.p[c], all[wib], threadIdx.x & 31, (warp + total - base % total) % total, warp, total,
-                                  M.p[c].slow_tasks, n);
+                                  which ? M.p[c].slow2_tasks : M.p[c].slow_tasks, n);
     base += n;
   }
 }
@@ -3650,7 +3786,19 @@ void launch_chain(const LaunchParams & p, void * stream)
   if (p.n_active == 0)
     return;
   uint32_t const grid = (p.n_active + CHAIN_THREADS - 1) / CHAIN_THREADS;
-  chain_kernel<<<grid, CHAIN_THREADS, 0, (cudaStream_t)stream>>>(p);
+  size_t const smem = (size_t)CHAIN_THREADS * FT_WORDS * 4;
+  {
+    static bool attr_set[64] = {false}; // > 48 KB of dynamic shared memory is a per-device opt-in
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev])
+    {
+      cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (dev >= 0 && dev < 64)
+        attr_set[dev] = true;
+    }
+  }
+  chain_kernel<<<grid, CHAIN_THREADS, smem, (cudaStream_t)stream>>>(p);
 }
 
 // Grid for the upper bound of queued tasks (the exact count is read on the device; blocks beyond it return at once).
@@ -3667,7 +3815,7 @@ void launch_chain_general(const LaunchParams & p, void * stream)
 }
 
 // persistent grid (a multiple of the SM count); the number of queued tasks is read on the device
-void launch_slow(const MultiLaunch & m, void * stream)
+void launch_slow(const MultiLaunch & m, int which, void * stream)
 {
   bool any = false;
   for (int c = 0; c < m.n; ++c)
@@ -3688,8 +3836,9 @@ void launch_slow(const MultiLaunch & m, void * stream)
         attr_set[dev] = true;
     }
   }
-  slow_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(m);
-  huge_kernel<<<(uint32_t)sm_count(), 32, 0, (cudaStream_t)stream>>>(m);
+  slow_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(m, which);
+  if (which)
+    huge_kernel<<<(uint32_t)sm_count(), 32, 0, (cudaStream_t)stream>>>(m);
 }
 
 size_t huge_state_bytes() { return (size_t)sm_count() * sizeof(HugeState); }

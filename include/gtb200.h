@@ -219,8 +219,10 @@ int gtb_sample_depths(const gtb_accumulators *acc, uint16_t *ref_total_depth /*[
 int gtb_replay_last(gtb_ctx *ctx, gtb_submit_stats *stats);
 int gtb_last_timing(gtb_ctx *ctx, float *h2d_ms, float *align_ms, float *score_ms, float *d2h_ms);
 /* align_ms = batch preparation + probe_kernel + chain_kernel; score_ms = everything after chain_kernel measured as ONE span
- * (slow_kernel / huge_kernel run beside the first score pass, then the second pass), so align_ms + score_ms is the device
- * time of the launch sequence when the submit was a single chunk. */
+ * (chain_general_kernel and the first slow_kernel launch run beside the first score pass, then slow_kernel / huge_kernel for
+ * what they re-queued and the second score pass), so align_ms + score_ms is the device time of the launch sequence when the
+ * submit was a single chunk.  gtb_last_kernel_timing: chain_ms = both chain tiers, slow_ms = both slow launches + huge_kernel,
+ * score_ms = both score passes, each summed over the chunks although they overlap. */
 int gtb_last_kernel_timing(gtb_ctx *ctx, float *probe_ms, float *chain_ms, float *slow_ms, float *score_ms,
                            uint64_t *n_slow);
 /* The two tiers of the chaining / end-extension stage in the last submit/replay: device time (ms) of chain_kernel (fast tier,

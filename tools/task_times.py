@@ -1,5 +1,5 @@
-"""Per-task timeline of chain_kernel (profiling aid): GTB_TASK_TIMES=<file> makes the library dump start/end globaltimer
-values of every chain_kernel task of chunk 0; this script runs the bench workload once with 1 chunk and summarises."""
+"""Per-task timeline of chain_general_kernel (profiling aid): GTB_TASK_TIMES=<file> makes the library dump start/end globaltimer
+values of every chain_general_kernel task of chunk 0; this script runs the bench workload once with 1 chunk and summarises."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -27,10 +27,11 @@ dur = end - start
 print(f"tasks {n}; kernel span {end.max():.1f} us; task duration us: mean {dur.mean():.1f} median {np.median(dur):.1f} "
       f"p90 {np.percentile(dur, 90):.1f} p99 {np.percentile(dur, 99):.1f} max {dur.max():.1f}")
 print("start time us: p50 %.1f p90 %.1f max %.1f" % (np.median(start), np.percentile(start, 90), start.max()))
-w = n // 32
-wd = dur[:w * 32].reshape(w, 32)
+lanes = int(os.environ.get("GTB_GEN_LANES", 8))
+w = n // lanes
+wd = dur[:w * lanes].reshape(w, lanes)
 print("per warp: max-task mean %.1f, mean-task mean %.1f; warp end p50 %.1f p90 %.1f p99 %.1f max %.1f" % (
-    wd.max(1).mean(), wd.mean(1).mean(), *np.percentile(end[:w * 32].reshape(w, 32).max(1), [50, 90, 99, 100])))
+    wd.max(1).mean(), wd.mean(1).mean(), *np.percentile(end[:w * lanes].reshape(w, lanes).max(1), [50, 90, 99, 100])))
 hist, edges = np.histogram(end, bins=12)
 print("end-time histogram:", list(zip(np.round(edges[:-1]).astype(int), hist)))
 blk = n // 128
