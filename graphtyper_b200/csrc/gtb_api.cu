@@ -118,6 +118,7 @@ struct Region
   uint32_t depth_size = 0, reference_offset = 0; // SV graphs only
   int n_samples = 0;
   bool pool_open = false;
+  bool borrowed = false; // gtb_region_attach: graph + index arenas belong to another context
   // device
   DeviceBuffer arena;   // graph + index (host-built index) or graph only (device-built index)
   DeviceBuffer index_arena; // device-built index: labels + distinct k-mers + table + bitmap
@@ -199,7 +200,8 @@ struct Ctx
   // batch
   DeviceBuffer d_tap_counts, d_tap_pool, d_spill, d_huge;
   std::vector<DeviceBuffer> buffer_cache; // arenas / accumulators of ended regions, reused by the next regions
-  PinnedBuffer h_stage, h_accum, h_segments;
+  PinnedBuffer h_stage, h_accum, h_segments, h_varstats;
+  DeviceBuffer d_varstats;
   DeviceBuffer d_segments, d_gather;
   int segments_flip = 0;
   bool have_last = false;
@@ -579,6 +581,8 @@ void gtb_destroy(gtb_ctx * ctx)
     c->h_accum.release();
     c->h_conn_state.release();
     c->h_segments.release();
+    c->h_varstats.release();
+    c->d_varstats.release();
     c->d_segments.release();
     c->d_gather.release();
     for (DeviceBuffer * b : {&c->d_idx_small, &c->d_idx_jobs, &c->d_idx_keys, &c->d_idx_keys2, &c->d_idx_labels, &c->d_idx_idx,
@@ -1097,6 +1101,73 @@ int gtb_region_begin(gtb_ctx * ctx, int region_id, const gtb_graph_view * g)
   if (!ctx)
     return fail(GTB_ERR_ARG, "null ctx");
   return gtb_region_begin_multi(ctx, 1, &region_id, g);
+}
+
+// A region of another context on the same device, shared: graph, index and lookup tables stay the owner's (read-only from
+// here on), this context adds its own pool state (accumulators, connection table).  One pool thread = one context is the
+// reference's own threading model (paw::Station workers, src/typer/caller.cpp:272-391); with attached regions N pool threads
+// cost N sets of accumulators, not N copies of every region's graph + 8 MiB k-mer table.
+int gtb_region_attach(gtb_ctx * ctx, int region_id, gtb_ctx * owner, int owner_region_id)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  auto * o = reinterpret_cast<Ctx *>(owner);
+  if (!c || !o || c == o)
+    return fail(GTB_ERR_ARG, "gtb_region_attach needs two different contexts");
+  if (c->device < 0 || c->device != o->device)
+    return fail(GTB_ERR_ARG, "gtb_region_attach: both contexts must use the same CUDA device");
+  if (c->regions.count(region_id))
+    return fail(GTB_ERR_STATE, "region id already in use");
+  auto it = o->regions.find(owner_region_id);
+  if (it == o->regions.end())
+    return fail(GTB_ERR_STATE, "unknown region in the owner context");
+  Region const & S = *it->second;
+  auto R = std::make_unique<Region>();
+  R->id = region_id;
+  R->borrowed = true;
+  R->bubble_order = S.bubble_order;
+  R->n_alleles = S.n_alleles;
+  R->score_off = S.score_off;
+  R->cov_off = S.cov_off;
+  R->index = S.index; // host-built index (empty for a device-built one): gtb_index_size / gtb_index_export keep working
+  R->n_bubbles = S.n_bubbles;
+  R->depth_size = S.depth_size;
+  R->reference_offset = S.reference_offset;
+  R->dev_index = S.dev_index;
+  R->dev_n_keys = S.dev_n_keys;
+  R->dev_n_labels = S.dev_n_labels;
+  R->idx = S.idx;
+  R->dev = S.dev;
+  // the pool state is this context's own
+  R->dev.n_samples = 0;
+  R->dev.log_score = R->dev.gt_cov = R->dev.max_log_score = R->dev.amb = R->dev.amb_alt = R->dev.alt_pp = nullptr;
+  R->dev.vs_clipped_reads = R->dev.vs_mapq_squared = R->dev.pa_clipped_bp = R->dev.pa_mapq_squared = nullptr;
+  R->dev.pa_score_diff = R->dev.pa_mismatches = nullptr;
+  R->dev.read_strand = nullptr;
+  R->dev.ref_depth_delta = nullptr;
+  R->dev.conn_keys = nullptr;
+  R->dev.conn_vals = R->dev.conn_state = nullptr;
+  R->dev.conn_mask = 0;
+  cudaSetDevice(c->device);
+  CUDA_TRY(cudaStreamSynchronize(o->stream)); // the owner's upload + index build are complete
+  int slot = -1;
+  for (size_t k = 0; k < c->slot_region.size(); ++k)
+    if (c->slot_region[k] < 0)
+    {
+      slot = (int)k;
+      break;
+    }
+  if (slot < 0)
+  {
+    slot = (int)c->slot_region.size();
+    c->slot_region.push_back(-1);
+  }
+  if (slot > 0xFFFF)
+    return fail(GTB_ERR_CAPACITY, "more than 65536 resident regions");
+  c->slot_region[slot] = region_id;
+  R->slot = slot;
+  c->regions_dirty = true;
+  c->regions[region_id] = std::move(R);
+  return 0;
 }
 
 int gtb_region_end(gtb_ctx * ctx, int region_id)
@@ -3182,6 +3253,72 @@ int gtb_allreduce_accumulators_multi(gtb_ctx * ctx, int n, const int * region_id
 int gtb_allreduce_accumulators(gtb_ctx * ctx, int region_id, void * nccl_comm)
 {
   return gtb_allreduce_accumulators_multi(ctx, 1, &region_id, nccl_comm);
+}
+
+// Cross-pool merge of the per-bubble summaries over the ranks of a sample-sharded run = VarStats::add_stats
+// (src/typer/var_stats.cpp:141-189) as three collectives in ONE NCCL group: sum over every counter, max over
+// maximum_alt_support (column 8 of the allele rows) and over maximum_alt_support_ratio; n_max_alt_proper_pairs (column 3 of
+// the var rows) is summed as the reference's uint8 does.  The arrays may cover any number of regions back to back.
+int gtb_allreduce_varstats(gtb_ctx * ctx, uint64_t n_var_rows, uint64_t n_allele_rows, uint64_t * var, uint64_t * allele,
+                           double * ratio, void * nccl_comm)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !var || !allele || !ratio)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  if (c->device < 0)
+    return fail(GTB_ERR_CUDA, "host-only context");
+  void * comm = nccl_comm ? nccl_comm : c->nccl_comm;
+  if (!comm)
+    return fail(GTB_ERR_STATE, "no NCCL communicator (gtb_nccl_init)");
+  if (int rc = load_nccl())
+    return rc;
+  cudaSetDevice(c->device);
+  size_t const n_sum = (size_t)n_var_rows * 9 + (size_t)n_allele_rows * 13, n_max = (size_t)n_allele_rows;
+  size_t const bytes = (n_sum + 2 * n_max) * 8;
+  if (int rc = c->h_varstats.reserve(bytes))
+    return rc;
+  if (int rc = c->d_varstats.reserve(bytes))
+    return rc;
+  uint64_t * h = static_cast<uint64_t *>(c->h_varstats.p);
+  memcpy(h, var, (size_t)n_var_rows * 9 * 8);
+  memcpy(h + (size_t)n_var_rows * 9, allele, (size_t)n_allele_rows * 13 * 8);
+  uint64_t * hmax = h + n_sum;
+  double * hratio = reinterpret_cast<double *>(hmax + n_max);
+  for (size_t a = 0; a < n_max; ++a)
+  {
+    hmax[a] = allele[a * 13 + 8];
+    hratio[a] = ratio[a];
+  }
+  uint64_t * d = static_cast<uint64_t *>(c->d_varstats.p);
+  CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+  // ncclUint64 = 5, ncclFloat64 = 8, ncclSum = 0, ncclMax = 2
+  int r = g_nccl.GroupStart ? g_nccl.GroupStart() : 0;
+  if (r == 0 && n_sum)
+    r = g_nccl.AllReduce(d, d, n_sum, 5, 0, comm, c->stream);
+  if (r == 0 && n_max)
+    r = g_nccl.AllReduce(d + n_sum, d + n_sum, n_max, 5, 2, comm, c->stream);
+  if (r == 0 && n_max)
+    r = g_nccl.AllReduce(d + n_sum + n_max, d + n_sum + n_max, n_max, 8, 2, comm, c->stream);
+  if (g_nccl.GroupEnd)
+  {
+    int const r2 = g_nccl.GroupEnd();
+    if (r == 0)
+      r = r2;
+  }
+  if (r != 0)
+    return fail(GTB_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  CUDA_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  memcpy(var, h, (size_t)n_var_rows * 9 * 8);
+  memcpy(allele, h + (size_t)n_var_rows * 9, (size_t)n_allele_rows * 13 * 8);
+  for (size_t b = 0; b < n_var_rows; ++b)
+    var[b * 9 + 3] &= 0xFFu;
+  for (size_t a = 0; a < n_max; ++a)
+  {
+    allele[a * 13 + 8] = hmax[a];
+    ratio[a] = hratio[a];
+  }
+  return 0;
 }
 
 

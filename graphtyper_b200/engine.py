@@ -26,7 +26,7 @@ EXPORTS = [
     "gtb_sw_align_batch", "gtb_sw_last_timing", "gtb_sw_replay_last", "gtb_set_index_build",
     "gtb_set_connections", "gtb_connections_size", "gtb_connections", "gtb_phase_support", "gtb_last_prep_timing",
     "gtb_submit_bam_records", "gtb_submit_bam_records_multi", "gtb_debug_bam_columns", "gtb_merge_connections", "gtb_sample_depths",
-    "gtb_last_chain_timing",
+    "gtb_last_chain_timing", "gtb_region_attach", "gtb_allreduce_varstats",
 ]
 
 
@@ -56,6 +56,7 @@ def load_library() -> C.CDLL:
     L.gtb_region_begin.argtypes = [vp, C.c_int, C.POINTER(abi.GraphView)]
     L.gtb_region_begin_multi.argtypes = [vp, C.c_int, abi.i32p, C.POINTER(abi.GraphView)]
     L.gtb_region_end.argtypes = [vp, C.c_int]
+    L.gtb_region_attach.argtypes = [vp, C.c_int, vp, C.c_int]
     L.gtb_index_size.argtypes = [vp, C.c_int, abi.u64p, abi.u64p]
     L.gtb_index_export.argtypes = [vp, C.c_int, abi.u64p, abi.u32p, C.POINTER(abi.Label)]
     L.gtb_pool_begin.argtypes = [vp, C.c_int, C.c_int]
@@ -88,6 +89,7 @@ def load_library() -> C.CDLL:
     L.gtb_allreduce_accumulators.argtypes = [vp, C.c_int, vp]
     L.gtb_allreduce_accumulators_multi.argtypes = [vp, C.c_int, abi.i32p, vp]
     L.gtb_debug_counters.argtypes = [vp, abi.u64p]
+    L.gtb_allreduce_varstats.argtypes = [vp, C.c_uint64, C.c_uint64, abi.u64p, abi.u64p, C.POINTER(C.c_double), vp]
     L.gtb_sw_align_batch.argtypes = [vp, C.c_int, abi.u8p, abi.i32p, abi.u8p, abi.i32p, C.c_void_p]
     L.gtb_sw_last_timing.argtypes = [vp, fp, fp, fp]
     L.gtb_sw_replay_last.argtypes = [vp]
@@ -193,6 +195,12 @@ class Context:
         self._check(self.lib.gtb_region_begin_multi(self.h, n, ids, arr))
         for r, g in zip(region_ids, graphs):
             self._graphs[r] = g
+
+    def region_attach(self, region_id: int, owner: "Context", owner_region_id: int) -> None:
+        """Shares graph + index of a region another context (same device) built; pools stay per context (one context per
+        pool thread, gtb_region_attach)."""
+        self._check(self.lib.gtb_region_attach(self.h, region_id, owner.h, owner_region_id))
+        self._graphs[region_id] = owner._graphs[owner_region_id]
 
     def region_end(self, region_id: int) -> None:
         self._check(self.lib.gtb_region_end(self.h, region_id))
@@ -416,7 +424,21 @@ class Context:
                                             allele.ctypes.data_as(abi.u64p), ratio.ctypes.data_as(C.POINTER(C.c_double))))
         return var, allele, ratio
 
+    def merge_varstats(self, var, allele, ratio, var_src, allele_src, ratio_src) -> None:
+        """Cross-pool merge VarStats::add_stats of (var_src, allele_src, ratio_src) into (var, allele, ratio), in place."""
+        dp = C.POINTER(C.c_double)
+        self._check(self.lib.gtb_merge_varstats(len(var) // 9, len(ratio), var.ctypes.data_as(abi.u64p),
+                                                allele.ctypes.data_as(abi.u64p), ratio.ctypes.data_as(dp),
+                                                var_src.ctypes.data_as(abi.u64p), allele_src.ctypes.data_as(abi.u64p),
+                                                ratio_src.ctypes.data_as(dp)))
+
     # -- multi-GPU
+    def allreduce_varstats(self, var: np.ndarray, allele: np.ndarray, ratio: np.ndarray) -> None:
+        """VarStats::add_stats over the ranks (sample-sharded runs), in place; rows of any number of regions back to back."""
+        self._check(self.lib.gtb_allreduce_varstats(self.h, len(var) // 9, len(ratio), var.ctypes.data_as(abi.u64p),
+                                                    allele.ctypes.data_as(abi.u64p),
+                                                    ratio.ctypes.data_as(C.POINTER(C.c_double)), None))
+
     def nccl_unique_id(self) -> np.ndarray:
         buf = np.zeros(128, np.uint8)
         self._check(self.lib.gtb_nccl_unique_id(buf.ctypes.data_as(abi.u8p)))

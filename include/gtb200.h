@@ -169,6 +169,14 @@ int gtb_region_begin(gtb_ctx *ctx, int region_id, const gtb_graph_view *graph);
  * the builds run in parallel threads and the uploads follow). */
 int gtb_region_begin_multi(gtb_ctx *ctx, int n, const int *region_ids, const gtb_graph_view *graphs);
 int gtb_region_end(gtb_ctx *ctx, int region_id);
+/* Threading: a context serves ONE host thread at a time; different contexts may be used from different threads concurrently
+ * (own CUDA streams and buffers each).  This is the reference's model -- one pool per worker thread, no locks on the hot
+ * path (paw::Station in src/typer/caller.cpp:272-391; SURVEY.md section 8b "Threading") -- and the index is shared by all
+ * pool threads by const pointer (PHIndex const *, include/graphtyper/utilities/hts_parallel_reader.hpp:69-82):
+ * gtb_region_attach makes region `owner_region_id` of `owner` (same device) usable in `ctx` as `region_id` WITHOUT copying
+ * graph or index; pools (gtb_pool_begin ... gtb_pool_finish) are per context.  The owner must keep the region alive and must
+ * not end it while it is attached elsewhere; gtb_region_end(ctx, region_id) detaches. */
+int gtb_region_attach(gtb_ctx *ctx, int region_id, gtb_ctx *owner, int owner_region_id);
 
 /* Index inspection (parity with PHIndex contents): keys ascending, labels in bucket order. */
 int gtb_index_size(gtb_ctx *ctx, int region_id, uint64_t *n_keys, uint64_t *n_labels);
@@ -343,6 +351,15 @@ int gtb_merge_connections(uint64_t n_a, const gtb_connection *a, uint64_t n_b, c
 int gtb_allreduce_accumulators(gtb_ctx *ctx, int region_id, void *nccl_comm);
 /* Several regions in ONE NCCL group and one stream synchronisation. */
 int gtb_allreduce_accumulators_multi(gtb_ctx *ctx, int n, const int *region_ids, void *nccl_comm);
+
+/* Sample-sharded runs (the reference's own pool split src/typer/caller.cpp:272-391): every rank owns a
+ * block of samples, accumulators and calls stay local, and the ONE exchange at the end is the cross-pool merge of the
+ * per-bubble summaries, VarStats::add_stats (src/typer/var_stats.cpp:141-189): every counter summed, maximum_alt_support and
+ * maximum_alt_support_ratio max-ed, n_max_alt_proper_pairs summed as a uint8 -- three collectives in one NCCL group.
+ * var / allele / ratio: the gtb_scan_calls layouts, any number of regions back to back (n_var_rows bubbles,
+ * n_allele_rows alleles in total); in place, result valid on every rank. */
+int gtb_allreduce_varstats(gtb_ctx *ctx, uint64_t n_var_rows, uint64_t n_allele_rows, uint64_t *var, uint64_t *allele,
+                           double *ratio, void *nccl_comm);
 
 /* Discovery re-alignment.  Replaces paw::pairwise_alignment(read, haplotype window, opts)
  * + AlignmentResults::get_database_begin_end + apply_clipping as realign_to_indels calls them

@@ -53,6 +53,14 @@ def build_reference(jobs: int = 8) -> Optional[str]:
     return REF_BIN
 
 
+def binned_pl() -> Optional[np.ndarray]:
+    """The reference's PL / GQ output binning table (vcf.cpp:1107-1113), dumped by the reference build."""
+    p = os.path.join(HERE, "_ref", "gen", "binned_pl.txt")
+    if not os.path.exists(p):
+        return None
+    return np.loadtxt(p, dtype=np.int64)
+
+
 def ref_binary(name: str) -> Optional[str]:
     p = os.path.join(REF_BIN, name)
     return p if os.path.exists(p) else None
