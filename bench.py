@@ -533,25 +533,18 @@ def main() -> None:
     # ---- e2e: host buffers through the public C-ABI calls, K steps back to back over n_threads pool threads
     def final_reduce():
         # sample-sharded job end: per-variant summaries of the local pools, then ONE NCCL reduce over the ranks
-        var, allele, ratio = [], [], []
-        for t in range(len(ctxs)):
-            for a in acc_bufs[t]:
-                ph, _, _ = ctxs[t].calls(a)
-                v, al, ra = ctxs[t].scan_calls(a, ph)
-                var.append(v)
-                allele.append(al)
-                ratio.append(ra)
-        n = len(ids)
-        V, A, R = np.concatenate(var[:n]), np.concatenate(allele[:n]), np.concatenate(ratio[:n])
-        for t in range(1, len(ctxs)):  # cross-pool merge on this rank (VarStats::add_stats)
-            owner.merge_varstats(V, A, R, np.concatenate(var[t * n:(t + 1) * n]), np.concatenate(allele[t * n:(t + 1) * n]),
-                                 np.concatenate(ratio[t * n:(t + 1) * n]))
+        per_ctx = [ctxs[t].scan_calls_multi(acc_bufs[t]) for t in range(len(ctxs))]
+        V, A, R = per_ctx[0]
+        for v, a, r in per_ctx[1:]:  # cross-pool merge on this rank (VarStats::add_stats)
+            owner.merge_varstats(V, A, R, v, a, r)
         t0 = time.perf_counter()
         owner.allreduce_varstats(V, A, R)
         return time.perf_counter() - t0, int(V.sum() % (1 << 62))
 
     for s in range(warmup):
         e2e_step(s % n_threads)
+    if world > 1:
+        final_reduce()  # warm-up of the reduce as well (NCCL sets its channels up on the first collective)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

@@ -3094,6 +3094,35 @@ int gtb_scan_calls(const gtb_accumulators * acc, const uint8_t * phred, uint64_t
 }
 
 // VarStats::add_stats (src/typer/var_stats.cpp:141-189) on the arrays of gtb_scan_calls: dst += src
+// Per-pool summaries of several regions in one call (the regions are independent jobs for the host pool): PHRED calls, then
+// Variant::scan_calls; rows of region i start at var + 9 * (bubbles before it) / allele + 13 * (alleles before it).
+int gtb_scan_calls_multi(int n, const gtb_accumulators * accs, uint64_t * var, uint64_t * allele, double * ratio)
+{
+  if (n <= 0 || !accs || !var || !allele || !ratio)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  std::vector<size_t> b0(n + 1, 0), a0(n + 1, 0);
+  for (int i = 0; i < n; ++i)
+  {
+    b0[i + 1] = b0[i] + accs[i].n_bubbles;
+    a0[i + 1] = a0[i] + accs[i].cov_off[accs[i].n_bubbles];
+  }
+  std::vector<int> rcs(n, 0);
+  parallel_for(n, [&](int i)
+               {
+                 gtb_accumulators const & A = accs[i];
+                 size_t const NS = A.n_samples, NB = A.n_bubbles;
+                 std::vector<uint8_t> phred((size_t)A.score_off[NB] * NS), gq(NB * NS);
+                 std::vector<uint16_t> gt(NB * NS * 2);
+                 rcs[i] = gtb_calls_from_accumulators(&A, phred.data(), gt.data(), gq.data());
+                 if (!rcs[i])
+                   rcs[i] = gtb_scan_calls(&A, phred.data(), var + 9 * b0[i], allele + 13 * a0[i], ratio + a0[i]);
+               });
+  for (int i = 0; i < n; ++i)
+    if (rcs[i])
+      return fail(rcs[i], "gtb_scan_calls_multi: a region failed");
+  return 0;
+}
+
 int gtb_merge_varstats(uint32_t n_bubbles, uint64_t n_alleles_total, uint64_t * var, uint64_t * allele, double * ratio,
                        const uint64_t * var_src, const uint64_t * allele_src, const double * ratio_src)
 {

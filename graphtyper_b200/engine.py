@@ -26,7 +26,7 @@ EXPORTS = [
     "gtb_sw_align_batch", "gtb_sw_last_timing", "gtb_sw_replay_last", "gtb_set_index_build",
     "gtb_set_connections", "gtb_connections_size", "gtb_connections", "gtb_phase_support", "gtb_last_prep_timing",
     "gtb_submit_bam_records", "gtb_submit_bam_records_multi", "gtb_debug_bam_columns", "gtb_merge_connections", "gtb_sample_depths",
-    "gtb_last_chain_timing", "gtb_region_attach", "gtb_allreduce_varstats",
+    "gtb_last_chain_timing", "gtb_region_attach", "gtb_allreduce_varstats", "gtb_scan_calls_multi",
 ]
 
 
@@ -422,6 +422,19 @@ class Context:
         ratio = np.zeros(n_cov, np.float64)
         self._check(self.lib.gtb_scan_calls(C.byref(acc.view), phred.ctypes.data_as(abi.u8p), var.ctypes.data_as(abi.u64p),
                                             allele.ctypes.data_as(abi.u64p), ratio.ctypes.data_as(C.POINTER(C.c_double))))
+        return var, allele, ratio
+
+    def scan_calls_multi(self, accs: Sequence[abi.HostAccumulators]):
+        """Per-pool summaries of several regions in one call: concatenated (var, allele, ratio) rows."""
+        n = len(accs)
+        arr = (abi.Accumulators * n)(*[a.view for a in accs])
+        nb = sum(a.n_bubbles for a in accs)
+        na = sum(int(a.cov_off[-1]) for a in accs)
+        var, allele, ratio = np.zeros(nb * 9, np.uint64), np.zeros(na * 13, np.uint64), np.zeros(na, np.float64)
+        fn = self.lib.gtb_scan_calls_multi
+        fn.argtypes = [C.c_int, C.POINTER(abi.Accumulators), abi.u64p, abi.u64p, C.POINTER(C.c_double)]
+        self._check(fn(n, arr, var.ctypes.data_as(abi.u64p), allele.ctypes.data_as(abi.u64p),
+                       ratio.ctypes.data_as(C.POINTER(C.c_double))))
         return var, allele, ratio
 
     def merge_varstats(self, var, allele, ratio, var_src, allele_src, ratio_src) -> None:

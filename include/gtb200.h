@@ -270,6 +270,9 @@ int gtb_nccl_init(gtb_ctx *ctx, int n_ranks, int rank, const uint8_t *id128);
  *                 het_multi0 het_multi1 hom_multi0 hom_multi1          (a runs over cov_off[b] + allele)
  *   ratio[a]      maximum_alt_support_ratio */
 int gtb_scan_calls(const gtb_accumulators *acc, const uint8_t *phred, uint64_t *var, uint64_t *allele, double *ratio);
+/* gtb_calls_from_accumulators + gtb_scan_calls for n regions in one call; the rows of the regions follow each other in
+ * var / allele / ratio (the layout gtb_allreduce_varstats and gtb_merge_varstats take). */
+int gtb_scan_calls_multi(int n, const gtb_accumulators *accs, uint64_t *var, uint64_t *allele, double *ratio);
 int gtb_merge_varstats(uint32_t n_bubbles, uint64_t n_alleles_total, uint64_t *var, uint64_t *allele, double *ratio,
                        const uint64_t *var_src, const uint64_t *allele_src, const double *ratio_src);
 

@@ -136,3 +136,26 @@ def test_rejects_malformed_graph():
     with pytest.raises(engine.GtbError):
         ctx.region_begin(0, g)
     ctx.close()
+
+
+def test_scan_calls_multi_equals_per_region_calls(oracle_lib):
+    """gtb_scan_calls_multi (several regions, rows back to back) = gtb_calls_from_accumulators + gtb_scan_calls per region."""
+    from conftest import fixture_prefixes
+    from graphtyper_b200 import abi, engine, gtba
+    ctx = engine.Context(device=-1)
+    accs = []
+    for pre in fixture_prefixes(False)[:3]:
+        g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+        rd = gtba.load(pre + ".reads.gtba")
+        ns = len(rd["sample_names"].tobytes().split(b"\n")) - 1
+        h = oracle_lib.index_build(g)
+        accs.append(oracle_lib.result_accum(oracle_lib.pool_run(g, h, ns, abi.batch_from_probe(rd), tap=False), ns))
+    V, A, R = ctx.scan_calls_multi(accs)
+    ev, ea, er = [], [], []
+    for a in accs:
+        ph, _, _ = ctx.calls(a)
+        v, al, ra = ctx.scan_calls(a, ph)
+        ev.append(v)
+        ea.append(al)
+        er.append(ra)
+    assert np.array_equal(V, np.concatenate(ev)) and np.array_equal(A, np.concatenate(ea)) and np.array_equal(R, np.concatenate(er))

@@ -1,5 +1,9 @@
-"""Run under torchrun on N GPUs: one pool's records sharded over the ranks (abi.shard_batch), every rank accumulates
-its shard on its GPU, ONE grouped NCCL all-reduce, result compared bit-for-bit with the reference's golden accumulators."""
+"""Run under torchrun on N GPUs (tests/test_gpu_multi.py does):
+ * read sharding: one pool's records sharded over the ranks (abi.shard_batch), every rank accumulates its shard on its GPU,
+   ONE grouped NCCL all-reduce, result compared bit-for-bit with the reference's golden accumulators;
+ * sample sharding: every rank genotypes the whole pool (as if each rank owned a copy of the samples), the per-variant
+   summaries are merged over the ranks with gtb_allreduce_varstats and must equal N host-side merges
+   (gtb_merge_varstats = VarStats::add_stats, pinned to the reference on the CPU suite)."""
 import glob, os, sys
 import numpy as np
 import torch, torch.distributed as dist
@@ -33,7 +37,23 @@ for k, pre in enumerate(pres):
         if rank == 0: print("OK  ", os.path.basename(pre), "shard sizes", len(shard))
     except AssertionError as e:
         ok = False; print("FAIL", os.path.basename(pre), e)
+    # sample sharding: local summaries -> NCCL sum / max
+    full = abi.batch_from_probe(rd)
+    ctx.pool_reset(k)
+    ctx.submit(k, full)
+    acc = ctx.pool_finish(k)
+    ph, _, _ = ctx.calls(acc)
+    var, allele, ratio = ctx.scan_calls(acc, ph)
+    ev, ea, er = var.copy(), allele.copy(), ratio.copy()
+    for _ in range(world - 1):
+        ctx.merge_varstats(ev, ea, er, var, allele, ratio)
+    ctx.allreduce_varstats(var, allele, ratio)
+    if not (np.array_equal(var, ev) and np.array_equal(allele, ea) and np.array_equal(ratio, er)):
+        ok = False; print("FAIL varstats", os.path.basename(pre), "rank", rank)
     ctx.region_end(k)
+flag = torch.tensor([1 if ok else 0], device=f"cuda:{lr}")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+ok = bool(int(flag[0]))
 dist.barrier()
 if rank == 0: print("multi-GPU sharded parity:", "PASS" if ok else "FAIL")
 dist.destroy_process_group()
