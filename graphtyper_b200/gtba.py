@@ -5,6 +5,8 @@ u32 kind (0 unsigned, 1 signed, 2 float), u64 count, raw little-endian data padd
 """
 from __future__ import annotations
 
+import gzip
+import os
 import struct
 from typing import Dict
 
@@ -16,8 +18,15 @@ _DT = {(1, 0): np.uint8, (2, 0): np.uint16, (4, 0): np.uint32, (8, 0): np.uint64
 
 
 def load(path: str) -> Dict[str, np.ndarray]:
-    with open(path, "rb") as f:
-        buf = f.read()
+    """Reads PATH, or PATH.gz when only the gzip-compressed file exists (the larger committed fixtures)."""
+    if not os.path.exists(path) and os.path.exists(path + ".gz"):
+        path += ".gz"
+    if path.endswith(".gz"):
+        with gzip.open(path, "rb") as f:
+            buf = f.read()
+    else:
+        with open(path, "rb") as f:
+            buf = f.read()
     if buf[:8] != b"GTBA0001":
         raise ValueError(f"{path}: not a GTBA file")
     (n,) = struct.unpack_from("<Q", buf, 8)

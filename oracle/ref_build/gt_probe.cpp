@@ -375,7 +375,7 @@ int main(int argc, char ** argv)
 {
   using namespace gyper;
   std::string ref_fn, vcf_fn, region_str, out, sams_arg;
-  bool is_sv = false, dump_seeds = true;
+  bool is_sv = false, dump_seeds = true, light = false;
   long pad = 1000;
 
   for (int i = 1; i < argc; ++i)
@@ -406,6 +406,8 @@ int main(int argc, char ** argv)
       pad = std::stol(next());
     else if (a == "--no-seeds")
       dump_seeds = false;
+    else if (a == "--light") // large pools: no index / per-read dumps, only the record stream's identity + accumulators
+      light = true;
     else
     {
       fprintf(stderr, "unknown arg %s\n", a.c_str());
@@ -438,7 +440,8 @@ int main(int argc, char ** argv)
   dump_graph(out + ".graph.gtba");
 
   PHIndex ph_index = index_graph(graph);
-  dump_index(ph_index, out + ".index.gtba");
+  if (!light)
+    dump_index(ph_index, out + ".index.gtba");
 
   if (sams_arg.empty())
     return 0;
@@ -473,6 +476,9 @@ int main(int argc, char ** argv)
   std::vector<uint32_t> r_lqname;
   PathDump pd;
   SeedDump sd0, sd1;
+  // --light: which record of which file every processed record is (ordinal counts every record the reader delivered)
+  std::vector<int32_t> r_ord;
+  std::vector<int64_t> file_count(sams.size(), 0);
 
   std::pair<GenotypePaths, GenotypePaths> prev_paths;
   HtsRecord prev, curr;
@@ -486,6 +492,29 @@ int main(int argc, char ** argv)
     auto const & c = b->core;
     long sample_i = 0, rg_i = 0;
     hts_preader.get_sample_and_rg_index(sample_i, rg_i, h);
+    if (light)
+    {
+      r_flag.push_back(c.flag);
+      r_sample.push_back(sample_i);
+      r_file.push_back(h.file_index);
+      r_ord.push_back((int32_t)(file_count[h.file_index] - 1));
+      {
+        // record identity for the regenerating harness: the trailing decimal number of the read name (the generator's pair
+        // id); the reader re-sorts same-position records of a file by sequence, so a delivery ordinal is not a file line
+        char const * qn = bam_get_qname(b);
+        size_t const len = strlen(qn);
+        size_t k = len;
+        while (k > 0 && qn[k - 1] >= '0' && qn[k - 1] <= '9')
+          --k;
+        r_pos.push_back(k < len ? std::strtoll(qn + k, nullptr, 10) : -1);
+      }
+      r_isdup.push_back(is_dup ? 1 : 0);
+      std::pair<GenotypePaths, GenotypePaths> scratch =
+        std::make_pair(GenotypePaths(c.flag, c.l_qseq), GenotypePaths(c.flag, c.l_qseq));
+      update_paths(scratch, b);
+      r_score_diff_first.push_back(scratch.first.score_diff);
+      return;
+    }
     r_flag.push_back(c.flag);
     r_pos.push_back(c.pos);
     r_mpos.push_back(c.mpos);
@@ -520,7 +549,7 @@ int main(int argc, char ** argv)
   auto process = [&](HtsRecord const & h, bool update_prev)
   {
     record_columns(h, !update_prev);
-    if (update_prev)
+    if (update_prev && !light)
     {
       // golden per-read alignment (same call genotype_only makes internally)
       seqan::IupacString s1, s2;
@@ -548,15 +577,22 @@ int main(int argc, char ** argv)
                   update_prev, IS_SV);
   };
 
-  bool is_done = !hts_preader.read_record(prev);
+  auto read_next = [&](HtsRecord & h)
+  {
+    bool const ok = hts_preader.read_record(h);
+    if (ok)
+      ++file_count[h.file_index];
+    return ok;
+  };
+  bool is_done = !read_next(prev);
   while (!is_done && ((prev.record->core.flag & opts.sam_flag_filter) != 0u || (IS_SV && !is_good_read_sv(prev.record))))
-    is_done = !hts_preader.read_record(prev);
+    is_done = !read_next(prev);
 
   if (!is_done)
   {
     process(prev, true);
     have_prev = true;
-    while (hts_preader.read_record(curr))
+    while (read_next(curr))
     {
       if ((curr.record->core.flag & opts.sam_flag_filter) != 0u || (IS_SV && !is_good_read_sv(curr.record)))
         continue;
@@ -604,6 +640,26 @@ int main(int argc, char ** argv)
     maps.clear();
   }
 
+  if (light)
+  {
+    ArrayFile af;
+    af.add("flag", r_flag);
+    af.add("sample", r_sample, 1);
+    af.add("file", r_file, 1);
+    af.add("ord", r_ord, 1);
+    af.add("name_id", r_pos, 1);
+    af.add("isdup", r_isdup);
+    af.add("score_diff", r_score_diff_first);
+    std::vector<uint8_t> sample_names;
+    for (auto const & s : writer.pns)
+    {
+      sample_names.insert(sample_names.end(), s.begin(), s.end());
+      sample_names.push_back('\n');
+    }
+    af.add("sample_names", sample_names);
+    af.write(out + ".stream.gtba");
+  }
+  else
   {
     ArrayFile af;
     af.add("flag", r_flag);

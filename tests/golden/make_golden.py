@@ -3,7 +3,7 @@
 (oracle/_ref/bin/gt_probe, built by oracle/ref_build/Makefile) on seeded synthetic inputs.
 
   python tests/golden/make_golden.py          # small fixtures -> tests/golden/      (committed)
-  python tests/golden/make_golden.py --big    # larger fixtures -> tests/data_local/ (git-ignored, ships to the GPU box)
+  python tests/golden/make_golden.py --big    # larger fixtures -> tests/golden/big/*.gtba.gz (committed, gzip -9)
 
 Only runnable where /root/reference was compiled (this container); the GPU box uses the produced files.
 """
@@ -103,7 +103,7 @@ def run_sv(name: str, kw: dict, out_dir: str) -> None:
 def main() -> None:
     big = "--big" in sys.argv
     only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
-    out_dir = os.path.join(ROOT, "tests", "data_local" if big else "golden")
+    out_dir = os.path.join(ROOT, "tests", "golden", "big") if big else os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     for name, (kw, rs) in (BIG if big else SMALL).items():
         if not only or name in only:
@@ -111,6 +111,10 @@ def main() -> None:
     for name, kw in (BIG_SV if big else SMALL_SV).items():
         if not only or name in only:
             run_sv(name, kw, out_dir)
+    if big:  # the committed form is gzip-compressed (gtba.load reads either)
+        import glob
+        for p in glob.glob(os.path.join(out_dir, "*.gtba")):
+            subprocess.run(["gzip", "-9", "-n", "-f", p], check=True)
 
 
 if __name__ == "__main__":

@@ -20,8 +20,8 @@ if rank == 0:
     uid.copy_(torch.from_numpy(ctx.nccl_unique_id()))
 dist.broadcast(uid, 0)
 ctx.nccl_init(world, rank, uid.cpu().numpy())
-pres = sorted(p[:-len(".graph.gtba")] for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.graph.gtba")) +
-              glob.glob(os.path.join(ROOT, "tests", "data_local", "*.graph.gtba")))
+from conftest import fixture_prefixes
+pres = fixture_prefixes(include_big=True)
 ok = True
 for k, pre in enumerate(pres):
     g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
