@@ -1,10 +1,16 @@
 // gtb_shim.hpp -- the reference-side binding of libgtb200: what a graphtyper maintainer adds to the tree.
 //
-// Header-only C++17 on top of the reference's own headers and include/gtb200.h.  It does three things and nothing else:
-//   flatten()   gyper::Graph            -> gtb_graph_view        (input of gtb_region_begin; replaces index_graph's argument)
-//   Records     HtsRecord stream        -> gtb_bam_batch         (input of gtb_submit_bam_records; replaces genotype_only's
+// Header-only C++17 on top of the reference's own headers and include/gtb200.h:
+//   flatten()       gyper::Graph            -> gtb_graph_view    (input of gtb_region_begin; replaces index_graph's argument)
+//   Records         HtsRecord stream        -> gtb_bam_batch     (input of gtb_submit_bam_records; replaces genotype_only's
 //                                                                 per-record work, src/utilities/hts_parallel_reader.cpp:245-338)
-//   die()       gtb_status              -> print_log(error) + std::exit(1), the reference's error convention
+//   is_good_read()  the SV pre-filter of the pool loop           (hts_parallel_reader.cpp:528-568)
+//   CoverageCap     the per-sample 50-bp bin cap of the pool loop (hts_parallel_reader.cpp:599-633)
+//   Accumulators    caller-owned buffers of gtb_pool_finish
+//   fill_writer()   gtb_accumulators (+ connections) -> VcfWriter::haplotypes[*].hap_samples[*] / var_stats, ReferenceDepth:
+//                   the state the reference's own pool finalisation (Vcf::add_haplotype, src/typer/vcf.cpp:1507) reads
+//   die()           gtb_status              -> print_log(error) + std::exit(1), the reference's error convention
+// integration/gtb_pool_reader.cpp puts them together into replacements of index_graph and parallel_reader_genotype_only.
 //
 // Compiled and exercised against the unmodified reference objects by oracle/ref_build/shim_probe.cpp
 // (tests/test_shim_against_reference.py).
@@ -17,6 +23,8 @@
 #include <vector>
 
 #include <graphtyper/graph/graph.hpp>
+#include <graphtyper/graph/reference_depth.hpp>
+#include <graphtyper/typer/vcf_writer.hpp>
 #include <graphtyper/utilities/hts_parallel_reader.hpp>
 #include <graphtyper/utilities/logging.hpp>
 
@@ -157,4 +165,205 @@ struct Records
     return b;
   }
 };
+
+// The pool loop's read filter when calling SVs (src/utilities/hts_parallel_reader.cpp:528-568): mapped; not (MAPQ <= 15 with
+// the mate on another contig or more than 200 kb away); not soft-clipped at both ends; not (MAPQ <= 15 and >= 12 bases
+// soft-clipped at one end).
+inline bool is_good_read(bam1_t const * r)
+{
+  auto const & c = r->core;
+  if ((c.flag & BAM_FUNMAP) != 0)
+    return false;
+  bool const mate_far = c.tid != c.mtid || std::abs((long)(c.pos - c.mpos)) > 200000l;
+  if (c.qual <= 15 && mate_far)
+    return false;
+  if (c.n_cigar >= 2)
+  {
+    uint32_t const * cig = bam_get_cigar(r);
+    uint32_t const front = cig[0], back = cig[c.n_cigar - 1];
+    bool const front_clip = bam_cigar_op(front) == BAM_CSOFT_CLIP, back_clip = bam_cigar_op(back) == BAM_CSOFT_CLIP;
+    bool const one_long = (front_clip && bam_cigar_oplen(front) >= 12) || (back_clip && bam_cigar_oplen(back) >= 12);
+    if ((front_clip && back_clip) || (c.qual <= 15 && one_long))
+      return false;
+  }
+  return true;
+}
+
+// The (extreme) coverage filter of the pool loop when calling SVs (hts_parallel_reader.cpp:587-633): per sample, reads are
+// counted in 50-bp bins from the first record's position; a bin that already holds more than avg_cov_by_readlen * 150 reads
+// takes no more.  A record that opens a new bin is always kept; duplicates of the previous record are counted but never
+// skipped (the caller decides that, exactly like the reference's loop: :666-707).
+struct CoverageCap
+{
+  bool active = false;
+  long first_pos = 0;
+  std::vector<double> const * avg_cov = nullptr;
+  std::vector<std::vector<uint16_t>> bins;
+
+  void start(bool is_active, long n_samples, long first_record_pos, std::vector<double> const * avg_cov_by_readlen)
+  {
+    active = is_active;
+    first_pos = first_record_pos;
+    avg_cov = avg_cov_by_readlen;
+    if (active)
+      bins.assign(n_samples, {});
+  }
+
+  // counts the record in; false = its bin is full
+  bool admit(long sample_i, long pos)
+  {
+    if (!active || !avg_cov || sample_i >= (long)avg_cov->size() || (*avg_cov)[sample_i] <= 0.0)
+      return true;
+    uint16_t const cap = (uint16_t)std::min(65535l, (long)((*avg_cov)[sample_i] * 50.0 * 3.0 + 0.5));
+    auto & b = bins[sample_i];
+    long const bin = (pos - first_pos) / 50l;
+    if (bin >= (long)b.size())
+    {
+      b.resize(bin + 1, 0u);
+      ++b[bin];
+      return true;
+    }
+    if (b[bin] > cap)
+      return false;
+    ++b[bin];
+    return true;
+  }
+};
+
+// Caller-owned buffers behind a gtb_accumulators (sized with gtb_accumulator_sizes / gtb_ref_depth_size).
+struct Accumulators
+{
+  std::vector<uint32_t> bubble_id, n_alleles, saturated, read_strand;
+  std::vector<uint64_t> score_off, cov_off, vs_clipped_reads, vs_mapq_squared, pa_clipped_bp, pa_mapq_squared, pa_score_diff,
+    pa_mismatches;
+  std::vector<uint16_t> log_score, gt_coverage, max_log_score, ref_depth;
+  std::vector<uint8_t> amb, amb_alt, alt_pp;
+  gtb_accumulators view{};
+
+  void resize(uint32_t nb, uint64_t n_scores, uint64_t n_cov, uint32_t ns, uint32_t depth_size)
+  {
+    size_t const cells = (size_t)nb * ns;
+    bubble_id.assign(nb, 0);
+    n_alleles.assign(nb, 0);
+    score_off.assign(nb + 1, 0);
+    cov_off.assign(nb + 1, 0);
+    log_score.assign(n_scores * ns, 0);
+    gt_coverage.assign(n_cov * ns, 0);
+    max_log_score.assign(cells, 0);
+    amb.assign(cells, 0);
+    amb_alt.assign(cells, 0);
+    alt_pp.assign(cells, 0);
+    saturated.assign(cells, 0);
+    vs_clipped_reads.assign(nb, 0);
+    vs_mapq_squared.assign(nb, 0);
+    pa_clipped_bp.assign(n_cov, 0);
+    pa_mapq_squared.assign(n_cov, 0);
+    pa_score_diff.assign(n_cov, 0);
+    pa_mismatches.assign(n_cov, 0);
+    read_strand.assign(n_cov * 4, 0);
+    ref_depth.assign((size_t)depth_size * ns, 0);
+    view = gtb_accumulators{};
+    view.n_bubbles = nb;
+    view.n_samples = ns;
+    view.bubble_id = bubble_id.data();
+    view.n_alleles = n_alleles.data();
+    view.score_off = score_off.data();
+    view.cov_off = cov_off.data();
+    view.log_score = log_score.data();
+    view.gt_coverage = gt_coverage.data();
+    view.max_log_score = max_log_score.data();
+    view.ambiguous_depth = amb.data();
+    view.ambiguous_depth_alt = amb_alt.data();
+    view.alt_proper_pair_depth = alt_pp.data();
+    view.saturated = saturated.data();
+    view.vs_clipped_reads = vs_clipped_reads.data();
+    view.vs_mapq_squared = vs_mapq_squared.data();
+    view.pa_clipped_bp = pa_clipped_bp.data();
+    view.pa_mapq_squared = pa_mapq_squared.data();
+    view.pa_score_diff = pa_score_diff.data();
+    view.pa_mismatches = pa_mismatches.data();
+    view.read_strand = read_strand.data();
+    view.depth_size = depth_size;
+    view.ref_depth = depth_size ? ref_depth.data() : nullptr;
+  }
+};
+
+// The pool's results into the objects the reference's pool finalisation reads (hts_parallel_reader.cpp:782-1029):
+// VcfWriter::haplotypes[b].hap_samples[s] (include/graphtyper/graph/haplotype.hpp:25-75), Haplotype::var_stats
+// (include/graphtyper/typer/var_stats.hpp:15-84), and for SV graphs the per-sample depth tracks of ReferenceDepth.
+// `writer` comes straight from set_samples (all zero); bubble b of the accumulators is haplotype b (both follow the graph's
+// bubble order, checked through Genotype::id).
+inline void fill_writer(gyper::VcfWriter & writer, gyper::ReferenceDepth & reference_depth, gtb_accumulators const & A,
+                        gtb_connection const * conn, uint64_t n_conn)
+{
+  using namespace gyper;
+  size_t const NS = A.n_samples;
+  if (writer.haplotypes.size() != A.n_bubbles)
+  {
+    print_log(log_severity::error, "[gtb200] ", writer.haplotypes.size(), " haplotypes in the writer but ", A.n_bubbles,
+              " bubbles in the accumulators");
+    std::exit(1);
+  }
+  for (size_t b = 0; b < A.n_bubbles; ++b)
+  {
+    Haplotype & hap = writer.haplotypes[b];
+    size_t const cnum = A.n_alleles[b], tri = cnum * (cnum + 1) / 2;
+    if (hap.gt.id != A.bubble_id[b] || hap.gt.num != cnum || hap.hap_samples.size() != NS)
+    {
+      print_log(log_severity::error, "[gtb200] haplotype ", b, " does not match bubble ", A.bubble_id[b]);
+      std::exit(1);
+    }
+    for (size_t s = 0; s < NS; ++s)
+    {
+      HapSample & hs = hap.hap_samples[s];
+      uint16_t const * ls = A.log_score + A.score_off[b] * NS + s * tri;
+      uint16_t const * gc = A.gt_coverage + A.cov_off[b] * NS + s * cnum;
+      hs.log_score.assign(ls, ls + tri);
+      hs.gt_coverage.assign(gc, gc + cnum);
+      hs.max_log_score = A.max_log_score[b * NS + s];
+      // the three depths are private saturating uint8 counters: counted up to their (already clamped) values
+      for (unsigned k = 0; k < A.ambiguous_depth[b * NS + s]; ++k)
+        hs.increment_ambiguous_depth();
+      for (unsigned k = 0; k < A.ambiguous_depth_alt[b * NS + s]; ++k)
+        hs.increment_ambiguous_depth_alt();
+      for (unsigned k = 0; k < A.alt_proper_pair_depth[b * NS + s]; ++k)
+        hs.increment_alt_proper_pair_depth();
+    }
+    VarStats & vs = hap.var_stats;
+    vs.clipped_reads = (uint32_t)A.vs_clipped_reads[b];
+    vs.mapq_squared = A.vs_mapq_squared[b];
+    for (size_t a = 0; a < cnum && a < vs.per_allele.size(); ++a)
+    {
+      size_t const i = A.cov_off[b] + a;
+      vs.per_allele[a].clipped_bp = A.pa_clipped_bp[i];
+      vs.per_allele[a].mapq_squared = A.pa_mapq_squared[i];
+      vs.per_allele[a].score_diff = (uint32_t)A.pa_score_diff[i];
+      vs.per_allele[a].mismatches = (uint32_t)A.pa_mismatches[i];
+      vs.read_strand[a].r1_forward = A.read_strand[i * 4];
+      vs.read_strand[a].r1_reverse = A.read_strand[i * 4 + 1];
+      vs.read_strand[a].r2_forward = A.read_strand[i * 4 + 2];
+      vs.read_strand[a].r2_reverse = A.read_strand[i * 4 + 3];
+    }
+  }
+  // HapSample::connections[allele1][hap2] = support per allele of hap2 (haplotype.hpp:42)
+  for (uint64_t k = 0; k < n_conn; ++k)
+  {
+    gtb_connection const & c = conn[k];
+    auto & m = writer.haplotypes[c.hap1].hap_samples[c.sample].connections[c.allele1];
+    auto & v = m[c.hap2];
+    if (v.empty())
+      v.assign(writer.haplotypes[c.hap2].gt.num, 0u);
+    v[c.allele2] = (uint16_t)c.count;
+  }
+  if (A.ref_depth && A.depth_size)
+  {
+    reference_depth.reference_offset = A.reference_offset;
+    for (size_t s = 0; s < NS && s < reference_depth.depths.size(); ++s)
+    {
+      auto & d = reference_depth.depths[s];
+      size_t const n = std::min<size_t>(d.size(), A.depth_size);
+      std::copy(A.ref_depth + s * A.depth_size, A.ref_depth + s * A.depth_size + n, d.begin());
+    }
+  }
+}
 } // namespace gtb_shim
