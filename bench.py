@@ -344,6 +344,62 @@ def sw_key(ctx):
     return out
 
 
+def cli_end_to_end(ref, sites, rs, regions):
+    """end-to-end CLI wall.  ONE process genotypes all 20 regions of the sample from one indexed BAM
+    (`graphtyper genotype REF --sam=all.bam --region_file=... --vcf=...`, bamshrink included) -- once with the stock
+    binary, once with the drop-in binary oracle/_ref/bin/graphtyper_gtb (the same reference with index_graph and
+    parallel_reader_genotype_only replaced by libgtb200, integration/gtb_pool_reader.cpp); the VCFs must be identical."""
+    import gzip
+    import oracle
+    from graphtyper_b200 import synth
+    exe = {k: oracle.ref_binary(k) for k in ("graphtyper", "graphtyper_gtb", "bgzip", "tabix", "sam2bam")}
+    if not all(exe.values()):
+        return {"unavailable": "needs " + ", ".join(k for k, v in exe.items() if not v) + " under oracle/_ref/bin"}
+    tmp = tempfile.mkdtemp(prefix="gtb_cli_")
+    try:
+        fa = os.path.join(tmp, "ref.fa")
+        synth.write_fasta(fa, ref)
+        vcf = os.path.join(tmp, "sites.vcf")
+        synth.write_vcf(vcf, sites, "chr1", len(ref))
+        subprocess.run([exe["bgzip"], "-f", vcf], check=True)
+        subprocess.run([exe["tabix"], "-f", "-p", "vcf", vcf + ".gz"], check=True)
+        sam = os.path.join(tmp, "all.sam")
+        synth.write_sam(sam, rs, "chr1", len(ref))
+        bam = os.path.join(tmp, "all.bam")
+        subprocess.run([exe["sam2bam"], sam, bam], check=True)
+        os.unlink(sam)
+        rf = os.path.join(tmp, "regions.txt")
+        with open(rf, "w") as f:
+            f.write("".join(f"chr1:{b}-{e}\n" for b, e in regions))
+        res, text = {}, {}
+        for name in ("graphtyper", "graphtyper_gtb"):
+            times = []
+            for rep in range(2):  # the second run has the page cache and (GPU) the driver warm
+                out = os.path.join(tmp, f"out_{name}")
+                shutil.rmtree(out, ignore_errors=True)
+                t0 = time.perf_counter()
+                r = subprocess.run([exe[name], "genotype", fa, f"--sam={bam}", f"--region_file={rf}", f"--vcf={vcf}.gz",
+                                    "--threads=1", f"--output={out}"], capture_output=True, text=True,
+                                   env=dict(os.environ, TMPDIR=tmp))
+                times.append(time.perf_counter() - t0)
+                if r.returncode != 0:
+                    return {"error": f"{name} failed: {r.stderr[-400:]}"}
+            res[name] = min(times)
+            text[name] = {}
+            for v in sorted(glob.glob(os.path.join(tmp, f"out_{name}", "chr1", "*.vcf.gz"))):
+                with gzip.open(v, "rt") as fh:
+                    text[name][os.path.basename(v)] = fh.read()
+        same = text["graphtyper"] == text["graphtyper_gtb"] and len(text["graphtyper"]) == len(regions)
+        n_rec = sum(sum(1 for ln in t.splitlines() if ln and not ln.startswith("#")) for t in text["graphtyper"].values())
+        return {"reference_cli_s": res["graphtyper"], "dropin_cli_s": res["graphtyper_gtb"],
+                "speedup": res["graphtyper"] / res["graphtyper_gtb"], "vcf_files": len(text["graphtyper"]),
+                "vcf_records": n_rec, "vcfs_identical": bool(same), "reads": int(len(rs)),
+                "note": "one process, --threads=1 (one sample), 20 regions from one indexed BAM incl. bamshrink, graph "
+                        "construction, VCF merge + BGZF; best of 2 runs each; the drop-in run includes CUDA context creation"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_pipelined(n_threads: int, steps: int, fn):
     """steps calls of fn(thread, step) dealt round-robin to n_threads host threads; returns wall seconds from the common
     start to the last thread's end (the callers bracket it with barrier + synchronize and CUDA events)."""
@@ -694,6 +750,13 @@ def main() -> None:
                 out["sw"] = sw_key(owner)
             except Exception as ex:
                 out["sw"] = {"error": repr(ex)}
+            try:
+                out["cli"] = cli_end_to_end(ref, sites, rs, regions)
+            except Exception as ex:
+                out["cli"] = {"error": repr(ex)}
+            if out["cli"].get("vcfs_identical") is False:
+                print(json.dumps({"error": "the drop-in binary's VCFs differ from the reference's", "cli": out["cli"]}))
+                sys.exit(1)
         print(json.dumps(out))
     for c in ctxs[1:]:
         c.close()

@@ -182,7 +182,12 @@ int gtb_region_attach(gtb_ctx *ctx, int region_id, gtb_ctx *owner, int owner_reg
 int gtb_index_size(gtb_ctx *ctx, int region_id, uint64_t *n_keys, uint64_t *n_labels);
 int gtb_index_export(gtb_ctx *ctx, int region_id, uint64_t *keys, uint32_t *label_off, gtb_label *labels);
 
-/* Pool of samples for one region. */
+/* Pool of samples for one region.
+ * A submit that returns an error (bad links, a read longer than 2 * GTB_SEQ_STRIDE bases, a device capacity, two mates with the
+ * same first-in-pair flag ...) may already have added the batch's other records to the pool's accumulators: the pool is then
+ * undefined until gtb_pool_reset (or a new gtb_pool_begin).  Callers that want to recover rather than exit must check what
+ * they can BEFORE submitting -- the reference-side reader (integration/gtb_pool_reader.cpp) checks read lengths while it
+ * collects the records, and bubbles beyond the allele capacity are refused by gtb_region_begin before anything runs. */
 int gtb_pool_begin(gtb_ctx *ctx, int region_id, int n_samples);
 int gtb_submit_reads(gtb_ctx *ctx, int region_id, const gtb_read_batch *batch, gtb_submit_stats *stats);
 int gtb_accumulator_sizes(gtb_ctx *ctx, int region_id, uint32_t *n_bubbles, uint64_t *n_scores, uint64_t *n_cov);

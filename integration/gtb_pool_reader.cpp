@@ -220,6 +220,7 @@ void parallel_reader_genotype_only(
   //      merge order.  Alignment, the duplicate shortcut, mate pairing and the accumulation happen on the device.
   gtb_shim::Records recs;
   long n_dup = 0;
+  bool too_long = false; // a read beyond the device's read length (GTB_SEQ_STRIDE * 2 bases): found before anything is submitted
   {
     auto rejected = [&](HtsRecord const & h)
     { return (h.record->core.flag & opts.sam_flag_filter) != 0u || (is_sv && !gtb_shim::is_good_read(h.record)); };
@@ -239,10 +240,12 @@ void parallel_reader_genotype_only(
       cap.start(is_sv && !opts.no_filter_on_coverage, n_samples, prev.record->core.pos, avg_cov_ptr);
       cap.admit(sample_of(prev), prev.record->core.pos);
       recs.add(hts_preader, prev);
-      while (hts_preader.read_record(curr))
+      too_long = prev.record->core.l_qseq > (int)(GTB_SEQ_STRIDE * 2);
+      while (!too_long && hts_preader.read_record(curr))
       {
         if (rejected(curr))
           continue;
+        too_long = curr.record->core.l_qseq > (int)(GTB_SEQ_STRIDE * 2);
         if (equal_pos_seq(prev.record, curr.record))
         {
           // same position and bases as the last aligned record: counted in its bin, never skipped
@@ -261,6 +264,20 @@ void parallel_reader_genotype_only(
     }
     print_log(log_severity::debug, "[gtb200] pool ", thread_id, ": ", recs.core.size(), " records (", n_dup,
               " equal to their predecessor)");
+  }
+
+  if (too_long)
+  {
+    // The reference has no read-length limit in call() (MAX_READ_LENGTH is only a default variant distance); the device
+    // path holds 152 bases per read.  Nothing has touched the device yet: this pool runs the reference's CPU code.
+    print_log(log_severity::warning, "[gtb200] pool ", thread_id, " holds a read longer than ", GTB_SEQ_STRIDE * 2,
+              " bases: reference CPU path");
+    recs = gtb_shim::Records();
+    PHIndex const cpu_index = index_graph_cpu(graph);
+    parallel_reader_genotype_only_cpu(thread_id, out_path, hts_paths_ptr, avg_cov_ptr, output_dir_ptr, reference_fn_ptr,
+                                      region_ptr, &cpu_index, primers, ph_ptr, is_writing_calls_vcf, is_writing_hap,
+                                      allele_hap_gts_ptr);
+    return;
   }
 
   // ---- the device part: one context per pool thread on the shared region
