@@ -52,6 +52,17 @@ def _run_both(args, tmp, extra_env=None):
         assert ref[k] == gtb[k], f"{k}: the drop-in binary's VCF differs from the reference's"
         n_records += sum(1 for line in ref[k].splitlines() if line and not line.startswith("#"))
     assert "CPU path" not in outs["graphtyper_gtb"][1], outs["graphtyper_gtb"][1][-2000:]
+    # N4: the pools' calls reach the merge through memory (integration/gtb_vcf_store.cpp) -- with --no_cleanup the
+    # reference leaves its cereal + gzip batch files <tmp>/graphtyper_*/it1/<first sample>/<n> behind, the drop-in none
+    left = {}
+    for exe in ("graphtyper", "graphtyper_gtb"):
+        t2 = os.path.join(tmp, "keep_" + exe)
+        os.makedirs(t2)
+        r = subprocess.run([os.path.join(BIN, exe)] + args + [f"--output={os.path.join(t2, 'out')}", "--no_cleanup"],
+                           capture_output=True, text=True, env=dict(os.environ, TMPDIR=t2), timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        left[exe] = [f for f in glob.glob(os.path.join(t2, "graphtyper_*", "it*", "*", "*")) if os.path.basename(f).isdigit()]
+    assert left["graphtyper"] and not left["graphtyper_gtb"], left
     return n_records
 
 
