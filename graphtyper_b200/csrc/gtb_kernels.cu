@@ -1734,7 +1734,7 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
     int const bshift = R.table_shift - 34 + (use_filter && fold > 0 ? fold : 0); // hash -> presence bit index
     int const tshift = R.table_shift - 32;                                        // hash -> table slot
     const uint4 * const table = reinterpret_cast<const uint4 *>(R.table);
-    const uint32_t * const bitmap = R.bitmap;
+    const uint32_t * const fbase = use_filter ? s_filter : R.bitmap; // presence bits: shared filter, else the global bitmap
 
     // per-warp software pipeline over its tasks: the task id / record / length of the NEXT task are requested while the
     // current one is processed (a dependent chain of three global loads otherwise opens every task)
@@ -1801,7 +1801,7 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
         for (int q = 0; q < 3; ++q)
         {
           nb[q] = (kh ^ hm[q]) >> bshift;
-          nw[q] = use_filter ? s_filter[nb[q] >> 5] : __ldg(bitmap + (nb[q] >> 5));
+          nw[q] = fbase[nb[q] >> 5];
         }
         uint64_t const val = (uint64_t)v << (2 * (31 - lane));
         uint32_t const lo = __reduce_or_sync(FULL, (uint32_t)val);
@@ -1867,15 +1867,10 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
         unsigned const fm = __ballot_sync(FULL, hit);
         if (fm == 0 || dropped)
           return;
-        uint32_t inc = hit ? cnt : 0u;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
-        {
-          uint32_t const tt = __shfl_up_sync(FULL, inc, d);
-          if (lane >= d)
-            inc += tt;
-        }
-        if (__any_sync(FULL, hit && (total + inc) > 75u)) // PHIndex::multi_get give-up rule (ph_index.cpp:84-89)
+        // PHIndex::multi_get gives the slot up as soon as the running label count passes 75 (ph_index.cpp:84-89); every
+        // bucket holds at least one label, so the running count peaks at its end: one warp sum decides
+        uint32_t const sum = __reduce_add_sync(FULL, hit ? cnt : 0u);
+        if (total + sum > 75u)
         {
           dropped = true;
           return;
@@ -1887,7 +1882,7 @@ __global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(Launch
           reflist[pos] = (uint8_t)(2 * i + 1);
         }
         nrefs += __popc(fm);
-        total += __shfl_sync(FULL, inc, 31);
+        total += sum;
       };
       auto exact_hit = [&](int i, uint32_t off, uint32_t cnt, int src_lane, uint32_t & c0) { // exact-match list: 1 key, never dropped
         if (nrefs < SEED_INLINE)
