@@ -7,7 +7,7 @@ each with its own graph + k-mer index.  One "step" = one pass of the hot path ov
 (all 20 regions in ONE region-batched launch sequence: prep, probe, chain, chain_general, slow, huge, score kernels).
 
 Steps are issued the way the reference issues pools: one pool per worker thread (paw::Station, caller.cpp:272-391), all
-threads sharing one index.  Here: GTB_BENCH_THREADS (default 3) host threads, one context each, the regions shared through
+threads sharing one index.  Here: GTB_BENCH_THREADS (default 4) host threads, one context each, the regions shared through
 gtb_region_attach, every context with its own sample (read set); the K timed steps are dealt round-robin to the threads
 and run back to back, so one step's tail (general / slow tiers, second score pass, D2H) overlaps the next step's front.
 
@@ -413,7 +413,7 @@ def cli_end_to_end(ref, sites, rs, regions):
                 "speedup": res["graphtyper"] / res["graphtyper_gtb"], "vcf_files": len(text["graphtyper"]),
                 "vcf_records": n_rec, "vcfs_identical": bool(same), "reads": int(len(rs)),
                 "note": "one process, --threads=1 (one sample), 20 regions from one indexed BAM incl. bamshrink, graph "
-                        "construction, VCF merge + BGZF; best of 4 runs each; the drop-in runs include ~0.6 s of CUDA context creation, steady_state_s_per_region (median time between the regions' "Finished!" log lines) does not"}
+                        "construction, VCF merge + BGZF; best of 4 runs each; the drop-in runs include ~0.6 s of CUDA context creation, steady_state_s_per_region (median time between the regions' 'Finished!' log lines) does not"}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -499,7 +499,7 @@ def main() -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     host_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    n_threads = max(1, env_int("GTB_BENCH_THREADS", 3))
+    n_threads = max(1, env_int("GTB_BENCH_THREADS", 4))
     steps, warmup = max(1, args.steps), max(3, args.warmup)
 
     # ---- one read set (sample) per context; the graph is the same for all
@@ -553,6 +553,12 @@ def main() -> None:
         torch.cuda.synchronize()
 
     h2d_bytes = sum(b.nbytes_h2d() for b in batches[0])
+
+    # with several pool threads the overlap of copies and kernels comes from the other pools: one launch sequence per submit;
+    # a lone pool thread keeps the library's automatic 4-chunk pipeline
+    e2e_chunks = env_int("GTB_BENCH_E2E_CHUNKS", 1 if n_threads > 1 else 0)
+    for c in ctxs:
+        c.set_chunks(e2e_chunks)
 
     def e2e_step(t, s=0):
         c = ctxs[t]
@@ -638,6 +644,9 @@ def main() -> None:
 
     # one step alone through the same calls (what a single pool thread sees)
     single_e2e = []
+    ctxs[0].set_chunks(0)  # a lone pool thread: the library's own copy / compute pipeline
+    for _ in range(3):
+        e2e_step(0)  # (its chunk buffers are allocated on first use)
     for _ in range(5):
         flush_l2()
         t0 = time.perf_counter()
@@ -723,8 +732,9 @@ def main() -> None:
                   "with a 256 MiB L2 flush before every step",
             "value_path": "device-resident: reset + replay of the resident launch sequence (prep, probe, chain, chain_general, "
                           "slow, huge, score x2), K steps over %d pool threads" % n_threads,
-            "e2e_path": "gtb_pool_reset_multi + gtb_submit_reads_multi (4 concurrent chunks) + gtb_pool_finish_multi, pinned "
-                        "host buffers, K steps over %d pool threads sharing the regions (gtb_region_attach)" % n_threads
+            "e2e_path": "gtb_pool_reset_multi + gtb_submit_reads_multi (%s) + gtb_pool_finish_multi, pinned "
+                        "host buffers, K steps over %d pool threads sharing the regions (gtb_region_attach)"
+                        % ("one launch sequence per submit" if e2e_chunks == 1 else "the library's concurrent chunks", n_threads)
                         + ("; the job ends with ONE NCCL reduce of the per-variant summaries" if world > 1 else ""),
             "host_cores": host_cores})
         out = {

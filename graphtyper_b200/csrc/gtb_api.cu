@@ -346,7 +346,15 @@ public:
         fn(i);
       return;
     }
-    std::lock_guard<std::mutex> serial(run_m_);
+    // one fork-join at a time; a caller that finds the pool busy (another context's submit is staging) does its own
+    // blocks inline instead of queueing behind it -- several pool threads then stage in parallel
+    std::unique_lock<std::mutex> serial(run_m_, std::try_to_lock);
+    if (!serial.owns_lock())
+    {
+      for (int i = 0; i < n; ++i)
+        fn(i);
+      return;
+    }
     {
       std::lock_guard<std::mutex> lk(m_);
       fn_ = &fn;
