@@ -418,9 +418,10 @@ def cli_end_to_end(ref, sites, rs, regions):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
-def run_pipelined(n_threads: int, steps: int, fn):
-    """steps calls of fn(thread, step) dealt round-robin to n_threads host threads; returns wall seconds from the common
-    start to the last thread's end (the callers bracket it with barrier + synchronize and CUDA events)."""
+def run_pipelined(n_threads: int, steps: int, fn, at_end=None):
+    """steps calls of fn(thread, step) dealt round-robin to n_threads host threads (then at_end(thread), if given); returns
+    wall seconds from the common start to the last thread's end (the callers bracket it with barrier + synchronize and CUDA
+    events)."""
     bar = threading.Barrier(n_threads + 1)
     errors = []
 
@@ -429,6 +430,8 @@ def run_pipelined(n_threads: int, steps: int, fn):
             bar.wait()
             for s in range(t, steps, n_threads):
                 fn(t, s)
+            if at_end is not None:
+                at_end(t)
         except Exception as ex:
             errors.append(ex)
         finally:
@@ -499,7 +502,15 @@ def main() -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     host_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    n_threads = max(1, env_int("GTB_BENCH_THREADS", 4))
+    if world > 1 and hasattr(os, "sched_setaffinity") and not os.environ.get("GTB_BENCH_NO_PIN"):
+        # one slice of the node's cores per rank: the ranks' pool and staging threads stop migrating over each other
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // world)
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        os.environ["GTB_HOST_THREADS"] = str(len(mine))
+    # pool threads per rank: 4, fewer when the ranks of the node have to share the host cores
+    n_threads = max(1, env_int("GTB_BENCH_THREADS", max(2, min(4, host_cores // max(1, world) - 1))))
     steps, warmup = max(1, args.steps), max(3, args.warmup)
 
     # ---- one read set (sample) per context; the graph is the same for all
@@ -611,15 +622,28 @@ def main() -> None:
             sys.exit(1)
 
     # ---- e2e: host buffers through the public C-ABI calls, K steps back to back over n_threads pool threads
+    # sample-sharded job end (N > 1): every pool thread summarises its own pools when it is done, as the reference's pool
+    # threads do (Variant::scan_calls inside parallel_reader_genotype_only, hts_parallel_reader.cpp:1018-1022); then ONE
+    # reduce: the rank's pools are merged while they are packed, NCCL sum / max over the ranks
+    per_ctx = [None] * len(ctxs)
+
+    def summarise(t):
+        per_ctx[t] = ctxs[t].scan_calls_multi(acc_bufs[t])
+
     def final_reduce():
-        # sample-sharded job end: per-variant summaries of the local pools, then ONE NCCL reduce over the ranks
-        per_ctx = [ctxs[t].scan_calls_multi(acc_bufs[t]) for t in range(len(ctxs))]
-        V, A, R = per_ctx[0]
-        for v, a, r in per_ctx[1:]:  # cross-pool merge on this rank (VarStats::add_stats)
-            owner.merge_varstats(V, A, R, v, a, r)
         t0 = time.perf_counter()
-        owner.allreduce_varstats(V, A, R)
-        return time.perf_counter() - t0, int(V.sum() % (1 << 62))
+        for t in range(len(ctxs)):
+            if per_ctx[t] is None:
+                summarise(t)
+        t1 = time.perf_counter()
+        owner.allreduce_varstats_multi(per_ctx)
+        t2 = time.perf_counter()
+        V, A, R = per_ctx[0]
+        out = {"leftover_scan_calls_ms": (t1 - t0) * 1e3, "merge_and_nccl_ms": (t2 - t1) * 1e3,
+               "checksum": int(V.sum() % (1 << 62)), "bytes_reduced": int(V.nbytes + A.nbytes + R.nbytes)}
+        for t in range(len(ctxs)):
+            per_ctx[t] = None
+        return out
 
     for s in range(warmup):
         e2e_step(s % n_threads)
@@ -628,13 +652,12 @@ def main() -> None:
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    wall_e2e = run_pipelined(n_threads, steps, e2e_step)
+    wall_e2e = run_pipelined(n_threads, steps, e2e_step, at_end=summarise if world > 1 else None)
     t_reduce = None
     if world > 1:
         tr0 = time.perf_counter()
-        t_nccl, reduce_checksum = final_reduce()
-        t_reduce = {"final_reduce_ms": (time.perf_counter() - tr0) * 1e3, "nccl_part_ms": t_nccl * 1e3,
-                    "checksum": reduce_checksum}
+        t_reduce = final_reduce()
+        t_reduce["final_reduce_ms"] = (time.perf_counter() - tr0) * 1e3
         wall_e2e += time.perf_counter() - tr0
     torch.cuda.synchronize()
     ev1.record()

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <dlfcn.h>
 
 #include "gtb_device.cuh"
@@ -191,6 +192,7 @@ struct Ctx
   cudaStream_t copy_stream = nullptr;
   cudaStream_t copy_stream2 = nullptr; // second H2D queue: per-region copies of < 1 MB do not reach PCIe peak one at a time
   cudaEvent_t ev_copy2 = nullptr;
+  cudaEvent_t ev_block = nullptr; // wait_stream() in blocking mode
   BatchState bs[MAX_CHUNKS];
   int n_chunks_last = 0;
   std::map<int, std::unique_ptr<Region>> regions;
@@ -266,6 +268,31 @@ void give_buffer(Ctx * c, DeviceBuffer & b)
   b.cap = 0;
 }
 
+// Waits for everything queued on the main stream.  Spinning (cudaStreamSynchronize) has the lowest latency; with several
+// ranks and pool threads per node every waiting thread would burn a core, so there the wait sleeps on an event created with
+// cudaEventBlockingSync -- measured on the bench workload that costs more than it saves (wake-up latency on every submit and
+// finish: 0.94 -> 1.27 ms per step with 4 pool threads), so spinning is the default and GTB_SYNC=block the opt-in for nodes
+// that are short of cores.
+cudaError_t wait_stream(Ctx * c)
+{
+  static int const mode = []() {
+    const char * e = getenv("GTB_SYNC");
+    return e && strcmp(e, "block") == 0 ? 1 : 0;
+  }();
+  if (mode == 0)
+    return cudaStreamSynchronize(c->stream);
+  if (!c->ev_block)
+  {
+    cudaError_t const e = cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess)
+      return e;
+  }
+  cudaError_t e = cudaEventRecord(c->ev_block, c->stream);
+  if (e == cudaSuccess)
+    e = cudaEventSynchronize(c->ev_block);
+  return e;
+}
+
 int upload_region_table(Ctx * c)
 {
   if (!c->regions_dirty)
@@ -278,7 +305,7 @@ int upload_region_table(Ctx * c)
   if (int rc = c->d_regions.reserve(tab.size() * sizeof(DevRegion)))
     return rc;
   CUDA_TRY(cudaMemcpyAsync(c->d_regions.p, tab.data(), tab.size() * sizeof(DevRegion), cudaMemcpyHostToDevice, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(wait_stream(c));
   c->regions_dirty = false;
   return 0;
 }
@@ -320,8 +347,19 @@ class WorkPool
 public:
   WorkPool()
   {
-    int const hw = (int)std::thread::hardware_concurrency();
-    n_workers_ = std::max(1, std::min(8, hw > 0 ? hw : 1)) - 1; // the caller thread works too
+    // cores this process may use, shared with the other ranks of the node (torchrun exports LOCAL_WORLD_SIZE): 8 ranks
+    // with 8 staging threads each on a 32-core box only fight each other
+    int hw = (int)std::thread::hardware_concurrency();
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0)
+      hw = CPU_COUNT(&set);
+    int local_world = 1;
+    if (const char * e = getenv("LOCAL_WORLD_SIZE"))
+      local_world = std::max(1, atoi(e));
+    if (const char * e = getenv("GTB_HOST_THREADS"))
+      hw = std::max(1, atoi(e)) * local_world;
+    n_workers_ = std::max(1, std::min(8, (hw > 0 ? hw : 1) / local_world)) - 1; // the caller thread works too
     for (int t = 0; t < n_workers_; ++t)
       threads_.emplace_back([this]() { worker(); });
   }
@@ -425,7 +463,7 @@ int upload_segments(Ctx * c, int n, F make, unsigned long long & max_bytes)
   size_t const bytes = (size_t)n * sizeof(Segment);
   if (c->h_segments.cap < 2 * bytes)
   {
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(wait_stream(c));
     if (int rc = c->h_segments.reserve(2 * bytes))
       return rc;
   }
@@ -482,7 +520,7 @@ int conn_reserve(Ctx * c, Region & R, uint64_t n_new)
   if (int rc = conn_alloc(c, R, (uint32_t)ncap))
     return rc;
   launch_conn_rehash(old_dev.conn_keys, old_dev.conn_vals, old_cap, R.dev, c->stream);
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(wait_stream(c));
   give_buffer(c, old);
   return 0;
 }
@@ -613,6 +651,8 @@ void gtb_destroy(gtb_ctx * ctx)
       cudaStreamDestroy(c->copy_stream2);
     if (c->ev_copy2)
       cudaEventDestroy(c->ev_copy2);
+    if (c->ev_block)
+      cudaEventDestroy(c->ev_block);
 
     if (c->stream)
       cudaStreamDestroy(c->stream);
@@ -777,7 +817,7 @@ static int upload_region(Ctx * c, Region & R, const gtb_graph_view * g, bool dev
                        reinterpret_cast<IndexSlot *>(d + o_table), R.index.table_mask, R.index.table_shift,
                        reinterpret_cast<uint32_t *>(d + o_bitmap), c->stream);
   }
-  CUDA_TRY(cudaStreamSynchronize(c->stream)); // h_stage is reused by the next region
+  CUDA_TRY(wait_stream(c)); // h_stage is reused by the next region
   CUDA_TRY(cudaGetLastError());
 
   DevRegion & D = R.dev;
@@ -925,7 +965,7 @@ static int build_indexes_on_device(Ctx * c, std::vector<std::unique_ptr<Region>>
   idx_launch_region_totals(d_joff, d_rjo, n, d_rto, c->stream);
   CUDA_TRY(cudaMemcpyAsync(hs + o_rto, d_rto, (n + 1) * 4 + 0, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaMemcpyAsync(hs + o_err, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(wait_stream(c));
   CUDA_TRY(cudaGetLastError());
   const uint32_t * rto = reinterpret_cast<const uint32_t *>(hs + o_rto);
   if (*reinterpret_cast<const uint32_t *>(hs + o_err))
@@ -1004,7 +1044,7 @@ static int build_indexes_on_device(Ctx * c, std::vector<std::unique_ptr<Region>>
     idx_launch_group(d_desc, k2, i2, le, head, head + total, c->d_idx_temp.p, c->d_idx_temp.cap, d_rto, n, total, d_nu, c->stream);
   }
   CUDA_TRY(cudaMemcpyAsync(hs + o_nu, d_nu, n * 4, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(wait_stream(c));
   CUDA_TRY(cudaGetLastError());
   const uint32_t * nu = reinterpret_cast<const uint32_t *>(hs + o_nu);
   for (uint32_t i = 0; i < n; ++i)
@@ -1411,7 +1451,7 @@ static int launch_back(Ctx * c, int n_chunks)
 // After the stream has been synchronised: timings, counters, errors of all chunks of the last submit/replay.
 static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
 {
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(wait_stream(c));
   CUDA_TRY(cudaGetLastError());
   if (c->debug && c->n_chunks_last == 1 && c->bs[0].unit_begin.empty())
   {
@@ -1836,7 +1876,7 @@ static int conn_check(Ctx * c, int n, Region * const * regs)
   for (int i = 0; i < n; ++i)
     if (regs[i]->conn_cap)
       CUDA_TRY(cudaMemcpyAsync(h + 2 * k++, regs[i]->dev.conn_state, 8, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(wait_stream(c));
   k = 0;
   bool full = false;
   for (int i = 0; i < n; ++i)
@@ -2403,7 +2443,7 @@ int gtb_pool_finish_multi(gtb_ctx * ctx, int n, const int * region_ids, gtb_accu
     launch_gather_segments(static_cast<const Segment *>(c->d_segments.p), n, max_bytes, c->d_gather.p, c->stream);
     CUDA_TRY(cudaMemcpyAsync(h, c->d_gather.p, off[n], cudaMemcpyDeviceToHost, c->stream));
   }
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(wait_stream(c));
   CUDA_TRY(cudaGetLastError());
   parallel_for(n, [&](int i) { convert_accumulators(*regs[i], h + off[i], &outs[i]); });
   return 0;
@@ -2476,7 +2516,7 @@ static int conn_fetch(Ctx * c, Region & R, std::vector<gtb_connection> & out)
   cudaSetDevice(c->device);
   uint32_t st[2] = {0, 0};
   CUDA_TRY(cudaMemcpyAsync(st, R.dev.conn_state, 8, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(wait_stream(c));
   uint32_t const n = st[0];
   if (n == 0)
     return 0;
@@ -2493,7 +2533,7 @@ static int conn_fetch(Ctx * c, Region & R, std::vector<gtb_connection> & out)
   std::vector<uint32_t> vals(n);
   CUDA_TRY(cudaMemcpyAsync(keys.data(), d_keys, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaMemcpyAsync(vals.data(), d_vals, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(wait_stream(c));
   CUDA_TRY(cudaGetLastError());
   give_buffer(c, d);
   std::vector<uint32_t> order(n);
@@ -3283,7 +3323,7 @@ int gtb_allreduce_accumulators_multi(gtb_ctx * ctx, int n, const int * region_id
   }
   if (r != 0)
     return fail(GTB_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(wait_stream(c));
   return 0;
 }
 
@@ -3296,11 +3336,11 @@ int gtb_allreduce_accumulators(gtb_ctx * ctx, int region_id, void * nccl_comm)
 // (src/typer/var_stats.cpp:141-189) as three collectives in ONE NCCL group: sum over every counter, max over
 // maximum_alt_support (column 8 of the allele rows) and over maximum_alt_support_ratio; n_max_alt_proper_pairs (column 3 of
 // the var rows) is summed as the reference's uint8 does.  The arrays may cover any number of regions back to back.
-int gtb_allreduce_varstats(gtb_ctx * ctx, uint64_t n_var_rows, uint64_t n_allele_rows, uint64_t * var, uint64_t * allele,
-                           double * ratio, void * nccl_comm)
+int gtb_allreduce_varstats_multi(gtb_ctx * ctx, int n_src, uint64_t n_var_rows, uint64_t n_allele_rows, uint64_t * const * var,
+                                 uint64_t * const * allele, double * const * ratio, void * nccl_comm)
 {
   auto * c = reinterpret_cast<Ctx *>(ctx);
-  if (!c || !var || !allele || !ratio)
+  if (!c || n_src <= 0 || !var || !allele || !ratio)
     return fail(GTB_ERR_ARG, "bad arguments");
   if (c->device < 0)
     return fail(GTB_ERR_CUDA, "host-only context");
@@ -3310,21 +3350,56 @@ int gtb_allreduce_varstats(gtb_ctx * ctx, uint64_t n_var_rows, uint64_t n_allele
   if (int rc = load_nccl())
     return rc;
   cudaSetDevice(c->device);
-  size_t const n_sum = (size_t)n_var_rows * 9 + (size_t)n_allele_rows * 13, n_max = (size_t)n_allele_rows;
+  size_t const nv = (size_t)n_var_rows * 9, na = (size_t)n_allele_rows * 13;
+  size_t const n_sum = nv + na, n_max = (size_t)n_allele_rows;
   size_t const bytes = (n_sum + 2 * n_max) * 8;
   if (int rc = c->h_varstats.reserve(bytes))
     return rc;
   if (int rc = c->d_varstats.reserve(bytes))
     return rc;
   uint64_t * h = static_cast<uint64_t *>(c->h_varstats.p);
-  memcpy(h, var, (size_t)n_var_rows * 9 * 8);
-  memcpy(h + (size_t)n_var_rows * 9, allele, (size_t)n_allele_rows * 13 * 8);
   uint64_t * hmax = h + n_sum;
   double * hratio = reinterpret_cast<double *>(hmax + n_max);
-  for (size_t a = 0; a < n_max; ++a)
+  // pack = the cross-pool merge of this rank's pools (VarStats::add_stats over the sources), in parallel blocks
   {
-    hmax[a] = allele[a * 13 + 8];
-    hratio[a] = ratio[a];
+    constexpr size_t BLK = 1 << 15;
+    size_t const n_blk_v = (nv + BLK - 1) / BLK, n_blk_a = (n_max + (BLK / 16) - 1) / (BLK / 16);
+    parallel_for((int)(n_blk_v + n_blk_a), [&](int bi)
+                 {
+                   if ((size_t)bi < n_blk_v)
+                   {
+                     size_t const lo = (size_t)bi * BLK, hi = std::min(nv, lo + BLK);
+                     for (size_t i = lo; i < hi; ++i)
+                     {
+                       uint64_t v = 0;
+                       for (int k = 0; k < n_src; ++k)
+                         v += var[k][i];
+                       h[i] = v;
+                     }
+                     return;
+                   }
+                   size_t const lo = ((size_t)bi - n_blk_v) * (BLK / 16), hi = std::min(n_max, lo + BLK / 16);
+                   for (size_t a = lo; a < hi; ++a)
+                   {
+                     uint64_t mx = 0;
+                     double mr = 0.0;
+                     for (int col = 0; col < 13; ++col)
+                     {
+                       uint64_t v = 0;
+                       for (int k = 0; k < n_src; ++k)
+                         v += allele[k][a * 13 + col];
+                       h[nv + a * 13 + col] = v;
+                     }
+                     for (int k = 0; k < n_src; ++k)
+                     {
+                       mx = std::max(mx, allele[k][a * 13 + 8]);
+                       mr = std::max(mr, ratio[k][a]);
+                     }
+                     h[nv + a * 13 + 8] = 0; // maximum_alt_support travels in the max block
+                     hmax[a] = mx;
+                     hratio[a] = mr;
+                   }
+                 });
   }
   uint64_t * d = static_cast<uint64_t *>(c->d_varstats.p);
   CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -3345,19 +3420,24 @@ int gtb_allreduce_varstats(gtb_ctx * ctx, uint64_t n_var_rows, uint64_t n_allele
   if (r != 0)
     return fail(GTB_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
   CUDA_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
-  memcpy(var, h, (size_t)n_var_rows * 9 * 8);
-  memcpy(allele, h + (size_t)n_var_rows * 9, (size_t)n_allele_rows * 13 * 8);
-  for (size_t b = 0; b < n_var_rows; ++b)
-    var[b * 9 + 3] &= 0xFFu;
+  CUDA_TRY(wait_stream(c));
+  memcpy(var[0], h, nv * 8);
+  memcpy(allele[0], h + nv, na * 8);
+  for (size_t b2 = 0; b2 < n_var_rows; ++b2)
+    var[0][b2 * 9 + 3] &= 0xFFu; // n_max_alt_proper_pairs is a uint8 the reference sums
   for (size_t a = 0; a < n_max; ++a)
   {
-    allele[a * 13 + 8] = hmax[a];
-    ratio[a] = hratio[a];
+    allele[0][a * 13 + 8] = hmax[a];
+    ratio[0][a] = hratio[a];
   }
   return 0;
 }
 
+int gtb_allreduce_varstats(gtb_ctx * ctx, uint64_t n_var_rows, uint64_t n_allele_rows, uint64_t * var, uint64_t * allele,
+                           double * ratio, void * nccl_comm)
+{
+  return gtb_allreduce_varstats_multi(ctx, 1, n_var_rows, n_allele_rows, &var, &allele, &ratio, nccl_comm);
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Discovery re-alignment: batch of (read, haplotype window) pairs through sw_kernel (gtb_sw.cu).
@@ -3423,7 +3503,7 @@ int gtb_sw_align_batch(gtb_ctx * ctx, int n_pairs, const uint8_t * query, const 
   // the input staging area is reused for the results once the H2D copy has been consumed (same stream => ordered)
   CUDA_TRY(cudaMemcpyAsync(h, c->d_sw_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaEventRecord(c->sw_ev[3], c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(wait_stream(c));
   memcpy(out, h, out_bytes);
   cudaEventElapsedTime(&c->t_sw_h2d, c->sw_ev[0], c->sw_ev[1]);
   cudaEventElapsedTime(&c->t_sw_kernel, c->sw_ev[1], c->sw_ev[2]);
@@ -3442,7 +3522,7 @@ int gtb_sw_replay_last(gtb_ctx * ctx)
   launch_sw(c->sw_last, c->sw_warps, c->stream);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(c->sw_ev[2], c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(wait_stream(c));
   cudaEventElapsedTime(&c->t_sw_kernel, c->sw_ev[1], c->sw_ev[2]);
   return 0;
 }

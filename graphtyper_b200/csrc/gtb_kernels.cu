@@ -1623,7 +1623,10 @@ void launch_prep_fill(const PrepParams & p, void * stream)
 // The table hash is GF(2)-linear (gtb_device.cuh): hash(key) is one __reduce_xor_sync over per-lane words, the hash of a
 // neighbour one XOR with a per-lane constant.  PHIndex::multi_get's ">75 labels => drop the slot" rule is a warp scan over
 // the compacted hits.
-constexpr int PROBE_BLOCK_WARPS = 32;
+#ifndef GTB_PROBE_BLOCK_WARPS
+#define GTB_PROBE_BLOCK_WARPS 32
+#endif
+constexpr int PROBE_BLOCK_WARPS = GTB_PROBE_BLOCK_WARPS;
 constexpr uint32_t FILTER_LOG2_BITS = 20; // 128 KiB
 constexpr uint32_t FILTER_WORDS = 1u << (FILTER_LOG2_BITS - 5);
 constexpr int FILTER_MAX_FOLD = 2;        // log2: the bitmap is folded at most 4x
@@ -1641,7 +1644,7 @@ __device__ __forceinline__ uint32_t or_fold2(uint32_t x) // bit j of the result 
 }
 } // namespace
 
-__global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1) probe_kernel(LaunchParams P)
+__global__ void __launch_bounds__(PROBE_BLOCK_WARPS * 32, 1024 / (PROBE_BLOCK_WARPS * 32)) probe_kernel(LaunchParams P)
 {
   extern __shared__ __align__(16) uint32_t s_filter[]; // FILTER_WORDS
   __shared__ uint16_t s_cand[PROBE_BLOCK_WARPS][4 * 97 + 4]; // candidates of a task, slot-major and in key order:

@@ -27,6 +27,7 @@ EXPORTS = [
     "gtb_set_connections", "gtb_connections_size", "gtb_connections", "gtb_phase_support", "gtb_last_prep_timing",
     "gtb_submit_bam_records", "gtb_submit_bam_records_multi", "gtb_debug_bam_columns", "gtb_merge_connections", "gtb_sample_depths",
     "gtb_last_chain_timing", "gtb_region_attach", "gtb_allreduce_varstats", "gtb_scan_calls_multi",
+    "gtb_allreduce_varstats_multi",
 ]
 
 
@@ -451,6 +452,17 @@ class Context:
         self._check(self.lib.gtb_allreduce_varstats(self.h, len(var) // 9, len(ratio), var.ctypes.data_as(abi.u64p),
                                                     allele.ctypes.data_as(abi.u64p),
                                                     ratio.ctypes.data_as(C.POINTER(C.c_double)), None))
+
+    def allreduce_varstats_multi(self, triples) -> None:
+        """Merges the (var, allele, ratio) summaries of this rank's pools and reduces them over the ranks; result in triples[0]."""
+        n = len(triples)
+        dp = C.POINTER(C.c_double)
+        V = (abi.u64p * n)(*[t[0].ctypes.data_as(abi.u64p) for t in triples])
+        A = (abi.u64p * n)(*[t[1].ctypes.data_as(abi.u64p) for t in triples])
+        R = (dp * n)(*[t[2].ctypes.data_as(dp) for t in triples])
+        fn = self.lib.gtb_allreduce_varstats_multi
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(abi.u64p), C.POINTER(abi.u64p), C.POINTER(dp), C.c_void_p]
+        self._check(fn(self.h, n, len(triples[0][0]) // 9, len(triples[0][2]), V, A, R, None))
 
     def nccl_unique_id(self) -> np.ndarray:
         buf = np.zeros(128, np.uint8)

@@ -368,6 +368,11 @@ int gtb_allreduce_accumulators_multi(gtb_ctx *ctx, int n, const int *region_ids,
  * n_allele_rows alleles in total); in place, result valid on every rank. */
 int gtb_allreduce_varstats(gtb_ctx *ctx, uint64_t n_var_rows, uint64_t n_allele_rows, uint64_t *var, uint64_t *allele,
                            double *ratio, void *nccl_comm);
+/* The same with the cross-pool merge of this rank's own pools folded in: n_src summaries of the same regions (one per pool
+ * thread) are merged (VarStats::add_stats) while they are packed for the collective; the result lands in var[0] / allele[0] /
+ * ratio[0]. */
+int gtb_allreduce_varstats_multi(gtb_ctx *ctx, int n_src, uint64_t n_var_rows, uint64_t n_allele_rows, uint64_t *const *var,
+                                 uint64_t *const *allele, double *const *ratio, void *nccl_comm);
 
 /* Discovery re-alignment.  Replaces paw::pairwise_alignment(read, haplotype window, opts)
  * + AlignmentResults::get_database_begin_end + apply_clipping as realign_to_indels calls them

@@ -47,9 +47,17 @@ for k, pre in enumerate(pres):
     ev, ea, er = var.copy(), allele.copy(), ratio.copy()
     for _ in range(world - 1):
         ctx.merge_varstats(ev, ea, er, var, allele, ratio)
-    ctx.allreduce_varstats(var, allele, ratio)
-    if not (np.array_equal(var, ev) and np.array_equal(allele, ea) and np.array_equal(ratio, er)):
+    v1, a1, r1 = var.copy(), allele.copy(), ratio.copy()
+    ctx.allreduce_varstats(v1, a1, r1)
+    if not (np.array_equal(v1, ev) and np.array_equal(a1, ea) and np.array_equal(r1, er)):
         ok = False; print("FAIL varstats", os.path.basename(pre), "rank", rank)
+    # two pools per rank merged while packing (gtb_allreduce_varstats_multi) = 2 * world host merges
+    for _ in range(world):
+        ctx.merge_varstats(ev, ea, er, var, allele, ratio)
+    trip = [(var.copy(), allele.copy(), ratio.copy()), (var.copy(), allele.copy(), ratio.copy())]
+    ctx.allreduce_varstats_multi(trip)
+    if not (np.array_equal(trip[0][0], ev) and np.array_equal(trip[0][1], ea) and np.array_equal(trip[0][2], er)):
+        ok = False; print("FAIL varstats multi", os.path.basename(pre), "rank", rank)
     ctx.region_end(k)
 flag = torch.tensor([1 if ok else 0], device=f"cuda:{lr}")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
