@@ -302,7 +302,7 @@ def sw_key(ctx):
     """Discovery re-alignment kernel (N1): pairs/s, GCUPS and the share of the integer-issue peak, next to compiled paw."""
     from graphtyper_b200 import engine, synth
     n_pairs = 100000
-    q0, d0 = synth.make_sw_pairs(20000, seed=3, min_db=400, max_db=520, min_query=20)
+    q0, d0 = synth.make_sw_pairs(20000, seed=3, min_db=400, max_db=520, min_query=140)  # reads of 140-151 bp, as realign_to_indels sees
     q, d = (q0 * 5)[:n_pairs], (d0 * 5)[:n_pairs]
     qb, qo = engine.pack_sequences(q)
     db, do = engine.pack_sequences(d)
