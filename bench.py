@@ -382,8 +382,10 @@ def cli_end_to_end(ref, sites, rs, regions):
                 if name.endswith("+files"):
                     env["GTB200_VCF_FILES"] = "1"  # pool results through the reference's cereal + gzip files again
                 log = os.path.join(tmp, f"log_{name}.txt")
+                if os.path.exists(log):
+                    os.unlink(log)
                 r = subprocess.run([exe[name.split("+")[0]], "genotype", fa, f"--sam={bam}", f"--region_file={rf}",
-                                    f"--vcf={vcf}.gz", "--threads=1", f"--output={out}", f"--log={log}"],
+                                    f"--vcf={vcf}.gz", "--threads=1", f"--output={out}", "--verbose", f"--log={log}"],
                                    capture_output=True, text=True, env=env)
                 times.append(time.perf_counter() - t0)
                 if r.returncode != 0:
@@ -392,7 +394,7 @@ def cli_end_to_end(ref, sites, rs, regions):
             res[name + " median"] = float(np.median(times))
             # steady state per region from the tool's own log: time between consecutive "Finished! Output written" lines
             stamps = []
-            with open(os.path.join(tmp, f"log_{name}.txt")) as f:
+            with open(os.path.join(tmp, f"log_{name}.txt")) as f:  # (the log of the last run)
                 for line in f:
                     m = _TS.match(line.replace("<info> ", "<info> x:0 ", 1)) if "Finished! Output written" in line else None
                     if m:
