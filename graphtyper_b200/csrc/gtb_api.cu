@@ -26,6 +26,7 @@
 
 #include <cuda_runtime.h>
 #include <sched.h>
+#include <time.h>
 #include <dlfcn.h>
 
 #include "gtb_device.cuh"
@@ -119,6 +120,10 @@ struct Region
   uint32_t depth_size = 0, reference_offset = 0; // SV graphs only
   int n_samples = 0;
   bool pool_open = false;
+  // pool states that refuse further work until gtb_pool_reset / gtb_pool_begin:
+  bool poisoned = false; // a submit failed after (possibly) adding part of its batch to the accumulators
+  bool reduced = false;  // gtb_allreduce_accumulators summed the ranks' accumulators in place: another submit or another
+                         // reduce would count the other ranks' reads again
   bool borrowed = false; // gtb_region_attach: graph + index arenas belong to another context
   // device
   DeviceBuffer arena;   // graph + index (host-built index) or graph only (device-built index)
@@ -268,29 +273,46 @@ void give_buffer(Ctx * c, DeviceBuffer & b)
   b.cap = 0;
 }
 
-// Waits for everything queued on the main stream.  Spinning (cudaStreamSynchronize) has the lowest latency; with several
-// ranks and pool threads per node every waiting thread would burn a core, so there the wait sleeps on an event created with
-// cudaEventBlockingSync -- measured on the bench workload that costs more than it saves (wake-up latency on every submit and
-// finish: 0.94 -> 1.27 ms per step with 4 pool threads), so spinning is the default and GTB_SYNC=block the opt-in for nodes
-// that are short of cores.
+// Waits for everything queued on the main stream.  cudaStreamSynchronize spins: lowest latency, but with several ranks and
+// pool threads per node every waiting thread burns a core the staging threads need (8 ranks x 3 pool threads on a 32-core
+// box).  A wait that sleeps on a cudaEventBlockingSync event frees the core but wakes up late (measured: 0.94 -> 1.27 ms per
+// step with 4 pool threads).  Default = polite polling: cudaStreamQuery, giving the core away between polls (sched_yield),
+// short naps once the wait has lasted 200 us.  GTB_SYNC=spin|block selects the other two.
 cudaError_t wait_stream(Ctx * c)
 {
   static int const mode = []() {
     const char * e = getenv("GTB_SYNC");
-    return e && strcmp(e, "block") == 0 ? 1 : 0;
+    return !e ? 2 : strcmp(e, "block") == 0 ? 1 : strcmp(e, "spin") == 0 ? 0 : 2;
   }();
   if (mode == 0)
     return cudaStreamSynchronize(c->stream);
-  if (!c->ev_block)
+  if (mode == 1)
   {
-    cudaError_t const e = cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
-    if (e != cudaSuccess)
-      return e;
+    if (!c->ev_block)
+    {
+      cudaError_t const e = cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+      if (e != cudaSuccess)
+        return e;
+    }
+    cudaError_t e = cudaEventRecord(c->ev_block, c->stream);
+    if (e == cudaSuccess)
+      e = cudaEventSynchronize(c->ev_block);
+    return e;
   }
-  cudaError_t e = cudaEventRecord(c->ev_block, c->stream);
-  if (e == cudaSuccess)
-    e = cudaEventSynchronize(c->ev_block);
-  return e;
+  auto const t0 = std::chrono::steady_clock::now();
+  for (unsigned n = 0;; ++n)
+  {
+    cudaError_t const e = cudaStreamQuery(c->stream);
+    if (e != cudaErrorNotReady)
+      return e;
+    if ((n & 15u) == 15u && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200))
+    {
+      timespec ts{0, 20000}; // 20 us
+      nanosleep(&ts, nullptr);
+    }
+    else
+      sched_yield();
+  }
 }
 
 int upload_region_table(Ctx * c)
@@ -1345,6 +1367,7 @@ int gtb_pool_begin(gtb_ctx * ctx, int region_id, int n_samples)
   D.read_strand = reinterpret_cast<uint32_t *>(d + o_rs);
   R.n_samples = n_samples;
   R.pool_open = true;
+  R.poisoned = R.reduced = false;
   c->regions_dirty = true;
   D.conn_keys = nullptr;
   D.conn_vals = nullptr;
@@ -1564,9 +1587,6 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     return fail(GTB_ERR_CAPACITY, "read longer than 152 bases (reference MAX_READ_LENGTH is 151)");
   if (input_bits & PREP_ERR_RECORD)
     return fail(GTB_ERR_ARG, "malformed record: qname + cigar + seq + qual do not fit its data block");
-  if (input_bits & PREP_ERR_COLLISION)
-    return fail(GTB_ERR_INPUT, "two different read names share one 64-bit hash (nothing was mis-paired; resubmit through "
-                               "gtb_submit_reads with host-side mate links)");
   if (n_input_error)
     return fail(GTB_ERR_INPUT, "two mates with the same IS_FIRST_IN_PAIR flag (the reference aborts here, "
                                "hts_parallel_reader.cpp:306-315)");
@@ -1909,6 +1929,10 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
       return fail(GTB_ERR_STATE, "unknown region in submit");
     if (!it->second->pool_open)
       return fail(GTB_ERR_STATE, "gtb_pool_begin must precede gtb_submit_reads");
+    if (it->second->poisoned)
+      return fail(GTB_ERR_STATE, "an earlier submit on this pool failed: gtb_pool_reset before using it again");
+    if (it->second->reduced)
+      return fail(GTB_ERR_STATE, "the pool's accumulators were all-reduced in place: gtb_pool_reset before submitting again");
     regs[i] = it->second.get();
     if (batches[i].n_reads && batches[i].seq_stride != GTB_SEQ_STRIDE)
       return fail(GTB_ERR_ARG, "seq_stride must be GTB_SEQ_STRIDE (76)");
@@ -1996,7 +2020,11 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
             tr.c_str(), (int)since(), c->t_h2d * 1e3, c->t_prep * 1e3, c->t_probe * 1e3, c->t_chain * 1e3, c->t_score0 * 1e3,
             c->t_slow * 1e3, c->t_score1 * 1e3, c->t_total * 1e3);
   if (rc_collect)
+  {
+    for (Region * r : regs)
+      r->poisoned = true; // part of the batch may already sit in the accumulators (include/gtb200.h, gtb_pool_begin)
     return rc_collect;
+  }
   return conn_check(c, n, regs.data());
 }
 
@@ -2019,6 +2047,10 @@ int gtb_submit_bam_records_multi(gtb_ctx * ctx, int n, const int * region_ids, c
       return fail(GTB_ERR_STATE, "unknown region in submit");
     if (!it->second->pool_open)
       return fail(GTB_ERR_STATE, "gtb_pool_begin must precede gtb_submit_bam_records");
+    if (it->second->poisoned)
+      return fail(GTB_ERR_STATE, "an earlier submit on this pool failed: gtb_pool_reset before using it again");
+    if (it->second->reduced)
+      return fail(GTB_ERR_STATE, "the pool's accumulators were all-reduced in place: gtb_pool_reset before submitting again");
     regs[i] = it->second.get();
     gtb_bam_batch const & b = batches[i];
     if (b.n_reads && (!b.core || !b.data || !b.data_off || !b.sample || !b.rg))
@@ -2115,6 +2147,11 @@ int gtb_submit_bam_records_multi(gtb_ctx * ctx, int n, const int * region_ids, c
   Q.isize = reinterpret_cast<int32_t *>(d + Lo.o_isize);
   Q.mate = reinterpret_cast<int32_t *>(d + Lo.o_mate);
   Q.dup_of = reinterpret_cast<int32_t *>(d + Lo.o_dup);
+  {
+    const char * hb = getenv("GTB_BAM_HASH_BITS"); // tests: narrow the name hash so that different names share a run
+    int const bits = hb ? std::max(1, std::min(64, atoi(hb))) : 64;
+    Q.hash_mask = bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
+  }
   Q.name_hash = reinterpret_cast<unsigned long long *>(r + o_hash);
   Q.name_hash_sorted = reinterpret_cast<unsigned long long *>(r + o_hash2);
   Q.idx = reinterpret_cast<uint32_t *>(r + o_idx);
@@ -2129,7 +2166,11 @@ int gtb_submit_bam_records_multi(gtb_ctx * ctx, int n, const int * region_ids, c
     return rc;
   c->have_last = true;
   if (int rc = collect_chunks(c, stats, true))
+  {
+    for (Region * r : regs)
+      r->poisoned = true; // part of the batch may already sit in the accumulators
     return rc;
+  }
   return conn_check(c, n, regs.data());
 }
 
@@ -2325,6 +2366,7 @@ int gtb_pool_reset(gtb_ctx * ctx, int region_id)
   if (it == c->regions.end() || !it->second->pool_open)
     return fail(GTB_ERR_STATE, "unknown region / pool not open");
   cudaSetDevice(c->device);
+  it->second->poisoned = it->second->reduced = false;
   CUDA_TRY(cudaMemsetAsync(it->second->accum.p, 0, it->second->accum_bytes, c->stream));
   if (it->second->conn_cap)
     CUDA_TRY(cudaMemsetAsync(it->second->conn.p, 0, conn_table_bytes(it->second->conn_cap), c->stream));
@@ -2471,6 +2513,10 @@ int gtb_pool_finish(gtb_ctx * ctx, int region_id, gtb_accumulators * out)
 int gtb_pool_reset_multi(gtb_ctx * ctx, int n, const int * region_ids)
 {
   auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || n <= 0 || !region_ids)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  if (c->device < 0)
+    return fail(GTB_ERR_CUDA, "host-only context");
   cudaSetDevice(c->device);
   std::vector<Region *> regs(n);
   for (int i = 0; i < n; ++i)
@@ -2479,6 +2525,7 @@ int gtb_pool_reset_multi(gtb_ctx * ctx, int n, const int * region_ids)
     if (it == c->regions.end() || !it->second->pool_open)
       return fail(GTB_ERR_STATE, "unknown region / pool not open");
     regs[i] = it->second.get();
+    regs[i]->poisoned = regs[i]->reduced = false;
     if (regs[i]->conn_cap)
       CUDA_TRY(cudaMemsetAsync(regs[i]->conn.p, 0, conn_table_bytes(regs[i]->conn_cap), c->stream));
     regs[i]->conn_used = 0;
@@ -3297,6 +3344,8 @@ int gtb_allreduce_accumulators_multi(gtb_ctx * ctx, int n, const int * region_id
     auto it = c->regions.find(region_ids[i]);
     if (it == c->regions.end() || !it->second->pool_open)
       return fail(GTB_ERR_STATE, "unknown region / pool not open");
+    if (it->second->reduced)
+      return fail(GTB_ERR_STATE, "the pool's accumulators are already all-reduced (a second reduce would count every rank again)");
     regs[i] = it->second.get();
   }
   // one NCCL group for all regions: three typed spans per accumulator arena (u32 | u64 | u32 read_strand)
@@ -3324,6 +3373,8 @@ int gtb_allreduce_accumulators_multi(gtb_ctx * ctx, int n, const int * region_id
   if (r != 0)
     return fail(GTB_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
   CUDA_TRY(wait_stream(c));
+  for (Region * R : regs)
+    R->reduced = true;
   return 0;
 }
 

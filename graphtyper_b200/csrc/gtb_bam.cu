@@ -11,8 +11,8 @@
 //   cub::DeviceRadixSort (stable) of (hash, record index), then
 //   bam_mate_kernel    1 thread / run of equal hashes: genotype_only's read-name map (hts_parallel_reader.cpp:270-337) replayed
 //                      over the run in record order -- a record whose name waits pairs with it (paired flag or not), else a
-//                      paired record waits, an unpaired one stays alone; names are compared byte by byte (a hash collision is
-//                      reported, never mis-paired); SV graphs: what still waits is a leftover mate (:719-772)
+//                      paired record waits, an unpaired one stays alone; names are compared byte by byte, and a run that holds several
+//                      distinct names (a 64-bit hash collision) is replayed once per name; SV graphs: what still waits is a leftover mate (:719-772)
 #include <cstdint>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) bam_parse_kernel(BamParams p)
   h ^= h >> 33;
   h *= 0xFF51AFD7ED558CCDull;
   h ^= h >> 33;
-  p.name_hash[k] = h;
+  p.name_hash[k] = h & p.hash_mask; // all ones; tests narrow it (GTB_BAM_HASH_BITS) to force colliding names into one run
 }
 
 __global__ void __launch_bounds__(256) bam_seq_kernel(BamParams p)
@@ -232,41 +232,51 @@ __global__ void __launch_bounds__(128) bam_mate_kernel(BamParams p)
   unsigned long long const key = p.name_hash_sorted[q0];
   if (q0 > 0 && p.name_hash_sorted[q0 - 1] == key)
     return; // not the head of its run
-  uint32_t const head = p.idx_sorted[q0];
-  RecLoc const hloc = locate(p, head);
-  const uint8_t * hname = p.data + hloc.o0;
-  int32_t const hrg = p.rg[head];
-  int32_t waiting = -1;
-  for (uint32_t q = q0; q < p.n && p.name_hash_sorted[q] == key; ++q)
+  uint32_t q1 = q0 + 1;
+  while (q1 < p.n && p.name_hash_sorted[q1] == key)
+    ++q1;
+  // same read group, same pool and the same name, byte by byte
+  auto same_name = [&](uint32_t ra, uint32_t rb) {
+    RecLoc const la = locate(p, ra), lb = locate(p, rb);
+    if (p.rg[ra] != p.rg[rb] || la.reg != lb.reg)
+      return false;
+    const uint8_t * na = p.data + la.o0;
+    const uint8_t * nb = p.data + lb.o0;
+    for (uint32_t j = 0;; ++j)
+    {
+      if (na[j] != nb[j])
+        return false;
+      if (na[j] == 0)
+        return true;
+    }
+  };
+  // A run of equal hashes is one read name -- or, once in ~2^64 / n^2 pools, several names that collide.  Every distinct name
+  // of the run gets its own replay of the read-name map (a run has 2 records almost always, so the quadratic scan is nothing).
+  for (uint32_t g = q0; g < q1; ++g)
   {
-    uint32_t const r = p.idx_sorted[q]; // ascending within the run: the sort is stable
-    if (q != q0)
+    uint32_t const head = p.idx_sorted[g]; // ascending within the run: the sort is stable
+    bool first_of_its_name = true;
+    for (uint32_t e = q0; e < g && first_of_its_name; ++e)
+      first_of_its_name = !same_name(p.idx_sorted[e], head);
+    if (!first_of_its_name)
+      continue;
+    int32_t waiting = -1;
+    for (uint32_t q = g; q < q1; ++q)
     {
-      RecLoc const rloc = locate(p, r);
-      const uint8_t * name = p.data + rloc.o0;
-      bool same = p.rg[r] == hrg && rloc.reg == hloc.reg;
-      for (uint32_t j = 0; same; ++j)
-      {
-        same = name[j] == hname[j];
-        if (name[j] == 0 || hname[j] == 0)
-          break;
-      }
-      if (!same)
-      {
-        atomicOr(&p.counters->input_bits, PREP_ERR_COLLISION); // two different names with one 64-bit hash: reported, not mis-paired
+      uint32_t const r = p.idx_sorted[q];
+      if (q != g && !same_name(head, r))
         continue;
+      if (waiting >= 0)
+      {
+        p.mate[r] = waiting;
+        waiting = -1;
       }
+      else if (p.flag[r] & 1u)
+        waiting = (int32_t)r;
     }
-    if (waiting >= 0)
-    {
-      p.mate[r] = waiting;
-      waiting = -1;
-    }
-    else if (p.flag[r] & 1u)
-      waiting = (int32_t)r;
+    if (waiting >= 0 && p.regions[p.slots[locate(p, head).reg]].is_sv)
+      p.leftover[waiting] = 1;
   }
-  if (waiting >= 0 && p.regions[p.slots[hloc.reg]].is_sv)
-    p.leftover[waiting] = 1;
 }
 } // namespace
 

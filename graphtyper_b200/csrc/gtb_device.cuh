@@ -225,8 +225,7 @@ struct DevCounters
 // why the fast tier handed a task to the general tier
 constexpr int T0_SV = 0, T0_LABELS = 1, T0_VARS = 2, T0_MULTI = 3, T0_SURVIVORS = 4, T0_NO_CHAIN = 5, T0_END_IN_BUBBLE = 6,
               T0_WALK_CAP = 7, T0_WALK_MULTI = 8, T0_SPECIAL = 9, T0_POOL = 10;
-constexpr uint32_t PREP_ERR_SAMPLE = 1, PREP_ERR_DUP = 2, PREP_ERR_MATE = 4, PREP_ERR_LEN = 8, PREP_ERR_RECORD = 16,
-                   PREP_ERR_COLLISION = 32;
+constexpr uint32_t PREP_ERR_SAMPLE = 1, PREP_ERR_DUP = 2, PREP_ERR_MATE = 4, PREP_ERR_LEN = 8, PREP_ERR_RECORD = 16;
 
 // Record parsing on the device (gtb_bam.cu): raw htslib records of one pool -> the chunk's record columns
 struct BamParams
@@ -253,6 +252,7 @@ struct BamParams
   int32_t * isize;
   int32_t * mate;
   int32_t * dup_of;
+  unsigned long long hash_mask;          // kept bits of the name hash (all ones; fewer only in tests)
   unsigned long long * name_hash;        // [n] hash of (read group, read name)
   unsigned long long * name_hash_sorted; // [n]
   uint32_t * idx;                        // [n] 0 .. n-1

@@ -185,7 +185,8 @@ int gtb_index_export(gtb_ctx *ctx, int region_id, uint64_t *keys, uint32_t *labe
 /* Pool of samples for one region.
  * A submit that returns an error (bad links, a read longer than 2 * GTB_SEQ_STRIDE bases, a device capacity, two mates with the
  * same first-in-pair flag ...) may already have added the batch's other records to the pool's accumulators: the pool is then
- * undefined until gtb_pool_reset (or a new gtb_pool_begin).  Callers that want to recover rather than exit must check what
+ * undefined until gtb_pool_reset (or a new gtb_pool_begin), and the library enforces it: further submits on that pool return
+ * GTB_ERR_STATE until it is reset.  Callers that want to recover rather than exit must check what
  * they can BEFORE submitting -- the reference-side reader (integration/gtb_pool_reader.cpp) checks read lengths while it
  * collects the records, and bubbles beyond the allele capacity are refused by gtb_region_begin before anything runs. */
 int gtb_pool_begin(gtb_ctx *ctx, int region_id, int n_samples);
@@ -355,7 +356,10 @@ int gtb_merge_connections(uint64_t n_a, const gtb_connection *a, uint64_t n_b, c
 
 /* Multi-GPU: sum-reduce widened accumulators of a region over an NCCL communicator supplied by the host
  * (ncclComm_t passed as void*; all ranks call; result valid on every rank).  Used when ONE sample's reads
- * are split over GPUs; with sample sharding no collective is needed. */
+ * are split over GPUs; with sample sharding no collective is needed.
+ * The sum is taken in place: afterwards the pool holds the total of all ranks, so another submit or another reduce would
+ * count the other ranks' reads again -- both return GTB_ERR_STATE until gtb_pool_reset.  Connection lists are not reduced
+ * here: merge them with gtb_merge_connections. */
 int gtb_allreduce_accumulators(gtb_ctx *ctx, int region_id, void *nccl_comm);
 /* Several regions in ONE NCCL group and one stream synchronisation. */
 int gtb_allreduce_accumulators_multi(gtb_ctx *ctx, int n, const int *region_ids, void *nccl_comm);

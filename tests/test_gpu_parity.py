@@ -110,6 +110,30 @@ def test_cuda_record_parsing_matches_reference(pre, ctx, oracle_lib):
         ctx.region_end(11)
 
 
+@pytest.mark.parametrize("bits", [3, 9])
+def test_record_parsing_survives_name_hash_collisions(ctx, oracle_lib, bits, monkeypatch):
+    """Different read names that share one 64-bit hash land in one run of the sorted hashes; the pairing kernel replays the
+    read-name map once per distinct name of a run.  Forced here by keeping only `bits` bits of the hash (2^3 = 8 runs for
+    thousands of names): mates, leftovers and accumulators must not change."""
+    for pre in [p for p in ALL if os.path.basename(p).startswith(("mini_stress", "mini_sv"))]:
+        g = abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba"))
+        rd = gtba.load(pre + ".reads.gtba")
+        bam = abi.HostBamBatch.from_probe(rd)
+        want = oracle_lib.parse_bam(bam, is_sv=g.is_sv_graph)
+        monkeypatch.setenv("GTB_BAM_HASH_BITS", str(bits))
+        ctx.region_begin(12, g)
+        try:
+            ctx.pool_begin(12, n_samples_of(rd))
+            ctx.submit_bam(12, bam)
+            col = ctx.debug_bam_columns(len(bam))
+            for k in ("mate", "dup_of", "leftover"):
+                assert np.array_equal(col[k], getattr(want, k)), (k, bits)
+            compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), ctx.pool_finish(12).as_dict(), "collisions")
+        finally:
+            monkeypatch.delenv("GTB_BAM_HASH_BITS")
+            ctx.region_end(12)
+
+
 def test_record_parsing_of_several_pools_in_one_call(ctx):
     """gtb_submit_bam_records_multi: pairing and the duplicate shortcut stay inside each pool; same accumulators as one call
     per region.  Also: records built from the synthetic generator (abi.bam_batch_from_readsets) give the same accumulators as
@@ -166,9 +190,14 @@ def test_record_parsing_rejects_bad_records(ctx):
         with pytest.raises(engine.GtbError) as e:   # sequence + qualities do not fit the data block
             ctx.submit_bam(12, one(100, b"r1\0\0" + b"\x11" * 20))
         assert e.value.code == -1
+        with pytest.raises(engine.GtbError) as e:   # a failed submit leaves the pool undefined: refused until it is reset
+            ctx.submit_bam(12, one(100, b"r1\0\0" + b"\x11" * 50 + b"I" * 100))
+        assert e.value.code == -3
+        ctx.pool_reset(12)
         with pytest.raises(engine.GtbError) as e:   # longer than the reference's MAX_READ_LENGTH
             ctx.submit_bam(12, one(200, b"r1\0\0" + b"\x11" * 100 + b"I" * 200))
         assert e.value.code == -4
+        ctx.pool_reset(12)
         st = ctx.submit_bam(12, abi.HostBamBatch(np.zeros(0, abi.BAM_CORE_DTYPE), np.zeros(0, np.uint8), np.zeros(1, np.uint64),
                                                  np.zeros(0, np.int32), np.zeros(0, np.int32)))
         assert st.n_records == 0
@@ -432,9 +461,14 @@ def test_input_errors_are_reported(ctx):
         with pytest.raises(engine.GtbError) as e:  # both mates first-in-pair: the reference exits (hts_parallel_reader.cpp:306)
             ctx.submit(22, _batch_from_seqs([s, s], [65, 65], mates=[-1, 0]))
         assert e.value.code == -5
+        with pytest.raises(engine.GtbError) as e:  # the pool is undefined after a failed submit: refused until it is reset
+            ctx.submit(22, _batch_from_seqs([s], [0]))
+        assert e.value.code == -3
+        ctx.pool_reset(22)
         with pytest.raises(engine.GtbError) as e:  # longer than the 152-base device limit
             ctx.submit(22, _batch_from_seqs([s], [0], lens=[153]))
         assert e.value.code == -4
+        ctx.pool_reset(22)
         with pytest.raises(engine.GtbError) as e:  # forward mate reference
             ctx.submit(22, _batch_from_seqs([s, s], [65, 129], mates=[1, -1]))
         assert e.value.code == -1
