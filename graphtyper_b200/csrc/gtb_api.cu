@@ -151,10 +151,16 @@ struct BatchState
   std::vector<uint32_t> unit_begin;    // per region: first unit index (size n+1)
   std::vector<uint32_t> rec_begin;
   bool with_conn = false;              // some region of this chunk collects phasing connections
+  int gather_launches = 0;             // gather_columns_kernel launches of this chunk (zero-copy staging)
   PrepParams prep{};                   // device-side batch preparation of this chunk
   BamParams bam{};                     // record parsing (gtb_submit_bam_records); bam.n == 0: columns came from the host
   DeviceBuffer d_bam, d_bam_sort;
   size_t bam_sort_bytes = 0;
+  // gtb_submit_bgzf: compressed bytes + tables | inflated bytes | record lists and sort buffers | cub temp
+  DeviceBuffer d_bgzf_in, d_bgzf_out, d_bgzf_tmp, d_bgzf_cub;
+  PinnedBuffer h_bgzf;
+  BgzfParams bgzf{};
+  uint32_t bgzf_n = 0; // records the last gtb_submit_bgzf built (gtb_debug_bgzf_records)
   DeviceBuffer d_scan_temp;
   size_t scan_temp_bytes = 0;
   cudaStream_t stream = nullptr;       // probe + chain of this chunk (chunks run concurrently, each on its own stream)
@@ -175,6 +181,11 @@ struct BatchState
     d_scan_temp.release();
     d_bam.release();
     d_bam_sort.release();
+    d_bgzf_in.release();
+    d_bgzf_out.release();
+    d_bgzf_tmp.release();
+    d_bgzf_cub.release();
+    h_bgzf.release();
     d_slow.release();
     h_batch.release();
     h_counters.release();
@@ -207,10 +218,9 @@ struct Ctx
   // batch
   DeviceBuffer d_tap_counts, d_tap_pool, d_spill, d_huge;
   std::vector<DeviceBuffer> buffer_cache; // arenas / accumulators of ended regions, reused by the next regions
-  PinnedBuffer h_stage, h_accum, h_segments, h_varstats;
+  PinnedBuffer h_stage, h_accum, h_varstats;
   DeviceBuffer d_varstats;
-  DeviceBuffer d_segments, d_gather;
-  int segments_flip = 0;
+  DeviceBuffer d_gather;
   bool have_last = false;
   bool debug = false;
   int forced_chunks = 0; // gtb_set_chunks / GTB_CHUNKS: 0 = automatic
@@ -313,6 +323,37 @@ cudaError_t wait_stream(Ctx * c)
     else
       sched_yield();
   }
+}
+
+// Pools of different contexts (one per pool thread) share the device.  Left alone, their H2D transfers interleave copy by copy,
+// so pools that were issued one after the other get their bases together, late.  A per-device token keeps the issue order:
+// the transfers of a submit start after those of the submit issued before it, whichever context that was.  The same token
+// for the wide kernels (probe_kernel owns every SM's register file, chain_kernel most of it) was measured and is off by
+// default: end to end 0.999 -> 0.954 ms per step with both tokens, 0.968 with the copy token alone, but the device-resident
+// replay loses (0.725 -> 0.775 ms): the fronts of two pools do overlap usefully at their edges.  A token is ONE event per
+// device: wait for its latest record, queue the work, record it again -- under a mutex, so the chain of records is the issue
+// order.  GTB_FIFO: bit 0 = kernels, bit 1 = copies (default 2).
+struct DeviceFifo
+{
+  std::mutex m_front, m_copy;
+  cudaEvent_t front = nullptr, copy = nullptr; // created on first use, never destroyed (another context may still wait on them)
+};
+DeviceFifo & fifo_of(int device)
+{
+  static DeviceFifo f[64];
+  return f[device & 63];
+}
+int fifo_mode()
+{
+  static int const mode = []() { const char * e = getenv("GTB_FIFO"); return e ? atoi(e) : 2; }();
+  return mode;
+}
+// waits (on stream s) for the token's latest record; creates the event on first use
+cudaError_t fifo_wait(cudaEvent_t & ev, cudaStream_t s)
+{
+  if (!ev)
+    return cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  return cudaStreamWaitEvent(s, ev, 0);
 }
 
 int upload_region_table(Ctx * c)
@@ -477,30 +518,19 @@ void parallel_for(int n, const std::function<void(int)> & fn)
   pool.run(n, fn);
 }
 
-// Segment table of a gather / zero launch: staged in pinned memory, copied on the main stream.  Tables alternate between
-// two pinned halves so that the previous call's (asynchronous) copy is never overwritten while still in flight.
+// Segment table of a gather / zero launch.  It is handed to the kernels by value (parameter space): nothing is staged, so
+// nothing can be overwritten while an asynchronous copy of it is still in flight.
 template <typename F>
-int upload_segments(Ctx * c, int n, F make, unsigned long long & max_bytes)
+std::vector<Segment> make_segments(int n, F make, unsigned long long & max_bytes)
 {
-  size_t const bytes = (size_t)n * sizeof(Segment);
-  if (c->h_segments.cap < 2 * bytes)
-  {
-    CUDA_TRY(wait_stream(c));
-    if (int rc = c->h_segments.reserve(2 * bytes))
-      return rc;
-  }
-  if (int rc = c->d_segments.reserve(bytes))
-    return rc;
-  c->segments_flip ^= 1;
-  Segment * h = reinterpret_cast<Segment *>(static_cast<uint8_t *>(c->h_segments.p) + (c->segments_flip ? c->h_segments.cap / 2 / 16 * 16 : 0));
+  std::vector<Segment> seg((size_t)n);
   max_bytes = 0;
   for (int i = 0; i < n; ++i)
   {
-    h[i] = make(i);
-    max_bytes = std::max(max_bytes, h[i].bytes);
+    seg[i] = make(i);
+    max_bytes = std::max(max_bytes, seg[i].bytes);
   }
-  CUDA_TRY(cudaMemcpyAsync(c->d_segments.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
-  return 0;
+  return seg;
 }
 
 // ---- phasing-connection table of one pool
@@ -648,10 +678,8 @@ void gtb_destroy(gtb_ctx * ctx)
     c->h_stage.release();
     c->h_accum.release();
     c->h_conn_state.release();
-    c->h_segments.release();
     c->h_varstats.release();
     c->d_varstats.release();
-    c->d_segments.release();
     c->d_gather.release();
     for (DeviceBuffer * b : {&c->d_idx_small, &c->d_idx_jobs, &c->d_idx_keys, &c->d_idx_keys2, &c->d_idx_labels, &c->d_idx_idx,
                              &c->d_idx_idx2, &c->d_idx_head, &c->d_idx_temp})
@@ -1411,6 +1439,14 @@ static int launch_front(Ctx * c, BatchState & B, cudaEvent_t after)
       return fail(GTB_ERR_CUDA, "prefix scan of the batch preparation failed");
   launch_prep_fill(B.prep, s);
   CUDA_TRY(cudaEventRecord(B.ev[6], s));
+  std::unique_lock<std::mutex> front_lock;
+  DeviceFifo * fifo = nullptr;
+  if (fifo_mode() & 1)
+  {
+    fifo = &fifo_of(c->device);
+    front_lock = std::unique_lock<std::mutex>(fifo->m_front);
+    CUDA_TRY(fifo_wait(fifo->front, s)); // the front issued before this one, whichever context issued it
+  }
   launch_probe(P, s);
   CUDA_TRY(cudaEventRecord(B.ev[3], s));
   // chain_kernel finishes ~95 % of the read orientations itself.  The rest runs beside the first score pass, on side
@@ -1420,6 +1456,11 @@ static int launch_front(Ctx * c, BatchState & B, cudaEvent_t after)
   P.defer = 1u;
   launch_chain(P, s);
   CUDA_TRY(cudaEventRecord(B.ev[8], s));
+  if (fifo)
+  {
+    CUDA_TRY(cudaEventRecord(fifo->front, s));
+    front_lock.unlock();
+  }
   CUDA_TRY(cudaStreamWaitEvent(B.stream_gen, B.ev[8], 0));
   CUDA_TRY(cudaEventRecord(B.ev[9], B.stream_gen));
   launch_chain_general(P, B.stream_gen);
@@ -1554,6 +1595,7 @@ static int collect_chunks(Ctx * c, gtb_submit_stats * stats, bool record_h2d)
     // prep_flags, scan, prep_fill, probe, chain, chain_general, slow (first launch), first score pass
     st.kernel_launches += B.P.batch.n_records ? 8 : 0;
     st.kernel_launches += B.bam.n ? 7 : 0; // parse, seq, dup, radix sort (3 kernels at these sizes), mate
+    st.kernel_launches += record_h2d ? B.gather_launches : 0;
     n_overflow += kc->n_overflow;
     n_input_error += kc->n_input_error;
     for (int q = 0; q < 12; ++q)
@@ -1675,7 +1717,88 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
         direct_seq = false;
       }
     }
+  // The small columns (27 bytes per record) as well: when every one of them is page-locked and mapped, the device reads
+  // them straight from the caller's arrays (gather_columns_kernel) and the host touches no record at all.  GTB_ZERO_COPY=0
+  // keeps the staged path.
+  static bool const zero_copy_on = []() { const char * e = getenv("GTB_ZERO_COPY"); return !e || atoi(e) != 0; }();
+  bool direct_cols = direct_seq && zero_copy_on;
+  std::vector<ColumnJob> jobs;
+  if (direct_cols)
+  {
+    jobs.reserve(n);
+    auto dev_alias = [&](const void * p, bool optional) -> const void * {
+      if (!p)
+      {
+        direct_cols = direct_cols && optional;
+        return nullptr;
+      }
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer)
+      {
+        cudaGetLastError();
+        direct_cols = false;
+        return nullptr;
+      }
+      return at.devicePointer;
+    };
+    for (int i = 0; i < n && direct_cols; ++i)
+    {
+      gtb_read_batch const & b = batches[i];
+      if (!b.n_reads)
+        continue;
+      ColumnJob J{};
+      J.lseq = static_cast<const uint16_t *>(dev_alias(b.lseq, false));
+      J.flag = static_cast<const uint16_t *>(dev_alias(b.flag, false));
+      J.mapq = static_cast<const uint8_t *>(dev_alias(b.mapq, false));
+      J.same_tid = static_cast<const uint8_t *>(dev_alias(b.same_tid, false));
+      J.score_diff = static_cast<const uint8_t *>(dev_alias(b.score_diff, false));
+      J.clipped = static_cast<const uint8_t *>(dev_alias(b.clipped, true));
+      J.leftover = static_cast<const uint8_t *>(dev_alias(b.leftover, true));
+      J.isize = static_cast<const int32_t *>(dev_alias(b.isize, false));
+      J.sample = static_cast<const int32_t *>(dev_alias(b.sample, false));
+      J.mate = static_cast<const int32_t *>(dev_alias(b.mate, true));
+      J.dup_of = static_cast<const int32_t *>(dev_alias(b.dup_of, true));
+      J.n = b.n_reads;
+      J.rec_base = (uint32_t)rec_base[i];
+      J.slot = (uint32_t)regs[i]->slot;
+      jobs.push_back(J);
+    }
+  }
+  std::unique_lock<std::mutex> copy_lock;
+  DeviceFifo * fifo = nullptr;
+  if (direct_cols && (fifo_mode() & 2))
+  {
+    // nothing but queueing between here and the record below: the transfers of this submit go behind those of the submit
+    // issued before it instead of sharing the link with them copy by copy
+    fifo = &fifo_of(c->device);
+    copy_lock = std::unique_lock<std::mutex>(fifo->m_copy);
+    CUDA_TRY(fifo_wait(fifo->copy, c->copy_stream));
+  }
   CUDA_TRY(cudaEventRecord(B.ev[0], c->copy_stream));
+  B.gather_launches = 0;
+  if (direct_cols)
+  {
+    // before the bases: the device can start on the columns while the copy engine is still being programmed
+    for (size_t j0 = 0; j0 < jobs.size(); j0 += GATHER_JOBS_PER_LAUNCH)
+    {
+      ColumnGather G{};
+      G.dst = static_cast<uint8_t *>(B.d_batch.p);
+      G.o_lseq = o_lseq, G.o_flag = o_flag, G.o_region = o_region, G.o_mapq = o_mapq, G.o_same = o_same, G.o_sd = o_sd;
+      G.o_clip = o_clip, G.o_left = o_left, G.o_isize = o_isize, G.o_sample = o_sample, G.o_mate = o_mate, G.o_dup = o_dup;
+      G.n_jobs = (uint32_t)std::min<size_t>(GATHER_JOBS_PER_LAUNCH, jobs.size() - j0);
+      uint32_t tiles = 0;
+      for (uint32_t j = 0; j < G.n_jobs; ++j)
+      {
+        G.job[j] = jobs[j0 + j];
+        G.job[j].tile_begin = tiles;
+        tiles += (G.job[j].n + GATHER_TILE - 1) / GATHER_TILE;
+      }
+      G.n_tiles = tiles;
+      launch_gather_columns(G, c->copy_stream);
+      ++B.gather_launches;
+    }
+    CUDA_TRY(cudaGetLastError());
+  }
   static int const n_copy_streams = []() { const char * e = getenv("GTB_COPY_STREAMS"); return e ? atoi(e) : 2; }();
   if (direct_seq)
   {
@@ -1700,6 +1823,11 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
       CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_copy2, 0));
     }
   }
+  if (fifo)
+  {
+    CUDA_TRY(cudaEventRecord(fifo->copy, c->copy_stream));
+    copy_lock.unlock();
+  }
   // ---- gather the small columns: independent blocks of records, so the pool is busy whatever the number of regions
   struct Block
   {
@@ -1708,7 +1836,7 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
   };
   std::vector<Block> blocks;
   constexpr uint32_t BLOCK = 8192;
-  for (int i = 0; i < n; ++i)
+  for (int i = 0; i < n && !direct_cols; ++i)
     for (uint32_t k0 = 0; k0 < batches[i].n_reads; k0 += BLOCK)
       blocks.push_back({i, k0, std::min<uint32_t>(k0 + BLOCK, batches[i].n_reads)});
   parallel_for((int)blocks.size(), [&](int bi)
@@ -1757,7 +1885,7 @@ static int stage_chunk(Ctx * c, BatchState & B, int n, const int * region_ids, c
                });
 
   size_t const copy_begin = direct_seq ? o_lseq : 0;
-  if (copy_end > copy_begin)
+  if (copy_end > copy_begin && !direct_cols)
     CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(B.d_batch.p) + copy_begin, h + copy_begin, copy_end - copy_begin,
                              cudaMemcpyHostToDevice, c->copy_stream));
   CUDA_TRY(cudaEventRecord(B.ev[1], c->copy_stream));
@@ -2028,6 +2156,106 @@ int gtb_submit_reads_multi(gtb_ctx * ctx, int n, const int * region_ids, const g
   return conn_check(c, n, regs.data());
 }
 
+// Device block of a record-parsing submit: the raw records (core fields, data blocks, offsets, read groups), the name-hash
+// sort buffers and the small per-region tables.
+struct BamLayout
+{
+  size_t o_core, o_doff, o_rg, o_hash, o_hash2, o_idx, o_idx2, o_tab, o_data, bytes;
+  BamLayout(size_t total, size_t n_regions, size_t n_data)
+  {
+    size_t off = 0;
+    o_core = place<gtb_bam_core>(off, total);
+    o_doff = place<unsigned long long>(off, total + n_regions);
+    o_rg = place<int32_t>(off, total);
+    o_hash = place<unsigned long long>(off, total);
+    o_hash2 = place<unsigned long long>(off, total);
+    o_idx = place<uint32_t>(off, total);
+    o_idx2 = place<uint32_t>(off, total);
+    o_tab = place<unsigned long long>(off, n_regions * 3 + 4); // data_base[n] | rec_begin[n + 1] | slots[n]
+    o_data = place<uint8_t>(off, n_data + 16);
+    bytes = align_up(off, 256);
+  }
+};
+
+// small tables of a record-parsing submit through the chunk's pinned staging buffer (copy stream)
+static int upload_bam_tables(Ctx * c, BatchState & B, BamLayout const & L, int n, const unsigned long long * data_base,
+                             const uint32_t * rec_begin, Region * const * regs)
+{
+  size_t const tab_bytes = (size_t)n * 8 + (size_t)(n + 1) * 4 + (size_t)n * 2;
+  if (int rc = B.h_batch.reserve(align_up(tab_bytes, 256)))
+    return rc;
+  uint8_t * ht = static_cast<uint8_t *>(B.h_batch.p);
+  memcpy(ht, data_base, (size_t)n * 8);
+  memcpy(ht + (size_t)n * 8, rec_begin, (size_t)(n + 1) * 4);
+  for (int i = 0; i < n; ++i)
+    reinterpret_cast<uint16_t *>(ht + (size_t)n * 8 + (size_t)(n + 1) * 4)[i] = (uint16_t)regs[i]->slot;
+  CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(B.d_bam.p) + L.o_tab, ht, tab_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  return 0;
+}
+
+// The raw records of chunk B are (or will be, once B.ev[1] has fired) on the device in layout L: parse them and run the
+// launch sequence of a submit.
+static int run_bam_chunk(Ctx * c, BatchState & B, ChunkLayout const & Lo, BamLayout const & L, size_t total, int n,
+                         Region * const * regs, gtb_submit_stats * stats)
+{
+  uint8_t * r = static_cast<uint8_t *>(B.d_bam.p);
+  B.bam_sort_bytes = bam_sort_temp_bytes((uint32_t)std::max<size_t>(total, 1));
+  if (int rc = B.d_bam_sort.reserve(B.bam_sort_bytes + 16))
+    return rc;
+  if (int rc = bind_chunk(c, B, Lo, total, c->debug))
+    return rc;
+  uint8_t * d = static_cast<uint8_t *>(B.d_batch.p);
+  BamParams & Q = B.bam;
+  memset(&Q, 0, sizeof(Q));
+  Q.n = (uint32_t)total;
+  Q.n_regions = (uint32_t)n;
+  Q.data_base = reinterpret_cast<const unsigned long long *>(r + L.o_tab);
+  Q.rec_begin = reinterpret_cast<const uint32_t *>(r + L.o_tab + (size_t)n * 8);
+  Q.slots = reinterpret_cast<const uint16_t *>(r + L.o_tab + (size_t)n * 8 + (size_t)(n + 1) * 4);
+  Q.regions = B.P.regions;
+  Q.core = reinterpret_cast<const gtb_bam_core *>(r + L.o_core);
+  Q.data = r + L.o_data;
+  Q.data_off = reinterpret_cast<const unsigned long long *>(r + L.o_doff);
+  Q.rg = reinterpret_cast<const int32_t *>(r + L.o_rg);
+  Q.seq4 = d + Lo.o_seq4;
+  Q.lseq = reinterpret_cast<uint16_t *>(d + Lo.o_lseq);
+  Q.flag = reinterpret_cast<uint16_t *>(d + Lo.o_flag);
+  Q.region = reinterpret_cast<uint16_t *>(d + Lo.o_region);
+  Q.mapq = d + Lo.o_mapq;
+  Q.same_tid = d + Lo.o_same;
+  Q.score_diff = d + Lo.o_sd;
+  Q.clipped = d + Lo.o_clip;
+  Q.leftover = d + Lo.o_left;
+  Q.isize = reinterpret_cast<int32_t *>(d + Lo.o_isize);
+  Q.mate = reinterpret_cast<int32_t *>(d + Lo.o_mate);
+  Q.dup_of = reinterpret_cast<int32_t *>(d + Lo.o_dup);
+  {
+    const char * hb = getenv("GTB_BAM_HASH_BITS"); // tests: narrow the name hash so that different names share a run
+    int const bits = hb ? std::max(1, std::min(64, atoi(hb))) : 64;
+    Q.hash_mask = bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
+  }
+  Q.name_hash = reinterpret_cast<unsigned long long *>(r + L.o_hash);
+  Q.name_hash_sorted = reinterpret_cast<unsigned long long *>(r + L.o_hash2);
+  Q.idx = reinterpret_cast<uint32_t *>(r + L.o_idx);
+  Q.idx_sorted = reinterpret_cast<uint32_t *>(r + L.o_idx2);
+  Q.counters = B.P.counters;
+  B.with_conn = false;
+  for (int i = 0; i < n; ++i)
+    B.with_conn = B.with_conn || regs[i]->conn_cap != 0;
+  if (int rc = launch_front(c, B, c->ev_slow[2]))
+    return rc;
+  if (int rc = launch_back(c, 1))
+    return rc;
+  c->have_last = true;
+  if (int rc = collect_chunks(c, stats, true))
+  {
+    for (int i = 0; i < n; ++i)
+      regs[i]->poisoned = true; // part of the batch may already sit in the accumulators
+    return rc;
+  }
+  return conn_check(c, n, regs);
+}
+
 // Records of one pool per region as htslib holds them -> parsed, paired and de-duplicated on the device, then the same
 // kernels as gtb_submit_reads_multi (one chunk: the mates of a pool pair within one call).
 int gtb_submit_bam_records_multi(gtb_ctx * ctx, int n, const int * region_ids, const gtb_bam_batch * batches, gtb_submit_stats * stats)
@@ -2078,105 +2306,436 @@ int gtb_submit_bam_records_multi(gtb_ctx * ctx, int n, const int * region_ids, c
   B.regions.assign(region_ids, region_ids + n);
   B.rec_begin = rec_begin;
   B.unit_begin.clear();
-  // raw records + tables + sort buffers
-  size_t off = 0;
-  size_t const o_core = place<gtb_bam_core>(off, total);
-  size_t const o_doff = place<unsigned long long>(off, total + n);
-  size_t const o_rg = place<int32_t>(off, total);
-  size_t const o_hash = place<unsigned long long>(off, total);
-  size_t const o_hash2 = place<unsigned long long>(off, total);
-  size_t const o_idx = place<uint32_t>(off, total);
-  size_t const o_idx2 = place<uint32_t>(off, total);
-  size_t const o_tab = place<unsigned long long>(off, (size_t)n * 3 + 4); // data_base[n] | rec_begin[n + 1] | slots[n]
-  size_t const o_data = place<uint8_t>(off, n_data + 16);
-  if (int rc = B.d_bam.reserve(align_up(off, 256)))
+  BamLayout const L(total, (size_t)n, n_data);
+  if (int rc = B.d_bam.reserve(L.bytes))
     return rc;
-  B.bam_sort_bytes = bam_sort_temp_bytes((uint32_t)std::max<size_t>(total, 1));
-  if (int rc = B.d_bam_sort.reserve(B.bam_sort_bytes + 16))
-    return rc;
-  // small tables through the chunk's pinned staging buffer
-  size_t const tab_bytes = (size_t)n * 8 + (size_t)(n + 1) * 4 + (size_t)n * 2;
-  if (int rc = B.h_batch.reserve(align_up(tab_bytes, 256)))
-    return rc;
-  uint8_t * ht = static_cast<uint8_t *>(B.h_batch.p);
-  memcpy(ht, data_base.data(), (size_t)n * 8);
-  memcpy(ht + (size_t)n * 8, rec_begin.data(), (size_t)(n + 1) * 4);
-  for (int i = 0; i < n; ++i)
-    reinterpret_cast<uint16_t *>(ht + (size_t)n * 8 + (size_t)(n + 1) * 4)[i] = (uint16_t)regs[i]->slot;
   uint8_t * r = static_cast<uint8_t *>(B.d_bam.p);
   uint8_t * d = static_cast<uint8_t *>(B.d_batch.p);
   CUDA_TRY(cudaEventRecord(c->ev_slow[2], c->stream));
   CUDA_TRY(cudaEventRecord(B.ev[0], c->copy_stream));
-  CUDA_TRY(cudaMemcpyAsync(r + o_tab, ht, tab_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  if (int rc = upload_bam_tables(c, B, L, n, data_base.data(), rec_begin.data(), regs.data()))
+    return rc;
   for (int i = 0; i < n; ++i)
   {
     gtb_bam_batch const & b = batches[i];
     size_t const m = b.n_reads, at = rec_begin[i];
     if (m == 0)
       continue;
-    CUDA_TRY(cudaMemcpyAsync(r + o_core + at * sizeof(gtb_bam_core), b.core, m * sizeof(gtb_bam_core), cudaMemcpyHostToDevice, c->copy_stream));
-    CUDA_TRY(cudaMemcpyAsync(r + o_doff + (at + i) * 8, b.data_off, (m + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
-    CUDA_TRY(cudaMemcpyAsync(r + o_rg + at * 4, b.rg, m * 4, cudaMemcpyHostToDevice, c->copy_stream));
-    CUDA_TRY(cudaMemcpyAsync(r + o_data + data_base[i], b.data, (size_t)b.data_off[m], cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(r + L.o_core + at * sizeof(gtb_bam_core), b.core, m * sizeof(gtb_bam_core), cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(r + L.o_doff + (at + i) * 8, b.data_off, (m + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(r + L.o_rg + at * 4, b.rg, m * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(r + L.o_data + data_base[i], b.data, (size_t)b.data_off[m], cudaMemcpyHostToDevice, c->copy_stream));
     CUDA_TRY(cudaMemcpyAsync(d + Lo.o_sample + at * 4, b.sample, m * 4, cudaMemcpyHostToDevice, c->copy_stream));
   }
   CUDA_TRY(cudaEventRecord(B.ev[1], c->copy_stream));
-  if (int rc = bind_chunk(c, B, Lo, total, c->debug))
-    return rc;
-  BamParams & Q = B.bam;
-  memset(&Q, 0, sizeof(Q));
-  Q.n = (uint32_t)total;
-  Q.n_regions = (uint32_t)n;
-  Q.data_base = reinterpret_cast<const unsigned long long *>(r + o_tab);
-  Q.rec_begin = reinterpret_cast<const uint32_t *>(r + o_tab + (size_t)n * 8);
-  Q.slots = reinterpret_cast<const uint16_t *>(r + o_tab + (size_t)n * 8 + (size_t)(n + 1) * 4);
-  Q.regions = B.P.regions;
-  Q.core = reinterpret_cast<const gtb_bam_core *>(r + o_core);
-  Q.data = r + o_data;
-  Q.data_off = reinterpret_cast<const unsigned long long *>(r + o_doff);
-  Q.rg = reinterpret_cast<const int32_t *>(r + o_rg);
-  Q.seq4 = d + Lo.o_seq4;
-  Q.lseq = reinterpret_cast<uint16_t *>(d + Lo.o_lseq);
-  Q.flag = reinterpret_cast<uint16_t *>(d + Lo.o_flag);
-  Q.region = reinterpret_cast<uint16_t *>(d + Lo.o_region);
-  Q.mapq = d + Lo.o_mapq;
-  Q.same_tid = d + Lo.o_same;
-  Q.score_diff = d + Lo.o_sd;
-  Q.clipped = d + Lo.o_clip;
-  Q.leftover = d + Lo.o_left;
-  Q.isize = reinterpret_cast<int32_t *>(d + Lo.o_isize);
-  Q.mate = reinterpret_cast<int32_t *>(d + Lo.o_mate);
-  Q.dup_of = reinterpret_cast<int32_t *>(d + Lo.o_dup);
-  {
-    const char * hb = getenv("GTB_BAM_HASH_BITS"); // tests: narrow the name hash so that different names share a run
-    int const bits = hb ? std::max(1, std::min(64, atoi(hb))) : 64;
-    Q.hash_mask = bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
-  }
-  Q.name_hash = reinterpret_cast<unsigned long long *>(r + o_hash);
-  Q.name_hash_sorted = reinterpret_cast<unsigned long long *>(r + o_hash2);
-  Q.idx = reinterpret_cast<uint32_t *>(r + o_idx);
-  Q.idx_sorted = reinterpret_cast<uint32_t *>(r + o_idx2);
-  Q.counters = B.P.counters;
-  B.with_conn = false;
-  for (int i = 0; i < n; ++i)
-    B.with_conn = B.with_conn || regs[i]->conn_cap != 0;
-  if (int rc = launch_front(c, B, c->ev_slow[2]))
-    return rc;
-  if (int rc = launch_back(c, 1))
-    return rc;
-  c->have_last = true;
-  if (int rc = collect_chunks(c, stats, true))
-  {
-    for (Region * r : regs)
-      r->poisoned = true; // part of the batch may already sit in the accumulators
-    return rc;
-  }
-  return conn_check(c, n, regs.data());
+  return run_bam_chunk(c, B, Lo, L, total, n, regs.data(), stats);
 }
 
 int gtb_submit_bam_records(gtb_ctx * ctx, int region_id, const gtb_bam_batch * batch, gtb_submit_stats * stats)
 {
   return gtb_submit_bam_records_multi(ctx, 1, &region_id, batch, stats);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BGZF entry: compressed blocks of the pool's files -> records in merge order on the device -> gtb_submit_bam_records' path.
+namespace
+{
+struct BgzfPlan
+{
+  std::vector<BgzfBlock> blocks;
+  std::vector<BgzfSegment> segs;
+  std::vector<BgzfFile> files;
+  std::vector<const uint8_t *> seg_src; // host bytes of every segment
+  std::vector<unsigned long long> seg_comp_off, seg_comp_bytes;
+  unsigned long long comp_bytes = 0, out_bytes = 0;
+  uint32_t n_slots = 0;
+};
+
+// Walks the block headers of every segment (the only thing the host reads of the compressed bytes).
+int plan_bgzf(int n_files, const gtb_bgzf_file * files, BgzfPlan & P)
+{
+  for (int fi = 0; fi < n_files; ++fi)
+  {
+    gtb_bgzf_file const & f = files[fi];
+    if (f.n_segments && !f.segments)
+      return fail(GTB_ERR_ARG, "gtb_submit_bgzf: file without segments array");
+    BgzfFile F{};
+    F.seg_begin = (uint32_t)P.segs.size();
+    F.sample = f.sample;
+    F.rg = f.rg;
+    unsigned long long file_out = 0;
+    for (uint32_t si = 0; si < f.n_segments; ++si)
+    {
+      gtb_bgzf_segment const & g = f.segments[si];
+      if (g.comp_bytes && !g.comp)
+        return fail(GTB_ERR_ARG, "gtb_submit_bgzf: segment without bytes");
+      BgzfSegment S{};
+      S.block_begin = (uint32_t)P.blocks.size();
+      S.out_begin = P.out_bytes;
+      S.v_end = g.v_end;
+      S.first_offset = g.first_offset;
+      S.to_eof = g.to_eof;
+      unsigned long long const comp_base = P.comp_bytes;
+      unsigned long long at = 0;
+      while (at < g.comp_bytes)
+      {
+        BgzfBlockInfo info{};
+        int const rc = bgzf_block_info(g.comp + at, g.comp_bytes - at, &info);
+        if (rc == INF_ERR_INPUT && at > 0)
+          break; // a partial block at the end of the bytes handed over: ignored (the walk reports it if it needs it)
+        if (rc != INF_OK)
+          return fail(GTB_ERR_INPUT, "gtb_submit_bgzf: not a BGZF block header");
+        if (info.isize > 65536u)
+          return fail(GTB_ERR_INPUT, "gtb_submit_bgzf: BGZF block announces more than 64 KiB");
+        if (info.isize == 0)
+        {
+          // the end-of-file marker: bgzf_read stops at an empty block (bgzf.c:1242-1244); nothing behind it is looked at.
+          // The offset behind the last record is then this block's address (bgzf.c:1266-1269), which `at` still is.
+          S.to_eof = 1;
+          break;
+        }
+        BgzfBlock b{};
+        b.comp_off = comp_base + at;
+        b.file_off = g.file_offset + at;
+        b.out_off = P.out_bytes;
+        b.comp_bytes = info.block_bytes;
+        b.isize = info.isize;
+        P.blocks.push_back(b);
+        P.out_bytes += info.isize;
+        at += info.block_bytes;
+      }
+      S.block_end = (uint32_t)P.blocks.size();
+      S.out_end = P.out_bytes;
+      S.end_file_off = g.file_offset + at;
+      if (S.first_offset > S.out_end - S.out_begin)
+        return fail(GTB_ERR_ARG, "gtb_submit_bgzf: first_offset beyond the first block");
+      P.seg_src.push_back(g.comp);
+      P.seg_comp_off.push_back(comp_base);
+      P.seg_comp_bytes.push_back(at);
+      P.comp_bytes = align_up(comp_base + at, 16);
+      file_out += S.out_end - S.out_begin;
+      P.out_bytes = align_up(P.out_bytes, 16) + 64; // slack between segments: no record read crosses into the next one
+      P.segs.push_back(S);
+    }
+    F.seg_end = (uint32_t)P.segs.size();
+    F.rec_base = P.n_slots;
+    F.rec_cap = (uint32_t)std::min<unsigned long long>(file_out / 36 + 2, 0x7FFFFFFFull);
+    if ((unsigned long long)P.n_slots + F.rec_cap >= 0x7FFFFFFFull)
+      return fail(GTB_ERR_ARG, "gtb_submit_bgzf: too many bytes in one call");
+    P.n_slots += F.rec_cap;
+    P.files.push_back(F);
+  }
+  return 0;
+}
+
+BamQuery make_query(const gtb_bgzf_query * q)
+{
+  BamQuery Q{};
+  Q.tid = q->tid;
+  Q.beg = q->beg;
+  Q.end = q->end;
+  Q.flag_filter = q->flag_filter;
+  Q.sv_filter = q->sv_read_filter;
+  Q.max_lseq = (uint32_t)MAX_SEQ;
+  return Q;
+}
+
+const char * bgzf_error_text(int st)
+{
+  switch (st)
+  {
+  case INF_ERR_INPUT: return "a DEFLATE stream ends before its block does";
+  case INF_ERR_TYPE: return "DEFLATE block type 3";
+  case INF_ERR_STORED: return "stored DEFLATE block with LEN != ~NLEN";
+  case INF_ERR_CODE: return "invalid Huffman code lengths";
+  case INF_ERR_SYMBOL: return "invalid symbol in a DEFLATE stream";
+  case INF_ERR_DIST: return "DEFLATE match distance reaches before the block";
+  case INF_ERR_OUTPUT: return "a BGZF block inflates to more than its ISIZE";
+  case INF_ERR_SIZE: return "a BGZF block inflates to less than its ISIZE";
+  case INF_ERR_CRC: return "CRC-32 mismatch in a BGZF block";
+  case INF_ERR_HEADER: return "not a BGZF block header";
+  case SCAN_ERR_TRUNCATED: return "the bytes handed over end before the chunk does";
+  case SCAN_ERR_RECORD: return "malformed BAM record";
+  case SCAN_ERR_CAPACITY: return "more records than the byte count allows";
+  default: return "unknown decode error";
+  }
+}
+} // namespace
+
+int gtb_submit_bgzf(gtb_ctx * ctx, int region_id, int n_files, const gtb_bgzf_file * files, const gtb_bgzf_query * query,
+                    gtb_submit_stats * stats)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || n_files < 0 || (n_files > 0 && !files) || !query)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  if (c->device < 0)
+    return fail(GTB_ERR_CUDA, "host-only context: the genotyping path needs a CUDA device (no CPU fallback)");
+  auto it = c->regions.find(region_id);
+  if (it == c->regions.end())
+    return fail(GTB_ERR_STATE, "unknown region in submit");
+  Region * reg = it->second.get();
+  if (!reg->pool_open)
+    return fail(GTB_ERR_STATE, "gtb_pool_begin must precede gtb_submit_bgzf");
+  if (reg->poisoned)
+    return fail(GTB_ERR_STATE, "an earlier submit on this pool failed: gtb_pool_reset before using it again");
+  if (reg->reduced)
+    return fail(GTB_ERR_STATE, "the pool's accumulators were all-reduced in place: gtb_pool_reset before submitting again");
+  for (int i = 0; i < n_files; ++i)
+    if (files[i].sample < 0 || files[i].sample >= reg->n_samples)
+      return fail(GTB_ERR_ARG, "gtb_submit_bgzf: sample index outside the pool");
+  BgzfPlan P;
+  if (int rc = plan_bgzf(n_files, files, P))
+    return rc;
+  cudaSetDevice(c->device);
+  if (int rc = upload_region_table(c))
+    return rc;
+  c->have_last = false;
+  c->n_chunks_last = 1;
+  BatchState & B = c->bs[0];
+  B.bgzf_n = 0;
+  // ---- device blocks
+  size_t off = 0;
+  size_t const o_blocks = place<BgzfBlock>(off, P.blocks.size());
+  size_t const o_segs = place<BgzfSegment>(off, P.segs.size());
+  size_t const o_files = place<BgzfFile>(off, P.files.size());
+  size_t const tab_bytes = off;
+  size_t const o_comp = place<uint8_t>(off, P.comp_bytes + 16);
+  if (int rc = B.d_bgzf_in.reserve(align_up(off, 256)))
+    return rc;
+  if (int rc = B.d_bgzf_out.reserve(align_up(P.out_bytes + 64, 256)))
+    return rc;
+  size_t const ns = P.n_slots;
+  size_t t = 0;
+  size_t const o_status = place<uint32_t>(t, 8);
+  size_t const o_nrec = place<uint32_t>(t, P.files.size());
+  size_t const o_start = place<unsigned long long>(t, ns);
+  size_t const o_keep = place<uint32_t>(t, ns);
+  size_t const o_kpos = place<uint32_t>(t, ns);
+  size_t const o_filt = place<uint8_t>(t, ns);
+  size_t const o_sel = place<unsigned long long>(t, ns);
+  size_t const o_sfile = place<uint32_t>(t, ns);
+  size_t const o_key = place<unsigned long long>(t, ns);
+  size_t const o_key2 = place<unsigned long long>(t, ns);
+  size_t const o_idx = place<uint32_t>(t, ns);
+  size_t const o_idx2 = place<uint32_t>(t, ns);
+  size_t const o_newg = place<uint32_t>(t, ns);
+  size_t const o_rank = place<uint32_t>(t, ns);
+  size_t const o_fsort = place<uint32_t>(t, ns);
+  size_t const o_final = place<uint32_t>(t, ns);
+  size_t const o_keep2 = place<uint32_t>(t, ns);
+  size_t const o_k2pos = place<uint32_t>(t, ns);
+  size_t const o_outidx = place<uint32_t>(t, ns);
+  size_t const o_perm = place<uint32_t>(t, ns);
+  if (int rc = B.d_bgzf_tmp.reserve(align_up(t, 256)))
+    return rc;
+  size_t const cub_bytes = bgzf_temp_bytes((uint32_t)std::max<size_t>(ns, 1));
+  if (int rc = B.d_bgzf_cub.reserve(cub_bytes))
+    return rc;
+  if (int rc = B.h_bgzf.reserve(align_up(tab_bytes + 128, 256)))
+    return rc;
+  uint8_t * din = static_cast<uint8_t *>(B.d_bgzf_in.p);
+  uint8_t * dt = static_cast<uint8_t *>(B.d_bgzf_tmp.p);
+  uint8_t * hb = static_cast<uint8_t *>(B.h_bgzf.p);
+  uint32_t * h_status = reinterpret_cast<uint32_t *>(hb + align_up(tab_bytes, 16));
+  if (!P.blocks.empty())
+    memcpy(hb + o_blocks, P.blocks.data(), P.blocks.size() * sizeof(BgzfBlock));
+  if (!P.segs.empty())
+    memcpy(hb + o_segs, P.segs.data(), P.segs.size() * sizeof(BgzfSegment));
+  if (!P.files.empty())
+    memcpy(hb + o_files, P.files.data(), P.files.size() * sizeof(BgzfFile));
+  cudaStream_t const s = B.stream;
+  CUDA_TRY(cudaEventRecord(c->ev_slow[2], c->stream));
+  CUDA_TRY(cudaStreamWaitEvent(s, c->ev_slow[2], 0));
+  CUDA_TRY(cudaEventRecord(B.ev[0], s)); // "H2D" of this entry = compressed bytes + decode, up to the resident record batch
+  if (tab_bytes)
+    CUDA_TRY(cudaMemcpyAsync(din, hb, tab_bytes, cudaMemcpyHostToDevice, s));
+  for (size_t k = 0; k < P.seg_src.size(); ++k)
+    if (P.seg_comp_bytes[k])
+      CUDA_TRY(cudaMemcpyAsync(din + o_comp + P.seg_comp_off[k], P.seg_src[k], P.seg_comp_bytes[k], cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemsetAsync(dt + o_status, 0, 32, s));
+  BgzfParams & Z = B.bgzf;
+  memset(&Z, 0, sizeof(Z));
+  Z.comp = din + o_comp;
+  Z.out = static_cast<uint8_t *>(B.d_bgzf_out.p);
+  Z.blocks = reinterpret_cast<const BgzfBlock *>(din + o_blocks);
+  Z.segs = reinterpret_cast<const BgzfSegment *>(din + o_segs);
+  Z.files = reinterpret_cast<const BgzfFile *>(din + o_files);
+  Z.n_blocks = (uint32_t)P.blocks.size();
+  Z.n_files = (uint32_t)P.files.size();
+  Z.n_slots = (uint32_t)ns;
+  Z.check_crc = query->check_crc;
+  Z.q = make_query(query);
+  Z.status = reinterpret_cast<int *>(dt + o_status);
+  Z.n_too_long = reinterpret_cast<uint32_t *>(dt + o_status) + 1;
+  Z.n_kept = reinterpret_cast<uint32_t *>(dt + o_status) + 2;
+  Z.n_final = reinterpret_cast<uint32_t *>(dt + o_status) + 3;
+  Z.need_host = reinterpret_cast<uint32_t *>(dt + o_status) + 4;
+  Z.file_nrec = reinterpret_cast<uint32_t *>(dt + o_nrec);
+  Z.rec_start = reinterpret_cast<unsigned long long *>(dt + o_start);
+  Z.keep = reinterpret_cast<uint32_t *>(dt + o_keep);
+  Z.keep_pos = reinterpret_cast<uint32_t *>(dt + o_kpos);
+  Z.filtered = dt + o_filt;
+  Z.sel_start = reinterpret_cast<unsigned long long *>(dt + o_sel);
+  Z.sel_file = reinterpret_cast<uint32_t *>(dt + o_sfile);
+  Z.key = reinterpret_cast<unsigned long long *>(dt + o_key);
+  Z.key_sorted = reinterpret_cast<unsigned long long *>(dt + o_key2);
+  Z.idx = reinterpret_cast<uint32_t *>(dt + o_idx);
+  Z.idx_sorted = reinterpret_cast<uint32_t *>(dt + o_idx2);
+  Z.new_group = reinterpret_cast<uint32_t *>(dt + o_newg);
+  Z.rank = reinterpret_cast<uint32_t *>(dt + o_rank);
+  Z.file_sorted = reinterpret_cast<uint32_t *>(dt + o_fsort);
+  Z.idx_final = reinterpret_cast<uint32_t *>(dt + o_final);
+  Z.keep2 = reinterpret_cast<uint32_t *>(dt + o_keep2);
+  Z.keep2_pos = reinterpret_cast<uint32_t *>(dt + o_k2pos);
+  Z.out_idx = reinterpret_cast<uint32_t *>(dt + o_outidx);
+  if (launch_bgzf_front(Z, B.d_bgzf_cub.p, cub_bytes, s) != 0)
+    return fail(GTB_ERR_CUDA, "gtb_submit_bgzf: decode launch failed");
+  CUDA_TRY(cudaMemcpyAsync(h_status, dt + o_status, 32, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  if ((int)h_status[0] != 0)
+    return fail(GTB_ERR_INPUT, std::string("gtb_submit_bgzf: ") + bgzf_error_text((int)h_status[0]));
+  if (h_status[1] != 0)
+    return fail(GTB_ERR_CAPACITY, "read longer than 152 bases (reference MAX_READ_LENGTH is 151)");
+  uint32_t const m_order = ns ? h_status[2] : 0; // records the iterators return
+  size_t const total = ns ? h_status[3] : 0;     // records the pool loop keeps
+  // ---- order of the pool's records
+  const uint32_t * d_perm = nullptr;
+  if (m_order)
+  {
+    if (launch_bgzf_order(Z, m_order, B.d_bgzf_cub.p, cub_bytes, s) != 0)
+      return fail(GTB_ERR_CUDA, "gtb_submit_bgzf: sort launch failed");
+    CUDA_TRY(cudaMemcpyAsync(h_status + 4, dt + o_status + 16, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    static bool const force_merge = getenv("GTB_BGZF_FORCE_MERGE") != nullptr; // tests: always replay the reference's merge
+    if (h_status[4] != 0 || force_merge)
+    {
+      // exact duplicates in different files / a position with more than 16 records: the reference's order depends on its
+      // standard library's sort and heap, replayed here on (key, rank, file order, file) integers -- 20 bytes per record
+      std::vector<unsigned long long> keys(m_order);
+      std::vector<uint32_t> rank(m_order), order(m_order), file(m_order), perm;
+      CUDA_TRY(cudaMemcpyAsync(keys.data(), Z.key_sorted, (size_t)m_order * 8, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaMemcpyAsync(rank.data(), Z.rank, (size_t)m_order * 4, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaMemcpyAsync(order.data(), Z.idx_sorted, (size_t)m_order * 4, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaMemcpyAsync(file.data(), Z.file_sorted, (size_t)m_order * 4, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      reference_merge_order(m_order, (uint32_t)P.files.size(), keys.data(), rank.data(), order.data(), file.data(), perm);
+      if (perm.size() != m_order)
+        return fail(GTB_ERR_INPUT, "gtb_submit_bgzf: merge replay lost records");
+      CUDA_TRY(cudaMemcpyAsync(dt + o_perm, perm.data(), (size_t)m_order * 4, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaStreamSynchronize(s)); // perm is a local
+      d_perm = reinterpret_cast<const uint32_t *>(dt + o_perm);
+    }
+  }
+  // ---- from here on: gtb_submit_bam_records with the batch already resident
+  if (int rc = conn_reserve(c, *reg, total))
+    return rc;
+  ChunkLayout const Lo(total);
+  if (int rc = B.d_batch.reserve(Lo.bytes))
+    return rc;
+  B.regions.assign(1, region_id);
+  B.rec_begin.assign({0u, (uint32_t)total});
+  B.unit_begin.clear();
+  BamLayout const L(total, 1, (size_t)P.out_bytes);
+  if (int rc = B.d_bam.reserve(L.bytes))
+    return rc;
+  uint8_t * r = static_cast<uint8_t *>(B.d_bam.p);
+  Z.core = reinterpret_cast<gtb_bam_core *>(r + L.o_core);
+  Z.data = r + L.o_data;
+  Z.data_off = reinterpret_cast<unsigned long long *>(r + L.o_doff);
+  Z.rg = reinterpret_cast<int32_t *>(r + L.o_rg);
+  Z.sample = reinterpret_cast<int32_t *>(static_cast<uint8_t *>(B.d_batch.p) + Lo.o_sample);
+  if (launch_bgzf_back(Z, m_order, (uint32_t)total, d_perm, B.d_bgzf_cub.p, cub_bytes, s) != 0)
+    return fail(GTB_ERR_CUDA, "gtb_submit_bgzf: gather launch failed");
+  B.bgzf_n = (uint32_t)total;
+  unsigned long long const data_base[2] = {0, 0};
+  uint32_t const rec_begin[2] = {0u, (uint32_t)total};
+  CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, B.ev[0], 0));
+  if (int rc = upload_bam_tables(c, B, L, 1, data_base, rec_begin, &reg))
+    return rc;
+  CUDA_TRY(cudaEventRecord(B.ev[4], s)); // the record batch is complete on the chunk stream ...
+  CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, B.ev[4], 0));
+  CUDA_TRY(cudaEventRecord(B.ev[1], c->copy_stream)); // ... and the tables on the copy stream: launch_front waits for ev[1]
+  return run_bam_chunk(c, B, Lo, L, total, 1, &reg, stats);
+}
+
+int gtb_debug_bgzf_records(gtb_ctx * ctx, uint32_t * n_reads, uint64_t * n_data, gtb_bam_core * core, uint8_t * data,
+                           uint64_t * data_off, int32_t * sample, int32_t * rg)
+{
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || c->device < 0 || !n_reads || !n_data)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  cudaSetDevice(c->device);
+  BatchState & B = c->bs[0];
+  uint32_t const n = B.bgzf_n;
+  *n_reads = n;
+  *n_data = 0;
+  if (n == 0)
+    return 0;
+  BgzfParams const & Z = B.bgzf;
+  unsigned long long total = 0;
+  CUDA_TRY(cudaMemcpy(&total, Z.data_off + n, 8, cudaMemcpyDeviceToHost));
+  *n_data = total;
+  if (core)
+    CUDA_TRY(cudaMemcpy(core, Z.core, (size_t)n * sizeof(gtb_bam_core), cudaMemcpyDeviceToHost));
+  if (data)
+    CUDA_TRY(cudaMemcpy(data, Z.data, (size_t)total, cudaMemcpyDeviceToHost));
+  if (data_off)
+    CUDA_TRY(cudaMemcpy(data_off, Z.data_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost));
+  if (sample)
+    CUDA_TRY(cudaMemcpy(sample, Z.sample, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (rg)
+    CUDA_TRY(cudaMemcpy(rg, Z.rg, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gtb_debug_bgzf_host(int n_files, const gtb_bgzf_file * files, const gtb_bgzf_query * query, uint32_t * n_reads,
+                        uint64_t * n_data, gtb_bam_core * core, uint8_t * data, uint64_t * data_off, int32_t * sample, int32_t * rg,
+                        uint64_t * n_inflated, uint8_t * inflated)
+{
+  if (n_files < 0 || (n_files > 0 && !files) || !query || !n_reads || !n_data)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  BgzfPlan P;
+  if (int rc = plan_bgzf(n_files, files, P))
+    return rc;
+  std::vector<uint8_t> comp(P.comp_bytes + 16, 0);
+  for (size_t k = 0; k < P.seg_src.size(); ++k)
+    if (P.seg_comp_bytes[k])
+      memcpy(comp.data() + P.seg_comp_off[k], P.seg_src[k], P.seg_comp_bytes[k]);
+  std::vector<uint8_t> out, d;
+  std::vector<gtb_bam_core> cr;
+  std::vector<unsigned long long> doff;
+  std::vector<int32_t> smp, rgv;
+  uint32_t too_long = 0;
+  int const st = bgzf_host_pipeline(comp.data(), P.blocks, P.segs, P.files, make_query(query), query->check_crc != 0, out, cr, d,
+                                    doff, smp, rgv, &too_long, getenv("GTB_BGZF_FORCE_MERGE") != nullptr);
+  if (st != 0)
+    return fail(GTB_ERR_INPUT, std::string("gtb_debug_bgzf_host: ") + bgzf_error_text(st));
+  if (too_long)
+    return fail(GTB_ERR_CAPACITY, "read longer than 152 bases (reference MAX_READ_LENGTH is 151)");
+  bool const fits = *n_reads >= cr.size() && *n_data >= d.size();
+  *n_reads = (uint32_t)cr.size();
+  *n_data = d.size();
+  if (n_inflated)
+  {
+    bool const room = *n_inflated >= P.out_bytes;
+    *n_inflated = P.out_bytes;
+    if (inflated && room)
+      memcpy(inflated, out.data(), (size_t)P.out_bytes);
+  }
+  if (!fits || !core)
+    return 0; // sizes only
+  memcpy(core, cr.data(), cr.size() * sizeof(gtb_bam_core));
+  if (data && !d.empty())
+    memcpy(data, d.data(), d.size());
+  if (data_off)
+    for (size_t i = 0; i < doff.size(); ++i)
+      data_off[i] = doff[i];
+  if (sample && !smp.empty())
+    memcpy(sample, smp.data(), smp.size() * 4);
+  if (rg && !rgv.empty())
+    memcpy(rg, rgv.data(), rgv.size() * 4);
+  return 0;
 }
 
 // The per-record columns the device derived in the last gtb_submit_bam_records (duplicate links resolved to the record whose
@@ -2480,9 +3039,8 @@ int gtb_pool_finish_multi(gtb_ctx * ctx, int n, const int * region_ids, gtb_accu
     if (int rc = c->d_gather.reserve(off[n]))
       return rc;
     unsigned long long max_bytes = 0;
-    if (int rc = upload_segments(c, n, [&](int i) { return Segment{regs[i]->accum.p, off[i], regs[i]->accum_bytes}; }, max_bytes))
-      return rc;
-    launch_gather_segments(static_cast<const Segment *>(c->d_segments.p), n, max_bytes, c->d_gather.p, c->stream);
+    std::vector<Segment> const seg = make_segments(n, [&](int i) { return Segment{regs[i]->accum.p, off[i], regs[i]->accum_bytes}; }, max_bytes);
+    launch_gather_segments(seg.data(), n, max_bytes, c->d_gather.p, c->stream);
     CUDA_TRY(cudaMemcpyAsync(h, c->d_gather.p, off[n], cudaMemcpyDeviceToHost, c->stream));
   }
   CUDA_TRY(wait_stream(c));
@@ -2537,9 +3095,8 @@ int gtb_pool_reset_multi(gtb_ctx * ctx, int n, const int * region_ids)
     return 0;
   }
   unsigned long long max_bytes = 0; // one launch for all regions instead of one memset each
-  if (int rc = upload_segments(c, n, [&](int i) { return Segment{regs[i]->accum.p, 0, regs[i]->accum_bytes}; }, max_bytes))
-    return rc;
-  launch_zero_segments(static_cast<const Segment *>(c->d_segments.p), n, max_bytes, c->stream);
+  std::vector<Segment> const seg = make_segments(n, [&](int i) { return Segment{regs[i]->accum.p, 0, regs[i]->accum_bytes}; }, max_bytes);
+  launch_zero_segments(seg.data(), n, max_bytes, c->stream);
   return 0;
 }
 

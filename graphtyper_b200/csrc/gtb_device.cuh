@@ -2,9 +2,11 @@
 #pragma once
 
 #include <cstdint>
+#include <vector>
 
 #include "../../include/gtb200.h"
 #include "gtb_index_host.hpp"
+#include "gtb_bamscan.cuh"
 
 namespace gtb
 {
@@ -262,6 +264,60 @@ struct BamParams
 size_t bam_sort_temp_bytes(uint32_t n);
 int launch_bam_parse(const BamParams & p, void * sort_temp, size_t sort_temp_bytes, void * stream);
 
+// BGZF blocks -> the pool's records in merge order (gtb_bgzf.cu): everything gtb_submit_bam_records expects from the host
+// (core, data, data_off, rg, sample) is produced on the device.
+struct BgzfParams
+{
+  const uint8_t * comp; // compressed bytes of all segments
+  uint8_t * out;        // inflated bytes (a segment's blocks are contiguous)
+  const BgzfBlock * blocks;
+  const BgzfSegment * segs;
+  const BgzfFile * files;
+  uint32_t n_blocks, n_files, n_slots, check_crc;
+  BamQuery q;
+  // one 32-byte block, read back by the host between the parts of the pipeline
+  int * status;          // first error (INF_ERR_* / SCAN_ERR_*), 0 = none
+  uint32_t * n_too_long; // records beyond the read-length capacity
+  uint32_t * n_kept;     // m: records the iterators return (the ordering set)
+  uint32_t * n_final;    // n: of those, the records the pool loop keeps
+  uint32_t * need_host;  // bit 0: exact duplicates in different files, bit 1: more than 16 records of one position
+  unsigned long long * rec_start; // [n_slots] scanned records, file-major
+  uint32_t * file_nrec;           // [n_files]
+  uint32_t * keep;                // [n_slots]
+  uint32_t * keep_pos;            // [n_slots]
+  uint8_t * filtered;             // [n_slots]
+  unsigned long long * sel_start; // [m] the ordering set in (file, file order)
+  uint32_t * sel_file;            // file | 0x80000000 when the pool loop filters the record
+  unsigned long long * key;       // (position, length)
+  unsigned long long * key_sorted;
+  uint32_t * idx;
+  uint32_t * idx_sorted;
+  uint32_t * new_group;           // [m] sorted position j opens a new (position, length, sequence) group
+  uint32_t * rank;                // [m] dense rank
+  uint32_t * file_sorted;         // [m]
+  uint32_t * idx_final;           // [m] ordering-set index at final position t
+  uint32_t * keep2;               // [m]
+  uint32_t * keep2_pos;           // [m]
+  uint32_t * out_idx;             // [n]
+  // the record batch in gtb_submit_bam_records' layout
+  gtb_bam_core * core;
+  uint8_t * data;
+  unsigned long long * data_off;
+  int32_t * rg;
+  int32_t * sample;
+};
+size_t bgzf_temp_bytes(uint32_t n_slots);
+int launch_bgzf_front(const BgzfParams & p, void * temp, size_t temp_bytes, void * stream);
+int launch_bgzf_order(const BgzfParams & p, uint32_t m, void * temp, size_t temp_bytes, void * stream);
+int launch_bgzf_back(const BgzfParams & p, uint32_t m, uint32_t n, const uint32_t * perm, void * temp, size_t temp_bytes, void * stream);
+void reference_merge_order(uint32_t m, uint32_t n_files, const unsigned long long * key_sorted, const uint32_t * rank,
+                           const uint32_t * idx_sorted, const uint32_t * file_sorted, std::vector<uint32_t> & perm);
+// the same pipeline serially on the CPU (gtb_debug_bgzf_host)
+int bgzf_host_pipeline(const uint8_t * comp, const std::vector<BgzfBlock> & blocks, const std::vector<BgzfSegment> & segs,
+                       const std::vector<BgzfFile> & files, const BamQuery & q, bool check_crc, std::vector<uint8_t> & inflated,
+                       std::vector<gtb_bam_core> & core, std::vector<uint8_t> & data, std::vector<unsigned long long> & data_off,
+                       std::vector<int32_t> & sample, std::vector<int32_t> & rg, uint32_t * n_too_long, bool force_merge);
+
 // Batch preparation on the device (the per-record part of what genotype_only's caller does, hts_parallel_reader.cpp:655-708):
 // alignment units (records that are not duplicates of an earlier one), the list of read orientations align_read aligns at
 // all (alignment.cpp:331-363), link validation.
@@ -361,8 +417,37 @@ struct Segment
   unsigned long long dst_off;
   unsigned long long bytes;
 };
+// The segment table travels in the kernel's parameter space (no staging buffer, no copy to wait for): seg is a HOST array,
+// launches take SEGMENTS_PER_LAUNCH entries each.
+constexpr int SEGMENTS_PER_LAUNCH = 160;
+struct SegmentTable
+{
+  Segment s[SEGMENTS_PER_LAUNCH];
+};
 void launch_gather_segments(const Segment * seg, int n, unsigned long long max_bytes, void * dst, void * stream);
 void launch_zero_segments(const Segment * seg, int n, unsigned long long max_bytes, void * stream);
+
+// Small record columns of a read batch, read by the device straight from the caller's page-locked (mapped) host buffers:
+// one job per region of the chunk, pointers are DEVICE aliases of the caller's arrays (cudaPointerGetAttributes).  Replaces the
+// host-side gather into a staging buffer + one H2D copy; mate / duplicate links are rebased to chunk-global record indices and
+// the region slot column is filled on the way.  The table travels in the kernel's parameter space.
+constexpr int GATHER_JOBS_PER_LAUNCH = 28;
+struct ColumnJob
+{
+  const uint16_t *lseq, *flag;
+  const uint8_t *mapq, *same_tid, *score_diff, *clipped, *leftover; // clipped / leftover may be null (zeros)
+  const int32_t *isize, *sample, *mate, *dup_of;                    // mate / dup_of may be null (-1)
+  uint32_t n, rec_base, slot, tile_begin;                           // tile_begin: first work item of this job
+};
+struct ColumnGather
+{
+  uint8_t * dst; // the chunk's device block (ChunkLayout offsets below)
+  unsigned long long o_lseq, o_flag, o_region, o_mapq, o_same, o_sd, o_clip, o_left, o_isize, o_sample, o_mate, o_dup;
+  uint32_t n_jobs, n_tiles;
+  ColumnJob job[GATHER_JOBS_PER_LAUNCH];
+};
+constexpr uint32_t GATHER_TILE = 4096; // records per work item
+void launch_gather_columns(const ColumnGather & g, void * stream);
 // connection table maintenance: re-insert every entry of (keys, vals)[0..n_slots) into R's (larger, zeroed) table;
 // compact the non-empty entries of R's table into (out_keys, out_vals), count in *out_n
 void launch_conn_rehash(const unsigned long long * keys, const uint32_t * vals, uint32_t n_slots, const DevRegion & R, void * stream);

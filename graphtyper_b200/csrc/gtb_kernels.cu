@@ -28,6 +28,8 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <type_traits>
 
@@ -3624,9 +3626,9 @@ __device__ void score_record(const LaunchParams & P, uint32_t const i)
 }
 
 // ================================================================================================ segment gather / zero
-__global__ void __launch_bounds__(256) gather_segments_kernel(const Segment * seg, uint8_t * dst)
+__global__ void __launch_bounds__(256) gather_segments_kernel(const __grid_constant__ SegmentTable tab, uint8_t * dst)
 {
-  Segment const sg = seg[blockIdx.y];
+  Segment const & sg = tab.s[blockIdx.y];
   const uint4 * src = static_cast<const uint4 *>(sg.ptr);
   uint4 * out = reinterpret_cast<uint4 *>(dst + sg.dst_off);
   size_t const n = sg.bytes / 16;
@@ -3634,9 +3636,9 @@ __global__ void __launch_bounds__(256) gather_segments_kernel(const Segment * se
     out[i] = src[i];
 }
 
-__global__ void __launch_bounds__(256) zero_segments_kernel(const Segment * seg)
+__global__ void __launch_bounds__(256) zero_segments_kernel(const __grid_constant__ SegmentTable tab)
 {
-  Segment const sg = seg[blockIdx.y];
+  Segment const & sg = tab.s[blockIdx.y];
   uint4 * out = static_cast<uint4 *>(sg.ptr);
   size_t const n = sg.bytes / 16;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -3652,14 +3654,125 @@ static dim3 segment_grid(int n, unsigned long long max_bytes)
 
 void launch_gather_segments(const Segment * seg, int n, unsigned long long max_bytes, void * dst, void * stream)
 {
-  if (n > 0)
-    gather_segments_kernel<<<segment_grid(n, max_bytes), 256, 0, (cudaStream_t)stream>>>(seg, static_cast<uint8_t *>(dst));
+  for (int at = 0; at < n; at += SEGMENTS_PER_LAUNCH)
+  {
+    int const m = std::min(SEGMENTS_PER_LAUNCH, n - at);
+    SegmentTable tab;
+    memcpy(tab.s, seg + at, (size_t)m * sizeof(Segment));
+    gather_segments_kernel<<<segment_grid(m, max_bytes), 256, 0, (cudaStream_t)stream>>>(tab, static_cast<uint8_t *>(dst));
+  }
 }
 
 void launch_zero_segments(const Segment * seg, int n, unsigned long long max_bytes, void * stream)
 {
-  if (n > 0)
-    zero_segments_kernel<<<segment_grid(n, max_bytes), 256, 0, (cudaStream_t)stream>>>(seg);
+  for (int at = 0; at < n; at += SEGMENTS_PER_LAUNCH)
+  {
+    int const m = std::min(SEGMENTS_PER_LAUNCH, n - at);
+    SegmentTable tab;
+    memcpy(tab.s, seg + at, (size_t)m * sizeof(Segment));
+    zero_segments_kernel<<<segment_grid(m, max_bytes), 256, 0, (cudaStream_t)stream>>>(tab);
+  }
+}
+
+// ================================================================================================ column gather (zero copy)
+// One column of one tile: m elements from mapped host memory to the chunk's device block, f applied to every element.
+// 16-byte loads wherever the source allows it (a PCIe read request per 16 bytes of a lane, 512 bytes per warp), several of
+// them in flight per thread; the destination is written with 16-byte stores when it happens to be aligned as well.
+template <typename T, typename F>
+__device__ __forceinline__ void gather_col(const T * __restrict__ src, T * __restrict__ dst, uint32_t m, F f)
+{
+  constexpr uint32_t PER = 16 / sizeof(T);
+  uint32_t head = (uint32_t)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u) / sizeof(T));
+  head = head < m ? head : m;
+  for (uint32_t i = threadIdx.x; i < head; i += blockDim.x)
+    dst[i] = f(src[i]);
+  uint32_t const nv = (m - head) / PER;
+  const uint4 * sv = reinterpret_cast<const uint4 *>(src + head);
+  T * d = dst + head;
+  bool const aligned_dst = (reinterpret_cast<uintptr_t>(d) & 15u) == 0;
+#pragma unroll 4
+  for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x)
+  {
+    union
+    {
+      uint4 v;
+      T e[PER];
+    } u;
+    u.v = sv[i];
+#pragma unroll
+    for (uint32_t j = 0; j < PER; ++j)
+      u.e[j] = f(u.e[j]);
+    if (aligned_dst)
+      reinterpret_cast<uint4 *>(d)[i] = u.v;
+    else
+    {
+#pragma unroll
+      for (uint32_t j = 0; j < PER; ++j)
+        d[i * PER + j] = u.e[j];
+    }
+  }
+  for (uint32_t i = head + nv * PER + threadIdx.x; i < m; i += blockDim.x)
+    dst[i] = f(src[i]);
+}
+
+template <typename T>
+__device__ __forceinline__ void fill_col(T * dst, uint32_t m, T value)
+{
+  for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+    dst[i] = value;
+}
+
+__global__ void __launch_bounds__(512) gather_columns_kernel(const __grid_constant__ ColumnGather g)
+{
+  for (uint32_t w = blockIdx.x; w < g.n_tiles; w += gridDim.x)
+  {
+    uint32_t ji = 0;
+    while (ji + 1 < g.n_jobs && g.job[ji + 1].tile_begin <= w)
+      ++ji;
+    ColumnJob const & J = g.job[ji];
+    uint32_t const k0 = (w - J.tile_begin) * GATHER_TILE;
+    uint32_t const m = J.n - k0 < GATHER_TILE ? J.n - k0 : GATHER_TILE;
+    size_t const at = (size_t)J.rec_base + k0;
+    auto same = [](auto v) { return v; };
+    int32_t const rb = (int32_t)J.rec_base;
+    auto rebase = [rb](int32_t v) { return v < 0 ? -1 : rb + v; };
+    gather_col(J.lseq + k0, reinterpret_cast<uint16_t *>(g.dst + g.o_lseq) + at, m, same);
+    gather_col(J.flag + k0, reinterpret_cast<uint16_t *>(g.dst + g.o_flag) + at, m, same);
+    gather_col(J.mapq + k0, g.dst + g.o_mapq + at, m, same);
+    gather_col(J.same_tid + k0, g.dst + g.o_same + at, m, same);
+    gather_col(J.score_diff + k0, g.dst + g.o_sd + at, m, same);
+    if (J.clipped)
+      gather_col(J.clipped + k0, g.dst + g.o_clip + at, m, same);
+    else
+      fill_col<uint8_t>(g.dst + g.o_clip + at, m, 0);
+    if (J.leftover)
+      gather_col(J.leftover + k0, g.dst + g.o_left + at, m, same);
+    else
+      fill_col<uint8_t>(g.dst + g.o_left + at, m, 0);
+    gather_col(J.isize + k0, reinterpret_cast<int32_t *>(g.dst + g.o_isize) + at, m, same);
+    gather_col(J.sample + k0, reinterpret_cast<int32_t *>(g.dst + g.o_sample) + at, m, same);
+    // links are batch-local; a link at or beyond its own record stays >= its chunk-global index and is reported by
+    // prep_flags_kernel
+    if (J.mate)
+      gather_col(J.mate + k0, reinterpret_cast<int32_t *>(g.dst + g.o_mate) + at, m, rebase);
+    else
+      fill_col<int32_t>(reinterpret_cast<int32_t *>(g.dst + g.o_mate) + at, m, -1);
+    if (J.dup_of)
+      gather_col(J.dup_of + k0, reinterpret_cast<int32_t *>(g.dst + g.o_dup) + at, m, rebase);
+    else
+      fill_col<int32_t>(reinterpret_cast<int32_t *>(g.dst + g.o_dup) + at, m, -1);
+    fill_col<uint16_t>(reinterpret_cast<uint16_t *>(g.dst + g.o_region) + at, m, (uint16_t)J.slot);
+  }
+}
+
+// A few fat blocks: the kernel waits on PCIe reads, not on issue slots, and every SM it sits on is an SM the persistent
+// probe_kernel of another pool cannot start on.  24 blocks x 512 threads x 4 loads of 16 bytes = 0.8 MB in flight.
+void launch_gather_columns(const ColumnGather & g, void * stream)
+{
+  if (g.n_tiles == 0)
+    return;
+  unsigned const blocks = std::min<unsigned>(g.n_tiles, 24u);
+  gather_columns_kernel<<<blocks, 512, 0, (cudaStream_t)stream>>>(g);
 }
 
 // ================================================================================================ connection table upkeep

@@ -27,7 +27,7 @@ EXPORTS = [
     "gtb_set_connections", "gtb_connections_size", "gtb_connections", "gtb_phase_support", "gtb_last_prep_timing",
     "gtb_submit_bam_records", "gtb_submit_bam_records_multi", "gtb_debug_bam_columns", "gtb_merge_connections", "gtb_sample_depths",
     "gtb_last_chain_timing", "gtb_region_attach", "gtb_allreduce_varstats", "gtb_scan_calls_multi",
-    "gtb_allreduce_varstats_multi",
+    "gtb_allreduce_varstats_multi", "gtb_submit_bgzf", "gtb_debug_bgzf_records", "gtb_debug_bgzf_host",
 ]
 
 
@@ -102,6 +102,10 @@ def load_library() -> C.CDLL:
     L.gtb_debug_bam_columns.argtypes = [vp, C.c_uint32, abi.u8p, abi.u16p, abi.u16p, abi.u8p, abi.i32p, abi.u8p, abi.u8p, abi.i32p,
                                         abi.i32p, abi.u8p]
     L.gtb_set_connections.argtypes = [vp, C.c_int]
+    L.gtb_submit_bgzf.argtypes = [vp, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(abi.SubmitStats)]
+    L.gtb_debug_bgzf_records.argtypes = [vp, abi.u32p, abi.u64p, C.c_void_p, abi.u8p, abi.u64p, abi.i32p, abi.i32p]
+    L.gtb_debug_bgzf_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, abi.u32p, abi.u64p, C.c_void_p, abi.u8p, abi.u64p, abi.i32p,
+                                      abi.i32p, abi.u64p, abi.u8p]
     L.gtb_connections_size.argtypes = [vp, C.c_int, abi.u64p]
     L.gtb_connections.argtypes = [vp, C.c_int, C.c_void_p]
     _lib = L
@@ -120,9 +124,9 @@ class PinnedArena:
         self.nbytes = nbytes
         self.used = 0
 
-    def take(self, arr: np.ndarray) -> np.ndarray:
-        """Copy of `arr` living in the arena."""
-        off = (self.used + 255) // 256 * 256
+    def take(self, arr: np.ndarray, skew: int = 0) -> np.ndarray:
+        """Copy of `arr` living in the arena (256-byte aligned; `skew` elements further for tests of unaligned columns)."""
+        off = (self.used + 255) // 256 * 256 + skew * arr.dtype.itemsize
         if off + arr.nbytes > self.nbytes:
             raise MemoryError("pinned arena exhausted")
         buf = (C.c_uint8 * arr.nbytes).from_address(self.ptr.value + off)
@@ -137,15 +141,17 @@ class PinnedArena:
             self.ptr = C.c_void_p()
 
 
-def pin_batches(batches: Sequence[abi.HostBatch]) -> Tuple[List[abi.HostBatch], "PinnedArena"]:
-    """Re-homes the batch columns in page-locked memory (what a production caller fills directly)."""
+def pin_batches(batches: Sequence[abi.HostBatch], skew: int = 0) -> Tuple[List[abi.HostBatch], "PinnedArena"]:
+    """Re-homes the batch columns in page-locked memory (what a production caller fills directly): the bases are then DMA-ed
+    and the small columns read by the device straight from these arrays (no host staging)."""
     total = sum(b.nbytes_h2d() + 16 * 256 for b in batches) + 4096
     arena = PinnedArena(total)
     out = []
     for b in batches:
-        out.append(abi.HostBatch(arena.take(b.seq4), arena.take(b.lseq), arena.take(b.flag), arena.take(b.mapq),
-                                 arena.take(b.isize), arena.take(b.same_tid), arena.take(b.score_diff),
-                                 arena.take(b.clipped), arena.take(b.sample), arena.take(b.mate), arena.take(b.dup_of)))
+        t = lambda a: arena.take(a, skew)
+        out.append(abi.HostBatch(arena.take(b.seq4), t(b.lseq), t(b.flag), t(b.mapq), t(b.isize), t(b.same_tid),
+                                 t(b.score_diff), t(b.clipped), t(b.sample), t(b.mate), t(b.dup_of),
+                                 leftover=t(b.leftover)))
     return out, arena
 
 
@@ -155,6 +161,29 @@ def pin_bam_batches(bams: Sequence[abi.HostBamBatch]) -> Tuple[List[abi.HostBamB
     arena = PinnedArena(total)
     return [abi.HostBamBatch(arena.take(b.core), arena.take(b.data), arena.take(b.data_off), arena.take(b.sample), arena.take(b.rg))
             for b in bams], arena
+
+
+def bgzf_host(files, query, want_inflated: bool = False):
+    """gtb_debug_bgzf_host: decode + selection + merge order of gtb_submit_bgzf computed serially on the CPU from the same
+    source functions (parity infrastructure).  Returns the HostBamBatch (and the inflated bytes)."""
+    lib = load_library()
+    n, nd, ni = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+
+    def check(rc):
+        if rc != 0:
+            raise GtbError(rc, lib.gtb_last_error().decode())
+    check(lib.gtb_debug_bgzf_host(files.n_files, C.addressof(files.files), C.addressof(query), C.byref(n), C.byref(nd), None, None,
+                                  None, None, None, C.byref(ni), None))
+    core = np.zeros(n.value, abi.BAM_CORE_DTYPE)
+    data = np.zeros(max(1, nd.value), np.uint8)
+    off = np.zeros(n.value + 1, np.uint64)
+    smp, rg = np.zeros(n.value, np.int32), np.zeros(n.value, np.int32)
+    infl = np.zeros(max(1, ni.value), np.uint8)
+    check(lib.gtb_debug_bgzf_host(files.n_files, C.addressof(files.files), C.addressof(query), C.byref(n), C.byref(nd),
+                                  core.ctypes.data, abi._ptr(data, abi.u8p), abi._ptr(off, abi.u64p), abi._ptr(smp, abi.i32p),
+                                  abi._ptr(rg, abi.i32p), C.byref(ni), abi._ptr(infl, abi.u8p)))
+    batch = abi.HostBamBatch(core, data[:nd.value], off, smp, rg)
+    return (batch, infl[:ni.value]) if want_inflated else batch
 
 
 class Context:
@@ -289,6 +318,27 @@ class Context:
         st = abi.SubmitStats()
         self._check(self.lib.gtb_submit_bam_records_multi(self.h, n, ids, arr, C.byref(st)))
         return st
+
+    def submit_bgzf(self, region_id: int, files, query) -> abi.SubmitStats:
+        """Compressed BGZF segments of the pool's BAM files (graphtyper_b200.bgzf.HostBgzfFiles + bgzf.query): inflated,
+        scanned, filtered, merged, parsed and genotyped on the device."""
+        st = abi.SubmitStats()
+        self._check(self.lib.gtb_submit_bgzf(self.h, region_id, files.n_files, C.addressof(files.files), C.addressof(query),
+                                             C.byref(st)))
+        return st
+
+    def debug_bgzf_records(self) -> abi.HostBamBatch:
+        """The record batch the last submit_bgzf built on the device (parity tap)."""
+        n, nd = C.c_uint32(0), C.c_uint64(0)
+        self._check(self.lib.gtb_debug_bgzf_records(self.h, C.byref(n), C.byref(nd), None, None, None, None, None))
+        core = np.zeros(n.value, abi.BAM_CORE_DTYPE)
+        data = np.zeros(max(1, nd.value), np.uint8)
+        off = np.zeros(n.value + 1, np.uint64)
+        smp, rg = np.zeros(n.value, np.int32), np.zeros(n.value, np.int32)
+        if n.value:
+            self._check(self.lib.gtb_debug_bgzf_records(self.h, C.byref(n), C.byref(nd), core.ctypes.data, abi._ptr(data, abi.u8p),
+                                                        abi._ptr(off, abi.u64p), abi._ptr(smp, abi.i32p), abi._ptr(rg, abi.i32p)))
+        return abi.HostBamBatch(core, data[:nd.value], off, smp, rg)
 
     def debug_bam_columns(self, n: int) -> Dict[str, np.ndarray]:
         """Per-record columns the device derived in the last submit_bam (parity tap)."""

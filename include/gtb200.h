@@ -312,6 +312,53 @@ typedef struct gtb_bam_batch {
   const int32_t *rg;          /* [n_reads] read-group index: one read-name map per read group */
 } gtb_bam_batch;
 int gtb_submit_bam_records(gtb_ctx *ctx, int region_id, const gtb_bam_batch *batch, gtb_submit_stats *stats);
+/* BGZF entry (SURVEY.md section 8f, N3 -- second step: the decode itself).  The shim hands over, for every BAM file of the pool,
+ * the file's COMPRESSED bytes that cover the region -- the chunks of the region iterator (hts_itr_t::off, htslib hts.c:4046-4098;
+ * adjacent chunks merged), each starting at a BGZF block boundary and running far enough behind the chunk's end for the last
+ * record that is read (or to the end of the file).  On the device: DEFLATE + CRC-32 of every block (one warp per block),
+ * record boundaries, the iterator's rules (a chunk is read while the offset behind the last record is below its end; the first
+ * record on another contig or at / beyond the region's end finishes the file; records that do not overlap the region are
+ * skipped), the pool loop's flag filter (hts_parallel_reader.cpp:655-663) and, for SV calling, is_good_read (:528-568), the
+ * merge order of HtsReader::get_next_read_in_order + the heap of HtsParallelReader (hts_reader.cpp:166-303,
+ * hts_parallel_reader.cpp:66-136: ascending position, sequence length, packed sequence bytes; exact ties in file order), and
+ * from there everything gtb_submit_bam_records does.  Limits (the shim keeps the reference's host reader for these): CRAM,
+ * files with more than one read group (sample / read-group index are per file here), the coverage-bin cap, an empty BGZF block
+ * before the end of the file.  A stream that does not decode, a malformed record or bytes that end before the chunk does return
+ * GTB_ERR_INPUT, a read beyond the length capacity GTB_ERR_CAPACITY -- both BEFORE anything is added to the pool's
+ * accumulators, so the caller can fall back to its own reader for this pool. */
+typedef struct gtb_bgzf_segment {
+  const uint8_t *comp;      /* compressed bytes; comp[0] is the first byte of a BGZF block */
+  uint64_t comp_bytes;
+  uint64_t file_offset;     /* of comp[0] in the file (virtual offsets are relative to the file) */
+  uint64_t v_end;           /* virtual offset at which the chunk ends (hts_pair64_t::v) */
+  uint32_t first_offset;    /* of the first record inside the first block's inflated bytes (hts_pair64_t::u & 0xFFFF) */
+  uint32_t to_eof;          /* the bytes run to the end of the file */
+} gtb_bgzf_segment;
+typedef struct gtb_bgzf_file {
+  uint32_t n_segments;
+  uint32_t reserved;
+  const gtb_bgzf_segment *segments; /* in file order */
+  int32_t sample;           /* sample index within the pool */
+  int32_t rg;               /* read-group index within the pool */
+} gtb_bgzf_file;
+typedef struct gtb_bgzf_query {
+  int32_t tid;              /* contig of the region */
+  uint32_t flag_filter;     /* Options::sam_flag_filter */
+  int64_t beg, end;         /* 0-based, half open (hts_itr_t::beg / end) */
+  uint32_t sv_read_filter;  /* 1: is_good_read (SV calling) */
+  uint32_t check_crc;       /* 1: verify the CRC-32 of every block as htslib does */
+} gtb_bgzf_query;
+int gtb_submit_bgzf(gtb_ctx *ctx, int region_id, int n_files, const gtb_bgzf_file *files, const gtb_bgzf_query *query,
+                    gtb_submit_stats *stats);
+/* Parity taps.  gtb_debug_bgzf_records: the record batch the last gtb_submit_bgzf built on the device, in the layout of
+ * gtb_bam_batch; sizes first: pass NULL arrays.  gtb_debug_bgzf_host: the same decode + selection + order computed serially
+ * on the CPU from the same source functions (test infrastructure of the CPU suite; no device needed, never used by a submit). */
+int gtb_debug_bgzf_records(gtb_ctx *ctx, uint32_t *n_reads, uint64_t *n_data, gtb_bam_core *core, uint8_t *data,
+                           uint64_t *data_off, int32_t *sample, int32_t *rg);
+int gtb_debug_bgzf_host(int n_files, const gtb_bgzf_file *files, const gtb_bgzf_query *query, uint32_t *n_reads,
+                        uint64_t *n_data, gtb_bam_core *core, uint8_t *data, uint64_t *data_off, int32_t *sample, int32_t *rg,
+                        uint64_t *n_inflated, uint8_t *inflated);
+
 /* Several regions' pools in one launch sequence (region_ids[i] / batches[i]); pairing and the duplicate shortcut never cross
  * a pool.  gtb_debug_bam_columns then addresses the concatenation of the batches. */
 int gtb_submit_bam_records_multi(gtb_ctx *ctx, int n, const int *region_ids, const gtb_bam_batch *batches,

@@ -9,10 +9,13 @@
 //          PHIndex (nothing on the GPU path reads it)
 //   gyper::parallel_reader_genotype_only(thread_id, ...)   include/graphtyper/utilities/hts_parallel_reader.hpp:69-82,
 //                                                          src/utilities/hts_parallel_reader.cpp:458-1029
-//       -> the pool thread entry: reads the pool's records with the reference's HtsParallelReader (flag filter, SV read
-//          filter, coverage-bin cap exactly as the loop applies them), hands them to the GPU in ONE gtb_submit_bam_records
-//          call, fills VcfWriter::haplotypes / ReferenceDepth from the accumulators and then finishes the pool with the
-//          reference's own code: Vcf::add_haplotype, Variant::scan_calls, reformat_sv_vcf_records, save_vcf.
+//       -> the pool thread entry: hands the pool's BAM files to the GPU as COMPRESSED bytes (gtb_submit_bgzf: the chunks of
+//          the region iterators HtsReader::open computed from the index; inflate, filters, merge order, parsing, pairing on
+//          the device) -- or, for what that entry declines (CRAM, several read groups per file, the SV coverage cap), reads
+//          the records with the reference's HtsParallelReader (flag filter, SV read filter, coverage-bin cap exactly as the
+//          loop applies them) and hands them over in ONE gtb_submit_bam_records call; fills VcfWriter::haplotypes /
+//          ReferenceDepth from the accumulators and then finishes the pool with the reference's own code:
+//          Vcf::add_haplotype, Variant::scan_calls, reformat_sv_vcf_records, save_vcf.
 //
 // The originals stay reachable as index_graph_cpu / parallel_reader_genotype_only_cpu (the Makefile renames the symbols in
 // copies of indexer.o / hts_parallel_reader.o with objcopy): flows this path does not serve -- discovery iterations, primers,
@@ -216,11 +219,56 @@ void parallel_reader_genotype_only(
   if (is_sv)
     reference_depth.set_depth_sizes(n_samples);
 
-  // ---- the record loop (hts_parallel_reader.cpp:570-716) without the per-record work: which records the pool sees, in
-  //      merge order.  Alignment, the duplicate shortcut, mate pairing and the accumulation happen on the device.
+  // ---- the device part: one context per pool thread on the shared region
+  gtb_ctx * ctx = S.acquire();
+  int const rid = 1;
+  gtb_shim::die(gtb_region_attach(ctx, rid, S.owner, owner_region));
+  gtb_shim::die(gtb_set_connections(ctx, is_writing_hap ? 1 : 0)); // HapSample::connections are only read when is_writing_hap
+  gtb_shim::die(gtb_pool_begin(ctx, rid, (int)n_samples));
+
+  // ---- first choice: the files' COMPRESSED bytes go to the device (gtb_submit_bgzf): inflate, record boundaries, the
+  //      iterator's and the pool loop's filters, the merge order and everything after it happen there.  Not with the
+  //      coverage-bin cap (order dependent, per sample, on the host: hts_parallel_reader.cpp:587-633), and not for what
+  //      BgzfPool::collect declines; a stream the device rejects leaves the pool untouched.  GTB200_BGZF=0 switches it off.
+  bool submitted = false;
+  {
+    static bool const bgzf_on = []() { const char * e = getenv("GTB200_BGZF"); return !e || atoi(e) != 0; }();
+    bool cap_possible = false;
+    if (is_sv && !opts.no_filter_on_coverage && avg_cov_ptr)
+      for (double c : *avg_cov_ptr)
+        cap_possible = cap_possible || c > 0.0;
+    if (bgzf_on && !cap_possible)
+    {
+      gtb_shim::BgzfPool pool;
+      std::string why;
+      if (pool.collect(hts_preader, (uint32_t)opts.sam_flag_filter, is_sv, why))
+      {
+        gtb_submit_stats st{};
+        int const rc = gtb_submit_bgzf(ctx, rid, (int)pool.files.size(), pool.files.data(), &pool.query, &st);
+        if (rc == 0)
+        {
+          submitted = true;
+          print_log(log_severity::debug, "[gtb200] pool ", thread_id, ": ", st.n_records, " records decoded on the device from ",
+                    pool.n_bytes, " compressed bytes");
+        }
+        else if (rc == GTB_ERR_INPUT || rc == GTB_ERR_CAPACITY)
+          print_log(log_severity::warning, "[gtb200] pool ", thread_id, ": device decode declined (", gtb_last_error(),
+                    "): reading with htslib");
+        else
+          gtb_shim::die(rc);
+      }
+      else
+        print_log(log_severity::debug, "[gtb200] pool ", thread_id, ": reading with htslib (", why, ")");
+    }
+  }
+
+  // ---- second choice: the record loop (hts_parallel_reader.cpp:570-716) without the per-record work: which records the pool
+  //      sees, in merge order, read by the reference's HtsParallelReader.  Alignment, the duplicate shortcut, mate pairing
+  //      and the accumulation happen on the device.
   gtb_shim::Records recs;
   long n_dup = 0;
   bool too_long = false; // a read beyond the device's read length (GTB_SEQ_STRIDE * 2 bases): found before anything is submitted
+  if (!submitted)
   {
     auto rejected = [&](HtsRecord const & h)
     { return (h.record->core.flag & opts.sam_flag_filter) != 0u || (is_sv && !gtb_shim::is_good_read(h.record)); };
@@ -269,9 +317,11 @@ void parallel_reader_genotype_only(
   if (too_long)
   {
     // The reference has no read-length limit in call() (MAX_READ_LENGTH is only a default variant distance); the device
-    // path holds 152 bases per read.  Nothing has touched the device yet: this pool runs the reference's CPU code.
+    // path holds 152 bases per read.  Nothing has been added to the pool on the device: it runs the reference's CPU code.
     print_log(log_severity::warning, "[gtb200] pool ", thread_id, " holds a read longer than ", GTB_SEQ_STRIDE * 2,
               " bases: reference CPU path");
+    gtb_shim::die(gtb_region_end(ctx, rid));
+    S.release(ctx);
     recs = gtb_shim::Records();
     PHIndex const cpu_index = index_graph_cpu(graph);
     parallel_reader_genotype_only_cpu(thread_id, out_path, hts_paths_ptr, avg_cov_ptr, output_dir_ptr, reference_fn_ptr,
@@ -280,13 +330,7 @@ void parallel_reader_genotype_only(
     return;
   }
 
-  // ---- the device part: one context per pool thread on the shared region
-  gtb_ctx * ctx = S.acquire();
-  int const rid = 1;
-  gtb_shim::die(gtb_region_attach(ctx, rid, S.owner, owner_region));
-  gtb_shim::die(gtb_set_connections(ctx, is_writing_hap ? 1 : 0)); // HapSample::connections are only read when is_writing_hap
-  gtb_shim::die(gtb_pool_begin(ctx, rid, (int)n_samples));
-  if (!recs.core.empty())
+  if (!submitted && !recs.core.empty())
   {
     gtb_bam_batch const batch = recs.view();
     gtb_shim::die(gtb_submit_bam_records(ctx, rid, &batch, nullptr));

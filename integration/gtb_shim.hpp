@@ -20,13 +20,21 @@
 #include <cstdint>
 #include <cstdlib>
 #include <map>
+#include <string>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <graphtyper/graph/graph.hpp>
 #include <graphtyper/graph/reference_depth.hpp>
 #include <graphtyper/typer/vcf_writer.hpp>
 #include <graphtyper/utilities/hts_parallel_reader.hpp>
 #include <graphtyper/utilities/logging.hpp>
+
+#include <htslib/hts.h>
+#include <htslib/sam.h>
 
 #include <gtb200.h>
 
@@ -226,6 +234,107 @@ struct CoverageCap
     if (b[bin] > cap)
       return false;
     ++b[bin];
+    return true;
+  }
+};
+
+// The pool's files as COMPRESSED bytes for gtb_submit_bgzf: for every BAM file the chunks of its region iterator
+// (hts_itr_t::off, which HtsReader::open has already computed from the index: src/utilities/hts_reader.cpp:99-118), adjacent
+// chunks merged, each read from the file as it is -- no inflate, no record parsing, no heap on the host.  collect() says why
+// when the pool has to stay with the reference's reader: CRAM / SAM, no region iterator, several read groups in one file
+// (sample and read group are per file on the device), files that number the contig differently.
+struct BgzfPool
+{
+  std::vector<std::vector<uint8_t>> bytes; // one buffer per segment
+  std::vector<std::vector<gtb_bgzf_segment>> segs;
+  std::vector<gtb_bgzf_file> files;
+  gtb_bgzf_query query{};
+  uint64_t n_bytes = 0;
+
+  bool collect(gyper::HtsParallelReader const & reader, uint32_t flag_filter, bool is_sv, std::string & why_not)
+  {
+    size_t const nf = reader.hts_files.size();
+    segs.assign(nf, {});
+    files.assign(nf, gtb_bgzf_file{});
+    for (size_t i = 0; i < nf; ++i)
+    {
+      gyper::HtsReader const & f = reader.hts_files[i];
+      if (!f.fp || f.fp->format.format != bam || f.fp->format.compression != bgzf)
+        return why_not = "not a BAM file", false;
+      hts_itr_t const * it = f.hts_iter;
+      if (!it || it->read_rest || it->nocoor || it->multi || it->tid < 0)
+        return why_not = "no single-region iterator", false;
+      if (f.rg2sample_i.size() > 1)
+        return why_not = "several read groups in one file", false;
+      if (i == 0)
+      {
+        query.tid = it->tid;
+        query.beg = it->beg;
+        query.end = it->end;
+      }
+      else if (query.tid != it->tid || query.beg != it->beg || query.end != it->end)
+        return why_not = "files disagree on the region's contig index", false;
+      int const fd = ::open(f.fp->fn, O_RDONLY);
+      if (fd < 0)
+        return why_not = "cannot open the file for raw reads", false;
+      struct stat st;
+      if (::fstat(fd, &st) != 0)
+      {
+        ::close(fd);
+        return why_not = "cannot stat the file", false;
+      }
+      uint64_t const file_size = (uint64_t)st.st_size;
+      for (int k = 0; k < it->n_off; ++k)
+      {
+        uint64_t const u = it->off[k].u;
+        uint64_t v = it->off[k].v;
+        while (k + 1 < it->n_off && it->off[k + 1].u == v) // adjacent chunks: hts_itr_next reads on without a seek
+          v = it->off[++k].v;
+        uint64_t const begin = u >> 16;
+        // the last record that is read starts before v and may reach into the blocks behind v's: three more block sizes
+        uint64_t const end = std::min<uint64_t>(file_size, (v >> 16) + 4 * 65536ull);
+        if (begin >= end)
+          continue;
+        std::vector<uint8_t> buf(end - begin);
+        uint64_t got = 0;
+        while (got < buf.size())
+        {
+          ssize_t const r = ::pread(fd, buf.data() + got, buf.size() - got, (off_t)(begin + got));
+          if (r <= 0)
+            break;
+          got += (uint64_t)r;
+        }
+        if (got != buf.size())
+        {
+          ::close(fd);
+          return why_not = "short read", false;
+        }
+        gtb_bgzf_segment g{};
+        g.comp_bytes = buf.size();
+        g.file_offset = begin;
+        g.v_end = v;
+        g.first_offset = (uint32_t)(u & 0xFFFFu);
+        g.to_eof = end == file_size ? 1u : 0u;
+        n_bytes += buf.size();
+        bytes.push_back(std::move(buf));
+        segs[i].push_back(g);
+      }
+      ::close(fd);
+      files[i].sample = f.sample_index_offset;
+      files[i].rg = f.rg_index_offset;
+    }
+    // pointers last: the vectors above no longer move
+    size_t b = 0;
+    for (size_t i = 0; i < nf; ++i)
+    {
+      for (auto & g : segs[i])
+        g.comp = bytes[b++].data();
+      files[i].n_segments = (uint32_t)segs[i].size();
+      files[i].segments = segs[i].data();
+    }
+    query.flag_filter = flag_filter;
+    query.sv_read_filter = is_sv ? 1u : 0u;
+    query.check_crc = 1u;
     return true;
   }
 };

@@ -1,0 +1,136 @@
+"""BGZF decode + record selection + merge order: the host/device source functions of csrc/gtb_inflate.cuh and
+csrc/gtb_bamscan.cuh, run serially on the CPU through gtb_debug_bgzf_host, against zlib and a plain-Python restatement of
+htslib's region iterator and the reference's merge order (graphtyper_b200/bgzf.py).  The GPU kernels call the same functions
+(tests/test_gpu_bgzf.py compares them with this emulation bit for bit)."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import bgzf_cases as cases
+from conftest import fixture_prefixes
+from graphtyper_b200 import abi, bgzf, engine
+
+SMALL = [p for p in fixture_prefixes(include_big=False)]
+MODES = [(6, zlib.Z_DEFAULT_STRATEGY, 0xFF00), (0, zlib.Z_DEFAULT_STRATEGY, 0x8000), (6, zlib.Z_FIXED, 0xFF00),
+         (9, zlib.Z_DEFAULT_STRATEGY, 3000), (1, zlib.Z_HUFFMAN_ONLY, 0xFF00), (4, zlib.Z_RLE, 20000)]
+
+
+@pytest.mark.parametrize("level,strategy,block", MODES)
+def test_inflate_equals_zlib_source(level, strategy, block):
+    """Dynamic, fixed and stored DEFLATE blocks, match-free and run-length streams, small and full-size BGZF blocks; the
+    CRC-32 of every block is verified through the combine identity the warp uses."""
+    rd, bam = cases.fixture_batch(SMALL[2])
+    tid, beg, end = cases.region_of(bam)
+    made = cases.pool_files(bam, tid, beg, end, block, level, strategy)
+    files = cases.whole_file_segments(made)
+    got, infl = engine.bgzf_host(files, bgzf.query(tid, beg, end), want_inflated=True)
+    at = 0
+    for raw, stream, blocks, hlen, s, g in made:
+        first = [b for b in blocks if b[1] <= hlen < b[1] + b[2]][0]
+        want = stream[first[1]:]
+        assert bytes(infl[at:at + len(want)]) == want
+        at = (at + len(want) + 15) // 16 * 16 + 64
+    assert len(got) > 0
+
+
+def test_corrupt_and_truncated_blocks_are_reported():
+    rd, bam = cases.fixture_batch(SMALL[0])
+    tid, beg, end = cases.region_of(bam)
+    made = cases.pool_files(bam, tid, beg, end)
+    raw, stream, blocks, hlen, s, g = made[0]
+    offs = [[b[0] for b in blocks] + [len(raw) - 28, len(raw)]]
+    u = bgzf.voffset_of(blocks, hlen)
+    bad = bytearray(raw)
+    bad[blocks[0][0] + 40] ^= 0x55  # somewhere in the first block's DEFLATE stream
+    with pytest.raises(engine.GtbError) as e:
+        engine.bgzf_host(bgzf.HostBgzfFiles([(bytes(bad), [(u, len(raw) << 16, True)], 0, 0)], offs), bgzf.query(tid, beg, end))
+    assert e.value.code == -5
+    crc = bytearray(raw)
+    crc[blocks[0][0] + (blocks[1][0] if len(blocks) > 1 else len(raw) - 28) - blocks[0][0] - 8] ^= 1  # the stored CRC-32
+    with pytest.raises(engine.GtbError) as e:
+        engine.bgzf_host(bgzf.HostBgzfFiles([(bytes(crc), [(u, len(raw) << 16, True)], 0, 0)], offs), bgzf.query(tid, beg, end))
+    assert e.value.code == -5 and "CRC" in str(e.value)
+    engine.bgzf_host(bgzf.HostBgzfFiles([(bytes(crc), [(u, len(raw) << 16, True)], 0, 0)], offs),
+                     bgzf.query(tid, beg, end, check_crc=False))  # not checked: decodes
+    # bytes that end inside the chunk: the first block only, chunk end far behind it
+    if len(blocks) > 1:
+        cut = raw[:blocks[1][0]]
+        files = bgzf.HostBgzfFiles([(cut, [(u, len(raw) << 16, False)], 0, 0)], [[blocks[0][0], blocks[1][0]]])
+        files.files[0].segments[0].to_eof = 0
+        with pytest.raises(engine.GtbError) as e:
+            engine.bgzf_host(files, bgzf.query(tid, beg, end))
+        assert e.value.code == -5 and "end before" in str(e.value)
+    with pytest.raises(engine.GtbError) as e:  # not BGZF at all
+        engine.bgzf_host(bgzf.HostBgzfFiles([(b"\0" * 100, [(0, 100 << 16, True)], 0, 0)], [[0, 100]]), bgzf.query(0, 0, 10))
+    assert e.value.code == -5
+
+
+@pytest.mark.parametrize("pre", SMALL, ids=[os.path.basename(p) for p in SMALL])
+def test_whole_file_records_equal_python_iterator(pre):
+    """One chunk per file (sample / read group), decoys around and between the records: the emulation's record batch equals
+    the plain-Python iterator + filters + merge order, byte for byte."""
+    rd, bam = cases.fixture_batch(pre)
+    if len(bam) == 0:
+        pytest.skip("no records")
+    tid, beg, end = cases.region_of(bam)
+    sv = "sv" in os.path.basename(pre)
+    made = cases.pool_files(bam, tid, beg, end, block_size=0x4000)
+    files = cases.whole_file_segments(made)
+    got = engine.bgzf_host(files, bgzf.query(tid, beg, end, sv=sv))
+    want = cases.expected_batch(made, cases.whole_file_chunks(made), tid, beg, end, sv=sv)
+    cases.assert_batches_equal(got, want, pre, modulo_ties=len(made) > 1)
+    # and it is the fixture's own record set (the decoys are all dropped): same multiset of (sample, pos, flag, name + rest)
+    assert len(got) == len(bam)
+
+
+@pytest.mark.parametrize("n_chunks,gap,block", [(2, 4, 0x1000), (4, 9, 0x800), (3, 1, 0xFF00)])
+def test_chunked_files_follow_the_iterator_rules(n_chunks, gap, block):
+    """Several non-adjacent chunks per file: a chunk is read until the offset BEHIND a record reaches its end (so the first
+    record of a gap is still read), the next chunk starts with a seek."""
+    rd, bam = cases.fixture_batch(SMALL[2])
+    tid, beg, end = cases.region_of(bam)
+    made = cases.pool_files(bam, tid, beg, end, block_size=block)
+    files, chunk_lists = cases.chunked_segments(made, n_chunks, gap)
+    got = engine.bgzf_host(files, bgzf.query(tid, beg, end))
+    want = cases.expected_batch(made, chunk_lists, tid, beg, end)
+    cases.assert_batches_equal(got, want, "chunked", modulo_ties=True)
+    assert 0 < len(got) < len(bam)  # the gaps are really skipped
+
+
+def test_region_bounds_and_long_reads():
+    rd, bam = cases.fixture_batch(SMALL[2])
+    tid, beg, end = cases.region_of(bam)
+    made = cases.pool_files(bam, tid, beg, end)
+    mid = (beg + end) // 2
+    files = cases.whole_file_segments(made)
+    got = engine.bgzf_host(files, bgzf.query(tid, mid, mid + 40))
+    want = cases.expected_batch(made, cases.whole_file_chunks(made), tid, mid, mid + 40)
+    cases.assert_batches_equal(got, want, "sub-region", modulo_ties=True)
+    assert 0 < len(got) < len(bam)
+    empty = engine.bgzf_host(files, bgzf.query(tid + 1, 1000, 2000))  # first record on another contig: nothing is read
+    assert len(empty) == 0
+    # a read longer than the device capacity inside the region: capacity error, before anything runs
+    long_rec = bgzf.bam_record(tid, mid, 60, 99, b"long", [(200 << 4) | 0], bytes([0x11]) * 100, 200, bytes([30]) * 200, b"")
+    stream = bgzf.bam_header(cases.REFS) + long_rec
+    raw, blocks = bgzf.bgzf_compress(stream)
+    f = bgzf.HostBgzfFiles([(raw, [(bgzf.voffset_of(blocks, len(stream) - len(long_rec)), len(raw) << 16, True)], 0, 0)],
+                           [[b[0] for b in blocks] + [len(raw) - 28, len(raw)]])
+    with pytest.raises(engine.GtbError) as e:
+        engine.bgzf_host(f, bgzf.query(tid, beg, end))
+    assert e.value.code == -4
+
+
+def test_replayed_merge_equals_device_order_when_nothing_is_ambiguous(monkeypatch):
+    """Single file, no position with more than 16 records: the device order (exact duplicates in reverse file order) IS what
+    the replay of std::sort + the heap gives."""
+    rd, bam = cases.fixture_batch(SMALL[1])
+    tid, beg, end = cases.region_of(bam)
+    made = cases.pool_files(bam, tid, beg, end)
+    assert len(made) == 1
+    files = cases.whole_file_segments(made)
+    a = engine.bgzf_host(files, bgzf.query(tid, beg, end))
+    monkeypatch.setenv("GTB_BGZF_FORCE_MERGE", "1")
+    b = engine.bgzf_host(files, bgzf.query(tid, beg, end))
+    cases.assert_batches_equal(a, b, "forced merge")

@@ -407,6 +407,44 @@ def test_pinned_inputs_take_the_direct_dma_path_with_equal_results(ctx):
         arena.close()
 
 
+@pytest.mark.parametrize("skew,n_chunks", [(0, 1), (1, 1), (3, 2), (5, 0)])
+def test_zero_copy_columns_equal_staged_columns(ctx, skew, n_chunks, monkeypatch):
+    """gather_columns_kernel: with every column page-locked the device reads lengths, flags, links ... straight from the
+    caller's arrays (links rebased to chunk-global indices on the device).  All fixtures in ONE submit, so that record bases
+    are odd and destinations unaligned; `skew` shifts every source column off its 16-byte alignment; SV fixtures carry the
+    leftover column.  The submit must report the gather launch, and every pool must equal the golden accumulators."""
+    pres = [p for p in ALL[:9] if n_chunks == 1 or "sv" not in os.path.basename(p)]
+    ids = list(range(700, 700 + len(pres)))
+    graphs, batches, ns = [], [], []
+    for pre in pres:
+        graphs.append(abi.HostGraph.from_gtba(gtba.load(pre + ".graph.gtba")))
+        rd = gtba.load(pre + ".reads.gtba")
+        batches.append(abi.batch_from_probe(rd))
+        ns.append(n_samples_of(rd))
+    pinned, arena = engine.pin_batches(batches, skew=skew)
+    ctx.region_begin_multi(ids, graphs)
+    try:
+        for k, n in zip(ids, ns):
+            ctx.pool_begin(k, n)
+        ctx.set_chunks(n_chunks)
+        st = ctx.submit_multi(ids, pinned)
+        launches_zero_copy = st.kernel_launches
+        assert st.n_records == sum(len(b) for b in batches)
+        for pre, acc in zip(pres, ctx.pool_finish_multi(ids)):
+            compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), acc.as_dict(), f"zero-copy skew={skew}")
+        # the same submit from pageable memory takes the staged path: fewer launches (no gather kernel), same results
+        ctx.pool_reset_multi(ids)
+        st = ctx.submit_multi(ids, batches)
+        assert st.kernel_launches < launches_zero_copy
+        for pre, acc in zip(pres, ctx.pool_finish_multi(ids)):
+            compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), acc.as_dict(), "staged")
+    finally:
+        ctx.set_chunks(0)
+        for k in ids:
+            ctx.region_end(k)
+        arena.close()
+
+
 # ------------------------------------------------------------------------------------------------ edge cases
 def _plain_graph(length=400, seed=3):
     """A region without any variant: a single ref node."""

@@ -37,6 +37,11 @@ def run(nt, mode):
             c.pool_reset_multi(ids)
             if mode == "replay":
                 c.replay()
+            elif mode == "replay+finish":  # kernels + D2H, no H2D
+                c.replay()
+                c.pool_finish_multi(ids, out=acc[t])
+            elif mode == "submit":         # H2D + kernels, no D2H
+                c.submit_multi(ids, batches)
             else:
                 c.submit_multi(ids, batches)
                 c.pool_finish_multi(ids, out=acc[t])
@@ -54,8 +59,9 @@ def run(nt, mode):
     return dt / (steps * nt)
 
 
-for mode in ("replay", "e2e"):
-    for nt in range(1, max_threads + 1):
+only = int(os.environ.get("PP_ONLY", 0))
+for mode in os.environ.get("PP_MODES", "replay,e2e").split(","):
+    for nt in ([only] if only else range(1, max_threads + 1)):
         run(nt, mode)
         ms = run(nt, mode) * 1e3
         print(f"{mode:6s} threads {nt}: {ms:.3f} ms/step  {n_reads / ms / 1e3:.1f} M reads/s")
