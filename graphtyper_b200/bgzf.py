@@ -294,3 +294,30 @@ def bam_header_length(stream: bytes) -> int:
         (l_name,) = struct.unpack_from("<i", stream, at)
         at += 4 + l_name + 4
     return at
+
+
+def bgzf_compress_records(header: bytes, records: Sequence[bytes], block_size: int = 0xFF00, level: int = 6):
+    """BGZF bytes as htslib writes BAM: the header in blocks of its own, then records, a block being flushed when the next
+    record does not fit (bam_write1 / bgzf_flush_try: no record straddles two blocks).  Returns (bytes, blocks)."""
+    chunks = [header[at:at + block_size] for at in range(0, len(header), block_size)]
+    cur = bytearray()
+    for r in records:
+        if len(cur) + len(r) > block_size and cur:
+            chunks.append(bytes(cur))
+            cur = bytearray()
+        cur += r
+    if cur:
+        chunks.append(bytes(cur))
+    out = bytearray()
+    blocks = []
+    unc = 0
+    for chunk in chunks:
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 9)
+        body = co.compress(chunk) + co.flush()
+        bsize = 18 + len(body) + 8
+        blocks.append((len(out), unc, len(chunk)))
+        out += struct.pack("<BBBBIBBHBBHH", 31, 139, 8, 4, 0, 0, 255, 6, 66, 67, 2, bsize - 1)
+        out += body + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk))
+        unc += len(chunk)
+    out += EOF_BLOCK
+    return bytes(out), blocks

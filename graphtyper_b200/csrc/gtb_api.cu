@@ -161,6 +161,7 @@ struct BatchState
   PinnedBuffer h_bgzf;
   BgzfParams bgzf{};
   uint32_t bgzf_n = 0; // records the last gtb_submit_bgzf built (gtb_debug_bgzf_records)
+  uint32_t bgzf_stitched = 0; // files of that call whose per-block record walks stitched (no serial walk)
   DeviceBuffer d_scan_temp;
   size_t scan_temp_bytes = 0;
   cudaStream_t stream = nullptr;       // probe + chain of this chunk (chunks run concurrently, each on its own stream)
@@ -2348,7 +2349,7 @@ struct BgzfPlan
   std::vector<const uint8_t *> seg_src; // host bytes of every segment
   std::vector<unsigned long long> seg_comp_off, seg_comp_bytes;
   unsigned long long comp_bytes = 0, out_bytes = 0;
-  uint32_t n_slots = 0;
+  uint32_t n_slots = 0, n_block_slots = 0;
 };
 
 // Walks the block headers of every segment (the only thing the host reads of the compressed bytes).
@@ -2400,6 +2401,9 @@ int plan_bgzf(int n_files, const gtb_bgzf_file * files, BgzfPlan & P)
         b.out_off = P.out_bytes;
         b.comp_bytes = info.block_bytes;
         b.isize = info.isize;
+        b.segment = (uint32_t)P.segs.size();
+        b.slot_base = P.n_block_slots;
+        P.n_block_slots += info.isize / 36 + 1;
         P.blocks.push_back(b);
         P.out_bytes += info.isize;
         at += info.block_bytes;
@@ -2439,6 +2443,8 @@ BamQuery make_query(const gtb_bgzf_query * q)
   Q.max_lseq = (uint32_t)MAX_SEQ;
   return Q;
 }
+
+uint32_t g_bgzf_host_stitched = 0; // files of the last gtb_debug_bgzf_host whose per-block walks stitched
 
 const char * bgzf_error_text(int st)
 {
@@ -2526,6 +2532,10 @@ int gtb_submit_bgzf(gtb_ctx * ctx, int region_id, int n_files, const gtb_bgzf_fi
   size_t const o_k2pos = place<uint32_t>(t, ns);
   size_t const o_outidx = place<uint32_t>(t, ns);
   size_t const o_perm = place<uint32_t>(t, ns);
+  size_t const o_bslot = place<unsigned long long>(t, P.n_block_slots);
+  size_t const o_walks = place<BlockWalk>(t, P.blocks.size());
+  size_t const o_take = place<uint32_t>(t, P.blocks.size());
+  size_t const o_bdst = place<uint32_t>(t, P.blocks.size());
   if (int rc = B.d_bgzf_tmp.reserve(align_up(t, 256)))
     return rc;
   size_t const cub_bytes = bgzf_temp_bytes((uint32_t)std::max<size_t>(ns, 1));
@@ -2570,6 +2580,16 @@ int gtb_submit_bgzf(gtb_ctx * ctx, int region_id, int n_files, const gtb_bgzf_fi
   Z.n_kept = reinterpret_cast<uint32_t *>(dt + o_status) + 2;
   Z.n_final = reinterpret_cast<uint32_t *>(dt + o_status) + 3;
   Z.need_host = reinterpret_cast<uint32_t *>(dt + o_status) + 4;
+  Z.n_serial_files = reinterpret_cast<uint32_t *>(dt + o_status) + 5;
+  Z.block_slot = reinterpret_cast<unsigned long long *>(dt + o_bslot);
+  Z.walks = reinterpret_cast<BlockWalk *>(dt + o_walks);
+  Z.block_take = reinterpret_cast<uint32_t *>(dt + o_take);
+  Z.block_dst = reinterpret_cast<uint32_t *>(dt + o_bdst);
+  Z.n_block_slots = P.n_block_slots;
+  {
+    static bool const serial = getenv("GTB_BGZF_SERIAL_WALK") != nullptr;
+    Z.serial_walk = serial ? 1u : 0u;
+  }
   Z.file_nrec = reinterpret_cast<uint32_t *>(dt + o_nrec);
   Z.rec_start = reinterpret_cast<unsigned long long *>(dt + o_start);
   Z.keep = reinterpret_cast<uint32_t *>(dt + o_keep);
@@ -2598,6 +2618,7 @@ int gtb_submit_bgzf(gtb_ctx * ctx, int region_id, int n_files, const gtb_bgzf_fi
   if (h_status[1] != 0)
     return fail(GTB_ERR_CAPACITY, "read longer than 152 bases (reference MAX_READ_LENGTH is 151)");
   uint32_t const m_order = ns ? h_status[2] : 0; // records the iterators return
+  B.bgzf_stitched = (uint32_t)P.files.size() - h_status[5];
   size_t const total = ns ? h_status[3] : 0;     // records the pool loop keeps
   // ---- order of the pool's records
   const uint32_t * d_perm = nullptr;
@@ -2689,6 +2710,16 @@ int gtb_debug_bgzf_records(gtb_ctx * ctx, uint32_t * n_reads, uint64_t * n_data,
   return 0;
 }
 
+// files whose per-block walks stitched: last gtb_debug_bgzf_host (ctx == NULL) or last gtb_submit_bgzf of ctx
+int gtb_debug_bgzf_stitched(gtb_ctx * ctx, uint32_t * n_files_stitched)
+{
+  if (!n_files_stitched)
+    return fail(GTB_ERR_ARG, "bad arguments");
+  auto * c = reinterpret_cast<Ctx *>(ctx);
+  *n_files_stitched = c ? c->bs[0].bgzf_stitched : g_bgzf_host_stitched;
+  return 0;
+}
+
 int gtb_debug_bgzf_host(int n_files, const gtb_bgzf_file * files, const gtb_bgzf_query * query, uint32_t * n_reads,
                         uint64_t * n_data, gtb_bam_core * core, uint8_t * data, uint64_t * data_off, int32_t * sample, int32_t * rg,
                         uint64_t * n_inflated, uint8_t * inflated)
@@ -2706,9 +2737,12 @@ int gtb_debug_bgzf_host(int n_files, const gtb_bgzf_file * files, const gtb_bgzf
   std::vector<gtb_bam_core> cr;
   std::vector<unsigned long long> doff;
   std::vector<int32_t> smp, rgv;
-  uint32_t too_long = 0;
+  uint32_t too_long = 0, n_stitched = 0;
   int const st = bgzf_host_pipeline(comp.data(), P.blocks, P.segs, P.files, make_query(query), query->check_crc != 0, out, cr, d,
-                                    doff, smp, rgv, &too_long, getenv("GTB_BGZF_FORCE_MERGE") != nullptr);
+                                    doff, smp, rgv, &too_long, getenv("GTB_BGZF_FORCE_MERGE") != nullptr, &n_stitched);
+  g_bgzf_host_stitched = n_stitched;
+  if (st == -30)
+    return fail(GTB_ERR_STATE, "gtb_debug_bgzf_host: the per-block walks disagree with the serial walk");
   if (st != 0)
     return fail(GTB_ERR_INPUT, std::string("gtb_debug_bgzf_host: ") + bgzf_error_text(st));
   if (too_long)

@@ -165,6 +165,8 @@ struct BgzfBlock
   unsigned long long file_off; // of the block in its file (virtual offsets)
   unsigned long long out_off;  // in the inflated bytes
   uint32_t comp_bytes, isize;
+  uint32_t segment;            // index of the block's segment
+  uint32_t slot_base;          // first of the block's isize / 36 + 1 slots in the per-block record list
 };
 struct BgzfSegment
 {
@@ -256,5 +258,132 @@ GTB_HD uint32_t bam_walk_file(const uint8_t * out, const BgzfBlock * blocks, con
     }
   }
   return n;
+}
+
+// ---- the same walk, one thread per BGZF block.  htslib never lets a record straddle two blocks (bam_write1 flushes the block
+// when the next record does not fit, sam.c / bgzf_flush_try), so in practice every block starts at a record boundary.  That is
+// only a guess here: bam_walk_block walks ONE block from its guessed entry and notes where it came out; bam_stitch_file then
+// follows the file's blocks in order and accepts a block only if the walk before it came out exactly at its guessed entry
+// (by induction from the chunk's known first record, accepted blocks hold true record boundaries); the first mismatch sends
+// the whole file to the serial walk above.  Events that end a serial walk (chunk end, iterator finished, malformed or
+// truncated record) end the block's walk at the same record, so the stitched result is the serial result.
+constexpr uint32_t WALK_NONE = 0, WALK_VCUT = 1 /* the record at `halt` is not read: chunk end */, WALK_STOP = 2 /* read, and the
+                   iterator is finished */, WALK_BAD = 3, WALK_TRUNC = 4;
+struct BlockWalk
+{
+  unsigned long long exit; // inflated offset behind the last record walked (reason NONE: >= the block's end)
+  uint32_t count;          // records recorded (for STOP including the one that stops)
+  uint32_t reason;
+};
+
+GTB_HD BlockWalk bam_walk_block(const uint8_t * out, const BgzfBlock & blk, const BgzfSegment & s, bool first_of_segment,
+                                const BamQuery & q, unsigned long long * slot)
+{
+  BlockWalk w{0, 0, WALK_NONE};
+  unsigned long long g = blk.out_off + (first_of_segment ? s.first_offset : 0u);
+  unsigned long long const block_end = blk.out_off + blk.isize;
+  bool first = first_of_segment;
+  while (g < block_end)
+  {
+    if (!first && ((blk.file_off << 16) | (g - blk.out_off)) >= s.v_end)
+    {
+      w.reason = WALK_VCUT;
+      break;
+    }
+    first = false;
+    if (g + 36 > s.out_end)
+    {
+      w.reason = WALK_TRUNC;
+      break;
+    }
+    BamFixed const f = bam_fixed(out + g);
+    if (!bam_layout_ok(f))
+    {
+      w.reason = WALK_BAD;
+      break;
+    }
+    if (g + 4ull + (unsigned long long)f.block_size > s.out_end)
+    {
+      w.reason = WALK_TRUNC;
+      break;
+    }
+    slot[w.count++] = g;
+    g += 4ull + (unsigned long long)f.block_size;
+    if (f.tid != q.tid || (long long)f.pos >= q.end)
+    {
+      w.reason = WALK_STOP;
+      break;
+    }
+  }
+  w.exit = g;
+  return w;
+}
+
+// Follows the blocks of a file.  take[b] = records of block b that the iterator reads, dst[b] = where they go in rec_start
+// (file-major).  Returns false when a guess failed (the caller runs bam_walk_file instead); otherwise *n_rec / *status are
+// what bam_walk_file would have returned.
+GTB_HD bool bam_stitch_file(const BgzfBlock * blocks, const BgzfSegment * segs, const BgzfFile & file, const BlockWalk * walks,
+                            uint32_t * take, uint32_t * dst, uint32_t * n_rec, int * status)
+{
+  uint32_t n = 0;
+  *status = SCAN_OK;
+  bool done = false;
+  for (uint32_t si = file.seg_begin; si < file.seg_end; ++si)
+  {
+    BgzfSegment const & s = segs[si];
+    for (uint32_t b = s.block_begin; b < s.block_end; ++b)
+      take[b] = 0;
+    if (done)
+      continue;
+    unsigned long long g = s.out_begin + s.first_offset;
+    bool any = false, segment_over = false;
+    for (uint32_t b = s.block_begin; b < s.block_end && !segment_over && !done; ++b)
+    {
+      unsigned long long const entry = blocks[b].out_off + (b == s.block_begin ? s.first_offset : 0u);
+      if (g != entry)
+      {
+        if (g > entry && g >= blocks[b].out_off + blocks[b].isize)
+          continue; // the last record ran over this whole block (a record larger than a block): nothing starts here
+        return false;
+      }
+      BlockWalk const & w = walks[b];
+      if (n + w.count > file.rec_cap)
+      {
+        *status = SCAN_ERR_CAPACITY;
+        *n_rec = n;
+        return true;
+      }
+      take[b] = w.count;
+      dst[b] = file.rec_base + n;
+      n += w.count;
+      any = any || w.count > 0;
+      g = w.exit;
+      switch (w.reason)
+      {
+      case WALK_VCUT: segment_over = true; break;
+      case WALK_STOP: done = true; break;
+      case WALK_BAD: *status = SCAN_ERR_RECORD; *n_rec = n; return true;
+      case WALK_TRUNC: *status = SCAN_ERR_TRUNCATED; *n_rec = n; return true;
+      default: break;
+      }
+    }
+    if (done || segment_over)
+      continue;
+    // the bytes of the segment are used up (g >= out_end), as in bam_walk_file
+    if (g < s.out_end)
+      return false; // a walk that stopped inside the segment without a reason cannot happen; be safe
+    if (any && (s.end_file_off << 16) >= s.v_end)
+      continue;
+    if (s.to_eof)
+      done = true;
+    else
+    {
+      *status = SCAN_ERR_TRUNCATED;
+      *n_rec = n;
+      return true;
+    }
+  }
+  *n_rec = n;
+  return true;
 }
 } // namespace gtb

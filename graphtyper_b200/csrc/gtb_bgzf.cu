@@ -46,15 +46,55 @@ __global__ void __launch_bounds__(INFLATE_WARPS * 32) bgzf_inflate_kernel(BgzfPa
     atomicCAS(p.status, 0, rc);
 }
 
+__global__ void __launch_bounds__(64) bam_walk_blocks_kernel(BgzfParams p)
+{
+  uint32_t const b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.n_blocks || *p.status != 0)
+    return;
+  BgzfBlock const & blk = p.blocks[b];
+  BgzfSegment const & s = p.segs[blk.segment];
+  p.walks[b] = bam_walk_block(p.out, blk, s, b == s.block_begin, p.q, p.block_slot + blk.slot_base);
+}
+
 __global__ void __launch_bounds__(32) bam_walk_kernel(BgzfParams p)
 {
   uint32_t const f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= p.n_files || *p.status != 0)
     return;
   int st = SCAN_OK;
-  p.file_nrec[f] = bam_walk_file(p.out, p.blocks, p.segs, p.files[f], p.q, p.rec_start, &st);
+  uint32_t n = 0;
+  BgzfFile const & file = p.files[f];
+  if (p.serial_walk || !bam_stitch_file(p.blocks, p.segs, file, p.walks, p.block_take, p.block_dst, &n, &st))
+  {
+    // a record straddles two blocks where the per-block walks guessed a boundary: the serial walk decides
+    for (uint32_t si = file.seg_begin; si < file.seg_end; ++si)
+      for (uint32_t b = p.segs[si].block_begin; b < p.segs[si].block_end; ++b)
+        p.block_take[b] = 0;
+    n = bam_walk_file(p.out, p.blocks, p.segs, file, p.q, p.rec_start, &st);
+    atomicAdd(p.n_serial_files, 1u);
+  }
+  p.file_nrec[f] = n;
   if (st != SCAN_OK)
     atomicCAS(p.status, 0, st);
+}
+
+__global__ void __launch_bounds__(256) bam_walk_scatter_kernel(BgzfParams p)
+{
+  uint32_t const slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= p.n_block_slots || *p.status != 0)
+    return;
+  uint32_t lo = 0, hi = p.n_blocks; // last block with slot_base <= slot
+  while (hi - lo > 1)
+  {
+    uint32_t const mid = (lo + hi) >> 1;
+    if (p.blocks[mid].slot_base <= slot)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  uint32_t const i = slot - p.blocks[lo].slot_base;
+  if (i < p.block_take[lo])
+    p.rec_start[p.block_dst[lo] + i] = p.block_slot[slot];
 }
 
 // slot -> file (slots of a file are contiguous)
@@ -273,8 +313,12 @@ int launch_bgzf_front(const BgzfParams & p, void * temp, size_t temp_bytes, void
   cudaStream_t const s = (cudaStream_t)stream;
   if (p.n_blocks)
     bgzf_inflate_kernel<<<(p.n_blocks + INFLATE_WARPS - 1) / INFLATE_WARPS, INFLATE_WARPS * 32, 0, s>>>(p);
+  if (p.n_blocks && !p.serial_walk)
+    bam_walk_blocks_kernel<<<(p.n_blocks + 63) / 64, 64, 0, s>>>(p);
   if (p.n_files)
     bam_walk_kernel<<<(p.n_files + 31) / 32, 32, 0, s>>>(p);
+  if (p.n_block_slots && !p.serial_walk)
+    bam_walk_scatter_kernel<<<(p.n_block_slots + 255) / 256, 256, 0, s>>>(p);
   if (p.n_slots)
   {
     bam_classify_kernel<<<(p.n_slots + 255) / 256, 256, 0, s>>>(p);
@@ -389,8 +433,10 @@ void reference_merge_order(uint32_t m, uint32_t n_files, const unsigned long lon
 int bgzf_host_pipeline(const uint8_t * comp, const std::vector<BgzfBlock> & blocks, const std::vector<BgzfSegment> & segs,
                        const std::vector<BgzfFile> & files, const BamQuery & q, bool check_crc, std::vector<uint8_t> & inflated,
                        std::vector<gtb_bam_core> & core, std::vector<uint8_t> & data, std::vector<unsigned long long> & data_off,
-                       std::vector<int32_t> & sample, std::vector<int32_t> & rg, uint32_t * n_too_long, bool force_merge)
+                       std::vector<int32_t> & sample, std::vector<int32_t> & rg, uint32_t * n_too_long, bool force_merge,
+                       uint32_t * n_stitched)
 {
+  *n_stitched = 0;
   unsigned long long out_bytes = 0;
   for (auto const & b : blocks)
     out_bytes = std::max(out_bytes, b.out_off + b.isize);
@@ -410,6 +456,31 @@ int bgzf_host_pipeline(const uint8_t * comp, const std::vector<BgzfBlock> & bloc
   {
     int st = SCAN_OK;
     uint32_t const nr = bam_walk_file(inflated.data(), blocks.data(), segs.data(), files[fi], q, rec_start.data(), &st);
+    {
+      // the per-block walks + stitch the device uses must agree with the serial walk whenever the stitch accepts them
+      std::vector<BlockWalk> walks(blocks.size());
+      std::vector<uint32_t> take(blocks.size(), 0), dst(blocks.size(), 0);
+      uint32_t n_block_slots = 0;
+      for (auto const & b : blocks)
+        n_block_slots = std::max(n_block_slots, b.slot_base + b.isize / 36 + 1);
+      std::vector<unsigned long long> slot(n_block_slots, 0);
+      for (uint32_t si = files[fi].seg_begin; si < files[fi].seg_end; ++si)
+        for (uint32_t b = segs[si].block_begin; b < segs[si].block_end; ++b)
+          walks[b] = bam_walk_block(inflated.data(), blocks[b], segs[si], b == segs[si].block_begin, q, slot.data() + blocks[b].slot_base);
+      uint32_t n2 = 0;
+      int st2 = SCAN_OK;
+      if (bam_stitch_file(blocks.data(), segs.data(), files[fi], walks.data(), take.data(), dst.data(), &n2, &st2))
+      {
+        if (n2 != nr || st2 != st)
+          return -30;
+        for (uint32_t si = files[fi].seg_begin; si < files[fi].seg_end; ++si)
+          for (uint32_t b = segs[si].block_begin; b < segs[si].block_end; ++b)
+            for (uint32_t i = 0; i < take[b]; ++i)
+              if (slot[blocks[b].slot_base + i] != rec_start[dst[b] + i])
+                return -30;
+        ++*n_stitched;
+      }
+    }
     if (st != SCAN_OK)
       return st;
     for (uint32_t i = 0; i < nr; ++i)

@@ -281,7 +281,13 @@ struct BgzfParams
   uint32_t * n_kept;     // m: records the iterators return (the ordering set)
   uint32_t * n_final;    // n: of those, the records the pool loop keeps
   uint32_t * need_host;  // bit 0: exact duplicates in different files, bit 1: more than 16 records of one position
+  uint32_t * n_serial_files; // files whose per-block walks did not stitch (records straddling blocks): walked serially
   unsigned long long * rec_start; // [n_slots] scanned records, file-major
+  unsigned long long * block_slot; // [n_block_slots] records found by the per-block walks
+  BlockWalk * walks;              // [n_blocks]
+  uint32_t * block_take;          // [n_blocks] records of the block the iterator reads
+  uint32_t * block_dst;           // [n_blocks] their place in rec_start
+  uint32_t n_block_slots, serial_walk; // serial_walk: skip the per-block walks (GTB_BGZF_SERIAL_WALK, measurements)
   uint32_t * file_nrec;           // [n_files]
   uint32_t * keep;                // [n_slots]
   uint32_t * keep_pos;            // [n_slots]
@@ -316,7 +322,8 @@ void reference_merge_order(uint32_t m, uint32_t n_files, const unsigned long lon
 int bgzf_host_pipeline(const uint8_t * comp, const std::vector<BgzfBlock> & blocks, const std::vector<BgzfSegment> & segs,
                        const std::vector<BgzfFile> & files, const BamQuery & q, bool check_crc, std::vector<uint8_t> & inflated,
                        std::vector<gtb_bam_core> & core, std::vector<uint8_t> & data, std::vector<unsigned long long> & data_off,
-                       std::vector<int32_t> & sample, std::vector<int32_t> & rg, uint32_t * n_too_long, bool force_merge);
+                       std::vector<int32_t> & sample, std::vector<int32_t> & rg, uint32_t * n_too_long, bool force_merge,
+                       uint32_t * n_stitched);
 
 // Batch preparation on the device (the per-record part of what genotype_only's caller does, hts_parallel_reader.cpp:655-708):
 // alignment units (records that are not duplicates of an earlier one), the list of read orientations align_read aligns at

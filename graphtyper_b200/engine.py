@@ -27,7 +27,7 @@ EXPORTS = [
     "gtb_set_connections", "gtb_connections_size", "gtb_connections", "gtb_phase_support", "gtb_last_prep_timing",
     "gtb_submit_bam_records", "gtb_submit_bam_records_multi", "gtb_debug_bam_columns", "gtb_merge_connections", "gtb_sample_depths",
     "gtb_last_chain_timing", "gtb_region_attach", "gtb_allreduce_varstats", "gtb_scan_calls_multi",
-    "gtb_allreduce_varstats_multi", "gtb_submit_bgzf", "gtb_debug_bgzf_records", "gtb_debug_bgzf_host",
+    "gtb_allreduce_varstats_multi", "gtb_submit_bgzf", "gtb_debug_bgzf_records", "gtb_debug_bgzf_host", "gtb_debug_bgzf_stitched",
 ]
 
 
@@ -103,6 +103,7 @@ def load_library() -> C.CDLL:
                                         abi.i32p, abi.u8p]
     L.gtb_set_connections.argtypes = [vp, C.c_int]
     L.gtb_submit_bgzf.argtypes = [vp, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(abi.SubmitStats)]
+    L.gtb_debug_bgzf_stitched.argtypes = [vp, abi.u32p]
     L.gtb_debug_bgzf_records.argtypes = [vp, abi.u32p, abi.u64p, C.c_void_p, abi.u8p, abi.u64p, abi.i32p, abi.i32p]
     L.gtb_debug_bgzf_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, abi.u32p, abi.u64p, C.c_void_p, abi.u8p, abi.u64p, abi.i32p,
                                       abi.i32p, abi.u64p, abi.u8p]
@@ -184,6 +185,12 @@ def bgzf_host(files, query, want_inflated: bool = False):
                                   abi._ptr(rg, abi.i32p), C.byref(ni), abi._ptr(infl, abi.u8p)))
     batch = abi.HostBamBatch(core, data[:nd.value], off, smp, rg)
     return (batch, infl[:ni.value]) if want_inflated else batch
+
+
+def bgzf_host_stitched() -> int:
+    n = C.c_uint32(0)
+    load_library().gtb_debug_bgzf_stitched(None, C.byref(n))
+    return n.value
 
 
 class Context:
@@ -326,6 +333,12 @@ class Context:
         self._check(self.lib.gtb_submit_bgzf(self.h, region_id, files.n_files, C.addressof(files.files), C.addressof(query),
                                              C.byref(st)))
         return st
+
+    def debug_bgzf_stitched(self) -> int:
+        """Files of the last submit_bgzf whose record boundaries came from the per-block walks (no serial walk)."""
+        n = C.c_uint32(0)
+        self._check(self.lib.gtb_debug_bgzf_stitched(self.h, C.byref(n)))
+        return n.value
 
     def debug_bgzf_records(self) -> abi.HostBamBatch:
         """The record batch the last submit_bgzf built on the device (parity tap)."""

@@ -355,6 +355,9 @@ int gtb_submit_bgzf(gtb_ctx *ctx, int region_id, int n_files, const gtb_bgzf_fil
  * on the CPU from the same source functions (test infrastructure of the CPU suite; no device needed, never used by a submit). */
 int gtb_debug_bgzf_records(gtb_ctx *ctx, uint32_t *n_reads, uint64_t *n_data, gtb_bam_core *core, uint8_t *data,
                            uint64_t *data_off, int32_t *sample, int32_t *rg);
+/* Files whose record boundaries were found by the per-block walks (every guessed block entry confirmed) rather than by the
+ * serial walk: of the last gtb_submit_bgzf of ctx, or of the last gtb_debug_bgzf_host when ctx is NULL. */
+int gtb_debug_bgzf_stitched(gtb_ctx *ctx, uint32_t *n_files_stitched);
 int gtb_debug_bgzf_host(int n_files, const gtb_bgzf_file *files, const gtb_bgzf_query *query, uint32_t *n_reads,
                         uint64_t *n_data, gtb_bam_core *core, uint8_t *data, uint64_t *data_off, int32_t *sample, int32_t *rg,
                         uint64_t *n_inflated, uint8_t *inflated);

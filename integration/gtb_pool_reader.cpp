@@ -248,7 +248,7 @@ void parallel_reader_genotype_only(
         if (rc == 0)
         {
           submitted = true;
-          print_log(log_severity::debug, "[gtb200] pool ", thread_id, ": ", st.n_records, " records decoded on the device from ",
+          print_log(log_severity::info, "[gtb200] pool ", thread_id, ": ", st.n_records, " records decoded on the device from ",
                     pool.n_bytes, " compressed bytes");
         }
         else if (rc == GTB_ERR_INPUT || rc == GTB_ERR_CAPACITY)

@@ -49,6 +49,7 @@ def test_bgzf_submit_matches_golden_accumulators(pre, ctx):
         st = ctx.submit_bgzf(40, files, q)
         assert st.n_records == len(bam)
         cases.assert_batches_equal(ctx.debug_bgzf_records(), want_batch, "device vs CPU emulation")
+        assert ctx.debug_bgzf_stitched() == engine.bgzf_host_stitched()  # these files cut records anywhere: mostly serial walks
         compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), ctx.pool_finish(40).as_dict(), "bgzf")
     finally:
         ctx.region_end(40)
@@ -140,6 +141,7 @@ def test_bgzf_against_the_reference_reader_on_htslib_files(ctx):
                 ctx.pool_begin(43, int(want.sample.max()) + 1)
                 ctx.submit_bgzf(43, files, bgzf.query(0, 0, 1 << 40))
                 cases.assert_batches_equal(ctx.debug_bgzf_records(), want, name)
+                assert ctx.debug_bgzf_stitched() == files.n_files  # record boundaries from the per-block walks
                 compare.compare_accum(compare.probe_accum(gtba.load(pre + ".accum.gtba")), ctx.pool_finish(43).as_dict(), name)
             finally:
                 ctx.region_end(43)

@@ -36,7 +36,7 @@ def _vcf_text(out_dir):
     return text
 
 
-def _run_both(args, tmp, extra_env=None):
+def _run_both(args, tmp, extra_env=None, expect_in_log=None):
     outs = {}
     for exe in ("graphtyper", "graphtyper_gtb"):
         out = os.path.join(tmp, "out_" + exe)
@@ -52,6 +52,8 @@ def _run_both(args, tmp, extra_env=None):
         assert ref[k] == gtb[k], f"{k}: the drop-in binary's VCF differs from the reference's"
         n_records += sum(1 for line in ref[k].splitlines() if line and not line.startswith("#"))
     assert "CPU path" not in outs["graphtyper_gtb"][1], outs["graphtyper_gtb"][1][-2000:]
+    if expect_in_log:
+        assert expect_in_log in outs["graphtyper_gtb"][1], outs["graphtyper_gtb"][1][-3000:]
     # N4: the pools' calls reach the merge through memory (integration/gtb_vcf_store.cpp) -- with --no_cleanup the
     # reference leaves its cereal + gzip batch files <tmp>/graphtyper_*/it1/<first sample>/<n> behind, the drop-in none
     left = {}
@@ -81,6 +83,33 @@ def test_genotype_vcf_cli_is_byte_identical():
             f.write("\n".join(man["regions"][0]["sams"]) + "\n")
         n = _run_both(["genotype", man["fasta"], f"--sams={sams}", f"--region={man['contig']}:1-60000", f"--vcf={man['vcf']}.gz",
                        "--no_bamshrink", "--threads=2"], tmp)
+        assert n > 400
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def test_genotype_vcf_cli_on_indexed_bams_decodes_on_the_device():
+    """`genotype --vcf` from indexed BAM files: the drop-in reader hands the files' COMPRESSED bytes to the device
+    (gtb_submit_bgzf: the chunks of the region iterators; inflate, filters, merge order, parsing on the GPU) -- the log must say
+    so for every pool, and the final VCF must still be the reference's, byte for byte."""
+    _need("graphtyper", "graphtyper_gtb", "bgzip", "tabix", "sam2bam")
+    tmp = tempfile.mkdtemp(prefix="gtb_dropin_bgzf_")
+    try:
+        ds = synth.make_dataset(length=60000, n_sites=600, n_samples=3, seed=611, coverage=20, err=0.003, lowmapq_rate=0.05,
+                                unpaired_rate=0.02, improper_rate=0.03)
+        man = synth.write_dataset(ds, tmp, region_size=60000)
+        subprocess.run([os.path.join(BIN, "bgzip"), "-f", "-k", man["vcf"]], check=True)
+        subprocess.run([os.path.join(BIN, "tabix"), "-f", "-p", "vcf", man["vcf"] + ".gz"], check=True)
+        bams = []
+        for sam in man["regions"][0]["sams"]:
+            bam = sam[:-4] + ".bam"
+            subprocess.run([os.path.join(BIN, "sam2bam"), sam, bam], check=True)
+            bams.append(bam)
+        lst = os.path.join(tmp, "bams.txt")
+        with open(lst, "w") as f:
+            f.write("\n".join(bams) + "\n")
+        n = _run_both(["genotype", man["fasta"], f"--sams={lst}", f"--region={man['contig']}:1-60000", f"--vcf={man['vcf']}.gz",
+                       "--no_bamshrink", "--threads=2"], tmp, expect_in_log="records decoded on the device")
         assert n > 400
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
