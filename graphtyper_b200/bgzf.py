@@ -163,7 +163,7 @@ def expected_pool_records(per_file: Sequence[List[ParsedRecord]], flag_filter: i
                 continue
             if sv_filter and not r.good_read_sv():
                 continue
-            rows.append(((r.pos, r.l_seq, r.seq, -fi, -k), fi, r))
+            rows.append(((r.tid, r.pos, r.l_seq, r.seq, -fi, -k), fi, r))
     rows.sort(key=lambda x: x[0])
     return [(fi, r) for _, fi, r in rows]
 
@@ -181,7 +181,7 @@ class BgzfFile(C.Structure):
 
 class BgzfQuery(C.Structure):
     _fields_ = [("tid", C.c_int32), ("flag_filter", C.c_uint32), ("beg", C.c_int64), ("end", C.c_int64),
-                ("sv_read_filter", C.c_uint32), ("check_crc", C.c_uint32)]
+                ("sv_read_filter", C.c_uint32), ("check_crc", C.c_uint32), ("whole_file", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class HostBgzfFiles:
@@ -224,8 +224,10 @@ class HostBgzfFiles:
             self.files[fi].rg = rg
 
 
-def query(tid: int, beg: int, end: int, flag_filter: int = 3840, sv: bool = False, check_crc: bool = True) -> BgzfQuery:
+def query(tid: int, beg: int, end: int, flag_filter: int = 3840, sv: bool = False, check_crc: bool = True,
+          whole_file: bool = False) -> BgzfQuery:
     q = BgzfQuery()
+    q.whole_file = 1 if whole_file else 0
     q.tid, q.beg, q.end, q.flag_filter = tid, beg, end, flag_filter
     q.sv_read_filter = 1 if sv else 0
     q.check_crc = 1 if check_crc else 0

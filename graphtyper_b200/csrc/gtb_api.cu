@@ -2441,6 +2441,7 @@ BamQuery make_query(const gtb_bgzf_query * q)
   Q.flag_filter = q->flag_filter;
   Q.sv_filter = q->sv_read_filter;
   Q.max_lseq = (uint32_t)MAX_SEQ;
+  Q.whole_file = q->whole_file;
   return Q;
 }
 
@@ -2463,6 +2464,8 @@ const char * bgzf_error_text(int st)
   case SCAN_ERR_TRUNCATED: return "the bytes handed over end before the chunk does";
   case SCAN_ERR_RECORD: return "malformed BAM record";
   case SCAN_ERR_CAPACITY: return "more records than the byte count allows";
+  case SCAN_ERR_KEY: return "contig index or read length beyond the sort key";
+  case SCAN_ERR_UNSORTED: return "a file is not in coordinate order";
   default: return "unknown decode error";
   }
 }
@@ -2626,8 +2629,10 @@ int gtb_submit_bgzf(gtb_ctx * ctx, int region_id, int n_files, const gtb_bgzf_fi
   {
     if (launch_bgzf_order(Z, m_order, B.d_bgzf_cub.p, cub_bytes, s) != 0)
       return fail(GTB_ERR_CUDA, "gtb_submit_bgzf: sort launch failed");
-    CUDA_TRY(cudaMemcpyAsync(h_status + 4, dt + o_status + 16, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h_status, dt + o_status, 32, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    if ((int)h_status[0] != 0)
+      return fail(GTB_ERR_INPUT, std::string("gtb_submit_bgzf: ") + bgzf_error_text((int)h_status[0]));
     static bool const force_merge = getenv("GTB_BGZF_FORCE_MERGE") != nullptr; // tests: always replay the reference's merge
     if (h_status[4] != 0 || force_merge)
     {

@@ -31,6 +31,8 @@ struct BamQuery
   uint32_t flag_filter; // records with any of these flag bits are dropped
   uint32_t sv_filter;   // 1: is_good_read
   uint32_t max_lseq;    // longer reads are an error (device read-length capacity)
+  uint32_t whole_file;  // no region: every record of the file is returned (sam_read1 instead of the iterator; `genotype` reads
+                        // its pools' files this way, src/utilities/hts_reader.cpp:94-97)
 };
 
 GTB_HD uint32_t le32(const uint8_t * p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
@@ -112,10 +114,13 @@ constexpr int BAM_SKIP = 0, BAM_KEEP = 1, BAM_STOP = 2, BAM_TOO_LONG = 3, BAM_FI
 // sort and the heap see them) and leave afterwards.
 GTB_HD int bam_classify(const uint8_t * rec, const BamFixed & f, const BamQuery & q)
 {
-  if (f.tid != q.tid || (long long)f.pos >= q.end)
-    return BAM_STOP;
-  if (!(bam_end_position(rec, f) > q.beg))
-    return BAM_SKIP;
+  if (!q.whole_file)
+  {
+    if (f.tid != q.tid || (long long)f.pos >= q.end)
+      return BAM_STOP;
+    if (!(bam_end_position(rec, f) > q.beg))
+      return BAM_SKIP;
+  }
   if ((f.flag & q.flag_filter) != 0)
     return BAM_FILTERED;
   if (q.sv_filter && !bam_good_read_sv(rec, f))
@@ -125,11 +130,16 @@ GTB_HD int bam_classify(const uint8_t * rec, const BamFixed & f, const BamQuery 
   return BAM_KEEP;
 }
 
-// first sort key: position and sequence length (the contig is the query's for every kept record)
+// first sort key: contig, position, sequence length as gt_pos_seq compares them (signed contig index: -1 sorts first).
+// 16 | 32 | 16 bits; bam_key_fits says whether a record fits them.
 GTB_HD unsigned long long bam_order_key(const BamFixed & f)
 {
-  return ((unsigned long long)(uint32_t)(f.pos + 1) << 32) | (uint32_t)f.l_seq; // pos >= -1
+  return ((unsigned long long)(uint32_t)(f.tid + 1) << 48) | ((unsigned long long)(uint32_t)(f.pos + 1) << 16) | (uint32_t)f.l_seq;
 }
+GTB_HD bool bam_key_fits(const BamFixed & f) { return f.tid >= -1 && f.tid < 65535 && f.pos >= -1 && f.l_seq >= 0 && f.l_seq < 65536; }
+// (contig, position) part and position part of a key
+GTB_HD unsigned long long key_place(unsigned long long key) { return key >> 16; }
+GTB_HD uint32_t key_pos(unsigned long long key) { return (uint32_t)(key >> 16); }
 // ties of the first key: packed sequence bytes (cmp < 0, 0, > 0)
 GTB_HD int bam_seq_compare(const uint8_t * a, const BamFixed & fa, const uint8_t * b, const BamFixed & fb)
 {
@@ -203,7 +213,9 @@ GTB_HD unsigned long long bgzf_voffset(const BgzfBlock * blocks, const BgzfSegme
 }
 
 constexpr int SCAN_OK = 0, SCAN_ERR_TRUNCATED = -20 /* a record that must be read runs past the bytes handed over */,
-              SCAN_ERR_RECORD = -21 /* malformed record */, SCAN_ERR_CAPACITY = -22 /* more records than slots */;
+              SCAN_ERR_RECORD = -21 /* malformed record */, SCAN_ERR_CAPACITY = -22 /* more records than slots */,
+              SCAN_ERR_KEY = -23 /* contig index / length beyond the sort key's fields */,
+              SCAN_ERR_UNSORTED = -24 /* a file is not in coordinate order: the merge would not be the sorted order */;
 
 // The records one file's iterator reads, in file order: start offsets into the inflated bytes.  Serial by nature (every
 // record's length sits in its own first four bytes).  Returns the number of records read and the status.
@@ -252,7 +264,7 @@ GTB_HD uint32_t bam_walk_file(const uint8_t * out, const BgzfBlock * blocks, con
         return n;
       }
       rec_start[file.rec_base + n++] = g;
-      if (f.tid != q.tid || (long long)f.pos >= q.end)
+      if (!q.whole_file && (f.tid != q.tid || (long long)f.pos >= q.end))
         return n; // the iterator is finished: later chunks are not read either
       g += 4ull + (unsigned long long)f.block_size;
     }
@@ -309,7 +321,7 @@ GTB_HD BlockWalk bam_walk_block(const uint8_t * out, const BgzfBlock & blk, cons
     }
     slot[w.count++] = g;
     g += 4ull + (unsigned long long)f.block_size;
-    if (f.tid != q.tid || (long long)f.pos >= q.end)
+    if (!q.whole_file && (f.tid != q.tid || (long long)f.pos >= q.end))
     {
       w.reason = WALK_STOP;
       break;

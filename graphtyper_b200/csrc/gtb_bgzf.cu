@@ -151,7 +151,10 @@ __global__ void __launch_bounds__(256) bam_compact_kernel(BgzfParams p)
   unsigned long long const g = p.rec_start[slot];
   p.sel_start[at] = g;
   p.sel_file[at] = file_of_slot(p, slot) | (p.filtered[slot] ? 0x80000000u : 0u);
-  p.key[at] = bam_order_key(bam_fixed(p.out + g));
+  BamFixed const f = bam_fixed(p.out + g);
+  if (!bam_key_fits(f))
+    atomicCAS(p.status, 0, SCAN_ERR_KEY);
+  p.key[at] = bam_order_key(f);
   p.idx[at] = at;
 }
 
@@ -203,6 +206,18 @@ __global__ void __launch_bounds__(128) bam_tie_kernel(BgzfParams p, uint32_t n)
   }
 }
 
+// The merge of the files is the sorted order only if every file is in coordinate order itself (and the reader's "records of one
+// position" groups do not mix contigs): checked on the ordering set, which is in (file, file order).
+__global__ void __launch_bounds__(256) bam_sorted_check_kernel(BgzfParams p, uint32_t m)
+{
+  uint32_t const at = blockIdx.x * blockDim.x + threadIdx.x;
+  if (at == 0 || at >= m || (p.sel_file[at] & 0x7FFFFFFFu) != (p.sel_file[at - 1] & 0x7FFFFFFFu))
+    return;
+  unsigned long long const a = p.key[at - 1], b = p.key[at];
+  if (key_place(b) < key_place(a) || (key_pos(a) == key_pos(b) && key_place(a) != key_place(b)))
+    atomicCAS(p.status, 0, SCAN_ERR_UNSORTED);
+}
+
 // new_group[j] = record j of the sorted ordering set differs from j - 1 in (position, length, sequence); what only the
 // reference's own algorithms can order is flagged in *p.need_host
 __global__ void __launch_bounds__(256) bam_rank_kernel(BgzfParams p, uint32_t m)
@@ -228,7 +243,8 @@ __global__ void __launch_bounds__(256) bam_rank_kernel(BgzfParams p, uint32_t m)
   }
   p.new_group[j] = fresh;
   // more than 16 records of one position: std::sort leaves insertion sort for introsort
-  if (j + 16 < m && (j == 0 || (p.key_sorted[j - 1] >> 32) != (p.key_sorted[j] >> 32)) && (p.key_sorted[j + 16] >> 32) == (p.key_sorted[j] >> 32))
+  if (j + 16 < m && (j == 0 || key_place(p.key_sorted[j - 1]) != key_place(p.key_sorted[j])) &&
+      key_place(p.key_sorted[j + 16]) == key_place(p.key_sorted[j]))
     atomicOr(p.need_host, 2u);
 }
 
@@ -335,6 +351,7 @@ int launch_bgzf_order(const BgzfParams & p, uint32_t m, void * temp, size_t temp
   cudaStream_t const s = (cudaStream_t)stream;
   if (m == 0)
     return 0;
+  bam_sorted_check_kernel<<<(m + 255) / 256, 256, 0, s>>>(p, m);
   if (cub::DeviceRadixSort::SortPairs(temp, temp_bytes, p.key, p.key_sorted, p.idx, p.idx_sorted, (int)m, 0, 64, s) != cudaSuccess)
     return -1;
   bam_tie_kernel<<<(m + 127) / 128, 128, 0, s>>>(p, m);
@@ -389,7 +406,7 @@ void reference_merge_order(uint32_t m, uint32_t n_files, const unsigned long lon
     for (size_t i = 0; i < v.size();)
     {
       size_t e = i + 1;
-      while (e < v.size() && (key_sorted[v[e].j] >> 32) == (key_sorted[v[i].j] >> 32))
+      while (e < v.size() && key_pos(key_sorted[v[e].j]) == key_pos(key_sorted[v[i].j]))
         ++e;
       group.assign(v.begin() + i, v.begin() + e);
       std::sort(group.begin(), group.end(), greater);
@@ -491,6 +508,8 @@ int bgzf_host_pipeline(const uint8_t * comp, const std::vector<BgzfBlock> & bloc
         ++*n_too_long;
       if (c == BAM_KEEP || c == BAM_FILTERED)
       {
+        if (!bam_key_fits(bam_fixed(rec)))
+          return SCAN_ERR_KEY;
         sel_start.push_back(rec_start[files[fi].rec_base + i]);
         sel_file.push_back(fi);
         sel_filtered.push_back(c == BAM_FILTERED);
@@ -498,6 +517,14 @@ int bgzf_host_pipeline(const uint8_t * comp, const std::vector<BgzfBlock> & bloc
     }
   }
   uint32_t const m = (uint32_t)sel_start.size();
+  for (uint32_t at = 1; at < m; ++at)
+    if (sel_file[at] == sel_file[at - 1])
+    {
+      unsigned long long const a = bam_order_key(bam_fixed(inflated.data() + sel_start[at - 1])),
+                               b = bam_order_key(bam_fixed(inflated.data() + sel_start[at]));
+      if (key_place(b) < key_place(a) || (key_pos(a) == key_pos(b) && key_place(a) != key_place(b)))
+        return SCAN_ERR_UNSORTED;
+    }
   std::vector<uint32_t> sorted(m);
   for (uint32_t i = 0; i < m; ++i)
     sorted[i] = i;
@@ -535,7 +562,8 @@ int bgzf_host_pipeline(const uint8_t * comp, const std::vector<BgzfBlock> & bloc
       }
     }
     rank[j] = (j ? rank[j - 1] : 0u) + (fresh ? 1u : 0u);
-    if (j + 16 < m && (j == 0 || (key_sorted[j - 1] >> 32) != (key_sorted[j] >> 32)) && (key_sorted[j + 16] >> 32) == (key_sorted[j] >> 32))
+    if (j + 16 < m && (j == 0 || key_place(key_sorted[j - 1]) != key_place(key_sorted[j])) &&
+        key_place(key_sorted[j + 16]) == key_place(key_sorted[j]))
       need_host |= 2u;
   }
   std::vector<uint32_t> perm;

@@ -323,7 +323,8 @@ int gtb_submit_bam_records(gtb_ctx *ctx, int region_id, const gtb_bam_batch *bat
  * hts_parallel_reader.cpp:66-136: ascending position, sequence length, packed sequence bytes; exact ties in file order), and
  * from there everything gtb_submit_bam_records does.  Limits (the shim keeps the reference's host reader for these): CRAM,
  * files with more than one read group (sample / read-group index are per file here), the coverage-bin cap, an empty BGZF block
- * before the end of the file.  A stream that does not decode, a malformed record or bytes that end before the chunk does return
+ * before the end of the file, a file that is not in coordinate order (the reference's heap merge is the sorted order only for
+ * sorted files; unmapped reads behind the mapped ones count as unsorted), more than 65 534 contigs.  A stream that does not decode, a malformed record or bytes that end before the chunk does return
  * GTB_ERR_INPUT, a read beyond the length capacity GTB_ERR_CAPACITY -- both BEFORE anything is added to the pool's
  * accumulators, so the caller can fall back to its own reader for this pool. */
 typedef struct gtb_bgzf_segment {
@@ -347,6 +348,10 @@ typedef struct gtb_bgzf_query {
   int64_t beg, end;         /* 0-based, half open (hts_itr_t::beg / end) */
   uint32_t sv_read_filter;  /* 1: is_good_read (SV calling) */
   uint32_t check_crc;       /* 1: verify the CRC-32 of every block as htslib does */
+  uint32_t whole_file;      /* 1: no region -- every record from the segment's first record to the end of the file, as
+                             * HtsReader reads with region "." (src/utilities/hts_reader.cpp:94-97; `genotype` reads its
+                             * pools' bamshrink output this way); tid / beg / end are ignored */
+  uint32_t reserved;
 } gtb_bgzf_query;
 int gtb_submit_bgzf(gtb_ctx *ctx, int region_id, int n_files, const gtb_bgzf_file *files, const gtb_bgzf_query *query,
                     gtb_submit_stats *stats);

@@ -33,6 +33,7 @@
 #include <graphtyper/utilities/hts_parallel_reader.hpp>
 #include <graphtyper/utilities/logging.hpp>
 
+#include <htslib/bgzf.h>
 #include <htslib/hts.h>
 #include <htslib/sam.h>
 
@@ -240,8 +241,9 @@ struct CoverageCap
 
 // The pool's files as COMPRESSED bytes for gtb_submit_bgzf: for every BAM file the chunks of its region iterator
 // (hts_itr_t::off, which HtsReader::open has already computed from the index: src/utilities/hts_reader.cpp:99-118), adjacent
-// chunks merged, each read from the file as it is -- no inflate, no record parsing, no heap on the host.  collect() says why
-// when the pool has to stay with the reference's reader: CRAM / SAM, no region iterator, several read groups in one file
+// chunks merged -- or, with region "." (how `genotype` reads its pools' bamshrink output), everything behind the header --
+// each read from the file as it is: no inflate, no record parsing, no heap on the host.  collect() says why
+// when the pool has to stay with the reference's reader: CRAM / SAM, several read groups in one file
 // (sample and read group are per file on the device), files that number the contig differently.
 struct BgzfPool
 {
@@ -250,6 +252,7 @@ struct BgzfPool
   std::vector<gtb_bgzf_file> files;
   gtb_bgzf_query query{};
   uint64_t n_bytes = 0;
+  std::vector<uint64_t> whole_u; // whole-file reading: virtual offset of every file's first record
 
   bool collect(gyper::HtsParallelReader const & reader, uint32_t flag_filter, bool is_sv, std::string & why_not)
   {
@@ -262,11 +265,34 @@ struct BgzfPool
       if (!f.fp || f.fp->format.format != bam || f.fp->format.compression != bgzf)
         return why_not = "not a BAM file", false;
       hts_itr_t const * it = f.hts_iter;
-      if (!it || it->read_rest || it->nocoor || it->multi || it->tid < 0)
+      bool const whole = it == nullptr; // region ".": HtsReader reads the file with sam_read1 (hts_reader.cpp:94-97)
+      if (i == 0)
+        query.whole_file = whole ? 1u : 0u;
+      else if ((query.whole_file != 0) != whole)
+        return why_not = "files disagree on region / whole-file reading", false;
+      if (!whole && (it->read_rest || it->nocoor || it->multi || it->tid < 0))
         return why_not = "no single-region iterator", false;
       if (f.rg2sample_i.size() > 1)
         return why_not = "several read groups in one file", false;
-      if (i == 0)
+      if (whole)
+      {
+        // where the records start: behind the header, found by reading the header once more on a handle of our own
+        htsFile * hf = hts_open(f.fp->fn, "r");
+        if (!hf)
+          return why_not = "cannot reopen the file", false;
+        sam_hdr_t * hh = sam_hdr_read(hf);
+        uint64_t const u = hh ? (uint64_t)bgzf_tell(hf->fp.bgzf) : 0;
+        if (hh)
+          sam_hdr_destroy(hh);
+        hts_close(hf);
+        if (!hh)
+          return why_not = "cannot read the header", false;
+        struct stat st0;
+        if (::stat(f.fp->fn, &st0) != 0 || (uint64_t)st0.st_size - (u >> 16) > (1ull << 31))
+          return why_not = "more than 2 GiB to read without a region", false;
+        whole_u.push_back(u);
+      }
+      else if (i == 0)
       {
         query.tid = it->tid;
         query.beg = it->beg;
@@ -284,15 +310,16 @@ struct BgzfPool
         return why_not = "cannot stat the file", false;
       }
       uint64_t const file_size = (uint64_t)st.st_size;
-      for (int k = 0; k < it->n_off; ++k)
+      int const n_chunks = whole ? 1 : it->n_off;
+      for (int k = 0; k < n_chunks; ++k)
       {
-        uint64_t const u = it->off[k].u;
-        uint64_t v = it->off[k].v;
-        while (k + 1 < it->n_off && it->off[k + 1].u == v) // adjacent chunks: hts_itr_next reads on without a seek
+        uint64_t const u = whole ? whole_u.back() : it->off[k].u;
+        uint64_t v = whole ? (file_size << 16) : it->off[k].v;
+        while (!whole && k + 1 < it->n_off && it->off[k + 1].u == v) // adjacent chunks: hts_itr_next reads on without a seek
           v = it->off[++k].v;
         uint64_t const begin = u >> 16;
         // the last record that is read starts before v and may reach into the blocks behind v's: three more block sizes
-        uint64_t const end = std::min<uint64_t>(file_size, (v >> 16) + 4 * 65536ull);
+        uint64_t const end = whole ? file_size : std::min<uint64_t>(file_size, (v >> 16) + 4 * 65536ull);
         if (begin >= end)
           continue;
         std::vector<uint8_t> buf(end - begin);

@@ -134,3 +134,45 @@ def test_replayed_merge_equals_device_order_when_nothing_is_ambiguous(monkeypatc
     monkeypatch.setenv("GTB_BGZF_FORCE_MERGE", "1")
     b = engine.bgzf_host(files, bgzf.query(tid, beg, end))
     cases.assert_batches_equal(a, b, "forced merge")
+
+
+def _two_contig_records(order):
+    recs = []
+    for k, (tid, pos) in enumerate(order):
+        seq = bytes([0x12 + (k % 7)] * 30)
+        recs.append(bgzf.bam_record(tid, pos, 60, 0 if tid >= 0 else 4, b"w%03d" % k, [(60 << 4) | 0] if tid >= 0 else [], seq, 60,
+                                    bytes([30]) * 60, b"ASC\x05", -1, -1, 0))
+    return recs
+
+
+def test_whole_file_reading_spans_contigs_and_needs_sorted_files():
+    """whole_file = the reader without a region (sam_read1): every record of every contig, merged by (contig, position, length,
+    sequence).  A file that is not in coordinate order -- unmapped reads behind the mapped ones included, contig -1 sorts first
+    in the reference's heap -- is declined: only for sorted files is the heap's output the sorted order."""
+    a = _two_contig_records([(0, 100), (0, 100), (0, 250), (1, 5), (1, 90)])
+    b = _two_contig_records([(0, 90), (0, 250), (1, 5), (1, 400)])
+    made = []
+    for fi, recs in enumerate((a, b)):
+        hdr = bgzf.bam_header(cases.REFS)
+        stream = hdr + b"".join(recs)
+        raw, blocks = bgzf.bgzf_compress(stream, 300)
+        made.append((raw, stream, blocks, len(hdr), fi, fi))
+    files = cases.whole_file_segments(made)
+    got = engine.bgzf_host(files, bgzf.query(0, 0, 0, whole_file=True))
+    assert len(got) == 9
+    assert list(zip(got.core["tid"], got.core["pos"])) == sorted(zip(got.core["tid"], got.core["pos"]))
+    per_file = [[bgzf.ParsedRecord(r[4:]) for r in recs] for recs in (a, b)]
+    rows = bgzf.expected_pool_records(per_file, 3840, False)
+    assert [(r.tid, r.pos) for _, r in rows] == list(zip(got.core["tid"], got.core["pos"]))
+    assert [fi for fi, _ in rows if True][:1] == [int(got.sample[0])]
+    # a region query on the same files stops at the first record of the next contig
+    reg = engine.bgzf_host(files, bgzf.query(0, 0, 1000))
+    assert len(reg) == 5 and set(reg.core["tid"]) == {0}
+    for bad_order in ([(0, 100), (0, 50)], [(1, 5), (0, 90)], [(0, 100), (-1, -1)]):
+        hdr = bgzf.bam_header(cases.REFS)
+        stream = hdr + b"".join(_two_contig_records(bad_order))
+        raw, blocks = bgzf.bgzf_compress(stream)
+        f = cases.whole_file_segments([(raw, stream, blocks, len(hdr), 0, 0)])
+        with pytest.raises(engine.GtbError) as e:
+            engine.bgzf_host(f, bgzf.query(0, 0, 0, whole_file=True))
+        assert e.value.code == -5 and "coordinate order" in str(e.value)

@@ -113,7 +113,7 @@ def test_record_batch_equals_the_reference_reader(name):
     tmp = tempfile.mkdtemp(prefix="gtb_bgzf_ref_")
     try:
         pre, want, files = build_case(name, tmp)
-        got = engine.bgzf_host(files, bgzf.query(0, 0, 1 << 40))
+        got = engine.bgzf_host(files, bgzf.query(0, 0, 0, whole_file=True))  # gt_probe reads the files without a region
         # exact duplicates within a file exist in these pools: the order below is the reference's own
         n_ties = 0
         for k in range(1, len(want)):
