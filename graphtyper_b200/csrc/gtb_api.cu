@@ -2611,7 +2611,14 @@ int gtb_submit_bgzf(gtb_ctx * ctx, int region_id, int n_files, const gtb_bgzf_fi
   Z.keep2 = reinterpret_cast<uint32_t *>(dt + o_keep2);
   Z.keep2_pos = reinterpret_cast<uint32_t *>(dt + o_k2pos);
   Z.out_idx = reinterpret_cast<uint32_t *>(dt + o_outidx);
-  if (launch_bgzf_front(Z, B.d_bgzf_cub.p, cub_bytes, s) != 0)
+  static bool const trace = getenv("GTB_TRACE") != nullptr; // timeline of the decode (profiling aid)
+  static thread_local cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+  auto const t_begin = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
+  if (trace && !tev[0])
+    for (auto & e : tev)
+      CUDA_TRY(cudaEventCreate(&e));
+  if (launch_bgzf_front(Z, B.d_bgzf_cub.p, cub_bytes, s, trace ? reinterpret_cast<void * const *>(tev) : nullptr) != 0)
     return fail(GTB_ERR_CUDA, "gtb_submit_bgzf: decode launch failed");
   CUDA_TRY(cudaMemcpyAsync(h_status, dt + o_status, 32, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -2620,6 +2627,7 @@ int gtb_submit_bgzf(gtb_ctx * ctx, int region_id, int n_files, const gtb_bgzf_fi
     return fail(GTB_ERR_INPUT, std::string("gtb_submit_bgzf: ") + bgzf_error_text((int)h_status[0]));
   if (h_status[1] != 0)
     return fail(GTB_ERR_CAPACITY, "read longer than 152 bases (reference MAX_READ_LENGTH is 151)");
+  double const us_front = since();
   uint32_t const m_order = ns ? h_status[2] : 0; // records the iterators return
   B.bgzf_stitched = (uint32_t)P.files.size() - h_status[5];
   size_t const total = ns ? h_status[3] : 0;     // records the pool loop keeps
@@ -2671,8 +2679,19 @@ int gtb_submit_bgzf(gtb_ctx * ctx, int region_id, int n_files, const gtb_bgzf_fi
   Z.data_off = reinterpret_cast<unsigned long long *>(r + L.o_doff);
   Z.rg = reinterpret_cast<int32_t *>(r + L.o_rg);
   Z.sample = reinterpret_cast<int32_t *>(static_cast<uint8_t *>(B.d_batch.p) + Lo.o_sample);
+  double const us_order = since();
   if (launch_bgzf_back(Z, m_order, (uint32_t)total, d_perm, B.d_bgzf_cub.p, cub_bytes, s) != 0)
     return fail(GTB_ERR_CUDA, "gtb_submit_bgzf: gather launch failed");
+  if (trace)
+  {
+    float inflate = 0, walk = 0, compact = 0;
+    cudaEventElapsedTime(&inflate, tev[0], tev[1]);
+    cudaEventElapsedTime(&walk, tev[1], tev[2]);
+    cudaEventElapsedTime(&compact, tev[2], tev[3]);
+    fprintf(stderr, "[gtb trace us] bgzf: %zu blocks, %u + %u records | host: front synced %.0f, order + merge %.0f (replayed on the host: %d) | "
+                    "dev: inflate %.0f walk %.0f classify + compact %.0f\n",
+            P.blocks.size(), m_order, (unsigned)total, us_front, us_order - us_front, d_perm ? 1 : 0, inflate * 1e3, walk * 1e3, compact * 1e3);
+  }
   B.bgzf_n = (uint32_t)total;
   unsigned long long const data_base[2] = {0, 0};
   uint32_t const rec_begin[2] = {0u, (uint32_t)total};

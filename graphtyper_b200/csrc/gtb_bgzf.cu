@@ -324,17 +324,24 @@ size_t bgzf_temp_bytes(uint32_t n_slots)
 }
 
 // first part: up to the sizes (the host needs them for what follows): ordering set m = *n_kept, final batch n = *n_final
-int launch_bgzf_front(const BgzfParams & p, void * temp, size_t temp_bytes, void * stream)
+int launch_bgzf_front(const BgzfParams & p, void * temp, size_t temp_bytes, void * stream, void * const * trace_events)
 {
   cudaStream_t const s = (cudaStream_t)stream;
+  auto mark = [&](int i) {
+    if (trace_events)
+      cudaEventRecord((cudaEvent_t)trace_events[i], s);
+  };
+  mark(0);
   if (p.n_blocks)
     bgzf_inflate_kernel<<<(p.n_blocks + INFLATE_WARPS - 1) / INFLATE_WARPS, INFLATE_WARPS * 32, 0, s>>>(p);
+  mark(1);
   if (p.n_blocks && !p.serial_walk)
     bam_walk_blocks_kernel<<<(p.n_blocks + 63) / 64, 64, 0, s>>>(p);
   if (p.n_files)
     bam_walk_kernel<<<(p.n_files + 31) / 32, 32, 0, s>>>(p);
   if (p.n_block_slots && !p.serial_walk)
     bam_walk_scatter_kernel<<<(p.n_block_slots + 255) / 256, 256, 0, s>>>(p);
+  mark(2);
   if (p.n_slots)
   {
     bam_classify_kernel<<<(p.n_slots + 255) / 256, 256, 0, s>>>(p);
@@ -342,6 +349,7 @@ int launch_bgzf_front(const BgzfParams & p, void * temp, size_t temp_bytes, void
       return -1;
     bam_compact_kernel<<<(p.n_slots + 255) / 256, 256, 0, s>>>(p);
   }
+  mark(3);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -313,7 +313,8 @@ struct BgzfParams
   int32_t * sample;
 };
 size_t bgzf_temp_bytes(uint32_t n_slots);
-int launch_bgzf_front(const BgzfParams & p, void * temp, size_t temp_bytes, void * stream);
+// trace_events: four cudaEvent_t recorded before the inflate, after it, after the record walks, after the compaction (or null)
+int launch_bgzf_front(const BgzfParams & p, void * temp, size_t temp_bytes, void * stream, void * const * trace_events);
 int launch_bgzf_order(const BgzfParams & p, uint32_t m, void * temp, size_t temp_bytes, void * stream);
 int launch_bgzf_back(const BgzfParams & p, uint32_t m, uint32_t n, const uint32_t * perm, void * temp, size_t temp_bytes, void * stream);
 void reference_merge_order(uint32_t m, uint32_t n_files, const unsigned long long * key_sorted, const uint32_t * rank,

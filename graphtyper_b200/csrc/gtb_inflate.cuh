@@ -50,6 +50,15 @@ struct BitReader
 
 GTB_HD void br_refill(BitReader & b)
 {
+  // four bytes at once while they are there (four independent loads, one latency), single bytes at the end of the input
+  if (b.cnt <= 32 && b.ie - b.ip >= 4)
+  {
+    uint32_t const w = (uint32_t)b.ip[0] | ((uint32_t)b.ip[1] << 8) | ((uint32_t)b.ip[2] << 16) | ((uint32_t)b.ip[3] << 24);
+    b.buf |= (unsigned long long)w << b.cnt;
+    b.cnt += 32;
+    b.ip += 4;
+    return;
+  }
   while (b.cnt <= 56 && b.ip < b.ie)
   {
     b.buf |= (unsigned long long)(*b.ip++) << b.cnt;

@@ -57,3 +57,25 @@ for a, b in zip(acc_rec, acc_bgzf):
 print(f"record entry {t_rec*1e3:.2f} ms ({n/t_rec/1e6:.2f} M reads/s; copy phase {d_rec:.2f} ms); "
       f"BGZF entry {t_bgzf*1e3:.2f} ms ({n/t_bgzf/1e6:.2f} M reads/s, {comp_bytes/t_bgzf/1e9:.2f} GB/s compressed; decode phase "
       f"{d_bgzf:.2f} ms, files stitched {ctx.debug_bgzf_stitched()}); zlib inflate alone on one host core {t_zlib*1e3:.1f} ms; accumulators identical")
+
+# ---- several pools in flight: one context per pool thread on the shared regions, as the drop-in reader runs them
+T = int(os.environ.get("BB_THREADS", 4))
+if T > 1:
+    extra = []
+    for t in range(T):
+        c = engine.Context(0)
+        for k in ids:
+            c.region_attach(k, ctx, k)
+            c.pool_begin(k, 1)
+        extra.append(c)
+
+    def pool(t, s):
+        k = s % len(ids)
+        extra[t].pool_reset(k)
+        extra[t].submit_bgzf(k, pools[k][1], queries[k])
+
+    reps = 4 * len(ids)
+    bench.run_pipelined(T, reps, pool)
+    wall = bench.run_pipelined(T, reps, pool)
+    per = wall / reps
+    print(f"{T} pool threads: {per*1e3:.2f} ms per region pool ({n/len(ids)/per/1e6:.2f} M reads/s, {comp_bytes/len(ids)/per/1e9:.2f} GB/s compressed)")
