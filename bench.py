@@ -344,6 +344,75 @@ def sw_key(ctx):
     return out
 
 
+def bgzf_key(owner, ids, graphs, regions, rs, n_regions=6, n_threads=4):
+    """N3: the BGZF entry (gtb_submit_bgzf: compressed BAM bytes in, genotyped pool out) on the first regions of the workload,
+    one pool per call as the drop-in reader issues them, several pool threads in flight; next to the record entry on the same
+    records (same accumulators required) and to zlib inflating the same bytes on one host core."""
+    from graphtyper_b200 import abi, bgzf, engine, synth
+    ids = ids[:n_regions]
+    bams = [abi.bam_batch_from_readsets([rs], [synth.reads_for_region(rs, b, e)]) for (b, e) in regions[:n_regions]]
+    n = sum(len(b) for b in bams)
+    hdr = bgzf.bam_header([("chr1", 250000000)])
+    pools, queries, comp_bytes, raws = [], [], 0, []
+    for bam in bams:
+        raw, blocks = bgzf.bgzf_compress_records(hdr, bgzf.records_from_batch(bam))  # blocks cut at record boundaries, as htslib writes
+        u = bgzf.voffset_of(blocks, len(hdr))
+        pools.append(bgzf.HostBgzfFiles([(raw, [(u, len(raw) << 16, True)], 0, 0)], [[b[0] for b in blocks] + [len(raw) - 28, len(raw)]]))
+        pos = bam.core["pos"].astype(np.int64)
+        queries.append(bgzf.query(int(bam.core["tid"][0]), int(pos.min()), int(pos.max()) + 1))
+        comp_bytes += len(raw)
+        raws.append(raw)
+    t0 = time.perf_counter()
+    inflated = sum(len(bgzf.inflate_file(r)) for r in raws)
+    t_zlib = time.perf_counter() - t0
+    ctxs = []
+    for t in range(n_threads):
+        c = engine.Context(device=owner.device)
+        for k in ids:
+            c.region_attach(k, owner, k)
+            c.pool_begin(k, 1)
+        ctxs.append(c)
+    try:
+        c0 = ctxs[0]
+        want = []
+        for k in ids:  # the record entry on the same records: the accumulators the BGZF entry must reproduce
+            c0.submit_bam(k, bams[k])
+            want.append({a: b.copy() for a, b in c0.pool_finish(k).as_dict().items()})
+            c0.pool_reset(k)
+        lat = []
+        same = True
+        for k in ids:
+            t0 = time.perf_counter()
+            c0.submit_bgzf(k, pools[k], queries[k])
+            lat.append(time.perf_counter() - t0)
+            got = c0.pool_finish(k).as_dict()
+            same = same and all(np.array_equal(got[a], want[k][a]) for a in want[k])
+            c0.pool_reset(k)
+        stitched = c0.debug_bgzf_stitched()
+
+        def pool(t, s):
+            k = s % len(ids)
+            ctxs[t].pool_reset(k)
+            ctxs[t].submit_bgzf(k, pools[k], queries[k])
+
+        reps = 4 * len(ids)
+        run_pipelined(n_threads, reps, pool)
+        per = run_pipelined(n_threads, reps, pool) / reps
+    finally:
+        for c in ctxs:
+            c.close()
+    return {"regions": len(ids), "records": n, "compressed_bytes": comp_bytes, "inflated_bytes": inflated,
+            "accumulators_equal_record_entry": bool(same), "files_with_parallel_record_walk": stitched,
+            "ms_per_pool_one_at_a_time": float(np.median(lat)) * 1e3, "pool_threads": n_threads, "ms_per_pool_pooled": per * 1e3,
+            "reads_per_s": n / len(ids) / per, "compressed_GBps": comp_bytes / len(ids) / per / 1e9,
+            "cpu_baseline": {"kind": "port", "cores": 1, "value": inflated / t_zlib / 1e9, "unit": "GB/s inflated",
+                             "sample": "zlib inflate of the same BGZF bytes alone (no record parsing, no merge), one host core"},
+            "gpu_inflated_GBps": inflated / len(ids) / per / 1e9,
+            "note": "one warp per BGZF block (a serial Huffman decode per block: one pool alone waits ~2.4 ms for its slowest "
+                    "block, pools in flight overlap); compressed bytes -> accumulators, nothing but 32 status bytes comes back "
+                    "before the pool is finished"}
+
+
 def cli_end_to_end(ref, sites, rs, regions):
     """end-to-end CLI wall.  ONE process genotypes all 20 regions of the sample from one indexed BAM
     (`graphtyper genotype REF --sam=all.bam --region_file=... --vcf=...`, bamshrink included) -- once with the stock
@@ -803,6 +872,13 @@ def main() -> None:
                 out["sw"] = sw_key(owner)
             except Exception as ex:
                 out["sw"] = {"error": repr(ex)}
+            try:
+                out["bgzf"] = bgzf_key(owner, ids, graphs, regions, rs)
+            except Exception as ex:
+                out["bgzf"] = {"error": repr(ex)}
+            if out["bgzf"].get("accumulators_equal_record_entry") is False:
+                print(json.dumps({"error": "the BGZF entry's accumulators differ from the record entry's", "bgzf": out["bgzf"]}))
+                sys.exit(1)
             try:
                 out["cli"] = cli_end_to_end(ref, sites, rs, regions)
             except Exception as ex:

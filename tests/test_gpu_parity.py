@@ -422,6 +422,7 @@ def test_zero_copy_columns_equal_staged_columns(ctx, skew, n_chunks, monkeypatch
         batches.append(abi.batch_from_probe(rd))
         ns.append(n_samples_of(rd))
     pinned, arena = engine.pin_batches(batches, skew=skew)
+    monkeypatch.setenv("GTB_ZERO_COPY", "1")  # the default only with several ranks per host (LOCAL_WORLD_SIZE > 1)
     ctx.region_begin_multi(ids, graphs)
     try:
         for k, n in zip(ids, ns):
