@@ -3002,6 +3002,8 @@ int gtb_pool_reset(gtb_ctx * ctx, int region_id)
 int gtb_accumulator_sizes(gtb_ctx * ctx, int region_id, uint32_t * n_bubbles, uint64_t * n_scores, uint64_t * n_cov)
 {
   auto * c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !n_bubbles || !n_scores || !n_cov)
+    return fail(GTB_ERR_ARG, "bad arguments");
   auto it = c->regions.find(region_id);
   if (it == c->regions.end())
     return fail(GTB_ERR_STATE, "unknown region");
@@ -4135,6 +4137,8 @@ int gtb_sw_align_batch(gtb_ctx * ctx, int n_pairs, const uint8_t * query, const 
   }
   if (q_off[0] != 0 || d_off[0] != 0)
     return fail(GTB_ERR_ARG, "gtb_sw_align_batch: offsets must start at 0");
+  if (c->device < 0)
+    return fail(GTB_ERR_CUDA, "host-only context: the re-alignment kernel needs a CUDA device (no CPU fallback)");
   cudaSetDevice(c->device);
   for (auto & e : c->sw_ev)
     if (!e)
