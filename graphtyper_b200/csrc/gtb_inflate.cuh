@@ -12,6 +12,7 @@
 //     (the crc32_combine identity), so the check htslib makes on every block (bgzf.c: inflate_block / check) is kept.
 // Tables live in shared memory on the device (3.2 KiB per warp).
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 #if defined(__CUDACC__)
@@ -422,8 +423,12 @@ GTB_HDN int inflate_raw(const uint8_t * in, uint32_t in_len, uint8_t * out, uint
       mdist = GTB_INF_BCAST(mdist);
       GTB_INF_SYNC(); // lane 0's literals are visible to the lanes that copy
       uint32_t const from = op - mdist;
-      for (uint32_t i = lane; i < mlen; i += GTB_INF_WIDTH)
-        out[op + i] = out[from + (mdist >= mlen ? i : i % mdist)];
+      if (mdist >= mlen)
+        for (uint32_t i = lane; i < mlen; i += GTB_INF_WIDTH)
+          out[op + i] = out[from + i];
+      else // the match overlaps its own output: period mdist
+        for (uint32_t i = lane; i < mlen; i += GTB_INF_WIDTH)
+          out[op + i] = out[from + i % mdist];
       op += mlen;
       GTB_INF_SYNC();
     }
@@ -439,7 +444,22 @@ GTB_HD uint32_t crc32_update(uint32_t crc, const uint8_t * p, uint32_t n)
   constexpr uint32_t NIB[16] = {0x00000000u, 0x1DB71064u, 0x3B6E20C8u, 0x26D930ACu, 0x76DC4190u, 0x6B6B51F4u, 0x4DB26158u, 0x5005713Cu,
                                 0xEDB88320u, 0xF00F9344u, 0xD6D6A3E8u, 0xCB61B38Cu, 0x9B64C2B0u, 0x86D3D2D4u, 0xA00AE278u, 0xBDBDF21Cu};
   crc = ~crc;
-  for (uint32_t i = 0; i < n; ++i)
+  uint32_t i = 0;
+  for (; i < n && (reinterpret_cast<uintptr_t>(p + i) & 3u) != 0; ++i)
+  {
+    crc ^= p[i];
+    crc = NIB[crc & 15u] ^ (crc >> 4);
+    crc = NIB[crc & 15u] ^ (crc >> 4);
+  }
+  // aligned body, a little-endian word at a time: one load per four bytes, and the loads do not depend on the CRC chain
+  for (; i + 4 <= n; i += 4)
+  {
+    crc ^= *reinterpret_cast<const uint32_t *>(p + i);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      crc = NIB[crc & 15u] ^ (crc >> 4);
+  }
+  for (; i < n; ++i)
   {
     crc ^= p[i];
     crc = NIB[crc & 15u] ^ (crc >> 4);
