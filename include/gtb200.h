@@ -11,6 +11,12 @@
  *                                  update_paths + get_better_paths + VcfWriter::update_haplotype_scores_geno
  *                                  (src/utilities/hts_parallel_reader.cpp:245-338,655-708; src/typer/alignment.cpp:331,482,557;
  *                                  src/typer/vcf_writer.cpp:88-250,503-676; src/graph/haplotype.cpp:180-585)
+ *   gtb_submit_bam_records()  the same with the per-record derivations (sequence, AS-XS, duplicate shortcut, read-name
+ *                                  maps) on the device; the caller still reads the records with HtsParallelReader
+ *   gtb_submit_bgzf()    replaces  that reader as well: HtsReader::get_next_read_in_order + HtsParallelReader::read_record +
+ *                                  the pool loop's filters (src/utilities/hts_reader.cpp:166-303, hts_parallel_reader.cpp:66-136,
+ *                                  528-568,655-663) and, below them, htslib's bgzf_read_block / bam_read1 / hts_itr_next -- the
+ *                                  caller hands over the files' COMPRESSED bytes
  *   gtb_pool_finish()    replaces  reading VcfWriter::haplotypes[*].hap_samples[*]   include/graphtyper/typer/vcf_writer.hpp:51-52
  *                                  (input of Vcf::add_haplotype, src/typer/vcf.cpp:1507)
  *   gtb_calls_from_accumulators()  = get_haplotype_phred + SampleCall ctor/get_gt_call/get_gq
