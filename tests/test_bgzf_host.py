@@ -176,3 +176,68 @@ def test_whole_file_reading_spans_contigs_and_needs_sorted_files():
         with pytest.raises(engine.GtbError) as e:
             engine.bgzf_host(f, bgzf.query(0, 0, 0, whole_file=True))
         assert e.value.code == -5 and "coordinate order" in str(e.value)
+
+
+def _one_file(stream_records, block, level, strategy):
+    hdr = bgzf.bam_header(cases.REFS)
+    stream = hdr + b"".join(stream_records)
+    raw, blocks = bgzf.bgzf_compress(stream, block, level, strategy)
+    offs = [[b[0] for b in blocks] + [len(raw) - 28, len(raw)]]
+    u = bgzf.voffset_of(blocks, len(hdr))
+    return raw, stream, blocks, len(hdr), offs, u
+
+
+def test_inflate_fuzz_random_streams_and_corruptions():
+    """Seeded fuzz of the decoder: (1) random payloads of every entropy (runs, text-like, noise) under random zlib settings
+    inflate to their source; (2) random bit flips and truncations anywhere in the compressed bytes either decode to something
+    the CRC / ISIZE check rejects or are reported as a stream error -- never a crash, a hang or a different record batch
+    accepted silently (a flip may hit bytes that do not matter, e.g. the gzip MTIME field: then the batch must be unchanged)."""
+    rng = np.random.default_rng(2024)
+    recs = []
+    for k in range(400):
+        kind = k % 4
+        l = int(rng.integers(40, 150))
+        if kind == 0:
+            seq = bytes([0x11]) * ((l + 1) // 2)
+        elif kind == 1:
+            seq = bytes(rng.choice([0x12, 0x48, 0x84, 0x21], (l + 1) // 2).astype(np.uint8))
+        else:
+            seq = bytes(rng.integers(0, 256, (l + 1) // 2, dtype=np.uint8))
+        qual = bytes(rng.integers(2, 41, l, dtype=np.uint8)) if kind != 0 else bytes([30]) * l
+        recs.append(bgzf.bam_record(0, 1000 + k // 2, 60, 0, b"fz%04d" % k, [(l << 4) | 0], seq, l, qual, b"ASC\x07XSC\x01NMC\x00"))
+    q = bgzf.query(0, 0, 0, whole_file=True)
+    want = None
+    for trial in range(12):
+        level = int(rng.integers(0, 10))
+        strategy = int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]))
+        block = int(rng.choice([700, 4096, 20000, 0xFF00]))
+        raw, stream, blocks, hlen, offs, u = _one_file(recs, block, level, strategy)
+        files = bgzf.HostBgzfFiles([(raw, [(u, len(raw) << 16, True)], 0, 0)], offs)
+        got, infl = engine.bgzf_host(files, q, want_inflated=True)
+        first = [b for b in blocks if b[1] <= hlen < b[1] + b[2]][0]
+        assert bytes(infl[:len(stream) - first[1]]) == stream[first[1]:], (level, strategy, block)
+        assert len(got) == len(recs)
+        if want is None:
+            want = got
+        else:
+            cases.assert_batches_equal(got, want, "same records under every compression")
+    raw, stream, blocks, hlen, offs, u = _one_file(recs, 4096, 6, zlib.Z_DEFAULT_STRATEGY)
+    n_rejected = 0
+    for trial in range(300):
+        bad = bytearray(raw)
+        if trial % 5 == 4:
+            cut = int(rng.integers(blocks[0][0] + 20, len(raw) - 30))
+            bad = bad[:cut]
+        else:
+            for _ in range(int(rng.integers(1, 4))):
+                at = int(rng.integers(blocks[0][0], len(raw) - 28))
+                bad[at] ^= 1 << int(rng.integers(0, 8))
+        files = bgzf.HostBgzfFiles([(bytes(bad), [(u, len(raw) << 16, True)], 0, 0)], offs)
+        try:
+            got = engine.bgzf_host(files, q)
+        except engine.GtbError as e:
+            assert e.code in (-5, -4, -1), e
+            n_rejected += 1
+            continue
+        cases.assert_batches_equal(got, want, "a flip that was accepted must not have changed anything")
+    assert n_rejected > 200
