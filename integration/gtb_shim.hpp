@@ -253,6 +253,8 @@ struct BgzfPool
   gtb_bgzf_query query{};
   uint64_t n_bytes = 0;
   std::vector<uint64_t> whole_u; // whole-file reading: virtual offset of every file's first record
+  // the device needs ~4 bytes of working memory per inflated byte (record lists, sort buffers): pools beyond this stay with htslib
+  static constexpr uint64_t max_pool_bytes = 256ull << 20;
 
   bool collect(gyper::HtsParallelReader const & reader, uint32_t flag_filter, bool is_sv, std::string & why_not)
   {
@@ -288,8 +290,8 @@ struct BgzfPool
         if (!hh)
           return why_not = "cannot read the header", false;
         struct stat st0;
-        if (::stat(f.fp->fn, &st0) != 0 || (uint64_t)st0.st_size - (u >> 16) > (1ull << 31))
-          return why_not = "more than 2 GiB to read without a region", false;
+        if (::stat(f.fp->fn, &st0) != 0 || (uint64_t)st0.st_size - (u >> 16) > max_pool_bytes)
+          return why_not = "more than 256 MiB to read without a region", false;
         whole_u.push_back(u);
       }
       else if (i == 0)
@@ -343,6 +345,11 @@ struct BgzfPool
         g.first_offset = (uint32_t)(u & 0xFFFFu);
         g.to_eof = end == file_size ? 1u : 0u;
         n_bytes += buf.size();
+        if (n_bytes > max_pool_bytes)
+        {
+          ::close(fd);
+          return why_not = "more than 256 MiB of compressed bytes in one pool", false;
+        }
         bytes.push_back(std::move(buf));
         segs[i].push_back(g);
       }
