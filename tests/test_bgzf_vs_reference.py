@@ -54,6 +54,7 @@ def doctor_sams(sams, seed=7):
 
 CASES = {
     "one_file": dict(length=6000, n_sites=40, n_samples=1, seed=131, coverage=40, err=0.0, read_len=100),
+    "twelve_files": dict(length=2500, n_sites=25, n_samples=12, seed=171, coverage=45, err=0.001, read_len=100, unpaired_rate=0.05),
     "six_files_many_ties": dict(length=3000, n_sites=30, n_samples=6, seed=141, coverage=60, err=0.0, read_len=100),
     "pileup_and_flags": dict(length=5000, n_sites=40, n_samples=3, seed=151, coverage=30, err=0.0, read_len=100),
     "three_files": dict(length=8000, n_sites=120, n_samples=3, seed=121, coverage=16, err=0.004, n_rate=0.002, lowmapq_rate=0.1,
