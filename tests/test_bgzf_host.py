@@ -241,3 +241,17 @@ def test_inflate_fuzz_random_streams_and_corruptions():
             continue
         cases.assert_batches_equal(got, want, "a flip that was accepted must not have changed anything")
     assert n_rejected > 200
+
+
+def test_submit_bgzf_has_no_cpu_fallback():
+    """The emulation above is a parity tap: the product entry refuses to run without a device."""
+    c = engine.Context(device=-1)
+    try:
+        rd, bam = cases.fixture_batch(SMALL[0])
+        tid, beg, end = cases.region_of(bam)
+        files = cases.whole_file_segments(cases.pool_files(bam, tid, beg, end))
+        with pytest.raises(engine.GtbError) as e:
+            c.submit_bgzf(1, files, bgzf.query(tid, beg, end))
+        assert e.value.code == -2
+    finally:
+        c.close()
