@@ -141,9 +141,46 @@ __device__ __forceinline__ void sw_stage_rows_async(uint32_t (*rows)[32], const 
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// The same staging as ONE bulk asynchronous copy per refill (cp.async.bulk, the 1-D form of TMA: SASS UBLKCP): the rows
+// base .. top of a warp's slab are contiguous (128 bytes each), so lane 0 arms the buffer's mbarrier with the byte count and
+// issues one copy of up to 2 KiB that the copy unit completes on the barrier; the buffer then holds the rows in ASCENDING
+// order, row r at index r - (top - SW_ROWS_CACHED + 1).  Returns false when there is no row left to stage.
+__device__ __forceinline__ bool sw_stage_rows_bulk(uint32_t (*rows)[32], unsigned long long * bar, const uint32_t * bt, int top, int lane)
+{
+  if (top < 0)
+    return false;
+  int const first = top - (SW_ROWS_CACHED - 1);
+  int const base = first < 0 ? 0 : first;
+  if (lane == 0)
+  {
+    unsigned const bytes = (unsigned)(top - base + 1) * 128u;
+    unsigned const dst = (unsigned)__cvta_generic_to_shared(&rows[base - first][0]);
+    unsigned const b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(bt + (size_t)base * 32), "r"(bytes), "r"(b)
+                 : "memory");
+  }
+  return true;
+}
+__device__ __forceinline__ void sw_wait_rows(unsigned long long * bar, unsigned phase)
+{
+  unsigned const b = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done;
+  do
+  {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(b), "r"(phase)
+                 : "memory");
+  } while (!done);
+}
+
+template <bool BULK>
 __global__ void __launch_bounds__(SW_WARPS * 32, SW_MIN_BLOCKS) sw_kernel(SwParams P)
 {
-  __shared__ uint32_t s_rows[SW_WARPS][2][SW_ROWS_CACHED][32];
+  __shared__ __align__(128) uint32_t s_rows[SW_WARPS][2][SW_ROWS_CACHED][32];
+  __shared__ __align__(8) unsigned long long s_bar[SW_WARPS][2]; // BULK: one mbarrier per staging buffer of every warp
   __shared__ uint8_t s_db[SW_WARPS][GTB_SW_MAX_DATABASE];
   __shared__ uint8_t s_q[SW_WARPS][SW_MAX_Q];
   int const lane = threadIdx.x & 31;
@@ -153,6 +190,18 @@ __global__ void __launch_bounds__(SW_WARPS * 32, SW_MIN_BLOCKS) sw_kernel(SwPara
   // per-warp scratch slabs are max_db + 5 rows apart: a power-of-two stride would map every warp's row r to the same
   // L2 sets
   uint32_t * bt = P.bt + (size_t)warp_global * (size_t)(P.max_db + 5) * 32;
+  unsigned bar_phase[2] = {0u, 0u};
+  if (BULK)
+  {
+    if (lane == 0)
+    {
+      for (int k = 0; k < 2; ++k)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_bar[wib][k])) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+  }
 
   for (int pair = warp_global; pair < P.n_pairs; pair += total_warps)
   {
@@ -198,22 +247,55 @@ __global__ void __launch_bounds__(SW_WARPS * 32, SW_MIN_BLOCKS) sw_kernel(SwPara
       // s_rows[wib][cur][k] holds row (cached_top - k); the other buffer is being filled with the SW_ROWS_CACHED rows
       // below.  The walk only ever moves to the same or the previous row.
       int cur = 0, cached_top = n - 1;
-      sw_stage_rows_async(s_rows[wib][0], bt, cached_top, lane);
-      sw_stage_rows_async(s_rows[wib][1], bt, cached_top - SW_ROWS_CACHED, lane);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-      __syncwarp();
+      bool pending[2] = {false, false}; // BULK: a copy into the buffer is in flight (its barrier has not been waited for)
+      if (BULK)
+      {
+        // the DP's row stores (generic proxy) precede the copy unit's reads of the slab (async proxy)
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __syncwarp();
+        pending[0] = sw_stage_rows_bulk(s_rows[wib][0], &s_bar[wib][0], bt, cached_top, lane);
+        pending[1] = sw_stage_rows_bulk(s_rows[wib][1], &s_bar[wib][1], bt, cached_top - SW_ROWS_CACHED, lane);
+        sw_wait_rows(&s_bar[wib][0], bar_phase[0]);
+        bar_phase[0] ^= 1u;
+        pending[0] = false;
+      }
+      else
+      {
+        sw_stage_rows_async(s_rows[wib][0], bt, cached_top, lane);
+        sw_stage_rows_async(s_rows[wib][1], bt, cached_top - SW_ROWS_CACHED, lane);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+      }
       auto bits_at = [&](int row, int col) -> uint32_t
       {
         if (row <= cached_top - SW_ROWS_CACHED)
         {
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          __syncwarp();
-          cached_top -= SW_ROWS_CACHED;
-          sw_stage_rows_async(s_rows[wib][cur], bt, cached_top - SW_ROWS_CACHED, lane);
-          cur ^= 1;
+          if (BULK)
+          {
+            int const nxt = cur ^ 1;
+            if (pending[nxt])
+            {
+              sw_wait_rows(&s_bar[wib][nxt], bar_phase[nxt]);
+              bar_phase[nxt] ^= 1u;
+              pending[nxt] = false;
+            }
+            __syncwarp(); // every lane is done with the buffer that is refilled next
+            cached_top -= SW_ROWS_CACHED;
+            pending[cur] = sw_stage_rows_bulk(s_rows[wib][cur], &s_bar[wib][cur], bt, cached_top - SW_ROWS_CACHED, lane);
+            cur = nxt;
+          }
+          else
+          {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            cached_top -= SW_ROWS_CACHED;
+            sw_stage_rows_async(s_rows[wib][cur], bt, cached_top - SW_ROWS_CACHED, lane);
+            cur ^= 1;
+          }
         }
         int const wl = ((col - 1) * cpl_inv) >> 16; // (col - 1) / cpl, exact for col <= 160
-        uint32_t const w = s_rows[wib][cur][cached_top - row][wl];
+        // cp.async buffers hold the rows top-down, bulk buffers bottom-up
+        uint32_t const w = s_rows[wib][cur][BULK ? SW_ROWS_CACHED - 1 - (cached_top - row) : cached_top - row][wl];
         return (w >> (4 * (cpl - 1 - (col - 1 - wl * cpl)))) & 15u;
       };
       while (i > 0 || j > 0)
@@ -286,8 +368,16 @@ __global__ void __launch_bounds__(SW_WARPS * 32, SW_MIN_BLOCKS) sw_kernel(SwPara
             tmp_score -= MISMATCH;
         }
       }
+      if (BULK) // copies the walk did not need any more: their barriers complete a phase all the same
+        for (int k = 0; k < 2; ++k)
+          if (pending[k])
+          {
+            sw_wait_rows(&s_bar[wib][k], bar_phase[k]);
+            bar_phase[k] ^= 1u;
+          }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!BULK)
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0)
     {
       gtb_sw_result r;
@@ -312,7 +402,7 @@ int sw_resident_warps(int max_db)
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sw_kernel, SW_WARPS * 32, 0) != cudaSuccess || nb < 1)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sw_kernel<false>, SW_WARPS * 32, 0) != cudaSuccess || nb < 1)
     nb = 1;
   if (nb > SW_MIN_BLOCKS)
     nb = SW_MIN_BLOCKS;
@@ -335,7 +425,12 @@ void launch_sw(const SwParams & p, int resident_warps, void * stream)
   int const need = (p.n_pairs + SW_WARPS - 1) / SW_WARPS;
   if (need < grid)
     grid = need;
-  sw_kernel<<<grid, SW_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  // GTB_SW_BULK=1: traceback rows staged by bulk asynchronous copies (cp.async.bulk + mbarrier) instead of per-lane cp.async
+  static bool const bulk = []() { const char * e = getenv("GTB_SW_BULK"); return e && atoi(e) != 0; }();
+  if (bulk)
+    sw_kernel<true><<<grid, SW_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  else
+    sw_kernel<false><<<grid, SW_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
 }
 
 } // namespace gtb

@@ -289,7 +289,7 @@ int gtb_merge_varstats(uint32_t n_bubbles, uint64_t n_alleles_total, uint64_t *v
                        const uint64_t *var_src, const uint64_t *allele_src, const double *ratio_src);
 
 /* Record-parsing entry (SURVEY.md section 8f, N3 -- first step: everything genotype_only's caller derives per record moves
- * to the device; BGZF inflate and the k-way merge stay in htslib).  The shim hands over the records of one pool in merge
+ * to the device; for THIS entry BGZF inflate and the k-way merge stay in htslib -- gtb_submit_bgzf below takes those as well).  The shim hands over the records of one pool in merge
  * order (after the flag filter, hts_parallel_reader.cpp:655-663, and for SV graphs is_good_read, :528-568) as htslib holds
  * them: the core fields below (bam1_core_t, htslib/sam.h) + bam1_t::data (qname | cigar | seq | qual | aux), concatenated.
  * On the device: 4-bit bases, lengths, flags, MAPQ, insert size, AS-XS exactly as get_score_diff walks the aux block
