@@ -5,6 +5,7 @@ import zlib
 
 import numpy as np
 
+from oracle import bam_oracle
 from graphtyper_b200 import abi, bgzf, gtba
 
 REFS = [("chr1", 250000000), ("chr2", 240000000)]
@@ -103,8 +104,8 @@ def expected_batch(made, chunk_lists, tid, beg, end, flag_filter=3840, sv=False)
     """Plain-Python expectation as a HostBamBatch in file layout (l_qname = name length + 1, no padding)."""
     per_file = []
     for (raw, stream, blocks, hlen, s, g), chunks in zip(made, chunk_lists):
-        per_file.append(bgzf.iterate_region(stream, blocks, chunks, tid, beg, end))
-    rows = bgzf.expected_pool_records(per_file, flag_filter, sv)
+        per_file.append(bam_oracle.iterate_region(stream, blocks, chunks, tid, beg, end))
+    rows = bam_oracle.expected_pool_records(per_file, flag_filter, sv)
     n = len(rows)
     core = np.zeros(n, abi.BAM_CORE_DTYPE)
     data = bytearray()

@@ -1,6 +1,6 @@
 """BGZF decode + record selection + merge order: the host/device source functions of csrc/gtb_inflate.cuh and
 csrc/gtb_bamscan.cuh, run serially on the CPU through gtb_debug_bgzf_host, against zlib and a plain-Python restatement of
-htslib's region iterator and the reference's merge order (graphtyper_b200/bgzf.py).  The GPU kernels call the same functions
+htslib's region iterator and the reference's merge order (oracle/bam_oracle.py).  The GPU kernels call the same functions
 (tests/test_gpu_bgzf.py compares them with this emulation bit for bit)."""
 import os
 import zlib
@@ -10,6 +10,7 @@ import pytest
 
 import bgzf_cases as cases
 from conftest import fixture_prefixes
+from oracle import bam_oracle
 from graphtyper_b200 import abi, bgzf, engine
 
 SMALL = [p for p in fixture_prefixes(include_big=False)]
@@ -161,8 +162,8 @@ def test_whole_file_reading_spans_contigs_and_needs_sorted_files():
     got = engine.bgzf_host(files, bgzf.query(0, 0, 0, whole_file=True))
     assert len(got) == 9
     assert list(zip(got.core["tid"], got.core["pos"])) == sorted(zip(got.core["tid"], got.core["pos"]))
-    per_file = [[bgzf.ParsedRecord(r[4:]) for r in recs] for recs in (a, b)]
-    rows = bgzf.expected_pool_records(per_file, 3840, False)
+    per_file = [[bam_oracle.ParsedRecord(r[4:]) for r in recs] for recs in (a, b)]
+    rows = bam_oracle.expected_pool_records(per_file, 3840, False)
     assert [(r.tid, r.pos) for _, r in rows] == list(zip(got.core["tid"], got.core["pos"]))
     assert [fi for fi, _ in rows if True][:1] == [int(got.sample[0])]
     # a region query on the same files stops at the first record of the next contig
