@@ -6,7 +6,11 @@
 //   3. the compute entry points refuse to run without a device (no CPU fallback);
 //   4. with --gpu (on the GPU box): region + pool + records through the C ABI on the device, every HapSample and per-bubble
 //      statistic compared with the reference's own pool loop (genotype_only + VcfWriter) run in the same process.
-// Prints "SHIM PASS ..." (and "SHIM GPU PASS ...") or the first difference.
+//   5. with --bgzf REGION a.bam[,b.bam] [--sv]: gtb_shim::BgzfPool::collect on the pool's files as the reference's own reader
+//      opened them (the chunks of the real index, or everything behind the header for region "."), decoded by the CPU run of
+//      the device's source functions (gtb_debug_bgzf_host), compared record by record with what HtsParallelReader::read_record
+//      + the pool loop's filters hand out.  No GPU needed.
+// Prints "SHIM PASS ..." (and "SHIM GPU PASS ...", "SHIM BGZF PASS ...") or the first difference.
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -167,9 +171,112 @@ int compare_with_reference_loop(std::vector<std::string> const & sams, gyper::PH
 }
 } // namespace
 
+namespace
+{
+std::vector<std::string> split_list(std::string const & s)
+{
+  std::vector<std::string> out;
+  size_t b = 0;
+  while (b <= s.size())
+  {
+    size_t e = s.find(',', b);
+    if (e == std::string::npos)
+      e = s.size();
+    if (e > b)
+      out.push_back(s.substr(b, e - b));
+    b = e + 1;
+  }
+  return out;
+}
+
+// 5. (--bgzf) the compressed-bytes hand-off against the reference's reader on the same files and region
+int bgzf_check(std::string const & region, std::vector<std::string> const & paths, bool is_sv)
+{
+  using namespace gyper;
+  Options const & opts = *Options::const_instance();
+  HtsParallelReader a;
+  a.open(paths, "", region);
+  gtb_shim::BgzfPool pool;
+  std::string why;
+  if (!pool.collect(a, (uint32_t)opts.sam_flag_filter, is_sv, why))
+  {
+    printf("SHIM BGZF DECLINED: %s\n", why.c_str());
+    return 0;
+  }
+  uint32_t n = 0;
+  uint64_t nd = 0;
+  if (gtb_debug_bgzf_host((int)pool.files.size(), pool.files.data(), &pool.query, &n, &nd, nullptr, nullptr, nullptr, nullptr, nullptr,
+                          nullptr, nullptr) != 0)
+  {
+    printf("SHIM BGZF FAIL: %s\n", gtb_last_error());
+    return 1;
+  }
+  std::vector<gtb_bam_core> core(n);
+  std::vector<uint8_t> data(nd + 1);
+  std::vector<uint64_t> off(n + 1);
+  std::vector<int32_t> sample(n), rg(n);
+  if (n && gtb_debug_bgzf_host((int)pool.files.size(), pool.files.data(), &pool.query, &n, &nd, core.data(), data.data(), off.data(),
+                               sample.data(), rg.data(), nullptr, nullptr) != 0)
+  {
+    printf("SHIM BGZF FAIL: %s\n", gtb_last_error());
+    return 1;
+  }
+  // the reference's reader on the same files: records in its order, the pool loop's filters applied
+  HtsParallelReader b;
+  b.open(paths, "", region);
+  HtsRecord rec;
+  uint64_t k = 0;
+  while (b.read_record(rec))
+  {
+    bam1_t const * r = rec.record;
+    if ((r->core.flag & opts.sam_flag_filter) != 0u || (is_sv && !gtb_shim::is_good_read(r)))
+      continue;
+    if (k >= n)
+    {
+      printf("SHIM BGZF FAIL: the reference reads more than %u records\n", n);
+      return 1;
+    }
+    long s_i = 0, rg_i = 0;
+    b.get_sample_and_rg_index(s_i, rg_i, rec);
+    gtb_bam_core const & c = core[k];
+    const uint8_t * d = data.data() + off[k];
+    uint64_t const len = off[k + 1] - off[k];
+    size_t const name_len = strlen(bam_get_qname(r)) + 1; // the file's l_read_name; htslib pads the name in memory
+    bool ok = c.pos == r->core.pos && c.mpos == r->core.mpos && c.isize == r->core.isize && c.tid == r->core.tid && c.mtid == r->core.mtid &&
+              c.l_qseq == r->core.l_qseq && c.n_cigar == r->core.n_cigar && c.flag == r->core.flag && c.mapq == r->core.qual &&
+              c.l_qname == name_len && sample[k] == s_i && rg[k] == rg_i;
+    uint64_t const rest = (uint64_t)r->l_data - r->core.l_qname;
+    ok = ok && len == name_len + rest && memcmp(d, r->data, name_len) == 0 && memcmp(d + name_len, r->data + r->core.l_qname, rest) == 0;
+    if (!ok)
+    {
+      printf("SHIM BGZF FAIL: record %llu (%s at %lld) differs\n", (unsigned long long)k, bam_get_qname(r), (long long)r->core.pos);
+      return 1;
+    }
+    ++k;
+  }
+  if (k != n)
+  {
+    printf("SHIM BGZF FAIL: %u records decoded, the reference reads %llu\n", n, (unsigned long long)k);
+    return 1;
+  }
+  size_t n_seg = 0;
+  for (auto const & f : pool.files)
+    n_seg += f.n_segments;
+  printf("SHIM BGZF PASS records=%u files=%zu segments=%zu compressed_bytes=%llu whole_file=%u\n", n, pool.files.size(), n_seg,
+         (unsigned long long)pool.n_bytes, pool.query.whole_file);
+  return 0;
+}
+} // namespace
+
 int main(int argc, char ** argv)
 {
   using namespace gyper;
+  if (argc >= 4 && std::string(argv[1]) == "--bgzf")
+  {
+    Options::instance();
+    gyper::log_singleton = std::unique_ptr<gyper::log_singleton_t>{new gyper::log_singleton_t{gyper::log_severity::warning, std::clog}};
+    return bgzf_check(argv[2], split_list(argv[3]), argc > 4 && std::string(argv[4]) == "--sv");
+  }
   if (argc < 5)
   {
     fprintf(stderr, "usage: shim_probe REF.fa VCF.gz chr:b-e a.sam[,b.sam]\n");
